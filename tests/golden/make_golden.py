@@ -1,0 +1,353 @@
+"""Generate golden vectors by running the UNMODIFIED reference (/root/reference, AgileRL 2.6.1)
+through ``oracle.refshim`` and check the oracle restatement against it while doing so.
+
+Run here (the build container) only:   python tests/golden/make_golden.py
+Outputs small ``.npz`` fixtures next to this file; they travel to the GPU box, /root/reference
+does not.  Every fixture stores the inputs, any injected randomness, and the reference's outputs.
+
+What is real and what is a stand-in: the reference's own code runs for segment trees, replay
+buffers, Transition, Sampler, NoisyLinear/MLP/CNN/RainbowQNetwork/QNetwork, RainbowDQN/DQN
+``learn`` and TournamentSelection.  ``tensordict`` and ``gymnasium.spaces`` are the stand-ins of
+``agilerl_b200.compat`` (the real packages are not in the image); torch is 2.11 (reference pins
+2.9).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import refshim  # noqa: E402
+
+refshim.install()
+
+from gymnasium import spaces  # noqa: E402
+from tensordict import TensorDict  # noqa: E402
+
+from agilerl.algorithms.dqn import DQN  # noqa: E402
+from agilerl.algorithms.dqn_rainbow import RainbowDQN  # noqa: E402
+from agilerl.components.data import Transition  # noqa: E402
+from agilerl.components.replay_buffer import (  # noqa: E402
+    MultiStepReplayBuffer, PrioritizedReplayBuffer, ReplayBuffer)
+from agilerl.components.segment_tree import MinSegmentTree, SumSegmentTree  # noqa: E402
+from agilerl.hpo.tournament import TournamentSelection  # noqa: E402
+
+from oracle import learn as olearn, nets as onets, replay as oreplay, tournament as otourn  # noqa: E402
+from oracle.segtree import CSegTree, PySegTree  # noqa: E402
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **arrays)
+    print(f"wrote {name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+def sd_np(sd):
+    return {k: v.detach().cpu().numpy().copy() for k, v in sd.items()}
+
+
+# ------------------------------------------------------------------------------------------------
+def gen_tree():
+    rng = np.random.default_rng(7)
+    cap = 64
+    n_ops = 400
+    idx = rng.integers(0, cap, n_ops)
+    val = rng.random(n_ops) ** 0.6 * 3.0
+    rs, rm = SumSegmentTree(cap), MinSegmentTree(cap)
+    ps, pm = PySegTree(cap, "sum"), PySegTree(cap, "min")
+    cs, cm = CSegTree(cap, "sum"), CSegTree(cap, "min")
+    snap_sum, snap_min = [], []
+    for k, (i, v) in enumerate(zip(idx, val)):
+        for t in (rs, rm, ps, pm, cs, cm):
+            t[int(i)] = float(v)
+        if k % 50 == 49:
+            snap_sum.append(np.array(rs.tree)); snap_min.append(np.array(rm.tree))
+    assert rs.tree == ps.tree == list(cs.tree) and rm.tree == pm.tree == list(cm.tree)
+    ubs = rng.random(200) * rs.sum()
+    ret = np.array([rs.retrieve(float(u)) for u in ubs])
+    assert all(ps.retrieve(float(u)) == r == cs.retrieve(float(u)) for u, r in zip(ubs, ret))
+    ranges = np.array([(a, b) for a in range(0, cap, 7) for b in range(a + 1, cap + 1, 9)])
+    rsum = np.array([rs.sum(int(a), int(b)) for a, b in ranges])
+    rmin = np.array([rm.min(int(a), int(b)) for a, b in ranges])
+    save("tree_ops.npz", cap=cap, idx=idx, val=val, snap_sum=np.stack(snap_sum),
+         snap_min=np.stack(snap_min), final_sum=np.array(rs.tree), final_min=np.array(rm.tree),
+         ubs=ubs, retrieve=ret, ranges=ranges, range_sum=rsum, range_min=rmin)
+
+
+# ------------------------------------------------------------------------------------------------
+def _mk_transition(g, E, obs_shape, n_act, p_done, t):
+    return dict(
+        obs=torch.randint(0, 256, (E, *obs_shape), dtype=torch.uint8, generator=g),
+        action=torch.randint(0, n_act, (E,), generator=g),
+        reward=torch.randn(E, generator=g),
+        next_obs=torch.randint(0, 256, (E, *obs_shape), dtype=torch.uint8, generator=g),
+        done=(torch.rand(E, generator=g) < p_done),
+    )
+
+
+def gen_replay():
+    """PER + n-step ingest through the real Transition/MultiStep/PER classes, then sampling with
+    injected uniforms, then priority updates; checks the oracle along the way."""
+    g = torch.Generator().manual_seed(11)
+    E, obs_shape, n_act, max_size, n_step, gamma, alpha = 2, (3, 6, 6), 4, 48, 3, 0.99, 0.6
+    mem = PrioritizedReplayBuffer(max_size, alpha=alpha)
+    nmem = MultiStepReplayBuffer(max_size, n_step=n_step, gamma=gamma)
+    omem = oreplay.OraclePER(max_size, alpha=alpha)
+    onmem = oreplay.OracleNStep(max_size, n_step=n_step, gamma=gamma)
+    raw = []
+    for t in range(40):  # 40 steps x 2 envs -> wraps the 48-slot ring
+        tr = _mk_transition(g, E, obs_shape, n_act, 0.15, t)
+        raw.append(tr)
+        td = Transition(obs=tr["obs"].numpy(), action=tr["action"].numpy(), reward=tr["reward"].numpy(),
+                        next_obs=tr["next_obs"].numpy(), done=tr["done"].numpy(),
+                        batch_size=[E]).to_tensordict()
+        one = nmem.add(td)
+        if one is not None:
+            mem.add(one)
+        # oracle side: same casts as Transition.__post_init__ (data.py:85-87)
+        od = dict(obs=tr["obs"], action=tr["action"].float(), reward=tr["reward"].float(),
+                  next_obs=tr["next_obs"], done=tr["done"].float())
+        oone = onmem.add(od)
+        if oone is not None:
+            omem.add(oone)
+    for k in mem.storage.keys():
+        assert torch.equal(mem.storage[k], omem.storage[k]), k
+        assert torch.equal(nmem.storage[k], onmem.storage[k]), k
+    assert (mem._cursor, mem._size, mem.tree_ptr) == (omem.cursor, omem.size, omem.tree_ptr)
+
+    # priority updates (numpy f32 priorities like learn() returns, and [B,1] idxs like sample())
+    rng = np.random.default_rng(5)
+    upd_idx = rng.integers(0, mem.size, (3, 16))
+    upd_pri = np.abs(rng.standard_normal((3, 16))).astype(np.float32)
+    upd_pri[0, 0] = 1e-9  # exercises the 1e-5 floor
+    upd_idx[1, 3] = upd_idx[1, 2]  # duplicate index inside one batch (last writer wins)
+    trees_after = []
+    for r in range(3):
+        mem.update_priorities(torch.from_numpy(upd_idx[r]).unsqueeze(1), upd_pri[r])
+        omem.update_priorities(torch.from_numpy(upd_idx[r]), upd_pri[r])
+        assert mem.sum_tree.tree == list(omem.sum_tree.tree) and mem.min_tree.tree == list(omem.min_tree.tree)
+        trees_after.append((np.array(mem.sum_tree.tree), np.array(mem.min_tree.tree)))
+    assert mem.max_priority == omem.max_priority
+
+    # sampling with injected uniforms (the reference test's own trick, test_replay_buffer.py:859-883)
+    B, beta = 16, 0.4
+    uniforms = torch.rand(B, generator=g)
+    it = iter(uniforms.tolist())
+    orig = torch.rand
+    torch.rand = lambda *a, **k: torch.tensor([next(it)])
+    try:
+        batch = mem.sample(B, beta)
+    finally:
+        torch.rand = orig
+    obatch = omem.sample(B, beta, uniforms=uniforms)
+    for k in batch.keys():
+        assert torch.equal(batch[k], obatch[k]), k
+    nbatch = nmem.sample_from_indices(batch["idxs"].squeeze(1))
+    save("replay_per_nstep.npz",
+         E=E, max_size=max_size, n_step=n_step, gamma=gamma, alpha=alpha, beta=beta,
+         **{f"raw_{k}": torch.stack([r[k] for r in raw]).numpy() for k in raw[0]},
+         **{f"per_{k}": v.numpy() for k, v in mem.storage.items()},
+         **{f"nstep_{k}": v.numpy() for k, v in nmem.storage.items()},
+         cursor=mem._cursor, size=mem._size, tree_ptr=mem.tree_ptr, max_priority=mem.max_priority,
+         upd_idx=upd_idx, upd_pri=upd_pri,
+         sum_after=np.stack([t[0] for t in trees_after]), min_after=np.stack([t[1] for t in trees_after]),
+         uniforms=uniforms.numpy(), sample_idxs=batch["idxs"].numpy(), sample_weights=batch["weights"].numpy(),
+         **{f"batch_{k}": batch[k].numpy() for k in ("obs", "action", "reward", "next_obs", "done")},
+         **{f"nbatch_{k}": nbatch[k].numpy() for k in ("obs", "action", "reward", "next_obs", "done")})
+
+    # uniform buffer ring layout incl. wrap (test_replay_buffer.py:144-177)
+    rb = ReplayBuffer(max_size=3)
+    d1 = TensorDict({"obs": torch.tensor([[1.0, 2.0], [3.0, 4.0]]), "reward": torch.tensor([1.0, 2.0])}, batch_size=[2])
+    d2 = TensorDict({"obs": torch.tensor([[5.0, 6.0], [7.0, 8.0]]), "reward": torch.tensor([3.0, 4.0])}, batch_size=[2])
+    rb.add(d1); rb.add(d2)
+    save("replay_ring.npz", obs=rb.storage["obs"].numpy(), reward=rb.storage["reward"].numpy(),
+         cursor=rb._cursor, size=rb._size, counter=rb.counter)
+
+
+# ------------------------------------------------------------------------------------------------
+def _draw_noise(spec):
+    """Same RNG calls reset_noise makes (custom_components.py:116-131), per net."""
+    return torch.cat([torch.cat([torch.randn(a), torch.randn(b)]) for _, a, b in onets.noisy_layer_keys(spec)])
+
+
+def _rainbow_case(name, obs_shape, n_act, net_config, spec, B, *, weights_shape, driver_shapes=False,
+                  n_step=True, combined=False, seed=0, v_min=-10.0, v_max=10.0, full=True):
+    torch.manual_seed(seed)
+    obs_space = spaces.Box(0, 255, obs_shape, np.uint8) if len(obs_shape) == 3 else spaces.Box(-1, 1, obs_shape, np.float32)
+    agent = RainbowDQN(obs_space, spaces.Discrete(n_act), net_config=net_config, batch_size=B,
+                       v_min=v_min, v_max=v_max, lr=1e-3, combined_reward=combined)
+    # make target differ from online and give the net a non-trivial state
+    with torch.no_grad():
+        for p in agent.actor_target.parameters():
+            p.add_(0.01 * torch.randn_like(p))
+    actor0, target0 = sd_np(agent.actor.state_dict()), sd_np(agent.actor_target.state_dict())
+    g = torch.Generator().manual_seed(seed + 100)
+    def mk(shape_extra=()):
+        if len(obs_shape) == 3:
+            o = torch.randint(0, 256, (B, *obs_shape), dtype=torch.uint8, generator=g)
+            no = torch.randint(0, 256, (B, *obs_shape), dtype=torch.uint8, generator=g)
+        else:
+            o = torch.randn((B, *obs_shape), generator=g); no = torch.randn((B, *obs_shape), generator=g)
+        return dict(obs=o, action=torch.randint(0, n_act, (B, 1), generator=g).float(),
+                    reward=torch.randn(B, 1, generator=g) * 3.0, next_obs=no,
+                    done=(torch.rand(B, 1, generator=g) < 0.2).float())
+    exp, nexp = mk(), mk()
+    # hit the projection edge cases: exact-integer b (u==L), clamp at both ends
+    nexp["reward"][0] = 0.0; nexp["done"][0] = 1.0          # t_z == 0 for all atoms -> b integer mid
+    nexp["reward"][1] = 50.0                                  # clamps to v_max (u==L==N-1)
+    nexp["reward"][2] = -50.0                                 # clamps to v_min (u==L==0)
+    exp["reward"][0] = 0.0; exp["done"][0] = 1.0
+    w = torch.rand(B, generator=g) * 0.9 + 0.1
+    exp["weights"] = w.view(weights_shape)
+    exp["idxs"] = torch.randint(0, 1000, (B, 1), generator=g)
+    if driver_shapes:   # what train_off_policy actually feeds: storage[idxs [B,1]] (quirk Q2)
+        nexp = {k: v.unsqueeze(1) for k, v in nexp.items()}
+    exp_td = TensorDict({k: v.clone() for k, v in exp.items()}, batch_size=[B])
+    nexp_td = TensorDict({k: v.clone() for k, v in nexp.items()}, batch_size=[B])
+
+    torch.manual_seed(seed + 7)
+    loss, idxs, pri = agent.learn(exp_td, n_experiences=nexp_td if n_step else None, per=True)
+    torch.manual_seed(seed + 7)
+    z_actor, z_target = _draw_noise(spec), _draw_noise(spec)
+    actor1, target1 = sd_np(agent.actor.state_dict()), sd_np(agent.actor_target.state_dict())
+    grads = {k: p.grad.detach().numpy().copy() for k, p in agent.actor.named_parameters()}
+    adam = agent.optimizer.optimizer.state_dict()["state"]
+    names = [k for k, _ in agent.actor.named_parameters()]
+    exp_avg = {names[i]: s["exp_avg"].numpy().copy() for i, s in adam.items()}
+    exp_avg_sq = {names[i]: s["exp_avg_sq"].numpy().copy() for i, s in adam.items()}
+
+    # ---- oracle must reproduce the reference exactly (same torch CPU ops, same machine) ----
+    oa = olearn.OracleAgent(spec, {k: torch.from_numpy(v) for k, v in actor0.items()},
+                            {k: torch.from_numpy(v) for k, v in target0.items()},
+                            batch_size=B, lr=1e-3, v_min=v_min, v_max=v_max, combined_reward=combined)
+    oloss, _, opri = oa.learn_rainbow(exp, nexp if n_step else None, per=True, noise_normals=(z_actor, z_target))
+    assert oloss == loss, (oloss, loss)
+    assert np.array_equal(opri, pri)
+    for k in actor1:
+        assert np.array_equal(oa.actor[k].detach().numpy(), actor1[k]), k
+        assert np.array_equal(oa.target[k].detach().numpy(), target1[k]), k
+    print(f"  {name}: oracle == reference bit-exact (loss {loss:.6f})")
+
+    out = dict(loss=np.float64(loss), priorities=pri, idxs=idxs.numpy(), z_actor=z_actor.numpy(),
+               z_target=z_target.numpy(), proj_dist=oa.last_proj_dist.numpy(), B=B)
+    for k, v in exp.items():
+        out[f"exp_{k}"] = v.numpy()
+    for k, v in nexp.items():
+        out[f"nexp_{k}"] = v.numpy()
+    if full:
+        for tag, d in (("actor0", actor0), ("target0", target0), ("actor1", actor1), ("target1", target1),
+                       ("grad", grads), ("m", exp_avg), ("v", exp_avg_sq)):
+            for k, v in d.items():
+                out[f"{tag}/{k}"] = v
+    save(name, **out)
+
+
+def gen_rainbow():
+    small_cfg = {"encoder_config": {"channel_size": [8, 16], "kernel_size": [4, 3], "stride_size": [2, 1]},
+                 "head_config": {"hidden_size": [32]}, "latent_dim": 16}
+    def small_spec():
+        return onets.rainbow_spec((3, 20, 20), 4, (8, 16), (4, 3), (2, 1), 16, (32,))
+    import copy
+    _rainbow_case("rainbow_small_canonical.npz", (3, 20, 20), 4, copy.deepcopy(small_cfg), small_spec(), 16,
+                  weights_shape=(16,))
+    _rainbow_case("rainbow_small_wcol.npz", (3, 20, 20), 4, copy.deepcopy(small_cfg), small_spec(), 16,
+                  weights_shape=(16, 1), seed=1, full=False)                 # quirk Q1
+    _rainbow_case("rainbow_small_driver.npz", (3, 20, 20), 4, copy.deepcopy(small_cfg), small_spec(), 16,
+                  weights_shape=(16, 1), driver_shapes=True, seed=2, full=False)   # quirks Q1+Q2
+    _rainbow_case("rainbow_small_combined.npz", (3, 20, 20), 4, copy.deepcopy(small_cfg), small_spec(), 16,
+                  weights_shape=(16,), combined=True, seed=3, full=False)
+    _rainbow_case("rainbow_small_1step.npz", (3, 20, 20), 4, copy.deepcopy(small_cfg), small_spec(), 16,
+                  weights_shape=(16,), n_step=False, seed=4, full=False)
+    # vector observations -> noisy MLP encoder with layer norm (q_networks.py:189-206)
+    vec_cfg = {"encoder_config": {"hidden_size": [24, 24]}, "head_config": {"hidden_size": [32, 16]}, "latent_dim": 16}
+    vspec = onets.rainbow_spec((5,), 3, latent_dim=16, hidden_size=(32, 16), encoder_hidden=(24, 24))
+    _rainbow_case("rainbow_vector.npz", (5,), 3, vec_cfg, vspec, 8, weights_shape=(8,), seed=5)
+    # the north-star architecture at B=16 (outputs only)
+    ns_cfg = {"encoder_config": {"channel_size": [32, 32], "kernel_size": [8, 4], "stride_size": [4, 2]}}
+    ns_spec = onets.rainbow_spec((4, 84, 84), 6)
+    _rainbow_case("rainbow_northstar_b16.npz", (4, 84, 84), 6, ns_cfg, ns_spec, 16, weights_shape=(16,), seed=6,
+                  full=False)
+
+
+def gen_dqn():
+    for double, seed in ((False, 0), (True, 1)):
+        torch.manual_seed(seed)
+        B, obs_shape, n_act = 16, (4,), 2
+        agent = DQN(spaces.Box(-1, 1, obs_shape, np.float32), spaces.Discrete(n_act), batch_size=B, lr=1e-3,
+                    double=double)
+        with torch.no_grad():
+            for p in agent.actor_target.parameters():
+                p.add_(0.01 * torch.randn_like(p))
+        actor0, target0 = sd_np(agent.actor.state_dict()), sd_np(agent.actor_target.state_dict())
+        g = torch.Generator().manual_seed(seed + 50)
+        exp = dict(obs=torch.randn(B, 4, generator=g), action=torch.randint(0, n_act, (B, 1), generator=g).float(),
+                   reward=torch.randn(B, 1, generator=g), next_obs=torch.randn(B, 4, generator=g),
+                   done=(torch.rand(B, 1, generator=g) < 0.2).float())
+        loss = agent.learn(TensorDict({k: v.clone() for k, v in exp.items()}, batch_size=[B]))
+        actor1, target1 = sd_np(agent.actor.state_dict()), sd_np(agent.actor_target.state_dict())
+        spec = onets.q_spec(obs_shape, n_act)
+        oa = olearn.OracleAgent(spec, {k: torch.from_numpy(v) for k, v in actor0.items()},
+                                {k: torch.from_numpy(v) for k, v in target0.items()}, batch_size=B, lr=1e-3,
+                                double=double)
+        oloss = oa.learn_dqn(exp)
+        assert oloss == loss, (oloss, loss)
+        for k in actor1:
+            assert np.array_equal(oa.actor[k].detach().numpy(), actor1[k]), k
+            assert np.array_equal(oa.target[k].detach().numpy(), target1[k]), k
+        print(f"  dqn double={double}: oracle == reference bit-exact (loss {loss:.6f})")
+        out = dict(loss=np.float64(loss), B=B, double=double)
+        for k, v in exp.items():
+            out[f"exp_{k}"] = v.numpy()
+        for tag, d in (("actor0", actor0), ("target0", target0), ("actor1", actor1), ("target1", target1)):
+            for k, v in d.items():
+                out[f"{tag}/{k}"] = v
+        save(f"dqn_vector_double{int(double)}.npz", **out)
+
+
+def gen_tournament():
+    class A:
+        algo = "DQN"
+        def __init__(self, index, fitness):
+            self.index, self.fitness = index, list(fitness)
+        def clone(self, index=None, wrap=True):
+            a = A(self.index if index is None else index, self.fitness); a.parent = getattr(self, "parent", self.index)
+            a.parent = self.index
+            return a
+    rng = np.random.default_rng(3)
+    cases = []
+    for c, (pop, tsize, elit) in enumerate([(6, 2, True), (8, 3, True), (8, 4, False), (4, 2, True)]):
+        fit = rng.standard_normal((pop, 5)) * 10
+        idxs = rng.permutation(pop * 2)[:pop]
+        agents = [A(int(i), f) for i, f in zip(idxs, fit)]
+        ts = TournamentSelection(tsize, elit, pop, eval_loop=3)
+        np.random.seed(100 + c)
+        elite, new_pop = ts.select(agents)
+        np.random.seed(100 + c)
+        epos, sel = otourn.select_positions([a.fitness for a in agents], [a.index for a in agents], tsize, elit, pop, 3)
+        assert agents[epos].index == elite.index
+        assert [(agents[p].index, ni) for p, ni in sel] == [(a.parent, a.index) for a in new_pop]
+        cases.append(dict(fit=fit, idxs=idxs, tsize=tsize, elit=elit, seed=100 + c, elite_index=elite.index,
+                          parents=np.array([a.parent for a in new_pop]), new_index=np.array([a.index for a in new_pop])))
+    # the reference's own known-answer case (tests/test_hpo/test_tournament.py:74-125): elite = index 4
+    out = {}
+    for c, d in enumerate(cases):
+        for k, v in d.items():
+            out[f"c{c}_{k}"] = np.asarray(v)
+    out["n_cases"] = len(cases)
+    save("tournament.npz", **out)
+    print("  tournament: oracle == reference")
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(1)   # deterministic CPU reductions while generating
+    gen_tree()
+    gen_replay()
+    gen_rainbow()
+    gen_dqn()
+    gen_tournament()
