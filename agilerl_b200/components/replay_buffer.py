@@ -1,0 +1,377 @@
+"""HBM-resident replay buffers with the reference's class surface.
+
+Drop-in for ``agilerl/components/replay_buffer.py``:
+
+* ``ReplayBuffer``            (:12-138)  circular SoA storage, ``add`` / ``sample`` / ``clear``
+* ``MultiStepReplayBuffer``   (:141-258) n-step return roll at ingest, ``sample_from_indices``
+* ``PrioritizedReplayBuffer`` (:261-428) PER with fp64 sum/min trees
+
+Same constructor arguments, attributes (``max_size, device, dtype, counter, initialized, _cursor,
+_size, _storage, n_step_buffer, reward_key/done_key/ns_key, alpha, max_priority, tree_ptr,
+sum_tree, min_tree``) and return shapes (``weights [B,1]`` f32, ``idxs [B,1]`` int64).  All data
+movement and tree arithmetic run in libb2rl.so (csrc/replay.cu, csrc/tree.cu) on the buffer's CUDA
+device; there is no CPU storage path.
+
+Host work that stays on the host by design: the cursor/size bookkeeping (integers), the RNG draw
+(``torch.randperm`` / ``torch.rand`` from torch's global CPU generator, so seeded runs consume the
+same stream as the reference) and ``priority ** alpha`` in CPython doubles — the reference computes
+exactly that on the host (replay_buffer.py:322) and glibc ``pow`` is what makes the leaves
+bit-identical; the trees themselves are updated on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes
+from collections import deque
+from typing import Any
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..compat import TensorDict, TensorDictBase, is_tensor_collection
+from .segment_tree import MinSegmentTree, SumSegmentTree
+
+DataType = Any
+
+
+def _leaf_items(td, prefix=()):
+    """Flatten a (possibly nested) tensor collection into ((path), tensor) pairs."""
+    for k, v in td.items():
+        if is_tensor_collection(v) or isinstance(v, dict):
+            yield from _leaf_items(v, (*prefix, k))
+        else:
+            yield (*prefix, k), v
+
+
+def _unflatten(leaves: dict, batch_size) -> TensorDict:
+    root: dict = {}
+    for path, v in leaves.items():
+        d = root
+        for k in path[:-1]:
+            d = d.setdefault(k, {})
+        d[path[-1]] = v
+
+    def build(d):
+        return TensorDict({k: (build(v) if isinstance(v, dict) else v) for k, v in d.items()},
+                          batch_size=batch_size)
+
+    return build(root)
+
+
+def _as_collection(data) -> Any:
+    if is_tensor_collection(data):
+        return data
+    if isinstance(data, dict):
+        return TensorDict(data)
+    if hasattr(data, "to_tensordict"):
+        return data.to_tensordict()
+    raise TypeError(f"Cannot store data of type {type(data)} in a replay buffer")
+
+
+class ReplayBuffer:
+    """Circular replay buffer resident in HBM (replay_buffer.py:12-138)."""
+
+    def __init__(self, max_size: int, device: str | torch.device = "cuda",
+                 dtype: torch.dtype = torch.float32) -> None:
+        self.max_size = max_size
+        self.device = device
+        self._dev = _lib.as_device(device)      # raises: no CPU fallback
+        self.dtype = dtype
+        self.counter = 0
+        self.initialized = False
+        self._cursor = 0
+        self._size = 0
+        self._storage: TensorDict | None = None
+        self._fields: dict[tuple, torch.Tensor] = {}
+        self._lib = _lib.load()
+
+    # -- properties (replay_buffer.py:39-58) ---------------------------------------------------
+    @property
+    def storage(self) -> TensorDict | None:
+        return self._storage
+
+    @property
+    def size(self) -> int:
+        return self._size
+
+    @size.setter
+    def size(self, value: int) -> None:
+        self._size = value
+
+    @property
+    def is_full(self) -> bool:
+        return len(self) == self.max_size
+
+    def __len__(self) -> int:
+        return self._size
+
+    # -- ingest ---------------------------------------------------------------------------------
+    def _prepare(self, data) -> tuple[dict[tuple, torch.Tensor], int]:
+        data = _as_collection(data)
+        leaves = {}
+        n = None
+        for path, v in _leaf_items(data):
+            if not isinstance(v, torch.Tensor):
+                v = torch.as_tensor(v)
+            v = v.to(self._dev, non_blocking=True)
+            if n is None:
+                n = v.shape[0]
+            if v.ndim == 1:                       # :85-94 scalar leaves become (n, 1)
+                v = v.reshape(v.shape[0], 1)
+            leaves[path] = v.contiguous()
+        if n is None:
+            raise ValueError("empty transition")
+        return leaves, n
+
+    def _init(self, leaves: dict[tuple, torch.Tensor]) -> None:
+        """:60-70 — storage shape/dtype follow the first batch (uint8 frames stay uint8)."""
+        self._fields = {
+            path: torch.zeros((self.max_size, *v.shape[1:]), dtype=v.dtype, device=self._dev)
+            for path, v in leaves.items()
+        }
+        self._storage = _unflatten(self._fields, (self.max_size,))
+        self.initialized = True
+
+    def add(self, data: DataType) -> None:
+        """:72-112 — ring write with wrap-around split (b2rl_ring_write, one call per field)."""
+        leaves, n = self._prepare(data)
+        if self._storage is None:
+            self._init(leaves)
+        if n > self.max_size:
+            raise ValueError("cannot add more transitions than max_size in one call")
+        stream = _lib.stream_ptr(self._dev)
+        for path, v in leaves.items():
+            dst = self._fields[path]
+            if v.dtype != dst.dtype:
+                v = v.to(dst.dtype)
+            row_bytes = dst[0].numel() * dst.element_size()
+            assert v[0].numel() * v.element_size() == row_bytes, f"shape mismatch for {path}"
+            _lib.check(self._lib.b2rl_ring_write(dst.data_ptr(), v.data_ptr(), row_bytes, self._cursor, n,
+                                                 self.max_size, stream))
+        self._cursor = (self._cursor + n) % self.max_size
+        self._size = min(self._size + n, self.max_size)
+        self.counter += n
+
+    # -- gather ---------------------------------------------------------------------------------
+    def _gather(self, idx: torch.Tensor) -> TensorDict:
+        """storage[idx] -> fresh tensors of shape idx.shape + feature shape (b2rl_gather_rows)."""
+        idx_dev = idx.to(self._dev, dtype=torch.int64, non_blocking=True).contiguous()
+        flat = idx_dev.reshape(-1)
+        nrows = flat.numel()
+        stream = _lib.stream_ptr(self._dev)
+        out = {}
+        for path, src in self._fields.items():
+            dst = torch.empty((nrows, *src.shape[1:]), dtype=src.dtype, device=self._dev)
+            row_bytes = src[0].numel() * src.element_size()
+            _lib.check(self._lib.b2rl_gather_rows(dst.data_ptr(), src.data_ptr(), flat.data_ptr(), row_bytes,
+                                                  nrows, stream))
+            out[path] = dst.reshape(*idx_dev.shape, *src.shape[1:])
+        return _unflatten(out, tuple(idx_dev.shape))
+
+    def sample(self, batch_size: int, return_idx: bool = False) -> TensorDict:
+        """:114-131 — uniform WITHOUT replacement (randperm from torch's CPU generator, Q12)."""
+        indices = torch.randperm(self.size)[:batch_size]
+        samples = self._gather(indices)
+        if return_idx:
+            samples["idxs"] = indices.to(self._dev)
+        return samples
+
+    def clear(self) -> None:
+        """:133-138."""
+        self._size = 0
+        self._cursor = 0
+        self._storage = None
+        self._fields = {}
+        self.initialized = False
+
+
+class MultiStepReplayBuffer(ReplayBuffer):
+    """n-step returns rolled at ingest (replay_buffer.py:141-258)."""
+
+    def __init__(self, max_size: int, n_step: int = 3, gamma: float = 0.99,
+                 device: str | torch.device = "cuda", dtype: torch.dtype = torch.float32) -> None:
+        super().__init__(max_size, device, dtype)
+        self.n_step = n_step
+        self.gamma = gamma
+        self.n_step_buffer: deque = deque(maxlen=n_step)
+        self.reward_key = "reward"
+        self.done_key = None
+        self.ns_key = "next_obs"
+
+    def add(self, data: DataType):
+        """:173-194 — returns the oldest transition of the window (or None while filling)."""
+        data = _as_collection(data).to(self._dev)
+        self.n_step_buffer.append(data)
+        if len(self.n_step_buffer) < self.n_step:
+            return None
+        n_step_data = self._get_n_step_info()
+        super().add(n_step_data)
+        return self.n_step_buffer[0]
+
+    def sample_from_indices(self, idxs: torch.Tensor) -> TensorDict:
+        """:196-204 — ``storage[idxs]`` (keeps the idxs shape, e.g. [B,1] -> fields [B,1,...])."""
+        if not isinstance(idxs, torch.Tensor):
+            idxs = torch.as_tensor(np.asarray(idxs))
+        return self._gather(idxs)
+
+    def _get_n_step_info(self) -> TensorDict:
+        """:206-258 on device: b2rl_nstep_fold (reward) + b2rl_select_copy (next_obs, done)."""
+        window = list(self.n_step_buffer)
+        first = window[0]
+        if not self.initialized:
+            assert self.reward_key in first, (
+                f"Reward key not found in transition. Expected key: {self.reward_key}")
+            assert self.ns_key in first, (
+                f"Next observation key not found in transition. Expected key: {self.ns_key}")
+            done_key = None
+            expected_keys = ["done", "termination", "terminated"]
+            for key in expected_keys:
+                if key in first:
+                    done_key = key
+                    break
+            assert done_key is not None, (
+                f"No done/termination key found in transition. Expected keys: {expected_keys}")
+            self.done_key = done_key
+
+        out = first.clone()
+        n = len(window)
+        if n == 1:
+            return out
+        stream = _lib.stream_ptr(self._dev)
+        rewards = [w[self.reward_key].to(torch.float32).contiguous() for w in window]
+        dones = [w[self.done_key].to(torch.float32).contiguous() for w in window]
+        num_envs = rewards[0].numel()
+        reward_out = torch.empty_like(rewards[0])
+        last = torch.empty(1, dtype=torch.int32, device=self._dev)
+        arr_t = ctypes.c_void_p * n
+        _lib.check(self._lib.b2rl_nstep_fold(arr_t(*[r.data_ptr() for r in rewards]),
+                                             arr_t(*[d.data_ptr() for d in dones]), n, num_envs,
+                                             float(self.gamma), reward_out.data_ptr(), last.data_ptr(), stream))
+        # carry next_obs / done of the step the fold stopped at; `last` stays on device
+        for key in (self.ns_key, self.done_key):
+            leaves0 = dict(_leaf_items({key: first[key]}))
+            for path in leaves0:
+                srcs = []
+                for w in window:
+                    v = w[path[0]]
+                    for k in path[1:]:
+                        v = v[k]
+                    srcs.append(v.contiguous())
+                dst = torch.empty_like(srcs[0])
+                # window[0] can only be selected when n_step == 1; slot 0 is a valid dummy
+                _lib.check(self._lib.b2rl_select_copy(dst.data_ptr(), arr_t(*[s.data_ptr() for s in srcs]), n,
+                                                      last.data_ptr(), dst.numel() * dst.element_size(), stream))
+                if len(path) == 1:
+                    out[key] = dst
+                else:
+                    tgt = out[path[0]]
+                    for k in path[1:-1]:
+                        tgt = tgt[k]
+                    tgt[path[-1]] = dst
+                self._keepalive = (srcs, rewards, dones)
+        out[self.reward_key] = reward_out.reshape(first[self.reward_key].shape).to(first[self.reward_key].dtype)
+        return out
+
+
+class PrioritizedReplayBuffer(ReplayBuffer):
+    """Prioritized replay with fp64 sum/min trees in HBM (replay_buffer.py:261-428)."""
+
+    def __init__(self, max_size: int, alpha: float = 0.6, device: str | torch.device = "cuda",
+                 dtype: torch.dtype = torch.float32) -> None:
+        super().__init__(max_size, device, dtype)
+        self.alpha = alpha
+        self.max_priority = 1.0
+        self.tree_ptr = 0
+        tree_capacity = 1
+        while tree_capacity < max_size:
+            tree_capacity *= 2
+        self.sum_tree = SumSegmentTree(tree_capacity, device=self._dev)
+        self.min_tree = MinSegmentTree(tree_capacity, device=self._dev)
+        self._cap = tree_capacity
+        # production sampling may draw uniforms on device (Philox) instead of torch's CPU stream
+        self.device_rng = False
+        self._philox_seed = 0x5EED
+        self._philox_offset = 0
+
+    def add(self, data: DataType) -> None:
+        """:296-309 — ring write, then the n new leaves get max_priority**alpha."""
+        leaves, n = self._prepare(data)
+        ReplayBuffer.add(self, _unflatten(leaves, (n,)))
+        p_alpha = float(self.max_priority) ** self.alpha
+        _lib.check(self._lib.b2rl_tree_set_range(self.sum_tree.data_ptr, self.min_tree.data_ptr, self._cap,
+                                                 self.tree_ptr, n, self.max_size, p_alpha,
+                                                 _lib.stream_ptr(self._dev)))
+        self.tree_ptr = (self.tree_ptr + n) % self.max_size
+
+    def _update_priority(self, idx: int, priority: float) -> None:
+        """:311-329."""
+        assert 0 <= idx < self.max_size
+        priority_alpha = priority ** self.alpha
+        self.sum_tree[idx] = priority_alpha
+        self.min_tree[idx] = priority_alpha
+        self.max_priority = max(self.max_priority, priority)
+
+    def _uniforms(self, batch_size: int) -> torch.Tensor:
+        # B x torch.rand(1).item() (replay_buffer.py:377) == torch.rand(B) on the CPU generator
+        return torch.rand(batch_size).to(self._dev, non_blocking=True)
+
+    def _sample(self, batch_size: int, beta: float | None):
+        idx = torch.empty(batch_size, dtype=torch.int64, device=self._dev)
+        w = torch.empty(batch_size, dtype=torch.float32, device=self._dev) if beta is not None else None
+        stream = _lib.stream_ptr(self._dev)
+        if self.device_rng:
+            _lib.check(self._lib.b2rl_per_sample_philox(
+                self.sum_tree.data_ptr, self.min_tree.data_ptr, self._cap, self._philox_seed, self._philox_offset,
+                batch_size, 0.0 if beta is None else float(beta), self._size, idx.data_ptr(),
+                None if w is None else w.data_ptr(), stream))
+            self._philox_offset += batch_size
+        else:
+            u = self._uniforms(batch_size)
+            _lib.check(self._lib.b2rl_per_sample(
+                self.sum_tree.data_ptr, self.min_tree.data_ptr, self._cap, u.data_ptr(), batch_size,
+                0.0 if beta is None else float(beta), self._size, idx.data_ptr(),
+                None if w is None else w.data_ptr(), stream))
+        return idx, w
+
+    def _sample_proportional(self, batch_size: int) -> torch.Tensor:
+        """:357-381 — stratified proportional sampling (indices int64 [B])."""
+        return self._sample(batch_size, None)[0]
+
+    def _calculate_weights(self, indices: torch.Tensor, beta: float) -> torch.Tensor:
+        """:383-409 for arbitrary indices (off the fused path; fp64 on device, cast to f32)."""
+        idx = indices.to(self._dev, dtype=torch.int64).reshape(-1)
+        st, mt = self.sum_tree._t, self.min_tree._t
+        total = st[1]
+        p_min = mt[1] / total
+        max_w = (p_min * self._size) ** -beta
+        p = st[self._cap + idx] / total
+        return (((p * self._size) ** -beta) / max_w).to(torch.float32)
+
+    def sample(self, batch_size: int, beta: float = 0.4) -> TensorDict:
+        """:331-355 — one kernel for tree descent + IS weights, one gather per field."""
+        indices, weights = self._sample(batch_size, beta)
+        samples = self._gather(indices)
+        samples["weights"] = weights.unsqueeze(1)
+        samples["idxs"] = indices.unsqueeze(1)
+        return samples
+
+    def update_priorities(self, indices, priorities) -> None:
+        """:411-428 — floor at 1e-5, leaf = p**alpha in CPython doubles (host, bit-exact),
+        batched last-writer-wins tree update on device (b2rl_tree_set)."""
+        if isinstance(priorities, torch.Tensor):
+            pri = priorities.detach().reshape(-1).cpu().tolist()
+        else:
+            pri = np.asarray(priorities).reshape(-1).tolist()
+        if isinstance(indices, torch.Tensor):
+            idx_dev = indices.detach().reshape(-1).to(self._dev, dtype=torch.int64)
+        else:
+            idx_dev = torch.as_tensor(np.asarray(indices).reshape(-1), dtype=torch.int64).to(self._dev)
+        n = min(idx_dev.numel(), len(pri))
+        alpha = self.alpha
+        floored = [p if p > 1e-5 else 1e-5 for p in pri[:n]]        # max(priority.item(), 1e-5)
+        p_alpha = torch.tensor([p ** alpha for p in floored], dtype=torch.float64)
+        self.max_priority = max(self.max_priority, max(floored)) if n else self.max_priority
+        pa_dev = p_alpha.to(self._dev, non_blocking=True)
+        _lib.check(self._lib.b2rl_tree_set(self.sum_tree.data_ptr, self.min_tree.data_ptr, self._cap,
+                                           idx_dev.data_ptr(), pa_dev.data_ptr(), n, _lib.stream_ptr(self._dev)))
+        self._keep = (idx_dev, pa_dev)

@@ -1,0 +1,173 @@
+// replay.cu — HBM-resident ring storage: wrap-split write, row gather, n-step fold.
+//
+// Replaces the TensorDict slice-assign / fancy-index of agilerl/components/replay_buffer.py
+// (:100-107 write, :126/:204/:345 gather) and the Python loop of _get_n_step_info (:236-256).
+// Pure byte movement: 128-bit coalesced loads/stores when rows are 16-byte multiples (uint8
+// 4x84x84 frames are 28224 B = 1764 x 16 B), scalar path otherwise.
+#include "common.cuh"
+
+namespace b2rl {
+
+template <typename V>
+__global__ void ring_write_kernel(V *__restrict__ storage, const V *__restrict__ src, int64_t row_v,
+                                  int64_t start, int64_t n, int64_t max_size) {
+    const int64_t total = n * row_v;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / row_v, c = e - r * row_v;
+        const int64_t dst_row = (start + r) % max_size;
+        storage[dst_row * row_v + c] = src[e];
+    }
+}
+
+// One CTA per row (grid-stride over rows) when rows are big; flat element loop when small.
+template <typename V>
+__global__ void gather_rows_kernel(V *__restrict__ dst, const V *__restrict__ storage,
+                                   const int64_t *__restrict__ idx, int64_t row_v, int64_t n) {
+    if (row_v >= 256) {
+        for (int64_t r = blockIdx.x; r < n; r += gridDim.x) {
+            const V *s = storage + idx[r] * row_v;
+            V *d = dst + r * row_v;
+            for (int64_t c = threadIdx.x; c < row_v; c += blockDim.x) d[c] = __ldg(s + c);
+        }
+    } else {
+        const int64_t total = n * row_v;
+        for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
+             e += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t r = e / row_v, c = e - r * row_v;
+            dst[e] = __ldg(storage + idx[r] * row_v + c);
+        }
+    }
+}
+
+constexpr int kMaxNStep = 16;
+struct StepPtrs {
+    const float *reward[kMaxNStep];
+    const float *done[kMaxNStep];
+    float scale[kMaxNStep];   // (float)(gamma ** k)
+};
+
+__global__ void nstep_fold_kernel(StepPtrs p, int n_step, int64_t num_envs, float *__restrict__ reward_out,
+                                  int32_t *__restrict__ last_out) {
+    // replay_buffer.py:236-256 — quirk Q3: reward of step k is added BEFORE its done is examined,
+    // the loop stops after a step where ANY env is done, step 0's own done never stops it.
+    for (int64_t e = threadIdx.x; e < num_envs; e += blockDim.x) reward_out[e] = p.reward[0][e];
+    int last = 0;
+    for (int k = 1; k < n_step; ++k) {
+        int any = 0;
+        for (int64_t e = threadIdx.x; e < num_envs; e += blockDim.x) {
+            reward_out[e] = __fadd_rn(reward_out[e], __fmul_rn(p.reward[k][e], p.scale[k]));
+            any |= (p.done[k][e] != 0.f);
+        }
+        last = k;
+        if (__syncthreads_or(any)) break;
+    }
+    if (threadIdx.x == 0) *last_out = last;
+}
+
+struct SrcPtrs { const void *p[kMaxNStep]; };
+__global__ void select_copy_kernel(uint8_t *__restrict__ dst, SrcPtrs srcs, const int32_t *__restrict__ which,
+                                   int64_t bytes) {
+    const uint8_t *s = static_cast<const uint8_t *>(srcs.p[*which]);
+    const bool vec = ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(dst) | (uintptr_t)bytes) & 15) == 0;
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
+    if (vec) {
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(s);
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+        for (int64_t i = tid; i < bytes / 16; i += nt) d4[i] = s4[i];
+    } else {
+        for (int64_t i = tid; i < bytes; i += nt) dst[i] = s[i];
+    }
+}
+
+template <typename F>
+static int dispatch_width(const void *a, const void *b, int64_t row_bytes, F &&f) {
+    const uintptr_t al = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | (uintptr_t)row_bytes;
+    if ((al & 15) == 0) return f(uint4{}, row_bytes / 16);
+    if ((al & 3) == 0) return f(uint32_t{}, row_bytes / 4);
+    return f(uint8_t{}, row_bytes);
+}
+
+}  // namespace b2rl
+
+using namespace b2rl;
+
+extern "C" {
+
+int b2rl_ring_write(void *storage, const void *src, int64_t row_bytes, int64_t start, int64_t n,
+                    int64_t max_size, void *stream) {
+    B2RL_CHECK_ARG(storage && src, "NULL buffer");
+    B2RL_CHECK_ARG(row_bytes > 0 && max_size > 0, "row_bytes and max_size must be positive");
+    B2RL_CHECK_ARG(start >= 0 && start < max_size, "cursor out of range");
+    B2RL_CHECK_ARG(n >= 0 && n <= max_size, "cannot add more rows than max_size in one call");
+    if (n == 0) return B2RL_OK;
+    cudaStream_t s = as_stream(stream);
+    return dispatch_width(storage, src, row_bytes, [&](auto tag, int64_t row_v) -> int {
+        using V = decltype(tag);
+        const int64_t total = n * row_v;
+        int blocks = (int)((total + 255) / 256);
+        const int cap_blocks = sm_count() * 8;
+        if (blocks > cap_blocks) blocks = cap_blocks;
+        ring_write_kernel<V><<<blocks, 256, 0, s>>>(static_cast<V *>(storage), static_cast<const V *>(src), row_v,
+                                                    start, n, max_size);
+        B2RL_LAUNCH_CHECK();
+        return B2RL_OK;
+    });
+}
+
+int b2rl_gather_rows(void *dst, const void *storage, const int64_t *idx, int64_t row_bytes, int64_t n,
+                     void *stream) {
+    B2RL_CHECK_ARG(dst && storage && idx, "NULL buffer");
+    B2RL_CHECK_ARG(row_bytes > 0, "row_bytes must be positive");
+    if (n <= 0) return B2RL_OK;
+    cudaStream_t s = as_stream(stream);
+    return dispatch_width(dst, storage, row_bytes, [&](auto tag, int64_t row_v) -> int {
+        using V = decltype(tag);
+        int blocks;
+        if (row_v >= 256) blocks = (int)(n < (int64_t)sm_count() * 8 ? n : (int64_t)sm_count() * 8);
+        else {
+            const int64_t total = n * row_v;
+            blocks = (int)((total + 255) / 256);
+            if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+        }
+        gather_rows_kernel<V><<<blocks, 256, 0, s>>>(static_cast<V *>(dst), static_cast<const V *>(storage), idx,
+                                                     row_v, n);
+        B2RL_LAUNCH_CHECK();
+        return B2RL_OK;
+    });
+}
+
+int b2rl_nstep_fold(const float *const *reward_steps, const float *const *done_steps, int n_step,
+                    int64_t num_envs, double gamma, float *reward_out, int32_t *last_step_out, void *stream) {
+    B2RL_CHECK_ARG(n_step >= 1 && n_step <= kMaxNStep, "n_step must be in [1, %d]", kMaxNStep);
+    B2RL_CHECK_ARG(reward_steps && done_steps && reward_out && last_step_out, "NULL buffer");
+    StepPtrs p;
+    double g = 1.0;
+    for (int k = 0; k < n_step; ++k) {
+        p.reward[k] = reward_steps[k];
+        p.done[k] = done_steps[k];
+        // gamma ** k as CPython computes it (pow), then rounded to f32 by the tensor*scalar multiply
+        p.scale[k] = (float)(k == 0 ? 1.0 : pow(gamma, (double)k));
+        (void)g;
+    }
+    nstep_fold_kernel<<<1, 256, 0, as_stream(stream)>>>(p, n_step, num_envs, reward_out, last_step_out);
+    B2RL_LAUNCH_CHECK();
+    return B2RL_OK;
+}
+
+int b2rl_select_copy(void *dst, const void *const *srcs_host, int n_srcs, const int32_t *which, int64_t bytes,
+                     void *stream) {
+    B2RL_CHECK_ARG(n_srcs >= 1 && n_srcs <= kMaxNStep, "n_srcs must be in [1, %d]", kMaxNStep);
+    B2RL_CHECK_ARG(dst && srcs_host && which, "NULL buffer");
+    if (bytes <= 0) return B2RL_OK;
+    SrcPtrs sp;
+    for (int i = 0; i < kMaxNStep; ++i) sp.p[i] = srcs_host[i < n_srcs ? i : 0];
+    int blocks = (int)((bytes / 16 + 255) / 256);
+    if (blocks < 1) blocks = 1;
+    if (blocks > sm_count() * 4) blocks = sm_count() * 4;
+    select_copy_kernel<<<blocks, 256, 0, as_stream(stream)>>>(static_cast<uint8_t *>(dst), sp, which, bytes);
+    B2RL_LAUNCH_CHECK();
+    return B2RL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,302 @@
+// tree.cu — fp64 sum/min priority trees resident in HBM (K2 / K1a of SURVEY §2).
+//
+// Replaces agilerl/components/segment_tree.py (list-backed Python trees) and the PER loops of
+// agilerl/components/replay_buffer.py:306-309, 357-428.  Everything here is IEEE fp64 with
+// explicit round-to-nearest intrinsics (no FMA contraction), so that given identical leaves the
+// trees, the stratified upper bounds and the retrieved indices are bit-identical to the
+// reference's CPython-double arithmetic.
+#include <cstdarg>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace b2rl {
+
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char *last_error() { return g_err; }
+
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+    }
+    return n;
+}
+
+__device__ __forceinline__ double dmin_py(double a, double b) { return b < a ? b : a; }  // Python min(a,b)
+
+__global__ void tree_fill_kernel(double *st, double *mt, int64_t n2) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    for (; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+        st[i] = 0.0;
+        mt[i] = inf;
+    }
+}
+
+// One CTA walks the <= kMaxItems touched leaves up to the root, level by level.
+// Sequential semantics of n __setitem__ calls: leaf <- last writer; every ancestor of a touched
+// leaf is a pure function of its two children, so recomputing bottom-up after all leaves are
+// placed yields the same bits as the reference's one-at-a-time updates.
+constexpr int kTreeThreads = 1024;
+constexpr int64_t kTreeChunk = 4096;
+
+template <bool kRange, bool kFromPriority>
+__global__ void __launch_bounds__(kTreeThreads)
+tree_set_kernel(double *__restrict__ st, double *__restrict__ mt, int64_t cap,
+                const int64_t *__restrict__ idx, const double *__restrict__ pa,
+                const float *__restrict__ pri, int64_t n, int64_t tree_ptr, int64_t max_size,
+                double range_val, double alpha, double floor_, double *max_priority) {
+    const int tid = threadIdx.x;
+    auto index_of = [&](int64_t i) -> int64_t {
+        if (kRange) return (tree_ptr + i) % max_size;
+        return idx[i];
+    };
+    double local_max = 0.0;
+    for (int64_t i = tid; i < n; i += kTreeThreads) {
+        const int64_t id = index_of(i);
+        bool last = true;
+        if (!kRange) {
+            for (int64_t j = i + 1; j < n; ++j)
+                if (idx[j] == id) { last = false; break; }
+        } else {
+            last = (i + max_size >= n);  // a later lap over the ring overwrites this slot
+        }
+        double v;
+        if (kRange) v = range_val;
+        else if (kFromPriority) {
+            double p = (double)pri[i];
+            p = p < floor_ ? floor_ : p;          // max(priority, 1e-5), replay_buffer.py:425
+            local_max = p > local_max ? p : local_max;
+            v = pow(p, alpha);
+        } else v = pa[i];
+        if (last) {
+            if (st) st[cap + id] = v;
+            if (mt) mt[cap + id] = v;
+        }
+    }
+    if (kFromPriority && max_priority != nullptr) {
+        // block max -> *max_priority = max(*max_priority, max_i p_i)  (replay_buffer.py:329)
+        __shared__ double smax[kTreeThreads / 32];
+        for (int o = 16; o > 0; o >>= 1) {
+            double other = __shfl_xor_sync(0xffffffffu, local_max, o);
+            local_max = other > local_max ? other : local_max;
+        }
+        if ((tid & 31) == 0) smax[tid >> 5] = local_max;
+        __syncthreads();
+        if (tid == 0) {
+            double m = *max_priority;
+            for (int w = 0; w < kTreeThreads / 32; ++w) m = smax[w] > m ? smax[w] : m;
+            *max_priority = m;
+        }
+    }
+    __syncthreads();
+    for (int shift = 1; (cap >> shift) >= 1; ++shift) {
+        for (int64_t i = tid; i < n; i += kTreeThreads) {
+            const int64_t node = (cap + index_of(i)) >> shift;
+            if (st) st[node] = __dadd_rn(st[2 * node], st[2 * node + 1]);
+            if (mt) mt[node] = dmin_py(mt[2 * node], mt[2 * node + 1]);
+        }
+        __syncthreads();
+    }
+}
+
+// Bulk rebuild of one level (used when a range update touches more than kTreeChunk leaves).
+__global__ void tree_level_kernel(double *st, double *mt, int64_t first, int64_t count) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    for (; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t node = first + i;
+        st[node] = __dadd_rn(st[2 * node], st[2 * node + 1]);
+        mt[node] = dmin_py(mt[2 * node], mt[2 * node + 1]);
+    }
+}
+__global__ void tree_range_leaves_kernel(double *st, double *mt, int64_t cap, int64_t tree_ptr,
+                                         int64_t n, int64_t max_size, double v) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    for (; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t id = (tree_ptr + i) % max_size;
+        st[cap + id] = v;
+        mt[cap + id] = v;
+    }
+}
+
+__device__ __forceinline__ int64_t retrieve_dev(const double *__restrict__ st, int64_t cap, double ub) {
+    int64_t idx = 1;
+    while (idx < cap) {  // segment_tree.py:148-155 — strict '>' tie rule (quirk Q6)
+        const int64_t left = 2 * idx;
+        const double l = __ldg(st + left);
+        if (l > ub) idx = left;
+        else { ub = __dsub_rn(ub, l); idx = left + 1; }
+    }
+    return idx - cap;
+}
+
+__global__ void tree_retrieve_kernel(const double *st, int64_t cap, const double *ub, int64_t n, int64_t *out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = retrieve_dev(st, cap, ub[i]);
+}
+
+// Philox4x32-10, one 128-bit block per counter; returns word `lane` (0..3).
+__device__ __forceinline__ void philox4x32_10(uint64_t seed, uint64_t c_lo, uint64_t c_hi, uint32_t out[4]) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    uint32_t c0 = (uint32_t)c_lo, c1 = (uint32_t)(c_lo >> 32), c2 = (uint32_t)c_hi, c3 = (uint32_t)(c_hi >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+template <bool kPhilox>
+__global__ void per_sample_kernel(const double *__restrict__ st, const double *__restrict__ mt, int64_t cap,
+                                  const float *__restrict__ uniforms, uint64_t seed, uint64_t offset,
+                                  int64_t B, double beta, int64_t size, int64_t *__restrict__ out_idx,
+                                  float *__restrict__ out_w) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const double total = st[1];                                   // sum_tree.sum()
+    const double segment = __ddiv_rn(total, (double)B);           // replay_buffer.py:369
+    const double a = __dmul_rn(segment, (double)i);
+    const double b = __dmul_rn(segment, (double)(i + 1));
+    float u;
+    if (kPhilox) {
+        uint32_t r[4];
+        philox4x32_10(seed, offset + (uint64_t)i, 0x50455253ull /* "PERS" */, r);
+        u = (float)(r[0] >> 8) * (1.0f / 16777216.0f);            // [0,1) with 24 bits like torch.rand
+    } else {
+        u = uniforms[i];
+    }
+    const double ub = __dadd_rn(__dmul_rn((double)u, __dsub_rn(b, a)), a);   // :377
+    const int64_t idx = retrieve_dev(st, cap, ub);
+    out_idx[i] = idx;
+    if (out_w != nullptr) {                                        // :383-409
+        const double p_min = __ddiv_rn(mt[1], total);
+        const double max_w = pow(__dmul_rn(p_min, (double)size), -beta);
+        const double p = __ddiv_rn(st[cap + idx], total);
+        const double w = pow(__dmul_rn(p, (double)size), -beta);
+        out_w[i] = (float)__ddiv_rn(w, max_w);
+    }
+}
+
+static bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
+
+}  // namespace b2rl
+
+using namespace b2rl;
+
+extern "C" {
+
+int b2rl_version(void) { return 100; }
+const char *b2rl_last_error(void) { return b2rl::last_error(); }
+
+int b2rl_device_sm_count(int device, int *out_host) {
+    B2RL_CHECK_ARG(out_host != nullptr, "out_host is NULL");
+    B2RL_CUDA(cudaDeviceGetAttribute(out_host, cudaDevAttrMultiProcessorCount, device));
+    return B2RL_OK;
+}
+
+int b2rl_tree_init(double *sum_tree, double *min_tree, int64_t cap, void *stream) {
+    B2RL_CHECK_ARG(is_pow2(cap), "capacity must be positive and a power of 2.");
+    B2RL_CHECK_ARG(sum_tree && min_tree, "tree pointer is NULL");
+    const int64_t n2 = 2 * cap;
+    const int blocks = (int)((n2 + 255) / 256 < 4096 ? (n2 + 255) / 256 : 4096);
+    tree_fill_kernel<<<blocks, 256, 0, as_stream(stream)>>>(sum_tree, min_tree, n2);
+    B2RL_LAUNCH_CHECK();
+    return B2RL_OK;
+}
+
+int b2rl_tree_set(double *sum_tree, double *min_tree, int64_t cap, const int64_t *idx,
+                  const double *p_alpha, int64_t n, void *stream) {
+    B2RL_CHECK_ARG(is_pow2(cap), "capacity must be positive and a power of 2.");
+    B2RL_CHECK_ARG(n >= 0, "n must be >= 0");
+    B2RL_CHECK_ARG(sum_tree || min_tree, "both trees are NULL");
+    for (int64_t off = 0; off < n; off += kTreeChunk) {   // chunks keep last-writer-wins order
+        const int64_t m = n - off < kTreeChunk ? n - off : kTreeChunk;
+        tree_set_kernel<false, false><<<1, kTreeThreads, 0, as_stream(stream)>>>(
+            sum_tree, min_tree, cap, idx + off, p_alpha + off, nullptr, m, 0, 0, 0.0, 0.0, 0.0, nullptr);
+        B2RL_LAUNCH_CHECK();
+    }
+    return B2RL_OK;
+}
+
+int b2rl_tree_set_from_priorities(double *sum_tree, double *min_tree, int64_t cap, const int64_t *idx,
+                                  const float *priority, int64_t n, double alpha, double floor_,
+                                  double *max_priority, void *stream) {
+    B2RL_CHECK_ARG(is_pow2(cap), "capacity must be positive and a power of 2.");
+    for (int64_t off = 0; off < n; off += kTreeChunk) {
+        const int64_t m = n - off < kTreeChunk ? n - off : kTreeChunk;
+        tree_set_kernel<false, true><<<1, kTreeThreads, 0, as_stream(stream)>>>(
+            sum_tree, min_tree, cap, idx + off, nullptr, priority + off, m, 0, 0, 0.0, alpha, floor_, max_priority);
+        B2RL_LAUNCH_CHECK();
+    }
+    return B2RL_OK;
+}
+
+int b2rl_tree_set_range(double *sum_tree, double *min_tree, int64_t cap, int64_t tree_ptr, int64_t n,
+                        int64_t max_size, double p_alpha, void *stream) {
+    B2RL_CHECK_ARG(is_pow2(cap), "capacity must be positive and a power of 2.");
+    B2RL_CHECK_ARG(max_size > 0 && max_size <= cap, "max_size must be in (0, cap]");
+    B2RL_CHECK_ARG(tree_ptr >= 0 && tree_ptr < max_size, "tree_ptr out of range");
+    if (n <= 0) return B2RL_OK;
+    cudaStream_t s = as_stream(stream);
+    if (n <= kTreeChunk) {
+        tree_set_kernel<true, false><<<1, kTreeThreads, 0, s>>>(sum_tree, min_tree, cap, nullptr, nullptr, nullptr,
+                                                                 n, tree_ptr, max_size, p_alpha, 0.0, 0.0, nullptr);
+        B2RL_LAUNCH_CHECK();
+        return B2RL_OK;
+    }
+    const int64_t m = n < max_size ? n : max_size;   // more than a lap rewrites every slot
+    tree_range_leaves_kernel<<<(int)((m + 255) / 256 < 2048 ? (m + 255) / 256 : 2048), 256, 0, s>>>(
+        sum_tree, min_tree, cap, tree_ptr, m, max_size, p_alpha);
+    B2RL_LAUNCH_CHECK();
+    for (int64_t count = cap / 2; count >= 1; count /= 2) {
+        const int blocks = (int)((count + 255) / 256 < 2048 ? (count + 255) / 256 : 2048);
+        tree_level_kernel<<<blocks, 256, 0, s>>>(sum_tree, min_tree, count, count);
+        B2RL_LAUNCH_CHECK();
+    }
+    return B2RL_OK;
+}
+
+int b2rl_tree_retrieve(const double *sum_tree, int64_t cap, const double *upperbound, int64_t n,
+                       int64_t *out_idx, void *stream) {
+    B2RL_CHECK_ARG(is_pow2(cap), "capacity must be positive and a power of 2.");
+    if (n <= 0) return B2RL_OK;
+    tree_retrieve_kernel<<<(int)((n + 127) / 128), 128, 0, as_stream(stream)>>>(sum_tree, cap, upperbound, n, out_idx);
+    B2RL_LAUNCH_CHECK();
+    return B2RL_OK;
+}
+
+int b2rl_per_sample(const double *sum_tree, const double *min_tree, int64_t cap, const float *uniforms,
+                    int64_t B, double beta, int64_t size, int64_t *out_idx, float *out_w, void *stream) {
+    B2RL_CHECK_ARG(is_pow2(cap), "capacity must be positive and a power of 2.");
+    B2RL_CHECK_ARG(B > 0 && uniforms && out_idx, "bad sample arguments");
+    per_sample_kernel<false><<<(int)((B + 63) / 64), 64, 0, as_stream(stream)>>>(
+        sum_tree, min_tree, cap, uniforms, 0, 0, B, beta, size, out_idx, out_w);
+    B2RL_LAUNCH_CHECK();
+    return B2RL_OK;
+}
+
+int b2rl_per_sample_philox(const double *sum_tree, const double *min_tree, int64_t cap, uint64_t seed,
+                           uint64_t offset, int64_t B, double beta, int64_t size, int64_t *out_idx,
+                           float *out_w, void *stream) {
+    B2RL_CHECK_ARG(is_pow2(cap), "capacity must be positive and a power of 2.");
+    B2RL_CHECK_ARG(B > 0 && out_idx, "bad sample arguments");
+    per_sample_kernel<true><<<(int)((B + 63) / 64), 64, 0, as_stream(stream)>>>(
+        sum_tree, min_tree, cap, nullptr, seed, offset, B, beta, size, out_idx, out_w);
+    B2RL_LAUNCH_CHECK();
+    return B2RL_OK;
+}
+
+}  // extern "C"

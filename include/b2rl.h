@@ -1,0 +1,231 @@
+/* b2rl.h — C ABI of libb2rl.so: the B200 (sm_100a) hot path behind AgileRL's off-policy learn().
+ *
+ * The reference (AgileRL 2.6.1) is pure Python and has NO FFI / plugin interface: its boundary
+ * for this path is the Python class surface.  This header is therefore the new
+ * seam a maintainer would bind from those classes (ctypes stub in INTEGRATION.md).  Every entry
+ * point cites the reference routine it replaces.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.  All pointers are DEVICE
+ *     pointers unless the name ends in _host.  `stream` is a cudaStream_t passed as void*.
+ *   - every function returns 0 on success, a negative B2RL_E* code on failure;
+ *     b2rl_last_error() returns a thread-local message.  Nothing here synchronises the stream
+ *     unless documented; nothing allocates device memory (the caller owns every buffer).
+ *   - integer / index / priority-tree work is bit-exact w.r.t. the reference's Python-double
+ *     arithmetic (IEEE fp64, no FMA contraction); fp32 network math follows torch op order where
+ *     it matters (projection, noise composition, Polyak) and is within 1e-5 elsewhere.
+ */
+#ifndef B2RL_H_
+#define B2RL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2RL_OK 0
+#define B2RL_EINVAL (-1)   /* bad argument (maps to AssertionError / ValueError in the wrappers) */
+#define B2RL_ECUDA (-2)    /* CUDA runtime error (RuntimeError) */
+#define B2RL_EUNSUPPORTED (-3) /* architecture/activation outside what the kernels implement */
+
+int b2rl_version(void);
+const char *b2rl_last_error(void);
+/* Device properties the host side sizes grids with (SM count, etc.). */
+int b2rl_device_sm_count(int device, int *out_host);
+
+/* ------------------------------------------------------------------------------------------
+ * Priority trees — agilerl/components/segment_tree.py (SumSegmentTree / MinSegmentTree).
+ * Layout: array heap of 2*cap fp64 per tree, node i has children 2i, 2i+1, leaf j at cap+j,
+ * root at 1 (tree[0] unused, holds the init value like the reference list).
+ * ------------------------------------------------------------------------------------------ */
+
+/* SegmentTree.__init__ (segment_tree.py:19-26): sum tree <- 0.0, min tree <- +inf. */
+int b2rl_tree_init(double *sum_tree, double *min_tree, int64_t cap, void *stream);
+
+/* n x SegmentTree.__setitem__ (segment_tree.py:81-95) on BOTH trees, sequential semantics:
+ * duplicate indices resolve to the LAST writer; every touched ancestor is recomputed bottom-up
+ * as op(tree[2i], tree[2i+1]).  leaf values are the already-exponentiated p**alpha
+ * (PrioritizedReplayBuffer._update_priority, replay_buffer.py:311-329).  idx in [0, cap).
+ * Either tree pointer may be NULL to update only the other one (SegmentTree.__setitem__). */
+int b2rl_tree_set(double *sum_tree, double *min_tree, int64_t cap, const int64_t *idx,
+                  const double *p_alpha, int64_t n, void *stream);
+
+/* PrioritizedReplayBuffer.add's priority loop (replay_buffer.py:306-309): n consecutive slots
+ * starting at tree_ptr, wrapping modulo max_size (not cap — quirk Q7), all set to p_alpha. */
+int b2rl_tree_set_range(double *sum_tree, double *min_tree, int64_t cap, int64_t tree_ptr,
+                        int64_t n, int64_t max_size, double p_alpha, void *stream);
+
+/* Device variant used by the fused path: leaf = pow(max(priority, floor), alpha) computed ON
+ * DEVICE (<= 1 ulp from glibc pow: leaves are NOT guaranteed bit-identical to the reference;
+ * the tree arithmetic above them is).  Also folds max(priority) into *max_priority (fp64). */
+int b2rl_tree_set_from_priorities(double *sum_tree, double *min_tree, int64_t cap,
+                                  const int64_t *idx, const float *priority, int64_t n,
+                                  double alpha, double floor_, double *max_priority, void *stream);
+
+/* SumSegmentTree.retrieve (segment_tree.py:136-156) for n upper bounds. */
+int b2rl_tree_retrieve(const double *sum_tree, int64_t cap, const double *upperbound, int64_t n,
+                       int64_t *out_idx, void *stream);
+
+/* PrioritizedReplayBuffer._sample_proportional + _calculate_weights
+ * (replay_buffer.py:357-409): stratified proportional sample from B float32 uniforms and the
+ * importance weights ((p_i*size)^-beta / (p_min*size)^-beta), fp64 then cast to f32.
+ * out_idx int64[B], out_w float[B]. */
+int b2rl_per_sample(const double *sum_tree, const double *min_tree, int64_t cap,
+                    const float *uniforms, int64_t B, double beta, int64_t size, int64_t *out_idx,
+                    float *out_w, void *stream);
+/* Same, drawing the uniforms on device from Philox(seed, offset) (production path). */
+int b2rl_per_sample_philox(const double *sum_tree, const double *min_tree, int64_t cap,
+                           uint64_t seed, uint64_t offset, int64_t B, double beta, int64_t size,
+                           int64_t *out_idx, float *out_w, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Ring storage — ReplayBuffer.add / storage[indices] (replay_buffer.py:72-112, :126, :204, :345).
+ * One call per field (SoA); rows are opaque byte strings of row_bytes.
+ * ------------------------------------------------------------------------------------------ */
+
+/* storage[start:start+n] (with wrap split at max_size) <- src[0:n]. */
+int b2rl_ring_write(void *storage, const void *src, int64_t row_bytes, int64_t start, int64_t n,
+                    int64_t max_size, void *stream);
+/* dst[i] <- storage[idx[i]], i < n (idx int64 on device, values in [0, max_size)). */
+int b2rl_gather_rows(void *dst, const void *storage, const int64_t *idx, int64_t row_bytes,
+                     int64_t n, void *stream);
+
+/* MultiStepReplayBuffer._get_n_step_info (replay_buffer.py:206-258) over a device window of n
+ * per-env batches (oldest first): reward_out[e] = sum_i gamma^i r_i[e] (fp32 accumulate, gamma^i a
+ * double rounded to f32 like torch scalar mul), stop after the first step i>=1 where ANY env is
+ * done; last_step_out (int32, 1 element) = index of the step whose next_obs/done are carried. */
+int b2rl_nstep_fold(const float *const *reward_steps, const float *const *done_steps, int n_step,
+                    int64_t num_envs, double gamma, float *reward_out, int32_t *last_step_out,
+                    void *stream);
+
+/* dst[0:bytes] <- srcs[*which][0:bytes]: carries next_obs/done of the step the fold stopped
+ * at (replay_buffer.py:249-250) without a host round trip.  srcs_host: HOST array of n_srcs
+ * device pointers; which: DEVICE int32. */
+int b2rl_select_copy(void *dst, const void *const *srcs_host, int n_srcs, const int32_t *which,
+                     int64_t bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Networks — RainbowQNetwork / QNetwork forward+backward, RainbowDQN/DQN learn tail.
+ * A network is a flat fp32 parameter buffer plus a layer table.
+ * ------------------------------------------------------------------------------------------ */
+enum { B2RL_ACT_NONE = 0, B2RL_ACT_RELU = 1, B2RL_ACT_ELU = 2, B2RL_ACT_GELU = 3, B2RL_ACT_TANH = 4 };
+enum { B2RL_LAYER_CONV = 0, B2RL_LAYER_LINEAR = 1 };
+enum { B2RL_LN_NONE = 0, B2RL_LN_AFFINE = 1, B2RL_LN_PLAIN = 2 };
+enum { B2RL_NET_Q = 0, B2RL_NET_RAINBOW = 1 };
+
+typedef struct b2rl_layer {
+    int32_t kind;                       /* B2RL_LAYER_* */
+    int32_t in_c, in_h, in_w;           /* conv input  (linear: in_c = in_features, h=w=1) */
+    int32_t out_c, out_h, out_w;        /* conv output (linear: out_c = out_features) */
+    int32_t ksize, stride;
+    int32_t act;                        /* activation applied after (LN if any) */
+    int32_t ln;                         /* B2RL_LN_* applied between linear and activation */
+    int32_t noisy;                      /* NoisyLinear: W = mu + sigma*eps */
+    int64_t w_off, b_off;               /* offsets (floats) into the parameter buffer (mu) */
+    int64_t ws_off, bs_off;             /* sigma offsets (noisy only) */
+    int64_t we_off, be_off;             /* epsilon offsets into the eps buffer (noisy only) */
+    int64_t lnw_off, lnb_off;           /* LayerNorm affine (B2RL_LN_AFFINE only) */
+} b2rl_layer;
+
+#define B2RL_MAX_ENC 12
+#define B2RL_MAX_HEAD 6
+
+typedef struct b2rl_net_desc {
+    int32_t kind;                       /* B2RL_NET_* */
+    int32_t n_enc, n_val, n_adv;        /* layer counts (n_adv = 0 for B2RL_NET_Q) */
+    b2rl_layer enc[B2RL_MAX_ENC];       /* encoder: convs then linears (flatten is implicit) */
+    b2rl_layer val[B2RL_MAX_HEAD];      /* value head / plain Q head */
+    b2rl_layer adv[B2RL_MAX_HEAD];      /* advantage head (rainbow) */
+    int32_t n_actions, n_atoms;
+    int32_t obs_u8;                     /* observations are uint8 (else float32) */
+    int32_t normalize;                  /* (x-low)/(high-low), algo_utils.py:1131-1180 */
+    float obs_low, obs_high;
+    int64_t obs_elems;                  /* elements per observation row */
+    int64_t n_params, n_eps;            /* sizes of the flat parameter / epsilon buffers */
+} b2rl_net_desc;
+
+/* Bytes of scratch a forward/learn call needs for `rows` observation rows. */
+int b2rl_net_workspace_bytes(const b2rl_net_desc *net_host, int64_t rows, int with_backward,
+                             size_t *out_host);
+
+/* NoisyLinear.reset_noise for every noisy layer in traversal order
+ * (custom_components.py:116-131): eps_W = f(e_out) (x) f(e_in), eps_b = f(e_out),
+ * f(x) = sign(x) sqrt|x|.  `normals` holds, per noisy layer, randn(in) then randn(out). */
+int b2rl_noise_reset_from_normals(const b2rl_net_desc *net_host, float *eps, const float *normals,
+                                  void *stream);
+/* Same with normals drawn on device: Philox4x32-10(seed, subsequence = layer, offset). */
+int b2rl_noise_reset_philox(const b2rl_net_desc *net_host, float *eps, uint64_t seed,
+                            uint64_t offset, void *stream);
+/* Number of standard normals one reset consumes. */
+int b2rl_noise_count(const b2rl_net_desc *net_host, int64_t *out_host);
+
+/* Forward only (get_action path: dqn_rainbow.py:239-282, dqn.py:262-264).
+ * obs: rows x obs_elems (uint8 or f32); row_idx (nullable) gathers rows from a ring.
+ * q_out: rows x n_actions expected values; argmax_out (nullable): int64 rows.
+ * use_noise: train-mode NoisyLinear (Rainbow acts in train mode). */
+int b2rl_net_forward_q(const b2rl_net_desc *net_host, const float *params, const float *eps,
+                       int use_noise, const void *obs, const int64_t *row_idx, int64_t rows,
+                       float *q_out, int64_t *argmax_out, void *workspace, size_t workspace_bytes,
+                       void *stream);
+
+/* Scalars of one learn step. */
+typedef struct b2rl_learn_cfg {
+    int64_t batch;                      /* B (== agent.batch_size, quirk Q17) */
+    float gamma;                        /* discount used in the target (gamma**n_step for n-step) */
+    float v_min, v_max;                 /* C51 support bounds (rainbow) */
+    double delta_z;                     /* (v_max - v_min)/(n_atoms-1) as the Python double */
+    int32_t weights_mode;               /* 0: no PER (mean l); 1: weights [B] -> mean(l*w);
+                                           2: weights [B,1] -> mean(l)*mean(w)  (quirk Q1) */
+    int32_t driver_shapes;              /* 1: reward/done arrived [B,1,1] (quirk Q2 semantics) */
+    int32_t double_dqn;                 /* DQN only */
+    int32_t clip;                       /* 1: clip_grad_norm_(10.0) (rainbow), 0: none (DQN) */
+    float max_grad_norm;
+    float lr, beta1, beta2, adam_eps;
+    double bias_correction1, bias_correction2; /* 1-beta^step as Python doubles */
+    float tau;
+    float prior_eps;
+    int32_t accumulate_loss;            /* 1: add this call's per-sample loss to loss_elem
+                                           (combined_reward second pass) */
+} b2rl_learn_cfg;
+
+/* Device buffers of one learn step (all fp32 unless stated). */
+typedef struct b2rl_learn_bufs {
+    float *actor_params, *target_params;     /* n_params each */
+    float *actor_eps, *target_eps;           /* n_eps each */
+    float *grads, *exp_avg, *exp_avg_sq;     /* n_params each */
+    const void *obs, *next_obs;              /* batch rows, or ring bases when row_idx != NULL */
+    const int64_t *row_idx;                  /* nullable: B ring rows */
+    const float *action, *reward, *done;     /* B each */
+    const float *weights;                    /* B (PER) or NULL */
+    const float *support;                    /* n_atoms (rainbow) */
+    float *loss_elem;                        /* out: B per-sample loss */
+    float *priorities;                       /* out: B, loss_elem + prior_eps (nullable) */
+    float *loss_scalar;                      /* out: 1, the scalar loss that was back-propagated */
+    float *proj_dist;                        /* out (nullable): B x n_atoms projected target */
+    void *workspace; size_t workspace_bytes;
+} b2rl_learn_bufs;
+
+/* RainbowDQN._dqn_loss (dqn_rainbow.py:284-367): three forwards, C51 projection, cross-entropy;
+ * writes per-sample loss, leaves dL/dlogits staged in the workspace.  Does not touch grads. */
+int b2rl_rainbow_loss(const b2rl_net_desc *net_host, const b2rl_learn_cfg *cfg_host,
+                      const b2rl_learn_bufs *bufs_host, void *stream);
+/* Back-propagate mean(loss*w) of the staged loss(es) into `grads` (loss.backward()).
+ * n_passes = 1, or 2 when combined_reward staged two losses. */
+int b2rl_rainbow_backward(const b2rl_net_desc *net_host, const b2rl_learn_cfg *cfg_host,
+                          const b2rl_learn_bufs *bufs_host, void *stream);
+/* Tail of learn (dqn_rainbow.py:473-488): clip_grad_norm_, Adam, soft_update. */
+int b2rl_optim_step(const b2rl_net_desc *net_host, const b2rl_learn_cfg *cfg_host,
+                    const b2rl_learn_bufs *bufs_host, void *stream);
+/* DQN.update + learn (dqn.py:274-347): (double) Q target, MSE, backward, Adam, soft update. */
+int b2rl_dqn_learn(const b2rl_net_desc *net_host, const b2rl_learn_cfg *cfg_host,
+                   const b2rl_learn_bufs *bufs_host, void *stream);
+/* Whole Rainbow learn step for the common case (one loss pass): loss + backward + optim. */
+int b2rl_rainbow_learn(const b2rl_net_desc *net_host, const b2rl_learn_cfg *cfg_host,
+                       const b2rl_learn_bufs *bufs_host, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2RL_H_ */
