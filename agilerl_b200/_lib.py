@@ -42,12 +42,12 @@ class NetDesc(Structure):
 
 class LearnCfg(Structure):
     _fields_ = [
-        ("batch", c_int64), ("gamma", c_float), ("v_min", c_float), ("v_max", c_float),
+        ("batch", c_int64), ("gamma", c_double), ("v_min", c_double), ("v_max", c_double),
         ("delta_z", c_double), ("weights_mode", c_int32), ("driver_shapes", c_int32),
-        ("double_dqn", c_int32), ("clip", c_int32), ("max_grad_norm", c_float),
-        ("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("adam_eps", c_float),
-        ("bias_correction1", c_double), ("bias_correction2", c_double), ("tau", c_float),
-        ("prior_eps", c_float), ("accumulate_loss", c_int32),
+        ("double_dqn", c_int32), ("clip", c_int32), ("max_grad_norm", c_double),
+        ("lr", c_double), ("beta1", c_double), ("beta2", c_double), ("adam_eps", c_double),
+        ("bias_correction1", c_double), ("bias_correction2", c_double), ("tau", c_double),
+        ("prior_eps", c_double), ("accumulate", c_int32), ("use_noise", c_int32),
     ]
 
 
@@ -84,8 +84,8 @@ _SIGS = {
     "b2rl_noise_reset_from_normals": ([POINTER(NetDesc), c_void_p, c_void_p, c_void_p], c_int),
     "b2rl_noise_reset_philox": ([POINTER(NetDesc), c_void_p, c_uint64, c_uint64, c_void_p], c_int),
     "b2rl_noise_count": ([POINTER(NetDesc), POINTER(c_int64)], c_int),
-    "b2rl_net_forward_q": ([POINTER(NetDesc), c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p,
-                            c_void_p, c_void_p, c_size_t, c_void_p], c_int),
+    "b2rl_net_forward_q": ([POINTER(NetDesc), c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64,
+                            c_void_p, c_void_p, c_void_p, c_size_t, c_void_p], c_int),
     "b2rl_rainbow_loss": ([POINTER(NetDesc), POINTER(LearnCfg), POINTER(LearnBufs), c_void_p], c_int),
     "b2rl_rainbow_backward": ([POINTER(NetDesc), POINTER(LearnCfg), POINTER(LearnBufs), c_void_p], c_int),
     "b2rl_optim_step": ([POINTER(NetDesc), POINTER(LearnCfg), POINTER(LearnBufs), c_void_p], c_int),

@@ -1,0 +1,209 @@
+"""Device-side state and launch logic of one learning agent (host glue over libb2rl.so).
+
+``NetBuffers`` = one network's flat fp32 parameter + epsilon buffers with named views that carry
+the reference's ``state_dict()`` keys.  ``LearnEngine`` = actor + target + Adam moments + scratch,
+and the calls that replace ``RainbowDQN.learn`` / ``DQN.learn`` bodies
+(agilerl/algorithms/dqn_rainbow.py:369-490, dqn.py:326-347).
+"""
+from __future__ import annotations
+
+import ctypes
+from collections import OrderedDict
+
+import torch
+
+from .. import _lib
+from ..networks.spec import FlatLayout
+
+
+class NetBuffers:
+    def __init__(self, layout: FlatLayout, device):
+        self.layout = layout
+        self.device = _lib.as_device(device)
+        self.params = torch.zeros(max(layout.n_params, 1), dtype=torch.float32, device=self.device)
+        self.eps = torch.zeros(max(layout.n_eps, 1), dtype=torch.float32, device=self.device)
+
+    def view(self, key: str) -> torch.Tensor:
+        e = self.layout.entries[key]
+        n = 1
+        for s in e.shape:
+            n *= s
+        buf = self.params if e.buf == "param" else self.eps
+        return buf[e.offset:e.offset + n].view(e.shape)
+
+    def state_dict(self) -> "OrderedDict[str, torch.Tensor]":
+        return OrderedDict((k, self.view(k).clone()) for k in self.layout.entries)
+
+    def load_state_dict(self, sd, strict: bool = True) -> None:
+        for k in self.layout.entries:
+            if k in sd:
+                v = sd[k]
+                v = v if isinstance(v, torch.Tensor) else torch.as_tensor(v)
+                self.view(k).copy_(v.to(self.device, dtype=torch.float32))
+            elif strict:
+                raise KeyError(f"missing key {k} in state_dict")
+
+    def copy_from(self, other: "NetBuffers") -> None:
+        self.params.copy_(other.params)
+        self.eps.copy_(other.eps)
+
+
+class LearnEngine:
+    def __init__(self, layout: FlatLayout, actor: NetBuffers, target: NetBuffers):
+        self.layout, self.actor, self.target = layout, actor, target
+        self.device = actor.device
+        self.lib = _lib.load()
+        n = max(layout.n_params, 1)
+        self.grads = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.step = 0
+        self._ws: dict[tuple, torch.Tensor] = {}
+        self._noise_count = ctypes.c_int64(0)
+        _lib.check(self.lib.b2rl_noise_count(ctypes.byref(layout.desc), ctypes.byref(self._noise_count)))
+        self.philox_seed = 0xB200
+        self.philox_offset = 0
+
+    # -- scratch -------------------------------------------------------------------------------
+    def workspace(self, rows: int, backward: bool) -> torch.Tensor:
+        key = (rows, backward)
+        ws = self._ws.get(key)
+        if ws is None:
+            need = ctypes.c_size_t(0)
+            _lib.check(self.lib.b2rl_net_workspace_bytes(ctypes.byref(self.layout.desc), rows, int(backward),
+                                                         ctypes.byref(need)))
+            ws = torch.empty(need.value, dtype=torch.uint8, device=self.device)
+            self._ws[key] = ws
+        return ws
+
+    @property
+    def noise_count(self) -> int:
+        return int(self._noise_count.value)
+
+    # -- noise ---------------------------------------------------------------------------------
+    def reset_noise(self, net: NetBuffers, normals: torch.Tensor | None = None) -> None:
+        """NoisyLinear.reset_noise for every noisy layer (custom_components.py:116-131)."""
+        if self.noise_count == 0:
+            return
+        stream = _lib.stream_ptr(self.device)
+        if normals is not None:
+            z = normals.to(self.device, dtype=torch.float32).contiguous()
+            assert z.numel() == self.noise_count, f"need {self.noise_count} normals, got {z.numel()}"
+            _lib.check(self.lib.b2rl_noise_reset_from_normals(ctypes.byref(self.layout.desc), net.eps.data_ptr(),
+                                                              z.data_ptr(), stream))
+            self._keep = z
+        else:
+            _lib.check(self.lib.b2rl_noise_reset_philox(ctypes.byref(self.layout.desc), net.eps.data_ptr(),
+                                                        self.philox_seed, self.philox_offset, stream))
+            self.philox_offset += self.noise_count
+
+    # -- forward -------------------------------------------------------------------------------
+    def q_values(self, net: NetBuffers, obs: torch.Tensor, support: torch.Tensor | None, use_noise: bool,
+                 row_idx: torch.Tensor | None = None, want_argmax: bool = False):
+        desc = self.layout.desc
+        rows = obs.shape[0] if row_idx is None else row_idx.numel()
+        obs = self._obs(obs)
+        q = torch.empty((rows, desc.n_actions), dtype=torch.float32, device=self.device)
+        am = torch.empty(rows, dtype=torch.int64, device=self.device) if want_argmax else None
+        ws = self.workspace(rows, False)
+        _lib.check(self.lib.b2rl_net_forward_q(
+            ctypes.byref(desc), net.params.data_ptr(), net.eps.data_ptr(), int(use_noise),
+            None if support is None else support.data_ptr(), obs.data_ptr(),
+            None if row_idx is None else row_idx.data_ptr(), rows, q.data_ptr(),
+            None if am is None else am.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(self.device)))
+        return (q, am) if want_argmax else q
+
+    def _obs(self, obs: torch.Tensor) -> torch.Tensor:
+        _lib.require_cuda_tensor(obs, "observation batch")
+        want = torch.uint8 if self.layout.desc.obs_u8 else torch.float32
+        if obs.dtype != want:
+            obs = obs.to(want)
+        return obs.contiguous()
+
+    @staticmethod
+    def _vec(t: torch.Tensor, device) -> torch.Tensor:
+        return t.to(device, dtype=torch.float32).reshape(-1).contiguous()
+
+    # -- learn ---------------------------------------------------------------------------------
+    def _cfg(self, B, *, gamma, v_min=0.0, v_max=0.0, delta_z=1.0, weights_mode=0, driver_shapes=0, double=0,
+             clip=1, lr=1e-4, tau=1e-3, prior_eps=1e-6, accumulate=0, use_noise=1, step=1) -> _lib.LearnCfg:
+        c = _lib.LearnCfg()
+        c.batch = B
+        c.gamma, c.v_min, c.v_max, c.delta_z = float(gamma), float(v_min), float(v_max), float(delta_z)
+        c.weights_mode, c.driver_shapes, c.double_dqn, c.clip = weights_mode, driver_shapes, double, clip
+        c.max_grad_norm = 10.0
+        c.lr, c.beta1, c.beta2, c.adam_eps = float(lr), 0.9, 0.999, 1e-8      # torch.optim.Adam defaults
+        c.bias_correction1 = 1.0 - 0.9 ** step
+        c.bias_correction2 = 1.0 - 0.999 ** step
+        c.tau, c.prior_eps = float(tau), float(prior_eps)
+        c.accumulate, c.use_noise = accumulate, use_noise
+        return c
+
+    def _bufs(self, B, batch: dict, weights, support, loss_elem, priorities, loss_scalar, proj, row_idx=None):
+        b = _lib.LearnBufs()
+        b.actor_params, b.target_params = self.actor.params.data_ptr(), self.target.params.data_ptr()
+        b.actor_eps, b.target_eps = self.actor.eps.data_ptr(), self.target.eps.data_ptr()
+        b.grads, b.exp_avg, b.exp_avg_sq = self.grads.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr()
+        keep = [self._obs(batch["obs"]), self._obs(batch["next_obs"]), self._vec(batch["action"], self.device),
+                self._vec(batch["reward"], self.device), self._vec(batch["done"], self.device)]
+        b.obs, b.next_obs, b.action, b.reward, b.done = (t.data_ptr() for t in keep)
+        if row_idx is not None:
+            b.row_idx = row_idx.data_ptr()
+        else:
+            for t in keep[2:]:
+                assert t.numel() == B, f"batch fields must have exactly batch_size={B} rows (quirk Q17)"
+        if weights is not None:
+            w = self._vec(weights, self.device)
+            keep.append(w)
+            b.weights = w.data_ptr()
+        if support is not None:
+            b.support = support.data_ptr()
+        b.loss_elem = loss_elem.data_ptr()
+        b.priorities = None if priorities is None else priorities.data_ptr()
+        b.loss_scalar = loss_scalar.data_ptr()
+        b.proj_dist = None if proj is None else proj.data_ptr()
+        ws = self.workspace(B, True)
+        b.workspace, b.workspace_bytes = ws.data_ptr(), ws.numel()
+        return b, keep
+
+    def rainbow_learn(self, passes: list, *, B: int, support: torch.Tensor, weights, weights_mode: int, hp: dict,
+                      noise_normals=None, want_proj: bool = False, row_idx=None):
+        """``passes`` = [(batch, gamma, driver_shapes)], one per ``_dqn_loss`` call of the reference
+        (1-step and/or n-step; two entries when combined_reward).  Returns device tensors
+        (loss_scalar[1], loss_elem[B], priorities[B], proj)."""
+        desc = ctypes.byref(self.layout.desc)
+        stream = _lib.stream_ptr(self.device)
+        loss_elem = torch.empty(B, dtype=torch.float32, device=self.device)
+        priorities = torch.empty(B, dtype=torch.float32, device=self.device)
+        loss_scalar = torch.empty(1, dtype=torch.float32, device=self.device)
+        proj = torch.empty((B, self.layout.desc.n_atoms), dtype=torch.float32, device=self.device) if want_proj else None
+        self.step += 1
+        keepalive = []
+        cfg = None
+        for i, (batch, gamma, driver) in enumerate(passes):
+            cfg = self._cfg(B, gamma=gamma, v_min=hp["v_min"], v_max=hp["v_max"], delta_z=hp["delta_z"],
+                            weights_mode=weights_mode, driver_shapes=int(driver), clip=1, lr=hp["lr"], tau=hp["tau"],
+                            prior_eps=hp["prior_eps"], accumulate=int(i > 0), use_noise=1, step=self.step)
+            bufs, keep = self._bufs(B, batch, weights, support, loss_elem, priorities, loss_scalar, proj, row_idx)
+            keepalive.append(keep)
+            _lib.check(self.lib.b2rl_rainbow_loss(desc, ctypes.byref(cfg), ctypes.byref(bufs), stream))
+            _lib.check(self.lib.b2rl_rainbow_backward(desc, ctypes.byref(cfg), ctypes.byref(bufs), stream))
+        _lib.check(self.lib.b2rl_optim_step(desc, ctypes.byref(cfg), ctypes.byref(bufs), stream))
+        # dqn_rainbow.py:484-485 — actor.reset_noise() then actor_target.reset_noise()
+        za, zt = noise_normals if noise_normals is not None else (None, None)
+        self.reset_noise(self.actor, za)
+        self.reset_noise(self.target, zt)
+        self._keepalive = keepalive
+        return loss_scalar, loss_elem, priorities, proj
+
+    def dqn_learn(self, batch: dict, *, B: int, hp: dict, double: bool):
+        desc = ctypes.byref(self.layout.desc)
+        loss_elem = torch.empty(B, dtype=torch.float32, device=self.device)
+        loss_scalar = torch.empty(1, dtype=torch.float32, device=self.device)
+        self.step += 1
+        cfg = self._cfg(B, gamma=hp["gamma"], double=int(double), clip=0, lr=hp["lr"], tau=hp["tau"], use_noise=0,
+                        step=self.step)
+        bufs, keep = self._bufs(B, batch, None, None, loss_elem, None, loss_scalar, None)
+        _lib.check(self.lib.b2rl_dqn_learn(desc, ctypes.byref(cfg), ctypes.byref(bufs), _lib.stream_ptr(self.device)))
+        self._keepalive = keep
+        return loss_scalar

@@ -69,4 +69,29 @@ __device__ __forceinline__ float act_bwd(int act, float x, float y) {
     }
 }
 
+// Philox4x32-10: one 128-bit block per (counter, key).
+__device__ __forceinline__ void philox4x32_10(uint64_t seed, uint64_t c_lo, uint64_t c_hi, uint32_t out[4]) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    uint32_t c0 = (uint32_t)c_lo, c1 = (uint32_t)(c_lo >> 32), c2 = (uint32_t)c_hi, c3 = (uint32_t)(c_hi >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+
+// standard normal from one Philox block (Box-Muller on two 24-bit uniforms)
+__device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t ctr, uint64_t stream) {
+    uint32_t r[4];
+    philox4x32_10(seed, ctr, stream, r);
+    const float u1 = ((float)(r[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float u2 = (float)(r[1] >> 8) * (1.0f / 16777216.0f);
+    return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
 }  // namespace b2rl

@@ -1,0 +1,1235 @@
+// nn.cu — RainbowQNetwork / QNetwork forward + backward and the learn() tail on sm_100a.
+//
+// Replaces, for the off-policy path:
+//   EvolvableCNN / EvolvableMLP forward            agilerl/modules/cnn.py:552-580, mlp.py:188-203
+//   NoisyLinear forward / reset_noise              agilerl/modules/custom_components.py:89-131
+//   DuelingDistributionalMLP.forward               agilerl/networks/custom_modules.py:127-162
+//   RainbowDQN._dqn_loss / learn / soft_update     agilerl/algorithms/dqn_rainbow.py:284-501
+//   DQN.update / learn                             agilerl/algorithms/dqn.py:274-358
+//   torch.autograd backward, clip_grad_norm_, torch.optim.Adam (all ATen in the reference)
+//
+// Layout in HBM: one flat fp32 parameter buffer per network (encoder | head mu | head sigma),
+// one flat epsilon buffer, NCHW activations, [rows, features] for linear layers.  Dense
+// contractions go through the separable-index GEMM engine (gemm.cuh); everything row-wise
+// (LayerNorm, dueling/softmax/projection/loss, optimiser) is a warp- or CTA-per-row kernel with
+// shuffle reductions.
+#include <math.h>
+#include <string.h>
+
+#include "gemm.cuh"
+
+namespace b2rl {
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+static inline int64_t layer_out_elems(const b2rl_layer &l) {
+    return l.kind == B2RL_LAYER_CONV ? (int64_t)l.out_c * l.out_h * l.out_w : (int64_t)l.out_c;
+}
+static inline int64_t layer_in_elems(const b2rl_layer &l) {
+    return l.kind == B2RL_LAYER_CONV ? (int64_t)l.in_c * l.in_h * l.in_w : (int64_t)l.in_c;
+}
+static inline int64_t layer_w_elems(const b2rl_layer &l) {
+    return l.kind == B2RL_LAYER_CONV ? (int64_t)l.out_c * l.in_c * l.ksize * l.ksize : (int64_t)l.out_c * l.in_c;
+}
+static inline bool needs_pre(const b2rl_layer &l) { return l.act == B2RL_ACT_GELU; }
+
+struct LayerBuf {
+    float *z = nullptr;      // pre-LayerNorm linear output (ln layers)
+    float *pre = nullptr;    // pre-activation (only kept for GELU)
+    float *a = nullptr;      // layer output
+    float *stats = nullptr;  // mean, rstd per row (ln layers)
+    float *g = nullptr;      // gradient w.r.t. the layer output (backward rows only)
+};
+struct PassBufs {
+    LayerBuf enc[B2RL_MAX_ENC], val[B2RL_MAX_HEAD], adv[B2RL_MAX_HEAD];
+    int64_t rows = 0;
+};
+
+struct Bump {
+    char *base;
+    size_t off = 0;
+    explicit Bump(void *b) : base(static_cast<char *>(b)) {}
+    template <typename T> T *take(size_t n) {
+        off = (off + 255) & ~size_t(255);
+        T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
+static void carve_layers(Bump &b, const b2rl_layer *layers, int n, LayerBuf *out, int64_t rows, int64_t grad_rows) {
+    for (int i = 0; i < n; ++i) {
+        const b2rl_layer &l = layers[i];
+        const int64_t oe = layer_out_elems(l);
+        out[i].a = b.take<float>(rows * oe);
+        if (l.ln != B2RL_LN_NONE) {
+            out[i].z = b.take<float>(rows * oe);
+            out[i].stats = b.take<float>(rows * 2);
+        }
+        if (needs_pre(l)) out[i].pre = b.take<float>(rows * oe);
+        if (grad_rows > 0) out[i].g = b.take<float>(grad_rows * oe);
+    }
+}
+static void carve_pass(Bump &b, const b2rl_net_desc &net, PassBufs &pb, int64_t rows, int64_t grad_rows) {
+    pb.rows = rows;
+    carve_layers(b, net.enc, net.n_enc, pb.enc, rows, grad_rows);
+    carve_layers(b, net.val, net.n_val, pb.val, rows, grad_rows);
+    carve_layers(b, net.adv, net.n_adv, pb.adv, rows, grad_rows);
+}
+
+static size_t gemm_need(int64_t M, int64_t N, int64_t K) {
+    if (M <= 0 || N <= 0 || K <= 0 || M > INT32_MAX) return 0;
+    return plan_gemm((int)M, (int)N, (int)K, M >= 4096, sm_count()).partial_floats;
+}
+// exact bound of the split-K scratch over every GEMM a pass can launch
+static size_t max_partial_floats(const b2rl_net_desc &net, int64_t rows, int64_t brows) {
+    size_t m = 0;
+    auto upd = [&](const b2rl_layer &l) {
+        size_t n;
+        if (l.kind == B2RL_LAYER_CONV) {
+            const int64_t P = (int64_t)l.out_h * l.out_w, Kc = (int64_t)l.in_c * l.ksize * l.ksize;
+            n = gemm_need(rows * P, l.out_c, Kc); if (n > m) m = n;
+            n = gemm_need(rows / 2 * P, l.out_c, Kc); if (n > m) m = n;     // first layer runs per chunk
+            if (brows) { n = gemm_need(l.out_c, Kc + 1, brows * P); if (n > m) m = n; }
+        } else {
+            n = gemm_need(rows, l.out_c, l.in_c); if (n > m) m = n;
+            n = gemm_need(rows / 2, l.out_c, l.in_c); if (n > m) m = n;
+            if (brows) {
+                n = gemm_need(l.out_c, l.in_c + 1, brows); if (n > m) m = n;
+                n = gemm_need(brows, l.in_c, l.out_c); if (n > m) m = n;
+            }
+        }
+    };
+    for (int i = 0; i < net.n_enc; ++i) upd(net.enc[i]);
+    for (int i = 0; i < net.n_val; ++i) upd(net.val[i]);
+    for (int i = 0; i < net.n_adv; ++i) upd(net.adv[i]);
+    return m;
+}
+
+constexpr int kNormBlocks = 296;
+
+struct LearnWS {
+    float *weff_actor, *weff_target, *gweff;
+    PassBufs online, target;
+    int32_t *a_star;
+    float *q_online, *q_target;     // [rows, A] expected values (DQN / debugging)
+    float *tdist;                   // [B, N] target distribution of a*
+    float *proj;                    // [B, N]
+    float *cmat;                    // [N, N] (driver-shape mode)
+    float *partial;
+    size_t partial_floats;
+    float *norm_partials;           // kNormBlocks
+    float *wsum;                    // 1
+    size_t bytes;
+};
+
+static void carve_learn(const b2rl_net_desc &net, int64_t B, bool two_sided_online, void *base, LearnWS &ws) {
+    Bump b(base);
+    ws.weff_actor = b.take<float>(net.n_params);
+    ws.weff_target = b.take<float>(net.n_params);
+    ws.gweff = b.take<float>(net.n_params);
+    const int64_t online_rows = two_sided_online ? 2 * B : B;
+    carve_pass(b, net, ws.online, online_rows, B);
+    carve_pass(b, net, ws.target, B, 0);
+    ws.a_star = b.take<int32_t>(B);
+    ws.q_online = b.take<float>(online_rows * net.n_actions);
+    ws.q_target = b.take<float>(B * net.n_actions);
+    ws.tdist = b.take<float>(B * net.n_atoms);
+    ws.proj = b.take<float>(B * net.n_atoms);
+    ws.cmat = b.take<float>((int64_t)net.n_atoms * net.n_atoms);
+    ws.partial_floats = max_partial_floats(net, online_rows, B);
+    ws.partial = b.take<float>(ws.partial_floats);
+    ws.norm_partials = b.take<float>(kNormBlocks);
+    ws.wsum = b.take<float>(4);
+    ws.bytes = b.off + 256;
+}
+
+struct FwdWS {
+    float *weff;
+    PassBufs pass;
+    float *partial;
+    size_t partial_floats;
+    size_t bytes;
+};
+static void carve_fwd(const b2rl_net_desc &net, int64_t rows, void *base, FwdWS &ws) {
+    Bump b(base);
+    ws.weff = b.take<float>(net.n_params);
+    carve_pass(b, net, ws.pass, rows, 0);
+    ws.partial_floats = max_partial_floats(net, rows, 0);
+    ws.partial = b.take<float>(ws.partial_floats);
+    ws.bytes = b.off + 256;
+}
+
+static int validate_net(const b2rl_net_desc &net) {
+    B2RL_CHECK_ARG(net.n_enc >= 1 && net.n_enc <= B2RL_MAX_ENC, "n_enc out of range");
+    B2RL_CHECK_ARG(net.n_val >= 1 && net.n_val <= B2RL_MAX_HEAD, "n_val out of range");
+    B2RL_CHECK_ARG(net.n_adv >= 0 && net.n_adv <= B2RL_MAX_HEAD, "n_adv out of range");
+    B2RL_CHECK_ARG((net.kind == B2RL_NET_RAINBOW) == (net.n_adv > 0), "rainbow nets need an advantage head");
+    B2RL_CHECK_ARG(net.n_actions >= 1 && net.n_atoms >= 1, "bad action/atom count");
+    return B2RL_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// NoisyLinear: W_eff = mu + sigma * eps   (custom_components.py:97-99; mul then add, no FMA)
+// ------------------------------------------------------------------------------------------
+struct Seg { float *dst; const float *mu; const float *sigma; const float *eps; int64_t n; };
+struct SegTable { Seg s[2 * (B2RL_MAX_ENC + 2 * B2RL_MAX_HEAD)]; int n; };
+
+__global__ void compose_kernel(SegTable t) {
+    const Seg sg = t.s[blockIdx.y];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < sg.n; i += (int64_t)gridDim.x * blockDim.x)
+        sg.dst[i] = __fadd_rn(sg.mu[i], __fmul_rn(sg.sigma[i], sg.eps[i]));
+}
+// grad_sigma = grad_Weff * eps  (autograd of mu + sigma*eps); grad_mu is grad_Weff itself.
+__global__ void noisy_grad_kernel(SegTable t, int accumulate) {
+    const Seg sg = t.s[blockIdx.y];   // dst = grad_sigma, mu = grad_Weff, eps = eps
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < sg.n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = sg.eps ? sg.mu[i] * sg.eps[i] : sg.mu[i];
+        sg.dst[i] = accumulate ? sg.dst[i] + v : v;
+    }
+}
+
+template <typename F>
+static void for_each_layer(const b2rl_net_desc &net, F &&f) {
+    for (int i = 0; i < net.n_enc; ++i) f(net.enc[i]);
+    for (int i = 0; i < net.n_val; ++i) f(net.val[i]);
+    for (int i = 0; i < net.n_adv; ++i) f(net.adv[i]);
+}
+
+static int compose_weights(const b2rl_net_desc &net, const float *params, const float *eps, float *weff,
+                           cudaStream_t s) {
+    SegTable t;
+    t.n = 0;
+    int64_t maxn = 0;
+    for_each_layer(net, [&](const b2rl_layer &l) {
+        if (!l.noisy) return;
+        const int64_t nw = layer_w_elems(l);
+        t.s[t.n++] = Seg{weff + l.w_off, params + l.w_off, params + l.ws_off, eps + l.we_off, nw};
+        t.s[t.n++] = Seg{weff + l.b_off, params + l.b_off, params + l.bs_off, eps + l.be_off, (int64_t)l.out_c};
+        if (nw > maxn) maxn = nw;
+    });
+    if (t.n == 0) return B2RL_OK;
+    int bx = (int)((maxn + 255) / 256);
+    if (bx > 64) bx = 64;
+    compose_kernel<<<dim3(bx, t.n), 256, 0, s>>>(t);
+    B2RL_LAUNCH_CHECK();
+    return B2RL_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm (+activation) forward / backward — one warp per row.
+// ------------------------------------------------------------------------------------------
+__global__ void ln_fwd_kernel(const float *__restrict__ z, const float *__restrict__ w, const float *__restrict__ b,
+                              int act, float *__restrict__ a, float *__restrict__ pre, float *__restrict__ stats,
+                              int64_t rows, int n) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float *zr = z + row * n;
+    float s = 0.f;
+    for (int c = lane; c < n; c += 32) s += zr[c];
+    const float mean = warp_sum(s) / (float)n;
+    float v = 0.f;
+    for (int c = lane; c < n; c += 32) { const float d = zr[c] - mean; v += d * d; }
+    const float var = warp_sum(v) / (float)n;          // biased variance, eps = 1e-5 (nn.LayerNorm)
+    const float rstd = 1.0f / sqrtf(var + 1e-5f);
+    if (lane == 0) { stats[row * 2] = mean; stats[row * 2 + 1] = rstd; }
+    for (int c = lane; c < n; c += 32) {
+        float y = (zr[c] - mean) * rstd;
+        if (w) y = y * w[c] + b[c];
+        if (pre) pre[row * n + c] = y;
+        a[row * n + c] = act_fwd(act, y);
+    }
+}
+
+// column sums for the LayerNorm affine gradients: dw[c] = sum_r gy*xhat, db[c] = sum_r gy
+__global__ void ln_affine_grad_kernel(const float *__restrict__ g, const float *__restrict__ z,
+                                      const float *__restrict__ stats, const float *__restrict__ a,
+                                      const float *__restrict__ pre, int act, float *__restrict__ dw,
+                                      float *__restrict__ db, int64_t rows, int n, int accumulate) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    float sw = 0.f, sb = 0.f;
+    for (int64_t r = 0; r < rows; ++r) {
+        const int64_t o = r * n + c;
+        const float gy = g[o] * act_bwd(act, pre ? pre[o] : 0.f, a[o]);
+        const float xhat = (z[o] - stats[r * 2]) * stats[r * 2 + 1];
+        sw += gy * xhat;
+        sb += gy;
+    }
+    dw[c] = accumulate ? dw[c] + sw : sw;
+    db[c] = accumulate ? db[c] + sb : sb;
+}
+
+// g (dL/da) -> dL/dz in place.
+__global__ void ln_bwd_kernel(float *__restrict__ g, const float *__restrict__ z, const float *__restrict__ stats,
+                              const float *__restrict__ w, const float *__restrict__ a,
+                              const float *__restrict__ pre, int act, int64_t rows, int n) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < n; c += 32) {
+        const int64_t o = row * n + c;
+        const float gy = g[o] * act_bwd(act, pre ? pre[o] : 0.f, a[o]);
+        const float gx = w ? gy * w[c] : gy;
+        const float xhat = (z[o] - mean) * rstd;
+        s1 += gx;
+        s2 += gx * xhat;
+    }
+    s1 = warp_sum(s1) / (float)n;
+    s2 = warp_sum(s2) / (float)n;
+    for (int c = lane; c < n; c += 32) {
+        const int64_t o = row * n + c;
+        const float gy = g[o] * act_bwd(act, pre ? pre[o] : 0.f, a[o]);
+        const float gx = w ? gy * w[c] : gy;
+        const float xhat = (z[o] - mean) * rstd;
+        g[o] = rstd * (gx - s1 - xhat * s2);
+    }
+}
+
+__global__ void act_bwd_kernel(float *__restrict__ g, const float *__restrict__ a, const float *__restrict__ pre,
+                               int act, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        g[i] *= act_bwd(act, pre ? pre[i] : 0.f, a[i]);
+}
+
+// ------------------------------------------------------------------------------------------
+// one layer forward
+// ------------------------------------------------------------------------------------------
+struct ObsChunk {          // first-layer input rows [row0, row0+rows) come from this source
+    const void *ptr;
+    const int64_t *gather; // nullable: ring row of each batch row
+    int64_t rows;
+};
+
+struct Scratch { float *partial; size_t floats; };
+
+static int layer_forward(const b2rl_net_desc &net, const b2rl_layer &l, const float *W, const float *bias,
+                         const float *params, const float *x_prev, const ObsChunk *chunks, int n_chunks,
+                         int64_t rows, const LayerBuf &lb, const Scratch &sc, cudaStream_t s) {
+    const int64_t oe = layer_out_elems(l);
+    const bool first = x_prev == nullptr;
+    const int n_runs = first ? n_chunks : 1;
+    int64_t row0 = 0;
+    for (int run = 0; run < n_runs; ++run) {
+        const int64_t r = first ? chunks[run].rows : rows;
+        Operand A, Bm;
+        Epilogue epi;
+        if (first) {
+            A.ptr = chunks[run].ptr;
+            A.u8 = net.obs_u8;
+            A.normalize = net.normalize;
+            A.low = net.obs_low;
+            A.high = net.obs_high;
+        } else {
+            A.ptr = x_prev;
+        }
+        const int64_t *gather = first ? chunks[run].gather : nullptr;
+        int M, N, K;
+        float *out_ptr = (l.ln != B2RL_LN_NONE ? lb.z : lb.a) + row0 * oe;
+        if (l.kind == B2RL_LAYER_CONV) {
+            const int P = l.out_h * l.out_w, KK = l.ksize * l.ksize;
+            M = (int)(r * P); N = l.out_c; K = l.in_c * KK;
+            A.row = map_pixel(P, l.out_w, (int64_t)l.in_c * l.in_h * l.in_w, l.stride * l.in_w, l.stride, gather);
+            A.red = map_kernel(l.ksize, l.in_h * l.in_w, l.in_w);
+            Bm.ptr = W; Bm.row = map_stride(K); Bm.red = map_stride(1);
+            epi.om = map_pixel(P, l.out_w, (int64_t)l.out_c * P, l.out_w, 1);
+            epi.on = map_stride(P);
+        } else {
+            M = (int)r; N = l.out_c; K = l.in_c;
+            A.row = map_stride(K, gather); A.red = map_stride(1);
+            Bm.ptr = W; Bm.row = map_stride(K); Bm.red = map_stride(1);
+            epi.om = map_stride(N); epi.on = map_stride(1);
+        }
+        epi.out = out_ptr;
+        epi.bias = bias;
+        if (l.ln == B2RL_LN_NONE) {
+            epi.act = l.act;
+            epi.pre_out = lb.pre ? lb.pre + row0 * oe : nullptr;
+        }
+        int rc = launch_igemm<true, true>(A, Bm, epi, M, N, K, sc.partial, sc.floats, s);
+        if (rc != B2RL_OK) return rc;
+        row0 += r;
+    }
+    if (l.ln != B2RL_LN_NONE) {
+        B2RL_CHECK_ARG(l.kind == B2RL_LAYER_LINEAR, "LayerNorm is only supported after linear layers");
+        const float *lw = l.ln == B2RL_LN_AFFINE ? params + l.lnw_off : nullptr;
+        const float *lbias = l.ln == B2RL_LN_AFFINE ? params + l.lnb_off : nullptr;
+        const int warps = 4;
+        ln_fwd_kernel<<<(int)((rows + warps - 1) / warps), warps * 32, 0, s>>>(lb.z, lw, lbias, l.act, lb.a, lb.pre,
+                                                                               lb.stats, rows, l.out_c);
+        B2RL_LAUNCH_CHECK();
+    }
+    return B2RL_OK;
+}
+
+static inline const float *eff_w(const b2rl_layer &l, const float *params, const float *weff, bool use_noise) {
+    return (l.noisy && use_noise) ? weff + l.w_off : params + l.w_off;
+}
+static inline const float *eff_b(const b2rl_layer &l, const float *params, const float *weff, bool use_noise) {
+    return (l.noisy && use_noise) ? weff + l.b_off : params + l.b_off;
+}
+
+static int forward_pass(const b2rl_net_desc &net, const float *params, const float *weff, bool use_noise,
+                        const ObsChunk *chunks, int n_chunks, int64_t rows, PassBufs &pb, const Scratch &sc,
+                        cudaStream_t s) {
+    const float *x = nullptr;
+    for (int i = 0; i < net.n_enc; ++i) {
+        const b2rl_layer &l = net.enc[i];
+        int rc = layer_forward(net, l, eff_w(l, params, weff, use_noise), eff_b(l, params, weff, use_noise), params, x,
+                               chunks, n_chunks, rows, pb.enc[i], sc, s);
+        if (rc != B2RL_OK) return rc;
+        x = pb.enc[i].a;
+    }
+    const float *latent = x;
+    const float *xv = latent;
+    for (int i = 0; i < net.n_val; ++i) {
+        const b2rl_layer &l = net.val[i];
+        int rc = layer_forward(net, l, eff_w(l, params, weff, use_noise), eff_b(l, params, weff, use_noise), params, xv,
+                               nullptr, 0, rows, pb.val[i], sc, s);
+        if (rc != B2RL_OK) return rc;
+        xv = pb.val[i].a;
+    }
+    const float *xa = latent;
+    for (int i = 0; i < net.n_adv; ++i) {
+        const b2rl_layer &l = net.adv[i];
+        int rc = layer_forward(net, l, eff_w(l, params, weff, use_noise), eff_b(l, params, weff, use_noise), params, xa,
+                               nullptr, 0, rows, pb.adv[i], sc, s);
+        if (rc != B2RL_OK) return rc;
+        xa = pb.adv[i].a;
+    }
+    return B2RL_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Rainbow head: dueling combine, softmax, clamp, expectation / argmax / projection / loss.
+// One CTA per batch row; dynamic smem holds x[A*N].
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_reduce_sum(float v, float *red) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    return t;
+}
+
+// x[a][n] = v[n] + adv[a][n] - mean_a adv[.][n]    (custom_modules.py:149-153)
+__device__ __forceinline__ void dueling_to_smem(const float *__restrict__ v, const float *__restrict__ adv, int A,
+                                                int N, float *x) {
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        float m = 0.f;
+        for (int a = 0; a < A; ++a) m += adv[a * N + n];
+        m = m / (float)A;
+        const float vn = v[n];
+        for (int a = 0; a < A; ++a) x[a * N + n] = vn + adv[a * N + n] - m;
+    }
+    __syncthreads();
+}
+
+// softmax over atoms of action row `a` (in place in smem), clamp(min=1e-3); one warp per action.
+__device__ __forceinline__ float softmax_clamp_row(float *xr, int N, const float *__restrict__ support) {
+    const int lane = threadIdx.x & 31;
+    float m = -INFINITY;
+    for (int n = lane; n < N; n += 32) m = fmaxf(m, xr[n]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int n = lane; n < N; n += 32) { const float e = expf(xr[n] - m); xr[n] = e; s += e; }
+    s = warp_sum(s);
+    float q = 0.f;
+    for (int n = lane; n < N; n += 32) {
+        float p = xr[n] / s;
+        p = fmaxf(p, 1e-3f);                       // clamp(min=1e-3), no renormalisation (quirk Q8)
+        xr[n] = p;
+        if (support) q += p * support[n];
+    }
+    return warp_sum(q);
+}
+
+// mode 0: write q[row][a]; argmax -> a_star (int32) and/or argmax64
+__global__ void rainbow_q_kernel(const float *__restrict__ v, const float *__restrict__ adv,
+                                 const float *__restrict__ support, int A, int N, float *__restrict__ q_out,
+                                 int32_t *__restrict__ a_star, int64_t *__restrict__ argmax64) {
+    extern __shared__ float sm[];
+    float *x = sm;            // A*N
+    float *q = sm + A * N;    // A
+    const int64_t row = blockIdx.x;
+    dueling_to_smem(v + row * N, adv + row * (int64_t)A * N, A, N, x);
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
+    for (int a = warp; a < A; a += nwarps) {
+        const float qa = softmax_clamp_row(x + a * N, N, support);
+        if (lane == 0) q[a] = qa;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int best = 0;
+        float bv = q[0];
+        for (int a = 1; a < A; ++a)
+            if (q[a] > bv) { bv = q[a]; best = a; }    // first maximum, like torch.argmax
+        if (a_star) a_star[row] = best;
+        if (argmax64) argmax64[row] = best;
+    }
+    if (q_out)
+        for (int a = threadIdx.x; a < A; a += blockDim.x) q_out[row * A + a] = q[a];
+}
+
+struct ProjCfg { float gamma, v_min, v_max, delta_z; };
+
+// Target distribution of a* and (canonical shapes) the C51 projection, sequential per row in the
+// reference's index_add_ order so the fp32 sums are bit-faithful (dqn_rainbow.py:318-360).
+__global__ void rainbow_target_kernel(const float *__restrict__ v, const float *__restrict__ adv,
+                                      const int32_t *__restrict__ a_star, const float *__restrict__ reward,
+                                      const float *__restrict__ done, const float *__restrict__ support, ProjCfg pc,
+                                      int A, int N, float *__restrict__ tdist, float *__restrict__ proj) {
+    extern __shared__ float sm[];
+    float *x = sm;                 // A*N
+    float *pr = sm + A * N;        // N   projected
+    float *wl = pr + N;            // N
+    float *wu = wl + N;            // N
+    int *Li = reinterpret_cast<int *>(wu + N);   // N
+    int *Ui = Li + N;                            // N
+    const int64_t row = blockIdx.x;
+    dueling_to_smem(v + row * N, adv + row * (int64_t)A * N, A, N, x);
+    const int as = a_star[row];
+    float *p = x + as * N;
+    if ((threadIdx.x >> 5) == 0) softmax_clamp_row(p, N, nullptr);
+    __syncthreads();
+    if (tdist)
+        for (int n = threadIdx.x; n < N; n += blockDim.x) tdist[row * N + n] = p[n];
+    if (!proj) return;
+    const float r = reward[row], d = done[row];
+    const float g = __fmul_rn(__fsub_rn(1.0f, d), pc.gamma);              // (1 - dones) * gamma
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        float tz = __fadd_rn(r, __fmul_rn(g, support[n]));                  // rewards + (..) * support
+        tz = fminf(fmaxf(tz, pc.v_min), pc.v_max);                          // clamp
+        const float b = __fdiv_rn(__fsub_rn(tz, pc.v_min), pc.delta_z);
+        int L = (int)floorf(b), U = (int)ceilf(b);
+        if (U > 0 && U == L) L -= 1;                                        // quirk Q9 order
+        if ((N - 1) > L && U == L) U += 1;
+        Li[n] = L; Ui[n] = U;
+        wl[n] = __fsub_rn((float)U, b);
+        wu[n] = __fsub_rn(b, (float)L);
+        pr[n] = 0.f;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int n = 0; n < N; ++n) pr[Li[n]] = __fadd_rn(pr[Li[n]], __fmul_rn(p[n], wl[n]));
+        for (int n = 0; n < N; ++n) pr[Ui[n]] = __fadd_rn(pr[Ui[n]], __fmul_rn(p[n], wu[n]));
+    }
+    __syncthreads();
+    for (int n = threadIdx.x; n < N; n += blockDim.x) proj[row * N + n] = pr[n];
+}
+
+// Driver-shape (quirk Q2) projection: reward/done arrive [B,1,1], the reference's broadcasting
+// makes every row's projected target the SUM over all B Bellman shifts applied to that row's
+// target distribution:  proj[j][m] = sum_n tdist[j][n] * C[n][m],
+// C[n][m] = sum_i ( wl[i][n] [L[i][n]==m] + wu[i][n] [U[i][n]==m] ).
+__global__ void q2_cmat_kernel(const float *__restrict__ reward, const float *__restrict__ done,
+                               const float *__restrict__ support, ProjCfg pc, int64_t B, int N,
+                               float *__restrict__ cmat) {
+    // one CTA per source atom n; accumulate over samples in order
+    const int n = blockIdx.x;
+    extern __shared__ float row[];   // N
+    for (int m = threadIdx.x; m < N; m += blockDim.x) row[m] = 0.f;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int64_t i = 0; i < B; ++i) {
+            const float g = __fmul_rn(__fsub_rn(1.0f, done[i]), pc.gamma);
+            float tz = __fadd_rn(reward[i], __fmul_rn(g, support[n]));
+            tz = fminf(fmaxf(tz, pc.v_min), pc.v_max);
+            const float b = __fdiv_rn(__fsub_rn(tz, pc.v_min), pc.delta_z);
+            int L = (int)floorf(b), U = (int)ceilf(b);
+            if (U > 0 && U == L) L -= 1;
+            if ((N - 1) > L && U == L) U += 1;
+            row[L] += __fsub_rn((float)U, b);
+            row[U] += __fsub_rn(b, (float)L);
+        }
+    }
+    __syncthreads();
+    for (int m = threadIdx.x; m < N; m += blockDim.x) cmat[n * N + m] = row[m];
+}
+__global__ void q2_project_kernel(const float *__restrict__ tdist, const float *__restrict__ cmat, int N,
+                                  float *__restrict__ proj) {
+    const int64_t j = blockIdx.x;
+    for (int m = threadIdx.x; m < N; m += blockDim.x) {
+        float s = 0.f;
+        for (int n = 0; n < N; ++n) s += tdist[j * N + n] * cmat[n * N + m];
+        proj[j * N + m] = s;
+    }
+}
+
+// Cross-entropy of the taken action's log-softmax against the projected target, plus dL/dlogits.
+// loss_i = -sum_n proj[i][n] * log_softmax(x[a_i])[n]                      (dqn_rainbow.py:362-367)
+// d loss_i / d x[a_i][n] = softmax[n] * sum_m proj[i][m] - proj[i][n]
+// dueling backward: dv[n] = dx[n];  dadv[a][n] = [a==a_i] dx[n] - dx[n]/A
+__global__ void rainbow_loss_kernel(const float *__restrict__ v, const float *__restrict__ adv,
+                                    const float *__restrict__ action, const float *__restrict__ proj,
+                                    const float *__restrict__ weights, int weights_mode, int64_t B, int A, int N,
+                                    int accumulate, float *__restrict__ loss_elem, float *__restrict__ dv,
+                                    float *__restrict__ dadv) {
+    extern __shared__ float sm[];
+    float *x = sm;              // N (action row only)
+    float *red = sm + N;        // 32
+    const int64_t row = blockIdx.x;
+    const float *vr = v + row * N;
+    const float *ar = adv + row * (int64_t)A * N;
+    const int ai = (int)(long long)action[row];            // actions.squeeze().long()
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        float m = 0.f;
+        for (int a = 0; a < A; ++a) m += ar[a * N + n];
+        m = m / (float)A;
+        x[n] = vr[n] + ar[ai * N + n] - m;
+    }
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) mx = fmaxf(mx, x[n]);
+    // block max via shuffles + smem
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+    float s = 0.f;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) s += expf(x[n] - mx);
+    s = block_reduce_sum(s, red);
+    const float lse = logf(s);
+    float l = 0.f, ps = 0.f;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        const float lp = x[n] - mx - lse;
+        const float pj = proj[row * N + n];
+        l -= pj * lp;
+        ps += pj;
+    }
+    l = block_reduce_sum(l, red);
+    ps = block_reduce_sum(ps, red);
+    // per-row gradient scale of the scalar loss
+    float gs;
+    if (weights_mode == 1) gs = weights[row] / (float)B;                    // mean(l * w)
+    else if (weights_mode == 2) {                                            // mean(l) * mean(w)  (Q1)
+        float ws = 0.f;
+        for (int64_t i = threadIdx.x; i < B; i += blockDim.x) ws += weights[i];
+        ws = block_reduce_sum(ws, red);
+        gs = (ws / (float)B) / (float)B;
+    } else gs = 1.0f / (float)B;
+    if (threadIdx.x == 0) loss_elem[row] = accumulate ? loss_elem[row] + l : l;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        const float sm_n = expf(x[n] - mx) / s;
+        const float dx = gs * (sm_n * ps - proj[row * N + n]);
+        dv[row * N + n] = dx;
+        const float sh = dx / (float)A;
+        for (int a = 0; a < A; ++a) dadv[row * (int64_t)A * N + a * N + n] = (a == ai ? dx : 0.f) - sh;
+    }
+}
+
+// scalar loss + priorities (single CTA): dqn_rainbow.py:434 / :487-488
+__global__ void rainbow_scalar_kernel(const float *__restrict__ loss_elem, const float *__restrict__ weights,
+                                      int weights_mode, int64_t B, float prior_eps, float *__restrict__ loss_scalar,
+                                      float *__restrict__ priorities) {
+    __shared__ float red[32];
+    float a = 0.f, w = 0.f;
+    for (int64_t i = threadIdx.x; i < B; i += blockDim.x) {
+        const float l = loss_elem[i];
+        if (weights_mode == 1) a += l * weights[i];
+        else a += l;
+        if (weights_mode == 2) w += weights[i];
+        if (priorities) priorities[i] = l + prior_eps;
+    }
+    a = block_reduce_sum(a, red);
+    w = block_reduce_sum(w, red);
+    if (threadIdx.x == 0) {
+        float L = a / (float)B;
+        if (weights_mode == 2) L *= w / (float)B;
+        *loss_scalar = L;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// DQN loss (dqn.py:290-314): y = r + gamma*q_t*(1-d); loss = mean((q[a]-y)^2); single CTA.
+// ------------------------------------------------------------------------------------------
+__global__ void dqn_loss_kernel(const float *__restrict__ q_eval, const float *__restrict__ q_next_online,
+                                const float *__restrict__ q_next_target, const float *__restrict__ action,
+                                const float *__restrict__ reward, const float *__restrict__ done, float gamma,
+                                int double_dqn, int64_t B, int A, float *__restrict__ dq,
+                                float *__restrict__ loss_elem, float *__restrict__ loss_scalar) {
+    __shared__ float red[32];
+    float acc = 0.f;
+    for (int64_t i = threadIdx.x; i < B; i += blockDim.x) {
+        const float *qt = q_next_target + i * A;
+        float qsel;
+        if (double_dqn) {
+            const float *qo = q_next_online + i * A;
+            int best = 0;
+            for (int a = 1; a < A; ++a) if (qo[a] > qo[best]) best = a;
+            qsel = qt[best];
+        } else {
+            qsel = qt[0];
+            for (int a = 1; a < A; ++a) qsel = fmaxf(qsel, qt[a]);
+        }
+        const float y = __fadd_rn(reward[i], __fmul_rn(__fmul_rn(gamma, qsel), __fsub_rn(1.0f, done[i])));
+        const int ai = (int)(long long)action[i];
+        const float diff = q_eval[i * A + ai] - y;
+        acc += diff * diff;
+        if (loss_elem) loss_elem[i] = diff * diff;
+        for (int a = 0; a < A; ++a) dq[i * A + a] = (a == ai) ? 2.0f * diff / (float)B : 0.f;
+    }
+    acc = block_reduce_sum(acc, red);
+    if (threadIdx.x == 0) *loss_scalar = acc / (float)B;
+}
+
+// copy / argmax of plain Q outputs
+__global__ void q_argmax_kernel(const float *__restrict__ q, int A, int64_t rows, float *__restrict__ q_out,
+                                int64_t *__restrict__ argmax64) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    int best = 0;
+    for (int a = 0; a < A; ++a) {
+        if (q_out) q_out[i * A + a] = q[i * A + a];
+        if (q[i * A + a] > q[i * A + best]) best = a;
+    }
+    if (argmax64) argmax64[i] = best;
+}
+
+// ------------------------------------------------------------------------------------------
+// backward of one layer
+// ------------------------------------------------------------------------------------------
+static int layer_backward(const b2rl_net_desc &net, const b2rl_layer &l, const float *W, const float *params,
+                          const float *x_in,            // input activations of this layer (backward rows)
+                          const ObsChunk *obs,          // first layer: where the observations come from
+                          const LayerBuf &lb, int64_t row_off,  // forward buffers + offset of the backward rows
+                          float *g_out,                 // dL/d(layer output) for the B backward rows
+                          float *g_in, bool accumulate_gin, float *grads, float *gweff, int accumulate_grads,
+                          int64_t B, const Scratch &sc, cudaStream_t s) {
+    const int64_t oe = layer_out_elems(l);
+    const float *a = lb.a + row_off * oe;
+    const float *pre = lb.pre ? lb.pre + row_off * oe : nullptr;
+    // (1) through activation (+LayerNorm)
+    if (l.ln != B2RL_LN_NONE) {
+        const float *z = lb.z + row_off * oe;
+        const float *st = lb.stats + row_off * 2;
+        if (l.ln == B2RL_LN_AFFINE) {
+            ln_affine_grad_kernel<<<(l.out_c + 127) / 128, 128, 0, s>>>(g_out, z, st, a, pre, l.act, grads + l.lnw_off,
+                                                                        grads + l.lnb_off, B, l.out_c, accumulate_grads);
+            B2RL_LAUNCH_CHECK();
+        }
+        const float *lw = l.ln == B2RL_LN_AFFINE ? params + l.lnw_off : nullptr;
+        ln_bwd_kernel<<<(int)((B + 3) / 4), 128, 0, s>>>(g_out, z, st, lw, a, pre, l.act, B, l.out_c);
+        B2RL_LAUNCH_CHECK();
+    } else if (l.act != B2RL_ACT_NONE) {
+        const int64_t n = B * oe;
+        int blocks = (int)((n + 255) / 256);
+        if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+        act_bwd_kernel<<<blocks, 256, 0, s>>>(g_out, a, pre, l.act, n);
+        B2RL_LAUNCH_CHECK();
+    }
+    // (2) weight + bias gradient:  dW[o][k] = sum_r G[r][o] * X[r][k],  db[o] = sum_r G[r][o]
+    float *gw = (l.noisy ? gweff : grads) + l.w_off;
+    float *gb = (l.noisy ? gweff : grads) + l.b_off;
+    const int acc_w = l.noisy ? 0 : accumulate_grads;   // noisy: accumulate happens in noisy_grad
+    {
+        Operand A, Bm;
+        Epilogue epi;
+        epi.kind = EPI_WGRAD;
+        epi.out = gw; epi.db = gb; epi.accumulate = acc_w;
+        int M, N, K;
+        int rc;
+        if (l.kind == B2RL_LAYER_CONV) {
+            const int P = l.out_h * l.out_w, KK = l.ksize * l.ksize;
+            const int Kc = l.in_c * KK;
+            M = l.out_c; N = Kc + 1; K = (int)(B * P);
+            epi.wcols = Kc;
+            A.ptr = g_out; A.row = map_stride(P); A.red = map_pixel(P, l.out_w, (int64_t)l.out_c * P, l.out_w, 1);
+            if (obs) {
+                Bm.ptr = obs->ptr; Bm.u8 = net.obs_u8; Bm.normalize = net.normalize; Bm.low = net.obs_low; Bm.high = net.obs_high;
+            } else Bm.ptr = x_in;
+            Bm.row = map_kernel(l.ksize, l.in_h * l.in_w, l.in_w);
+            Bm.red = map_pixel(P, l.out_w, (int64_t)l.in_c * l.in_h * l.in_w, l.stride * l.in_w, l.stride,
+                               obs ? obs->gather : nullptr);
+            Bm.ones_row = Kc;
+            rc = launch_igemm<true, false>(A, Bm, epi, M, N, K, sc.partial, sc.floats, s);
+        } else {
+            M = l.out_c; N = l.in_c + 1; K = (int)B;
+            epi.wcols = l.in_c;
+            A.ptr = g_out; A.row = map_stride(1); A.red = map_stride(l.out_c);
+            if (obs) {
+                Bm.ptr = obs->ptr; Bm.u8 = net.obs_u8; Bm.normalize = net.normalize; Bm.low = net.obs_low; Bm.high = net.obs_high;
+            } else Bm.ptr = x_in;
+            Bm.row = map_stride(1);
+            Bm.red = map_stride(l.in_c, obs ? obs->gather : nullptr);
+            Bm.ones_row = l.in_c;
+            rc = launch_igemm<false, false>(A, Bm, epi, M, N, K, sc.partial, sc.floats, s);
+        }
+        if (rc != B2RL_OK) return rc;
+    }
+    // (3) input gradient
+    if (g_in) {
+        Operand A, Bm;
+        Epilogue epi;
+        int rc;
+        if (l.kind == B2RL_LAYER_CONV) {
+            const int P = l.out_h * l.out_w, KK = l.ksize * l.ksize;
+            const int Kc = l.in_c * KK;
+            if (!accumulate_gin) B2RL_CUDA(cudaMemsetAsync(g_in, 0, sizeof(float) * B * layer_in_elems(l), s));
+            A.ptr = g_out; A.row = map_pixel(P, l.out_w, (int64_t)l.out_c * P, l.out_w, 1); A.red = map_stride(P);
+            Bm.ptr = W; Bm.row = map_stride(1); Bm.red = map_stride(Kc);
+            epi.kind = EPI_ATOMIC; epi.out = g_in;
+            epi.om = map_pixel(P, l.out_w, (int64_t)l.in_c * l.in_h * l.in_w, l.stride * l.in_w, l.stride);
+            epi.on = map_kernel(l.ksize, l.in_h * l.in_w, l.in_w);
+            rc = launch_igemm<false, false>(A, Bm, epi, (int)(B * P), Kc, l.out_c, nullptr, 0, s);
+        } else {
+            A.ptr = g_out; A.row = map_stride(l.out_c); A.red = map_stride(1);
+            Bm.ptr = W; Bm.row = map_stride(1); Bm.red = map_stride(l.in_c);
+            epi.out = g_in; epi.om = map_stride(l.in_c); epi.on = map_stride(1); epi.accumulate = accumulate_gin ? 1 : 0;
+            rc = launch_igemm<true, false>(A, Bm, epi, (int)B, l.in_c, l.out_c, sc.partial, sc.floats, s);
+        }
+        if (rc != B2RL_OK) return rc;
+    }
+    return B2RL_OK;
+}
+
+static int backward_pass(const b2rl_net_desc &net, const float *params, const float *weff, bool use_noise,
+                         const float *eps, PassBufs &pb, int64_t row_off, int64_t B, const ObsChunk &obs, float *grads,
+                         float *gweff, int accumulate, const Scratch &sc, cudaStream_t s) {
+    const LayerBuf &lat = pb.enc[net.n_enc - 1];
+    const float *latent = lat.a + row_off * layer_out_elems(net.enc[net.n_enc - 1]);
+    float *g_latent = lat.g;
+    // heads
+    for (int head = 0; head < 2; ++head) {
+        const b2rl_layer *layers = head == 0 ? net.val : net.adv;
+        LayerBuf *bufs = head == 0 ? pb.val : pb.adv;
+        const int n = head == 0 ? net.n_val : net.n_adv;
+        for (int i = n - 1; i >= 0; --i) {
+            const b2rl_layer &l = layers[i];
+            const float *x_in = i == 0 ? latent : bufs[i - 1].a + row_off * layer_out_elems(layers[i - 1]);
+            float *g_in = i == 0 ? g_latent : bufs[i - 1].g;
+            const bool acc_gin = (i == 0 && head == 1);
+            int rc = layer_backward(net, l, eff_w(l, params, weff, use_noise), params, x_in, nullptr, bufs[i], row_off,
+                                    bufs[i].g, g_in, acc_gin, grads, gweff, accumulate, B, sc, s);
+            if (rc != B2RL_OK) return rc;
+        }
+    }
+    // encoder
+    for (int i = net.n_enc - 1; i >= 0; --i) {
+        const b2rl_layer &l = net.enc[i];
+        const float *x_in = i == 0 ? nullptr : pb.enc[i - 1].a + row_off * layer_out_elems(net.enc[i - 1]);
+        float *g_in = i == 0 ? nullptr : pb.enc[i - 1].g;
+        int rc = layer_backward(net, l, eff_w(l, params, weff, use_noise), params, x_in, i == 0 ? &obs : nullptr,
+                                pb.enc[i], row_off, pb.enc[i].g, g_in, false, grads, gweff, accumulate, B, sc, s);
+        if (rc != B2RL_OK) return rc;
+    }
+    // noisy layers: grad_mu = grad_Weff, grad_sigma = grad_Weff * eps (autograd of mu + sigma*eps)
+    SegTable tm, tsg;
+    tm.n = tsg.n = 0;
+    int64_t maxn = 0;
+    for_each_layer(net, [&](const b2rl_layer &l) {
+        if (!l.noisy) return;
+        const int64_t nw = layer_w_elems(l);
+        tsg.s[tsg.n++] = Seg{grads + l.ws_off, gweff + l.w_off, nullptr, use_noise ? eps + l.we_off : nullptr, nw};
+        tsg.s[tsg.n++] = Seg{grads + l.bs_off, gweff + l.b_off, nullptr, use_noise ? eps + l.be_off : nullptr,
+                             (int64_t)l.out_c};
+        tm.s[tm.n++] = Seg{grads + l.w_off, gweff + l.w_off, nullptr, nullptr, nw};
+        tm.s[tm.n++] = Seg{grads + l.b_off, gweff + l.b_off, nullptr, nullptr, (int64_t)l.out_c};
+        if (nw > maxn) maxn = nw;
+    });
+    if (tsg.n > 0) {
+        int bx = (int)((maxn + 255) / 256);
+        if (bx > 64) bx = 64;
+        if (use_noise) {
+            noisy_grad_kernel<<<dim3(bx, tsg.n), 256, 0, s>>>(tsg, accumulate);
+            B2RL_LAUNCH_CHECK();
+        } else if (!accumulate) {   // eval-mode noisy layers: W = mu, sigma gets no gradient
+            for (int i = 0; i < tsg.n; ++i) B2RL_CUDA(cudaMemsetAsync(tsg.s[i].dst, 0, sizeof(float) * tsg.s[i].n, s));
+        }
+        noisy_grad_kernel<<<dim3(bx, tm.n), 256, 0, s>>>(tm, accumulate);
+        B2RL_LAUNCH_CHECK();
+    }
+    return B2RL_OK;
+}
+
+}  // namespace b2rl
+
+namespace b2rl {
+
+// ------------------------------------------------------------------------------------------
+// learn() tail: clip_grad_norm_ + Adam + Polyak  (dqn_rainbow.py:473-483, optimizer_wrapper.py)
+// ------------------------------------------------------------------------------------------
+struct AdamCfg {
+    int clip;
+    float max_norm;
+    float w1;            // 1 - beta1
+    float beta2, w2;     // beta2, 1 - beta2
+    float neg_step;      // -(lr / bias_correction1)
+    float bc2_sqrt;      // sqrt(bias_correction2)
+    float eps;
+    float tau, one_minus_tau;
+};
+
+__global__ void sqnorm_kernel(const float *__restrict__ g, int64_t n, float *__restrict__ partials) {
+    __shared__ float red[32];
+    float s = 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        s += g[i] * g[i];
+    s = block_reduce_sum(s, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+__global__ void adam_polyak_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m,
+                                   float *__restrict__ v, float *__restrict__ tgt, int64_t n,
+                                   const float *__restrict__ partials, int nparts, AdamCfg c) {
+    __shared__ float coef_s;
+    if (threadIdx.x == 0) {
+        float coef = 1.f;
+        if (c.clip) {
+            float tot = 0.f;
+            for (int i = 0; i < nparts; ++i) tot += partials[i];
+            const float total_norm = sqrtf(tot);
+            coef = c.max_norm / (total_norm + 1e-6f);      // clip_grad_norm_: clamp(coef, max=1)
+            coef = coef > 1.f ? 1.f : coef;
+        }
+        coef_s = coef;
+    }
+    __syncthreads();
+    const float coef = coef_s;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float gi = g[i];
+        if (c.clip) { gi = gi * coef; g[i] = gi; }
+        float mi = m[i], vi = v[i];
+        mi = fmaf(c.w1, gi - mi, mi);                        // exp_avg.lerp_(grad, 1-beta1)
+        vi = vi * c.beta2 + c.w2 * gi * gi;                  // mul_(beta2).addcmul_(g, g, 1-beta2)
+        m[i] = mi; v[i] = vi;
+        const float denom = sqrtf(vi) / c.bc2_sqrt + c.eps;
+        const float pi = p[i] + (c.neg_step * mi) / denom;   // addcdiv_(exp_avg, denom, value=-step_size)
+        p[i] = pi;
+        if (tgt) tgt[i] = __fadd_rn(__fmul_rn(c.tau, pi), __fmul_rn(c.one_minus_tau, tgt[i]));   // soft_update
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// NoisyLinear.reset_noise (custom_components.py:116-131)
+// ------------------------------------------------------------------------------------------
+struct NoiseSeg { float *eps_w; float *eps_b; int in, out; int64_t z_off; };
+struct NoiseTable { NoiseSeg s[B2RL_MAX_ENC + 2 * B2RL_MAX_HEAD]; int n; };
+
+__device__ __forceinline__ float scale_noise(float x) {    // x.sign() * x.abs().sqrt()
+    const float r = __fsqrt_rn(fabsf(x));
+    return x > 0.f ? r : (x < 0.f ? -r : 0.f);
+}
+
+template <bool kPhilox>
+__global__ void noise_reset_kernel(NoiseTable t, const float *__restrict__ normals, uint64_t seed, uint64_t offset) {
+    const NoiseSeg sg = t.s[blockIdx.y];
+    const int64_t n = (int64_t)sg.in * sg.out;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const int o = (int)(e / sg.in), i = (int)(e - (int64_t)o * sg.in);
+        float zi, zo;
+        if (kPhilox) {
+            zi = philox_normal(seed, offset + (uint64_t)(sg.z_off + i), 0x4E4F4953ull);
+            zo = philox_normal(seed, offset + (uint64_t)(sg.z_off + sg.in + o), 0x4E4F4953ull);
+        } else {
+            zi = normals[sg.z_off + i];
+            zo = normals[sg.z_off + sg.in + o];
+        }
+        const float fo = scale_noise(zo);
+        sg.eps_w[e] = __fmul_rn(fo, scale_noise(zi));       // epsilon_out.ger(epsilon_in)
+        if (i == 0) sg.eps_b[o] = fo;
+    }
+}
+
+static int64_t build_noise_table(const b2rl_net_desc &net, float *eps, NoiseTable &t) {
+    t.n = 0;
+    int64_t z = 0;
+    for_each_layer(net, [&](const b2rl_layer &l) {
+        if (!l.noisy) return;
+        t.s[t.n++] = NoiseSeg{eps ? eps + l.we_off : nullptr, eps ? eps + l.be_off : nullptr, l.in_c, l.out_c, z};
+        z += l.in_c + l.out_c;
+    });
+    return z;
+}
+
+static int noise_reset(const b2rl_net_desc &net, float *eps, const float *normals, uint64_t seed, uint64_t offset,
+                       cudaStream_t s) {
+    NoiseTable t;
+    build_noise_table(net, eps, t);
+    if (t.n == 0) return B2RL_OK;
+    int64_t maxn = 0;
+    for (int i = 0; i < t.n; ++i) {
+        const int64_t n = (int64_t)t.s[i].in * t.s[i].out;
+        if (n > maxn) maxn = n;
+    }
+    int bx = (int)((maxn + 255) / 256);
+    if (bx > 64) bx = 64;
+    if (normals) noise_reset_kernel<false><<<dim3(bx, t.n), 256, 0, s>>>(t, normals, 0, 0);
+    else noise_reset_kernel<true><<<dim3(bx, t.n), 256, 0, s>>>(t, nullptr, seed, offset);
+    B2RL_LAUNCH_CHECK();
+    return B2RL_OK;
+}
+
+static bool has_noisy(const b2rl_net_desc &net) {
+    bool any = false;
+    for_each_layer(net, [&](const b2rl_layer &l) { any |= l.noisy != 0; });
+    return any;
+}
+
+static int head_smem_check(size_t bytes) {
+    B2RL_CHECK_ARG(bytes <= 48 * 1024, "n_actions * n_atoms too large for the head kernels (%zu B smem)", bytes);
+    return B2RL_OK;
+}
+
+static int optim_step(const b2rl_net_desc &net, const b2rl_learn_cfg &cfg, const b2rl_learn_bufs &bufs, LearnWS &ws,
+                      cudaStream_t s) {
+    const int64_t n = net.n_params;
+    if (cfg.clip) {
+        sqnorm_kernel<<<kNormBlocks, 256, 0, s>>>(bufs.grads, n, ws.norm_partials);
+        B2RL_LAUNCH_CHECK();
+    }
+    AdamCfg c;
+    c.clip = cfg.clip;
+    c.max_norm = (float)cfg.max_grad_norm;
+    c.w1 = (float)(1.0 - cfg.beta1);
+    c.beta2 = (float)cfg.beta2;
+    c.w2 = (float)(1.0 - cfg.beta2);
+    c.neg_step = (float)(-(cfg.lr / cfg.bias_correction1));
+    c.bc2_sqrt = (float)sqrt(cfg.bias_correction2);
+    c.eps = (float)cfg.adam_eps;
+    c.tau = (float)cfg.tau;
+    c.one_minus_tau = (float)(1.0 - cfg.tau);
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > sm_count() * 4) blocks = sm_count() * 4;
+    adam_polyak_kernel<<<blocks, 256, 0, s>>>(bufs.actor_params, bufs.grads, bufs.exp_avg, bufs.exp_avg_sq,
+                                              bufs.target_params, n, ws.norm_partials, kNormBlocks, c);
+    B2RL_LAUNCH_CHECK();
+    return B2RL_OK;
+}
+
+static int rainbow_loss(const b2rl_net_desc &net, const b2rl_learn_cfg &cfg, const b2rl_learn_bufs &bufs, LearnWS &ws,
+                        cudaStream_t s) {
+    const int64_t B = cfg.batch;
+    const int A = net.n_actions, N = net.n_atoms;
+    const bool noise = cfg.use_noise != 0;
+    int rc;
+    if (noise) {
+        if ((rc = compose_weights(net, bufs.actor_params, bufs.actor_eps, ws.weff_actor, s)) != B2RL_OK) return rc;
+        if ((rc = compose_weights(net, bufs.target_params, bufs.target_eps, ws.weff_target, s)) != B2RL_OK) return rc;
+    }
+    Scratch sc{ws.partial, ws.partial_floats};
+    // online network on [next_obs ; obs]  (forwards #1 and #3 of _dqn_loss share weights and noise)
+    ObsChunk on_chunks[2] = {{bufs.next_obs, bufs.row_idx, B}, {bufs.obs, bufs.row_idx, B}};
+    if ((rc = forward_pass(net, bufs.actor_params, ws.weff_actor, noise, on_chunks, 2, 2 * B, ws.online, sc, s)) != B2RL_OK)
+        return rc;
+    // target network on next_obs (forward #2)
+    ObsChunk tg_chunk{bufs.next_obs, bufs.row_idx, B};
+    if ((rc = forward_pass(net, bufs.target_params, ws.weff_target, noise, &tg_chunk, 1, B, ws.target, sc, s)) != B2RL_OK)
+        return rc;
+    const float *v_on = ws.online.val[net.n_val - 1].a, *adv_on = ws.online.adv[net.n_adv - 1].a;
+    const float *v_tg = ws.target.val[net.n_val - 1].a, *adv_tg = ws.target.adv[net.n_adv - 1].a;
+    const size_t sm_q = sizeof(float) * ((size_t)A * N + A);
+    const size_t sm_t = sizeof(float) * ((size_t)A * N + 3 * (size_t)N) + sizeof(int) * 2 * (size_t)N;
+    if ((rc = head_smem_check(sm_t)) != B2RL_OK) return rc;
+    // next_actions = actor(next_obs).argmax(1)                              (dqn_rainbow.py:315)
+    rainbow_q_kernel<<<(int)B, 128, sm_q, s>>>(v_on, adv_on, bufs.support, A, N, nullptr, ws.a_star, nullptr);
+    B2RL_LAUNCH_CHECK();
+    ProjCfg pc{(float)cfg.gamma, (float)cfg.v_min, (float)cfg.v_max, (float)cfg.delta_z};
+    if (!cfg.driver_shapes) {
+        rainbow_target_kernel<<<(int)B, 128, sm_t, s>>>(v_tg, adv_tg, ws.a_star, bufs.reward, bufs.done, bufs.support,
+                                                        pc, A, N, nullptr, ws.proj);
+        B2RL_LAUNCH_CHECK();
+    } else {
+        rainbow_target_kernel<<<(int)B, 128, sm_t, s>>>(v_tg, adv_tg, ws.a_star, bufs.reward, bufs.done, bufs.support,
+                                                        pc, A, N, ws.tdist, nullptr);
+        B2RL_LAUNCH_CHECK();
+        q2_cmat_kernel<<<N, 64, sizeof(float) * N, s>>>(bufs.reward, bufs.done, bufs.support, pc, B, N, ws.cmat);
+        B2RL_LAUNCH_CHECK();
+        q2_project_kernel<<<(int)B, 64, 0, s>>>(ws.tdist, ws.cmat, N, ws.proj);
+        B2RL_LAUNCH_CHECK();
+    }
+    // log-softmax of the taken action on obs rows [B, 2B) + loss + dL/dlogits
+    rainbow_loss_kernel<<<(int)B, 128, sizeof(float) * ((size_t)N + 32), s>>>(
+        v_on + B * N, adv_on + B * (int64_t)A * N, bufs.action, ws.proj, bufs.weights, cfg.weights_mode, B, A, N,
+        cfg.accumulate, bufs.loss_elem, ws.online.val[net.n_val - 1].g, ws.online.adv[net.n_adv - 1].g);
+    B2RL_LAUNCH_CHECK();
+    rainbow_scalar_kernel<<<1, 256, 0, s>>>(bufs.loss_elem, bufs.weights, cfg.weights_mode, B, (float)cfg.prior_eps,
+                                            bufs.loss_scalar, bufs.priorities);
+    B2RL_LAUNCH_CHECK();
+    if (bufs.proj_dist)
+        B2RL_CUDA(cudaMemcpyAsync(bufs.proj_dist, ws.proj, sizeof(float) * B * N, cudaMemcpyDeviceToDevice, s));
+    return B2RL_OK;
+}
+
+static int check_learn_args(const b2rl_net_desc *net, const b2rl_learn_cfg *cfg, const b2rl_learn_bufs *bufs,
+                            LearnWS &ws) {
+    B2RL_CHECK_ARG(net && cfg && bufs, "NULL descriptor");
+    int rc = validate_net(*net);
+    if (rc != B2RL_OK) return rc;
+    B2RL_CHECK_ARG(cfg->batch >= 1, "Batch size must be greater than or equal to one.");
+    B2RL_CHECK_ARG(bufs->actor_params && bufs->target_params && bufs->grads && bufs->exp_avg && bufs->exp_avg_sq,
+                   "NULL parameter/optimizer buffer");
+    B2RL_CHECK_ARG(bufs->obs && bufs->next_obs && bufs->action && bufs->reward && bufs->done, "NULL batch buffer");
+    B2RL_CHECK_ARG(cfg->weights_mode == 0 || bufs->weights, "PER weights missing");
+    carve_learn(*net, cfg->batch, true, bufs->workspace, ws);
+    B2RL_CHECK_ARG(bufs->workspace && bufs->workspace_bytes >= ws.bytes, "workspace too small: need %zu bytes, got %zu",
+                   ws.bytes, bufs->workspace_bytes);
+    return B2RL_OK;
+}
+
+}  // namespace b2rl
+
+using namespace b2rl;
+
+extern "C" {
+
+int b2rl_net_workspace_bytes(const b2rl_net_desc *net_host, int64_t rows, int with_backward, size_t *out_host) {
+    B2RL_CHECK_ARG(net_host && out_host, "NULL argument");
+    int rc = validate_net(*net_host);
+    if (rc != B2RL_OK) return rc;
+    if (with_backward) {
+        LearnWS ws;
+        carve_learn(*net_host, rows, true, nullptr, ws);
+        *out_host = ws.bytes;
+    } else {
+        FwdWS ws;
+        carve_fwd(*net_host, rows, nullptr, ws);
+        *out_host = ws.bytes;
+    }
+    return B2RL_OK;
+}
+
+int b2rl_noise_count(const b2rl_net_desc *net_host, int64_t *out_host) {
+    B2RL_CHECK_ARG(net_host && out_host, "NULL argument");
+    NoiseTable t;
+    *out_host = build_noise_table(*net_host, nullptr, t);
+    return B2RL_OK;
+}
+
+int b2rl_noise_reset_from_normals(const b2rl_net_desc *net_host, float *eps, const float *normals, void *stream) {
+    B2RL_CHECK_ARG(net_host && normals, "NULL argument");
+    B2RL_CHECK_ARG(eps || !has_noisy(*net_host), "eps buffer is NULL");
+    return noise_reset(*net_host, eps, normals, 0, 0, as_stream(stream));
+}
+
+int b2rl_noise_reset_philox(const b2rl_net_desc *net_host, float *eps, uint64_t seed, uint64_t offset, void *stream) {
+    B2RL_CHECK_ARG(net_host, "NULL argument");
+    B2RL_CHECK_ARG(eps || !has_noisy(*net_host), "eps buffer is NULL");
+    return noise_reset(*net_host, eps, nullptr, seed, offset, as_stream(stream));
+}
+
+int b2rl_net_forward_q(const b2rl_net_desc *net_host, const float *params, const float *eps, int use_noise,
+                       const float *support, const void *obs, const int64_t *row_idx, int64_t rows, float *q_out,
+                       int64_t *argmax_out, void *workspace, size_t workspace_bytes, void *stream) {
+    B2RL_CHECK_ARG(net_host && params && obs, "NULL argument");
+    int rc = validate_net(*net_host);
+    if (rc != B2RL_OK) return rc;
+    if (rows <= 0) return B2RL_OK;
+    const b2rl_net_desc &net = *net_host;
+    FwdWS ws;
+    carve_fwd(net, rows, workspace, ws);
+    B2RL_CHECK_ARG(workspace && workspace_bytes >= ws.bytes, "workspace too small: need %zu bytes, got %zu", ws.bytes,
+                   workspace_bytes);
+    cudaStream_t s = as_stream(stream);
+    const bool noise = use_noise && has_noisy(net);
+    if (noise) {
+        B2RL_CHECK_ARG(eps, "eps buffer is NULL");
+        if ((rc = compose_weights(net, params, eps, ws.weff, s)) != B2RL_OK) return rc;
+    }
+    Scratch sc{ws.partial, ws.partial_floats};
+    ObsChunk chunk{obs, row_idx, rows};
+    if ((rc = forward_pass(net, params, ws.weff, noise, &chunk, 1, rows, ws.pass, sc, s)) != B2RL_OK) return rc;
+    const int A = net.n_actions, N = net.n_atoms;
+    if (net.kind == B2RL_NET_RAINBOW) {
+        const size_t sm_q = sizeof(float) * ((size_t)A * N + A);
+        if ((rc = head_smem_check(sm_q)) != B2RL_OK) return rc;
+        B2RL_CHECK_ARG(support, "support is NULL");
+        rainbow_q_kernel<<<(int)rows, 128, sm_q, s>>>(ws.pass.val[net.n_val - 1].a, ws.pass.adv[net.n_adv - 1].a, support,
+                                                      A, N, q_out, nullptr, argmax_out);
+        B2RL_LAUNCH_CHECK();
+        return B2RL_OK;
+    }
+    q_argmax_kernel<<<(int)((rows + 127) / 128), 128, 0, s>>>(ws.pass.val[net.n_val - 1].a, A, rows, q_out, argmax_out);
+    B2RL_LAUNCH_CHECK();
+    return B2RL_OK;
+}
+
+
+int b2rl_rainbow_loss(const b2rl_net_desc *net_host, const b2rl_learn_cfg *cfg_host, const b2rl_learn_bufs *bufs_host,
+                      void *stream) {
+    LearnWS ws;
+    int rc = check_learn_args(net_host, cfg_host, bufs_host, ws);
+    if (rc != B2RL_OK) return rc;
+    B2RL_CHECK_ARG(net_host->kind == B2RL_NET_RAINBOW, "not a rainbow network");
+    B2RL_CHECK_ARG(bufs_host->support && bufs_host->loss_elem && bufs_host->loss_scalar, "NULL rainbow buffer");
+    return rainbow_loss(*net_host, *cfg_host, *bufs_host, ws, as_stream(stream));
+}
+
+int b2rl_rainbow_backward(const b2rl_net_desc *net_host, const b2rl_learn_cfg *cfg_host,
+                          const b2rl_learn_bufs *bufs_host, void *stream) {
+    LearnWS ws;
+    int rc = check_learn_args(net_host, cfg_host, bufs_host, ws);
+    if (rc != B2RL_OK) return rc;
+    Scratch sc{ws.partial, ws.partial_floats};
+    ObsChunk obs{bufs_host->obs, bufs_host->row_idx, cfg_host->batch};
+    return backward_pass(*net_host, bufs_host->actor_params, ws.weff_actor, cfg_host->use_noise != 0,
+                         bufs_host->actor_eps, ws.online, cfg_host->batch, cfg_host->batch, obs, bufs_host->grads,
+                         ws.gweff, cfg_host->accumulate, sc, as_stream(stream));
+}
+
+int b2rl_optim_step(const b2rl_net_desc *net_host, const b2rl_learn_cfg *cfg_host, const b2rl_learn_bufs *bufs_host,
+                    void *stream) {
+    LearnWS ws;
+    int rc = check_learn_args(net_host, cfg_host, bufs_host, ws);
+    if (rc != B2RL_OK) return rc;
+    return optim_step(*net_host, *cfg_host, *bufs_host, ws, as_stream(stream));
+}
+
+int b2rl_rainbow_learn(const b2rl_net_desc *net_host, const b2rl_learn_cfg *cfg_host, const b2rl_learn_bufs *bufs_host,
+                       void *stream) {
+    int rc = b2rl_rainbow_loss(net_host, cfg_host, bufs_host, stream);
+    if (rc != B2RL_OK) return rc;
+    if ((rc = b2rl_rainbow_backward(net_host, cfg_host, bufs_host, stream)) != B2RL_OK) return rc;
+    return b2rl_optim_step(net_host, cfg_host, bufs_host, stream);
+}
+
+int b2rl_dqn_learn(const b2rl_net_desc *net_host, const b2rl_learn_cfg *cfg_host, const b2rl_learn_bufs *bufs_host,
+                   void *stream) {
+    LearnWS ws;
+    int rc = check_learn_args(net_host, cfg_host, bufs_host, ws);
+    if (rc != B2RL_OK) return rc;
+    const b2rl_net_desc &net = *net_host;
+    const b2rl_learn_cfg &cfg = *cfg_host;
+    const b2rl_learn_bufs &bufs = *bufs_host;
+    B2RL_CHECK_ARG(net.kind == B2RL_NET_Q, "not a Q network");
+    B2RL_CHECK_ARG(bufs.loss_scalar, "NULL loss buffer");
+    cudaStream_t s = as_stream(stream);
+    const int64_t B = cfg.batch;
+    const int A = net.n_actions;
+    Scratch sc{ws.partial, ws.partial_floats};
+    // q-networks run in eval mode inside DQN.update (plain Linear layers; no noise)
+    int64_t row_off = 0;
+    if (cfg.double_dqn) {
+        ObsChunk ch[2] = {{bufs.next_obs, bufs.row_idx, B}, {bufs.obs, bufs.row_idx, B}};
+        if ((rc = forward_pass(net, bufs.actor_params, ws.weff_actor, false, ch, 2, 2 * B, ws.online, sc, s)) != B2RL_OK)
+            return rc;
+        row_off = B;
+    } else {
+        ObsChunk ch{bufs.obs, bufs.row_idx, B};
+        if ((rc = forward_pass(net, bufs.actor_params, ws.weff_actor, false, &ch, 1, B, ws.online, sc, s)) != B2RL_OK)
+            return rc;
+    }
+    ObsChunk tg{bufs.next_obs, bufs.row_idx, B};
+    if ((rc = forward_pass(net, bufs.target_params, ws.weff_target, false, &tg, 1, B, ws.target, sc, s)) != B2RL_OK)
+        return rc;
+    const float *q_on = ws.online.val[net.n_val - 1].a;
+    dqn_loss_kernel<<<1, 256, 0, s>>>(q_on + row_off * A, q_on, ws.target.val[net.n_val - 1].a, bufs.action, bufs.reward,
+                                      bufs.done, (float)cfg.gamma, cfg.double_dqn, B, A,
+                                      ws.online.val[net.n_val - 1].g, bufs.loss_elem, bufs.loss_scalar);
+    B2RL_LAUNCH_CHECK();
+    ObsChunk obs{bufs.obs, bufs.row_idx, B};
+    if ((rc = backward_pass(net, bufs.actor_params, ws.weff_actor, false, bufs.actor_eps, ws.online, row_off, B, obs,
+                            bufs.grads, ws.gweff, 0, sc, s)) != B2RL_OK)
+        return rc;
+    return optim_step(net, cfg, bufs, ws, s);
+}
+
+}  // extern "C"

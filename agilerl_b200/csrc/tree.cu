@@ -144,21 +144,6 @@ __global__ void tree_retrieve_kernel(const double *st, int64_t cap, const double
     if (i < n) out[i] = retrieve_dev(st, cap, ub[i]);
 }
 
-// Philox4x32-10, one 128-bit block per counter; returns word `lane` (0..3).
-__device__ __forceinline__ void philox4x32_10(uint64_t seed, uint64_t c_lo, uint64_t c_hi, uint32_t out[4]) {
-    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    uint32_t c0 = (uint32_t)c_lo, c1 = (uint32_t)(c_lo >> 32), c2 = (uint32_t)c_hi, c3 = (uint32_t)(c_hi >> 32);
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-
 template <bool kPhilox>
 __global__ void per_sample_kernel(const double *__restrict__ st, const double *__restrict__ mt, int64_t cap,
                                   const float *__restrict__ uniforms, uint64_t seed, uint64_t offset,

@@ -164,30 +164,33 @@ int b2rl_noise_count(const b2rl_net_desc *net_host, int64_t *out_host);
 /* Forward only (get_action path: dqn_rainbow.py:239-282, dqn.py:262-264).
  * obs: rows x obs_elems (uint8 or f32); row_idx (nullable) gathers rows from a ring.
  * q_out: rows x n_actions expected values; argmax_out (nullable): int64 rows.
- * use_noise: train-mode NoisyLinear (Rainbow acts in train mode). */
+ * use_noise: train-mode NoisyLinear (Rainbow acts in train mode).  support: n_atoms C51 atoms
+ * (rainbow; NULL for Q nets). */
 int b2rl_net_forward_q(const b2rl_net_desc *net_host, const float *params, const float *eps,
-                       int use_noise, const void *obs, const int64_t *row_idx, int64_t rows,
-                       float *q_out, int64_t *argmax_out, void *workspace, size_t workspace_bytes,
-                       void *stream);
+                       int use_noise, const float *support, const void *obs,
+                       const int64_t *row_idx, int64_t rows, float *q_out, int64_t *argmax_out,
+                       void *workspace, size_t workspace_bytes, void *stream);
 
-/* Scalars of one learn step. */
+/* Scalars of one learn step (doubles are the Python floats of the reference, rounded to f32
+ * inside the kernels exactly where torch rounds them). */
 typedef struct b2rl_learn_cfg {
     int64_t batch;                      /* B (== agent.batch_size, quirk Q17) */
-    float gamma;                        /* discount used in the target (gamma**n_step for n-step) */
-    float v_min, v_max;                 /* C51 support bounds (rainbow) */
-    double delta_z;                     /* (v_max - v_min)/(n_atoms-1) as the Python double */
+    double gamma;                       /* discount used in the target (gamma**n_step for n-step) */
+    double v_min, v_max;                /* C51 support bounds (rainbow) */
+    double delta_z;                     /* (v_max - v_min)/(n_atoms-1) */
     int32_t weights_mode;               /* 0: no PER (mean l); 1: weights [B] -> mean(l*w);
                                            2: weights [B,1] -> mean(l)*mean(w)  (quirk Q1) */
     int32_t driver_shapes;              /* 1: reward/done arrived [B,1,1] (quirk Q2 semantics) */
     int32_t double_dqn;                 /* DQN only */
-    int32_t clip;                       /* 1: clip_grad_norm_(10.0) (rainbow), 0: none (DQN) */
-    float max_grad_norm;
-    float lr, beta1, beta2, adam_eps;
-    double bias_correction1, bias_correction2; /* 1-beta^step as Python doubles */
-    float tau;
-    float prior_eps;
-    int32_t accumulate_loss;            /* 1: add this call's per-sample loss to loss_elem
-                                           (combined_reward second pass) */
+    int32_t clip;                       /* 1: clip_grad_norm_(max_grad_norm) (rainbow), 0: none */
+    double max_grad_norm;
+    double lr, beta1, beta2, adam_eps;
+    double bias_correction1, bias_correction2; /* 1-beta^step */
+    double tau;
+    double prior_eps;
+    int32_t accumulate;                 /* 1: second pass of combined_reward — add this pass's
+                                           per-sample loss / gradients to the first pass's */
+    int32_t use_noise;                  /* NoisyLinear in train mode (always 1 in learn) */
 } b2rl_learn_cfg;
 
 /* Device buffers of one learn step (all fp32 unless stated). */
