@@ -108,11 +108,13 @@ def test_rainbow_learn_golden_canonical_full_state():
             assert (p1 - a1[k])[mask].abs().max().item() <= 5e-6, f"param {k}"
         np.testing.assert_allclose(eng.exp_avg[layout.entries[k].offset:layout.entries[k].offset + ref_numel(gref[k])]
                                    .cpu().numpy().reshape(gref[k].shape), g[f"m/{k}"], rtol=1e-4, atol=1e-8)
-    # noise reset from the injected normals == reference's new epsilon buffers
+    # noise reset from the injected normals == reference's new epsilon buffers.  Not bit-equal by
+    # construction: torch's CPU sqrt goes through MKL VML, which is not correctly rounded
+    # (0.6% of values are 1 ulp off IEEE sqrt); the device uses IEEE sqrt.rn.
     for k, v in a1.items():
         if k.endswith("_epsilon"):
-            np.testing.assert_array_equal(eng.actor.view(k).cpu().numpy(), v.numpy())
-            np.testing.assert_array_equal(eng.target.view(k).cpu().numpy(), _sd(g, "target1")[k].numpy())
+            np.testing.assert_allclose(eng.actor.view(k).cpu().numpy(), v.numpy(), rtol=2.5e-7, atol=0)
+            np.testing.assert_allclose(eng.target.view(k).cpu().numpy(), _sd(g, "target1")[k].numpy(), rtol=2.5e-7, atol=0)
 
 
 def ref_numel(t):
