@@ -75,6 +75,9 @@ _SIGS = {
                          c_void_p], c_int),
     "b2rl_per_sample_philox": ([c_void_p, c_void_p, c_int64, c_uint64, c_uint64, c_int64, c_double, c_int64,
                                 c_void_p, c_void_p, c_void_p], c_int),
+    "b2rl_per_sample_fused": ([c_void_p, c_void_p, c_int64, c_void_p, c_uint64, c_uint64, c_int64, c_double, c_int64,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p], c_int),
     "b2rl_ring_write": ([c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p], c_int),
     "b2rl_gather_rows": ([c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p], c_int),
     "b2rl_nstep_fold": ([POINTER(c_void_p), POINTER(c_void_p), c_int, c_int64, c_double, c_void_p, c_void_p,
@@ -86,6 +89,9 @@ _SIGS = {
     "b2rl_noise_count": ([POINTER(NetDesc), POINTER(c_int64)], c_int),
     "b2rl_net_forward_q": ([POINTER(NetDesc), c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64,
                             c_void_p, c_void_p, c_void_p, c_size_t, c_void_p], c_int),
+    "b2rl_encoder_layer_forward": ([POINTER(NetDesc), c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                    c_size_t, c_void_p], c_int),
+    "b2rl_launch_count": ([], ctypes.c_ulonglong),
     "b2rl_rainbow_loss": ([POINTER(NetDesc), POINTER(LearnCfg), POINTER(LearnBufs), c_void_p], c_int),
     "b2rl_rainbow_backward": ([POINTER(NetDesc), POINTER(LearnCfg), POINTER(LearnBufs), c_void_p], c_int),
     "b2rl_optim_step": ([POINTER(NetDesc), POINTER(LearnCfg), POINTER(LearnBufs), c_void_p], c_int),

@@ -144,7 +144,9 @@ class LearnEngine:
         b.actor_params, b.target_params = self.actor.params.data_ptr(), self.target.params.data_ptr()
         b.actor_eps, b.target_eps = self.actor.eps.data_ptr(), self.target.eps.data_ptr()
         b.grads, b.exp_avg, b.exp_avg_sq = self.grads.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr()
-        keep = [self._obs(batch["obs"]), self._obs(batch["next_obs"]), self._vec(batch["action"], self.device),
+        keep = [batch["obs"] if row_idx is not None else self._obs(batch["obs"]),
+                batch["next_obs"] if row_idx is not None else self._obs(batch["next_obs"]),
+                self._vec(batch["action"], self.device),
                 self._vec(batch["reward"], self.device), self._vec(batch["done"], self.device)]
         b.obs, b.next_obs, b.action, b.reward, b.done = (t.data_ptr() for t in keep)
         if row_idx is not None:
@@ -207,3 +209,19 @@ class LearnEngine:
         _lib.check(self.lib.b2rl_dqn_learn(desc, ctypes.byref(cfg), ctypes.byref(bufs), _lib.stream_ptr(self.device)))
         self._keepalive = keep
         return loss_scalar
+
+    # -- fused HBM-resident step ---------------------------------------------------------------
+    def rainbow_fused_step(self, per, n_step_memory, *, B: int, beta: float, support: torch.Tensor, hp: dict,
+                           gamma_n: float, weights_mode: int = 1, uniforms=None, noise_normals=None):
+        """One gradient step with the replay resident in HBM and no host round trip:
+        sample (tree descent + IS weights + n-step scalars, one kernel) -> learn with the encoder
+        reading frames from the ring through the sampled indices -> priorities written back into
+        the trees on device.  Equivalent to train_off_policy.py:399-412 for one agent."""
+        idx, w, a, r, d = per.sample_fused(B, beta, n_step_memory, uniforms)
+        f = n_step_memory._fields
+        batch = dict(obs=f[("obs",)], next_obs=f[(n_step_memory.ns_key,)], action=a, reward=r, done=d)
+        loss, loss_elem, pri, _ = self.rainbow_learn([(batch, gamma_n, False)], B=B, support=support, weights=w,
+                                                     weights_mode=weights_mode, hp=hp, noise_normals=noise_normals,
+                                                     row_idx=idx)
+        per.update_priorities_device(idx, pri)
+        return loss, idx, pri

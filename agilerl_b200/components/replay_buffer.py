@@ -280,7 +280,9 @@ class PrioritizedReplayBuffer(ReplayBuffer):
                  dtype: torch.dtype = torch.float32) -> None:
         super().__init__(max_size, device, dtype)
         self.alpha = alpha
-        self.max_priority = 1.0
+        self._max_priority = 1.0
+        self._max_priority_dev = torch.ones(1, dtype=torch.float64, device=self._dev)
+        self._dev_dirty = False
         self.tree_ptr = 0
         tree_capacity = 1
         while tree_capacity < max_size:
@@ -292,6 +294,19 @@ class PrioritizedReplayBuffer(ReplayBuffer):
         self.device_rng = False
         self._philox_seed = 0x5EED
         self._philox_offset = 0
+
+    @property
+    def max_priority(self) -> float:
+        """Running max of raw priorities (replay_buffer.py:329).  The fused device path folds its
+        maxima into a device scalar; reading the attribute reconciles the two (one 8-byte D2H)."""
+        if self._dev_dirty:
+            self._max_priority = max(self._max_priority, float(self._max_priority_dev.item()))
+            self._dev_dirty = False
+        return self._max_priority
+
+    @max_priority.setter
+    def max_priority(self, value: float) -> None:
+        self._max_priority = float(value)
 
     def add(self, data: DataType) -> None:
         """:296-309 — ring write, then the n new leaves get max_priority**alpha."""
@@ -375,3 +390,41 @@ class PrioritizedReplayBuffer(ReplayBuffer):
         _lib.check(self._lib.b2rl_tree_set(self.sum_tree.data_ptr, self.min_tree.data_ptr, self._cap,
                                            idx_dev.data_ptr(), pa_dev.data_ptr(), n, _lib.stream_ptr(self._dev)))
         self._keep = (idx_dev, pa_dev)
+
+    # -- fused HBM-resident path (no host round trips) -------------------------------------------
+    def sample_fused(self, batch_size: int, beta: float, n_step_memory: "MultiStepReplayBuffer",
+                     uniforms: torch.Tensor | None = None):
+        """One kernel: tree descent + IS weights + gather of the sampled slots' n-step
+        action/reward/done.  Returns device tensors (idx int64[B], weights, action, reward, done
+        f32[B]); frames stay in the ring and are read through ``idx`` by the encoder."""
+        f = n_step_memory._fields
+        dk = n_step_memory.done_key or "done"
+        ring = [f[("action",)], f[(n_step_memory.reward_key,)], f[(dk,)]]
+        for t in ring:
+            assert t.dtype == torch.float32 and t[0].numel() == 1, "fused path needs scalar f32 action/reward/done"
+        B = batch_size
+        idx = torch.empty(B, dtype=torch.int64, device=self._dev)
+        out = [torch.empty(B, dtype=torch.float32, device=self._dev) for _ in range(4)]
+        if uniforms is None and not self.device_rng:
+            uniforms = self._uniforms(B)
+        _lib.check(self._lib.b2rl_per_sample_fused(
+            self.sum_tree.data_ptr, self.min_tree.data_ptr, self._cap,
+            None if uniforms is None else uniforms.data_ptr(), self._philox_seed, self._philox_offset, B, float(beta),
+            self._size, ring[0].data_ptr(), ring[1].data_ptr(), ring[2].data_ptr(), idx.data_ptr(),
+            out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), _lib.stream_ptr(self._dev)))
+        if uniforms is None:
+            self._philox_offset += B
+        self._keep_u = uniforms
+        return idx, out[0], out[1], out[2], out[3]
+
+    def update_priorities_device(self, indices: torch.Tensor, priorities: torch.Tensor) -> None:
+        """Device-only variant of ``update_priorities``: floor, ``p**alpha`` (CUDA fp64 pow, <= 1 ulp
+        from glibc — see DESIGN.md), last-writer-wins tree update and max-priority fold, no sync."""
+        idx = indices.reshape(-1)
+        pri = priorities.reshape(-1)
+        assert idx.is_cuda and pri.is_cuda and idx.dtype == torch.int64 and pri.dtype == torch.float32
+        _lib.check(self._lib.b2rl_tree_set_from_priorities(
+            self.sum_tree.data_ptr, self.min_tree.data_ptr, self._cap, idx.data_ptr(), pri.data_ptr(), idx.numel(),
+            float(self.alpha), 1e-5, self._max_priority_dev.data_ptr(), _lib.stream_ptr(self._dev)))
+        self._dev_dirty = True
+

@@ -28,7 +28,12 @@ void set_error(const char *fmt, ...);
         }                                                                                \
     } while (0)
 
-#define B2RL_LAUNCH_CHECK() B2RL_CUDA(cudaGetLastError())
+extern unsigned long long g_launches;   // kernels launched by this library (bench.py's gpu_launches)
+#define B2RL_LAUNCH_CHECK()                 \
+    do {                                    \
+        ++::b2rl::g_launches;               \
+        B2RL_CUDA(cudaGetLastError());      \
+    } while (0)
 
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 

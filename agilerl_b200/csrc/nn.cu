@@ -1232,4 +1232,21 @@ int b2rl_dqn_learn(const b2rl_net_desc *net_host, const b2rl_learn_cfg *cfg_host
     return optim_step(net, cfg, bufs, ws, s);
 }
 
+
+int b2rl_encoder_layer_forward(const b2rl_net_desc *net_host, int layer, const float *params, const void *input,
+                               const int64_t *row_idx, int64_t rows, float *out, void *workspace,
+                               size_t workspace_bytes, void *stream) {
+    B2RL_CHECK_ARG(net_host && params && input && out, "NULL argument");
+    B2RL_CHECK_ARG(layer >= 0 && layer < net_host->n_enc, "layer out of range");
+    const b2rl_layer &l = net_host->enc[layer];
+    B2RL_CHECK_ARG(l.ln == B2RL_LN_NONE && !l.noisy, "profiling hook handles plain conv/linear layers");
+    LayerBuf lb;
+    lb.a = out;
+    Scratch sc{static_cast<float *>(workspace), workspace_bytes / sizeof(float)};
+    ObsChunk ch{input, row_idx, rows};
+    return layer_forward(*net_host, l, params + l.w_off, params + l.b_off, params,
+                         layer == 0 ? nullptr : static_cast<const float *>(input), &ch, 1, rows, lb, sc,
+                         as_stream(stream));
+}
+
 }  // extern "C"

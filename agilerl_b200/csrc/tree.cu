@@ -12,6 +12,7 @@
 
 namespace b2rl {
 
+unsigned long long g_launches = 0;
 static thread_local char g_err[512] = "";
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -148,7 +149,10 @@ template <bool kPhilox>
 __global__ void per_sample_kernel(const double *__restrict__ st, const double *__restrict__ mt, int64_t cap,
                                   const float *__restrict__ uniforms, uint64_t seed, uint64_t offset,
                                   int64_t B, double beta, int64_t size, int64_t *__restrict__ out_idx,
-                                  float *__restrict__ out_w) {
+                                  float *__restrict__ out_w, const float *__restrict__ action_ring,
+                                  const float *__restrict__ reward_ring, const float *__restrict__ done_ring,
+                                  float *__restrict__ out_action, float *__restrict__ out_reward,
+                                  float *__restrict__ out_done) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= B) return;
     const double total = st[1];                                   // sum_tree.sum()
@@ -173,6 +177,11 @@ __global__ void per_sample_kernel(const double *__restrict__ st, const double *_
         const double w = pow(__dmul_rn(p, (double)size), -beta);
         out_w[i] = (float)__ddiv_rn(w, max_w);
     }
+    // fused gather of the small n-step fields of the sampled slot (frames are NOT copied: the conv
+    // loader reads them straight from the ring through out_idx)
+    if (out_action) out_action[i] = __ldg(action_ring + idx);
+    if (out_reward) out_reward[i] = __ldg(reward_ring + idx);
+    if (out_done) out_done[i] = __ldg(done_ring + idx);
 }
 
 static bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
@@ -184,6 +193,7 @@ using namespace b2rl;
 extern "C" {
 
 int b2rl_version(void) { return 100; }
+unsigned long long b2rl_launch_count(void) { return b2rl::g_launches; }
 const char *b2rl_last_error(void) { return b2rl::last_error(); }
 
 int b2rl_device_sm_count(int device, int *out_host) {
@@ -268,7 +278,8 @@ int b2rl_per_sample(const double *sum_tree, const double *min_tree, int64_t cap,
     B2RL_CHECK_ARG(is_pow2(cap), "capacity must be positive and a power of 2.");
     B2RL_CHECK_ARG(B > 0 && uniforms && out_idx, "bad sample arguments");
     per_sample_kernel<false><<<(int)((B + 63) / 64), 64, 0, as_stream(stream)>>>(
-        sum_tree, min_tree, cap, uniforms, 0, 0, B, beta, size, out_idx, out_w);
+        sum_tree, min_tree, cap, uniforms, 0, 0, B, beta, size, out_idx, out_w, nullptr, nullptr, nullptr, nullptr, nullptr,
+        nullptr);
     B2RL_LAUNCH_CHECK();
     return B2RL_OK;
 }
@@ -279,7 +290,29 @@ int b2rl_per_sample_philox(const double *sum_tree, const double *min_tree, int64
     B2RL_CHECK_ARG(is_pow2(cap), "capacity must be positive and a power of 2.");
     B2RL_CHECK_ARG(B > 0 && out_idx, "bad sample arguments");
     per_sample_kernel<true><<<(int)((B + 63) / 64), 64, 0, as_stream(stream)>>>(
-        sum_tree, min_tree, cap, nullptr, seed, offset, B, beta, size, out_idx, out_w);
+        sum_tree, min_tree, cap, nullptr, seed, offset, B, beta, size, out_idx, out_w, nullptr, nullptr, nullptr, nullptr,
+        nullptr, nullptr);
+    B2RL_LAUNCH_CHECK();
+    return B2RL_OK;
+}
+
+
+int b2rl_per_sample_fused(const double *sum_tree, const double *min_tree, int64_t cap, const float *uniforms,
+                          uint64_t seed, uint64_t offset, int64_t B, double beta, int64_t size,
+                          const float *action_ring, const float *reward_ring, const float *done_ring,
+                          int64_t *out_idx, float *out_w, float *out_action, float *out_reward, float *out_done,
+                          void *stream) {
+    B2RL_CHECK_ARG(is_pow2(cap), "capacity must be positive and a power of 2.");
+    B2RL_CHECK_ARG(B > 0 && out_idx, "bad sample arguments");
+    B2RL_CHECK_ARG(action_ring && reward_ring && done_ring && out_action && out_reward && out_done, "NULL ring field");
+    if (uniforms)
+        per_sample_kernel<false><<<(int)((B + 63) / 64), 64, 0, as_stream(stream)>>>(
+            sum_tree, min_tree, cap, uniforms, 0, 0, B, beta, size, out_idx, out_w, action_ring, reward_ring, done_ring,
+            out_action, out_reward, out_done);
+    else
+        per_sample_kernel<true><<<(int)((B + 63) / 64), 64, 0, as_stream(stream)>>>(
+            sum_tree, min_tree, cap, nullptr, seed, offset, B, beta, size, out_idx, out_w, action_ring, reward_ring,
+            done_ring, out_action, out_reward, out_done);
     B2RL_LAUNCH_CHECK();
     return B2RL_OK;
 }

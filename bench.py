@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py — population gradient-steps/sec, Rainbow-DQN pop=8 (BASELINE.json metric, config 2).
+
+    python bench.py --gpus N --steps K --warmup W              # our CUDA path (one rank per GPU)
+    python bench.py --impl reference --steps K --warmup W      # the oracle port on host cores
+
+One *gradient step* of one agent = PER sample(B, beta) + n-step gather + RainbowDQN.learn
+(3 forwards, C51 projection, backward, clip, Adam, Polyak, noise reset) + update_priorities
+(SURVEY §8d).  A bench "step" = one such gradient step for EVERY agent of the population
+(pop=8, sharded pop/N agents per GPU; total work fixed -> "strong" scaling).
+
+  value : replay resident in HBM, fused device path (no host round trip), CUDA-event timed.
+  e2e   : same metric through the reference-shaped Python API with HOST buffers: every step
+          H2D-copies one env-step of transitions from pinned memory (memory.add), samples,
+          learns, D2H-reads loss + priorities and writes priorities back (update_priorities).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# --- workload constants ------------------------------------------------
+POP = 8
+B = 256
+OBS = (4, 84, 84)
+N_ACT = 6
+N_ATOMS = 51
+BUFFER = 100_000
+ALPHA, BETA, N_STEP, GAMMA = 0.6, 0.4, 3, 0.99
+V_MIN, V_MAX = -10.0, 10.0
+LR, TAU, PRIOR_EPS = 1e-4, 1e-3, 1e-6
+NUM_ENVS = 4                                  # env-steps ingested per e2e step
+ALG_BYTES_PER_STEP = 22_954_544
+ALG_FLOPS_PER_STEP = 12_067_307_520
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def build_rank(device, n_agents, seed0):
+    from agilerl_b200.algorithms._engine import LearnEngine, NetBuffers
+    from agilerl_b200.compat import TensorDict
+    from agilerl_b200.components import MultiStepReplayBuffer, PrioritizedReplayBuffer
+    from agilerl_b200.networks.init import init_state_dict
+    from agilerl_b200.networks.spec import FlatLayout, rainbow_spec
+
+    spec = rainbow_spec(OBS, N_ACT, channel_size=(32, 32), kernel_size=(8, 4), stride_size=(4, 2), latent_dim=32,
+                        hidden_size=(64,), num_atoms=N_ATOMS, obs_low=0.0, obs_high=255.0, obs_u8=True)
+    engines = []
+    for a in range(n_agents):
+        torch.manual_seed(seed0 + a)
+        layout = FlatLayout(spec)
+        sd = init_state_dict(layout)
+        actor, target = NetBuffers(layout, device), NetBuffers(layout, device)
+        actor.load_state_dict(sd, strict=False)
+        target.load_state_dict(sd, strict=False)
+        eng = LearnEngine(layout, actor, target)
+        eng.philox_seed = 0xB200 + seed0 + a
+        eng.reset_noise(actor); eng.reset_noise(target)
+        engines.append(eng)
+    # one replay pair per rank, shared by the rank's agents (reference: one buffer per process, Q15)
+    mem = PrioritizedReplayBuffer(BUFFER, ALPHA, device=device)
+    nmem = MultiStepReplayBuffer(BUFFER, N_STEP, GAMMA, device=device)
+    mem.device_rng = True
+    g = torch.Generator(device=device).manual_seed(seed0)
+    chunk = 10_000
+    for s in range(0, BUFFER, chunk):          # synthetic 84x84x4 uint8 frames, filled through add()
+        n = min(chunk, BUFFER - s)
+        for buf in (nmem, mem):
+            td = TensorDict({
+                "obs": torch.randint(0, 256, (n, *OBS), dtype=torch.uint8, device=device, generator=g),
+                "action": torch.randint(0, N_ACT, (n,), device=device, generator=g).float(),
+                "next_obs": torch.randint(0, 256, (n, *OBS), dtype=torch.uint8, device=device, generator=g),
+                "reward": torch.randn(n, device=device, generator=g),
+                "done": (torch.rand(n, device=device, generator=g) < 0.01).float(),
+            }, batch_size=[n])
+            if buf is nmem:
+                from agilerl_b200.components.replay_buffer import ReplayBuffer
+                ReplayBuffer.add(nmem, td)      # already-rolled synthetic n-step transitions
+                nmem.done_key = "done"
+            else:
+                buf.add(td)
+    # priorities initialised by one pass of |N(0,1)| + 1e-6
+    for s in range(0, BUFFER, 4096):
+        n = min(4096, BUFFER - s)
+        idx = torch.arange(s, s + n, device=device)
+        pri = torch.randn(n, device=device, generator=g).abs() + 1e-6
+        mem.update_priorities_device(idx, pri)
+    torch.cuda.synchronize(device)
+    return engines, mem, nmem
+
+
+def hp():
+    return dict(v_min=V_MIN, v_max=V_MAX, delta_z=(V_MAX - V_MIN) / (N_ATOMS - 1), lr=LR, tau=TAU, prior_eps=PRIOR_EPS)
+
+
+def fused_population_step(engines, mem, nmem, support):
+    last = None
+    for eng in engines:
+        last = eng.rainbow_fused_step(mem, nmem, B=B, beta=BETA, support=support, hp=hp(), gamma_n=GAMMA ** N_STEP)
+    return last
+
+
+def api_population_step(engines, mem, nmem, support, host_tr):
+    """The public-API path with host buffers (what train_off_policy.py:327-412 does per learn)."""
+    from agilerl_b200.compat import TensorDict
+    out = None
+    for eng in engines:
+        td = TensorDict({k: v for k, v in host_tr.items()}, batch_size=[NUM_ENVS])   # pinned host tensors
+        one = nmem.add(td)                      # H2D + n-step roll + ring write
+        if one is not None:
+            mem.add(one)                        # ring write + tree leaves
+        exp = mem.sample(B, BETA)               # tree sample + gather (materialised batch)
+        nexp = nmem.sample_from_indices(exp["idxs"].squeeze(1))
+        loss, _, pri, _ = eng.rainbow_learn([(nexp, GAMMA ** N_STEP, False)], B=B, support=support,
+                                            weights=exp["weights"].squeeze(1), weights_mode=1, hp=hp())
+        loss_f = loss.item()                    # D2H (the reference returns loss.item())
+        pri_np = pri.cpu().numpy()              # D2H priorities (np.ndarray like learn() returns)
+        mem.update_priorities(exp["idxs"], pri_np)
+        out = loss_f
+    return out
+
+
+def time_region(fn, steps, dist_on):
+    import torch.distributed as dist
+    if dist_on:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist_on:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+    return ms
+
+
+def conv1_roofline(eng, nmem, device):
+    """Dominant kernel = first conv layer of the online forward (igemm_kernel<128,32,...>): timed
+    alone with CUDA events on the launch stream; inputs are B random ring rows (ring >> L2)."""
+    from agilerl_b200 import _lib
+    lib = _lib.load()
+    desc = eng.layout.desc
+    L = desc.enc[0]
+    out = torch.empty(B * L.out_c * L.out_h * L.out_w, dtype=torch.float32, device=device)
+    ws = torch.empty(64 << 20, dtype=torch.uint8, device=device)
+    frames = nmem._fields[("obs",)]
+    flops = 2.0 * B * L.out_h * L.out_w * L.out_c * L.in_c * L.ksize * L.ksize
+    alg_bytes = B * desc.obs_elems + out.numel() * 4 + (L.out_c * L.in_c * L.ksize * L.ksize + L.out_c) * 4
+    times = []
+    stream = _lib.stream_ptr(torch.device(device))
+    for it in range(25):
+        idx = torch.randint(0, BUFFER, (B,), device=device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(lib.b2rl_encoder_layer_forward(ctypes.byref(desc), 0, eng.actor.params.data_ptr(), frames.data_ptr(),
+                                                  idx.data_ptr(), B, out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+        e1.record()
+        torch.cuda.synchronize()
+        if it >= 5:
+            times.append(e0.elapsed_time(e1))
+    ms = statistics.mean(times)
+    return flops, alg_bytes, ms
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference(steps, warmup, cores):
+    """The reference's CPU implementation of one gradient step, as restated by the oracle
+    (pure-Python list segment trees like the reference + torch-CPU learn): bounded sample."""
+    from oracle import learn as olearn, nets as onets, replay as oreplay
+    from oracle.segtree import PySegTree
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    n_buf = 4096                              # bounded replay (frames for 4096 slots = 0.46 GB of host RAM)
+    spec = onets.rainbow_spec(OBS, N_ACT)
+    from agilerl_b200.networks.init import init_state_dict
+    from agilerl_b200.networks.spec import FlatLayout, rainbow_spec
+    layout = FlatLayout(rainbow_spec(OBS, N_ACT, channel_size=(32, 32), kernel_size=(8, 4), stride_size=(4, 2),
+                                     obs_low=0.0, obs_high=255.0, obs_u8=True))
+    sd = init_state_dict(layout)
+    for k, e in layout.entries.items():
+        if e.buf == "eps":
+            sd[k] = torch.zeros(e.shape)
+    agent = olearn.OracleAgent(spec, sd, sd, batch_size=B, lr=LR, v_min=V_MIN, v_max=V_MAX)
+    agent.reset_noise()
+    mem = oreplay.OraclePER(n_buf, ALPHA, tree_cls=PySegTree)
+    nmem = oreplay.OracleReplay(n_buf)
+    g = torch.Generator().manual_seed(0)
+    for buf in (mem, nmem):
+        buf.add(dict(obs=torch.randint(0, 256, (n_buf, *OBS), dtype=torch.uint8, generator=g),
+                     action=torch.randint(0, N_ACT, (n_buf,), generator=g).float(),
+                     next_obs=torch.randint(0, 256, (n_buf, *OBS), dtype=torch.uint8, generator=g),
+                     reward=torch.randn(n_buf, generator=g), done=(torch.rand(n_buf, generator=g) < 0.01).float()))
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        exp = mem.sample(B, BETA)
+        nexp = nmem.gather(exp["idxs"].squeeze(1))
+        exp["weights"] = exp["weights"].squeeze(1)
+        loss, idxs, pri = agent.learn_rainbow(exp, nexp, per=True)
+        mem.update_priorities(idxs, pri)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return times
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = os.cpu_count() or 1
+    common_cfg = {"workload": "Rainbow-DQN learn step, synthetic 84x84x4 uint8, batch 256, PER+3-step+C51, pop=8 "
+                              "(BASELINE configs[1])", "pop": POP, "batch": B, "buffer": BUFFER, "n_actions": N_ACT,
+                  "atoms": N_ATOMS, "net": "conv[32,32] k[8,4] s[4,2] -> 2592 -> latent 32 -> noisy dueling head [64]",
+                  "shapes": "canonical ([B] weights, [B,1] reward/done); quirks Q1/Q2 off"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 10))     # bounded sample: ~1-3 s of CPU per gradient step
+        warm = max(1, min(args.warmup, 2))
+        times = cpu_reference(steps, warm, cores)
+        per_step = statistics.mean(times)
+        val = 1.0 / per_step                     # gradient-steps/s of ONE agent == population rate on one host
+        line = {"metric": "population gradient-steps/sec (Rainbow-DQN pop=8)", "value": val, "unit": "steps/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": per_step * 1e3 * POP,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "impl": "reference", "config": dict(common_cfg, parallelism="host cores, agents sequential"),
+                "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": "port",
+                                 "sample": f"{steps} gradient steps of one agent, B=256, replay bounded to 4096 slots, "
+                                           "pure-Python segment trees + torch-CPU learn (oracle restatement of the "
+                                           "reference; the reference itself cannot be installed on the box)"},
+                "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    device = f"cuda:{local_rank}"
+    dist_on = world > 1
+    if dist_on:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(device))
+    from agilerl_b200 import _lib
+    lib = _lib.load(require_cuda=True)
+
+    assert POP % world == 0, "population of 8 must divide over the ranks"
+    n_local = POP // world
+    engines, mem, nmem = build_rank(device, n_local, seed0=rank * n_local)
+    support = torch.linspace(V_MIN, V_MAX, N_ATOMS).to(device)
+
+    # ---- value: fused device path ------------------------------------------------------------
+    step_fn = lambda: fused_population_step(engines, mem, nmem, support)
+    for _ in range(max(args.warmup, 3)):
+        step_fn()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.b2rl_launch_count()
+    ms = time_region(step_fn, args.steps, dist_on)
+    launches = (lib.b2rl_launch_count() - l0)
+    clocks = sampler.stop() if rank == 0 else None
+    value = POP * args.steps / (ms / 1e3)
+
+    # ---- e2e: public API with host buffers ----------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        g = torch.Generator().manual_seed(123 + rank)
+        host_tr = {
+            "obs": torch.randint(0, 256, (NUM_ENVS, *OBS), dtype=torch.uint8, generator=g).pin_memory(),
+            "action": torch.randint(0, N_ACT, (NUM_ENVS,), generator=g).float().pin_memory(),
+            "next_obs": torch.randint(0, 256, (NUM_ENVS, *OBS), dtype=torch.uint8, generator=g).pin_memory(),
+            "reward": torch.randn(NUM_ENVS, generator=g).pin_memory(),
+            "done": (torch.rand(NUM_ENVS, generator=g) < 0.01).float().pin_memory(),
+        }
+        mem.device_rng = False                   # API path consumes torch's CPU RNG like the reference
+        api_fn = lambda: api_population_step(engines, mem, nmem, support, host_tr)
+        for _ in range(max(args.warmup, 3)):
+            api_fn()
+        ms_e2e = time_region(api_fn, args.steps, dist_on)
+        h2d = sum(v.numel() * v.element_size() for v in host_tr.values()) + B * 4 + B * 8      # + uniforms + p_alpha
+        d2h = 4 + B * 4
+        e2e = {"value": POP * args.steps / (ms_e2e / 1e3), "unit": "steps/s", "ms_per_step": ms_e2e / args.steps,
+               "h2d_bytes_per_step": h2d * n_local, "d2h_bytes_per_step": d2h * n_local}
+
+    if rank != 0:
+        if dist_on:
+            torch.distributed.destroy_process_group()
+        return
+
+    hbm_peak, tf_peak, peak_kind = peaks()
+    flops, kbytes, kms = conv1_roofline(engines[0], nmem, device)
+    achieved_tf = flops / (kms / 1e3) / 1e12
+    line = {
+        "metric": "population gradient-steps/sec (Rainbow-DQN pop=8)", "value": value, "unit": "steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(common_cfg, parallelism=f"pop{POP}/dp{world} ({n_local} agents per GPU, no data-path collective)",
+                       l2="inputs larger than L2: 11.3 GB replay ring per rank, fresh random rows every step"),
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "step_hbm": {"alg_bytes_per_grad_step": ALG_BYTES_PER_STEP,
+                     "achieved_gbs_per_gpu": ALG_BYTES_PER_STEP * value / world / 1e9,
+                     "frac_of_peak": ALG_BYTES_PER_STEP * value / world / 1e9 / hbm_peak, "peak_gbs": hbm_peak,
+                     "peak": peak_kind},
+        "roofline": {"kernel": "igemm_kernel<128,32,16,8,4> conv1 forward (4->32, k8 s4, B=256 ring rows)",
+                     "bound": "tensor", "achieved": achieved_tf, "peak": tf_peak, "unit": "TFLOP/s",
+                     "frac": achieved_tf / tf_peak, "traffic": None, "peak_kind": peak_kind,
+                     "flops_per_launch": flops, "alg_bytes_per_launch": kbytes, "ms_per_launch": kms,
+                     "note": "fp32 FFMA on CUDA cores (1e-5 parity); fraction is vs the measured dense bf16 tensor peak"},
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if not args.no_cpu_baseline and world == 1:
+        t = cpu_reference(3, 1, cores)
+        per = statistics.mean(t)
+        line["cpu_baseline"] = {"value": 1.0 / per, "unit": "steps/s", "cores": cores, "kind": "port",
+                                "sample": "3 gradient steps of one agent (B=256, replay bounded to 4096 slots), oracle "
+                                          "restatement of the reference: pure-Python segment trees + torch-CPU learn"}
+    print(json.dumps(line))
+    if dist_on:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

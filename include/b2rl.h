@@ -32,6 +32,8 @@ extern "C" {
 
 int b2rl_version(void);
 const char *b2rl_last_error(void);
+/* Number of CUDA kernels this library has launched in this process (bench.py: gpu_launches). */
+unsigned long long b2rl_launch_count(void);
 /* Device properties the host side sizes grids with (SM count, etc.). */
 int b2rl_device_sm_count(int device, int *out_host);
 
@@ -79,6 +81,19 @@ int b2rl_per_sample(const double *sum_tree, const double *min_tree, int64_t cap,
 int b2rl_per_sample_philox(const double *sum_tree, const double *min_tree, int64_t cap,
                            uint64_t seed, uint64_t offset, int64_t B, double beta, int64_t size,
                            int64_t *out_idx, float *out_w, void *stream);
+
+/* The fused sample step of the HBM-resident path (north star K1): one kernel does the sum-tree
+ * descent, the importance weights AND the gather of the sampled slots' n-step action / reward /
+ * done from the (ingest-rolled, replay_buffer.py:206-258) n-step ring.  Frames are not copied:
+ * the encoder's first-layer loader reads them from the ring through out_idx.  uniforms == NULL
+ * draws them from Philox(seed, offset).  *_ring are float32 [max_size] (the [max_size,1]
+ * storage columns). */
+int b2rl_per_sample_fused(const double *sum_tree, const double *min_tree, int64_t cap,
+                          const float *uniforms, uint64_t seed, uint64_t offset, int64_t B,
+                          double beta, int64_t size, const float *action_ring,
+                          const float *reward_ring, const float *done_ring, int64_t *out_idx,
+                          float *out_w, float *out_action, float *out_reward, float *out_done,
+                          void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Ring storage — ReplayBuffer.add / storage[indices] (replay_buffer.py:72-112, :126, :204, :345).
@@ -170,6 +185,13 @@ int b2rl_net_forward_q(const b2rl_net_desc *net_host, const float *params, const
                        int use_noise, const float *support, const void *obs,
                        const int64_t *row_idx, int64_t rows, float *q_out, int64_t *argmax_out,
                        void *workspace, size_t workspace_bytes, void *stream);
+
+/* Forward of ONE encoder layer (profiling / roofline hook: lets bench.py time the dominant
+ * contraction alone with CUDA events).  layer 0 reads observations (obs/row_idx as above), layer
+ * i>0 reads `input` = the previous layer's [rows, ...] fp32 activations.  out: rows x out elems. */
+int b2rl_encoder_layer_forward(const b2rl_net_desc *net_host, int layer, const float *params,
+                               const void *input, const int64_t *row_idx, int64_t rows, float *out,
+                               void *workspace, size_t workspace_bytes, void *stream);
 
 /* Scalars of one learn step (doubles are the Python floats of the reference, rounded to f32
  * inside the kernels exactly where torch rounds them). */
