@@ -16,6 +16,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "gemm.cuh"
 
 namespace b2rl {
@@ -80,7 +82,7 @@ static void carve_pass(Bump &b, const b2rl_net_desc &net, PassBufs &pb, int64_t 
 
 static size_t gemm_need(int64_t M, int64_t N, int64_t K) {
     if (M <= 0 || N <= 0 || K <= 0 || M > INT32_MAX) return 0;
-    return plan_gemm((int)M, (int)N, (int)K, M >= 4096, sm_count()).partial_floats;
+    return plan_gemm((int)M, (int)N, (int)K, use_big_tile(M), sm_count()).partial_floats;
 }
 // exact bound of the split-K scratch over every GEMM a pass can launch
 static size_t max_partial_floats(const b2rl_net_desc &net, int64_t rows, int64_t brows) {
@@ -91,7 +93,7 @@ static size_t max_partial_floats(const b2rl_net_desc &net, int64_t rows, int64_t
             const int64_t P = (int64_t)l.out_h * l.out_w, Kc = (int64_t)l.in_c * l.ksize * l.ksize;
             n = gemm_need(rows * P, l.out_c, Kc); if (n > m) m = n;
             n = gemm_need(rows / 2 * P, l.out_c, Kc); if (n > m) m = n;     // first layer runs per chunk
-            if (brows) { n = gemm_need(l.out_c, Kc + 1, brows * P); if (n > m) m = n; }
+            if (brows) { n = gemm_need(Kc + 1, l.out_c, brows * P); if (n > m) m = n; }
         } else {
             n = gemm_need(rows, l.out_c, l.in_c); if (n > m) m = n;
             n = gemm_need(rows / 2, l.out_c, l.in_c); if (n > m) m = n;
@@ -243,23 +245,33 @@ __global__ void ln_fwd_kernel(const float *__restrict__ z, const float *__restri
     }
 }
 
-// column sums for the LayerNorm affine gradients: dw[c] = sum_r gy*xhat, db[c] = sum_r gy
+// column sums for the LayerNorm affine gradients: dw[c] = sum_r gy*xhat, db[c] = sum_r gy.
+// 32 columns x 8 row-groups per CTA, fixed-order smem reduction over the row groups.
 __global__ void ln_affine_grad_kernel(const float *__restrict__ g, const float *__restrict__ z,
                                       const float *__restrict__ stats, const float *__restrict__ a,
                                       const float *__restrict__ pre, int act, float *__restrict__ dw,
                                       float *__restrict__ db, int64_t rows, int n, int accumulate) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n) return;
-    float sw = 0.f, sb = 0.f;
-    for (int64_t r = 0; r < rows; ++r) {
-        const int64_t o = r * n + c;
-        const float gy = g[o] * act_bwd(act, pre ? pre[o] : 0.f, a[o]);
-        const float xhat = (z[o] - stats[r * 2]) * stats[r * 2 + 1];
-        sw += gy * xhat;
-        sb += gy;
+    __shared__ float sw[8][33], sb[8][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cx;
+    float w = 0.f, b = 0.f;
+    if (c < n) {
+        for (int64_t r = ry; r < rows; r += 8) {
+            const int64_t o = r * n + c;
+            const float gy = g[o] * act_bwd(act, pre ? pre[o] : 0.f, a[o]);
+            const float xhat = (z[o] - stats[r * 2]) * stats[r * 2 + 1];
+            w += gy * xhat;
+            b += gy;
+        }
     }
-    dw[c] = accumulate ? dw[c] + sw : sw;
-    db[c] = accumulate ? db[c] + sb : sb;
+    sw[ry][cx] = w; sb[ry][cx] = b;
+    __syncthreads();
+    if (ry == 0 && c < n) {
+        float tw = 0.f, tb = 0.f;
+        for (int i = 0; i < 8; ++i) { tw += sw[i][cx]; tb += sb[i][cx]; }
+        dw[c] = accumulate ? dw[c] + tw : tw;
+        db[c] = accumulate ? db[c] + tb : tb;
+    }
 }
 
 // g (dL/da) -> dL/dz in place.
@@ -307,6 +319,18 @@ struct ObsChunk {          // first-layer input rows [row0, row0+rows) come from
 
 struct Scratch { float *partial; size_t floats; };
 
+// run f(std::integral_constant<int, ELEM>) for the element kind of an operand that may read
+// observations (only first-layer operands are ever not plain fp32)
+template <typename F>
+static int dispatch_elem(int kind, F &&f) {
+    switch (kind) {
+        case EL_U8: return f(std::integral_constant<int, EL_U8>{});
+        case EL_F32_NORM: return f(std::integral_constant<int, EL_F32_NORM>{});
+        default: return f(std::integral_constant<int, EL_F32>{});
+    }
+}
+using OpW = OpTraits<EL_F32, MAP_STRIDE, MAP_STRIDE, true, false>;     // weights [out, K], k contiguous
+
 static int layer_forward(const b2rl_net_desc &net, const b2rl_layer &l, const float *W, const float *bias,
                          const float *params, const float *x_prev, const ObsChunk *chunks, int n_chunks,
                          int64_t rows, const LayerBuf &lb, const Scratch &sc, cudaStream_t s) {
@@ -350,7 +374,19 @@ static int layer_forward(const b2rl_net_desc &net, const b2rl_layer &l, const fl
             epi.act = l.act;
             epi.pre_out = lb.pre ? lb.pre + row0 * oe : nullptr;
         }
-        int rc = launch_igemm<true, true>(A, Bm, epi, M, N, K, sc.partial, sc.floats, s);
+        int rc;
+        if (l.kind == B2RL_LAYER_CONV)
+            rc = dispatch_elem(A.elem_kind(), [&](auto ek) {
+                return launch_igemm<OpTraits<decltype(ek)::value, MAP_PIXEL, MAP_KERNEL, true, false>, OpW,
+                                    EpiTraits<EPI_STORE, MAP_PIXEL, MAP_STRIDE>>(A, Bm, epi, M, N, K, sc.partial,
+                                                                                   sc.floats, s);
+            });
+        else
+            rc = dispatch_elem(A.elem_kind(), [&](auto ek) {
+                return launch_igemm<OpTraits<decltype(ek)::value, MAP_STRIDE, MAP_STRIDE, true, false>, OpW,
+                                    EpiTraits<EPI_STORE, MAP_STRIDE, MAP_STRIDE>>(A, Bm, epi, M, N, K, sc.partial,
+                                                                                    sc.floats, s);
+            });
         if (rc != B2RL_OK) return rc;
         row0 += r;
     }
@@ -712,7 +748,7 @@ static int layer_backward(const b2rl_net_desc &net, const b2rl_layer &l, const f
         const float *z = lb.z + row_off * oe;
         const float *st = lb.stats + row_off * 2;
         if (l.ln == B2RL_LN_AFFINE) {
-            ln_affine_grad_kernel<<<(l.out_c + 127) / 128, 128, 0, s>>>(g_out, z, st, a, pre, l.act, grads + l.lnw_off,
+            ln_affine_grad_kernel<<<(l.out_c + 31) / 32, 256, 0, s>>>(g_out, z, st, a, pre, l.act, grads + l.lnw_off,
                                                                         grads + l.lnb_off, B, l.out_c, accumulate_grads);
             B2RL_LAUNCH_CHECK();
         }
@@ -740,17 +776,26 @@ static int layer_backward(const b2rl_net_desc &net, const b2rl_layer &l, const f
         if (l.kind == B2RL_LAYER_CONV) {
             const int P = l.out_h * l.out_w, KK = l.ksize * l.ksize;
             const int Kc = l.in_c * KK;
-            M = l.out_c; N = Kc + 1; K = (int)(B * P);
+            // dW^T[tap][co] = sum_pix im2col[tap][pix] * dOut[co][pix]: the im2col operand is the
+            // 128-row A tile (taps are hoisted per thread, one pixel decode per k-tile), dOut the
+            // 32-wide B tile; the extra row tap == Kc reads 1.0 and yields the bias gradient.
+            M = Kc + 1; N = l.out_c; K = (int)(B * P);
+            epi.kind = EPI_WGRAD_T;
             epi.wcols = Kc;
-            A.ptr = g_out; A.row = map_stride(P); A.red = map_pixel(P, l.out_w, (int64_t)l.out_c * P, l.out_w, 1);
             if (obs) {
-                Bm.ptr = obs->ptr; Bm.u8 = net.obs_u8; Bm.normalize = net.normalize; Bm.low = net.obs_low; Bm.high = net.obs_high;
-            } else Bm.ptr = x_in;
-            Bm.row = map_kernel(l.ksize, l.in_h * l.in_w, l.in_w);
-            Bm.red = map_pixel(P, l.out_w, (int64_t)l.in_c * l.in_h * l.in_w, l.stride * l.in_w, l.stride,
-                               obs ? obs->gather : nullptr);
-            Bm.ones_row = Kc;
-            rc = launch_igemm<true, false>(A, Bm, epi, M, N, K, sc.partial, sc.floats, s);
+                A.ptr = obs->ptr; A.u8 = net.obs_u8; A.normalize = net.normalize; A.low = net.obs_low; A.high = net.obs_high;
+            } else A.ptr = x_in;
+            A.row = map_kernel(l.ksize, l.in_h * l.in_w, l.in_w);
+            A.red = map_pixel(P, l.out_w, (int64_t)l.in_c * l.in_h * l.in_w, l.stride * l.in_w, l.stride,
+                              obs ? obs->gather : nullptr);
+            A.ones_row = Kc;
+            Bm.ptr = g_out; Bm.row = map_stride(P); Bm.red = map_pixel(P, l.out_w, (int64_t)l.out_c * P, l.out_w, 1);
+            rc = dispatch_elem(A.elem_kind(), [&](auto ek) {
+                return launch_igemm<OpTraits<decltype(ek)::value, MAP_KERNEL, MAP_PIXEL, true, true>,
+                                    OpTraits<EL_F32, MAP_STRIDE, MAP_PIXEL, true, false>,
+                                    EpiTraits<EPI_WGRAD_T, MAP_STRIDE, MAP_STRIDE>>(A, Bm, epi, M, N, K, sc.partial,
+                                                                                      sc.floats, s);
+            });
         } else {
             M = l.out_c; N = l.in_c + 1; K = (int)B;
             epi.wcols = l.in_c;
@@ -761,7 +806,12 @@ static int layer_backward(const b2rl_net_desc &net, const b2rl_layer &l, const f
             Bm.row = map_stride(1);
             Bm.red = map_stride(l.in_c, obs ? obs->gather : nullptr);
             Bm.ones_row = l.in_c;
-            rc = launch_igemm<false, false>(A, Bm, epi, M, N, K, sc.partial, sc.floats, s);
+            rc = dispatch_elem(Bm.elem_kind(), [&](auto ek) {
+                return launch_igemm<OpTraits<EL_F32, MAP_STRIDE, MAP_STRIDE, false, false>,
+                                    OpTraits<decltype(ek)::value, MAP_STRIDE, MAP_STRIDE, false, true>,
+                                    EpiTraits<EPI_WGRAD, MAP_STRIDE, MAP_STRIDE>>(A, Bm, epi, M, N, K, sc.partial,
+                                                                                    sc.floats, s);
+            });
         }
         if (rc != B2RL_OK) return rc;
     }
@@ -779,12 +829,18 @@ static int layer_backward(const b2rl_net_desc &net, const b2rl_layer &l, const f
             epi.kind = EPI_ATOMIC; epi.out = g_in;
             epi.om = map_pixel(P, l.out_w, (int64_t)l.in_c * l.in_h * l.in_w, l.stride * l.in_w, l.stride);
             epi.on = map_kernel(l.ksize, l.in_h * l.in_w, l.in_w);
-            rc = launch_igemm<false, false>(A, Bm, epi, (int)(B * P), Kc, l.out_c, nullptr, 0, s);
+            rc = launch_igemm<OpTraits<EL_F32, MAP_PIXEL, MAP_STRIDE, false, false>,
+                              OpTraits<EL_F32, MAP_STRIDE, MAP_STRIDE, false, false>,
+                              EpiTraits<EPI_ATOMIC, MAP_PIXEL, MAP_KERNEL>>(A, Bm, epi, (int)(B * P), Kc, l.out_c, nullptr,
+                                                                           0, s);
         } else {
             A.ptr = g_out; A.row = map_stride(l.out_c); A.red = map_stride(1);
             Bm.ptr = W; Bm.row = map_stride(1); Bm.red = map_stride(l.in_c);
             epi.out = g_in; epi.om = map_stride(l.in_c); epi.on = map_stride(1); epi.accumulate = accumulate_gin ? 1 : 0;
-            rc = launch_igemm<true, false>(A, Bm, epi, (int)B, l.in_c, l.out_c, sc.partial, sc.floats, s);
+            rc = launch_igemm<OpTraits<EL_F32, MAP_STRIDE, MAP_STRIDE, true, false>,
+                              OpTraits<EL_F32, MAP_STRIDE, MAP_STRIDE, false, false>,
+                              EpiTraits<EPI_STORE, MAP_STRIDE, MAP_STRIDE>>(A, Bm, epi, (int)B, l.in_c, l.out_c, sc.partial,
+                                                                           sc.floats, s);
         }
         if (rc != B2RL_OK) return rc;
     }

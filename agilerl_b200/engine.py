@@ -12,8 +12,8 @@ from collections import OrderedDict
 
 import torch
 
-from .. import _lib
-from ..networks.spec import FlatLayout
+from . import _lib
+from .networks.spec import FlatLayout
 
 
 class NetBuffers:

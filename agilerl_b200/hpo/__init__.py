@@ -1,0 +1,4 @@
+from .mutation import Mutations
+from .tournament import TournamentSelection
+
+__all__ = ["Mutations", "TournamentSelection"]

@@ -1,0 +1,205 @@
+"""``Mutations`` — drop-in for agilerl/hpo/mutation.py:168-1207 for single-agent value-based agents.
+
+Five mutation kinds with the reference's relative probabilities and RNG use (``self.rng =
+np.random.default_rng(rand_seed)`` :303, ``rng.choice`` over the option list :335-339):
+none / architecture / parameters / activation / RL hyper-parameter.  After architecture and
+activation mutations the shared networks (``actor_target``) are rebuilt from the mutated
+evaluation network and loaded with its weights (``reinit_shared_networks`` :104-164) and the
+optimiser restarts (``reinit_optimizers``).  All of it is host-side control; the Gaussian
+parameter mutation edits the flat HBM parameter buffer in place through named views."""
+from __future__ import annotations
+
+import random
+import warnings
+
+import numpy as np
+import torch
+
+
+def set_global_seed(seed: int | None) -> None:
+    """mutation.py:41-54 (fastrand is not in the image; numpy / torch / random are seeded)."""
+    if seed is None:
+        return
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    random.seed(seed)
+
+
+class Mutations:
+    def __init__(self, no_mutation: float, architecture: float, new_layer_prob: float, parameters: float,
+                 activation: float, rl_hp: float, mutation_sd: float = 0.1, activation_selection: list | None = None,
+                 mutate_elite: bool = True, rand_seed: int | None = None, device: str = "cuda", accelerator=None) -> None:
+        if activation_selection is None:
+            activation_selection = ["ReLU", "ELU", "GELU"]
+        for name, v in (("no mutation", no_mutation), ("architecture mutation", architecture),
+                        ("parameters mutation", parameters), ("activation mutation", activation),
+                        ("reinforcement learning hyperparameter mutation", rl_hp)):
+            assert isinstance(v, (float, int)), f"Probability of {name} must be a float or integer."
+            assert v >= 0, f"Probability of {name} must be greater than or equal to zero."
+        assert isinstance(new_layer_prob, (float, int)), (
+            "Probability of new layer architecture mutation must be a float or integer.")
+        assert 1 >= new_layer_prob >= 0, (
+            "Probability of new layer architecture mutation must be between zero and one (inclusive).")
+        assert mutation_sd >= 0, "Mutation strength must be greater than or equal to zero."
+        assert isinstance(mutation_sd, (float, int)), "Mutation strength must be a float or integer."
+        assert isinstance(mutate_elite, bool), "Mutate elite must be boolean value True or False."
+        assert isinstance(rand_seed, int) or rand_seed is None, "Random seed must be an integer or None."
+        if isinstance(rand_seed, int):
+            assert rand_seed >= 0, "Random seed must be greater than or equal to zero."
+        if accelerator is not None:
+            raise NotImplementedError("accelerate is replaced by one-agent-per-GPU sharding")
+        set_global_seed(rand_seed)
+        self.rng = np.random.default_rng(rand_seed)
+        self.no_mut, self.architecture_mut, self.new_layer_prob = no_mutation, architecture, new_layer_prob
+        self.parameters_mut, self.activation_mut, self.rl_hp_mut = parameters, activation, rl_hp
+        self.mutation_sd, self.activation_selection = mutation_sd, activation_selection
+        self.mutate_elite, self.device, self.accelerator = mutate_elite, device, None
+        self.mut_options, self.mut_proba = self._get_mutations_options()
+        self.pretraining_mut_options, self.pretraining_mut_proba = self._get_mutations_options(pretraining=True)
+
+    def _get_mutations_options(self, pretraining: bool = False):
+        """mutation.py:586-621."""
+        opts = [(self.no_mutation, self.no_mut), (self.architecture_mutate, self.architecture_mut),
+                (self.parameter_mutation, self.parameters_mut), (self.activation_mutation, self.activation_mut),
+                (self.rl_hyperparam_mutation, self.rl_hp_mut)]
+        if pretraining:
+            opts[0] = (self.no_mutation, 0)
+        funcs, probs = zip(*opts)
+        total = sum(probs)
+        if total == 0:
+            return [self.no_mutation], [1.0]
+        return list(funcs), [p / total for p in probs]
+
+    def mutation(self, population, pre_training_mut: bool = False):
+        """mutation.py:311-362."""
+        options = self.pretraining_mut_options if pre_training_mut else self.mut_options
+        proba = self.pretraining_mut_proba if pre_training_mut else self.mut_proba
+        choice = list(self.rng.choice(options, len(population), p=proba))
+        if not self.mutate_elite:
+            choice[0] = self.no_mutation
+        out = []
+        for mut, individual in zip(choice, population):
+            individual = mut(individual)
+            individual.mutation_hook()
+            out.append(individual)
+        return out
+
+    # -- the five kinds -----------------------------------------------------------------------------
+    def no_mutation(self, individual):
+        individual.mut = "None"
+        return individual
+
+    def _reinit_shared(self, individual):
+        """reinit_shared_networks (mutation.py:104-164): rebuild each shared network from the
+        mutated evaluation network's init_dict and load its weights."""
+        if individual.mut == "None":
+            return individual
+        for group in individual.registry.groups:
+            if group.shared_networks is None:
+                continue
+            eval_net = getattr(individual, group.eval_network)
+            for shared_name in group.shared_networks:
+                shared = type(eval_net)(**eval_net.init_dict)
+                shared.load_state_dict(eval_net.state_dict(), strict=False)
+                setattr(individual, shared_name, shared)
+        return individual
+
+    def architecture_mutate(self, individual):
+        """mutation.py:373-411 + _architecture_mutate_single :829-885."""
+        registry = individual.registry
+        policy = getattr(individual, registry.policy())
+        if not policy.mutation_methods:
+            individual.mut = "None"
+            return individual
+        method = policy.sample_mutation_method(self.new_layer_prob, self.rng)
+        method()
+        applied = policy.last_mutation_attr
+        individual.mut = applied if applied is not None else "None"
+        self._reinit_shared(individual)
+        individual.reinit_optimizers()
+        return individual
+
+    def rl_hyperparam_mutation(self, individual):
+        """mutation.py:413-452."""
+        hp_config = individual.registry.hp_config
+        if not hp_config:
+            individual.mut = "None"
+            return individual
+        attr, param = hp_config.sample()
+        if param.value is None:
+            param.value = getattr(individual, attr)
+        new_value = param.mutate()
+        setattr(individual, attr, new_value)
+        if attr in individual.get_lr_names():
+            individual.reinit_optimizers()
+        individual.mut = attr
+        return individual
+
+    def _permutate_activation(self, network):
+        """mutation.py _permutate_activation: pick a different activation from the selection."""
+        current = network.activation
+        choices = [a for a in self.activation_selection if a != current]
+        if not choices:
+            return network
+        network.change_activation(str(self.rng.choice(choices)), output=False)
+        return network
+
+    def activation_mutation(self, individual):
+        """mutation.py:454-519."""
+        if individual.algo in ["PPO", "DDPG", "TD3", "IPPO", "MADDPG", "MATD3", "GRPO"]:
+            warnings.warn(f"Activation mutations are not supported for {individual.algo}.", stacklevel=2)
+            individual.mut = "None"
+            return individual
+        for group in individual.registry.groups:
+            net = getattr(individual, group.eval_network)
+            if net.activation is None:
+                individual.mut = "None"
+                return individual
+            self._permutate_activation(net)
+        individual.mut = "act"
+        self._reinit_shared(individual)
+        individual.reinit_optimizers()
+        return individual
+
+    def parameter_mutation(self, individual):
+        """mutation.py:521-584."""
+        group = individual.registry.policy(return_group=True)
+        policy = getattr(individual, group.eval_network)
+        self._gaussian_parameter_mutation(policy)
+        for shared in group.shared_networks or []:
+            getattr(individual, shared).load_state_dict(policy.state_dict(), strict=False)
+        individual.reinit_optimizers()
+        individual.mut = "param"
+        return individual
+
+    def _gaussian_parameter_mutation(self, network):
+        """mutation.py:733-827, applied in place to the 2-D weight views of the flat buffer."""
+        mut_strength, frac = self.mutation_sd, 0.1
+        super_strength, super_prob = 10, 0.05
+        reset_prob, mag_limit = super_prob + 0.05, 1000000
+        views = {k: v for k, v in network.named_parameters()}
+        keys = [k for k, v in views.items() if "norm" not in k and "lstm" not in k and v.ndim == 2]
+        how_many = int(self.rng.integers(1, len(keys) + 1))
+        for key in self.rng.choice(keys, how_many, replace=False):
+            W = views[str(key)]
+            n_mut = int(np.ceil(frac * W.shape[0] * W.shape[1]))
+            if n_mut < 1:
+                continue
+            rows = torch.tensor(self.rng.integers(0, W.shape[0], size=n_mut), dtype=torch.long, device=W.device)
+            cols = torch.tensor(self.rng.integers(0, W.shape[1], size=n_mut), dtype=torch.long, device=W.device)
+            r = torch.tensor(self.rng.uniform(0, 1, size=n_mut), dtype=W.dtype, device=W.device)
+            cur = W[rows, cols]
+            new = cur.clone()
+            m_super, m_reset = r < super_prob, (r >= super_prob) & (r < reset_prob)
+            m_norm = r >= reset_prob
+            if m_super.sum() > 0:
+                std = (super_strength * cur[m_super]).abs()
+                new[m_super] = cur[m_super] + torch.normal(mean=torch.zeros_like(std), std=std)
+            if m_reset.sum() > 0:
+                k = int(m_reset.sum())
+                new[m_reset] = torch.normal(mean=torch.zeros(k, device=W.device), std=torch.ones(k, device=W.device))
+            if m_norm.sum() > 0:
+                std = (mut_strength * cur[m_norm]).abs()
+                new[m_norm] = cur[m_norm] + torch.normal(mean=torch.zeros_like(std), std=std)
+            W[rows, cols] = new.clamp(min=-mag_limit, max=mag_limit)
+        return network

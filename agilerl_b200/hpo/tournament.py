@@ -1,0 +1,159 @@
+"""``TournamentSelection`` — drop-in for agilerl/hpo/tournament.py:9-119, plus the population-
+sharded mode of this build.
+
+Single process (or ``sharded=False``): exactly the reference — rank by the mean of the last
+``eval_loop`` fitnesses with a double argsort (:63-65), keep the elite (:66-69), draw
+``tournament_size`` candidates per remaining slot from the GLOBAL ``np.random`` stream and clone
+the best-ranked (:41-51, :104-119).
+
+Sharded (one process per GPU, agents [r*n, (r+1)*n) of the population on rank r): ONE collective —
+an all-gather of (mean fitness, agent index) per agent — after which every rank computes the same
+ranking and the same tournament draws (a ``RandomState`` derived from a shared seed and the
+generation counter), so no plan needs broadcasting.  A winner that lives on another rank is moved
+with point-to-point sends of its flat parameter / epsilon / Adam buffers plus a small pickled
+architecture description (replacing the reference's disk-checkpoint transport,
+utils/utils.py:756-782).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist if (dist.is_available() and dist.is_initialized()) else None
+
+
+class TournamentSelection:
+    def __init__(self, tournament_size: int, elitism: bool, population_size: int, eval_loop: int,
+                 sharded: bool | None = None, seed: int = 0) -> None:
+        assert tournament_size > 0, "Tournament size must be greater than zero."
+        assert isinstance(elitism, bool), "Elitism must be boolean value True or False."
+        assert population_size > 0, "Population size must be greater than zero."
+        assert eval_loop > 0, "Evo step must be greater than zero."
+        self.tournament_size = tournament_size
+        self.elitism = elitism
+        self.population_size = population_size
+        self.eval_loop = eval_loop
+        self.language_model = None
+        self.sharded = sharded
+        self.seed = seed
+        self.generation = 0
+
+    # -- reference arithmetic -----------------------------------------------------------------------
+    def _tournament(self, fitness_values, rng=None) -> int:
+        """tournament.py:41-51."""
+        rng = np.random if rng is None else rng
+        selection = rng.randint(0, len(fitness_values), size=self.tournament_size)
+        selection_values = [fitness_values[i] for i in selection]
+        return selection[np.argmax(selection_values)]
+
+    def _elitism(self, population):
+        """tournament.py:53-69."""
+        last_fitness = [np.mean(indi.fitness[-self.eval_loop:]) for indi in population]
+        rank = np.argsort(last_fitness).argsort()
+        max_id = max([ind.index for ind in population])
+        model = population[int(np.argsort(rank)[-1])]
+        elite = model.clone()
+        return elite, rank, max_id
+
+    def select(self, population):
+        d = _dist()
+        sharded = self.sharded if self.sharded is not None else (d is not None and d.get_world_size() > 1)
+        if sharded and d is not None and d.get_world_size() > 1:
+            return self._select_sharded(population, d)
+        return self._select_standard_agents(population)
+
+    def _select_standard_agents(self, population):
+        """tournament.py:91-119."""
+        elite, rank, max_id = self._elitism(population)
+        new_population = []
+        if self.elitism:
+            new_population.append(elite.clone(wrap=False))
+            selection_size = self.population_size - 1
+        else:
+            selection_size = self.population_size
+        for _ in range(selection_size):
+            max_id += 1
+            actor_parent = population[self._tournament(rank)]
+            new_population.append(actor_parent.clone(max_id, wrap=False))
+        return elite, new_population
+
+    # -- sharded population -------------------------------------------------------------------------
+    def plan(self, fitness: np.ndarray, indices: np.ndarray):
+        """Deterministic selection plan from the gathered (fitness, index) vectors: identical on
+        every rank.  -> (elite_pos, [(parent_pos, new_index)] for every slot of the new population)."""
+        rank = np.argsort(fitness).argsort()
+        max_id = int(indices.max())
+        elite_pos = int(np.argsort(rank)[-1])
+        rng = np.random.RandomState((self.seed * 1_000_003 + self.generation) % (2 ** 31 - 1))
+        slots = []
+        n = self.population_size
+        if self.elitism:
+            slots.append((elite_pos, int(indices[elite_pos])))
+            n -= 1
+        for _ in range(n):
+            max_id += 1
+            slots.append((int(self._tournament(rank, rng)), max_id))
+        return elite_pos, slots
+
+    def _select_sharded(self, population, d):
+        world, me = d.get_world_size(), d.get_rank()
+        n_local = len(population)
+        assert n_local * world == self.population_size, "population_size must equal world_size * local agents"
+        dev = getattr(population[0], "_dev", None) or torch.device("cpu")
+        if d.get_backend() == "gloo":
+            dev = torch.device("cpu")
+        local = torch.tensor([[float(np.mean(a.fitness[-self.eval_loop:])), float(a.index)] for a in population],
+                             dtype=torch.float64, device=dev)
+        gathered = [torch.empty_like(local) for _ in range(world)]
+        d.all_gather(gathered, local)                              # the single collective of a generation
+        g = torch.cat(gathered).cpu().numpy()
+        fitness, indices = g[:, 0], g[:, 1].astype(np.int64)
+        elite_pos, slots = self.plan(fitness, indices)
+        self.generation += 1
+        new_local, elite = [], None
+        for slot, (parent, new_index) in enumerate(slots):
+            dst, src = slot // n_local, parent // n_local
+            keep_index = self.elitism and slot == 0
+            if src == me and dst == me:
+                p = population[parent % n_local]
+                child = p.clone(wrap=False) if keep_index else p.clone(new_index, wrap=False)
+            elif src == me:
+                self._send_agent(population[parent % n_local], dst, d)
+                child = None
+            elif dst == me:
+                child = self._recv_agent(type(population[0]), src, d, population[0])
+                if not keep_index:
+                    child.index = new_index
+            else:
+                child = None
+            if dst == me:
+                new_local.append(child)
+                if slot == 0 and self.elitism:
+                    elite = child
+        if elite is None:      # the elite lives on another rank: expose the local best for logging
+            elite = max(population, key=lambda a: np.mean(a.fitness[-self.eval_loop:]))
+        self.last_plan = (elite_pos, slots)
+        return elite, new_local
+
+    @staticmethod
+    def _send_agent(agent, dst: int, d) -> None:
+        meta, tensors = agent.export_state()
+        d.send_object_list([meta, [tuple(t.shape) for t in tensors], [str(t.dtype) for t in tensors]], dst=dst)
+        for t in tensors:
+            d.send(t.contiguous(), dst=dst)
+
+    @staticmethod
+    def _recv_agent(cls, src: int, d, like):
+        box = [None, None, None]
+        d.recv_object_list(box, src=src)
+        meta, shapes, dtypes = box
+        dev = torch.device("cpu") if d.get_backend() == "gloo" else getattr(like, "_dev", torch.device("cpu"))
+        tensors = []
+        for shape, dt in zip(shapes, dtypes):
+            t = torch.empty(shape, dtype=getattr(torch, dt.split(".")[-1]), device=dev)
+            d.recv(t, src=src)
+            tensors.append(t)
+        return cls.from_state(meta, tensors, like)

@@ -1,0 +1,3 @@
+from .train_off_policy import train_off_policy
+
+__all__ = ["train_off_policy"]

@@ -99,7 +99,7 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------------------------
 def build_rank(device, n_agents, seed0):
-    from agilerl_b200.algorithms._engine import LearnEngine, NetBuffers
+    from agilerl_b200.engine import LearnEngine, NetBuffers
     from agilerl_b200.compat import TensorDict
     from agilerl_b200.components import MultiStepReplayBuffer, PrioritizedReplayBuffer
     from agilerl_b200.networks.init import init_state_dict

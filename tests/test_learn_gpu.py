@@ -17,7 +17,7 @@ def _sd(g, tag):
 
 
 def _engine(spec, g):
-    from agilerl_b200.algorithms._engine import LearnEngine, NetBuffers
+    from agilerl_b200.engine import LearnEngine, NetBuffers
     from agilerl_b200.networks.spec import FlatLayout
     layout = FlatLayout(spec)
     actor, target = NetBuffers(layout, "cuda"), NetBuffers(layout, "cuda")
@@ -88,7 +88,7 @@ def test_rainbow_learn_golden_canonical_full_state():
     np.testing.assert_allclose(loss.item(), float(g["loss"]), **LOSS_TOL)
     # gradients (after clip_grad_norm_) per tensor, names as in the reference state_dict
     gref = _sd(g, "grad")
-    from agilerl_b200.algorithms._engine import NetBuffers
+    from agilerl_b200.engine import NetBuffers
     gv = NetBuffers(layout, "cuda"); gv.params.copy_(eng.grads)
     for k, ref in gref.items():
         got = gv.view(k).cpu()
@@ -136,7 +136,7 @@ def test_rainbow_learn_golden_variants(name, kw):
     B = int(g["B"])
     spec = _small_spec()
     ospec = onets.rainbow_spec((3, 20, 20), 4, (8, 16), (4, 3), (2, 1), 16, (32,))
-    from agilerl_b200.algorithms._engine import LearnEngine, NetBuffers
+    from agilerl_b200.engine import LearnEngine, NetBuffers
     from agilerl_b200.networks.spec import FlatLayout
     layout = FlatLayout(spec)
     gen = torch.Generator().manual_seed(123)
@@ -187,7 +187,7 @@ def test_rainbow_vector_obs_golden():
     np.testing.assert_allclose(pri.cpu().numpy(), g["priorities"], **LOSS_TOL)
     np.testing.assert_allclose(loss.item(), float(g["loss"]), **LOSS_TOL)
     gref = _sd(g, "grad")
-    from agilerl_b200.algorithms._engine import NetBuffers
+    from agilerl_b200.engine import NetBuffers
     gv = NetBuffers(layout, "cuda"); gv.params.copy_(eng.grads)
     for k, ref in gref.items():
         s = max(ref.abs().max().item(), 1e-6)
@@ -205,7 +205,7 @@ def test_dqn_learn_golden(double):
     np.testing.assert_allclose(loss.item(), float(g["loss"]), **LOSS_TOL)
     a1, t0 = _sd(g, "actor1"), _sd(g, "target0")
     a0 = _sd(g, "actor0")
-    from agilerl_b200.algorithms._engine import NetBuffers
+    from agilerl_b200.engine import NetBuffers
     gv = NetBuffers(layout, "cuda"); gv.params.copy_(eng.grads)
     for k in a1:
         p1 = eng.actor.view(k).cpu()
@@ -223,7 +223,7 @@ def test_northstar_b16_golden():
     head [64], 6 actions, 51 atoms) — outputs only."""
     from oracle import learn as olearn, nets as onets
     from agilerl_b200.networks.spec import rainbow_spec, FlatLayout
-    from agilerl_b200.algorithms._engine import LearnEngine, NetBuffers
+    from agilerl_b200.engine import LearnEngine, NetBuffers
     g = load_golden("rainbow_northstar_b16.npz")
     B = int(g["B"])
     spec = rainbow_spec((4, 84, 84), 6, channel_size=(32, 32), kernel_size=(8, 4), stride_size=(4, 2),

@@ -1,0 +1,94 @@
+"""CPU, world_size 2 over gloo: the population-sharded tournament (one fitness all-gather, same
+plan on every rank, point-to-point move of winners) and the no-collective learn sharding."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class FakeAgent:
+    """Host-only agent exposing what the sharded tournament needs (fitness, index, clone,
+    export_state / from_state) with CPU tensors standing in for the flat HBM buffers."""
+    device = "cpu"
+
+    def __init__(self, index, weights=None, fitness=None):
+        self.index = index
+        self.fitness = list(fitness or [])
+        self.w = torch.full((16,), float(index)) if weights is None else weights
+
+    def clone(self, index=None, wrap=True):
+        return FakeAgent(self.index if index is None else index, self.w.clone(), self.fitness)
+
+    def export_state(self):
+        return {"index": self.index, "fitness": self.fitness}, [self.w]
+
+    @classmethod
+    def from_state(cls, meta, tensors, like):
+        return cls(meta["index"], tensors[0].clone(), meta["fitness"])
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from agilerl_b200.hpo.tournament import TournamentSelection
+    n_local, pop_size = 2, 2 * world
+    fitness = {0: 1.0, 1: 9.0, 2: 5.0, 3: 3.0}
+    results = []
+    ts = TournamentSelection(2, True, pop_size, 1, seed=7)
+    pop = [FakeAgent(rank * n_local + i, fitness=[fitness[rank * n_local + i]]) for i in range(n_local)]
+    for gen in range(3):
+        elite, new_pop = ts.select(pop)
+        elite_pos, slots = ts.last_plan
+        results.append({"plan": slots, "elite_pos": elite_pos,
+                        "local": [(a.index, float(a.w[0]), a.fitness) for a in new_pop]})
+        pop = new_pop
+        for a in pop:                              # new generation's fitness depends on lineage only
+            a.fitness = a.fitness + [float(a.w[0]) + gen]
+    out[rank] = results
+    dist.destroy_process_group()
+
+
+def test_sharded_tournament_world2_gloo():
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    r0, r1 = out[0], out[1]
+    for g0, g1 in zip(r0, r1):
+        assert g0["plan"] == g1["plan"] and g0["elite_pos"] == g1["elite_pos"]     # same plan everywhere
+    # generation 0: fitness [1, 9, 5, 3] -> elite is global position 1 (index 1, on rank 0)
+    assert r0[0]["elite_pos"] == 1
+    plan = r0[0]["plan"]
+    assert plan[0] == (1, 1)                                       # elitism keeps the index
+    assert [ni for _, ni in plan[1:]] == [4, 5, 6]                 # fresh indices max_id+1...
+    # every slot carries its parent's weights (w == parent's original index), wherever it lived
+    new = r0[0]["local"] + r1[0]["local"]
+    for (parent, new_index), (idx, w0, fit) in zip(plan, new):
+        assert idx == new_index and w0 == float(parent)
+    # the plan matches the single-process oracle arithmetic given the same RandomState
+    from agilerl_b200.hpo.tournament import TournamentSelection
+    ts = TournamentSelection(2, True, 4, 1, seed=7)
+    _, ref = ts.plan(np.array([1.0, 9.0, 5.0, 3.0]), np.array([0, 1, 2, 3]))
+    assert ref == plan
+
+
+def test_plan_is_rank_invariant_and_ranks_by_mean_fitness():
+    from agilerl_b200.hpo.tournament import TournamentSelection
+    ts = TournamentSelection(3, False, 8, 3, seed=1)
+    fit = np.array([3.0, 1.0, 8.0, 2.0, 7.0, 5.0, 4.0, 6.0])
+    idx = np.arange(10, 18)
+    a = ts.plan(fit, idx)
+    b = TournamentSelection(3, False, 8, 3, seed=1).plan(fit, idx)
+    assert a == b and a[0] == 2 and len(a[1]) == 8
+    assert [n for _, n in a[1]] == list(range(18, 26))
+    # winners are never the worst-ranked of their draws: with tournament_size 3 the worst agent
+    # (position 1) can only win if drawn three times
+    assert sum(1 for p, _ in a[1] if p == 1) <= 1
