@@ -61,15 +61,15 @@ def test_rainbow_api_learn_matches_oracle_driver_and_canonical_shapes(monkeypatc
     from agilerl_b200.components import MultiStepReplayBuffer, PrioritizedReplayBuffer, Sampler
     from oracle import learn as olearn, nets as onets
     obs_space, act_space = _spaces()
-    torch.manual_seed(0)
-    agent = RainbowDQN(obs_space, act_space, net_config=dict(NET), batch_size=16, v_min=-10.0, v_max=10.0, lr=1e-3)
-    assert agent.algo == "Rainbow DQN" and agent.action_dim == 4
-    mem, nmem = PrioritizedReplayBuffer(128, 0.6), MultiStepReplayBuffer(128, 3, 0.99)
-    _fill(agent, mem, nmem, VecEnv((3, 20, 20), 4, image=True))
-    s, ns = Sampler(memory=mem), Sampler(memory=nmem)
-    assert s.per and ns.n_step
     ospec = onets.rainbow_spec((3, 20, 20), 4, (8, 16), (4, 3), (2, 1), 16, (32,))
     for driver_shapes in (True, False):
+        torch.manual_seed(0)          # fresh agent (fresh Adam state) per case, like the oracle side
+        agent = RainbowDQN(obs_space, act_space, net_config=dict(NET), batch_size=16, v_min=-10.0, v_max=10.0, lr=1e-3)
+        assert agent.algo == "Rainbow DQN" and agent.action_dim == 4
+        mem, nmem = PrioritizedReplayBuffer(128, 0.6), MultiStepReplayBuffer(128, 3, 0.99)
+        _fill(agent, mem, nmem, VecEnv((3, 20, 20), 4, image=True))
+        s, ns = Sampler(memory=mem), Sampler(memory=nmem)
+        assert s.per and ns.n_step
         exp = s.sample(16, agent.beta)
         nexp = ns.sample(exp["idxs"] if driver_shapes else exp["idxs"].squeeze(1))
         if not driver_shapes:
@@ -87,9 +87,11 @@ def test_rainbow_api_learn_matches_oracle_driver_and_canonical_shapes(monkeypatc
         assert abs(loss - oloss) <= 1e-5 * scale, (driver_shapes, loss, oloss)
         np.testing.assert_allclose(pri, opri, rtol=1e-5, atol=1e-5 * scale)
         mem.update_priorities(idxs, pri)
-        for k in oa.pkeys:     # parameters after the step
-            np.testing.assert_allclose(agent.actor.state_dict()[k].cpu().numpy(), oa.actor[k].detach().numpy(),
-                                       rtol=0, atol=2e-4, err_msg=k)
+        for k in oa.pkeys:     # parameters after the step (where Adam's first step has a clear sign)
+            mask = oa.last_grads[k].abs() > 1e-5
+            if mask.any():
+                diff = (agent.actor.state_dict()[k].cpu() - oa.actor[k].detach())[mask].abs().max().item()
+                assert diff <= 2e-5, (driver_shapes, k, diff)
 
 
 def test_learn_variants_and_return_types():
