@@ -99,26 +99,21 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------------------------
 def build_rank(device, n_agents, seed0):
-    from agilerl_b200.engine import LearnEngine, NetBuffers
-    from agilerl_b200.compat import TensorDict
+    from agilerl_b200.algorithms import RainbowDQN
+    from agilerl_b200.compat import TensorDict, spaces
     from agilerl_b200.components import MultiStepReplayBuffer, PrioritizedReplayBuffer
-    from agilerl_b200.networks.init import init_state_dict
-    from agilerl_b200.networks.spec import FlatLayout, rainbow_spec
 
-    spec = rainbow_spec(OBS, N_ACT, channel_size=(32, 32), kernel_size=(8, 4), stride_size=(4, 2), latent_dim=32,
-                        hidden_size=(64,), num_atoms=N_ATOMS, obs_low=0.0, obs_high=255.0, obs_u8=True)
-    engines = []
+    obs_space = spaces.Box(0, 255, OBS, np.uint8)
+    act_space = spaces.Discrete(N_ACT)
+    net_config = {"encoder_config": {"channel_size": [32, 32], "kernel_size": [8, 4], "stride_size": [4, 2]},
+                  "head_config": {"hidden_size": [64]}, "latent_dim": 32}
+    agents = []
     for a in range(n_agents):
         torch.manual_seed(seed0 + a)
-        layout = FlatLayout(spec)
-        sd = init_state_dict(layout)
-        actor, target = NetBuffers(layout, device), NetBuffers(layout, device)
-        actor.load_state_dict(sd, strict=False)
-        target.load_state_dict(sd, strict=False)
-        eng = LearnEngine(layout, actor, target)
-        eng.philox_seed = 0xB200 + seed0 + a
-        eng.reset_noise(actor); eng.reset_noise(target)
-        engines.append(eng)
+        agents.append(RainbowDQN(obs_space, act_space, index=seed0 + a, net_config=dict(net_config), batch_size=B, lr=LR,
+                                 gamma=GAMMA, tau=TAU, beta=BETA, prior_eps=PRIOR_EPS, num_atoms=N_ATOMS, v_min=V_MIN,
+                                 v_max=V_MAX, n_step=N_STEP, device=device))
+    engines = agents
     # one replay pair per rank, shared by the rank's agents (reference: one buffer per process, Q15)
     mem = PrioritizedReplayBuffer(BUFFER, ALPHA, device=device)
     nmem = MultiStepReplayBuffer(BUFFER, N_STEP, GAMMA, device=device)
@@ -155,29 +150,30 @@ def hp():
     return dict(v_min=V_MIN, v_max=V_MAX, delta_z=(V_MAX - V_MIN) / (N_ATOMS - 1), lr=LR, tau=TAU, prior_eps=PRIOR_EPS)
 
 
-def fused_population_step(engines, mem, nmem, support):
+def fused_population_step(agents, mem, nmem, support=None):
     last = None
-    for eng in engines:
-        last = eng.rainbow_fused_step(mem, nmem, B=B, beta=BETA, support=support, hp=hp(), gamma_n=GAMMA ** N_STEP)
+    for agent in agents:
+        last = agent.learn_from_buffers(mem, nmem)       # fused HBM-resident gradient step
     return last
 
 
-def api_population_step(engines, mem, nmem, support, host_tr):
-    """The public-API path with host buffers (what train_off_policy.py:327-412 does per learn)."""
-    from agilerl_b200.compat import TensorDict
+def api_population_step(agents, mem, nmem, support, host_tr):
+    """The public-API path with host buffers — exactly what train_off_policy.py:327-412 does per
+    learn step: Transition -> n_step_memory.add -> memory.add -> sampler.sample ->
+    n_step_sampler.sample -> agent.learn -> memory.update_priorities."""
+    from agilerl_b200.components import Transition
     out = None
-    for eng in engines:
-        td = TensorDict({k: v for k, v in host_tr.items()}, batch_size=[NUM_ENVS])   # pinned host tensors
+    for agent in agents:
+        td = Transition(obs=host_tr["obs"], action=host_tr["action"], reward=host_tr["reward"],
+                        next_obs=host_tr["next_obs"], done=host_tr["done"], batch_size=[NUM_ENVS]).to_tensordict()
         one = nmem.add(td)                      # H2D + n-step roll + ring write
         if one is not None:
             mem.add(one)                        # ring write + tree leaves
-        exp = mem.sample(B, BETA)               # tree sample + gather (materialised batch)
+        exp = mem.sample(agent.batch_size, agent.beta)          # tree sample + gather (materialised batch)
         nexp = nmem.sample_from_indices(exp["idxs"].squeeze(1))
-        loss, _, pri, _ = eng.rainbow_learn([(nexp, GAMMA ** N_STEP, False)], B=B, support=support,
-                                            weights=exp["weights"].squeeze(1), weights_mode=1, hp=hp())
-        loss_f = loss.item()                    # D2H (the reference returns loss.item())
-        pri_np = pri.cpu().numpy()              # D2H priorities (np.ndarray like learn() returns)
-        mem.update_priorities(exp["idxs"], pri_np)
+        exp["weights"] = exp["weights"].squeeze(1)              # canonical shapes (quirks Q1/Q2 off)
+        loss_f, idxs, pri_np = agent.learn(exp, n_experiences=nexp, per=True)   # float + np.ndarray: 2 D2H reads
+        mem.update_priorities(idxs, pri_np)
         out = loss_f
     return out
 
@@ -367,7 +363,7 @@ def main():
         return
 
     hbm_peak, tf_peak, peak_kind = peaks()
-    flops, kbytes, kms = conv1_roofline(engines[0], nmem, device)
+    flops, kbytes, kms = conv1_roofline(engines[0].engine, nmem, device)
     achieved_tf = flops / (kms / 1e3) / 1e12
     line = {
         "metric": "population gradient-steps/sec (Rainbow-DQN pop=8)", "value": value, "unit": "steps/s",

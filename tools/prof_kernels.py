@@ -18,7 +18,7 @@ def main():
     support = torch.linspace(bench.V_MIN, bench.V_MAX, bench.N_ATOMS).to(dev)
     if mode == "conv1":
         for _ in range(3):
-            print(bench.conv1_roofline(engines[0], nmem, dev))
+            print(bench.conv1_roofline(engines[0].engine, nmem, dev))
     else:
         for _ in range(4):
             bench.fused_population_step(engines, mem, nmem, support)
