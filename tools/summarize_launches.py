@@ -5,6 +5,21 @@ import re
 import sys
 
 
+# (A traits, B traits, epilogue traits) -> what the launch is  [elem,rowmap,redmap,red_fast,ones]
+ROLES = {
+    (("1", "1", "2", "1", "0"), ("0", "0", "0", "1", "0"), ("0", "1", "0")): "conv fwd, uint8 frames (layer 1)",
+    (("0", "1", "2", "1", "0"), ("0", "0", "0", "1", "0"), ("0", "1", "0")): "conv fwd, fp32 activations",
+    (("0", "0", "0", "1", "0"), ("0", "0", "0", "1", "0"), ("0", "0", "0")): "linear fwd",
+    (("0", "0", "0", "1", "0"), ("0", "0", "0", "0", "0"), ("0", "0", "0")): "linear dX",
+    (("0", "0", "0", "0", "0"), ("0", "0", "0", "0", "1"), ("2", "0", "0")): "linear dW+db",
+    (("1", "2", "1", "1", "1"), ("0", "0", "1", "1", "0"), ("3", "0", "0")): "conv wgrad+bgrad, uint8 frames (layer 1)",
+    (("0", "2", "1", "1", "1"), ("0", "0", "1", "1", "0"), ("3", "0", "0")): "conv wgrad+bgrad, fp32 activations",
+    (("0", "1", "0", "0", "0"), ("0", "0", "0", "0", "0"), ("1", "1", "2")): "conv dgrad (col2im atomics)",
+    (("0", "0", "1", "1", "0"), ("1", "2", "1", "0", "1"), ("2", "0", "0")): "conv wgrad (old roles), uint8",
+    (("0", "0", "1", "1", "0"), ("0", "2", "1", "0", "1"), ("2", "0", "0")): "conv wgrad (old roles), fp32",
+}
+
+
 def main(path):
     with open(path) as f:
         lines = [l for l in f if not l.startswith("==")]
@@ -18,19 +33,16 @@ def main(path):
             continue
         name = row[iK]
         v = float(row[iV].replace(",", ""))
-        m = re.match(r"(?:void )?(?:b2rl::)?([A-Za-z0-9_]+)(<.*>)?", name)
+        m = re.match(r"(?:void )?(?:b2rl::)?([A-Za-z0-9_]+)", name)
         short = m.group(1)
-        if m.group(2):
-            t = m.group(2)
-            tile = re.match(r"<(\d+), (\d+), (\d+), (\d+), (\d+)", t)
-            ops = re.findall(r"OpTraits<(\d), (\d), (\d), \(bool\)(\d), \(bool\)(\d)>", t)
-            epi = re.findall(r"EpiTraits<(\d), (\d), (\d)>", t)
-            if tile and ops:
-                short += f"<{tile.group(1)}x{tile.group(2)} A{''.join(ops[0])} B{''.join(ops[-1])} E{''.join(epi[0]) if epi else ''}>"
-            elif epi:
-                short += f"<E{''.join(epi[0])}>"
-            else:
-                short += t[:30]
+        tile = re.search(r"igemm_kernel<(\d+), (\d+), (\d+), (\d+), (\d+)", name)
+        ops = re.findall(r"OpTraits<(\d), (\d), (\d), (\d), (\d)>", name)
+        epi = re.findall(r"EpiTraits<(\d), (\d), (\d)>", name)
+        if tile and ops:
+            role = ROLES.get((ops[0], ops[1], epi[0] if epi else None), "")
+            short += f"<{tile.group(1)}x{tile.group(2)} A={''.join(ops[0])} B={''.join(ops[1])} E={''.join(epi[0])}> {role}"
+        elif epi:
+            short += f"<E={''.join(epi[0])}>"
         agg[short][0] += 1
         agg[short][1] += v
         n += 1
