@@ -18,7 +18,9 @@
 
 #include <type_traits>
 
+#include "conv_tc.cuh"
 #include "gemm.cuh"
+#include <cstdlib>
 
 namespace b2rl {
 
@@ -319,6 +321,16 @@ struct ObsChunk {          // first-layer input rows [row0, row0+rows) come from
 
 struct Scratch { float *partial; size_t floats; };
 
+// B2RL_DISABLE_TC=1 forces every convolution onto the fp32 FFMA engine (A/B testing, parity triage)
+static bool tc_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("B2RL_DISABLE_TC");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 // run f(std::integral_constant<int, ELEM>) for the element kind of an operand that may read
 // observations (only first-layer operands are ever not plain fp32)
 template <typename F>
@@ -374,14 +386,16 @@ static int layer_forward(const b2rl_net_desc &net, const b2rl_layer &l, const fl
             epi.act = l.act;
             epi.pre_out = lb.pre ? lb.pre + row0 * oe : nullptr;
         }
-        int rc;
-        if (l.kind == B2RL_LAYER_CONV)
+        int rc = 1;
+        if (l.kind == B2RL_LAYER_CONV && tc_enabled() && l.ln == B2RL_LN_NONE)
+            rc = launch_conv_fwd_tc(l, A, W, bias, out_ptr, lb.pre ? lb.pre + row0 * oe : nullptr, r, s);   // tcgen05 3xTF32
+        if (rc == 1 && l.kind == B2RL_LAYER_CONV)
             rc = dispatch_elem(A.elem_kind(), [&](auto ek) {
                 return launch_igemm<OpTraits<decltype(ek)::value, MAP_PIXEL, MAP_KERNEL, true, false>, OpW,
                                     EpiTraits<EPI_STORE, MAP_PIXEL, MAP_STRIDE>>(A, Bm, epi, M, N, K, sc.partial,
                                                                                    sc.floats, s);
             });
-        else
+        else if (rc == 1)
             rc = dispatch_elem(A.elem_kind(), [&](auto ek) {
                 return launch_igemm<OpTraits<decltype(ek)::value, MAP_STRIDE, MAP_STRIDE, true, false>, OpW,
                                     EpiTraits<EPI_STORE, MAP_STRIDE, MAP_STRIDE>>(A, Bm, epi, M, N, K, sc.partial,
