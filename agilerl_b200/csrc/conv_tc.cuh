@@ -95,6 +95,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ float tf32_rn(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -106,10 +114,11 @@ __device__ __forceinline__ float tf32_rn(float x) {
 constexpr int kTcBM = 128;      // pixels per CTA (UMMA M)
 constexpr int kTcBK = 32;       // k per stage (4 MMA k-steps of 8)
 constexpr int kTcStages = 2;
+constexpr int kTcThreads = 256; // two threads per im2col row (16 k each per stage)
 
 struct ConvTcParams {
     const void *x;              // input: uint8 frames / fp32 activations (NCHW)
-    const float *w;             // [Cout, K] row-major (K = Cin*k*k)
+    const float *w_hi, *w_lo;   // weights pre-split into tf32 hi/lo, already in the smem tile layout
     const float *bias;          // [Cout]
     float *out;                 // NCHW
     float *pre_out;             // optional pre-activation copy
@@ -121,6 +130,7 @@ struct ConvTcParams {
     int KK, KS, HW, W;          // kernel taps per channel, kernel size, input H*W, input W
     int act;
     int normalize;
+    int vec4;                   // uint8 input and every 4-tap chunk is 4 contiguous, 4-byte aligned bytes
     float low, high;
 };
 
@@ -129,37 +139,66 @@ static inline size_t conv_tc_smem_bytes(int n_pad, int k_pad) {
     return kTcStages * 2 * (a + b) + (size_t)k_pad * 4 + 256 * 4 + (size_t)n_pad * 4 + 64 + 1024;
 }
 
+// Split W [N, K] into tf32 hi / lo and store it in the order the conv kernel's B tiles use:
+//   [k-block][chunk c = (k%32)/4][n/8][n%8][k%4]   (n_pad * 32 floats per k-block, zero padded)
+__global__ void weight_split_kernel(const float *__restrict__ w, int N, int K, int n_pad, int k_pad,
+                                    float *__restrict__ w_hi, float *__restrict__ w_lo) {
+    const int total = n_pad * k_pad;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int k = e / n_pad, n = e - k * n_pad;
+        const float v = (n < N && k < K) ? w[(int64_t)n * K + k] : 0.f;
+        const float hi = tc::tf32_rn(v);
+        const int kb = k / kTcBK, kin = k - kb * kTcBK;
+        const int64_t o = (int64_t)kb * n_pad * kTcBK + (int64_t)(kin >> 2) * n_pad * 4 + (n >> 3) * 32 + (n & 7) * 4 + (kin & 3);
+        w_hi[o] = hi;
+        w_lo[o] = v - hi;
+    }
+}
+
+__device__ __noinline__ float act_fwd_slow(int act, float v) { return act_fwd(act, v); }
+
 template <int ELEM>
-__global__ void __launch_bounds__(128) conv_fwd_tc_kernel(const ConvTcParams p) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+__global__ void __launch_bounds__(kTcThreads) conv_fwd_tc_kernel(const ConvTcParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int row = tid & (kTcBM - 1), half = tid >> 7;       // im2col row, which 16 of the 32 k
     const uint32_t a_bytes = kTcBM * kTcBK * 4, b_bytes = (uint32_t)p.n_pad * kTcBK * 4;
-    // carve: [stage][A_hi, A_lo, B_hi, B_lo] | koff | lut | bias | barriers | tmem ptr
-    uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // carve (all addresses are 32-bit shared-space addresses so that the compiler emits LDS/STS):
+    //   [stage][A_hi, A_lo, B_hi, B_lo] | koff | lut | bias | barriers | tmem ptr
+    const uint32_t sbase = (tc::smem_u32(smem_raw) + 127u) & ~127u;
     const uint32_t stage_bytes = 2 * (a_bytes + b_bytes);
-    auto a_hi = [&](int s) { return base + (size_t)s * stage_bytes; };
-    auto a_lo = [&](int s) { return base + (size_t)s * stage_bytes + a_bytes; };
-    auto b_hi = [&](int s) { return base + (size_t)s * stage_bytes + 2 * a_bytes; };
-    auto b_lo = [&](int s) { return base + (size_t)s * stage_bytes + 2 * a_bytes + b_bytes; };
-    int *koff = reinterpret_cast<int *>(base + (size_t)kTcStages * stage_bytes);
-    float *lut = reinterpret_cast<float *>(koff + p.k_pad);
-    float *sbias = lut + 256;
-    uint64_t *bars = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(sbias + p.n_pad) + 15) & ~uintptr_t(15));
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + kTcStages);
+    auto a_hi = [&](int s) { return sbase + (uint32_t)s * stage_bytes; };
+    auto a_lo = [&](int s) { return sbase + (uint32_t)s * stage_bytes + a_bytes; };
+    auto b_hi = [&](int s) { return sbase + (uint32_t)s * stage_bytes + 2 * a_bytes; };
+    auto b_lo = [&](int s) { return sbase + (uint32_t)s * stage_bytes + 2 * a_bytes + b_bytes; };
+    const uint32_t koff_a = sbase + kTcStages * stage_bytes;
+    const uint32_t lut_a = koff_a + (uint32_t)p.k_pad * 4;
+    const uint32_t bias_a = lut_a + 256 * 4;
+    const uint32_t bars_a = (bias_a + (uint32_t)p.n_pad * 4 + 15u) & ~15u;
+    const uint32_t tptr_a = bars_a + 8 * kTcStages;
+    uint8_t *gen = smem_raw + (sbase - tc::smem_u32(smem_raw));        // generic alias of sbase (barriers only)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(gen + (bars_a - sbase));
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(gen + (tptr_a - sbase));
 
     // ---- one-time setup ----------------------------------------------------------------------
-    for (int k = tid; k < p.k_pad; k += 128) {
+    for (int k = tid; k < p.k_pad; k += kTcThreads) {
         int off = -1;
         if (k < p.K) {
             const int ci = k / p.KK, rem = k - ci * p.KK;
             const int ky = rem / p.KS, kx = rem - ky * p.KS;
             off = ci * p.HW + ky * p.W + kx;
         }
-        koff[k] = off;
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(koff_a + 4u * k), "r"(off) : "memory");
     }
     if (ELEM == EL_U8)
-        for (int i = tid; i < 256; i += 128) lut[i] = p.normalize ? __fdiv_rn((float)i - p.low, p.high - p.low) : (float)i;
-    for (int n = tid; n < p.n_pad; n += 128) sbias[n] = (n < p.N && p.bias) ? p.bias[n] : 0.f;
+        for (int i = tid; i < 256; i += kTcThreads) {
+            const float v = p.normalize ? __fdiv_rn((float)i - p.low, p.high - p.low) : (float)i;
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(lut_a + 4u * i), "f"(v) : "memory");
+        }
+    for (int n = tid; n < p.n_pad; n += kTcThreads) {
+        const float v = (n < p.N && p.bias) ? p.bias[n] : 0.f;
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_a + 4u * n), "f"(v) : "memory");
+    }
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < p.n_pad) tmem_cols <<= 1;
     if (warp == 0) tc::tmem_alloc(tmem_ptr, tmem_cols);
@@ -172,80 +211,98 @@ __global__ void __launch_bounds__(128) conv_fwd_tc_kernel(const ConvTcParams p) 
     tc::tc_fence_after();
     const uint32_t tmem_d = *tmem_ptr;
 
-    // this thread's im2col row (output pixel)
-    const int m = blockIdx.x * kTcBM + tid;
+    // this thread's im2col row (output pixel); rows beyond M read a safe in-bounds address
+    const int m = blockIdx.x * kTcBM + row;
     const bool row_ok = m < p.M;
-    int64_t rowbase = 0;
+    int64_t rowbase = p.gather ? p.gather[0] * p.in_bstride : 0;
     if (row_ok) {
         const int b = m / p.P, pix = m - b * p.P;
         const int oy = pix / p.OW, ox = pix - oy * p.OW;
         const int64_t bb = p.gather ? p.gather[b] : (int64_t)b;
         rowbase = bb * p.in_bstride + (int64_t)(oy * p.sy + ox * p.sx);
     }
+    const uint8_t *row_u8 = static_cast<const uint8_t *>(p.x) + rowbase;
+    const float *row_f32 = static_cast<const float *>(p.x) + rowbase;
     const uint32_t idesc = tc::make_idesc_tf32(kTcBM, p.n_pad);
     const uint32_t lbo_a = kTcBM * 16, lbo_b = (uint32_t)p.n_pad * 16;
     const int KB = p.k_pad / kTcBK;
-    const uint32_t row_off = (uint32_t)(tid >> 3) * 128 + (uint32_t)(tid & 7) * 16;   // (r/8)*128 + (r%8)*16
+    const uint32_t row_off = (uint32_t)(row >> 3) * 128 + (uint32_t)(row & 7) * 16;   // (r/8)*128 + (r%8)*16
+    constexpr int CH = kTcBK / 4 / 2;          // 4-tap chunks per thread per stage (4)
+    const int b_items = p.n_pad * (kTcBK / 4); // float4 items of one B operand tile (<= 2 per thread for N<=64)
+
+    // register double buffer: the gather of k-block kb+1 is in flight while kb is converted,
+    // fenced, synchronised and its MMAs are issued
+    uint32_t raw[CH * 4];
+    uint32_t vmask = 0;
+    auto gather = [&](int kb) {
+        const int k0 = kb * kTcBK + half * (CH * 4);
+        vmask = 0;
+        if (ELEM == EL_U8 && p.vec4) {
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                const int off = (int)tc::lds32(koff_a + 4u * (k0 + c * 4));
+                if (off >= 0) vmask |= 0xFu << (c * 4);
+                raw[c] = __ldg(reinterpret_cast<const uint32_t *>(row_u8 + (off < 0 ? 0 : off)));   // 4 packed taps
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < CH * 4; ++j) {
+                const int off = (int)tc::lds32(koff_a + 4u * (k0 + j));
+                vmask |= (uint32_t)(off >= 0) << j;
+                const int o2 = off < 0 ? 0 : off;
+                if (ELEM == EL_U8) raw[j] = (uint32_t)__ldg(row_u8 + o2);
+                else raw[j] = __float_as_uint(__ldg(row_f32 + o2));
+            }
+        }
+        if (!row_ok) vmask = 0;
+    };
+    gather(0);
 
     for (int kb = 0; kb < KB; ++kb) {
         const int s = kb & 1;
-        if (kb >= kTcStages) tc::mbar_wait(&bars[s], (uint32_t)((kb / kTcStages - 1) & 1));   // MMAs of this stage's last use done
-        // ---- A tile: 32 gathered values of this pixel row -> hi/lo -> 8 x 16 B stores each
-        uint32_t raw[kTcBK];
-#pragma unroll
-        for (int j = 0; j < kTcBK; ++j) {
-            const int off = koff[kb * kTcBK + j];
-            raw[j] = 0u;
-            if (row_ok && off >= 0) {
-                if (ELEM == EL_U8) raw[j] = (uint32_t)__ldg(static_cast<const uint8_t *>(p.x) + rowbase + off);
-                else raw[j] = __float_as_uint(__ldg(static_cast<const float *>(p.x) + rowbase + off));
+        if (kb >= kTcStages) tc::mbar_wait(&bars[s], (uint32_t)((kb / kTcStages - 1) & 1));   // stage free again
+        // ---- B tiles: straight 16-byte copies of the pre-split weights
+        {
+            const float4 *gh = reinterpret_cast<const float4 *>(p.w_hi + (int64_t)kb * p.n_pad * kTcBK);
+            const float4 *gl = reinterpret_cast<const float4 *>(p.w_lo + (int64_t)kb * p.n_pad * kTcBK);
+            for (int it = tid; it < b_items; it += kTcThreads) {
+                const float4 h = __ldg(gh + it), l = __ldg(gl + it);
+                tc::sts128(b_hi(s) + 16u * it, h.x, h.y, h.z, h.w);
+                tc::sts128(b_lo(s) + 16u * it, l.x, l.y, l.z, l.w);
             }
         }
-        uint8_t *ah = a_hi(s) + row_off, *al = a_lo(s) + row_off;
+        // ---- convert + hi/lo split + 16-byte smem stores of the gathered taps
+        const uint32_t ah = a_hi(s) + row_off + (uint32_t)(half * CH) * lbo_a, al = a_lo(s) + row_off + (uint32_t)(half * CH) * lbo_a;
 #pragma unroll
-        for (int c = 0; c < kTcBK / 4; ++c) {
+        for (int c = 0; c < CH; ++c) {
             float hi[4], lo[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int kk = c * 4 + j;
                 float v;
-                if (ELEM == EL_U8) v = (row_ok && koff[kb * kTcBK + kk] >= 0) ? lut[raw[kk]] : 0.f;
-                else if (ELEM == EL_F32_NORM)
-                    v = (row_ok && koff[kb * kTcBK + kk] >= 0) ? __fdiv_rn(__uint_as_float(raw[kk]) - p.low, p.high - p.low) : 0.f;
+                if (ELEM == EL_U8) {
+                    const uint32_t byte = p.vec4 ? ((raw[c] >> (8 * j)) & 0xFFu) : raw[kk];
+                    v = __uint_as_float(tc::lds32(lut_a + 4u * byte));
+                } else if (ELEM == EL_F32_NORM) v = __fdiv_rn(__uint_as_float(raw[kk]) - p.low, p.high - p.low);
                 else v = __uint_as_float(raw[kk]);
+                v = ((vmask >> kk) & 1u) ? v : 0.f;
                 hi[j] = tc::tf32_rn(v);
                 lo[j] = v - hi[j];
             }
-            *reinterpret_cast<float4 *>(ah + (size_t)c * lbo_a) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<float4 *>(al + (size_t)c * lbo_a) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            tc::sts128(ah + (uint32_t)c * lbo_a, hi[0], hi[1], hi[2], hi[3]);
+            tc::sts128(al + (uint32_t)c * lbo_a, lo[0], lo[1], lo[2], lo[3]);
         }
-        // ---- B tile: n_pad x 32 weights, 16 B (4 k) per item
-        for (int it = tid; it < p.n_pad * (kTcBK / 4); it += 128) {
-            const int n = it % p.n_pad, c = it / p.n_pad;
-            float hi[4], lo[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int k = kb * kTcBK + c * 4 + j;
-                const float v = (n < p.N && k < p.K) ? __ldg(p.w + (int64_t)n * p.K + k) : 0.f;
-                hi[j] = tc::tf32_rn(v);
-                lo[j] = v - hi[j];
-            }
-            const uint32_t o = (uint32_t)c * lbo_b + (uint32_t)(n >> 3) * 128 + (uint32_t)(n & 7) * 16;
-            *reinterpret_cast<float4 *>(b_hi(s) + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<float4 *>(b_lo(s) + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-        }
-        tc::fence_async_smem();          // generic-proxy smem writes -> visible to the async (tensor) proxy
+        if (kb + 1 < KB) gather(kb + 1);     // next k-block's loads overlap the fence / barrier / MMA issue
+        tc::fence_async_smem();              // generic-proxy smem writes -> visible to the async (tensor) proxy
         __syncthreads();
         if (tid == 0) {
             tc::tc_fence_after();
-            const uint32_t ah_addr = tc::smem_u32(a_hi(s)), al_addr = tc::smem_u32(a_lo(s));
-            const uint32_t bh_addr = tc::smem_u32(b_hi(s)), bl_addr = tc::smem_u32(b_lo(s));
 #pragma unroll
             for (int j = 0; j < kTcBK / 8; ++j) {      // one MMA k-step = 8 tf32 = 2 core-matrix columns
-                const uint64_t dah = tc::make_desc(ah_addr + 2 * j * lbo_a, lbo_a, 128);
-                const uint64_t dal = tc::make_desc(al_addr + 2 * j * lbo_a, lbo_a, 128);
-                const uint64_t dbh = tc::make_desc(bh_addr + 2 * j * lbo_b, lbo_b, 128);
-                const uint64_t dbl = tc::make_desc(bl_addr + 2 * j * lbo_b, lbo_b, 128);
+                const uint64_t dah = tc::make_desc(a_hi(s) + 2 * j * lbo_a, lbo_a, 128);
+                const uint64_t dal = tc::make_desc(a_lo(s) + 2 * j * lbo_a, lbo_a, 128);
+                const uint64_t dbh = tc::make_desc(b_hi(s) + 2 * j * lbo_b, lbo_b, 128);
+                const uint64_t dbl = tc::make_desc(b_lo(s) + 2 * j * lbo_b, lbo_b, 128);
                 tc::mma_tf32(tmem_d, dah, dbh, idesc, (kb | j) ? 1u : 0u);
                 tc::mma_tf32(tmem_d, dal, dbh, idesc, 1u);
                 tc::mma_tf32(tmem_d, dah, dbl, idesc, 1u);
@@ -260,21 +317,25 @@ __global__ void __launch_bounds__(128) conv_fwd_tc_kernel(const ConvTcParams p) 
     }
     tc::tc_fence_after();
 
-    // ---- epilogue: TMEM -> registers -> bias + activation -> NCHW ---------------------------------
-    int b_img = 0, pix = 0;
-    if (row_ok) { b_img = m / p.P; pix = m - b_img * p.P; }
-    for (int c0 = 0; c0 < p.n_pad; c0 += 32) {
-        uint32_t r[32];
-        tc::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
-        if (row_ok) {
+    // ---- epilogue (warps 0-3: one TMEM lane quarter each): TMEM -> regs -> bias + act -> NCHW ------
+    if (warp < 4) {
+        int b_img = 0, pix = 0;
+        if (row_ok) { b_img = m / p.P; pix = m - b_img * p.P; }
+        const bool relu = p.act == B2RL_ACT_RELU, ident = p.act == B2RL_ACT_NONE;
+        for (int c0 = 0; c0 < p.n_pad; c0 += 32) {
+            uint32_t r[32];
+            tc::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+            if (row_ok) {
+                float *o = p.out + ((int64_t)b_img * p.N + c0) * p.P + pix;
+                float *po = p.pre_out ? p.pre_out + ((int64_t)b_img * p.N + c0) * p.P + pix : nullptr;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int n = c0 + j;
-                if (n < p.N) {
-                    float v = __uint_as_float(r[j]) + sbias[n];
-                    const int64_t o = ((int64_t)b_img * p.N + n) * p.P + pix;
-                    if (p.pre_out) p.pre_out[o] = v;
-                    p.out[o] = act_fwd(p.act, v);
+                for (int j = 0; j < 32; ++j) {
+                    if (c0 + j < p.N) {
+                        float v = __uint_as_float(r[j]) + __uint_as_float(tc::lds32(bias_a + 4u * (c0 + j)));
+                        if (po) po[(int64_t)j * p.P] = v;
+                        v = relu ? fmaxf(v, 0.f) : (ident ? v : act_fwd_slow(p.act, v));
+                        o[(int64_t)j * p.P] = v;
+                    }
                 }
             }
         }
@@ -282,29 +343,44 @@ __global__ void __launch_bounds__(128) conv_fwd_tc_kernel(const ConvTcParams p) 
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem_d, tmem_cols);
-    (void)lane;
+}
+
+static inline size_t conv_tc_wsplit_floats(const b2rl_layer &l) {
+    const int K = l.in_c * l.ksize * l.ksize;
+    const int n_pad = (l.out_c + 15) / 16 * 16, k_pad = (K + kTcBK - 1) / kTcBK * kTcBK;
+    return (size_t)2 * n_pad * k_pad;
 }
 
 // returns B2RL_OK, or 1 when the shape is outside what the tensor-core kernel handles (caller falls
-// back to the FFMA engine)
+// back to the FFMA engine).  wsplit: scratch for the pre-split weights (conv_tc_wsplit_floats).
 static int launch_conv_fwd_tc(const b2rl_layer &l, const Operand &A, const float *W, const float *bias, float *out,
-                              float *pre_out, int64_t rows, cudaStream_t s) {
+                              float *pre_out, int64_t rows, float *wsplit, size_t wsplit_cap, cudaStream_t s) {
     const int KK = l.ksize * l.ksize, K = l.in_c * KK, P = l.out_h * l.out_w;
     const int n_pad = (l.out_c + 15) / 16 * 16, k_pad = (K + kTcBK - 1) / kTcBK * kTcBK;
     if (n_pad > 256 || k_pad > 8192 || rows * (int64_t)P > INT32_MAX) return 1;
     const size_t smem = conv_tc_smem_bytes(n_pad, k_pad);
-    if (smem > 200 * 1024) return 1;
+    if (smem > 200 * 1024 || wsplit == nullptr || conv_tc_wsplit_floats(l) > wsplit_cap) return 1;
+    float *w_hi = wsplit, *w_lo = wsplit + (size_t)n_pad * k_pad;
+    {
+        const int total = n_pad * k_pad;
+        weight_split_kernel<<<(total + 255) / 256, 256, 0, s>>>(W, l.out_c, K, n_pad, k_pad, w_hi, w_lo);
+        B2RL_LAUNCH_CHECK();
+    }
     ConvTcParams p;
-    p.x = A.ptr; p.w = W; p.bias = bias; p.out = out; p.pre_out = pre_out; p.gather = A.row.gather;
+    p.x = A.ptr; p.w_hi = w_hi; p.w_lo = w_lo; p.bias = bias; p.out = out; p.pre_out = pre_out; p.gather = A.row.gather;
     p.in_bstride = (int64_t)l.in_c * l.in_h * l.in_w;
     p.M = (int)(rows * P); p.N = l.out_c; p.K = K; p.n_pad = n_pad; p.k_pad = k_pad;
     p.P = P; p.OW = l.out_w; p.sy = l.stride * l.in_w; p.sx = l.stride;
     p.KK = KK; p.KS = l.ksize; p.HW = l.in_h * l.in_w; p.W = l.in_w;
     p.act = l.act; p.normalize = A.normalize; p.low = A.low; p.high = A.high;
+    // 4 consecutive taps are 4 contiguous, 4-byte aligned bytes when the kernel width, the column
+    // stride, the row pitch and the plane / image sizes are all multiples of 4
+    p.vec4 = (A.u8 && l.ksize % 4 == 0 && l.stride % 4 == 0 && l.in_w % 4 == 0 && (l.in_h * l.in_w) % 4 == 0 &&
+              (reinterpret_cast<uintptr_t>(A.ptr) % 4 == 0)) ? 1 : 0;
     const int grid = (p.M + kTcBM - 1) / kTcBM;
     auto launch = [&](auto kern) -> int {
         B2RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, 128, smem, s>>>(p);
+        kern<<<grid, kTcThreads, smem, s>>>(p);
         B2RL_LAUNCH_CHECK();
         return B2RL_OK;
     };

@@ -108,6 +108,11 @@ static size_t max_partial_floats(const b2rl_net_desc &net, int64_t rows, int64_t
     for (int i = 0; i < net.n_enc; ++i) upd(net.enc[i]);
     for (int i = 0; i < net.n_val; ++i) upd(net.val[i]);
     for (int i = 0; i < net.n_adv; ++i) upd(net.adv[i]);
+    for (int i = 0; i < net.n_enc; ++i)
+        if (net.enc[i].kind == B2RL_LAYER_CONV) {
+            const size_t n = conv_tc_wsplit_floats(net.enc[i]);
+            if (n > m) m = n;
+        }
     return m;
 }
 
@@ -388,7 +393,8 @@ static int layer_forward(const b2rl_net_desc &net, const b2rl_layer &l, const fl
         }
         int rc = 1;
         if (l.kind == B2RL_LAYER_CONV && tc_enabled() && l.ln == B2RL_LN_NONE)
-            rc = launch_conv_fwd_tc(l, A, W, bias, out_ptr, lb.pre ? lb.pre + row0 * oe : nullptr, r, s);   // tcgen05 3xTF32
+            rc = launch_conv_fwd_tc(l, A, W, bias, out_ptr, lb.pre ? lb.pre + row0 * oe : nullptr, r, sc.partial, sc.floats,
+                                    s);   // tcgen05 3xTF32 (pre-split weights live in the split-K scratch)
         if (rc == 1 && l.kind == B2RL_LAYER_CONV)
             rc = dispatch_elem(A.elem_kind(), [&](auto ek) {
                 return launch_igemm<OpTraits<decltype(ek)::value, MAP_PIXEL, MAP_KERNEL, true, false>, OpW,
