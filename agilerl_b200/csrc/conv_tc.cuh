@@ -391,4 +391,323 @@ static int launch_conv_fwd_tc(const b2rl_layer &l, const Operand &A, const float
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient on tcgen05:   dW[co][tap] = sum_pix  im2col(x)[pix][tap] * G[pix][co]
+//
+// UMMA view: D[M = 128 taps][N = Cout] += A[M][K = pixels] * B[N][K], both operands K-major
+// (pixels contiguous).  A thread owns one pixel (coalesced, packed gather exactly as in the forward
+// kernel) and scatters its 16 taps into the K-major tile with 4-byte stores; the K-chunk pitch is
+// padded by 16 B (LBO = 128*16 + 16) so that the 32 pixel-lanes of a warp hit 32 different banks.
+// (An MN-major im2col operand would allow 16-byte stores instead; not yet validated — round 2.)
+// Pixels are split over gridDim.y CTAs; the fp32 partials are reduced in fixed order by
+// splitk_reduce_kernel.
+//
+//   A (K-major, no swizzle):  (tap m, pixel k) at (k/4)*LBO_a + (m/8)*128 + (m%8)*16 + (k%4)*4,  LBO_a = 2064
+//   B (K-major, no swizzle):  (co n,  pixel k) at (k/4)*LBO_b + (n/8)*128 + (n%8)*16 + (k%4)*4
+// ------------------------------------------------------------------------------------------------
+struct ConvWgradTcParams {
+    const void *x;              // layer input (uint8 frames / fp32 activations), NCHW
+    const float *g;             // dL/d(conv output), NCHW [rows, Cout, P]
+    float *partial;             // [splits][taps_pad... = M][N] fp32
+    const int64_t *gather;
+    int64_t in_bstride;
+    int Mtaps, N, Kpix;         // taps (Cin*k*k), Cout, rows*P
+    int n_pad;
+    int P, OW, sy, sx;
+    int KK, KS, HW, W;
+    int pix_per_cta;            // multiple of 32
+    int normalize, vec4;
+    float low, high;
+};
+
+constexpr uint32_t kWgLboA = kTcBM * 16 + 16;        // padded K-chunk pitch of the wgrad A tile
+constexpr uint32_t kWgABytes = (kTcBK / 4) * kWgLboA;  // 8 chunks
+
+template <int ELEM>
+__global__ void __launch_bounds__(kTcThreads) conv_wgrad_tc_kernel(const ConvWgradTcParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int pl = tid & 31, tg = tid >> 5;                  // pixel lane within the 32-pixel block, tap group (16 taps)
+    const uint32_t a_bytes = kWgABytes, b_bytes = (uint32_t)p.n_pad * kTcBK * 4;
+    const uint32_t sbase = (tc::smem_u32(smem_raw) + 127u) & ~127u;
+    const uint32_t stage_bytes = 2 * (a_bytes + b_bytes);
+    auto a_hi = [&](int s) { return sbase + (uint32_t)s * stage_bytes; };
+    auto a_lo = [&](int s) { return sbase + (uint32_t)s * stage_bytes + a_bytes; };
+    auto b_hi = [&](int s) { return sbase + (uint32_t)s * stage_bytes + 2 * a_bytes; };
+    auto b_lo = [&](int s) { return sbase + (uint32_t)s * stage_bytes + 2 * a_bytes + b_bytes; };
+    const uint32_t toff_a = sbase + kTcStages * stage_bytes;              // tap offsets of this CTA's 128 taps
+    const uint32_t lut_a = toff_a + kTcBM * 4;
+    const uint32_t bars_a = (lut_a + 256 * 4 + 15u) & ~15u;
+    const uint32_t tptr_a = bars_a + 8 * kTcStages;
+    uint8_t *gen = smem_raw + (sbase - tc::smem_u32(smem_raw));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(gen + (bars_a - sbase));
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(gen + (tptr_a - sbase));
+
+    const int tap0 = blockIdx.x * kTcBM;
+    for (int t = tid; t < kTcBM; t += kTcThreads) {
+        const int k = tap0 + t;
+        int off = -1;
+        if (k < p.Mtaps) {
+            const int ci = k / p.KK, rem = k - ci * p.KK;
+            const int ky = rem / p.KS, kx = rem - ky * p.KS;
+            off = ci * p.HW + ky * p.W + kx;
+        }
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(toff_a + 4u * t), "r"(off) : "memory");
+    }
+    if (ELEM == EL_U8)
+        for (int i = tid; i < 256; i += kTcThreads) {
+            const float v = p.normalize ? __fdiv_rn((float)i - p.low, p.high - p.low) : (float)i;
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(lut_a + 4u * i), "f"(v) : "memory");
+        }
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < p.n_pad) tmem_cols <<= 1;
+    if (warp == 0) tc::tmem_alloc(tmem_ptr, tmem_cols);
+    if (tid == 0) {
+        for (int s = 0; s < kTcStages; ++s) tc::mbar_init(&bars[s], 1);
+        tc::fence_barrier_init();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_d = *tmem_ptr;
+
+    const int pix0 = blockIdx.y * p.pix_per_cta;
+    const int pix1 = min(p.Kpix, pix0 + p.pix_per_cta);
+    const int KB = (pix1 - pix0 + kTcBK - 1) / kTcBK;
+    const uint32_t idesc = tc::make_idesc_tf32(kTcBM, p.n_pad);
+    const uint32_t lbo_b = (uint32_t)p.n_pad * 16;
+    constexpr int CH = 4;                                   // 4-tap chunks per thread (16 taps)
+    const int64_t safe_base = p.gather ? p.gather[0] * p.in_bstride : 0;
+
+    uint32_t raw[CH * 4];
+    uint32_t vmask = 0;
+    float gval[4];
+    auto gather = [&](int kb) {
+        // ---- A: this thread's pixel, taps [tg*16, tg*16+16)
+        const int pix = pix0 + kb * kTcBK + pl;
+        const bool pok = pix < pix1;
+        int64_t base = safe_base;
+        if (pok) {
+            const int b = pix / p.P, pp = pix - b * p.P;
+            const int oy = pp / p.OW, ox = pp - oy * p.OW;
+            const int64_t bb = p.gather ? p.gather[b] : (int64_t)b;
+            base = bb * p.in_bstride + (int64_t)(oy * p.sy + ox * p.sx);
+        }
+        vmask = 0;
+        if (ELEM == EL_U8 && p.vec4) {
+            const uint8_t *rp = static_cast<const uint8_t *>(p.x) + base;
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                const int off = (int)tc::lds32(toff_a + 4u * (tg * 16 + c * 4));
+                if (off >= 0) vmask |= 0xFu << (c * 4);
+                raw[c] = __ldg(reinterpret_cast<const uint32_t *>(rp + (off < 0 ? 0 : off)));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < CH * 4; ++j) {
+                const int off = (int)tc::lds32(toff_a + 4u * (tg * 16 + j));
+                vmask |= (uint32_t)(off >= 0) << j;
+                const int o2 = off < 0 ? 0 : off;
+                if (ELEM == EL_U8) raw[j] = (uint32_t)__ldg(static_cast<const uint8_t *>(p.x) + base + o2);
+                else raw[j] = __float_as_uint(__ldg(static_cast<const float *>(p.x) + base + o2));
+            }
+        }
+        if (!pok) vmask = 0;
+        // ---- B: channel n = tid / 8 (+32 per pass), 4 consecutive pixels starting at (tid % 8) * 4
+        //      (only the first pass is prefetched; n_pad > 32 re-loads in the store phase)
+        const int n = tid >> 3, q = tid & 7;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int px = pix0 + kb * kTcBK + q * 4 + j;
+            float v = 0.f;
+            if (n < p.N && px < pix1) {
+                const int b = px / p.P, pp = px - b * p.P;
+                v = __ldg(p.g + ((int64_t)b * p.N + n) * p.P + pp);
+            }
+            gval[j] = v;
+        }
+    };
+    if (KB > 0) gather(0);
+
+    for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb & 1;
+        if (kb >= kTcStages) tc::mbar_wait(&bars[s], (uint32_t)((kb / kTcStages - 1) & 1));
+        // ---- A tile stores (transposed scatter): (k/4)*LBO_a + (m/8)*128 + (m%8)*16 + (k%4)*4, k = pl
+        const uint32_t a_off = (uint32_t)(pl >> 2) * kWgLboA + (uint32_t)(pl & 3) * 4;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int kk = c * 4 + j;
+                float v;
+                if (ELEM == EL_U8) {
+                    const uint32_t byte = p.vec4 ? ((raw[c] >> (8 * j)) & 0xFFu) : raw[kk];
+                    v = __uint_as_float(tc::lds32(lut_a + 4u * byte));
+                } else if (ELEM == EL_F32_NORM) v = __fdiv_rn(__uint_as_float(raw[kk]) - p.low, p.high - p.low);
+                else v = __uint_as_float(raw[kk]);
+                v = ((vmask >> kk) & 1u) ? v : 0.f;
+                const float hi = tc::tf32_rn(v), lo = v - hi;
+                const uint32_t m_ = (uint32_t)(tg * 16 + kk);
+                const uint32_t o = a_off + (m_ >> 3) * 128 + (m_ & 7) * 16;
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(a_hi(s) + o), "f"(hi) : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(a_lo(s) + o), "f"(lo) : "memory");
+            }
+        }
+        // ---- B tile stores: (k/4)*LBO_b + (n/8)*128 + (n%8)*16
+        {
+            const int n = tid >> 3, q = tid & 7;
+            float hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { hi[j] = tc::tf32_rn(gval[j]); lo[j] = gval[j] - hi[j]; }
+            const uint32_t o = (uint32_t)q * lbo_b + (uint32_t)(n >> 3) * 128 + (uint32_t)(n & 7) * 16;
+            if (n < p.n_pad) {          // n_pad may be 16: rows beyond it belong to the next K chunk
+                tc::sts128(b_hi(s) + o, hi[0], hi[1], hi[2], hi[3]);
+                tc::sts128(b_lo(s) + o, lo[0], lo[1], lo[2], lo[3]);
+            }
+            for (int n2 = n + 32; n2 < p.n_pad; n2 += 32) {        // wider layers: remaining channels
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int px = pix0 + kb * kTcBK + q * 4 + j;
+                    float v = 0.f;
+                    if (n2 < p.N && px < pix1) {
+                        const int b = px / p.P, pp = px - b * p.P;
+                        v = __ldg(p.g + ((int64_t)b * p.N + n2) * p.P + pp);
+                    }
+                    hi[j] = tc::tf32_rn(v); lo[j] = v - hi[j];
+                }
+                const uint32_t o2 = (uint32_t)q * lbo_b + (uint32_t)(n2 >> 3) * 128 + (uint32_t)(n2 & 7) * 16;
+                tc::sts128(b_hi(s) + o2, hi[0], hi[1], hi[2], hi[3]);
+                tc::sts128(b_lo(s) + o2, lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
+        if (kb + 1 < KB) gather(kb + 1);
+        tc::fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            tc::tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < kTcBK / 8; ++j) {                   // 8 pixels per MMA
+                const uint64_t dah = tc::make_desc(a_hi(s) + 2 * j * kWgLboA, kWgLboA, 128);
+                const uint64_t dal = tc::make_desc(a_lo(s) + 2 * j * kWgLboA, kWgLboA, 128);
+                const uint64_t dbh = tc::make_desc(b_hi(s) + 2 * j * lbo_b, lbo_b, 128);
+                const uint64_t dbl = tc::make_desc(b_lo(s) + 2 * j * lbo_b, lbo_b, 128);
+                tc::mma_tf32(tmem_d, dah, dbh, idesc, (kb | j) ? 1u : 0u);
+                tc::mma_tf32(tmem_d, dal, dbh, idesc, 1u);
+                tc::mma_tf32(tmem_d, dah, dbl, idesc, 1u);
+            }
+            tc::mma_commit(&bars[s]);
+        }
+    }
+    for (int s = 0; s < kTcStages; ++s) {
+        const int uses = (KB - s + kTcStages - 1) / kTcStages;
+        if (uses > 0) tc::mbar_wait(&bars[s], (uint32_t)((uses - 1) & 1));
+    }
+    tc::tc_fence_after();
+    // ---- epilogue: partial[z][tap][co]
+    if (warp < 4) {
+        const int tap = tap0 + warp * 32 + (tid & 31);
+        for (int c0 = 0; c0 < p.n_pad; c0 += 32) {
+            uint32_t r[32];
+            if (KB > 0) tc::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+            if (tap < p.Mtaps) {
+                float *o = p.partial + ((int64_t)blockIdx.y * p.Mtaps + tap) * p.N + c0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (c0 + j < p.N) o[j] = KB > 0 ? __uint_as_float(r[j]) : 0.f;
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_d, tmem_cols);
+}
+
+// db[co] = sum over rows and pixels of G[b][co][pix]   (one CTA per channel, fixed-order reduction)
+__global__ void conv_bias_grad_kernel(const float *__restrict__ g, int64_t rows, int N, int P, float *__restrict__ db,
+                                      int accumulate) {
+    __shared__ float red[32];
+    const int n = blockIdx.x;
+    float s = 0.f;
+    const int64_t total = rows * P;
+    for (int64_t e = threadIdx.x; e < total; e += blockDim.x) {
+        const int64_t b = e / P, pp = e - b * P;
+        s += g[(b * N + n) * P + pp];
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+        db[n] = accumulate ? db[n] + t : t;
+    }
+}
+
+static inline size_t conv_wgrad_tc_partial_floats(const b2rl_layer &l, int64_t rows, int sms) {
+    const int Kc = l.in_c * l.ksize * l.ksize;
+    const int64_t Kpix = rows * l.out_h * l.out_w;
+    const int mt = (Kc + kTcBM - 1) / kTcBM;
+    int64_t splits = (2 * (int64_t)sms + mt - 1) / mt;
+    const int64_t max_splits = (Kpix + 4 * kTcBK - 1) / (4 * kTcBK);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    return (size_t)splits * Kc * l.out_c;
+}
+
+// returns B2RL_OK, or 1 for shapes the tensor-core kernel does not take.
+static int launch_conv_wgrad_tc(const b2rl_layer &l, const Operand &X, const float *g, float *dw, float *db,
+                                int accumulate, int64_t rows, float *partial, size_t partial_cap, cudaStream_t s) {
+    const int KK = l.ksize * l.ksize, Kc = l.in_c * KK, P = l.out_h * l.out_w;
+    const int n_pad = (l.out_c + 15) / 16 * 16;
+    const int64_t Kpix = rows * P;
+    if (n_pad > 256 || Kpix > INT32_MAX || partial == nullptr) return 1;
+    const int mt = (Kc + kTcBM - 1) / kTcBM;
+    int64_t splits = (2 * (int64_t)sm_count() + mt - 1) / mt;
+    const int64_t max_splits = (Kpix + 4 * kTcBK - 1) / (4 * kTcBK);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    int pix_per_cta = (int)(((Kpix + splits - 1) / splits + kTcBK - 1) / kTcBK * kTcBK);
+    splits = (Kpix + pix_per_cta - 1) / pix_per_cta;
+    if ((size_t)splits * Kc * l.out_c > partial_cap) return 1;
+    const size_t smem = (size_t)kTcStages * 2 * ((size_t)kWgABytes + (size_t)n_pad * kTcBK * 4) + kTcBM * 4 + 1024 + 64 + 256;
+    if (smem > 200 * 1024) return 1;
+    ConvWgradTcParams p;
+    p.x = X.ptr; p.g = g; p.partial = partial; p.gather = X.red.gather;
+    p.in_bstride = (int64_t)l.in_c * l.in_h * l.in_w;
+    p.Mtaps = Kc; p.N = l.out_c; p.Kpix = (int)Kpix; p.n_pad = n_pad;
+    p.P = P; p.OW = l.out_w; p.sy = l.stride * l.in_w; p.sx = l.stride;
+    p.KK = KK; p.KS = l.ksize; p.HW = l.in_h * l.in_w; p.W = l.in_w;
+    p.pix_per_cta = pix_per_cta;
+    p.normalize = X.normalize; p.low = X.low; p.high = X.high;
+    p.vec4 = (X.u8 && l.ksize % 4 == 0 && l.stride % 4 == 0 && l.in_w % 4 == 0 && (l.in_h * l.in_w) % 4 == 0 &&
+              (reinterpret_cast<uintptr_t>(X.ptr) % 4 == 0)) ? 1 : 0;
+    dim3 grid(mt, (unsigned)splits);
+    auto launch = [&](auto kern) -> int {
+        B2RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kTcThreads, smem, s>>>(p);
+        B2RL_LAUNCH_CHECK();
+        return B2RL_OK;
+    };
+    int rc;
+    switch (X.elem_kind()) {
+        case EL_U8: rc = launch(conv_wgrad_tc_kernel<EL_U8>); break;
+        case EL_F32_NORM: rc = launch(conv_wgrad_tc_kernel<EL_F32_NORM>); break;
+        default: rc = launch(conv_wgrad_tc_kernel<EL_F32>); break;
+    }
+    if (rc != B2RL_OK) return rc;
+    // fixed-order reduction of the pixel splits, transposed into dW[co][tap]
+    Epilogue epi;
+    epi.kind = EPI_WGRAD_T; epi.out = dw; epi.db = nullptr; epi.wcols = Kc; epi.accumulate = accumulate;
+    const int64_t total = (int64_t)Kc * l.out_c;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+    splitk_reduce_kernel<EpiTraits<EPI_WGRAD_T, MAP_STRIDE, MAP_STRIDE>><<<blocks, 256, 0, s>>>(partial, (int)splits, Kc,
+                                                                                                 l.out_c, epi);
+    B2RL_LAUNCH_CHECK();
+    conv_bias_grad_kernel<<<l.out_c, 1024, 0, s>>>(g, rows, l.out_c, P, db, accumulate);
+    B2RL_LAUNCH_CHECK();
+    return B2RL_OK;
+}
+
 }  // namespace b2rl

@@ -110,8 +110,9 @@ static size_t max_partial_floats(const b2rl_net_desc &net, int64_t rows, int64_t
     for (int i = 0; i < net.n_adv; ++i) upd(net.adv[i]);
     for (int i = 0; i < net.n_enc; ++i)
         if (net.enc[i].kind == B2RL_LAYER_CONV) {
-            const size_t n = conv_tc_wsplit_floats(net.enc[i]);
+            size_t n = conv_tc_wsplit_floats(net.enc[i]);
             if (n > m) m = n;
+            if (brows) { n = conv_wgrad_tc_partial_floats(net.enc[i], brows, sm_count()); if (n > m) m = n; }
         }
     return m;
 }
@@ -810,7 +811,10 @@ static int layer_backward(const b2rl_net_desc &net, const b2rl_layer &l, const f
                               obs ? obs->gather : nullptr);
             A.ones_row = Kc;
             Bm.ptr = g_out; Bm.row = map_stride(P); Bm.red = map_pixel(P, l.out_w, (int64_t)l.out_c * P, l.out_w, 1);
-            rc = dispatch_elem(A.elem_kind(), [&](auto ek) {
+            rc = 1;
+            if (tc_enabled())   // tcgen05 3xTF32 (im2col operand MN-major, split over pixels)
+                rc = launch_conv_wgrad_tc(l, A, g_out, gw, gb, acc_w, B, sc.partial, sc.floats, s);
+            if (rc == 1) rc = dispatch_elem(A.elem_kind(), [&](auto ek) {
                 return launch_igemm<OpTraits<decltype(ek)::value, MAP_KERNEL, MAP_PIXEL, true, true>,
                                     OpTraits<EL_F32, MAP_STRIDE, MAP_PIXEL, true, false>,
                                     EpiTraits<EPI_WGRAD_T, MAP_STRIDE, MAP_STRIDE>>(A, Bm, epi, M, N, K, sc.partial,
