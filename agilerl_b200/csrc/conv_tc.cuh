@@ -234,10 +234,30 @@ __global__ void __launch_bounds__(kTcThreads) conv_fwd_tc_kernel(const ConvTcPar
     // fenced, synchronised and its MMAs are issued
     uint32_t raw[CH * 4];
     uint32_t vmask = 0;
+    float4 bh[2], bl[2];                       // this thread's share of the pre-split weight tile (n_pad <= 64)
     auto gather = [&](int kb) {
         const int k0 = kb * kTcBK + half * (CH * 4);
+        {
+            const float4 *gh = reinterpret_cast<const float4 *>(p.w_hi + (int64_t)kb * p.n_pad * kTcBK);
+            const float4 *gl = reinterpret_cast<const float4 *>(p.w_lo + (int64_t)kb * p.n_pad * kTcBK);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int it = tid + i * kTcThreads;
+                if (it < b_items) { bh[i] = __ldg(gh + it); bl[i] = __ldg(gl + it); }
+            }
+        }
         vmask = 0;
-        if (ELEM == EL_U8 && p.vec4) {
+        if (ELEM != EL_U8 && p.vec4) {          // fp32 activations: 4 taps = 2 aligned 8-byte loads
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                const int off = (int)tc::lds32(koff_a + 4u * (k0 + c * 4));
+                if (off >= 0) vmask |= 0xFu << (c * 4);
+                const float2 *q2 = reinterpret_cast<const float2 *>(row_f32 + (off < 0 ? 0 : off));
+                const float2 a = __ldg(q2), b = __ldg(q2 + 1);
+                raw[c * 4 + 0] = __float_as_uint(a.x); raw[c * 4 + 1] = __float_as_uint(a.y);
+                raw[c * 4 + 2] = __float_as_uint(b.x); raw[c * 4 + 3] = __float_as_uint(b.y);
+            }
+        } else if (ELEM == EL_U8 && p.vec4) {
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
                 const int off = (int)tc::lds32(koff_a + 4u * (k0 + c * 4));
@@ -261,15 +281,20 @@ __global__ void __launch_bounds__(kTcThreads) conv_fwd_tc_kernel(const ConvTcPar
     for (int kb = 0; kb < KB; ++kb) {
         const int s = kb & 1;
         if (kb >= kTcStages) tc::mbar_wait(&bars[s], (uint32_t)((kb / kTcStages - 1) & 1));   // stage free again
-        // ---- B tiles: straight 16-byte copies of the pre-split weights
-        {
-            const float4 *gh = reinterpret_cast<const float4 *>(p.w_hi + (int64_t)kb * p.n_pad * kTcBK);
-            const float4 *gl = reinterpret_cast<const float4 *>(p.w_lo + (int64_t)kb * p.n_pad * kTcBK);
-            for (int it = tid; it < b_items; it += kTcThreads) {
-                const float4 h = __ldg(gh + it), l = __ldg(gl + it);
-                tc::sts128(b_hi(s) + 16u * it, h.x, h.y, h.z, h.w);
-                tc::sts128(b_lo(s) + 16u * it, l.x, l.y, l.z, l.w);
+        // ---- B tiles: 16-byte stores of the prefetched pre-split weights
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int it = tid + i * kTcThreads;
+            if (it < b_items) {
+                tc::sts128(b_hi(s) + 16u * it, bh[i].x, bh[i].y, bh[i].z, bh[i].w);
+                tc::sts128(b_lo(s) + 16u * it, bl[i].x, bl[i].y, bl[i].z, bl[i].w);
             }
+        }
+        for (int it = tid + 2 * kTcThreads; it < b_items; it += kTcThreads) {      // wide layers (n_pad > 64)
+            const float4 h = __ldg(reinterpret_cast<const float4 *>(p.w_hi + (int64_t)kb * p.n_pad * kTcBK) + it);
+            const float4 l = __ldg(reinterpret_cast<const float4 *>(p.w_lo + (int64_t)kb * p.n_pad * kTcBK) + it);
+            tc::sts128(b_hi(s) + 16u * it, h.x, h.y, h.z, h.w);
+            tc::sts128(b_lo(s) + 16u * it, l.x, l.y, l.z, l.w);
         }
         // ---- convert + hi/lo split + 16-byte smem stores of the gathered taps
         const uint32_t ah = a_hi(s) + row_off + (uint32_t)(half * CH) * lbo_a, al = a_lo(s) + row_off + (uint32_t)(half * CH) * lbo_a;
@@ -375,8 +400,12 @@ static int launch_conv_fwd_tc(const b2rl_layer &l, const Operand &A, const float
     p.act = l.act; p.normalize = A.normalize; p.low = A.low; p.high = A.high;
     // 4 consecutive taps are 4 contiguous, 4-byte aligned bytes when the kernel width, the column
     // stride, the row pitch and the plane / image sizes are all multiples of 4
-    p.vec4 = (A.u8 && l.ksize % 4 == 0 && l.stride % 4 == 0 && l.in_w % 4 == 0 && (l.in_h * l.in_w) % 4 == 0 &&
-              (reinterpret_cast<uintptr_t>(A.ptr) % 4 == 0)) ? 1 : 0;
+    if (A.u8)
+        p.vec4 = (l.ksize % 4 == 0 && l.stride % 4 == 0 && l.in_w % 4 == 0 && (l.in_h * l.in_w) % 4 == 0 &&
+                  (reinterpret_cast<uintptr_t>(A.ptr) % 4 == 0)) ? 1 : 0;
+    else   // fp32: every 4-tap chunk starts on an even float (8-byte aligned) -> two 8-byte loads
+        p.vec4 = (l.ksize % 4 == 0 && l.stride % 2 == 0 && l.in_w % 2 == 0 && (l.in_h * l.in_w) % 2 == 0 &&
+                  p.in_bstride % 2 == 0 && (reinterpret_cast<uintptr_t>(A.ptr) % 8 == 0)) ? 1 : 0;
     const int grid = (p.M + kTcBM - 1) / kTcBM;
     auto launch = [&](auto kern) -> int {
         B2RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -418,6 +447,7 @@ struct ConvWgradTcParams {
     int KK, KS, HW, W;
     int pix_per_cta;            // multiple of 32
     int normalize, vec4;
+    int with_bias;              // partial has Mtaps+1 rows; the last one carries the bias gradient (N <= 32)
     float low, high;
 };
 
@@ -483,6 +513,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_wgrad_tc_kernel(const ConvWgr
     uint32_t raw[CH * 4];
     uint32_t vmask = 0;
     float gval[4];
+    float bsum = 0.f;                                       // bias gradient of channel tid/8 over this CTA's pixels
     auto gather = [&](int kb) {
         // ---- A: this thread's pixel, taps [tg*16, tg*16+16)
         const int pix = pix0 + kb * kTcBK + pl;
@@ -559,7 +590,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_wgrad_tc_kernel(const ConvWgr
             const int n = tid >> 3, q = tid & 7;
             float hi[4], lo[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { hi[j] = tc::tf32_rn(gval[j]); lo[j] = gval[j] - hi[j]; }
+            for (int j = 0; j < 4; ++j) { hi[j] = tc::tf32_rn(gval[j]); lo[j] = gval[j] - hi[j]; bsum += gval[j]; }
             const uint32_t o = (uint32_t)q * lbo_b + (uint32_t)(n >> 3) * 128 + (uint32_t)(n & 7) * 16;
             if (n < p.n_pad) {          // n_pad may be 16: rows beyond it belong to the next K chunk
                 tc::sts128(b_hi(s) + o, hi[0], hi[1], hi[2], hi[3]);
@@ -604,6 +635,14 @@ __global__ void __launch_bounds__(kTcThreads) conv_wgrad_tc_kernel(const ConvWgr
         if (uses > 0) tc::mbar_wait(&bars[s], (uint32_t)((uses - 1) & 1));
     }
     tc::tc_fence_after();
+    // ---- bias gradient partial (row Mtaps of the partial matrix): sum the 8 pixel-chunk lanes of a channel
+    if (p.with_bias && blockIdx.x == 0) {
+        bsum += __shfl_xor_sync(0xffffffffu, bsum, 1);
+        bsum += __shfl_xor_sync(0xffffffffu, bsum, 2);
+        bsum += __shfl_xor_sync(0xffffffffu, bsum, 4);
+        const int n = tid >> 3;
+        if ((tid & 7) == 0 && n < p.N) p.partial[((int64_t)blockIdx.y * (p.Mtaps + 1) + p.Mtaps) * p.N + n] = bsum;
+    }
     // ---- epilogue: partial[z][tap][co]
     if (warp < 4) {
         const int tap = tap0 + warp * 32 + (tid & 31);
@@ -611,7 +650,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_wgrad_tc_kernel(const ConvWgr
             uint32_t r[32];
             if (KB > 0) tc::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
             if (tap < p.Mtaps) {
-                float *o = p.partial + ((int64_t)blockIdx.y * p.Mtaps + tap) * p.N + c0;
+                float *o = p.partial + ((int64_t)blockIdx.y * (p.Mtaps + p.with_bias) + tap) * p.N + c0;
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                     if (c0 + j < p.N) o[j] = KB > 0 ? __uint_as_float(r[j]) : 0.f;
@@ -652,7 +691,7 @@ static inline size_t conv_wgrad_tc_partial_floats(const b2rl_layer &l, int64_t r
     const int64_t max_splits = (Kpix + 4 * kTcBK - 1) / (4 * kTcBK);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
-    return (size_t)splits * Kc * l.out_c;
+    return (size_t)splits * (Kc + 1) * l.out_c;
 }
 
 // returns B2RL_OK, or 1 for shapes the tensor-core kernel does not take.
@@ -669,7 +708,8 @@ static int launch_conv_wgrad_tc(const b2rl_layer &l, const Operand &X, const flo
     if (splits < 1) splits = 1;
     int pix_per_cta = (int)(((Kpix + splits - 1) / splits + kTcBK - 1) / kTcBK * kTcBK);
     splits = (Kpix + pix_per_cta - 1) / pix_per_cta;
-    if ((size_t)splits * Kc * l.out_c > partial_cap) return 1;
+    const int with_bias = l.out_c <= 32 ? 1 : 0;
+    if ((size_t)splits * (Kc + 1) * l.out_c > partial_cap) return 1;
     const size_t smem = (size_t)kTcStages * 2 * ((size_t)kWgABytes + (size_t)n_pad * kTcBK * 4) + kTcBM * 4 + 1024 + 64 + 256;
     if (smem > 200 * 1024) return 1;
     ConvWgradTcParams p;
@@ -679,6 +719,7 @@ static int launch_conv_wgrad_tc(const b2rl_layer &l, const Operand &X, const flo
     p.P = P; p.OW = l.out_w; p.sy = l.stride * l.in_w; p.sx = l.stride;
     p.KK = KK; p.KS = l.ksize; p.HW = l.in_h * l.in_w; p.W = l.in_w;
     p.pix_per_cta = pix_per_cta;
+    p.with_bias = with_bias;
     p.normalize = X.normalize; p.low = X.low; p.high = X.high;
     p.vec4 = (X.u8 && l.ksize % 4 == 0 && l.stride % 4 == 0 && l.in_w % 4 == 0 && (l.in_h * l.in_w) % 4 == 0 &&
               (reinterpret_cast<uintptr_t>(X.ptr) % 4 == 0)) ? 1 : 0;
@@ -696,17 +737,15 @@ static int launch_conv_wgrad_tc(const b2rl_layer &l, const Operand &X, const flo
         default: rc = launch(conv_wgrad_tc_kernel<EL_F32>); break;
     }
     if (rc != B2RL_OK) return rc;
-    // fixed-order reduction of the pixel splits, transposed into dW[co][tap]
+    // fixed-order reduction of the pixel splits, transposed into dW[co][tap] (+ db from the extra row)
     Epilogue epi;
-    epi.kind = EPI_WGRAD_T; epi.out = dw; epi.db = nullptr; epi.wcols = Kc; epi.accumulate = accumulate;
-    const int64_t total = (int64_t)Kc * l.out_c;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-    splitk_reduce_kernel<EpiTraits<EPI_WGRAD_T, MAP_STRIDE, MAP_STRIDE>><<<blocks, 256, 0, s>>>(partial, (int)splits, Kc,
-                                                                                                 l.out_c, epi);
+    epi.kind = EPI_WGRAD_T; epi.out = dw; epi.db = with_bias ? db : nullptr; epi.wcols = Kc; epi.accumulate = accumulate;
+    launch_splitk_reduce<EpiTraits<EPI_WGRAD_T, MAP_STRIDE, MAP_STRIDE>>(partial, (int)splits, Kc + with_bias, l.out_c, epi, s);
     B2RL_LAUNCH_CHECK();
-    conv_bias_grad_kernel<<<l.out_c, 1024, 0, s>>>(g, rows, l.out_c, P, db, accumulate);
-    B2RL_LAUNCH_CHECK();
+    if (!with_bias) {
+        conv_bias_grad_kernel<<<l.out_c, 1024, 0, s>>>(g, rows, l.out_c, P, db, accumulate);
+        B2RL_LAUNCH_CHECK();
+    }
     return B2RL_OK;
 }
 

@@ -323,17 +323,40 @@ igemm_kernel(const Operand A, const Operand Bop, const Epilogue epi, int M, int 
 }
 
 // Second stage of split-K: fixed-order sum over the kz partials, then the real epilogue.
+// 32 outputs x 8 z-slices per CTA: slice j sums z = j, j+8, ... ; the 8 slice sums are then added in
+// slice order by one thread per output -> deterministic, and 8x more loads in flight per output.
 template <class TE>
-__global__ void splitk_reduce_kernel(const float *__restrict__ partial, int splits, int M, int N, const Epilogue epi) {
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float *__restrict__ partial, int splits, int M, int N,
+                                                            const Epilogue epi) {
+    __shared__ float sl[8][33];
     const int64_t total = (int64_t)M * N;
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int ox = threadIdx.x & 31, zs = threadIdx.x >> 5;
+    for (int64_t e0 = (int64_t)blockIdx.x * 32; e0 < total; e0 += (int64_t)gridDim.x * 32) {
+        const int64_t e = e0 + ox;
         float v = 0.f;
-        for (int z = 0; z < splits; ++z) v += partial[(int64_t)z * total + e];
-        const int m = (int)(e / N), n = (int)(e % N);
-        int64_t om_off = 0;
-        if constexpr (TE::KIND != EPI_WGRAD && TE::KIND != EPI_WGRAD_T) om_off = map_off<TE::OMK>(epi.om, m);
-        epi_apply<TE>(epi, m, n, om_off, v);
+        if (e < total)
+            for (int z = zs; z < splits; z += 8) v += partial[(int64_t)z * total + e];
+        sl[zs][ox] = v;
+        __syncthreads();
+        if (zs == 0 && e < total) {
+            float t = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t += sl[j][ox];
+            const int m = (int)(e / N), n = (int)(e % N);
+            int64_t om_off = 0;
+            if constexpr (TE::KIND != EPI_WGRAD && TE::KIND != EPI_WGRAD_T) om_off = map_off<TE::OMK>(epi.om, m);
+            epi_apply<TE>(epi, m, n, om_off, t);
+        }
+        __syncthreads();
     }
+}
+
+template <class TE>
+static void launch_splitk_reduce(const float *partial, int splits, int M, int N, const Epilogue &epi, cudaStream_t s) {
+    const int64_t total = (int64_t)M * N;
+    int64_t blocks = (total + 31) / 32;
+    if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
+    splitk_reduce_kernel<TE><<<(int)blocks, 256, 0, s>>>(partial, splits, M, N, epi);
 }
 
 static inline bool use_big_tile(int64_t M) { return M >= 192; }
@@ -386,10 +409,7 @@ static int launch_igemm(const Operand &A, const Operand &B, const Epilogue &epi,
     }
     B2RL_LAUNCH_CHECK();
     if (part) {
-        const int64_t total = (int64_t)M * N;
-        int blocks = (int)((total + 255) / 256);
-        if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-        splitk_reduce_kernel<TE><<<blocks, 256, 0, s>>>(part, p.splits, M, N, epi);
+        launch_splitk_reduce<TE>(part, p.splits, M, N, epi, s);
         B2RL_LAUNCH_CHECK();
     }
     return B2RL_OK;

@@ -254,17 +254,17 @@ __global__ void ln_fwd_kernel(const float *__restrict__ z, const float *__restri
 }
 
 // column sums for the LayerNorm affine gradients: dw[c] = sum_r gy*xhat, db[c] = sum_r gy.
-// 32 columns x 8 row-groups per CTA, fixed-order smem reduction over the row groups.
+// 32 columns x 32 row-groups per CTA, fixed-order smem reduction over the row groups.
 __global__ void ln_affine_grad_kernel(const float *__restrict__ g, const float *__restrict__ z,
                                       const float *__restrict__ stats, const float *__restrict__ a,
                                       const float *__restrict__ pre, int act, float *__restrict__ dw,
                                       float *__restrict__ db, int64_t rows, int n, int accumulate) {
-    __shared__ float sw[8][33], sb[8][33];
+    __shared__ float sw[32][33], sb[32][33];
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cx;
     float w = 0.f, b = 0.f;
     if (c < n) {
-        for (int64_t r = ry; r < rows; r += 8) {
+        for (int64_t r = ry; r < rows; r += 32) {
             const int64_t o = r * n + c;
             const float gy = g[o] * act_bwd(act, pre ? pre[o] : 0.f, a[o]);
             const float xhat = (z[o] - stats[r * 2]) * stats[r * 2 + 1];
@@ -276,7 +276,7 @@ __global__ void ln_affine_grad_kernel(const float *__restrict__ g, const float *
     __syncthreads();
     if (ry == 0 && c < n) {
         float tw = 0.f, tb = 0.f;
-        for (int i = 0; i < 8; ++i) { tw += sw[i][cx]; tb += sb[i][cx]; }
+        for (int i = 0; i < 32; ++i) { tw += sw[i][cx]; tb += sb[i][cx]; }
         dw[c] = accumulate ? dw[c] + tw : tw;
         db[c] = accumulate ? db[c] + tb : tb;
     }
@@ -769,7 +769,7 @@ static int layer_backward(const b2rl_net_desc &net, const b2rl_layer &l, const f
         const float *z = lb.z + row_off * oe;
         const float *st = lb.stats + row_off * 2;
         if (l.ln == B2RL_LN_AFFINE) {
-            ln_affine_grad_kernel<<<(l.out_c + 31) / 32, 256, 0, s>>>(g_out, z, st, a, pre, l.act, grads + l.lnw_off,
+            ln_affine_grad_kernel<<<(l.out_c + 31) / 32, 1024, 0, s>>>(g_out, z, st, a, pre, l.act, grads + l.lnw_off,
                                                                         grads + l.lnb_off, B, l.out_c, accumulate_grads);
             B2RL_LAUNCH_CHECK();
         }
