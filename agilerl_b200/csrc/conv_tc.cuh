@@ -157,7 +157,12 @@ __global__ void weight_split_kernel(const float *__restrict__ w, int N, int K, i
 
 __device__ __noinline__ float act_fwd_slow(int act, float v) { return act_fwd(act, v); }
 
-template <int ELEM>
+// EXACT_A: uint8 observations with integer bounds.  (x - low) is a small integer, exactly
+// representable in tf32, so the im2col operand needs no lo part: 2 MMAs per k-step instead of 3,
+// no LUT, half the A-tile bytes; the 1/(high - low) of the normalisation is applied to the fp32
+// accumulator in the epilogue (one true division per output).  vs. the reference's
+// fl((x-low)/(high-low)) * w summed in fp32 the difference is <= 2^-23 relative per term.
+template <int ELEM, bool EXACT_A>
 __global__ void __launch_bounds__(kTcThreads) conv_fwd_tc_kernel(const ConvTcParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -166,11 +171,11 @@ __global__ void __launch_bounds__(kTcThreads) conv_fwd_tc_kernel(const ConvTcPar
     // carve (all addresses are 32-bit shared-space addresses so that the compiler emits LDS/STS):
     //   [stage][A_hi, A_lo, B_hi, B_lo] | koff | lut | bias | barriers | tmem ptr
     const uint32_t sbase = (tc::smem_u32(smem_raw) + 127u) & ~127u;
-    const uint32_t stage_bytes = 2 * (a_bytes + b_bytes);
+    const uint32_t stage_bytes = (EXACT_A ? 1 : 2) * a_bytes + 2 * b_bytes;
     auto a_hi = [&](int s) { return sbase + (uint32_t)s * stage_bytes; };
-    auto a_lo = [&](int s) { return sbase + (uint32_t)s * stage_bytes + a_bytes; };
-    auto b_hi = [&](int s) { return sbase + (uint32_t)s * stage_bytes + 2 * a_bytes; };
-    auto b_lo = [&](int s) { return sbase + (uint32_t)s * stage_bytes + 2 * a_bytes + b_bytes; };
+    auto a_lo = [&](int s) { return sbase + (uint32_t)s * stage_bytes + a_bytes; };     // unused when EXACT_A
+    auto b_hi = [&](int s) { return sbase + (uint32_t)s * stage_bytes + (EXACT_A ? 1 : 2) * a_bytes; };
+    auto b_lo = [&](int s) { return sbase + (uint32_t)s * stage_bytes + (EXACT_A ? 1 : 2) * a_bytes + b_bytes; };
     const uint32_t koff_a = sbase + kTcStages * stage_bytes;
     const uint32_t lut_a = koff_a + (uint32_t)p.k_pad * 4;
     const uint32_t bias_a = lut_a + 256 * 4;
@@ -190,7 +195,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_fwd_tc_kernel(const ConvTcPar
         }
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(koff_a + 4u * k), "r"(off) : "memory");
     }
-    if (ELEM == EL_U8)
+    if (ELEM == EL_U8 && !EXACT_A)
         for (int i = tid; i < 256; i += kTcThreads) {
             const float v = p.normalize ? __fdiv_rn((float)i - p.low, p.high - p.low) : (float)i;
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(lut_a + 4u * i), "f"(v) : "memory");
@@ -307,15 +312,16 @@ __global__ void __launch_bounds__(kTcThreads) conv_fwd_tc_kernel(const ConvTcPar
                 float v;
                 if (ELEM == EL_U8) {
                     const uint32_t byte = p.vec4 ? ((raw[c] >> (8 * j)) & 0xFFu) : raw[kk];
-                    v = __uint_as_float(tc::lds32(lut_a + 4u * byte));
+                    if (EXACT_A) v = (float)((int)byte - (int)p.low);            // exact in tf32
+                    else v = __uint_as_float(tc::lds32(lut_a + 4u * byte));
                 } else if (ELEM == EL_F32_NORM) v = __fdiv_rn(__uint_as_float(raw[kk]) - p.low, p.high - p.low);
                 else v = __uint_as_float(raw[kk]);
                 v = ((vmask >> kk) & 1u) ? v : 0.f;
-                hi[j] = tc::tf32_rn(v);
-                lo[j] = v - hi[j];
+                if (EXACT_A) { hi[j] = v; lo[j] = 0.f; }
+                else { hi[j] = tc::tf32_rn(v); lo[j] = v - hi[j]; }
             }
             tc::sts128(ah + (uint32_t)c * lbo_a, hi[0], hi[1], hi[2], hi[3]);
-            tc::sts128(al + (uint32_t)c * lbo_a, lo[0], lo[1], lo[2], lo[3]);
+            if (!EXACT_A) tc::sts128(al + (uint32_t)c * lbo_a, lo[0], lo[1], lo[2], lo[3]);
         }
         if (kb + 1 < KB) gather(kb + 1);     // next k-block's loads overlap the fence / barrier / MMA issue
         tc::fence_async_smem();              // generic-proxy smem writes -> visible to the async (tensor) proxy
@@ -329,7 +335,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_fwd_tc_kernel(const ConvTcPar
                 const uint64_t dbh = tc::make_desc(b_hi(s) + 2 * j * lbo_b, lbo_b, 128);
                 const uint64_t dbl = tc::make_desc(b_lo(s) + 2 * j * lbo_b, lbo_b, 128);
                 tc::mma_tf32(tmem_d, dah, dbh, idesc, (kb | j) ? 1u : 0u);
-                tc::mma_tf32(tmem_d, dal, dbh, idesc, 1u);
+                if (!EXACT_A) tc::mma_tf32(tmem_d, dal, dbh, idesc, 1u);
                 tc::mma_tf32(tmem_d, dah, dbl, idesc, 1u);
             }
             tc::mma_commit(&bars[s]);
@@ -356,7 +362,9 @@ __global__ void __launch_bounds__(kTcThreads) conv_fwd_tc_kernel(const ConvTcPar
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     if (c0 + j < p.N) {
-                        float v = __uint_as_float(r[j]) + __uint_as_float(tc::lds32(bias_a + 4u * (c0 + j)));
+                        float acc = __uint_as_float(r[j]);
+                        if (EXACT_A && p.normalize) acc = __fdiv_rn(acc, p.high - p.low);
+                        float v = acc + __uint_as_float(tc::lds32(bias_a + 4u * (c0 + j)));
                         if (po) po[(int64_t)j * p.P] = v;
                         v = relu ? fmaxf(v, 0.f) : (ident ? v : act_fwd_slow(p.act, v));
                         o[(int64_t)j * p.P] = v;
@@ -414,9 +422,12 @@ static int launch_conv_fwd_tc(const b2rl_layer &l, const Operand &A, const float
         return B2RL_OK;
     };
     switch (A.elem_kind()) {
-        case EL_U8: return launch(conv_fwd_tc_kernel<EL_U8>);
-        case EL_F32_NORM: return launch(conv_fwd_tc_kernel<EL_F32_NORM>);
-        default: return launch(conv_fwd_tc_kernel<EL_F32>);
+        case EL_U8: {
+            const bool exact = (!A.normalize || (A.low == floorf(A.low) && fabsf(A.low) <= 1024.f));
+            return exact ? launch(conv_fwd_tc_kernel<EL_U8, true>) : launch(conv_fwd_tc_kernel<EL_U8, false>);
+        }
+        case EL_F32_NORM: return launch(conv_fwd_tc_kernel<EL_F32_NORM, false>);
+        default: return launch(conv_fwd_tc_kernel<EL_F32, false>);
     }
 }
 

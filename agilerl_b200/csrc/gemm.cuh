@@ -359,7 +359,9 @@ static void launch_splitk_reduce(const float *partial, int splits, int M, int N,
     splitk_reduce_kernel<TE><<<(int)blocks, 256, 0, s>>>(partial, splits, M, N, epi);
 }
 
-static inline bool use_big_tile(int64_t M) { return M >= 192; }
+// 128-row tiles only pay off when there are many row tiles; the FFMA conv-wgrad fallback (M = taps)
+// asks for them explicitly through TE (EPI_WGRAD_T)
+static inline bool use_big_tile(int64_t M, bool wgrad_t = false) { return M >= 4096 || (wgrad_t && M >= 192); }
 
 struct GemmPlan {
     int splits = 1;
@@ -389,7 +391,7 @@ template <class TA, class TB, class TE>
 static int launch_igemm(const Operand &A, const Operand &B, const Epilogue &epi, int M, int N, int K,
                         float *partial, size_t partial_cap_floats, cudaStream_t s) {
     if (M <= 0 || N <= 0) return B2RL_OK;
-    const bool big = use_big_tile(M);
+    const bool big = use_big_tile(M, TE::KIND == EPI_WGRAD_T);
     GemmPlan p = plan_gemm(M, N, K, big, sm_count());
     if (p.splits > 1 && TE::KIND != EPI_ATOMIC && (partial == nullptr || p.partial_floats > partial_cap_floats))
         p.splits = 1;

@@ -82,9 +82,9 @@ static void carve_pass(Bump &b, const b2rl_net_desc &net, PassBufs &pb, int64_t 
     carve_layers(b, net.adv, net.n_adv, pb.adv, rows, grad_rows);
 }
 
-static size_t gemm_need(int64_t M, int64_t N, int64_t K) {
+static size_t gemm_need(int64_t M, int64_t N, int64_t K, bool wgrad_t = false) {
     if (M <= 0 || N <= 0 || K <= 0 || M > INT32_MAX) return 0;
-    return plan_gemm((int)M, (int)N, (int)K, use_big_tile(M), sm_count()).partial_floats;
+    return plan_gemm((int)M, (int)N, (int)K, use_big_tile(M, wgrad_t), sm_count()).partial_floats;
 }
 // exact bound of the split-K scratch over every GEMM a pass can launch
 static size_t max_partial_floats(const b2rl_net_desc &net, int64_t rows, int64_t brows) {
@@ -95,7 +95,7 @@ static size_t max_partial_floats(const b2rl_net_desc &net, int64_t rows, int64_t
             const int64_t P = (int64_t)l.out_h * l.out_w, Kc = (int64_t)l.in_c * l.ksize * l.ksize;
             n = gemm_need(rows * P, l.out_c, Kc); if (n > m) m = n;
             n = gemm_need(rows / 2 * P, l.out_c, Kc); if (n > m) m = n;     // first layer runs per chunk
-            if (brows) { n = gemm_need(Kc + 1, l.out_c, brows * P); if (n > m) m = n; }
+            if (brows) { n = gemm_need(Kc + 1, l.out_c, brows * P, true); if (n > m) m = n; }
         } else {
             n = gemm_need(rows, l.out_c, l.in_c); if (n > m) m = n;
             n = gemm_need(rows / 2, l.out_c, l.in_c); if (n > m) m = n;
