@@ -19,6 +19,7 @@
 #include <type_traits>
 
 #include "conv_tc.cuh"
+#include "head_fused.cuh"
 #include "gemm.cuh"
 #include <cstdlib>
 
@@ -442,6 +443,38 @@ static int forward_pass(const b2rl_net_desc &net, const float *params, const flo
         x = pb.enc[i].a;
     }
     const float *latent = x;
+    // ---- head: one fused launch for both chains when the tile fits in shared memory ----------------
+    {
+        HeadDesc hd;
+        hd.n_val = net.n_val; hd.n_adv = net.n_adv;
+        hd.latent = net.val[0].in_c;
+        int maxdim = hd.latent;
+        bool ok = tc_enabled() && (net.n_val + net.n_adv) <= kHeadMaxLayers;
+        auto fill = [&](const b2rl_layer &l, const LayerBuf &lb, HeadLayer &h) {
+            if (l.kind != B2RL_LAYER_LINEAR) ok = false;
+            h.w = eff_w(l, params, weff, use_noise); h.b = eff_b(l, params, weff, use_noise);
+            h.lnw = l.ln == B2RL_LN_AFFINE ? params + l.lnw_off : nullptr;
+            h.lnb = l.ln == B2RL_LN_AFFINE ? params + l.lnb_off : nullptr;
+            h.a = lb.a; h.z = lb.z; h.pre = lb.pre; h.stats = lb.stats;
+            h.in = l.in_c; h.out = l.out_c; h.ln = l.ln; h.act = l.act;
+            if (l.in_c > maxdim) maxdim = l.in_c;
+            if (l.out_c > maxdim) maxdim = l.out_c;
+        };
+        for (int i = 0; i < net.n_val && ok; ++i) fill(net.val[i], pb.val[i], hd.l[i]);
+        for (int i = 0; i < net.n_adv && ok; ++i) fill(net.adv[i], pb.adv[i], hd.l[net.n_val + i]);
+        hd.maxdim = maxdim;
+        const size_t smem = sizeof(float) * ((size_t)2 * kHeadRows * head_pitch(maxdim) + (kHeadThreads / 32) * kHeadRows);
+        if (ok && smem <= 160 * 1024) {
+            static bool attr_set = false;
+            if (!attr_set) {
+                B2RL_CUDA(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+                attr_set = true;
+            }
+            head_fwd_kernel<<<(int)((rows + kHeadRows - 1) / kHeadRows), kHeadThreads, smem, s>>>(hd, latent, rows);
+            B2RL_LAUNCH_CHECK();
+            return B2RL_OK;
+        }
+    }
     const float *xv = latent;
     for (int i = 0; i < net.n_val; ++i) {
         const b2rl_layer &l = net.val[i];
@@ -877,8 +910,66 @@ static int backward_pass(const b2rl_net_desc &net, const float *params, const fl
     const LayerBuf &lat = pb.enc[net.n_enc - 1];
     const float *latent = lat.a + row_off * layer_out_elems(net.enc[net.n_enc - 1]);
     float *g_latent = lat.g;
-    // heads
-    for (int head = 0; head < 2; ++head) {
+    // heads: two fused launches (dZ/dX chain, then every dW/db) when the tile fits in shared memory
+    bool head_done = false;
+    if (tc_enabled() && B <= 2048 && net.n_val + net.n_adv <= kHeadMaxLayers) {
+        HeadBwdDesc hd;
+        hd.n_val = net.n_val; hd.n_adv = net.n_adv; hd.latent = net.val[0].in_c;
+        hd.g_latent = g_latent; hd.accumulate = accumulate; hd.n_ln = 0;
+        const int n_tiles = (int)((B + kHeadRows - 1) / kHeadRows);
+        int maxdim = hd.latent, ctas = 0;
+        size_t part_used = 0;
+        bool ok = true;
+        auto fill = [&](const b2rl_layer *layers, LayerBuf *bufs, int i, int slot) {
+            const b2rl_layer &l = layers[i];
+            const LayerBuf &lb = bufs[i];
+            HeadBwdLayer &h = hd.l[slot];
+            if (l.kind != B2RL_LAYER_LINEAR) { ok = false; return; }
+            const int64_t oe = l.out_c;
+            h.w = eff_w(l, params, weff, use_noise);
+            h.lnw = l.ln == B2RL_LN_AFFINE ? params + l.lnw_off : nullptr;
+            h.a = lb.a + row_off * oe;
+            h.z = lb.z ? lb.z + row_off * oe : nullptr;
+            h.pre = lb.pre ? lb.pre + row_off * oe : nullptr;
+            h.stats = lb.stats ? lb.stats + row_off * 2 : nullptr;
+            h.x = i == 0 ? latent : bufs[i - 1].a + row_off * layers[i - 1].out_c;
+            h.g = lb.g;
+            h.dw = (l.noisy ? gweff : grads) + l.w_off;
+            h.db = (l.noisy ? gweff : grads) + l.b_off;
+            h.dlnw = h.dlnb = h.lnpart = nullptr;
+            if (l.ln == B2RL_LN_AFFINE) {
+                h.dlnw = grads + l.lnw_off; h.dlnb = grads + l.lnb_off;
+                h.lnpart = sc.partial + part_used;
+                part_used += (size_t)n_tiles * 2 * l.out_c;
+                hd.ln_layer[hd.n_ln++] = slot;
+            }
+            h.in = l.in_c; h.out = l.out_c; h.ln = l.ln; h.act = l.act;
+            h.acc_w = l.noisy ? 0 : accumulate;   // noisy: the accumulate happens in noisy_grad
+            if (l.in_c > maxdim) maxdim = l.in_c;
+            if (l.out_c > maxdim) maxdim = l.out_c;
+            hd.wg_start[slot] = ctas;
+            ctas += (l.out_c + kHeadThreads / 32 - 1) / (kHeadThreads / 32);
+        };
+        for (int i = 0; i < net.n_val && ok; ++i) fill(net.val, pb.val, i, i);
+        for (int i = 0; i < net.n_adv && ok; ++i) fill(net.adv, pb.adv, i, net.n_val + i);
+        hd.wg_start[net.n_val + net.n_adv] = ctas;
+        hd.maxdim = maxdim;
+        const size_t smem = sizeof(float) * ((size_t)(3 + kHeadThreads / 32) * kHeadRows * head_pitch(maxdim) +
+                                             (size_t)kHeadRows * hd.latent + (kHeadThreads / 32) * kHeadRows);
+        if (ok && smem <= 160 * 1024 && part_used <= sc.floats) {
+            static bool attr_set = false;
+            if (!attr_set) {
+                B2RL_CUDA(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+                attr_set = true;
+            }
+            head_bwd_kernel<<<n_tiles, kHeadThreads, smem, s>>>(hd, B);
+            B2RL_LAUNCH_CHECK();
+            head_wgrad_kernel<<<ctas + hd.n_ln, kHeadThreads, 0, s>>>(hd, B, n_tiles);
+            B2RL_LAUNCH_CHECK();
+            head_done = true;
+        }
+    }
+    for (int head = 0; head < 2 && !head_done; ++head) {
         const b2rl_layer *layers = head == 0 ? net.val : net.adv;
         LayerBuf *bufs = head == 0 ? pb.val : pb.adv;
         const int n = head == 0 ? net.n_val : net.n_adv;

@@ -71,8 +71,10 @@ class FlatLayout:
     def __init__(self, spec: NetSpec):
         self.spec = spec
         self.entries: "OrderedDict[str, Entry]" = OrderedDict()
-        self._np = 0
+        self._np = 0                # buffer lengths (entries padded to 4 words; the padding stays zero)
         self._ne = 0
+        self.n_param_elems = 0      # logical counts (what the reference's parameters()/buffers() hold)
+        self.n_eps_elems = 0
         self.desc = _lib.NetDesc()
         d = self.desc
         d.kind = _lib.NET_RAINBOW if spec.kind == "rainbow" else _lib.NET_Q
@@ -148,18 +150,20 @@ class FlatLayout:
         n = 1
         for s in shape:
             n *= s
-        off = self._np
+        off = self._np = (self._np + 3) & ~3      # 16-byte aligned views: float4 loads in the kernels
         self.entries[key] = Entry(key, tuple(shape), off, "param", init)
         self._np += n
+        self.n_param_elems += n
         return off
 
     def _eps(self, key, shape) -> int:
         n = 1
         for s in shape:
             n *= s
-        off = self._ne
+        off = self._ne = (self._ne + 3) & ~3
         self.entries[key] = Entry(key, tuple(shape), off, "eps", "eps")
         self._ne += n
+        self.n_eps_elems += n
         return off
 
     def _linear(self, key, n_in, n_out, act, ln, noisy, ln_key=None) -> _lib.Layer:

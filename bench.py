@@ -377,11 +377,16 @@ def main():
                      "achieved_gbs_per_gpu": ALG_BYTES_PER_STEP * value / world / 1e9,
                      "frac_of_peak": ALG_BYTES_PER_STEP * value / world / 1e9 / hbm_peak, "peak_gbs": hbm_peak,
                      "peak": peak_kind},
-        "roofline": {"kernel": "igemm_kernel<128,32,16,8,4> conv1 forward (4->32, k8 s4, B=256 ring rows)",
+        "roofline": {"kernel": "conv_fwd_tc_kernel<uint8, exact-A> + weight_split_kernel: conv1 forward (4->32, k8 s4) on "
+                               "B=256 ring rows, tcgen05.mma kind::tf32 (2xTF32 weight split, fp32 TMEM accumulate)",
                      "bound": "tensor", "achieved": achieved_tf, "peak": tf_peak, "unit": "TFLOP/s",
-                     "frac": achieved_tf / tf_peak, "traffic": None, "peak_kind": peak_kind,
+                     "frac": achieved_tf / tf_peak,
+                     # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture
+                     # profiles/r1_conv_fwd_tcgen05_v2.txt (frames 7.2 MB read; the 13 MB fp32 output stays in L2)
+                     "traffic": 7405824, "peak_kind": peak_kind + " (dense bf16 cuBLAS burst)",
                      "flops_per_launch": flops, "alg_bytes_per_launch": kbytes, "ms_per_launch": kms,
-                     "note": "fp32 FFMA on CUDA cores (1e-5 parity); fraction is vs the measured dense bf16 tensor peak"},
+                     "note": "algorithmic fp32-equivalent FLOPs (2*M*N*K); each costs 2 tf32 MMAs (3 for fp32 inputs); the "
+                             "kernel is bound by building the im2col tile on CUDA cores, not by the tensor pipe"},
     }
     if e2e is not None:
         line["e2e"] = e2e

@@ -230,7 +230,7 @@ def test_northstar_b16_golden():
                         obs_low=0.0, obs_high=255.0, obs_u8=True)
     ospec = onets.rainbow_spec((4, 84, 84), 6)
     layout = FlatLayout(spec)
-    assert layout.n_params == 162730 and layout.n_eps == 27429
+    assert layout.n_param_elems == 162730 and layout.n_eps_elems == 27429
     gen = torch.Generator().manual_seed(7)
     sd_a = {}
     for k, e in layout.entries.items():
