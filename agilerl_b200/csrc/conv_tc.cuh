@@ -41,6 +41,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared by the TMA unit; completion is signalled on the mbarrier's tx count
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -95,6 +107,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -113,12 +134,14 @@ __device__ __forceinline__ float tf32_rn(float x) {
 
 constexpr int kTcBM = 128;      // pixels per CTA (UMMA M)
 constexpr int kTcBK = 32;       // k per stage (4 MMA k-steps of 8)
-constexpr int kTcStages = 2;
+constexpr int kTcStages = 2;    // A-operand stages (built by the CTA's threads)
+constexpr int kTcBStages = 4;   // B-operand stages (bulk-copied by the TMA unit, two k-blocks ahead)
 constexpr int kTcThreads = 256; // two threads per im2col row (16 k each per stage)
 
 struct ConvTcParams {
     const void *x;              // input: uint8 frames / fp32 activations (NCHW)
     const float *w_hi, *w_lo;   // weights pre-split into tf32 hi/lo, already in the smem tile layout
+    const uint32_t *koff;       // [k_pad] input offset of every tap
     const float *bias;          // [Cout]
     float *out;                 // NCHW
     float *pre_out;             // optional pre-activation copy
@@ -130,19 +153,19 @@ struct ConvTcParams {
     int KK, KS, HW, W;          // kernel taps per channel, kernel size, input H*W, input W
     int act;
     int normalize;
-    int vec4;                   // uint8 input and every 4-tap chunk is 4 contiguous, 4-byte aligned bytes
     float low, high;
 };
 
-static inline size_t conv_tc_smem_bytes(int n_pad, int k_pad) {
+static inline size_t conv_tc_smem_bytes(int n_pad, int k_pad, int a_parts = 2) {
     const size_t a = (size_t)kTcBM * kTcBK * 4, b = (size_t)n_pad * kTcBK * 4;
-    return kTcStages * 2 * (a + b) + (size_t)k_pad * 4 + 256 * 4 + (size_t)n_pad * 4 + 64 + 1024;
+    return kTcStages * a_parts * a + kTcBStages * 2 * b + (size_t)k_pad * 4 + 256 * 4 + (size_t)n_pad * 4 + 160 + 1024;
 }
 
 // Split W [N, K] into tf32 hi / lo and store it in the order the conv kernel's B tiles use:
 //   [k-block][chunk c = (k%32)/4][n/8][n%8][k%4]   (n_pad * 32 floats per k-block, zero padded)
 __global__ void weight_split_kernel(const float *__restrict__ w, int N, int K, int n_pad, int k_pad,
-                                    float *__restrict__ w_hi, float *__restrict__ w_lo) {
+                                    float *__restrict__ w_hi, float *__restrict__ w_lo, int KK, int KS, int HW, int W,
+                                    uint32_t *__restrict__ koff) {
     const int total = n_pad * k_pad;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         const int k = e / n_pad, n = e - k * n_pad;
@@ -152,71 +175,130 @@ __global__ void weight_split_kernel(const float *__restrict__ w, int N, int K, i
         const int64_t o = (int64_t)kb * n_pad * kTcBK + (int64_t)(kin >> 2) * n_pad * 4 + (n >> 3) * 32 + (n & 7) * 4 + (kin & 3);
         w_hi[o] = hi;
         w_lo[o] = v - hi;
+        if (n == 0 && koff) {      // input offset of tap k = (ci, ky, kx); padded taps read offset 0 against zero weights
+            uint32_t off = 0;
+            if (k < K) {
+                const int ci = k / KK, rem = k - ci * KK;
+                const int ky = rem / KS, kx = rem - ky * KS;
+                off = (uint32_t)(ci * HW + ky * W + kx);
+            }
+            koff[k] = off;
+        }
     }
 }
 
 __device__ __noinline__ float act_fwd_slow(int act, float v) { return act_fwd(act, v); }
 
+// Forward convolution.  Latency structure (the kernel is bound by the im2col gather, not by the
+// tensor pipe): a thread keeps the raw taps of the next D k-blocks in registers (for packed uint8
+// frames D = 8 covers a whole 8x8x4 receptive field: every DRAM round trip of a row is in flight at
+// once), the weight tiles arrive by cp.async.bulk two k-blocks ahead into a 4-deep ring signalled
+// by mbarrier transaction counts, and tcgen05.commit releases A stage / B stage pairs.
+//
 // EXACT_A: uint8 observations with integer bounds.  (x - low) is a small integer, exactly
 // representable in tf32, so the im2col operand needs no lo part: 2 MMAs per k-step instead of 3,
 // no LUT, half the A-tile bytes; the 1/(high - low) of the normalisation is applied to the fp32
 // accumulator in the epilogue (one true division per output).  vs. the reference's
 // fl((x-low)/(high-low)) * w summed in fp32 the difference is <= 2^-23 relative per term.
-template <int ELEM, bool EXACT_A>
-__global__ void __launch_bounds__(kTcThreads) conv_fwd_tc_kernel(const ConvTcParams p) {
+// VEC: 4 consecutive taps are contiguous and aligned (4 packed bytes / two 8-byte fp32 loads).
+template <int ELEM, bool EXACT_A, bool VEC, int D>
+__global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const ConvTcParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
+    constexpr int RAWN = (ELEM == EL_U8 && VEC) ? 4 : 16;      // raw words per thread per k-block
+    constexpr int CH = kTcBK / 4 / 2;                          // 4-tap chunks per thread per k-block (4)
     const int tid = threadIdx.x, warp = tid >> 5;
     const int row = tid & (kTcBM - 1), half = tid >> 7;       // im2col row, which 16 of the 32 k
     const uint32_t a_bytes = kTcBM * kTcBK * 4, b_bytes = (uint32_t)p.n_pad * kTcBK * 4;
-    // carve (all addresses are 32-bit shared-space addresses so that the compiler emits LDS/STS):
-    //   [stage][A_hi, A_lo, B_hi, B_lo] | koff | lut | bias | barriers | tmem ptr
+    // carve (32-bit shared-space addresses so that the compiler emits LDS/STS):
+    //   A stages [hi (, lo)] | B stages [hi, lo] | koff | lut | bias | barriers | tmem ptr
     const uint32_t sbase = (tc::smem_u32(smem_raw) + 127u) & ~127u;
-    const uint32_t stage_bytes = (EXACT_A ? 1 : 2) * a_bytes + 2 * b_bytes;
-    auto a_hi = [&](int s) { return sbase + (uint32_t)s * stage_bytes; };
-    auto a_lo = [&](int s) { return sbase + (uint32_t)s * stage_bytes + a_bytes; };     // unused when EXACT_A
-    auto b_hi = [&](int s) { return sbase + (uint32_t)s * stage_bytes + (EXACT_A ? 1 : 2) * a_bytes; };
-    auto b_lo = [&](int s) { return sbase + (uint32_t)s * stage_bytes + (EXACT_A ? 1 : 2) * a_bytes + b_bytes; };
-    const uint32_t koff_a = sbase + kTcStages * stage_bytes;
+    const uint32_t a_stage = (EXACT_A ? 1 : 2) * a_bytes;
+    auto a_hi = [&](int s) { return sbase + (uint32_t)s * a_stage; };
+    auto a_lo = [&](int s) { return sbase + (uint32_t)s * a_stage + a_bytes; };          // unused when EXACT_A
+    const uint32_t bbase = sbase + kTcStages * a_stage;
+    auto b_hi = [&](int s) { return bbase + (uint32_t)s * 2 * b_bytes; };
+    auto b_lo = [&](int s) { return bbase + (uint32_t)s * 2 * b_bytes + b_bytes; };
+    const uint32_t koff_a = bbase + kTcBStages * 2 * b_bytes;
     const uint32_t lut_a = koff_a + (uint32_t)p.k_pad * 4;
     const uint32_t bias_a = lut_a + 256 * 4;
     const uint32_t bars_a = (bias_a + (uint32_t)p.n_pad * 4 + 15u) & ~15u;
-    const uint32_t tptr_a = bars_a + 8 * kTcStages;
+    const uint32_t tptr_a = bars_a + 8 * (2 * kTcStages + kTcBStages);
     uint8_t *gen = smem_raw + (sbase - tc::smem_u32(smem_raw));        // generic alias of sbase (barriers only)
-    uint64_t *bars = reinterpret_cast<uint64_t *>(gen + (bars_a - sbase));
+    uint64_t *mma_bar = reinterpret_cast<uint64_t *>(gen + (bars_a - sbase));   // [kTcStages] MMA group done
+    uint64_t *full_a = mma_bar + kTcStages;                                      // [kTcStages] im2col tile written
+    uint64_t *full_b = full_a + kTcStages;                                       // [kTcBStages] weight tile landed
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(gen + (tptr_a - sbase));
+    const int KB = p.k_pad / kTcBK;
 
     // ---- one-time setup ----------------------------------------------------------------------
-    for (int k = tid; k < p.k_pad; k += kTcThreads) {
-        int off = -1;
-        if (k < p.K) {
-            const int ci = k / p.KK, rem = k - ci * p.KK;
-            const int ky = rem / p.KS, kx = rem - ky * p.KS;
-            off = ci * p.HW + ky * p.W + kx;
+    if (tid == 0) {
+        for (int s = 0; s < kTcStages; ++s) {
+            tc::mbar_init(&mma_bar[s], 1);
+            tc::mbar_init(&full_a[s], kTcThreads / 32);      // one elected arrive per producer warp
         }
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(koff_a + 4u * k), "r"(off) : "memory");
+        for (int s = 0; s < kTcBStages; ++s) tc::mbar_init(&full_b[s], 1);
+        tc::fence_barrier_init();
     }
+    auto issue_b = [&](int kb) {       // elected thread: weight tile of k-block kb -> its ring slot
+        const int sb = kb & (kTcBStages - 1);
+        tc::mbar_expect_tx(&full_b[sb], 2 * b_bytes);
+        tc::bulk_g2s(b_hi(sb), p.w_hi + (int64_t)kb * p.n_pad * kTcBK, b_bytes, &full_b[sb]);
+        tc::bulk_g2s(b_lo(sb), p.w_lo + (int64_t)kb * p.n_pad * kTcBK, b_bytes, &full_b[sb]);
+    };
+    for (int k = tid; k < p.k_pad; k += kTcThreads + 32)
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(koff_a + 4u * k), "r"(__ldg(p.koff + k)) : "memory");
     if (ELEM == EL_U8 && !EXACT_A)
-        for (int i = tid; i < 256; i += kTcThreads) {
+        for (int i = tid; i < 256; i += kTcThreads + 32) {
             const float v = p.normalize ? __fdiv_rn((float)i - p.low, p.high - p.low) : (float)i;
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(lut_a + 4u * i), "f"(v) : "memory");
         }
-    for (int n = tid; n < p.n_pad; n += kTcThreads) {
+    for (int n = tid; n < p.n_pad; n += kTcThreads + 32) {
         const float v = (n < p.N && p.bias) ? p.bias[n] : 0.f;
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_a + 4u * n), "f"(v) : "memory");
     }
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < p.n_pad) tmem_cols <<= 1;
     if (warp == 0) tc::tmem_alloc(tmem_ptr, tmem_cols);
-    if (tid == 0) {
-        for (int s = 0; s < kTcStages; ++s) tc::mbar_init(&bars[s], 1);
-        tc::fence_barrier_init();
-    }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_d = *tmem_ptr;
+    const uint32_t idesc = tc::make_idesc_tf32(kTcBM, p.n_pad);
+    const uint32_t lbo_a = kTcBM * 16, lbo_b = (uint32_t)p.n_pad * 16;
 
-    // this thread's im2col row (output pixel); rows beyond M read a safe in-bounds address
+    if (warp == kTcThreads / 32) {
+        // ---- MMA warp: one lane feeds the tensor core; nothing else sits on its issue path ------------
+        if ((tid & 31) == 0) {
+            issue_b(0);
+            if (KB > 1) issue_b(1);
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb & (kTcStages - 1), sb = kb & (kTcBStages - 1);
+                if (kb + 2 < KB) {
+                    // B ring slot (kb+2)%4 was last read by MMA group kb-2
+                    if (kb >= kTcStages) tc::mbar_wait(&mma_bar[s], (uint32_t)((kb / kTcStages - 1) & 1));
+                    issue_b(kb + 2);
+                }
+                tc::mbar_wait(&full_b[sb], (uint32_t)((kb / kTcBStages) & 1));
+                tc::mbar_wait(&full_a[s], (uint32_t)((kb / kTcStages) & 1));
+                tc::tc_fence_after();
+                // descriptors of consecutive k-steps differ only in the 14-bit start-address field
+                const uint64_t dah0 = tc::make_desc(a_hi(s), lbo_a, 128), dal0 = tc::make_desc(a_lo(s), lbo_a, 128);
+                const uint64_t dbh0 = tc::make_desc(b_hi(sb), lbo_b, 128), dbl0 = tc::make_desc(b_lo(sb), lbo_b, 128);
+                const uint64_t da_step = (uint64_t)((2 * lbo_a) >> 4), db_step = (uint64_t)((2 * lbo_b) >> 4);
+#pragma unroll
+                for (int j = 0; j < kTcBK / 8; ++j) {      // one MMA k-step = 8 tf32 = 2 core-matrix columns
+                    tc::mma_tf32(tmem_d, dah0 + j * da_step, dbh0 + j * db_step, idesc, (kb | j) ? 1u : 0u);
+                    if (!EXACT_A) tc::mma_tf32(tmem_d, dal0 + j * da_step, dbh0 + j * db_step, idesc, 1u);
+                    tc::mma_tf32(tmem_d, dah0 + j * da_step, dbl0 + j * db_step, idesc, 1u);
+                }
+                tc::mma_commit(&mma_bar[s]);
+            }
+        }
+        __syncwarp();
+    }
+
+    if (warp < kTcThreads / 32) {
+    // ---- producer warps: this thread's im2col row (output pixel); rows beyond M read a safe address
     const int m = blockIdx.x * kTcBM + row;
     const bool row_ok = m < p.M;
     int64_t rowbase = p.gather ? p.gather[0] * p.in_bstride : 0;
@@ -228,81 +310,49 @@ __global__ void __launch_bounds__(kTcThreads) conv_fwd_tc_kernel(const ConvTcPar
     }
     const uint8_t *row_u8 = static_cast<const uint8_t *>(p.x) + rowbase;
     const float *row_f32 = static_cast<const float *>(p.x) + rowbase;
-    const uint32_t idesc = tc::make_idesc_tf32(kTcBM, p.n_pad);
-    const uint32_t lbo_a = kTcBM * 16, lbo_b = (uint32_t)p.n_pad * 16;
-    const int KB = p.k_pad / kTcBK;
     const uint32_t row_off = (uint32_t)(row >> 3) * 128 + (uint32_t)(row & 7) * 16;   // (r/8)*128 + (r%8)*16
-    constexpr int CH = kTcBK / 4 / 2;          // 4-tap chunks per thread per stage (4)
-    const int b_items = p.n_pad * (kTcBK / 4); // float4 items of one B operand tile (<= 2 per thread for N<=64)
+    const float exact_bias = 8388608.f + p.low;       // EXACT_A: (2^23 + byte) - (2^23 + low), both exact
 
-    // register double buffer: the gather of k-block kb+1 is in flight while kb is converted,
-    // fenced, synchronised and its MMAs are issued
-    uint32_t raw[CH * 4];
-    uint32_t vmask = 0;
-    float4 bh[2], bl[2];                       // this thread's share of the pre-split weight tile (n_pad <= 64)
-    auto gather = [&](int kb) {
+    uint32_t raw[D][RAWN];
+    auto gather = [&](int kb, uint32_t (&dst)[RAWN]) {
         const int k0 = kb * kTcBK + half * (CH * 4);
-        {
-            const float4 *gh = reinterpret_cast<const float4 *>(p.w_hi + (int64_t)kb * p.n_pad * kTcBK);
-            const float4 *gl = reinterpret_cast<const float4 *>(p.w_lo + (int64_t)kb * p.n_pad * kTcBK);
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int it = tid + i * kTcThreads;
-                if (it < b_items) { bh[i] = __ldg(gh + it); bl[i] = __ldg(gl + it); }
-            }
-        }
-        vmask = 0;
-        if (ELEM != EL_U8 && p.vec4) {          // fp32 activations: 4 taps = 2 aligned 8-byte loads
+        if (ELEM != EL_U8 && VEC) {             // fp32 activations: 4 taps = 2 aligned 8-byte loads
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
-                const int off = (int)tc::lds32(koff_a + 4u * (k0 + c * 4));
-                if (off >= 0) vmask |= 0xFu << (c * 4);
-                const float2 *q2 = reinterpret_cast<const float2 *>(row_f32 + (off < 0 ? 0 : off));
+                const uint32_t off = tc::lds32(koff_a + 4u * (k0 + c * 4));
+                const float2 *q2 = reinterpret_cast<const float2 *>(row_f32 + off);
                 const float2 a = __ldg(q2), b = __ldg(q2 + 1);
-                raw[c * 4 + 0] = __float_as_uint(a.x); raw[c * 4 + 1] = __float_as_uint(a.y);
-                raw[c * 4 + 2] = __float_as_uint(b.x); raw[c * 4 + 3] = __float_as_uint(b.y);
+                dst[c * 4 + 0] = __float_as_uint(a.x); dst[c * 4 + 1] = __float_as_uint(a.y);
+                dst[c * 4 + 2] = __float_as_uint(b.x); dst[c * 4 + 3] = __float_as_uint(b.y);
             }
-        } else if (ELEM == EL_U8 && p.vec4) {
+        } else if (ELEM == EL_U8 && VEC) {
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
-                const int off = (int)tc::lds32(koff_a + 4u * (k0 + c * 4));
-                if (off >= 0) vmask |= 0xFu << (c * 4);
-                raw[c] = __ldg(reinterpret_cast<const uint32_t *>(row_u8 + (off < 0 ? 0 : off)));   // 4 packed taps
+                const uint32_t off = tc::lds32(koff_a + 4u * (k0 + c * 4));
+                dst[c] = __ldg(reinterpret_cast<const uint32_t *>(row_u8 + off));   // 4 packed taps
             }
         } else {
 #pragma unroll
             for (int j = 0; j < CH * 4; ++j) {
-                const int off = (int)tc::lds32(koff_a + 4u * (k0 + j));
-                vmask |= (uint32_t)(off >= 0) << j;
-                const int o2 = off < 0 ? 0 : off;
-                if (ELEM == EL_U8) raw[j] = (uint32_t)__ldg(row_u8 + o2);
-                else raw[j] = __float_as_uint(__ldg(row_f32 + o2));
+                const uint32_t off = tc::lds32(koff_a + 4u * (k0 + j));
+                if (ELEM == EL_U8) dst[j] = (uint32_t)__ldg(row_u8 + off);
+                else dst[j] = __float_as_uint(__ldg(row_f32 + off));
             }
         }
-        if (!row_ok) vmask = 0;
     };
-    gather(0);
-
-    for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb & 1;
-        if (kb >= kTcStages) tc::mbar_wait(&bars[s], (uint32_t)((kb / kTcStages - 1) & 1));   // stage free again
-        // ---- B tiles: 16-byte stores of the prefetched pre-split weights
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int it = tid + i * kTcThreads;
-            if (it < b_items) {
-                tc::sts128(b_hi(s) + 16u * it, bh[i].x, bh[i].y, bh[i].z, bh[i].w);
-                tc::sts128(b_lo(s) + 16u * it, bl[i].x, bl[i].y, bl[i].z, bl[i].w);
-            }
-        }
-        for (int it = tid + 2 * kTcThreads; it < b_items; it += kTcThreads) {      // wide layers (n_pad > 64)
-            const float4 h = __ldg(reinterpret_cast<const float4 *>(p.w_hi + (int64_t)kb * p.n_pad * kTcBK) + it);
-            const float4 l = __ldg(reinterpret_cast<const float4 *>(p.w_lo + (int64_t)kb * p.n_pad * kTcBK) + it);
-            tc::sts128(b_hi(s) + 16u * it, h.x, h.y, h.z, h.w);
-            tc::sts128(b_lo(s) + 16u * it, l.x, l.y, l.z, l.w);
-        }
+    for (int d = 0; d < D; ++d)
+        if (d < KB) gather(d, raw[d]);
+
+    auto step = [&](int kb, uint32_t (&cur)[RAWN]) {
+        const int s = kb & (kTcStages - 1);
+        // MMA group kb-2 done: A stage s is free again
+        if (kb >= kTcStages) tc::mbar_wait(&mma_bar[s], (uint32_t)((kb / kTcStages - 1) & 1));
         // ---- convert + hi/lo split + 16-byte smem stores of the gathered taps
         const uint32_t ah = a_hi(s) + row_off + (uint32_t)(half * CH) * lbo_a, al = a_lo(s) + row_off + (uint32_t)(half * CH) * lbo_a;
+        const int k0 = kb * kTcBK + half * (CH * 4);
+        // padded taps meet zero weights; only non-finite fp32 garbage could leak through them
+        const bool tail = ELEM != EL_U8 && kb == KB - 1 && p.K != p.k_pad;
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
             float hi[4], lo[4];
@@ -311,59 +361,60 @@ __global__ void __launch_bounds__(kTcThreads) conv_fwd_tc_kernel(const ConvTcPar
                 const int kk = c * 4 + j;
                 float v;
                 if (ELEM == EL_U8) {
-                    const uint32_t byte = p.vec4 ? ((raw[c] >> (8 * j)) & 0xFFu) : raw[kk];
-                    if (EXACT_A) v = (float)((int)byte - (int)p.low);            // exact in tf32
-                    else v = __uint_as_float(tc::lds32(lut_a + 4u * byte));
-                } else if (ELEM == EL_F32_NORM) v = __fdiv_rn(__uint_as_float(raw[kk]) - p.low, p.high - p.low);
-                else v = __uint_as_float(raw[kk]);
-                v = ((vmask >> kk) & 1u) ? v : 0.f;
+                    if (EXACT_A) {
+                        const uint32_t w = VEC ? __byte_perm(cur[c], 0x4B000000u, 0x7650u + j) : (cur[kk] | 0x4B000000u);
+                        v = __uint_as_float(w) - exact_bias;                       // exact in tf32
+                    } else {
+                        const uint32_t byte = VEC ? ((cur[c] >> (8 * j)) & 0xFFu) : cur[kk];
+                        v = __uint_as_float(tc::lds32(lut_a + 4u * byte));
+                    }
+                } else if (ELEM == EL_F32_NORM) v = __fdiv_rn(__uint_as_float(cur[kk]) - p.low, p.high - p.low);
+                else v = __uint_as_float(cur[kk]);
+                if (tail) v = (k0 + kk < p.K) ? v : 0.f;
                 if (EXACT_A) { hi[j] = v; lo[j] = 0.f; }
                 else { hi[j] = tc::tf32_rn(v); lo[j] = v - hi[j]; }
             }
             tc::sts128(ah + (uint32_t)c * lbo_a, hi[0], hi[1], hi[2], hi[3]);
             if (!EXACT_A) tc::sts128(al + (uint32_t)c * lbo_a, lo[0], lo[1], lo[2], lo[3]);
         }
-        if (kb + 1 < KB) gather(kb + 1);     // next k-block's loads overlap the fence / barrier / MMA issue
-        tc::fence_async_smem();              // generic-proxy smem writes -> visible to the async (tensor) proxy
-        __syncthreads();
-        if (tid == 0) {
-            tc::tc_fence_after();
+        if (kb + D < KB) gather(kb + D, cur);   // refill this register slot D k-blocks ahead
+        tc::fence_async_smem();                  // generic-proxy smem writes -> visible to the async (tensor) proxy
+        __syncwarp();
+        if ((tid & 31) == 0) tc::mbar_arrive(&full_a[s]);
+    };
+    for (int kb0 = 0; kb0 < KB; kb0 += D) {
 #pragma unroll
-            for (int j = 0; j < kTcBK / 8; ++j) {      // one MMA k-step = 8 tf32 = 2 core-matrix columns
-                const uint64_t dah = tc::make_desc(a_hi(s) + 2 * j * lbo_a, lbo_a, 128);
-                const uint64_t dal = tc::make_desc(a_lo(s) + 2 * j * lbo_a, lbo_a, 128);
-                const uint64_t dbh = tc::make_desc(b_hi(s) + 2 * j * lbo_b, lbo_b, 128);
-                const uint64_t dbl = tc::make_desc(b_lo(s) + 2 * j * lbo_b, lbo_b, 128);
-                tc::mma_tf32(tmem_d, dah, dbh, idesc, (kb | j) ? 1u : 0u);
-                if (!EXACT_A) tc::mma_tf32(tmem_d, dal, dbh, idesc, 1u);
-                tc::mma_tf32(tmem_d, dah, dbl, idesc, 1u);
-            }
-            tc::mma_commit(&bars[s]);
-        }
+        for (int d = 0; d < D; ++d)
+            if (kb0 + d < KB) step(kb0 + d, raw[d]);
     }
     // ---- wait for every outstanding MMA group ----------------------------------------------------
     for (int s = 0; s < kTcStages; ++s) {
         const int uses = (KB - s + kTcStages - 1) / kTcStages;      // k-blocks that used stage s
-        if (uses > 0) tc::mbar_wait(&bars[s], (uint32_t)((uses - 1) & 1));
+        if (uses > 0) tc::mbar_wait(&mma_bar[s], (uint32_t)((uses - 1) & 1));
     }
     tc::tc_fence_after();
 
-    // ---- epilogue (warps 0-3: one TMEM lane quarter each): TMEM -> regs -> bias + act -> NCHW ------
-    if (warp < 4) {
+    // ---- epilogue: warp w owns TMEM lanes 32*(w%4)..+31 (its rows) and the 16-column groups of parity w/4
+    {
+        const int q = warp & 3;
+        const int er = q * 32 + (tid & 31);                  // tile row of this lane
+        const int em = blockIdx.x * kTcBM + er;
+        const bool e_ok = em < p.M;
         int b_img = 0, pix = 0;
-        if (row_ok) { b_img = m / p.P; pix = m - b_img * p.P; }
+        if (e_ok) { b_img = em / p.P; pix = em - b_img * p.P; }
         const bool relu = p.act == B2RL_ACT_RELU, ident = p.act == B2RL_ACT_NONE;
-        for (int c0 = 0; c0 < p.n_pad; c0 += 32) {
-            uint32_t r[32];
-            tc::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
-            if (row_ok) {
+        const float scale = (EXACT_A && p.normalize) ? 1.0f / (p.high - p.low) : 1.0f;
+        for (int c0 = (warp >> 2) * 16; c0 < p.n_pad; c0 += 32) {
+            uint32_t r[16];
+            tc::tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            if (e_ok) {
                 float *o = p.out + ((int64_t)b_img * p.N + c0) * p.P + pix;
                 float *po = p.pre_out ? p.pre_out + ((int64_t)b_img * p.N + c0) * p.P + pix : nullptr;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
+                for (int j = 0; j < 16; ++j) {
                     if (c0 + j < p.N) {
                         float acc = __uint_as_float(r[j]);
-                        if (EXACT_A && p.normalize) acc = __fdiv_rn(acc, p.high - p.low);
+                        if (EXACT_A) acc *= scale;
                         float v = acc + __uint_as_float(tc::lds32(bias_a + 4u * (c0 + j)));
                         if (po) po[(int64_t)j * p.P] = v;
                         v = relu ? fmaxf(v, 0.f) : (ident ? v : act_fwd_slow(p.act, v));
@@ -373,6 +424,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_fwd_tc_kernel(const ConvTcPar
             }
         }
     }
+    }   // producer warps
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem_d, tmem_cols);
@@ -381,7 +433,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_fwd_tc_kernel(const ConvTcPar
 static inline size_t conv_tc_wsplit_floats(const b2rl_layer &l) {
     const int K = l.in_c * l.ksize * l.ksize;
     const int n_pad = (l.out_c + 15) / 16 * 16, k_pad = (K + kTcBK - 1) / kTcBK * kTcBK;
-    return (size_t)2 * n_pad * k_pad;
+    return (size_t)2 * n_pad * k_pad + k_pad;      // hi, lo, tap offsets
 }
 
 // returns B2RL_OK, or 1 when the shape is outside what the tensor-core kernel handles (caller falls
@@ -391,43 +443,49 @@ static int launch_conv_fwd_tc(const b2rl_layer &l, const Operand &A, const float
     const int KK = l.ksize * l.ksize, K = l.in_c * KK, P = l.out_h * l.out_w;
     const int n_pad = (l.out_c + 15) / 16 * 16, k_pad = (K + kTcBK - 1) / kTcBK * kTcBK;
     if (n_pad > 256 || k_pad > 8192 || rows * (int64_t)P > INT32_MAX) return 1;
-    const size_t smem = conv_tc_smem_bytes(n_pad, k_pad);
+    const bool exact = A.u8 && (!A.normalize || (A.low == floorf(A.low) && fabsf(A.low) <= 1024.f));
+    const size_t smem = conv_tc_smem_bytes(n_pad, k_pad, exact ? 1 : 2);
     if (smem > 200 * 1024 || wsplit == nullptr || conv_tc_wsplit_floats(l) > wsplit_cap) return 1;
+    if (reinterpret_cast<uintptr_t>(wsplit) % 16 != 0) return 1;          // bulk copies need 16-byte aligned sources
     float *w_hi = wsplit, *w_lo = wsplit + (size_t)n_pad * k_pad;
+    uint32_t *koff = reinterpret_cast<uint32_t *>(wsplit + (size_t)2 * n_pad * k_pad);
     {
         const int total = n_pad * k_pad;
-        weight_split_kernel<<<(total + 255) / 256, 256, 0, s>>>(W, l.out_c, K, n_pad, k_pad, w_hi, w_lo);
+        weight_split_kernel<<<(total + 255) / 256, 256, 0, s>>>(W, l.out_c, K, n_pad, k_pad, w_hi, w_lo, KK, l.ksize, l.in_h * l.in_w,
+                                                                l.in_w, koff);
         B2RL_LAUNCH_CHECK();
     }
     ConvTcParams p;
-    p.x = A.ptr; p.w_hi = w_hi; p.w_lo = w_lo; p.bias = bias; p.out = out; p.pre_out = pre_out; p.gather = A.row.gather;
+    p.x = A.ptr; p.w_hi = w_hi; p.w_lo = w_lo; p.koff = koff; p.bias = bias; p.out = out; p.pre_out = pre_out; p.gather = A.row.gather;
     p.in_bstride = (int64_t)l.in_c * l.in_h * l.in_w;
     p.M = (int)(rows * P); p.N = l.out_c; p.K = K; p.n_pad = n_pad; p.k_pad = k_pad;
     p.P = P; p.OW = l.out_w; p.sy = l.stride * l.in_w; p.sx = l.stride;
     p.KK = KK; p.KS = l.ksize; p.HW = l.in_h * l.in_w; p.W = l.in_w;
-    p.act = l.act; p.normalize = A.normalize; p.low = A.low; p.high = A.high;
+    p.act = l.act; p.normalize = A.normalize; p.low = A.normalize ? A.low : 0.f; p.high = A.normalize ? A.high : 1.f;
     // 4 consecutive taps are 4 contiguous, 4-byte aligned bytes when the kernel width, the column
     // stride, the row pitch and the plane / image sizes are all multiples of 4
+    bool vec;
     if (A.u8)
-        p.vec4 = (l.ksize % 4 == 0 && l.stride % 4 == 0 && l.in_w % 4 == 0 && (l.in_h * l.in_w) % 4 == 0 &&
-                  (reinterpret_cast<uintptr_t>(A.ptr) % 4 == 0)) ? 1 : 0;
+        vec = l.ksize % 4 == 0 && l.stride % 4 == 0 && l.in_w % 4 == 0 && (l.in_h * l.in_w) % 4 == 0 &&
+              reinterpret_cast<uintptr_t>(A.ptr) % 4 == 0;
     else   // fp32: every 4-tap chunk starts on an even float (8-byte aligned) -> two 8-byte loads
-        p.vec4 = (l.ksize % 4 == 0 && l.stride % 2 == 0 && l.in_w % 2 == 0 && (l.in_h * l.in_w) % 2 == 0 &&
-                  p.in_bstride % 2 == 0 && (reinterpret_cast<uintptr_t>(A.ptr) % 8 == 0)) ? 1 : 0;
+        vec = l.ksize % 4 == 0 && l.stride % 2 == 0 && l.in_w % 2 == 0 && (l.in_h * l.in_w) % 2 == 0 &&
+              p.in_bstride % 2 == 0 && reinterpret_cast<uintptr_t>(A.ptr) % 8 == 0;
     const int grid = (p.M + kTcBM - 1) / kTcBM;
     auto launch = [&](auto kern) -> int {
         B2RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kTcThreads, smem, s>>>(p);
+        kern<<<grid, kTcThreads + 32, smem, s>>>(p);
         B2RL_LAUNCH_CHECK();
         return B2RL_OK;
     };
     switch (A.elem_kind()) {
-        case EL_U8: {
-            const bool exact = (!A.normalize || (A.low == floorf(A.low) && fabsf(A.low) <= 1024.f));
-            return exact ? launch(conv_fwd_tc_kernel<EL_U8, true>) : launch(conv_fwd_tc_kernel<EL_U8, false>);
-        }
-        case EL_F32_NORM: return launch(conv_fwd_tc_kernel<EL_F32_NORM, false>);
-        default: return launch(conv_fwd_tc_kernel<EL_F32, false>);
+        case EL_U8:
+            if (exact) return vec ? launch(conv_fwd_tc_kernel<EL_U8, true, true, 8>) : launch(conv_fwd_tc_kernel<EL_U8, true, false, 2>);
+            return vec ? launch(conv_fwd_tc_kernel<EL_U8, false, true, 8>) : launch(conv_fwd_tc_kernel<EL_U8, false, false, 2>);
+        case EL_F32_NORM:
+            return vec ? launch(conv_fwd_tc_kernel<EL_F32_NORM, false, true, 2>) : launch(conv_fwd_tc_kernel<EL_F32_NORM, false, false, 2>);
+        default:
+            return vec ? launch(conv_fwd_tc_kernel<EL_F32, false, true, 4>) : launch(conv_fwd_tc_kernel<EL_F32, false, false, 2>);
     }
 }
 
