@@ -505,57 +505,68 @@ static int launch_conv_fwd_tc(const b2rl_layer &l, const Operand &A, const float
 //   B (K-major, no swizzle):  (co n,  pixel k) at (k/4)*LBO_b + (n/8)*128 + (n%8)*16 + (k%4)*4
 // ------------------------------------------------------------------------------------------------
 struct ConvWgradTcParams {
-    const void *x;              // layer input (uint8 frames / fp32 activations), NCHW
-    const float *g;             // dL/d(conv output), NCHW [rows, Cout, P]
-    float *partial;             // [splits][taps_pad... = M][N] fp32
-    const int64_t *gather;
+    const void *x;              // layer input: uint8 frames / fp32 activations (NCHW)
+    const float *g;             // dL/d(layer output), NCHW [rows, N, P]
+    float *partial;             // [splits][Mtaps (+1)][N]
+    const int64_t *gather;      // optional ring rows per batch row
     int64_t in_bstride;
     int Mtaps, N, Kpix;         // taps (Cin*k*k), Cout, rows*P
     int n_pad;
     int P, OW, sy, sx;
     int KK, KS, HW, W;
     int pix_per_cta;            // multiple of 32
-    int normalize, vec4;
+    int normalize;
     int with_bias;              // partial has Mtaps+1 rows; the last one carries the bias gradient (N <= 32)
     float low, high;
+    float inv_ow;               // 1 / OW (pixel decode without integer division)
 };
 
 constexpr uint32_t kWgLboA = kTcBM * 16 + 16;        // padded K-chunk pitch of the wgrad A tile
 constexpr uint32_t kWgABytes = (kTcBK / 4) * kWgLboA;  // 8 chunks
 
-template <int ELEM>
-__global__ void __launch_bounds__(kTcThreads) conv_wgrad_tc_kernel(const ConvWgradTcParams p) {
+static inline size_t conv_wgrad_tc_smem_bytes(int n_pad, int a_parts) {
+    return (size_t)kTcStages * ((size_t)a_parts * kWgABytes + 2 * (size_t)n_pad * kTcBK * 4) + kTcBM * 4 + 256 * 4 + 64 + 1024 + 256;
+}
+
+// Same thread roles as the forward kernel: 8 producer warps build both operand tiles, a ninth warp's
+// elected lane issues the MMAs.  EXACT_A (uint8 frames, integer low): the im2col operand is the exact
+// integer x - low (one tf32 part, 2 MMAs per k-step) and 1/(high-low) scales the fp32 partial sums.
+template <int ELEM, bool EXACT_A, bool VEC, int D>
+__global__ void __launch_bounds__(kTcThreads + 32) conv_wgrad_tc_kernel(const ConvWgradTcParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
+    constexpr int RAWN = (ELEM == EL_U8 && VEC) ? 4 : 16;
+    constexpr int CH = 4;                                   // 4-tap chunks per thread (16 taps)
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int pl = tid & 31, tg = tid >> 5;                  // pixel lane within the 32-pixel block, tap group (16 taps)
+    const int pl = tid & 31, tg = (tid >> 5) & 7;            // pixel lane within the 32-pixel block, tap group (16 taps)
     const uint32_t a_bytes = kWgABytes, b_bytes = (uint32_t)p.n_pad * kTcBK * 4;
     const uint32_t sbase = (tc::smem_u32(smem_raw) + 127u) & ~127u;
-    const uint32_t stage_bytes = 2 * (a_bytes + b_bytes);
+    const uint32_t stage_bytes = (EXACT_A ? 1 : 2) * a_bytes + 2 * b_bytes;
     auto a_hi = [&](int s) { return sbase + (uint32_t)s * stage_bytes; };
-    auto a_lo = [&](int s) { return sbase + (uint32_t)s * stage_bytes + a_bytes; };
-    auto b_hi = [&](int s) { return sbase + (uint32_t)s * stage_bytes + 2 * a_bytes; };
-    auto b_lo = [&](int s) { return sbase + (uint32_t)s * stage_bytes + 2 * a_bytes + b_bytes; };
+    auto a_lo = [&](int s) { return sbase + (uint32_t)s * stage_bytes + a_bytes; };     // unused when EXACT_A
+    auto b_hi = [&](int s) { return sbase + (uint32_t)s * stage_bytes + (EXACT_A ? 1 : 2) * a_bytes; };
+    auto b_lo = [&](int s) { return sbase + (uint32_t)s * stage_bytes + (EXACT_A ? 1 : 2) * a_bytes + b_bytes; };
     const uint32_t toff_a = sbase + kTcStages * stage_bytes;              // tap offsets of this CTA's 128 taps
     const uint32_t lut_a = toff_a + kTcBM * 4;
     const uint32_t bars_a = (lut_a + 256 * 4 + 15u) & ~15u;
-    const uint32_t tptr_a = bars_a + 8 * kTcStages;
+    const uint32_t tptr_a = bars_a + 8 * 2 * kTcStages;
     uint8_t *gen = smem_raw + (sbase - tc::smem_u32(smem_raw));
-    uint64_t *bars = reinterpret_cast<uint64_t *>(gen + (bars_a - sbase));
+    uint64_t *mma_bar = reinterpret_cast<uint64_t *>(gen + (bars_a - sbase));   // [kTcStages] MMA group done
+    uint64_t *full = mma_bar + kTcStages;                                        // [kTcStages] both tiles written
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(gen + (tptr_a - sbase));
 
     const int tap0 = blockIdx.x * kTcBM;
-    for (int t = tid; t < kTcBM; t += kTcThreads) {
-        const int k = tap0 + t;
-        int off = -1;
+    if (tid < kTcBM) {
+        const int k = tap0 + tid;
+        uint32_t off = 0;                    // tile rows past Mtaps compute garbage that is never stored
         if (k < p.Mtaps) {
             const int ci = k / p.KK, rem = k - ci * p.KK;
             const int ky = rem / p.KS, kx = rem - ky * p.KS;
-            off = ci * p.HW + ky * p.W + kx;
+            off = (uint32_t)(ci * p.HW + ky * p.W + kx);
         }
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(toff_a + 4u * t), "r"(off) : "memory");
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(toff_a + 4u * tid), "r"(off) : "memory");
     }
-    if (ELEM == EL_U8)
-        for (int i = tid; i < 256; i += kTcThreads) {
+    if (ELEM == EL_U8 && !EXACT_A)
+        for (int i = tid; i < 256; i += kTcThreads + 32) {
             const float v = p.normalize ? __fdiv_rn((float)i - p.low, p.high - p.low) : (float)i;
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(lut_a + 4u * i), "f"(v) : "memory");
         }
@@ -563,7 +574,10 @@ __global__ void __launch_bounds__(kTcThreads) conv_wgrad_tc_kernel(const ConvWgr
     while ((int)tmem_cols < p.n_pad) tmem_cols <<= 1;
     if (warp == 0) tc::tmem_alloc(tmem_ptr, tmem_cols);
     if (tid == 0) {
-        for (int s = 0; s < kTcStages; ++s) tc::mbar_init(&bars[s], 1);
+        for (int s = 0; s < kTcStages; ++s) {
+            tc::mbar_init(&mma_bar[s], 1);
+            tc::mbar_init(&full[s], kTcThreads / 32);
+        }
         tc::fence_barrier_init();
     }
     tc::tc_fence_before();
@@ -576,153 +590,162 @@ __global__ void __launch_bounds__(kTcThreads) conv_wgrad_tc_kernel(const ConvWgr
     const int KB = (pix1 - pix0 + kTcBK - 1) / kTcBK;
     const uint32_t idesc = tc::make_idesc_tf32(kTcBM, p.n_pad);
     const uint32_t lbo_b = (uint32_t)p.n_pad * 16;
-    constexpr int CH = 4;                                   // 4-tap chunks per thread (16 taps)
-    const int64_t safe_base = p.gather ? p.gather[0] * p.in_bstride : 0;
 
-    uint32_t raw[CH * 4];
-    uint32_t vmask = 0;
-    float gval[4];
-    float bsum = 0.f;                                       // bias gradient of channel tid/8 over this CTA's pixels
-    auto gather = [&](int kb) {
-        // ---- A: this thread's pixel, taps [tg*16, tg*16+16)
-        const int pix = pix0 + kb * kTcBK + pl;
-        const bool pok = pix < pix1;
-        int64_t base = safe_base;
-        if (pok) {
-            const int b = pix / p.P, pp = pix - b * p.P;
-            const int oy = pp / p.OW, ox = pp - oy * p.OW;
-            const int64_t bb = p.gather ? p.gather[b] : (int64_t)b;
-            base = bb * p.in_bstride + (int64_t)(oy * p.sy + ox * p.sx);
-        }
-        vmask = 0;
-        if (ELEM == EL_U8 && p.vec4) {
-            const uint8_t *rp = static_cast<const uint8_t *>(p.x) + base;
+    if (warp == kTcThreads / 32) {
+        // ---- MMA warp ---------------------------------------------------------------------------------
+        if ((tid & 31) == 0) {
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb & (kTcStages - 1);
+                tc::mbar_wait(&full[s], (uint32_t)((kb / kTcStages) & 1));
+                tc::tc_fence_after();
+                const uint64_t dah0 = tc::make_desc(a_hi(s), kWgLboA, 128), dal0 = tc::make_desc(a_lo(s), kWgLboA, 128);
+                const uint64_t dbh0 = tc::make_desc(b_hi(s), lbo_b, 128), dbl0 = tc::make_desc(b_lo(s), lbo_b, 128);
+                const uint64_t da_step = (uint64_t)((2 * kWgLboA) >> 4), db_step = (uint64_t)((2 * lbo_b) >> 4);
 #pragma unroll
-            for (int c = 0; c < CH; ++c) {
-                const int off = (int)tc::lds32(toff_a + 4u * (tg * 16 + c * 4));
-                if (off >= 0) vmask |= 0xFu << (c * 4);
-                raw[c] = __ldg(reinterpret_cast<const uint32_t *>(rp + (off < 0 ? 0 : off)));
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < CH * 4; ++j) {
-                const int off = (int)tc::lds32(toff_a + 4u * (tg * 16 + j));
-                vmask |= (uint32_t)(off >= 0) << j;
-                const int o2 = off < 0 ? 0 : off;
-                if (ELEM == EL_U8) raw[j] = (uint32_t)__ldg(static_cast<const uint8_t *>(p.x) + base + o2);
-                else raw[j] = __float_as_uint(__ldg(static_cast<const float *>(p.x) + base + o2));
+                for (int j = 0; j < kTcBK / 8; ++j) {                   // 8 pixels per MMA
+                    tc::mma_tf32(tmem_d, dah0 + j * da_step, dbh0 + j * db_step, idesc, (kb | j) ? 1u : 0u);
+                    if (!EXACT_A) tc::mma_tf32(tmem_d, dal0 + j * da_step, dbh0 + j * db_step, idesc, 1u);
+                    tc::mma_tf32(tmem_d, dah0 + j * da_step, dbl0 + j * db_step, idesc, 1u);
+                }
+                tc::mma_commit(&mma_bar[s]);
             }
         }
-        if (!pok) vmask = 0;
-        // ---- B: channel n = tid / 8 (+32 per pass), 4 consecutive pixels starting at (tid % 8) * 4
-        //      (only the first pass is prefetched; n_pad > 32 re-loads in the store phase)
-        const int n = tid >> 3, q = tid & 7;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int px = pix0 + kb * kTcBK + q * 4 + j;
-            float v = 0.f;
-            if (n < p.N && px < pix1) {
-                const int b = px / p.P, pp = px - b * p.P;
-                v = __ldg(p.g + ((int64_t)b * p.N + n) * p.P + pp);
+        __syncwarp();
+    } else {
+        // ---- producer warps ---------------------------------------------------------------------------
+        const int64_t safe_base = p.gather ? p.gather[0] * p.in_bstride : 0;
+        const float exact_bias = 8388608.f + p.low;
+        const int n = (tid >> 3) & 31, q = tid & 7;             // B: channel n (+32 per pass), pixels q*4..q*4+3
+        uint32_t raw[D][RAWN];
+        float gval[D][4];
+        float bsum = 0.f;                                       // bias gradient of channel n over this CTA's pixels
+        auto gather = [&](int kb, uint32_t (&dst)[RAWN], float (&gv)[4]) {
+            // ---- A: this thread's pixel, taps [tg*16, tg*16+16); pixels past pix1 meet zero G values
+            const int pix = min(pix0 + kb * kTcBK + pl, pix1 - 1);
+            int64_t base;
+            {
+                const int b = pix / p.P, pp = pix - b * p.P;
+                const int oy = __float2int_rz(((float)pp + 0.5f) * p.inv_ow), ox = pp - oy * p.OW;
+                const int64_t bb = p.gather ? p.gather[b] : (int64_t)b;
+                base = bb * p.in_bstride + (int64_t)(oy * p.sy + ox * p.sx);
             }
-            gval[j] = v;
-        }
-    };
-    if (KB > 0) gather(0);
-
-    for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb & 1;
-        if (kb >= kTcStages) tc::mbar_wait(&bars[s], (uint32_t)((kb / kTcStages - 1) & 1));
-        // ---- A tile stores (transposed scatter): (k/4)*LBO_a + (m/8)*128 + (m%8)*16 + (k%4)*4, k = pl
-        const uint32_t a_off = (uint32_t)(pl >> 2) * kWgLboA + (uint32_t)(pl & 3) * 4;
+            if (ELEM == EL_U8 && VEC) {
+                const uint8_t *rp = static_cast<const uint8_t *>(p.x) + base;
 #pragma unroll
-        for (int c = 0; c < CH; ++c) {
+                for (int c = 0; c < CH; ++c)
+                    dst[c] = __ldg(reinterpret_cast<const uint32_t *>(rp + tc::lds32(toff_a + 4u * (tg * 16 + c * 4))));
+            } else {
+#pragma unroll
+                for (int j = 0; j < CH * 4; ++j) {
+                    const uint32_t off = tc::lds32(toff_a + 4u * (tg * 16 + j));
+                    if (ELEM == EL_U8) dst[j] = (uint32_t)__ldg(static_cast<const uint8_t *>(p.x) + base + off);
+                    else dst[j] = __float_as_uint(__ldg(static_cast<const float *>(p.x) + base + off));
+                }
+            }
+            // ---- B: 4 consecutive pixels of channel n (only the first 32 channels are prefetched)
+            const int px0 = pix0 + kb * kTcBK + q * 4;
+            int b = px0 / p.P, pp = px0 - b * p.P;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int kk = c * 4 + j;
-                float v;
-                if (ELEM == EL_U8) {
-                    const uint32_t byte = p.vec4 ? ((raw[c] >> (8 * j)) & 0xFFu) : raw[kk];
-                    v = __uint_as_float(tc::lds32(lut_a + 4u * byte));
-                } else if (ELEM == EL_F32_NORM) v = __fdiv_rn(__uint_as_float(raw[kk]) - p.low, p.high - p.low);
-                else v = __uint_as_float(raw[kk]);
-                v = ((vmask >> kk) & 1u) ? v : 0.f;
-                const float hi = tc::tf32_rn(v), lo = v - hi;
-                const uint32_t m_ = (uint32_t)(tg * 16 + kk);
-                const uint32_t o = a_off + (m_ >> 3) * 128 + (m_ & 7) * 16;
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(a_hi(s) + o), "f"(hi) : "memory");
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(a_lo(s) + o), "f"(lo) : "memory");
+                gv[j] = (n < p.N && px0 + j < pix1) ? __ldg(p.g + ((int64_t)b * p.N + n) * p.P + pp) : 0.f;
+                if (++pp == p.P) { pp = 0; ++b; }
             }
-        }
-        // ---- B tile stores: (k/4)*LBO_b + (n/8)*128 + (n%8)*16
-        {
-            const int n = tid >> 3, q = tid & 7;
-            float hi[4], lo[4];
+        };
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { hi[j] = tc::tf32_rn(gval[j]); lo[j] = gval[j] - hi[j]; bsum += gval[j]; }
-            const uint32_t o = (uint32_t)q * lbo_b + (uint32_t)(n >> 3) * 128 + (uint32_t)(n & 7) * 16;
-            if (n < p.n_pad) {          // n_pad may be 16: rows beyond it belong to the next K chunk
-                tc::sts128(b_hi(s) + o, hi[0], hi[1], hi[2], hi[3]);
-                tc::sts128(b_lo(s) + o, lo[0], lo[1], lo[2], lo[3]);
-            }
-            for (int n2 = n + 32; n2 < p.n_pad; n2 += 32) {        // wider layers: remaining channels
+        for (int d = 0; d < D; ++d)
+            if (d < KB) gather(d, raw[d], gval[d]);
+
+        auto step = [&](int kb, uint32_t (&cur)[RAWN], float (&gv)[4]) {
+            const int s = kb & (kTcStages - 1);
+            if (kb >= kTcStages) tc::mbar_wait(&mma_bar[s], (uint32_t)((kb / kTcStages - 1) & 1));
+            // ---- A tile stores (transposed scatter): (k/4)*LBO_a + (m/8)*128 + (m%8)*16 + (k%4)*4, k = pl
+            const uint32_t a_off = (uint32_t)(pl >> 2) * kWgLboA + (uint32_t)(pl & 3) * 4 + (uint32_t)(tg * 2) * 128;
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int px = pix0 + kb * kTcBK + q * 4 + j;
-                    float v = 0.f;
-                    if (n2 < p.N && px < pix1) {
-                        const int b = px / p.P, pp = px - b * p.P;
-                        v = __ldg(p.g + ((int64_t)b * p.N + n2) * p.P + pp);
+                    const int kk = c * 4 + j;
+                    float v;
+                    if (ELEM == EL_U8) {
+                        if (EXACT_A) {
+                            const uint32_t w = VEC ? __byte_perm(cur[c], 0x4B000000u, 0x7650u + j) : (cur[kk] | 0x4B000000u);
+                            v = __uint_as_float(w) - exact_bias;
+                        } else {
+                            const uint32_t byte = VEC ? ((cur[c] >> (8 * j)) & 0xFFu) : cur[kk];
+                            v = __uint_as_float(tc::lds32(lut_a + 4u * byte));
+                        }
+                    } else if (ELEM == EL_F32_NORM) v = __fdiv_rn(__uint_as_float(cur[kk]) - p.low, p.high - p.low);
+                    else v = __uint_as_float(cur[kk]);
+                    const uint32_t o = a_off + (uint32_t)(kk >> 3) * 128 + (uint32_t)(kk & 7) * 16;
+                    if (EXACT_A) {
+                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(a_hi(s) + o), "f"(v) : "memory");
+                    } else {
+                        const float hi = tc::tf32_rn(v), lo = v - hi;
+                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(a_hi(s) + o), "f"(hi) : "memory");
+                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(a_lo(s) + o), "f"(lo) : "memory");
                     }
-                    hi[j] = tc::tf32_rn(v); lo[j] = v - hi[j];
                 }
-                const uint32_t o2 = (uint32_t)q * lbo_b + (uint32_t)(n2 >> 3) * 128 + (uint32_t)(n2 & 7) * 16;
-                tc::sts128(b_hi(s) + o2, hi[0], hi[1], hi[2], hi[3]);
-                tc::sts128(b_lo(s) + o2, lo[0], lo[1], lo[2], lo[3]);
             }
-        }
-        if (kb + 1 < KB) gather(kb + 1);
-        tc::fence_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-            tc::tc_fence_after();
+            // ---- B tile stores: (k/4)*LBO_b + (n/8)*128 + (n%8)*16
+            {
+                float hi[4], lo[4];
 #pragma unroll
-            for (int j = 0; j < kTcBK / 8; ++j) {                   // 8 pixels per MMA
-                const uint64_t dah = tc::make_desc(a_hi(s) + 2 * j * kWgLboA, kWgLboA, 128);
-                const uint64_t dal = tc::make_desc(a_lo(s) + 2 * j * kWgLboA, kWgLboA, 128);
-                const uint64_t dbh = tc::make_desc(b_hi(s) + 2 * j * lbo_b, lbo_b, 128);
-                const uint64_t dbl = tc::make_desc(b_lo(s) + 2 * j * lbo_b, lbo_b, 128);
-                tc::mma_tf32(tmem_d, dah, dbh, idesc, (kb | j) ? 1u : 0u);
-                tc::mma_tf32(tmem_d, dal, dbh, idesc, 1u);
-                tc::mma_tf32(tmem_d, dah, dbl, idesc, 1u);
+                for (int j = 0; j < 4; ++j) { hi[j] = tc::tf32_rn(gv[j]); lo[j] = gv[j] - hi[j]; bsum += gv[j]; }
+                const uint32_t o = (uint32_t)q * lbo_b + (uint32_t)(n >> 3) * 128 + (uint32_t)(n & 7) * 16;
+                if (n < p.n_pad) {          // n_pad may be 16: rows beyond it belong to the next K chunk
+                    tc::sts128(b_hi(s) + o, hi[0], hi[1], hi[2], hi[3]);
+                    tc::sts128(b_lo(s) + o, lo[0], lo[1], lo[2], lo[3]);
+                }
+                for (int n2 = n + 32; n2 < p.n_pad; n2 += 32) {        // wider layers: remaining channels
+                    const int px0 = pix0 + kb * kTcBK + q * 4;
+                    int b = px0 / p.P, pp = px0 - b * p.P;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float v = (n2 < p.N && px0 + j < pix1) ? __ldg(p.g + ((int64_t)b * p.N + n2) * p.P + pp) : 0.f;
+                        if (++pp == p.P) { pp = 0; ++b; }
+                        hi[j] = tc::tf32_rn(v); lo[j] = v - hi[j];
+                    }
+                    const uint32_t o2 = (uint32_t)q * lbo_b + (uint32_t)(n2 >> 3) * 128 + (uint32_t)(n2 & 7) * 16;
+                    tc::sts128(b_hi(s) + o2, hi[0], hi[1], hi[2], hi[3]);
+                    tc::sts128(b_lo(s) + o2, lo[0], lo[1], lo[2], lo[3]);
+                }
             }
-            tc::mma_commit(&bars[s]);
-        }
-    }
-    for (int s = 0; s < kTcStages; ++s) {
-        const int uses = (KB - s + kTcStages - 1) / kTcStages;
-        if (uses > 0) tc::mbar_wait(&bars[s], (uint32_t)((uses - 1) & 1));
-    }
-    tc::tc_fence_after();
-    // ---- bias gradient partial (row Mtaps of the partial matrix): sum the 8 pixel-chunk lanes of a channel
-    if (p.with_bias && blockIdx.x == 0) {
-        bsum += __shfl_xor_sync(0xffffffffu, bsum, 1);
-        bsum += __shfl_xor_sync(0xffffffffu, bsum, 2);
-        bsum += __shfl_xor_sync(0xffffffffu, bsum, 4);
-        const int n = tid >> 3;
-        if ((tid & 7) == 0 && n < p.N) p.partial[((int64_t)blockIdx.y * (p.Mtaps + 1) + p.Mtaps) * p.N + n] = bsum;
-    }
-    // ---- epilogue: partial[z][tap][co]
-    if (warp < 4) {
-        const int tap = tap0 + warp * 32 + (tid & 31);
-        for (int c0 = 0; c0 < p.n_pad; c0 += 32) {
-            uint32_t r[32];
-            if (KB > 0) tc::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
-            if (tap < p.Mtaps) {
-                float *o = p.partial + ((int64_t)blockIdx.y * (p.Mtaps + p.with_bias) + tap) * p.N + c0;
+            if (kb + D < KB) gather(kb + D, cur, gv);
+            tc::fence_async_smem();
+            __syncwarp();
+            if ((tid & 31) == 0) tc::mbar_arrive(&full[s]);
+        };
+        for (int kb0 = 0; kb0 < KB; kb0 += D) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (c0 + j < p.N) o[j] = KB > 0 ? __uint_as_float(r[j]) : 0.f;
+            for (int d = 0; d < D; ++d)
+                if (kb0 + d < KB) step(kb0 + d, raw[d], gval[d]);
+        }
+        for (int s = 0; s < kTcStages; ++s) {
+            const int uses = (KB - s + kTcStages - 1) / kTcStages;
+            if (uses > 0) tc::mbar_wait(&mma_bar[s], (uint32_t)((uses - 1) & 1));
+        }
+        tc::tc_fence_after();
+        // ---- bias gradient partial (row Mtaps of the partial matrix): sum the 8 pixel-chunk lanes of a channel
+        if (p.with_bias && blockIdx.x == 0) {
+            bsum += __shfl_xor_sync(0xffffffffu, bsum, 1);
+            bsum += __shfl_xor_sync(0xffffffffu, bsum, 2);
+            bsum += __shfl_xor_sync(0xffffffffu, bsum, 4);
+            if (q == 0 && n < p.N) p.partial[((int64_t)blockIdx.y * (p.Mtaps + 1) + p.Mtaps) * p.N + n] = bsum;
+        }
+        // ---- epilogue: partial[z][tap][co]; warp w reads TMEM lanes 32*(w%4).., 16-column groups of parity w/4
+        {
+            const int qd = warp & 3;
+            const int tap = tap0 + qd * 32 + (tid & 31);
+            const float scale = (EXACT_A && p.normalize) ? 1.0f / (p.high - p.low) : 1.0f;
+            for (int c0 = (warp >> 2) * 16; c0 < p.n_pad; c0 += 32) {
+                uint32_t r[16];
+                if (KB > 0) tc::tmem_ld16(tmem_d + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, r);
+                if (tap < p.Mtaps) {
+                    float *o = p.partial + ((int64_t)blockIdx.y * (p.Mtaps + p.with_bias) + tap) * p.N + c0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < p.N) o[j] = KB > 0 ? __uint_as_float(r[j]) * scale : 0.f;
+                }
             }
         }
     }
@@ -779,7 +802,8 @@ static int launch_conv_wgrad_tc(const b2rl_layer &l, const Operand &X, const flo
     splits = (Kpix + pix_per_cta - 1) / pix_per_cta;
     const int with_bias = l.out_c <= 32 ? 1 : 0;
     if ((size_t)splits * (Kc + 1) * l.out_c > partial_cap) return 1;
-    const size_t smem = (size_t)kTcStages * 2 * ((size_t)kWgABytes + (size_t)n_pad * kTcBK * 4) + kTcBM * 4 + 1024 + 64 + 256;
+    const bool exact = X.u8 && (!X.normalize || (X.low == floorf(X.low) && fabsf(X.low) <= 1024.f));
+    const size_t smem = conv_wgrad_tc_smem_bytes(n_pad, exact ? 1 : 2);
     if (smem > 200 * 1024) return 1;
     ConvWgradTcParams p;
     p.x = X.ptr; p.g = g; p.partial = partial; p.gather = X.red.gather;
@@ -789,21 +813,25 @@ static int launch_conv_wgrad_tc(const b2rl_layer &l, const Operand &X, const flo
     p.KK = KK; p.KS = l.ksize; p.HW = l.in_h * l.in_w; p.W = l.in_w;
     p.pix_per_cta = pix_per_cta;
     p.with_bias = with_bias;
-    p.normalize = X.normalize; p.low = X.low; p.high = X.high;
-    p.vec4 = (X.u8 && l.ksize % 4 == 0 && l.stride % 4 == 0 && l.in_w % 4 == 0 && (l.in_h * l.in_w) % 4 == 0 &&
-              (reinterpret_cast<uintptr_t>(X.ptr) % 4 == 0)) ? 1 : 0;
+    p.normalize = X.normalize; p.low = X.normalize ? X.low : 0.f; p.high = X.normalize ? X.high : 1.f;
+    p.inv_ow = 1.0f / (float)l.out_w;
+    const bool vec = X.u8 && l.ksize % 4 == 0 && l.stride % 4 == 0 && l.in_w % 4 == 0 && (l.in_h * l.in_w) % 4 == 0 &&
+                     reinterpret_cast<uintptr_t>(X.ptr) % 4 == 0;
     dim3 grid(mt, (unsigned)splits);
     auto launch = [&](auto kern) -> int {
         B2RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kTcThreads, smem, s>>>(p);
+        kern<<<grid, kTcThreads + 32, smem, s>>>(p);
         B2RL_LAUNCH_CHECK();
         return B2RL_OK;
     };
     int rc;
     switch (X.elem_kind()) {
-        case EL_U8: rc = launch(conv_wgrad_tc_kernel<EL_U8>); break;
-        case EL_F32_NORM: rc = launch(conv_wgrad_tc_kernel<EL_F32_NORM>); break;
-        default: rc = launch(conv_wgrad_tc_kernel<EL_F32>); break;
+        case EL_U8:
+            if (exact) rc = vec ? launch(conv_wgrad_tc_kernel<EL_U8, true, true, 4>) : launch(conv_wgrad_tc_kernel<EL_U8, true, false, 2>);
+            else rc = vec ? launch(conv_wgrad_tc_kernel<EL_U8, false, true, 4>) : launch(conv_wgrad_tc_kernel<EL_U8, false, false, 2>);
+            break;
+        case EL_F32_NORM: rc = launch(conv_wgrad_tc_kernel<EL_F32_NORM, false, false, 2>); break;
+        default: rc = launch(conv_wgrad_tc_kernel<EL_F32, false, false, 2>); break;
     }
     if (rc != B2RL_OK) return rc;
     // fixed-order reduction of the pixel splits, transposed into dW[co][tap] (+ db from the extra row)

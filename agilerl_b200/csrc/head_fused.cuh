@@ -286,29 +286,70 @@ __global__ void __launch_bounds__(kHeadThreads) head_bwd_kernel(const HeadBwdDes
         if (rok) hd.g_latent[row * hd.latent + i] = lat[r * hd.latent + i];
 }
 
+constexpr int kHeadWgMaxIn = 512;                    // widest layer input the fused weight-gradient kernel takes
+constexpr int kHeadWgSmemFloats = 16384;              // 64 KB chunk of the layer input staged per pass
+
+// One CTA = 8 consecutive output neurons of one layer (one per warp).  The layer input x [B, in] and
+// the CTA's 8 columns of dZ are staged through shared memory in chunks of rows (coalesced, every load
+// in flight at once); each warp then walks the chunk's rows in order with its lanes striding the
+// input dimension: dW[o][i] = sum_r dz[r][o] * x[r][i], db[o] = sum_r dz[r][o]  (fixed order).
 __global__ void __launch_bounds__(kHeadThreads) head_wgrad_kernel(const HeadBwdDesc hd, int64_t B, int n_tiles) {
+    extern __shared__ __align__(16) float wsm[];
     const int nl = hd.n_val + hd.n_adv;
     const int t = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int kWarps = kHeadThreads / 32;
     if (t < hd.wg_start[nl]) {
         int li = 0;
         while (t >= hd.wg_start[li + 1]) ++li;
         const HeadBwdLayer L = hd.l[li];
-        const int o = (t - hd.wg_start[li]) * (kHeadThreads / 32) + warp;
-        if (o >= L.out) return;
-        for (int i0 = 0; i0 < L.in; i0 += 64) {            // two input columns per lane per sweep over the rows
-            const int ia = i0 + lane, ib = i0 + 32 + lane;
-            float acc_a = 0.f, acc_b = 0.f, accb = 0.f;
-#pragma unroll 4
-            for (int64_t rr = 0; rr < B; ++rr) {
-                const float dz = __ldg(L.g + rr * L.out + o);
-                accb += dz;
-                if (ia < L.in) acc_a = fmaf(dz, __ldg(L.x + rr * L.in + ia), acc_a);
-                if (ib < L.in) acc_b = fmaf(dz, __ldg(L.x + rr * L.in + ib), acc_b);
+        const int o0 = (t - hd.wg_start[li]) * kWarps;
+        const int o = o0 + warp;
+        const int rows_per = max(1, min((int)B, (kHeadWgSmemFloats - 0) / (L.in + kWarps)));
+        float *xs = wsm;                                   // [rows_per][in]
+        float *dzs = wsm + (size_t)rows_per * L.in;        // [rows_per][8]
+        float acc[kHeadWgMaxIn / 32];
+#pragma unroll
+        for (int c = 0; c < kHeadWgMaxIn / 32; ++c) acc[c] = 0.f;
+        float accb = 0.f;
+        const bool vec = (L.in & 3) == 0 && (reinterpret_cast<uintptr_t>(L.x) & 15) == 0;
+        for (int64_t r0 = 0; r0 < B; r0 += rows_per) {
+            const int rc = (int)min((int64_t)rows_per, B - r0);
+            __syncthreads();
+            if (vec) {
+                const float4 *src = reinterpret_cast<const float4 *>(L.x + r0 * L.in);
+                float4 *dst = reinterpret_cast<float4 *>(xs);
+                for (int e = threadIdx.x; e < rc * L.in / 4; e += kHeadThreads) dst[e] = __ldg(src + e);
+            } else {
+                for (int e = threadIdx.x; e < rc * L.in; e += kHeadThreads) xs[e] = __ldg(L.x + r0 * L.in + e);
             }
-            if (ia < L.in) { float *p = L.dw + (int64_t)o * L.in + ia; *p = L.acc_w ? *p + acc_a : acc_a; }
-            if (ib < L.in) { float *p = L.dw + (int64_t)o * L.in + ib; *p = L.acc_w ? *p + acc_b : acc_b; }
-            if (i0 == 0 && lane == 0) L.db[o] = L.acc_w ? L.db[o] + accb : accb;
+            for (int e = threadIdx.x; e < rc * kWarps; e += kHeadThreads) {
+                const int r = e / kWarps, w = e - r * kWarps;
+                dzs[e] = (o0 + w < L.out) ? __ldg(L.g + (r0 + r) * L.out + o0 + w) : 0.f;
+            }
+            __syncthreads();
+            if (o < L.out) {
+#pragma unroll 4
+                for (int r = 0; r < rc; ++r) {
+                    const float dz = dzs[r * kWarps + warp];
+                    accb += dz;
+                    const float *xr = xs + r * L.in + lane;
+#pragma unroll
+                    for (int c = 0; c < kHeadWgMaxIn / 32; ++c)
+                        if (c * 32 < L.in && c * 32 + lane < L.in) acc[c] = fmaf(dz, xr[c * 32], acc[c]);
+                }
+            }
+        }
+        if (o < L.out) {
+#pragma unroll
+            for (int c = 0; c < kHeadWgMaxIn / 32; ++c) {
+                const int i = c * 32 + lane;
+                if (i < L.in) {
+                    float *pw = L.dw + (int64_t)o * L.in + i;
+                    *pw = L.acc_w ? *pw + acc[c] : acc[c];
+                }
+            }
+            if (lane == 0) L.db[o] = L.acc_w ? L.db[o] + accb : accb;
         }
     } else {
         // LayerNorm affine gradients: fixed-order sum of the per-tile partials

@@ -956,15 +956,17 @@ static int backward_pass(const b2rl_net_desc &net, const float *params, const fl
         hd.maxdim = maxdim;
         const size_t smem = sizeof(float) * ((size_t)(3 + kHeadThreads / 32) * kHeadRows * head_pitch(maxdim) +
                                              (size_t)kHeadRows * hd.latent + (kHeadThreads / 32) * kHeadRows);
-        if (ok && smem <= 160 * 1024 && part_used <= sc.floats) {
+        if (ok && smem <= 160 * 1024 && part_used <= sc.floats && maxdim <= kHeadWgMaxIn) {
             static bool attr_set = false;
             if (!attr_set) {
                 B2RL_CUDA(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+                B2RL_CUDA(cudaFuncSetAttribute(head_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)(kHeadWgSmemFloats * sizeof(float))));
                 attr_set = true;
             }
             head_bwd_kernel<<<n_tiles, kHeadThreads, smem, s>>>(hd, B);
             B2RL_LAUNCH_CHECK();
-            head_wgrad_kernel<<<ctas + hd.n_ln, kHeadThreads, 0, s>>>(hd, B, n_tiles);
+            head_wgrad_kernel<<<ctas + hd.n_ln, kHeadThreads, kHeadWgSmemFloats * sizeof(float), s>>>(hd, B, n_tiles);
             B2RL_LAUNCH_CHECK();
             head_done = true;
         }
