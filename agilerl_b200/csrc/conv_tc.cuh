@@ -154,6 +154,11 @@ struct ConvTcParams {
     int act;
     int normalize;
     float low, high;
+    // PAD variant (input gradient as s*s stride-1 convolutions over dL/dout, one per parity class = blockIdx.y)
+    int pad, IH;                // implicit zero padding, input plane height (its width is W)
+    int cls_s;                  // classes per dimension (the forward stride); output pixel = (yy*s + py, xx*s + px)
+    int out_H, out_W;           // plane of the scattered output
+    int64_t w_class_stride;     // floats between the pre-split weights of consecutive classes
 };
 
 static inline size_t conv_tc_smem_bytes(int n_pad, int k_pad, int a_parts = 2) {
@@ -201,7 +206,7 @@ __device__ __noinline__ float act_fwd_slow(int act, float v) { return act_fwd(ac
 // accumulator in the epilogue (one true division per output).  vs. the reference's
 // fl((x-low)/(high-low)) * w summed in fp32 the difference is <= 2^-23 relative per term.
 // VEC: 4 consecutive taps are contiguous and aligned (4 packed bytes / two 8-byte fp32 loads).
-template <int ELEM, bool EXACT_A, bool VEC, int D>
+template <int ELEM, bool EXACT_A, bool VEC, int D, bool PAD = false>
 __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const ConvTcParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     constexpr int RAWN = (ELEM == EL_U8 && VEC) ? 4 : 16;      // raw words per thread per k-block
@@ -242,8 +247,9 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const Conv
     auto issue_b = [&](int kb) {       // elected thread: weight tile of k-block kb -> its ring slot
         const int sb = kb & (kTcBStages - 1);
         tc::mbar_expect_tx(&full_b[sb], 2 * b_bytes);
-        tc::bulk_g2s(b_hi(sb), p.w_hi + (int64_t)kb * p.n_pad * kTcBK, b_bytes, &full_b[sb]);
-        tc::bulk_g2s(b_lo(sb), p.w_lo + (int64_t)kb * p.n_pad * kTcBK, b_bytes, &full_b[sb]);
+        const int64_t wo = (PAD ? (int64_t)blockIdx.y * p.w_class_stride : 0) + (int64_t)kb * p.n_pad * kTcBK;
+        tc::bulk_g2s(b_hi(sb), p.w_hi + wo, b_bytes, &full_b[sb]);
+        tc::bulk_g2s(b_lo(sb), p.w_lo + wo, b_bytes, &full_b[sb]);
     };
     for (int k = tid; k < p.k_pad; k += kTcThreads + 32)
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(koff_a + 4u * k), "r"(__ldg(p.koff + k)) : "memory");
@@ -302,11 +308,18 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const Conv
     const int m = blockIdx.x * kTcBM + row;
     const bool row_ok = m < p.M;
     int64_t rowbase = p.gather ? p.gather[0] * p.in_bstride : 0;
+    uint32_t mask_y = 0, mask_x = 0;                  // PAD: which kernel rows / columns fall inside the plane
     if (row_ok) {
         const int b = m / p.P, pix = m - b * p.P;
         const int oy = pix / p.OW, ox = pix - oy * p.OW;
         const int64_t bb = p.gather ? p.gather[b] : (int64_t)b;
-        rowbase = bb * p.in_bstride + (int64_t)(oy * p.sy + ox * p.sx);
+        rowbase = bb * p.in_bstride + (int64_t)((oy * p.sy + ox * p.sx) - (PAD ? p.pad * (p.W + 1) : 0));
+        if (PAD) {
+            for (int a = 0; a < p.KS; ++a) {
+                mask_y |= (uint32_t)((unsigned)(oy - p.pad + a) < (unsigned)p.IH) << a;
+                mask_x |= (uint32_t)((unsigned)(ox - p.pad + a) < (unsigned)p.W) << a;
+            }
+        }
     }
     const uint8_t *row_u8 = static_cast<const uint8_t *>(p.x) + rowbase;
     const float *row_f32 = static_cast<const float *>(p.x) + rowbase;
@@ -316,7 +329,14 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const Conv
     uint32_t raw[D][RAWN];
     auto gather = [&](int kb, uint32_t (&dst)[RAWN]) {
         const int k0 = kb * kTcBK + half * (CH * 4);
-        if (ELEM != EL_U8 && VEC) {             // fp32 activations: 4 taps = 2 aligned 8-byte loads
+        if (PAD) {                              // fp32, per-tap bounds: entry = offset | ky << 24 | kx << 28
+#pragma unroll
+            for (int j = 0; j < CH * 4; ++j) {
+                const uint32_t e = tc::lds32(koff_a + 4u * (k0 + j));
+                const bool ok = ((mask_y >> ((e >> 24) & 15u)) & (mask_x >> (e >> 28)) & 1u) != 0;
+                dst[j] = ok ? __float_as_uint(__ldg(row_f32 + (e & 0xFFFFFFu))) : 0u;
+            }
+        } else if (ELEM != EL_U8 && VEC) {      // fp32 activations: 4 taps = 2 aligned 8-byte loads
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
                 const uint32_t off = tc::lds32(koff_a + 4u * (k0 + c * 4));
@@ -399,26 +419,34 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const Conv
         const int q = warp & 3;
         const int er = q * 32 + (tid & 31);                  // tile row of this lane
         const int em = blockIdx.x * kTcBM + er;
-        const bool e_ok = em < p.M;
         int b_img = 0, pix = 0;
+        bool e_ok = em < p.M;
         if (e_ok) { b_img = em / p.P; pix = em - b_img * p.P; }
+        int64_t out_P = p.P;
+        if (PAD) {                                           // scatter into the class's pixels of the full plane
+            const int yy = pix / p.OW, xx = pix - yy * p.OW;
+            const int y = yy * p.cls_s + (int)blockIdx.y / p.cls_s, x = xx * p.cls_s + (int)blockIdx.y % p.cls_s;
+            e_ok = e_ok && y < p.out_H && x < p.out_W;
+            pix = y * p.out_W + x;
+            out_P = (int64_t)p.out_H * p.out_W;
+        }
         const bool relu = p.act == B2RL_ACT_RELU, ident = p.act == B2RL_ACT_NONE;
         const float scale = (EXACT_A && p.normalize) ? 1.0f / (p.high - p.low) : 1.0f;
         for (int c0 = (warp >> 2) * 16; c0 < p.n_pad; c0 += 32) {
             uint32_t r[16];
             tc::tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
             if (e_ok) {
-                float *o = p.out + ((int64_t)b_img * p.N + c0) * p.P + pix;
-                float *po = p.pre_out ? p.pre_out + ((int64_t)b_img * p.N + c0) * p.P + pix : nullptr;
+                float *o = p.out + ((int64_t)b_img * p.N + c0) * out_P + pix;
+                float *po = p.pre_out ? p.pre_out + ((int64_t)b_img * p.N + c0) * out_P + pix : nullptr;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     if (c0 + j < p.N) {
                         float acc = __uint_as_float(r[j]);
                         if (EXACT_A) acc *= scale;
                         float v = acc + __uint_as_float(tc::lds32(bias_a + 4u * (c0 + j)));
-                        if (po) po[(int64_t)j * p.P] = v;
+                        if (po) po[(int64_t)j * out_P] = v;
                         v = relu ? fmaxf(v, 0.f) : (ident ? v : act_fwd_slow(p.act, v));
-                        o[(int64_t)j * p.P] = v;
+                        o[(int64_t)j * out_P] = v;
                     }
                 }
             }
@@ -462,6 +490,7 @@ static int launch_conv_fwd_tc(const b2rl_layer &l, const Operand &A, const float
     p.P = P; p.OW = l.out_w; p.sy = l.stride * l.in_w; p.sx = l.stride;
     p.KK = KK; p.KS = l.ksize; p.HW = l.in_h * l.in_w; p.W = l.in_w;
     p.act = l.act; p.normalize = A.normalize; p.low = A.normalize ? A.low : 0.f; p.high = A.normalize ? A.high : 1.f;
+    p.pad = 0; p.IH = l.in_h; p.cls_s = 1; p.out_H = l.out_h; p.out_W = l.out_w; p.w_class_stride = 0;
     // 4 consecutive taps are 4 contiguous, 4-byte aligned bytes when the kernel width, the column
     // stride, the row pitch and the plane / image sizes are all multiples of 4
     bool vec;
@@ -489,6 +518,85 @@ static int launch_conv_fwd_tc(const b2rl_layer &l, const Operand &A, const float
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Input gradient on tcgen05.  For stride s the input pixels split into s*s parity classes
+// (y mod s, x mod s); the pixels of one class receive contributions only from the kernel taps
+// ky = py + s*a, kx = px + s*b, so each class is a dense stride-1 convolution of dL/dout with a
+// T x T kernel (T = ceil(k/s)) and zero padding T-1:
+//   dX[b, ci, s*yy+py, s*xx+px] = sum_{co,a',b'} dOut[b, co, yy-(T-1)+a', xx-(T-1)+b'] * W[co, ci, py+s*(T-1-a'), px+s*(T-1-b')]
+// — the forward kernel with a bounds-checked gather (PAD) and a strided output scatter; gridDim.y
+// walks the classes.  No atomics, no memset, deterministic.
+// ------------------------------------------------------------------------------------------------
+__global__ void dgrad_weight_split_kernel(const float *__restrict__ w, int Cout, int Cin, int KS, int S, int T, int n_pad,
+                                          int k_pad, int in_plane, int in_w, float *__restrict__ w_hi,
+                                          float *__restrict__ w_lo, uint32_t *__restrict__ koff) {
+    const int cls = blockIdx.y, py = cls / S, px = cls % S;
+    const int K = Cout * T * T, total = n_pad * k_pad;
+    float *hi_c = w_hi + (int64_t)cls * total, *lo_c = w_lo + (int64_t)cls * total;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int k = e / n_pad, n = e - k * n_pad;          // k = (co, a', b'), n = ci
+        float v = 0.f;
+        int co = 0, a = 0, b = 0;
+        if (k < K) {
+            co = k / (T * T);
+            const int rem = k - co * T * T;
+            a = rem / T; b = rem - a * T;
+            const int ky = py + S * (T - 1 - a), kx = px + S * (T - 1 - b);
+            if (n < Cin && ky < KS && kx < KS) v = w[(((int64_t)co * Cin + n) * KS + ky) * KS + kx];
+        }
+        const float hi = tc::tf32_rn(v);
+        const int kb = k / kTcBK, kin = k - kb * kTcBK;
+        const int64_t o = (int64_t)kb * n_pad * kTcBK + (int64_t)(kin >> 2) * n_pad * 4 + (n >> 3) * 32 + (n & 7) * 4 + (kin & 3);
+        hi_c[o] = hi;
+        lo_c[o] = v - hi;
+        if (n == 0 && cls == 0)
+            koff[k] = k < K ? ((uint32_t)(co * in_plane + a * in_w + b) | ((uint32_t)a << 24) | ((uint32_t)b << 28)) : 0u;
+    }
+}
+
+static inline size_t conv_dgrad_tc_scratch_floats(const b2rl_layer &l) {
+    const int T = (l.ksize + l.stride - 1) / l.stride;
+    const int K = l.out_c * T * T;
+    const int n_pad = (l.in_c + 15) / 16 * 16, k_pad = (K + kTcBK - 1) / kTcBK * kTcBK;
+    return (size_t)l.stride * l.stride * 2 * n_pad * k_pad + k_pad;
+}
+
+// dL/d(layer input) [rows, Cin, in_h, in_w] (overwritten) from g = dL/d(layer output).
+// returns B2RL_OK, or 1 when the shape is outside what this path handles.
+static int launch_conv_dgrad_tc(const b2rl_layer &l, const float *g, const float *W, float *g_in, int64_t rows,
+                                float *scratch, size_t scratch_cap, cudaStream_t s) {
+    const int S = l.stride, T = (l.ksize + S - 1) / S;
+    const int K = l.out_c * T * T;
+    const int n_pad = (l.in_c + 15) / 16 * 16, k_pad = (K + kTcBK - 1) / kTcBK * kTcBK;
+    const int Yc = (l.in_h + S - 1) / S, Xc = (l.in_w + S - 1) / S;
+    const int64_t M = rows * Yc * Xc;
+    if (n_pad > 256 || k_pad > 8192 || M > INT32_MAX || T > 15 || S * S > 64) return 1;
+    if ((int64_t)l.out_c * l.out_h * l.out_w >= (1 << 24)) return 1;        // offset field of the tap table
+    const size_t smem = conv_tc_smem_bytes(n_pad, k_pad, 2);
+    if (smem > 200 * 1024 || scratch == nullptr || conv_dgrad_tc_scratch_floats(l) > scratch_cap) return 1;
+    if (reinterpret_cast<uintptr_t>(scratch) % 16 != 0) return 1;
+    const size_t cls_floats = (size_t)n_pad * k_pad;
+    float *w_hi = scratch, *w_lo = scratch + (size_t)S * S * cls_floats;
+    uint32_t *koff = reinterpret_cast<uint32_t *>(scratch + (size_t)2 * S * S * cls_floats);
+    dgrad_weight_split_kernel<<<dim3((unsigned)((cls_floats + 255) / 256), S * S), 256, 0, s>>>(
+        W, l.out_c, l.in_c, l.ksize, S, T, n_pad, k_pad, l.out_h * l.out_w, l.out_w, w_hi, w_lo, koff);
+    B2RL_LAUNCH_CHECK();
+    ConvTcParams p;
+    p.x = g; p.w_hi = w_hi; p.w_lo = w_lo; p.koff = koff; p.bias = nullptr; p.out = g_in; p.pre_out = nullptr; p.gather = nullptr;
+    p.in_bstride = (int64_t)l.out_c * l.out_h * l.out_w;
+    p.M = (int)M; p.N = l.in_c; p.K = K; p.n_pad = n_pad; p.k_pad = k_pad;
+    p.P = Yc * Xc; p.OW = Xc; p.sy = l.out_w; p.sx = 1;
+    p.KK = T * T; p.KS = T; p.HW = l.out_h * l.out_w; p.W = l.out_w;
+    p.act = B2RL_ACT_NONE; p.normalize = 0; p.low = 0.f; p.high = 1.f;
+    p.pad = T - 1; p.IH = l.out_h; p.cls_s = S; p.out_H = l.in_h; p.out_W = l.in_w;
+    p.w_class_stride = (int64_t)cls_floats;
+    auto kern = conv_fwd_tc_kernel<EL_F32, false, false, 2, true>;
+    B2RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3((unsigned)((p.M + kTcBM - 1) / kTcBM), S * S), kTcThreads + 32, smem, s>>>(p);
+    B2RL_LAUNCH_CHECK();
+    return B2RL_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 // Weight gradient on tcgen05:   dW[co][tap] = sum_pix  im2col(x)[pix][tap] * G[pix][co]

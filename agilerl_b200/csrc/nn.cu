@@ -114,6 +114,7 @@ static size_t max_partial_floats(const b2rl_net_desc &net, int64_t rows, int64_t
             size_t n = conv_tc_wsplit_floats(net.enc[i]);
             if (n > m) m = n;
             if (brows) { n = conv_wgrad_tc_partial_floats(net.enc[i], brows, sm_count()); if (n > m) m = n; }
+            if (brows && i > 0) { n = conv_dgrad_tc_scratch_floats(net.enc[i]); if (n > m) m = n; }
         }
     return m;
 }
@@ -880,6 +881,10 @@ static int layer_backward(const b2rl_net_desc &net, const b2rl_layer &l, const f
         if (l.kind == B2RL_LAYER_CONV) {
             const int P = l.out_h * l.out_w, KK = l.ksize * l.ksize;
             const int Kc = l.in_c * KK;
+            if (!accumulate_gin && tc_enabled()) {     // parity-class convolutions on tcgen05 (no atomics)
+                const int rc_tc = launch_conv_dgrad_tc(l, g_out, W, g_in, B, sc.partial, sc.floats, s);
+                if (rc_tc != 1) return rc_tc;
+            }
             if (!accumulate_gin) B2RL_CUDA(cudaMemsetAsync(g_in, 0, sizeof(float) * B * layer_in_elems(l), s));
             A.ptr = g_out; A.row = map_pixel(P, l.out_w, (int64_t)l.out_c * P, l.out_w, 1); A.red = map_stride(P);
             Bm.ptr = W; Bm.row = map_stride(1); Bm.red = map_stride(Kc);
