@@ -173,14 +173,23 @@ class RainbowDQN(RLAlgorithm):
         new_priorities = pri.cpu().numpy() if per else None       # elementwise_loss + prior_eps (:487-488)
         return loss.item(), idxs, new_priorities
 
-    def learn_from_buffers(self, memory, n_step_memory):
+    def learn_from_buffers(self, memory, n_step_memory, overlap: bool = False):
         """Fused HBM-resident gradient step (no host round trip): PER sample + learn + priority
         write-back, equivalent to train_off_policy.py:399-412 with canonical shapes.  Returns the
-        loss as a DEVICE tensor."""
+        loss as a DEVICE tensor.
+
+        ``overlap=True`` leaves this agent's backward + optimiser running on its own CUDA stream
+        when the call returns (the next agent's step can start meanwhile); ``synchronize()`` — or any
+        later learn / get_action of this agent — joins it.  Call ``synchronize()`` before touching
+        the parameters through torch (clone, state_dict, mutations) or adding to the buffers."""
         loss, idx, pri = self.engine.rainbow_fused_step(memory, n_step_memory, B=self.batch_size, beta=self.beta,
                                                         support=self.support, hp=self._hp(),
-                                                        gamma_n=self.gamma ** self.n_step)
+                                                        gamma_n=self.gamma ** self.n_step, overlap=overlap)
         return loss
+
+    def synchronize(self) -> None:
+        """Make the current stream wait for an overlapped learn tail of this agent."""
+        self.engine.join()
 
     def soft_update(self) -> None:
         """dqn_rainbow.py:492-501 (learn() already applies it inside the fused optimiser kernel)."""

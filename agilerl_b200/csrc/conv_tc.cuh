@@ -29,16 +29,18 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    // try_wait suspends the thread in hardware up to the hint before it returns false: few polls,
+    // no issue slots burnt while the tensor pipe or the producers are busy
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t"
         "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(0x989680u)
         : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
@@ -134,8 +136,8 @@ __device__ __forceinline__ float tf32_rn(float x) {
 
 constexpr int kTcBM = 128;      // pixels per CTA (UMMA M)
 constexpr int kTcBK = 32;       // k per stage (4 MMA k-steps of 8)
-constexpr int kTcStages = 2;    // A-operand stages (built by the CTA's threads)
-constexpr int kTcBStages = 4;   // B-operand stages (bulk-copied by the TMA unit, two k-blocks ahead)
+constexpr int kTcStages = 2;    // operand stages of the weight-gradient kernel (both tiles thread-built)
+constexpr int kTcBStages = 4;   // forward: B-operand ring (bulk-copied by the TMA unit, two k-blocks ahead)
 constexpr int kTcThreads = 256; // two threads per im2col row (16 k each per stage)
 
 struct ConvTcParams {
@@ -161,9 +163,9 @@ struct ConvTcParams {
     int64_t w_class_stride;     // floats between the pre-split weights of consecutive classes
 };
 
-static inline size_t conv_tc_smem_bytes(int n_pad, int k_pad, int a_parts = 2) {
+static inline size_t conv_tc_smem_bytes(int n_pad, int k_pad, int a_parts = 2, int a_stages = 2) {
     const size_t a = (size_t)kTcBM * kTcBK * 4, b = (size_t)n_pad * kTcBK * 4;
-    return kTcStages * a_parts * a + kTcBStages * 2 * b + (size_t)k_pad * 4 + 256 * 4 + (size_t)n_pad * 4 + 160 + 1024;
+    return a_stages * a_parts * a + kTcBStages * 2 * b + (size_t)k_pad * 4 + 256 * 4 + (size_t)n_pad * 4 + 192 + 1024;
 }
 
 // Split W [N, K] into tf32 hi / lo and store it in the order the conv kernel's B tiles use:
@@ -206,7 +208,7 @@ __device__ __noinline__ float act_fwd_slow(int act, float v) { return act_fwd(ac
 // accumulator in the epilogue (one true division per output).  vs. the reference's
 // fl((x-low)/(high-low)) * w summed in fp32 the difference is <= 2^-23 relative per term.
 // VEC: 4 consecutive taps are contiguous and aligned (4 packed bytes / two 8-byte fp32 loads).
-template <int ELEM, bool EXACT_A, bool VEC, int D, bool PAD = false>
+template <int ELEM, bool EXACT_A, bool VEC, int D, bool PAD = false, int SA = 2>
 __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const ConvTcParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     constexpr int RAWN = (ELEM == EL_U8 && VEC) ? 4 : 16;      // raw words per thread per k-block
@@ -220,30 +222,32 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const Conv
     const uint32_t a_stage = (EXACT_A ? 1 : 2) * a_bytes;
     auto a_hi = [&](int s) { return sbase + (uint32_t)s * a_stage; };
     auto a_lo = [&](int s) { return sbase + (uint32_t)s * a_stage + a_bytes; };          // unused when EXACT_A
-    const uint32_t bbase = sbase + kTcStages * a_stage;
+    const uint32_t bbase = sbase + SA * a_stage;
     auto b_hi = [&](int s) { return bbase + (uint32_t)s * 2 * b_bytes; };
     auto b_lo = [&](int s) { return bbase + (uint32_t)s * 2 * b_bytes + b_bytes; };
     const uint32_t koff_a = bbase + kTcBStages * 2 * b_bytes;
     const uint32_t lut_a = koff_a + (uint32_t)p.k_pad * 4;
     const uint32_t bias_a = lut_a + 256 * 4;
     const uint32_t bars_a = (bias_a + (uint32_t)p.n_pad * 4 + 15u) & ~15u;
-    const uint32_t tptr_a = bars_a + 8 * (2 * kTcStages + kTcBStages);
+    const uint32_t tptr_a = bars_a + 8 * (2 * SA + kTcBStages);
     uint8_t *gen = smem_raw + (sbase - tc::smem_u32(smem_raw));        // generic alias of sbase (barriers only)
-    uint64_t *mma_bar = reinterpret_cast<uint64_t *>(gen + (bars_a - sbase));   // [kTcStages] MMA group done
-    uint64_t *full_a = mma_bar + kTcStages;                                      // [kTcStages] im2col tile written
-    uint64_t *full_b = full_a + kTcStages;                                       // [kTcBStages] weight tile landed
+    uint64_t *mma_bar = reinterpret_cast<uint64_t *>(gen + (bars_a - sbase));   // [SA] MMA group done
+    uint64_t *full_a = mma_bar + SA;                                     // [SA] im2col tile written
+    uint64_t *full_b = full_a + SA;                                      // [kTcBStages] weight tile landed
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(gen + (tptr_a - sbase));
     const int KB = p.k_pad / kTcBK;
 
     // ---- one-time setup ----------------------------------------------------------------------
     if (tid == 0) {
-        for (int s = 0; s < kTcStages; ++s) {
+        for (int s = 0; s < SA; ++s) {
             tc::mbar_init(&mma_bar[s], 1);
             tc::mbar_init(&full_a[s], kTcThreads / 32);      // one elected arrive per producer warp
         }
         for (int s = 0; s < kTcBStages; ++s) tc::mbar_init(&full_b[s], 1);
         tc::fence_barrier_init();
     }
+    // MMA group j (k-block j) has retired: its A stage and its B ring slot may be overwritten
+    auto wait_mma = [&](int j) { tc::mbar_wait(&mma_bar[j % SA], (uint32_t)((j / SA) & 1)); };
     auto issue_b = [&](int kb) {       // elected thread: weight tile of k-block kb -> its ring slot
         const int sb = kb & (kTcBStages - 1);
         tc::mbar_expect_tx(&full_b[sb], 2 * b_bytes);
@@ -278,14 +282,13 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const Conv
             issue_b(0);
             if (KB > 1) issue_b(1);
             for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb & (kTcStages - 1), sb = kb & (kTcBStages - 1);
+                const int s = kb % SA, sb = kb & (kTcBStages - 1);
                 if (kb + 2 < KB) {
-                    // B ring slot (kb+2)%4 was last read by MMA group kb-2
-                    if (kb >= kTcStages) tc::mbar_wait(&mma_bar[s], (uint32_t)((kb / kTcStages - 1) & 1));
+                    if (kb >= 2) wait_mma(kb - 2);          // B ring slot (kb+2)%4 was last read by MMA group kb-2
                     issue_b(kb + 2);
                 }
                 tc::mbar_wait(&full_b[sb], (uint32_t)((kb / kTcBStages) & 1));
-                tc::mbar_wait(&full_a[s], (uint32_t)((kb / kTcStages) & 1));
+                tc::mbar_wait(&full_a[s], (uint32_t)((kb / SA) & 1));
                 tc::tc_fence_after();
                 // descriptors of consecutive k-steps differ only in the 14-bit start-address field
                 const uint64_t dah0 = tc::make_desc(a_hi(s), lbo_a, 128), dal0 = tc::make_desc(a_lo(s), lbo_a, 128);
@@ -365,9 +368,8 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const Conv
         if (d < KB) gather(d, raw[d]);
 
     auto step = [&](int kb, uint32_t (&cur)[RAWN]) {
-        const int s = kb & (kTcStages - 1);
-        // MMA group kb-2 done: A stage s is free again
-        if (kb >= kTcStages) tc::mbar_wait(&mma_bar[s], (uint32_t)((kb / kTcStages - 1) & 1));
+        const int s = kb % SA;
+        if (kb >= SA) wait_mma(kb - SA);     // A stage s is free again
         // ---- convert + hi/lo split + 16-byte smem stores of the gathered taps
         const uint32_t ah = a_hi(s) + row_off + (uint32_t)(half * CH) * lbo_a, al = a_lo(s) + row_off + (uint32_t)(half * CH) * lbo_a;
         const int k0 = kb * kTcBK + half * (CH * 4);
@@ -407,11 +409,8 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const Conv
         for (int d = 0; d < D; ++d)
             if (kb0 + d < KB) step(kb0 + d, raw[d]);
     }
-    // ---- wait for every outstanding MMA group ----------------------------------------------------
-    for (int s = 0; s < kTcStages; ++s) {
-        const int uses = (KB - s + kTcStages - 1) / kTcStages;      // k-blocks that used stage s
-        if (uses > 0) tc::mbar_wait(&mma_bar[s], (uint32_t)((uses - 1) & 1));
-    }
+    // ---- the last commit covers every earlier MMA of the issuing thread
+    if (KB > 0) wait_mma(KB - 1);
     tc::tc_fence_after();
 
     // ---- epilogue: warp w owns TMEM lanes 32*(w%4)..+31 (its rows) and the 16-column groups of parity w/4
@@ -432,23 +431,36 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const Conv
         }
         const bool relu = p.act == B2RL_ACT_RELU, ident = p.act == B2RL_ACT_NONE;
         const float scale = (EXACT_A && p.normalize) ? 1.0f / (p.high - p.low) : 1.0f;
+        const int oP = (int)out_P;
         for (int c0 = (warp >> 2) * 16; c0 < p.n_pad; c0 += 32) {
             uint32_t r[16];
             tc::tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
             if (e_ok) {
-                float *o = p.out + ((int64_t)b_img * p.N + c0) * out_P + pix;
-                float *po = p.pre_out ? p.pre_out + ((int64_t)b_img * p.N + c0) * out_P + pix : nullptr;
+                const int nv = min(16, p.N - c0);
+                float v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    if (c0 + j < p.N) {
-                        float acc = __uint_as_float(r[j]);
-                        if (EXACT_A) acc *= scale;
-                        float v = acc + __uint_as_float(tc::lds32(bias_a + 4u * (c0 + j)));
-                        if (po) po[(int64_t)j * out_P] = v;
-                        v = relu ? fmaxf(v, 0.f) : (ident ? v : act_fwd_slow(p.act, v));
-                        o[(int64_t)j * out_P] = v;
-                    }
+                    const float acc = EXACT_A ? __uint_as_float(r[j]) * scale : __uint_as_float(r[j]);
+                    v[j] = acc + __uint_as_float(tc::lds32(bias_a + 4u * (c0 + j)));
                 }
+                const int64_t o0 = ((int64_t)b_img * p.N + c0) * out_P + pix;
+                if (p.pre_out) {
+                    float *po = p.pre_out + o0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (j < nv) po[j * oP] = v[j];
+                }
+                if (relu) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                } else if (!ident) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = act_fwd_slow(p.act, v[j]);
+                }
+                float *o = p.out + o0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (j < nv) o[j * oP] = v[j];
             }
         }
     }
@@ -472,7 +484,9 @@ static int launch_conv_fwd_tc(const b2rl_layer &l, const Operand &A, const float
     const int n_pad = (l.out_c + 15) / 16 * 16, k_pad = (K + kTcBK - 1) / kTcBK * kTcBK;
     if (n_pad > 256 || k_pad > 8192 || rows * (int64_t)P > INT32_MAX) return 1;
     const bool exact = A.u8 && (!A.normalize || (A.low == floorf(A.low) && fabsf(A.low) <= 1024.f));
-    const size_t smem = conv_tc_smem_bytes(n_pad, k_pad, exact ? 1 : 2);
+    static const int sa_exact = getenv("B2RL_TC_SA") ? atoi(getenv("B2RL_TC_SA")) : 2;
+    const bool deep = exact && sa_exact == 3;
+    const size_t smem = conv_tc_smem_bytes(n_pad, k_pad, exact ? 1 : 2, deep ? 3 : 2);
     if (smem > 200 * 1024 || wsplit == nullptr || conv_tc_wsplit_floats(l) > wsplit_cap) return 1;
     if (reinterpret_cast<uintptr_t>(wsplit) % 16 != 0) return 1;          // bulk copies need 16-byte aligned sources
     float *w_hi = wsplit, *w_lo = wsplit + (size_t)n_pad * k_pad;
@@ -509,6 +523,7 @@ static int launch_conv_fwd_tc(const b2rl_layer &l, const Operand &A, const float
     };
     switch (A.elem_kind()) {
         case EL_U8:
+            if (exact && vec && deep) return launch(conv_fwd_tc_kernel<EL_U8, true, true, 8, false, 3>);
             if (exact) return vec ? launch(conv_fwd_tc_kernel<EL_U8, true, true, 8>) : launch(conv_fwd_tc_kernel<EL_U8, true, false, 2>);
             return vec ? launch(conv_fwd_tc_kernel<EL_U8, false, true, 8>) : launch(conv_fwd_tc_kernel<EL_U8, false, false, 2>);
         case EL_F32_NORM:

@@ -65,6 +65,19 @@ class LearnEngine:
         self.philox_offset = 0
 
     # -- scratch -------------------------------------------------------------------------------
+    # -- two-stream learn ----------------------------------------------------------------------
+    # With ``overlap=True`` the backward + optimiser + noise reset of a step run on the engine's own
+    # stream while the caller's stream is free to go on (the next agent's sample + forward, or the
+    # priority write-back): everything that reads or writes this engine's buffers first joins.
+    _bwd_stream = None
+    _opt_done = None
+
+    def join(self) -> None:
+        """Make the current stream wait for an overlapped backward/optimiser tail, if one is pending."""
+        if self._opt_done is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._opt_done)
+            self._opt_done = None
+
     def workspace(self, rows: int, backward: bool) -> torch.Tensor:
         key = (rows, backward)
         ws = self._ws.get(key)
@@ -82,6 +95,7 @@ class LearnEngine:
 
     # -- noise ---------------------------------------------------------------------------------
     def reset_noise(self, net: NetBuffers, normals: torch.Tensor | None = None) -> None:
+        self.join()
         """NoisyLinear.reset_noise for every noisy layer (custom_components.py:116-131)."""
         if self.noise_count == 0:
             return
@@ -100,6 +114,7 @@ class LearnEngine:
     # -- forward -------------------------------------------------------------------------------
     def q_values(self, net: NetBuffers, obs: torch.Tensor, support: torch.Tensor | None, use_noise: bool,
                  row_idx: torch.Tensor | None = None, want_argmax: bool = False):
+        self.join()
         desc = self.layout.desc
         rows = obs.shape[0] if row_idx is None else row_idx.numel()
         obs = self._obs(obs)
@@ -151,6 +166,7 @@ class LearnEngine:
         b.obs, b.next_obs, b.action, b.reward, b.done = (t.data_ptr() for t in keep)
         if row_idx is not None:
             b.row_idx = row_idx.data_ptr()
+            keep.append(row_idx)           # read again by the (possibly overlapped) backward
         else:
             for t in keep[2:]:
                 assert t.numel() == B, f"batch fields must have exactly batch_size={B} rows (quirk Q17)"
@@ -169,36 +185,69 @@ class LearnEngine:
         return b, keep
 
     def rainbow_learn(self, passes: list, *, B: int, support: torch.Tensor, weights, weights_mode: int, hp: dict,
-                      noise_normals=None, want_proj: bool = False, row_idx=None):
+                      noise_normals=None, want_proj: bool = False, row_idx=None, overlap: bool = False,
+                      after_loss=None):
         """``passes`` = [(batch, gamma, driver_shapes)], one per ``_dqn_loss`` call of the reference
         (1-step and/or n-step; two entries when combined_reward).  Returns device tensors
-        (loss_scalar[1], loss_elem[B], priorities[B], proj)."""
+        (loss_scalar[1], loss_elem[B], priorities[B], proj).
+
+        ``after_loss(priorities)`` (optional) is called once the loss / priorities of the last pass are
+        enqueued — before the backward — so the caller can enqueue the tree write-back there.
+        ``overlap`` (single pass only): backward + optimiser + noise reset go to the engine's own
+        stream; the caller's stream only carries sample, forward, loss and ``after_loss``."""
+        self.join()
         desc = ctypes.byref(self.layout.desc)
-        stream = _lib.stream_ptr(self.device)
         loss_elem = torch.empty(B, dtype=torch.float32, device=self.device)
         priorities = torch.empty(B, dtype=torch.float32, device=self.device)
         loss_scalar = torch.empty(1, dtype=torch.float32, device=self.device)
         proj = torch.empty((B, self.layout.desc.n_atoms), dtype=torch.float32, device=self.device) if want_proj else None
         self.step += 1
         keepalive = []
-        cfg = None
+        za, zt = noise_normals if noise_normals is not None else (None, None)
+        overlap = overlap and len(passes) == 1
+        cfg = bufs = None
         for i, (batch, gamma, driver) in enumerate(passes):
             cfg = self._cfg(B, gamma=gamma, v_min=hp["v_min"], v_max=hp["v_max"], delta_z=hp["delta_z"],
                             weights_mode=weights_mode, driver_shapes=int(driver), clip=1, lr=hp["lr"], tau=hp["tau"],
                             prior_eps=hp["prior_eps"], accumulate=int(i > 0), use_noise=1, step=self.step)
             bufs, keep = self._bufs(B, batch, weights, support, loss_elem, priorities, loss_scalar, proj, row_idx)
             keepalive.append(keep)
-            _lib.check(self.lib.b2rl_rainbow_loss(desc, ctypes.byref(cfg), ctypes.byref(bufs), stream))
+            _lib.check(self.lib.b2rl_rainbow_loss(desc, ctypes.byref(cfg), ctypes.byref(bufs), _lib.stream_ptr(self.device)))
+            if i + 1 < len(passes):
+                _lib.check(self.lib.b2rl_rainbow_backward(desc, ctypes.byref(cfg), ctypes.byref(bufs),
+                                                          _lib.stream_ptr(self.device)))
+        keepalive.append([loss_elem, priorities, loss_scalar, proj, support, weights])
+        self._keepalive = keepalive         # everything the tail reads stays allocated until the next join
+
+        def tail():
+            stream = _lib.stream_ptr(self.device)
             _lib.check(self.lib.b2rl_rainbow_backward(desc, ctypes.byref(cfg), ctypes.byref(bufs), stream))
-        _lib.check(self.lib.b2rl_optim_step(desc, ctypes.byref(cfg), ctypes.byref(bufs), stream))
-        # dqn_rainbow.py:484-485 — actor.reset_noise() then actor_target.reset_noise()
-        za, zt = noise_normals if noise_normals is not None else (None, None)
-        self.reset_noise(self.actor, za)
-        self.reset_noise(self.target, zt)
-        self._keepalive = keepalive
+            _lib.check(self.lib.b2rl_optim_step(desc, ctypes.byref(cfg), ctypes.byref(bufs), stream))
+            # dqn_rainbow.py:484-485 — actor.reset_noise() then actor_target.reset_noise()
+            self.reset_noise(self.actor, za)
+            self.reset_noise(self.target, zt)
+
+        if overlap:
+            fwd_done = torch.cuda.Event()
+            fwd_done.record(torch.cuda.current_stream(self.device))
+            if after_loss is not None:
+                after_loss(priorities)
+            if self._bwd_stream is None:
+                self._bwd_stream = torch.cuda.Stream(device=self.device)
+            with torch.cuda.stream(self._bwd_stream):
+                self._bwd_stream.wait_event(fwd_done)
+                tail()
+                done = torch.cuda.Event()
+                done.record(self._bwd_stream)
+            self._opt_done = done
+        else:
+            if after_loss is not None:
+                after_loss(priorities)
+            tail()
         return loss_scalar, loss_elem, priorities, proj
 
     def dqn_learn(self, batch: dict, *, B: int, hp: dict, double: bool):
+        self.join()
         desc = ctypes.byref(self.layout.desc)
         loss_elem = torch.empty(B, dtype=torch.float32, device=self.device)
         loss_scalar = torch.empty(1, dtype=torch.float32, device=self.device)
@@ -212,16 +261,23 @@ class LearnEngine:
 
     # -- fused HBM-resident step ---------------------------------------------------------------
     def rainbow_fused_step(self, per, n_step_memory, *, B: int, beta: float, support: torch.Tensor, hp: dict,
-                           gamma_n: float, weights_mode: int = 1, uniforms=None, noise_normals=None):
+                           gamma_n: float, weights_mode: int = 1, uniforms=None, noise_normals=None,
+                           overlap: bool = False):
         """One gradient step with the replay resident in HBM and no host round trip:
         sample (tree descent + IS weights + n-step scalars, one kernel) -> learn with the encoder
         reading frames from the ring through the sampled indices -> priorities written back into
-        the trees on device.  Equivalent to train_off_policy.py:399-412 for one agent."""
+        the trees on device.  Equivalent to train_off_policy.py:399-412 for one agent.
+
+        The priorities exist as soon as the loss does, so the tree write-back is enqueued before the
+        backward: with ``overlap`` the next sampler on this stream (the next agent of the population
+        sharing the buffer) sees exactly the tree the sequential loop would show it, while this
+        agent's backward + optimiser still run on its own stream."""
+        self.join()
         idx, w, a, r, d = per.sample_fused(B, beta, n_step_memory, uniforms)
         f = n_step_memory._fields
         batch = dict(obs=f[("obs",)], next_obs=f[(n_step_memory.ns_key,)], action=a, reward=r, done=d)
         loss, loss_elem, pri, _ = self.rainbow_learn([(batch, gamma_n, False)], B=B, support=support, weights=w,
                                                      weights_mode=weights_mode, hp=hp, noise_normals=noise_normals,
-                                                     row_idx=idx)
-        per.update_priorities_device(idx, pri)
+                                                     row_idx=idx, overlap=overlap,
+                                                     after_loss=lambda p: per.update_priorities_device(idx, p))
         return loss, idx, pri

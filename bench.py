@@ -150,10 +150,16 @@ def hp():
     return dict(v_min=V_MIN, v_max=V_MAX, delta_z=(V_MAX - V_MIN) / (N_ATOMS - 1), lr=LR, tau=TAU, prior_eps=PRIOR_EPS)
 
 
+OVERLAP = os.environ.get("B2RL_BENCH_OVERLAP", "1") != "0"
+
+
 def fused_population_step(agents, mem, nmem, support=None):
+    """One learn step of every local agent against the shared HBM replay.  The tree is read and
+    written in agent order on the caller's stream (the reference's sequential semantics); with
+    OVERLAP each agent's backward + optimiser runs on its own stream under the next agents' forwards."""
     last = None
     for agent in agents:
-        last = agent.learn_from_buffers(mem, nmem)       # fused HBM-resident gradient step
+        last = agent.learn_from_buffers(mem, nmem, overlap=OVERLAP)       # fused HBM-resident gradient step
     return last
 
 
@@ -178,7 +184,9 @@ def api_population_step(agents, mem, nmem, support, host_tr):
     return out
 
 
-def time_region(fn, steps, dist_on):
+def time_region(fn, steps, dist_on, finish=None):
+    """``finish`` joins work left on side streams (overlapped learn tails) into the timed stream
+    before the closing event, so the region covers every kernel of the K steps."""
     import torch.distributed as dist
     if dist_on:
         dist.barrier()
@@ -187,6 +195,8 @@ def time_region(fn, steps, dist_on):
     e0.record()
     for _ in range(steps):
         fn()
+    if finish is not None:
+        finish()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -326,12 +336,15 @@ def main():
     step_fn = lambda: fused_population_step(engines, mem, nmem, support)
     for _ in range(max(args.warmup, 3)):
         step_fn()
+    for a in engines:
+        a.synchronize()
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     l0 = lib.b2rl_launch_count()
-    ms = time_region(step_fn, args.steps, dist_on)
+    join_all = lambda: [a.synchronize() for a in engines]
+    ms = time_region(step_fn, args.steps, dist_on, finish=join_all)
     launches = (lib.b2rl_launch_count() - l0)
     clocks = sampler.stop() if rank == 0 else None
     value = POP * args.steps / (ms / 1e3)

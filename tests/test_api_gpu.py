@@ -225,3 +225,39 @@ def test_checkpoint_round_trip(tmp_path):
     for k, v in a.actor.state_dict().items():
         assert torch.equal(v, b.actor.state_dict()[k]), k
     assert b.fitness == [1.5]
+
+
+def test_overlapped_learn_tail_is_bit_identical_to_sequential():
+    """learn_from_buffers(overlap=True) leaves backward + optimiser on the agent's own stream; the
+    tree write-back stays ahead of the next agent's sampling on the caller's stream.  Parameters of
+    every agent and the priority trees must equal the sequential run bit for bit."""
+    from agilerl_b200.components import MultiStepReplayBuffer, PrioritizedReplayBuffer
+    from agilerl_b200.utils.utils import create_population
+    obs_space, act_space = _spaces()
+
+    def run(overlap):
+        torch.manual_seed(0)
+        np.random.seed(0)
+        pop = create_population("Rainbow DQN", obs_space, act_space, dict(NET),
+                                {"BATCH_SIZE": 16, "LEARN_STEP": 1, "V_MIN": -10.0, "V_MAX": 10.0, "N_STEP": 3},
+                                population_size=3)
+        for i, a in enumerate(pop):
+            a.engine.philox_seed, a.engine.philox_offset = 1000 + i, 0
+        mem, nmem = PrioritizedReplayBuffer(256, 0.6), MultiStepReplayBuffer(256, 3, 0.99)
+        _fill(pop[0], mem, nmem, VecEnv((3, 20, 20), 4, num_envs=2, image=True, seed=3), steps=60)
+        losses = []
+        for _ in range(4):
+            for a in pop:
+                losses.append(a.learn_from_buffers(mem, nmem, overlap=overlap))
+        for a in pop:
+            a.synchronize()
+        torch.cuda.synchronize()
+        params = [a.actor.buffers.params.clone() for a in pop] + [a.actor_target.buffers.params.clone() for a in pop]
+        return params, torch.stack([l.reshape(()) for l in losses]), mem.sum_tree._t.clone(), mem.min_tree._t.clone()
+
+    p0, l0, s0, m0 = run(False)
+    p1, l1, s1, m1 = run(True)
+    assert torch.equal(l0, l1)
+    assert torch.equal(s0, s1) and torch.equal(m0, m1)
+    for a, b in zip(p0, p1):
+        assert torch.equal(a, b)
