@@ -131,6 +131,8 @@ struct LearnWS {
     float *cmat;                    // [N, N] (driver-shape mode)
     float *partial;
     size_t partial_floats;
+    float *partial_tg;              // scratch of the target forward (runs concurrently with the online one)
+    size_t partial_tg_floats;
     float *norm_partials;           // kNormBlocks
     float *wsum;                    // 1
     size_t bytes;
@@ -152,9 +154,28 @@ static void carve_learn(const b2rl_net_desc &net, int64_t B, bool two_sided_onli
     ws.cmat = b.take<float>((int64_t)net.n_atoms * net.n_atoms);
     ws.partial_floats = max_partial_floats(net, online_rows, B);
     ws.partial = b.take<float>(ws.partial_floats);
+    ws.partial_tg_floats = max_partial_floats(net, B, 0);
+    ws.partial_tg = b.take<float>(ws.partial_tg_floats);
     ws.norm_partials = b.take<float>(kNormBlocks);
     ws.wsum = b.take<float>(4);
     ws.bytes = b.off + 256;
+}
+
+// side stream + events for the fork/join inside rainbow_loss (one set per process; the callers of the
+// loss are ordered among themselves, so one side stream keeps every dependency a stream order)
+struct ForkJoin {
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static int fork_join(ForkJoin **out) {
+    static ForkJoin fj;
+    if (!fj.side) {
+        B2RL_CUDA(cudaStreamCreateWithFlags(&fj.side, cudaStreamNonBlocking));
+        B2RL_CUDA(cudaEventCreateWithFlags(&fj.fork, cudaEventDisableTiming));
+        B2RL_CUDA(cudaEventCreateWithFlags(&fj.join, cudaEventDisableTiming));
+    }
+    *out = &fj;
+    return B2RL_OK;
 }
 
 struct FwdWS {
@@ -1194,14 +1215,26 @@ static int rainbow_loss(const b2rl_net_desc &net, const b2rl_learn_cfg &cfg, con
         if ((rc = compose_weights(net, bufs.target_params, bufs.target_eps, ws.weff_target, s)) != B2RL_OK) return rc;
     }
     Scratch sc{ws.partial, ws.partial_floats};
+    // target network on next_obs (forward #2) on a side stream, concurrently with the online pass
+    static const bool fork_on = !(getenv("B2RL_NO_FORK") && getenv("B2RL_NO_FORK")[0] == '1');
+    ForkJoin *fj = nullptr;
+    cudaStream_t st = s;
+    if (fork_on) {
+        if ((rc = fork_join(&fj)) != B2RL_OK) return rc;
+        B2RL_CUDA(cudaEventRecord(fj->fork, s));
+        B2RL_CUDA(cudaStreamWaitEvent(fj->side, fj->fork, 0));
+        st = fj->side;
+    }
+    ObsChunk tg_chunk{bufs.next_obs, bufs.row_idx, B};
+    Scratch sc_tg{ws.partial_tg, ws.partial_tg_floats};
+    if ((rc = forward_pass(net, bufs.target_params, ws.weff_target, noise, &tg_chunk, 1, B, ws.target, sc_tg, st)) != B2RL_OK)
+        return rc;
+    if (fork_on) B2RL_CUDA(cudaEventRecord(fj->join, fj->side));
     // online network on [next_obs ; obs]  (forwards #1 and #3 of _dqn_loss share weights and noise)
     ObsChunk on_chunks[2] = {{bufs.next_obs, bufs.row_idx, B}, {bufs.obs, bufs.row_idx, B}};
     if ((rc = forward_pass(net, bufs.actor_params, ws.weff_actor, noise, on_chunks, 2, 2 * B, ws.online, sc, s)) != B2RL_OK)
         return rc;
-    // target network on next_obs (forward #2)
-    ObsChunk tg_chunk{bufs.next_obs, bufs.row_idx, B};
-    if ((rc = forward_pass(net, bufs.target_params, ws.weff_target, noise, &tg_chunk, 1, B, ws.target, sc, s)) != B2RL_OK)
-        return rc;
+    if (fork_on) B2RL_CUDA(cudaStreamWaitEvent(s, fj->join, 0));
     const float *v_on = ws.online.val[net.n_val - 1].a, *adv_on = ws.online.adv[net.n_adv - 1].a;
     const float *v_tg = ws.target.val[net.n_val - 1].a, *adv_tg = ws.target.adv[net.n_adv - 1].a;
     const size_t sm_q = sizeof(float) * ((size_t)A * N + A);
