@@ -363,9 +363,14 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const Conv
             }
         }
     };
+    if (KB >= D) {
 #pragma unroll
-    for (int d = 0; d < D; ++d)
-        if (d < KB) gather(d, raw[d]);
+        for (int d = 0; d < D; ++d) gather(d, raw[d]);
+    } else {
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+            if (d < KB) gather(d, raw[d]);
+    }
 
     auto step = [&](int kb, uint32_t (&cur)[RAWN]) {
         const int s = kb % SA;
@@ -641,7 +646,7 @@ struct ConvWgradTcParams {
     int normalize;
     int with_bias;              // partial has Mtaps+1 rows; the last one carries the bias gradient (N <= 32)
     float low, high;
-    float inv_ow;               // 1 / OW (pixel decode without integer division)
+    float inv_ow, inv_p;        // 1 / OW, 1 / P (pixel decode without integer division; Kpix < 2^22)
 };
 
 constexpr uint32_t kWgLboA = kTcBM * 16 + 16;        // padded K-chunk pitch of the wgrad A tile
@@ -747,7 +752,8 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_wgrad_tc_kernel(const Co
             const int pix = min(pix0 + kb * kTcBK + pl, pix1 - 1);
             int64_t base;
             {
-                const int b = pix / p.P, pp = pix - b * p.P;
+                int b = __float2int_rz(((float)pix + 0.5f) * p.inv_p), pp = pix - b * p.P;
+                if (pp < 0) { --b; pp += p.P; } else if (pp >= p.P) { ++b; pp -= p.P; }      // reciprocal off by one
                 const int oy = __float2int_rz(((float)pp + 0.5f) * p.inv_ow), ox = pp - oy * p.OW;
                 const int64_t bb = p.gather ? p.gather[b] : (int64_t)b;
                 base = bb * p.in_bstride + (int64_t)(oy * p.sy + ox * p.sx);
@@ -767,7 +773,8 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_wgrad_tc_kernel(const Co
             }
             // ---- B: 4 consecutive pixels of channel n (only the first 32 channels are prefetched)
             const int px0 = pix0 + kb * kTcBK + q * 4;
-            int b = px0 / p.P, pp = px0 - b * p.P;
+            int b = __float2int_rz(((float)px0 + 0.5f) * p.inv_p), pp = px0 - b * p.P;
+            if (pp < 0) { --b; pp += p.P; } else if (pp >= p.P) { ++b; pp -= p.P; }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 gv[j] = (n < p.N && px0 + j < pix1) ? __ldg(p.g + ((int64_t)b * p.N + n) * p.P + pp) : 0.f;
@@ -915,7 +922,7 @@ static int launch_conv_wgrad_tc(const b2rl_layer &l, const Operand &X, const flo
     const int KK = l.ksize * l.ksize, Kc = l.in_c * KK, P = l.out_h * l.out_w;
     const int n_pad = (l.out_c + 15) / 16 * 16;
     const int64_t Kpix = rows * P;
-    if (n_pad > 256 || Kpix > INT32_MAX || partial == nullptr) return 1;
+    if (n_pad > 256 || Kpix >= (1 << 22) || partial == nullptr) return 1;     // float-reciprocal pixel decode is exact below 2^22
     const int mt = (Kc + kTcBM - 1) / kTcBM;
     int64_t splits = (2 * (int64_t)sm_count() + mt - 1) / mt;
     const int64_t max_splits = (Kpix + 4 * kTcBK - 1) / (4 * kTcBK);
@@ -937,7 +944,7 @@ static int launch_conv_wgrad_tc(const b2rl_layer &l, const Operand &X, const flo
     p.pix_per_cta = pix_per_cta;
     p.with_bias = with_bias;
     p.normalize = X.normalize; p.low = X.normalize ? X.low : 0.f; p.high = X.normalize ? X.high : 1.f;
-    p.inv_ow = 1.0f / (float)l.out_w;
+    p.inv_ow = 1.0f / (float)l.out_w; p.inv_p = 1.0f / (float)P;
     const bool vec = X.u8 && l.ksize % 4 == 0 && l.stride % 4 == 0 && l.in_w % 4 == 0 && (l.in_h * l.in_w) % 4 == 0 &&
                      reinterpret_cast<uintptr_t>(X.ptr) % 4 == 0;
     dim3 grid(mt, (unsigned)splits);

@@ -110,6 +110,158 @@ tree_set_kernel(double *__restrict__ st, double *__restrict__ mt, int64_t cap,
     }
 }
 
+// Fast path for a learn batch (n <= kFastMax distinct-or-not leaves, both trees, cap <= 2^24):
+// no global-memory round trip between levels.  A thread carries the value of the node on its own
+// leaf-to-root path in registers; the sibling at every level is either untouched by this batch —
+// then its value was prefetched from global memory up front, all levels at once, one latency — or
+// it lies on another thread's path, which published it the level before in a shared-memory hash
+// table (three tables in rotation: read l-1, fill l, clear l+1; one __syncthreads per level).
+// Same arithmetic as tree_set_kernel (left + right, Python min(left, right)), same last-writer rule.
+constexpr int kFastMax = 512;
+constexpr int kFastLevels = 24;
+constexpr int kFastEmpty = -1;
+
+__device__ __forceinline__ uint32_t fast_hash(uint32_t key, int bits) { return (key * 2654435761u) >> (32 - bits); }
+
+template <bool kFromPriority>
+__global__ void __launch_bounds__(kFastMax)
+tree_set_fast_kernel(double *__restrict__ st, double *__restrict__ mt, int64_t cap, int levels,
+                     const int64_t *__restrict__ idx, const double *__restrict__ pa, const float *__restrict__ pri,
+                     int n, int tbits, double alpha, double floor_, double *max_priority) {
+    extern __shared__ __align__(16) unsigned char tsm[];
+    const int T = 1 << tbits;
+    // [3][T] keys | [3][T] sum values | [3][T] min values | [T] last-writer position
+    int *keys = reinterpret_cast<int *>(tsm);
+    double *vs = reinterpret_cast<double *>(tsm + (size_t)3 * T * sizeof(int) + (size_t)T * sizeof(int));
+    double *vm = vs + (size_t)3 * T;
+    int *lastpos = keys + 3 * T;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 3 * T; i += blockDim.x) keys[i] = kFastEmpty;
+    for (int i = tid; i < T; i += blockDim.x) lastpos[i] = -1;
+    __syncthreads();
+
+    const bool have = tid < n;
+    const int id = have ? (int)idx[tid] : 0;
+    double v = 0.0, local_max = 0.0;
+    if (have) {
+        if (kFromPriority) {
+            double p = (double)pri[tid];
+            p = p < floor_ ? floor_ : p;          // max(priority, 1e-5), replay_buffer.py:425
+            local_max = p;
+            v = pow(p, alpha);
+        } else v = pa[tid];
+    }
+    // ---- last writer of every leaf (table 0 doubles as the leaf-id set for this phase)
+    int lslot = 0;
+    if (have) {
+        lslot = (int)fast_hash((uint32_t)id, tbits);
+        while (true) {
+            const int k = atomicCAS(&keys[lslot], kFastEmpty, id);
+            if (k == kFastEmpty || k == id) break;
+            lslot = (lslot + 1) & (T - 1);
+        }
+        atomicMax(&lastpos[lslot], tid);
+    }
+    if (kFromPriority && max_priority != nullptr) {
+        // block max -> *max_priority = max(*max_priority, max_i p_i)  (replay_buffer.py:329)
+        __shared__ double smax[kFastMax / 32];
+        for (int o = 16; o > 0; o >>= 1) {
+            const double other = __shfl_xor_sync(0xffffffffu, local_max, o);
+            local_max = other > local_max ? other : local_max;
+        }
+        if ((tid & 31) == 0) smax[tid >> 5] = local_max;
+        __syncthreads();
+        if (tid == 0) {
+            double m = *max_priority;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = smax[w] > m ? smax[w] : m;
+            *max_priority = m;
+        }
+    }
+    __syncthreads();
+    const bool active = have && lastpos[lslot] == tid;
+    __syncthreads();
+    for (int i = tid; i < T; i += blockDim.x) keys[i] = kFastEmpty;      // table 0 becomes the leaf level's table
+    // ---- prefetch the sibling of every node on this leaf's path (values before this batch)
+    uint32_t node = (uint32_t)cap + (uint32_t)id;
+    double sib_s[kFastLevels], sib_m[kFastLevels];
+#pragma unroll
+    for (int l = 0; l < kFastLevels; ++l) {
+        sib_s[l] = 0.0; sib_m[l] = 0.0;
+        if (active && l < levels) {
+            const uint32_t sb = (node >> l) ^ 1u;
+            sib_s[l] = st[sb];
+            sib_m[l] = mt[sb];
+        }
+    }
+    __syncthreads();
+    double my_s = v, my_m = v;
+    auto publish = [&](int table, uint32_t key, double a, double b) {
+        int *kt = keys + table * T;
+        int slot = (int)fast_hash(key, tbits);
+        while (true) {
+            const int k = atomicCAS(&kt[slot], kFastEmpty, (int)key);
+            if (k == kFastEmpty || k == (int)key) break;
+            slot = (slot + 1) & (T - 1);
+        }
+        vs[table * T + slot] = a;          // threads sharing the node hold identical values
+        vm[table * T + slot] = b;
+    };
+    if (active) {
+        st[node] = v;
+        mt[node] = v;
+        publish(0, node, v, v);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int l = 0; l < kFastLevels; ++l) {
+        if (l < levels) {
+            const int rd = l % 3, wr = (l + 1) % 3, cl = (l + 2) % 3;
+            for (int i = tid; i < T; i += blockDim.x) keys[cl * T + i] = kFastEmpty;
+            if (active) {
+                const uint32_t sb = node ^ 1u;
+                double o_s = sib_s[l], o_m = sib_m[l];
+                const int *kt = keys + rd * T;
+                int slot = (int)fast_hash(sb, tbits);
+                while (true) {
+                    const int k = kt[slot];
+                    if (k == (int)sb) { o_s = vs[rd * T + slot]; o_m = vm[rd * T + slot]; break; }
+                    if (k == kFastEmpty) break;
+                    slot = (slot + 1) & (T - 1);
+                }
+                const bool left = (node & 1u) == 0;
+                const double ns = left ? __dadd_rn(my_s, o_s) : __dadd_rn(o_s, my_s);
+                const double nm = left ? dmin_py(my_m, o_m) : dmin_py(o_m, my_m);
+                node >>= 1;
+                st[node] = ns;
+                mt[node] = nm;
+                my_s = ns; my_m = nm;
+                publish(wr, node, ns, nm);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+static bool tree_fast_ok(const double *st, const double *mt, int64_t cap, int64_t n) {
+    return st && mt && n >= 1 && n <= kFastMax && cap >= 2 && cap <= ((int64_t)1 << kFastLevels);
+}
+template <bool kFromPriority>
+static int launch_tree_fast(double *st, double *mt, int64_t cap, const int64_t *idx, const double *pa, const float *pri,
+                            int64_t n, double alpha, double floor_, double *max_priority, cudaStream_t s) {
+    int levels = 0;
+    while (((int64_t)1 << levels) < cap) ++levels;
+    int tbits = 6;
+    while ((1 << tbits) < 2 * n) ++tbits;
+    const int T = 1 << tbits;
+    const size_t smem = (size_t)4 * T * sizeof(int) + (size_t)6 * T * sizeof(double);
+    const int threads = (int)((n + 31) / 32 * 32);
+    auto kern = tree_set_fast_kernel<kFromPriority>;
+    if (smem > 48 * 1024) B2RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<1, threads, smem, s>>>(st, mt, cap, levels, idx, pa, pri, (int)n, tbits, alpha, floor_, max_priority);
+    B2RL_LAUNCH_CHECK();
+    return B2RL_OK;
+}
+
 // Bulk rebuild of one level (used when a range update touches more than kTreeChunk leaves).
 __global__ void tree_level_kernel(double *st, double *mt, int64_t first, int64_t count) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -217,6 +369,8 @@ int b2rl_tree_set(double *sum_tree, double *min_tree, int64_t cap, const int64_t
     B2RL_CHECK_ARG(is_pow2(cap), "capacity must be positive and a power of 2.");
     B2RL_CHECK_ARG(n >= 0, "n must be >= 0");
     B2RL_CHECK_ARG(sum_tree || min_tree, "both trees are NULL");
+    if (tree_fast_ok(sum_tree, min_tree, cap, n))
+        return launch_tree_fast<false>(sum_tree, min_tree, cap, idx, p_alpha, nullptr, n, 0.0, 0.0, nullptr, as_stream(stream));
     for (int64_t off = 0; off < n; off += kTreeChunk) {   // chunks keep last-writer-wins order
         const int64_t m = n - off < kTreeChunk ? n - off : kTreeChunk;
         tree_set_kernel<false, false><<<1, kTreeThreads, 0, as_stream(stream)>>>(
@@ -230,6 +384,9 @@ int b2rl_tree_set_from_priorities(double *sum_tree, double *min_tree, int64_t ca
                                   const float *priority, int64_t n, double alpha, double floor_,
                                   double *max_priority, void *stream) {
     B2RL_CHECK_ARG(is_pow2(cap), "capacity must be positive and a power of 2.");
+    if (tree_fast_ok(sum_tree, min_tree, cap, n))
+        return launch_tree_fast<true>(sum_tree, min_tree, cap, idx, nullptr, priority, n, alpha, floor_, max_priority,
+                                      as_stream(stream));
     for (int64_t off = 0; off < n; off += kTreeChunk) {
         const int64_t m = n - off < kTreeChunk ? n - off : kTreeChunk;
         tree_set_kernel<false, true><<<1, kTreeThreads, 0, as_stream(stream)>>>(
