@@ -170,7 +170,11 @@ struct ForkJoin {
 static int fork_join(ForkJoin **out) {
     static ForkJoin fj;
     if (!fj.side) {
-        B2RL_CUDA(cudaStreamCreateWithFlags(&fj.side, cudaStreamNonBlocking));
+        // the forward chain is the population's critical path (the next sampler waits on its priorities):
+        // give its side stream the highest priority so its CTAs are placed ahead of overlapped backward work
+        int lo = 0, hi = 0;
+        B2RL_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        B2RL_CUDA(cudaStreamCreateWithPriority(&fj.side, cudaStreamNonBlocking, hi));
         B2RL_CUDA(cudaEventCreateWithFlags(&fj.fork, cudaEventDisableTiming));
         B2RL_CUDA(cudaEventCreateWithFlags(&fj.join, cudaEventDisableTiming));
     }

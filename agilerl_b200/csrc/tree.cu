@@ -9,6 +9,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include <cstdlib>
 
 namespace b2rl {
 
@@ -243,7 +244,8 @@ tree_set_fast_kernel(double *__restrict__ st, double *__restrict__ mt, int64_t c
 }
 
 static bool tree_fast_ok(const double *st, const double *mt, int64_t cap, int64_t n) {
-    return st && mt && n >= 1 && n <= kFastMax && cap >= 2 && cap <= ((int64_t)1 << kFastLevels);
+    static const bool off = getenv("B2RL_TREE_SLOW") && getenv("B2RL_TREE_SLOW")[0] == '1';
+    return !off && st && mt && n >= 1 && n <= kFastMax && cap >= 2 && cap <= ((int64_t)1 << kFastLevels);
 }
 template <bool kFromPriority>
 static int launch_tree_fast(double *st, double *mt, int64_t cap, const int64_t *idx, const double *pa, const float *pri,

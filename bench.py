@@ -163,6 +163,17 @@ def fused_population_step(agents, mem, nmem, support=None):
     return last
 
 
+_HI = {}
+
+
+def hi_priority_stream(device):
+    """The sample -> forward -> loss -> priority write-back chain is serial over the population; run it
+    on a high-priority stream so the block scheduler places its CTAs ahead of the overlapped backward."""
+    if device not in _HI:
+        _HI[device] = torch.cuda.Stream(device=device, priority=-1)
+    return _HI[device]
+
+
 def api_population_step(agents, mem, nmem, support, host_tr):
     """The public-API path with host buffers — exactly what train_off_policy.py:327-412 does per
     learn step: Transition -> n_step_memory.add -> memory.add -> sampler.sample ->
@@ -333,7 +344,16 @@ def main():
     support = torch.linspace(V_MIN, V_MAX, N_ATOMS).to(device)
 
     # ---- value: fused device path ------------------------------------------------------------
-    step_fn = lambda: fused_population_step(engines, mem, nmem, support)
+    if OVERLAP and os.environ.get("B2RL_BENCH_HIPRI", "1") != "0":
+        hp_stream = hi_priority_stream(device)
+
+        def step_fn():
+            hp_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(hp_stream):
+                fused_population_step(engines, mem, nmem, support)
+            torch.cuda.current_stream().wait_stream(hp_stream)
+    else:
+        step_fn = lambda: fused_population_step(engines, mem, nmem, support)
     for _ in range(max(args.warmup, 3)):
         step_fn()
     for a in engines:
