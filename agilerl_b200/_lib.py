@@ -141,7 +141,19 @@ def check(rc: int) -> None:
     raise B2RLError(msg)
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr(device=None) -> int:
+    """cudaStream_t of torch's current stream on ``device`` (hot: called before every C-ABI launch)."""
+    if _raw_stream is not None:
+        if device is None:
+            idx = torch.cuda.current_device()
+        else:
+            idx = device.index if isinstance(device, torch.device) else torch.device(device).index
+            if idx is None:
+                idx = torch.cuda.current_device()
+        return _raw_stream(idx)
     return torch.cuda.current_stream(device).cuda_stream
 
 

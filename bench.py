@@ -154,24 +154,12 @@ OVERLAP = os.environ.get("B2RL_BENCH_OVERLAP", "1") != "0"
 
 
 def fused_population_step(agents, mem, nmem, support=None):
-    """One learn step of every local agent against the shared HBM replay.  The tree is read and
-    written in agent order on the caller's stream (the reference's sequential semantics); with
-    OVERLAP each agent's backward + optimiser runs on its own stream under the next agents' forwards."""
-    last = None
-    for agent in agents:
-        last = agent.learn_from_buffers(mem, nmem, overlap=OVERLAP)       # fused HBM-resident gradient step
-    return last
-
-
-_HI = {}
-
-
-def hi_priority_stream(device):
-    """The sample -> forward -> loss -> priority write-back chain is serial over the population; run it
-    on a high-priority stream so the block scheduler places its CTAs ahead of the overlapped backward."""
-    if device not in _HI:
-        _HI[device] = torch.cuda.Stream(device=device, priority=-1)
-    return _HI[device]
+    """One learn step of every local agent against the shared HBM replay (agilerl_b200.training.
+    population_learn).  The tree is read and written in agent order on one high-priority stream (the
+    reference's sequential semantics); each agent's backward + optimiser runs on its own stream under
+    the next agents' forwards.  Tails are joined once, at the end of the timed region."""
+    from agilerl_b200.training.population import population_learn
+    return population_learn(agents, mem, nmem, overlap=OVERLAP, join=False)[-1]
 
 
 def api_population_step(agents, mem, nmem, support, host_tr):
@@ -344,16 +332,7 @@ def main():
     support = torch.linspace(V_MIN, V_MAX, N_ATOMS).to(device)
 
     # ---- value: fused device path ------------------------------------------------------------
-    if OVERLAP and os.environ.get("B2RL_BENCH_HIPRI", "1") != "0":
-        hp_stream = hi_priority_stream(device)
-
-        def step_fn():
-            hp_stream.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(hp_stream):
-                fused_population_step(engines, mem, nmem, support)
-            torch.cuda.current_stream().wait_stream(hp_stream)
-    else:
-        step_fn = lambda: fused_population_step(engines, mem, nmem, support)
+    step_fn = lambda: fused_population_step(engines, mem, nmem, support)
     for _ in range(max(args.warmup, 3)):
         step_fn()
     for a in engines:

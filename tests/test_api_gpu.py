@@ -245,10 +245,13 @@ def test_overlapped_learn_tail_is_bit_identical_to_sequential():
             a.engine.philox_seed, a.engine.philox_offset = 1000 + i, 0
         mem, nmem = PrioritizedReplayBuffer(256, 0.6), MultiStepReplayBuffer(256, 3, 0.99)
         _fill(pop[0], mem, nmem, VecEnv((3, 20, 20), 4, num_envs=2, image=True, seed=3), steps=60)
+        from agilerl_b200.training import population_learn
         losses = []
         for _ in range(4):
-            for a in pop:
-                losses.append(a.learn_from_buffers(mem, nmem, overlap=overlap))
+            if overlap:      # high-priority forward chain + per-agent backward streams
+                losses += population_learn(pop, mem, nmem, overlap=True, join=False)
+            else:
+                losses += [a.learn_from_buffers(mem, nmem) for a in pop]
         for a in pop:
             a.synchronize()
         torch.cuda.synchronize()
