@@ -263,18 +263,32 @@ def cpu_reference(steps, warmup, cores):
                      action=torch.randint(0, N_ACT, (n_buf,), generator=g).float(),
                      next_obs=torch.randint(0, 256, (n_buf, *OBS), dtype=torch.uint8, generator=g),
                      reward=torch.randn(n_buf, generator=g), done=(torch.rand(n_buf, generator=g) < 0.01).float()))
-    times = []
-    for it in range(warmup + steps):
+    def one_step():
         t0 = time.perf_counter()
         exp = mem.sample(B, BETA)
         nexp = nmem.gather(exp["idxs"].squeeze(1))
         exp["weights"] = exp["weights"].squeeze(1)
         loss, idxs, pri = agent.learn_rainbow(exp, nexp, per=True)
         mem.update_priorities(idxs, pri)
-        dt = time.perf_counter() - t0
+        return time.perf_counter() - t0
+
+    # the host's best thread count for this workload (oversubscribing a many-core box slows torch's CPU
+    # convolutions down): one probe step per candidate, keep the fastest
+    one_step()
+    cands = sorted({c for c in (cores, cores // 2, cores // 4, 32, 16) if 1 <= c <= cores}, reverse=True)
+    best, best_t = cores, None
+    for c in cands:
+        torch.set_num_threads(c)
+        dt = one_step()
+        if best_t is None or dt < best_t:
+            best, best_t = c, dt
+    torch.set_num_threads(best)
+    times = []
+    for it in range(warmup + steps):
+        dt = one_step()
         if it >= warmup:
             times.append(dt)
-    return times
+    return times, best
 
 
 def main():
@@ -300,7 +314,7 @@ def main():
             return
         steps = max(1, min(args.steps, 10))     # bounded sample: ~1-3 s of CPU per gradient step
         warm = max(1, min(args.warmup, 2))
-        times = cpu_reference(steps, warm, cores)
+        times, cores = cpu_reference(steps, warm, cores)
         per_step = statistics.mean(times)
         val = 1.0 / per_step                     # gradient-steps/s of ONE agent == population rate on one host
         line = {"metric": "population gradient-steps/sec (Rainbow-DQN pop=8)", "value": val, "unit": "steps/s",
@@ -389,25 +403,31 @@ def main():
                      "achieved_gbs_per_gpu": ALG_BYTES_PER_STEP * value / world / 1e9,
                      "frac_of_peak": ALG_BYTES_PER_STEP * value / world / 1e9 / hbm_peak, "peak_gbs": hbm_peak,
                      "peak": peak_kind},
-        "roofline": {"kernel": "conv_fwd_tc_kernel<uint8, exact-A> + weight_split_kernel: conv1 forward (4->32, k8 s4) on "
-                               "B=256 ring rows, tcgen05.mma kind::tf32 (2xTF32 weight split, fp32 TMEM accumulate)",
-                     "bound": "tensor", "achieved": achieved_tf, "peak": tf_peak, "unit": "TFLOP/s",
-                     "frac": achieved_tf / tf_peak,
-                     # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture
-                     # profiles/r1_conv_fwd_tcgen05_v2.txt (frames 7.2 MB read; the 13 MB fp32 output stays in L2)
-                     "traffic": 7405824, "peak_kind": peak_kind + " (dense bf16 cuBLAS burst)",
-                     "flops_per_launch": flops, "alg_bytes_per_launch": kbytes, "ms_per_launch": kms,
-                     "note": "algorithmic fp32-equivalent FLOPs (2*M*N*K); each costs 2 tf32 MMAs (3 for fp32 inputs); the "
-                             "kernel is bound by building the im2col tile on CUDA cores, not by the tensor pipe"},
+        # conv1 forward: 1.68 GFLOP over 20.4 MB of algorithmic traffic = 82 FLOP/B, left of the B200 ridge
+        # (measured 1678 TFLOP/s / 6.59 TB/s = 255 FLOP/B): the roof that bounds it is HBM
+        "roofline": {"kernel": "conv_fwd_tc_kernel<uint8, exact-A> (+ weight_split_kernel): conv1 forward (4->32, k8 s4) "
+                               "of B=256 frames gathered from the replay ring, tcgen05.mma kind::tf32 (2xTF32 weight "
+                               "split, fp32 TMEM accumulate)",
+                     "bound": "hbm", "achieved": kbytes / (kms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": kbytes / (kms * 1e-3) / 1e9 / hbm_peak,
+                     # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (cold L2):
+                     # profiles/r1_conv_fwd_tcgen05_v2.txt (7.2 MB of frames read; the 13 MB fp32 output stays in L2)
+                     "traffic": 7405824, "peak_kind": peak_kind + " (copy bandwidth, burst)",
+                     "alg_bytes_per_launch": kbytes, "flops_per_launch": flops, "ms_per_launch": kms,
+                     "tflops": achieved_tf, "tflops_frac_of_bf16_peak": achieved_tf / tf_peak,
+                     "note": "uint8 frames read once + fp32 activations written once + weights; fp32-equivalent FLOPs "
+                             "2*M*N*K, each costing 2 tf32 MMAs; the kernel is issue/latency-bound on building the im2col "
+                             "tile with CUDA cores (DESIGN.md section 5), not on HBM or the tensor pipe"},
     }
     if e2e is not None:
         line["e2e"] = e2e
     if not args.no_cpu_baseline and world == 1:
-        t = cpu_reference(3, 1, cores)
+        t, used = cpu_reference(3, 1, cores)
         per = statistics.mean(t)
-        line["cpu_baseline"] = {"value": 1.0 / per, "unit": "steps/s", "cores": cores, "kind": "port",
-                                "sample": "3 gradient steps of one agent (B=256, replay bounded to 4096 slots), oracle "
-                                          "restatement of the reference: pure-Python segment trees + torch-CPU learn"}
+        line["cpu_baseline"] = {"value": 1.0 / per, "unit": "steps/s", "cores": used, "kind": "port",
+                                "sample": "3 gradient steps of one agent (B=256, replay bounded to 4096 slots) at the "
+                                          "fastest probed torch thread count, oracle restatement of the reference: "
+                                          "pure-Python segment trees + torch-CPU learn"}
     print(json.dumps(line))
     if dist_on:
         torch.distributed.destroy_process_group()
