@@ -48,6 +48,7 @@ class LearnCfg(Structure):
         ("lr", c_double), ("beta1", c_double), ("beta2", c_double), ("adam_eps", c_double),
         ("bias_correction1", c_double), ("bias_correction2", c_double), ("tau", c_double),
         ("prior_eps", c_double), ("accumulate", c_int32), ("use_noise", c_int32),
+        ("side_streams", c_int32), ("reserved_", c_int32),
     ]
 
 

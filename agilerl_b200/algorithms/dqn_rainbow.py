@@ -173,7 +173,7 @@ class RainbowDQN(RLAlgorithm):
         new_priorities = pri.cpu().numpy() if per else None       # elementwise_loss + prior_eps (:487-488)
         return loss.item(), idxs, new_priorities
 
-    def learn_from_buffers(self, memory, n_step_memory, overlap: bool = False):
+    def learn_from_buffers(self, memory, n_step_memory, overlap: bool = False, side_streams: int | None = None):
         """Fused HBM-resident gradient step (no host round trip): PER sample + learn + priority
         write-back, equivalent to train_off_policy.py:399-412 with canonical shapes.  Returns the
         loss as a DEVICE tensor.
@@ -181,10 +181,13 @@ class RainbowDQN(RLAlgorithm):
         ``overlap=True`` leaves this agent's backward + optimiser running on its own CUDA stream
         when the call returns (the next agent's step can start meanwhile); ``synchronize()`` — or any
         later learn / get_action of this agent — joins it.  Call ``synchronize()`` before touching
-        the parameters through torch (clone, state_dict, mutations) or adding to the buffers."""
+        the parameters through torch (clone, state_dict, mutations) or adding to the buffers.
+        ``side_streams`` (bit 0: target forward, bit 1: weight gradients on library-owned side streams)
+        defaults to 3 for a sequential step and 1 for an overlapped one."""
         loss, idx, pri = self.engine.rainbow_fused_step(memory, n_step_memory, B=self.batch_size, beta=self.beta,
                                                         support=self.support, hp=self._hp(),
-                                                        gamma_n=self.gamma ** self.n_step, overlap=overlap)
+                                                        gamma_n=self.gamma ** self.n_step, overlap=overlap,
+                                                        side_streams=side_streams)
         return loss
 
     def synchronize(self) -> None:

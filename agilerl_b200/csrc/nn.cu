@@ -133,6 +133,8 @@ struct LearnWS {
     size_t partial_floats;
     float *partial_tg;              // scratch of the target forward (runs concurrently with the online one)
     size_t partial_tg_floats;
+    float *partial_bw;              // scratch of the weight-gradient side stream
+    size_t partial_bw_floats;
     float *norm_partials;           // kNormBlocks
     float *wsum;                    // 1
     size_t bytes;
@@ -156,6 +158,8 @@ static void carve_learn(const b2rl_net_desc &net, int64_t B, bool two_sided_onli
     ws.partial = b.take<float>(ws.partial_floats);
     ws.partial_tg_floats = max_partial_floats(net, B, 0);
     ws.partial_tg = b.take<float>(ws.partial_tg_floats);
+    ws.partial_bw_floats = ws.partial_floats;
+    ws.partial_bw = b.take<float>(ws.partial_bw_floats);
     ws.norm_partials = b.take<float>(kNormBlocks);
     ws.wsum = b.take<float>(4);
     ws.bytes = b.off + 256;
@@ -164,8 +168,9 @@ static void carve_learn(const b2rl_net_desc &net, int64_t B, bool two_sided_onli
 // side stream + events for the fork/join inside rainbow_loss (one set per process; the callers of the
 // loss are ordered among themselves, so one side stream keeps every dependency a stream order)
 struct ForkJoin {
-    cudaStream_t side = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
+    cudaStream_t side = nullptr;       // target-network forward (highest priority)
+    cudaStream_t side_bw = nullptr;    // weight gradients of the backward (default priority)
+    cudaEvent_t fork = nullptr, join = nullptr, bw = nullptr;
 };
 static int fork_join(ForkJoin **out) {
     static ForkJoin fj;
@@ -177,6 +182,8 @@ static int fork_join(ForkJoin **out) {
         B2RL_CUDA(cudaStreamCreateWithPriority(&fj.side, cudaStreamNonBlocking, hi));
         B2RL_CUDA(cudaEventCreateWithFlags(&fj.fork, cudaEventDisableTiming));
         B2RL_CUDA(cudaEventCreateWithFlags(&fj.join, cudaEventDisableTiming));
+        B2RL_CUDA(cudaStreamCreateWithFlags(&fj.side_bw, cudaStreamNonBlocking));
+        B2RL_CUDA(cudaEventCreateWithFlags(&fj.bw, cudaEventDisableTiming));
     }
     *out = &fj;
     return B2RL_OK;
@@ -813,13 +820,26 @@ __global__ void q_argmax_kernel(const float *__restrict__ q, int A, int64_t rows
 // ------------------------------------------------------------------------------------------
 // backward of one layer
 // ------------------------------------------------------------------------------------------
+// Weight gradients do not feed the dL/dx chain: when a side stream is given they are enqueued there
+// (own scratch) right after the layer's dL/dz exists, and the caller joins before the optimiser.
+struct WgradSide {
+    cudaStream_t s;
+    Scratch sc;
+    cudaEvent_t ev;
+};
+static int fork_to(const WgradSide *side, cudaStream_t from) {
+    B2RL_CUDA(cudaEventRecord(side->ev, from));
+    B2RL_CUDA(cudaStreamWaitEvent(side->s, side->ev, 0));
+    return B2RL_OK;
+}
+
 static int layer_backward(const b2rl_net_desc &net, const b2rl_layer &l, const float *W, const float *params,
                           const float *x_in,            // input activations of this layer (backward rows)
                           const ObsChunk *obs,          // first layer: where the observations come from
                           const LayerBuf &lb, int64_t row_off,  // forward buffers + offset of the backward rows
                           float *g_out,                 // dL/d(layer output) for the B backward rows
                           float *g_in, bool accumulate_gin, float *grads, float *gweff, int accumulate_grads,
-                          int64_t B, const Scratch &sc, cudaStream_t s) {
+                          int64_t B, const Scratch &sc, cudaStream_t s, const WgradSide *side = nullptr) {
     const int64_t oe = layer_out_elems(l);
     const float *a = lb.a + row_off * oe;
     const float *pre = lb.pre ? lb.pre + row_off * oe : nullptr;
@@ -846,6 +866,14 @@ static int layer_backward(const b2rl_net_desc &net, const b2rl_layer &l, const f
     float *gw = (l.noisy ? gweff : grads) + l.w_off;
     float *gb = (l.noisy ? gweff : grads) + l.b_off;
     const int acc_w = l.noisy ? 0 : accumulate_grads;   // noisy: accumulate happens in noisy_grad
+    cudaStream_t sw = s;
+    const Scratch *scw = &sc;
+    if (side && g_in) {                                   // overlap this layer's dW with its dX and everything below
+        int rcf = fork_to(side, s);
+        if (rcf != B2RL_OK) return rcf;
+        sw = side->s;
+        scw = &side->sc;
+    }
     {
         Operand A, Bm;
         Epilogue epi;
@@ -872,12 +900,12 @@ static int layer_backward(const b2rl_net_desc &net, const b2rl_layer &l, const f
             Bm.ptr = g_out; Bm.row = map_stride(P); Bm.red = map_pixel(P, l.out_w, (int64_t)l.out_c * P, l.out_w, 1);
             rc = 1;
             if (tc_enabled())   // tcgen05 3xTF32 (im2col operand MN-major, split over pixels)
-                rc = launch_conv_wgrad_tc(l, A, g_out, gw, gb, acc_w, B, sc.partial, sc.floats, s);
+                rc = launch_conv_wgrad_tc(l, A, g_out, gw, gb, acc_w, B, scw->partial, scw->floats, sw);
             if (rc == 1) rc = dispatch_elem(A.elem_kind(), [&](auto ek) {
                 return launch_igemm<OpTraits<decltype(ek)::value, MAP_KERNEL, MAP_PIXEL, true, true>,
                                     OpTraits<EL_F32, MAP_STRIDE, MAP_PIXEL, true, false>,
-                                    EpiTraits<EPI_WGRAD_T, MAP_STRIDE, MAP_STRIDE>>(A, Bm, epi, M, N, K, sc.partial,
-                                                                                      sc.floats, s);
+                                    EpiTraits<EPI_WGRAD_T, MAP_STRIDE, MAP_STRIDE>>(A, Bm, epi, M, N, K, scw->partial,
+                                                                                      scw->floats, sw);
             });
         } else {
             M = l.out_c; N = l.in_c + 1; K = (int)B;
@@ -892,8 +920,8 @@ static int layer_backward(const b2rl_net_desc &net, const b2rl_layer &l, const f
             rc = dispatch_elem(Bm.elem_kind(), [&](auto ek) {
                 return launch_igemm<OpTraits<EL_F32, MAP_STRIDE, MAP_STRIDE, false, false>,
                                     OpTraits<decltype(ek)::value, MAP_STRIDE, MAP_STRIDE, false, true>,
-                                    EpiTraits<EPI_WGRAD, MAP_STRIDE, MAP_STRIDE>>(A, Bm, epi, M, N, K, sc.partial,
-                                                                                    sc.floats, s);
+                                    EpiTraits<EPI_WGRAD, MAP_STRIDE, MAP_STRIDE>>(A, Bm, epi, M, N, K, scw->partial,
+                                                                                    scw->floats, sw);
             });
         }
         if (rc != B2RL_OK) return rc;
@@ -936,7 +964,8 @@ static int layer_backward(const b2rl_net_desc &net, const b2rl_layer &l, const f
 
 static int backward_pass(const b2rl_net_desc &net, const float *params, const float *weff, bool use_noise,
                          const float *eps, PassBufs &pb, int64_t row_off, int64_t B, const ObsChunk &obs, float *grads,
-                         float *gweff, int accumulate, const Scratch &sc, cudaStream_t s) {
+                         float *gweff, int accumulate, const Scratch &sc, cudaStream_t s,
+                         const WgradSide *side = nullptr) {
     const LayerBuf &lat = pb.enc[net.n_enc - 1];
     const float *latent = lat.a + row_off * layer_out_elems(net.enc[net.n_enc - 1]);
     float *g_latent = lat.g;
@@ -969,7 +998,7 @@ static int backward_pass(const b2rl_net_desc &net, const float *params, const fl
             h.dlnw = h.dlnb = h.lnpart = nullptr;
             if (l.ln == B2RL_LN_AFFINE) {
                 h.dlnw = grads + l.lnw_off; h.dlnb = grads + l.lnb_off;
-                h.lnpart = sc.partial + part_used;
+                h.lnpart = (side ? side->sc.partial : sc.partial) + part_used;
                 part_used += (size_t)n_tiles * 2 * l.out_c;
                 hd.ln_layer[hd.n_ln++] = slot;
             }
@@ -986,7 +1015,7 @@ static int backward_pass(const b2rl_net_desc &net, const float *params, const fl
         hd.maxdim = maxdim;
         const size_t smem = sizeof(float) * ((size_t)(3 + kHeadThreads / 32) * kHeadRows * head_pitch(maxdim) +
                                              (size_t)kHeadRows * hd.latent + (kHeadThreads / 32) * kHeadRows);
-        if (ok && smem <= 160 * 1024 && part_used <= sc.floats && maxdim <= kHeadWgMaxIn) {
+        if (ok && smem <= 160 * 1024 && part_used <= (side ? side->sc.floats : sc.floats) && maxdim <= kHeadWgMaxIn) {
             static bool attr_set = false;
             if (!attr_set) {
                 B2RL_CUDA(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -996,7 +1025,13 @@ static int backward_pass(const b2rl_net_desc &net, const float *params, const fl
             }
             head_bwd_kernel<<<n_tiles, kHeadThreads, smem, s>>>(hd, B);
             B2RL_LAUNCH_CHECK();
-            head_wgrad_kernel<<<ctas + hd.n_ln, kHeadThreads, kHeadWgSmemFloats * sizeof(float), s>>>(hd, B, n_tiles);
+            cudaStream_t sw = s;
+            if (side) {
+                int rcf = fork_to(side, s);
+                if (rcf != B2RL_OK) return rcf;
+                sw = side->s;
+            }
+            head_wgrad_kernel<<<ctas + hd.n_ln, kHeadThreads, kHeadWgSmemFloats * sizeof(float), sw>>>(hd, B, n_tiles);
             B2RL_LAUNCH_CHECK();
             head_done = true;
         }
@@ -1011,7 +1046,7 @@ static int backward_pass(const b2rl_net_desc &net, const float *params, const fl
             float *g_in = i == 0 ? g_latent : bufs[i - 1].g;
             const bool acc_gin = (i == 0 && head == 1);
             int rc = layer_backward(net, l, eff_w(l, params, weff, use_noise), params, x_in, nullptr, bufs[i], row_off,
-                                    bufs[i].g, g_in, acc_gin, grads, gweff, accumulate, B, sc, s);
+                                    bufs[i].g, g_in, acc_gin, grads, gweff, accumulate, B, sc, s, nullptr);
             if (rc != B2RL_OK) return rc;
         }
     }
@@ -1021,8 +1056,12 @@ static int backward_pass(const b2rl_net_desc &net, const float *params, const fl
         const float *x_in = i == 0 ? nullptr : pb.enc[i - 1].a + row_off * layer_out_elems(net.enc[i - 1]);
         float *g_in = i == 0 ? nullptr : pb.enc[i - 1].g;
         int rc = layer_backward(net, l, eff_w(l, params, weff, use_noise), params, x_in, i == 0 ? &obs : nullptr,
-                                pb.enc[i], row_off, pb.enc[i].g, g_in, false, grads, gweff, accumulate, B, sc, s);
+                                pb.enc[i], row_off, pb.enc[i].g, g_in, false, grads, gweff, accumulate, B, sc, s, side);
         if (rc != B2RL_OK) return rc;
+    }
+    if (side) {                                           // every weight gradient must have landed before the tail
+        B2RL_CUDA(cudaEventRecord(side->ev, side->s));
+        B2RL_CUDA(cudaStreamWaitEvent(s, side->ev, 0));
     }
     // noisy layers: grad_mu = grad_Weff, grad_sigma = grad_Weff * eps (autograd of mu + sigma*eps)
     SegTable tm, tsg;
@@ -1220,7 +1259,8 @@ static int rainbow_loss(const b2rl_net_desc &net, const b2rl_learn_cfg &cfg, con
     }
     Scratch sc{ws.partial, ws.partial_floats};
     // target network on next_obs (forward #2) on a side stream, concurrently with the online pass
-    static const bool fork_on = !(getenv("B2RL_NO_FORK") && getenv("B2RL_NO_FORK")[0] == '1');
+    static const bool fork_env = !(getenv("B2RL_NO_FORK") && getenv("B2RL_NO_FORK")[0] == '1');
+    const bool fork_on = fork_env && (cfg.side_streams & 1);
     ForkJoin *fj = nullptr;
     cudaStream_t st = s;
     if (fork_on) {
@@ -1385,9 +1425,19 @@ int b2rl_rainbow_backward(const b2rl_net_desc *net_host, const b2rl_learn_cfg *c
     if (rc != B2RL_OK) return rc;
     Scratch sc{ws.partial, ws.partial_floats};
     ObsChunk obs{bufs_host->obs, bufs_host->row_idx, cfg_host->batch};
+    static const bool fork_env = !(getenv("B2RL_NO_FORK") && getenv("B2RL_NO_FORK")[0] == '1');
+    const bool fork_on = fork_env && (cfg_host->side_streams & 2);
+    WgradSide side_storage;
+    const WgradSide *side = nullptr;
+    if (fork_on) {
+        ForkJoin *fj = nullptr;
+        if ((rc = fork_join(&fj)) != B2RL_OK) return rc;
+        side_storage = WgradSide{fj->side_bw, Scratch{ws.partial_bw, ws.partial_bw_floats}, fj->bw};
+        side = &side_storage;
+    }
     return backward_pass(*net_host, bufs_host->actor_params, ws.weff_actor, cfg_host->use_noise != 0,
                          bufs_host->actor_eps, ws.online, cfg_host->batch, cfg_host->batch, obs, bufs_host->grads,
-                         ws.gweff, cfg_host->accumulate, sc, as_stream(stream));
+                         ws.gweff, cfg_host->accumulate, sc, as_stream(stream), side);
 }
 
 int b2rl_optim_step(const b2rl_net_desc *net_host, const b2rl_learn_cfg *cfg_host, const b2rl_learn_bufs *bufs_host,

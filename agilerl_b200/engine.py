@@ -48,6 +48,11 @@ class NetBuffers:
         self.eps.copy_(other.eps)
 
 
+import os as _os
+
+_SIDE = int(_os.environ["B2RL_SIDE_STREAMS"]) if "B2RL_SIDE_STREAMS" in _os.environ else None
+
+
 class LearnEngine:
     def __init__(self, layout: FlatLayout, actor: NetBuffers, target: NetBuffers):
         self.layout, self.actor, self.target = layout, actor, target
@@ -141,7 +146,8 @@ class LearnEngine:
 
     # -- learn ---------------------------------------------------------------------------------
     def _cfg(self, B, *, gamma, v_min=0.0, v_max=0.0, delta_z=1.0, weights_mode=0, driver_shapes=0, double=0,
-             clip=1, lr=1e-4, tau=1e-3, prior_eps=1e-6, accumulate=0, use_noise=1, step=1) -> _lib.LearnCfg:
+             clip=1, lr=1e-4, tau=1e-3, prior_eps=1e-6, accumulate=0, use_noise=1, step=1,
+             side_streams=0) -> _lib.LearnCfg:
         c = _lib.LearnCfg()
         c.batch = B
         c.gamma, c.v_min, c.v_max, c.delta_z = float(gamma), float(v_min), float(v_max), float(delta_z)
@@ -152,6 +158,7 @@ class LearnEngine:
         c.bias_correction2 = 1.0 - 0.999 ** step
         c.tau, c.prior_eps = float(tau), float(prior_eps)
         c.accumulate, c.use_noise = accumulate, use_noise
+        c.side_streams = side_streams      # bit 0: target forward, bit 1: weight gradients on library side streams
         return c
 
     def _bufs(self, B, batch: dict, weights, support, loss_elem, priorities, loss_scalar, proj, row_idx=None):
@@ -186,7 +193,7 @@ class LearnEngine:
 
     def rainbow_learn(self, passes: list, *, B: int, support: torch.Tensor, weights, weights_mode: int, hp: dict,
                       noise_normals=None, want_proj: bool = False, row_idx=None, overlap: bool = False,
-                      after_loss=None):
+                      after_loss=None, side_streams: int | None = None):
         """``passes`` = [(batch, gamma, driver_shapes)], one per ``_dqn_loss`` call of the reference
         (1-step and/or n-step; two entries when combined_reward).  Returns device tensors
         (loss_scalar[1], loss_elem[B], priorities[B], proj).
@@ -205,11 +212,18 @@ class LearnEngine:
         keepalive = []
         za, zt = noise_normals if noise_normals is not None else (None, None)
         overlap = overlap and len(passes) == 1
+        # the target forward always forks; the weight gradients fork when the agent's tail is not already
+        # running under other agents' work (then the extra streams only add contention)
+        if _SIDE is not None:
+            side_streams = _SIDE
+        elif side_streams is None:
+            side_streams = 1 if overlap else 3
         cfg = bufs = None
         for i, (batch, gamma, driver) in enumerate(passes):
             cfg = self._cfg(B, gamma=gamma, v_min=hp["v_min"], v_max=hp["v_max"], delta_z=hp["delta_z"],
                             weights_mode=weights_mode, driver_shapes=int(driver), clip=1, lr=hp["lr"], tau=hp["tau"],
-                            prior_eps=hp["prior_eps"], accumulate=int(i > 0), use_noise=1, step=self.step)
+                            prior_eps=hp["prior_eps"], accumulate=int(i > 0), use_noise=1, step=self.step,
+                            side_streams=side_streams)
             bufs, keep = self._bufs(B, batch, weights, support, loss_elem, priorities, loss_scalar, proj, row_idx)
             keepalive.append(keep)
             _lib.check(self.lib.b2rl_rainbow_loss(desc, ctypes.byref(cfg), ctypes.byref(bufs), _lib.stream_ptr(self.device)))
@@ -262,7 +276,7 @@ class LearnEngine:
     # -- fused HBM-resident step ---------------------------------------------------------------
     def rainbow_fused_step(self, per, n_step_memory, *, B: int, beta: float, support: torch.Tensor, hp: dict,
                            gamma_n: float, weights_mode: int = 1, uniforms=None, noise_normals=None,
-                           overlap: bool = False):
+                           overlap: bool = False, side_streams: int | None = None):
         """One gradient step with the replay resident in HBM and no host round trip:
         sample (tree descent + IS weights + n-step scalars, one kernel) -> learn with the encoder
         reading frames from the ring through the sampled indices -> priorities written back into
@@ -278,6 +292,6 @@ class LearnEngine:
         batch = dict(obs=f[("obs",)], next_obs=f[(n_step_memory.ns_key,)], action=a, reward=r, done=d)
         loss, loss_elem, pri, _ = self.rainbow_learn([(batch, gamma_n, False)], B=B, support=support, weights=w,
                                                      weights_mode=weights_mode, hp=hp, noise_normals=noise_normals,
-                                                     row_idx=idx, overlap=overlap,
+                                                     row_idx=idx, overlap=overlap, side_streams=side_streams,
                                                      after_loss=lambda p: per.update_priorities_device(idx, p))
         return loss, idx, pri

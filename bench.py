@@ -32,7 +32,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # --- workload constants ------------------------------------------------
-POP = 8
+POP = int(os.environ.get("B2RL_BENCH_POP", "8"))   # BASELINE configs[1]: pop=8 (override only for experiments)
 B = 256
 OBS = (4, 84, 84)
 N_ACT = 6

@@ -213,6 +213,11 @@ typedef struct b2rl_learn_cfg {
     int32_t accumulate;                 /* 1: second pass of combined_reward — add this pass's
                                            per-sample loss / gradients to the first pass's */
     int32_t use_noise;                  /* NoisyLinear in train mode (always 1 in learn) */
+    int32_t side_streams;               /* 1: b2rl_rainbow_loss may run the target forward, and
+                                           b2rl_rainbow_backward the weight gradients, on library-owned
+                                           side streams (joined before the call's work is complete in the
+                                           caller's stream order); 0: everything on `stream` */
+    int32_t reserved_;
 } b2rl_learn_cfg;
 
 /* Device buffers of one learn step (all fp32 unless stated). */
