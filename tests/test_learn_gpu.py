@@ -263,3 +263,72 @@ def test_northstar_b16_golden():
         ref = oa.actor[k].grad
         s = max(ref.abs().max().item(), 1e-6)
         assert (gv.view(k).cpu() - ref).abs().max().item() <= 5e-5 * s + 1e-8, f"grad {k}"
+
+
+def _random_state(layout, gen):
+    sd = {}
+    for k, e in layout.entries.items():
+        fan = e.shape[-1] if len(e.shape) > 1 else e.shape[0]
+        if "norm" in k and k.endswith("weight"):
+            sd[k] = torch.ones(e.shape) + 0.1 * torch.randn(e.shape, generator=gen)
+        elif "epsilon" in k:
+            sd[k] = torch.randn(e.shape, generator=gen) * 0.5
+        elif "conv" in k and k.endswith("weight"):
+            sd[k] = torch.randn(e.shape, generator=gen) * (1.0 / (e.shape[1] * e.shape[2] * e.shape[3]) ** 0.5)
+        else:
+            sd[k] = torch.randn(e.shape, generator=gen) * (0.5 / fan ** 0.5)
+    return sd
+
+
+@pytest.mark.parametrize("name,obs,chan,kern,stride,u8", [
+    ("k5s2_then_k3s1_odd", (3, 21, 21), (8, 12), (5, 3), (2, 1), True),         # k % s != 0, odd planes, T=3/S=1 dgrad
+    ("three_layers_k5s2_dgrad", (2, 30, 30), (16, 24, 8), (4, 5, 3), (2, 2, 1), True),   # zero-padded parity taps
+    ("wide_f32_cin40", (4, 16, 16), (40, 8), (3, 3), (1, 2), False),           # Cout 40 -> n_pad 48; k3 s2 dgrad over Cin 40
+    ("k2s2_k1s1", (1, 12, 12), (4, 4), (2, 1), (2, 1), True),                  # 1x1 kernel, single-tap classes
+])
+def test_conv_geometry_sweep_matches_oracle(name, obs, chan, kern, stride, u8):
+    """Forward, weight-gradient and input-gradient tensor-core kernels on geometries away from the
+    north-star net (kernel not a multiple of the stride, odd planes, three conv layers, wide layers,
+    float observations): loss / priorities within 1e-5, every gradient tensor within 2e-5 max|g|."""
+    from oracle import learn as olearn, nets as onets
+    from agilerl_b200.engine import LearnEngine, NetBuffers
+    from agilerl_b200.networks.spec import FlatLayout, rainbow_spec
+    B, A = 8, 3
+    lo, hi = (0.0, 255.0) if u8 else (None, None)
+    spec = rainbow_spec(obs, A, channel_size=chan, kernel_size=kern, stride_size=stride, latent_dim=16,
+                        hidden_size=(24,), obs_low=lo, obs_high=hi, obs_u8=u8)
+    ospec = onets.rainbow_spec(obs, A, channel_size=chan, kernel_size=kern, stride_size=stride, latent_dim=16,
+                               hidden_size=(24,), obs_low=lo, obs_high=hi)
+    layout = FlatLayout(spec)
+    gen = torch.Generator().manual_seed(sum(map(ord, name)))
+    sd_a = _random_state(layout, gen)
+    sd_t = {k: v + 0.01 * torch.randn(v.shape, generator=gen) for k, v in sd_a.items()}
+    actor, target = NetBuffers(layout, "cuda"), NetBuffers(layout, "cuda")
+    actor.load_state_dict(sd_a); target.load_state_dict(sd_t)
+    eng = LearnEngine(layout, actor, target)
+
+    def frames():
+        if u8:
+            return torch.randint(0, 256, (B, *obs), dtype=torch.uint8, generator=gen)
+        return torch.randn((B, *obs), generator=gen)
+    nexp = dict(obs=frames(), action=torch.randint(0, A, (B,), generator=gen).float(),
+                reward=torch.randn(B, 1, generator=gen), next_obs=frames(),
+                done=(torch.rand(B, 1, generator=gen) < 0.2).float())
+    exp = dict(nexp, weights=torch.rand(B, generator=gen) + 0.5, idxs=torch.arange(B))
+    oa = olearn.OracleAgent(ospec, sd_a, sd_t, batch_size=B, lr=1e-4)
+    z = (torch.randn(eng.noise_count, generator=gen), torch.randn(eng.noise_count, generator=gen))
+    oloss, _, opri = oa.learn_rainbow(exp, nexp, per=True, noise_normals=z)
+    hp = dict(v_min=-10.0, v_max=10.0, delta_z=20.0 / 50, lr=1e-4, tau=1e-3, prior_eps=1e-6)
+    loss, _, pri, _ = eng.rainbow_learn([({k: v.cuda() for k, v in nexp.items()}, 0.99 ** 3, False)], B=B,
+                                        support=torch.linspace(-10.0, 10.0, 51).cuda(), weights=exp["weights"].cuda(),
+                                        weights_mode=1, hp=hp, noise_normals=z)
+    torch.cuda.synchronize()
+    assert abs(loss.item() - oloss) <= 1e-5 * max(1.0, abs(oloss)), (loss.item(), oloss)
+    np.testing.assert_allclose(pri.cpu().numpy(), np.asarray(opri).reshape(-1), rtol=1e-5, atol=1e-5)
+    total = torch.sqrt(sum((g.double() ** 2).sum() for g in oa.last_grads.values())).item()
+    assert total < 10.0, "test weights must stay below the clip threshold"
+    gv = NetBuffers(layout, "cuda"); gv.params.copy_(eng.grads)
+    for k, ref in oa.last_grads.items():
+        got = gv.view(k).cpu()
+        scale = max(ref.abs().max().item(), 1e-6)
+        assert (got - ref).abs().max().item() <= 2e-5 * scale + 1e-8, f"grad {k}: {(got - ref).abs().max().item()} vs {scale}"
