@@ -43,6 +43,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "r"(parity), "r"(0x989680u)
         : "memory");
 }
+// one lane of a converged warp (the CUTLASS elect_one_sync idiom): code under `if (elect_one())` keeps
+// its operands in uniform registers, which is what the tcgen05 / bulk-copy instructions take
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -163,9 +176,9 @@ struct ConvTcParams {
     int64_t w_class_stride;     // floats between the pre-split weights of consecutive classes
 };
 
-static inline size_t conv_tc_smem_bytes(int n_pad, int k_pad, int a_parts = 2, int a_stages = 2) {
+static inline size_t conv_tc_smem_bytes(int n_pad, int k_pad, int a_parts = 2, int a_stages = 2, int b_stages = kTcBStages) {
     const size_t a = (size_t)kTcBM * kTcBK * 4, b = (size_t)n_pad * kTcBK * 4;
-    return a_stages * a_parts * a + kTcBStages * 2 * b + (size_t)k_pad * 4 + 256 * 4 + (size_t)n_pad * 4 + 192 + 1024;
+    return a_stages * a_parts * a + b_stages * 2 * b + (size_t)k_pad * 4 + 256 * 4 + (size_t)n_pad * 4 + 192 + 1024;
 }
 
 // Split W [N, K] into tf32 hi / lo and store it in the order the conv kernel's B tiles use:
@@ -208,7 +221,9 @@ __device__ __noinline__ float act_fwd_slow(int act, float v) { return act_fwd(ac
 // accumulator in the epilogue (one true division per output).  vs. the reference's
 // fl((x-low)/(high-low)) * w summed in fp32 the difference is <= 2^-23 relative per term.
 // VEC: 4 consecutive taps are contiguous and aligned (4 packed bytes / two 8-byte fp32 loads).
-template <int ELEM, bool EXACT_A, bool VEC, int D, bool PAD = false, int SA = 2>
+// SB: slots of the weight-tile ring; tiles are requested SB-2 k-blocks ahead (a bulk copy takes on the
+// order of a microsecond to land — more than one k-block of work)
+template <int ELEM, bool EXACT_A, bool VEC, int D, bool PAD = false, int SA = 2, int SB = kTcBStages>
 __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const ConvTcParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     constexpr int RAWN = (ELEM == EL_U8 && VEC) ? 4 : 16;      // raw words per thread per k-block
@@ -225,15 +240,15 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const Conv
     const uint32_t bbase = sbase + SA * a_stage;
     auto b_hi = [&](int s) { return bbase + (uint32_t)s * 2 * b_bytes; };
     auto b_lo = [&](int s) { return bbase + (uint32_t)s * 2 * b_bytes + b_bytes; };
-    const uint32_t koff_a = bbase + kTcBStages * 2 * b_bytes;
+    const uint32_t koff_a = bbase + SB * 2 * b_bytes;
     const uint32_t lut_a = koff_a + (uint32_t)p.k_pad * 4;
     const uint32_t bias_a = lut_a + 256 * 4;
     const uint32_t bars_a = (bias_a + (uint32_t)p.n_pad * 4 + 15u) & ~15u;
-    const uint32_t tptr_a = bars_a + 8 * (2 * SA + kTcBStages);
+    const uint32_t tptr_a = bars_a + 8 * (2 * SA + SB);
     uint8_t *gen = smem_raw + (sbase - tc::smem_u32(smem_raw));        // generic alias of sbase (barriers only)
     uint64_t *mma_bar = reinterpret_cast<uint64_t *>(gen + (bars_a - sbase));   // [SA] MMA group done
     uint64_t *full_a = mma_bar + SA;                                     // [SA] im2col tile written
-    uint64_t *full_b = full_a + SA;                                      // [kTcBStages] weight tile landed
+    uint64_t *full_b = full_a + SA;                                      // [SB] weight tile landed
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(gen + (tptr_a - sbase));
     const int KB = p.k_pad / kTcBK;
 
@@ -243,13 +258,13 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const Conv
             tc::mbar_init(&mma_bar[s], 1);
             tc::mbar_init(&full_a[s], kTcThreads / 32);      // one elected arrive per producer warp
         }
-        for (int s = 0; s < kTcBStages; ++s) tc::mbar_init(&full_b[s], 1);
+        for (int s = 0; s < SB; ++s) tc::mbar_init(&full_b[s], 1);
         tc::fence_barrier_init();
     }
     // MMA group j (k-block j) has retired: its A stage and its B ring slot may be overwritten
     auto wait_mma = [&](int j) { tc::mbar_wait(&mma_bar[j % SA], (uint32_t)((j / SA) & 1)); };
     auto issue_b = [&](int kb) {       // elected thread: weight tile of k-block kb -> its ring slot
-        const int sb = kb & (kTcBStages - 1);
+        const int sb = kb & (SB - 1);
         tc::mbar_expect_tx(&full_b[sb], 2 * b_bytes);
         const int64_t wo = (PAD ? (int64_t)blockIdx.y * p.w_class_stride : 0) + (int64_t)kb * p.n_pad * kTcBK;
         tc::bulk_g2s(b_hi(sb), p.w_hi + wo, b_bytes, &full_b[sb]);
@@ -277,23 +292,27 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const Conv
     const uint32_t lbo_a = kTcBM * 16, lbo_b = (uint32_t)p.n_pad * 16;
 
     if (warp == kTcThreads / 32) {
-        // ---- MMA warp: one lane feeds the tensor core; nothing else sits on its issue path ------------
-        if ((tid & 31) == 0) {
-            issue_b(0);
-            if (KB > 1) issue_b(1);
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % SA, sb = kb & (kTcBStages - 1);
-                if (kb + 2 < KB) {
-                    if (kb >= 2) wait_mma(kb - 2);          // B ring slot (kb+2)%4 was last read by MMA group kb-2
-                    issue_b(kb + 2);
-                }
-                tc::mbar_wait(&full_b[sb], (uint32_t)((kb / kTcBStages) & 1));
-                tc::mbar_wait(&full_a[s], (uint32_t)((kb / SA) & 1));
-                tc::tc_fence_after();
-                // descriptors of consecutive k-steps differ only in the 14-bit start-address field
-                const uint64_t dah0 = tc::make_desc(a_hi(s), lbo_a, 128), dal0 = tc::make_desc(a_lo(s), lbo_a, 128);
-                const uint64_t dbh0 = tc::make_desc(b_hi(sb), lbo_b, 128), dbl0 = tc::make_desc(b_lo(sb), lbo_b, 128);
-                const uint64_t da_step = (uint64_t)((2 * lbo_a) >> 4), db_step = (uint64_t)((2 * lbo_b) >> 4);
+        // ---- MMA warp.  The whole warp runs the loop converged (waits, descriptor arithmetic stay in the
+        // uniform datapath); one elected lane issues the copies, the MMAs and the commit.
+        if (tc::elect_one()) {
+            for (int j = 0; j < SB - 2 && j < KB; ++j) issue_b(j);
+        }
+        __syncwarp();
+        const uint64_t da_step = (uint64_t)((2 * lbo_a) >> 4), db_step = (uint64_t)((2 * lbo_b) >> 4);
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb % SA, sb = kb & (SB - 1);
+            if (kb + SB - 2 < KB) {
+                if (kb >= 2) wait_mma(kb - 2);          // ring slot (kb+SB-2)%SB was last read by MMA group kb-2
+                if (tc::elect_one()) issue_b(kb + SB - 2);
+                __syncwarp();
+            }
+            tc::mbar_wait(&full_b[sb], (uint32_t)((kb / SB) & 1));
+            tc::mbar_wait(&full_a[s], (uint32_t)((kb / SA) & 1));
+            tc::tc_fence_after();
+            // descriptors of consecutive k-steps differ only in the 14-bit start-address field
+            const uint64_t dah0 = tc::make_desc(a_hi(s), lbo_a, 128), dal0 = tc::make_desc(a_lo(s), lbo_a, 128);
+            const uint64_t dbh0 = tc::make_desc(b_hi(sb), lbo_b, 128), dbl0 = tc::make_desc(b_lo(sb), lbo_b, 128);
+            if (tc::elect_one()) {
 #pragma unroll
                 for (int j = 0; j < kTcBK / 8; ++j) {      // one MMA k-step = 8 tf32 = 2 core-matrix columns
                     tc::mma_tf32(tmem_d, dah0 + j * da_step, dbh0 + j * db_step, idesc, (kb | j) ? 1u : 0u);
@@ -302,8 +321,8 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const Conv
                 }
                 tc::mma_commit(&mma_bar[s]);
             }
+            __syncwarp();
         }
-        __syncwarp();
     }
 
     if (warp < kTcThreads / 32) {
@@ -475,6 +494,24 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const Conv
     if (warp == 0) tc::tmem_dealloc(tmem_d, tmem_cols);
 }
 
+}  // namespace b2rl
+#include "conv_tc_persist.cuh"
+namespace b2rl {
+
+// B2RL_TC_PERSIST=1 selects the persistent kernels of conv_tc_persist.cuh.  Measured on B200 (r1):
+// they tie with the one-tile-per-CTA kernels on a quiet GPU (conv1 forward 24 us both) and lose a few
+// percent when other streams share the SMs (fewer, longer-lived CTAs), so they are off by default.
+// Likewise B2RL_TC_SA=3 (three A stages) and B2RL_TC_SB=8 (weight tiles six k-blocks ahead) trade
+// residency (3 -> 2 CTAs per SM) for pipeline depth and measured slower.
+static bool tc_persist_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("B2RL_TC_PERSIST");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+
 static inline size_t conv_tc_wsplit_floats(const b2rl_layer &l) {
     const int K = l.in_c * l.ksize * l.ksize;
     const int n_pad = (l.out_c + 15) / 16 * 16, k_pad = (K + kTcBK - 1) / kTcBK * kTcBK;
@@ -490,8 +527,10 @@ static int launch_conv_fwd_tc(const b2rl_layer &l, const Operand &A, const float
     if (n_pad > 256 || k_pad > 8192 || rows * (int64_t)P > INT32_MAX) return 1;
     const bool exact = A.u8 && (!A.normalize || (A.low == floorf(A.low) && fabsf(A.low) <= 1024.f));
     static const int sa_exact = getenv("B2RL_TC_SA") ? atoi(getenv("B2RL_TC_SA")) : 2;
+    static const int sb_exact = getenv("B2RL_TC_SB") ? atoi(getenv("B2RL_TC_SB")) : 4;
     const bool deep = exact && sa_exact == 3;
-    const size_t smem = conv_tc_smem_bytes(n_pad, k_pad, exact ? 1 : 2, deep ? 3 : 2);
+    const bool wide_b = exact && !deep && sb_exact == 8 && k_pad / kTcBK > 4;
+    const size_t smem = conv_tc_smem_bytes(n_pad, k_pad, exact ? 1 : 2, deep ? 3 : 2, wide_b ? 8 : kTcBStages);
     if (smem > 200 * 1024 || wsplit == nullptr || conv_tc_wsplit_floats(l) > wsplit_cap) return 1;
     if (reinterpret_cast<uintptr_t>(wsplit) % 16 != 0) return 1;          // bulk copies need 16-byte aligned sources
     float *w_hi = wsplit, *w_lo = wsplit + (size_t)n_pad * k_pad;
@@ -526,9 +565,29 @@ static int launch_conv_fwd_tc(const b2rl_layer &l, const Operand &A, const float
         B2RL_LAUNCH_CHECK();
         return B2RL_OK;
     };
+    if (tc_persist_enabled()) {
+        static const int sa_p = getenv("B2RL_TC_PSA") ? atoi(getenv("B2RL_TC_PSA")) : 4;
+        const size_t smem_p = conv_tc_persist_smem_bytes(n_pad, k_pad, exact ? 1 : 2, 2);
+        int rcp = 1;
+        if (A.elem_kind() == EL_U8 && exact && vec) {
+            if (sa_p == 8)
+                rcp = launch_conv_persist(conv_fwd_tc_persist_kernel<EL_U8, true, true, 8, false, 8>, p, 1,
+                                          conv_tc_persist_smem_bytes(n_pad, k_pad, 1, 8), s);
+            else if (sa_p == 4)
+                rcp = launch_conv_persist(conv_fwd_tc_persist_kernel<EL_U8, true, true, 8, false, 4>, p, 1,
+                                          conv_tc_persist_smem_bytes(n_pad, k_pad, 1, 4), s);
+            else
+                rcp = launch_conv_persist(conv_fwd_tc_persist_kernel<EL_U8, true, true, 8, false, 2>, p, 1, smem_p, s);
+        }
+        else if (A.elem_kind() == EL_F32 && vec)
+            rcp = launch_conv_persist(conv_fwd_tc_persist_kernel<EL_F32, false, true, 2, false, 2>, p, 1, smem_p, s);
+        if (rcp != 1) return rcp;
+    }
     switch (A.elem_kind()) {
         case EL_U8:
             if (exact && vec && deep) return launch(conv_fwd_tc_kernel<EL_U8, true, true, 8, false, 3>);
+            if (exact && vec && wide_b) return launch(conv_fwd_tc_kernel<EL_U8, true, true, 8, false, 2, 8>);
+            if (exact && wide_b) return launch(conv_fwd_tc_kernel<EL_U8, true, false, 2, false, 2, 8>);
             if (exact) return vec ? launch(conv_fwd_tc_kernel<EL_U8, true, true, 8>) : launch(conv_fwd_tc_kernel<EL_U8, true, false, 2>);
             return vec ? launch(conv_fwd_tc_kernel<EL_U8, false, true, 8>) : launch(conv_fwd_tc_kernel<EL_U8, false, false, 2>);
         case EL_F32_NORM:
@@ -611,6 +670,11 @@ static int launch_conv_dgrad_tc(const b2rl_layer &l, const float *g, const float
     p.act = B2RL_ACT_NONE; p.normalize = 0; p.low = 0.f; p.high = 1.f;
     p.pad = T - 1; p.IH = l.out_h; p.cls_s = S; p.out_H = l.in_h; p.out_W = l.in_w;
     p.w_class_stride = (int64_t)cls_floats;
+    if (tc_persist_enabled()) {
+        const int rcp = launch_conv_persist(conv_fwd_tc_persist_kernel<EL_F32, false, false, 2, true, 2>, p, S * S,
+                                            conv_tc_persist_smem_bytes(n_pad, k_pad, 2, 2), s);
+        if (rcp != 1) return rcp;
+    }
     auto kern = conv_fwd_tc_kernel<EL_F32, false, false, 2, true>;
     B2RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3((unsigned)((p.M + kTcBM - 1) / kTcBM), S * S), kTcThreads + 32, smem, s>>>(p);
@@ -720,15 +784,15 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_wgrad_tc_kernel(const Co
     const uint32_t lbo_b = (uint32_t)p.n_pad * 16;
 
     if (warp == kTcThreads / 32) {
-        // ---- MMA warp ---------------------------------------------------------------------------------
-        if ((tid & 31) == 0) {
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb & (kTcStages - 1);
-                tc::mbar_wait(&full[s], (uint32_t)((kb / kTcStages) & 1));
-                tc::tc_fence_after();
-                const uint64_t dah0 = tc::make_desc(a_hi(s), kWgLboA, 128), dal0 = tc::make_desc(a_lo(s), kWgLboA, 128);
-                const uint64_t dbh0 = tc::make_desc(b_hi(s), lbo_b, 128), dbl0 = tc::make_desc(b_lo(s), lbo_b, 128);
-                const uint64_t da_step = (uint64_t)((2 * kWgLboA) >> 4), db_step = (uint64_t)((2 * lbo_b) >> 4);
+        // ---- MMA warp (converged loop, one elected lane issues) ------------------------------------------
+        const uint64_t da_step = (uint64_t)((2 * kWgLboA) >> 4), db_step = (uint64_t)((2 * lbo_b) >> 4);
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb & (kTcStages - 1);
+            tc::mbar_wait(&full[s], (uint32_t)((kb / kTcStages) & 1));
+            tc::tc_fence_after();
+            const uint64_t dah0 = tc::make_desc(a_hi(s), kWgLboA, 128), dal0 = tc::make_desc(a_lo(s), kWgLboA, 128);
+            const uint64_t dbh0 = tc::make_desc(b_hi(s), lbo_b, 128), dbl0 = tc::make_desc(b_lo(s), lbo_b, 128);
+            if (tc::elect_one()) {
 #pragma unroll
                 for (int j = 0; j < kTcBK / 8; ++j) {                   // 8 pixels per MMA
                     tc::mma_tf32(tmem_d, dah0 + j * da_step, dbh0 + j * db_step, idesc, (kb | j) ? 1u : 0u);
@@ -737,8 +801,8 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_wgrad_tc_kernel(const Co
                 }
                 tc::mma_commit(&mma_bar[s]);
             }
+            __syncwarp();
         }
-        __syncwarp();
     } else {
         // ---- producer warps ---------------------------------------------------------------------------
         const int64_t safe_base = p.gather ? p.gather[0] * p.in_bstride : 0;
