@@ -1123,16 +1123,17 @@ __global__ void adam_polyak_kernel(float *__restrict__ p, float *__restrict__ g,
                                    float *__restrict__ v, float *__restrict__ tgt, int64_t n,
                                    const float *__restrict__ partials, int nparts, AdamCfg c) {
     __shared__ float coef_s;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {                                 // every block combines the partial norms in the same order
         float coef = 1.f;
         if (c.clip) {
             float tot = 0.f;
-            for (int i = 0; i < nparts; ++i) tot += partials[i];
+            for (int i = threadIdx.x; i < nparts; i += 32) tot += partials[i];
+            tot = warp_sum(tot);
             const float total_norm = sqrtf(tot);
             coef = c.max_norm / (total_norm + 1e-6f);      // clip_grad_norm_: clamp(coef, max=1)
             coef = coef > 1.f ? 1.f : coef;
         }
-        coef_s = coef;
+        if (threadIdx.x == 0) coef_s = coef;
     }
     __syncthreads();
     const float coef = coef_s;

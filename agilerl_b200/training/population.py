@@ -31,7 +31,7 @@ def population_learn(pop, memory, n_step_memory, overlap: bool = True, join: boo
     join once at the end (``agent.synchronize()``)."""
     if not pop:
         return []
-    if not overlap or len(pop) == 1:      # nothing to overlap a lone agent's tail with: it forks internally instead
+    if not overlap:
         return [agent.learn_from_buffers(memory, n_step_memory) for agent in pop]
     device = pop[0]._dev
     cur = torch.cuda.current_stream(device)
@@ -39,6 +39,7 @@ def population_learn(pop, memory, n_step_memory, overlap: bool = True, join: boo
     hi.wait_stream(cur)
     with torch.cuda.stream(hi):
         # with few local agents the GPU still has room for each backward's weight gradients on a side stream
+        # (a lone agent still gains: its priority write-back runs beside its own backward)
         side = 3 if len(pop) <= 2 else 1
         losses = [agent.learn_from_buffers(memory, n_step_memory, overlap=True, side_streams=side) for agent in pop]
     cur.wait_stream(hi)
