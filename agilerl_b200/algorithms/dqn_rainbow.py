@@ -165,13 +165,12 @@ class RainbowDQN(RLAlgorithm):
             weights_mode = 2 if weights.ndim == 2 else 1          # quirk Q1
         elif n_step:
             idxs = experiences["idxs"]
-        if any(d for _, _, d in passes) and B > 1 and not per and False:
-            pass
-        loss, loss_elem, pri, _ = self.engine.rainbow_learn(passes, B=B, support=self.support, weights=weights,
-                                                            weights_mode=weights_mode, hp=self._hp(),
-                                                            noise_normals=noise_normals)
-        new_priorities = pri.cpu().numpy() if per else None       # elementwise_loss + prior_eps (:487-488)
-        return loss.item(), idxs, new_priorities
+        self.engine.rainbow_learn(passes, B=B, support=self.support, weights=weights, weights_mode=weights_mode,
+                                  hp=self._hp(), noise_normals=noise_normals, host_readback=True)
+        # loss and priorities were copied to the host before the backward was enqueued: this waits for the
+        # forward half of the step only; backward / optimiser keep running in stream order behind it
+        loss, pri = self.engine.readback()
+        return loss, idxs, (pri if per else None)                 # elementwise_loss + prior_eps (:487-488)
 
     def learn_from_buffers(self, memory, n_step_memory, overlap: bool = False, side_streams: int | None = None):
         """Fused HBM-resident gradient step (no host round trip): PER sample + learn + priority

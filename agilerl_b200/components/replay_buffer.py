@@ -58,6 +58,13 @@ def _unflatten(leaves: dict, batch_size) -> TensorDict:
     return build(root)
 
 
+def _shallow(td):
+    """New collection(s) around the same leaf tensors."""
+    if hasattr(td, "_map"):                      # compat stand-in
+        return td._map(lambda v: _shallow(v) if is_tensor_collection(v) else v)
+    return td.clone(False)                       # real tensordict: non-recursive clone shares the leaves
+
+
 def _as_collection(data) -> Any:
     if is_tensor_collection(data):
         return data
@@ -83,6 +90,7 @@ class ReplayBuffer:
         self._size = 0
         self._storage: TensorDict | None = None
         self._fields: dict[tuple, torch.Tensor] = {}
+        self._row_bytes: dict[tuple, int] = {}
         self._lib = _lib.load()
 
     # -- properties (replay_buffer.py:39-58) ---------------------------------------------------
@@ -113,12 +121,13 @@ class ReplayBuffer:
         for path, v in _leaf_items(data):
             if not isinstance(v, torch.Tensor):
                 v = torch.as_tensor(v)
-            v = v.to(self._dev, non_blocking=True)
+            if v.device != self._dev:
+                v = v.to(self._dev, non_blocking=True)
             if n is None:
                 n = v.shape[0]
             if v.ndim == 1:                       # :85-94 scalar leaves become (n, 1)
                 v = v.reshape(v.shape[0], 1)
-            leaves[path] = v.contiguous()
+            leaves[path] = v if v.is_contiguous() else v.contiguous()
         if n is None:
             raise ValueError("empty transition")
         return leaves, n
@@ -130,11 +139,15 @@ class ReplayBuffer:
             for path, v in leaves.items()
         }
         self._storage = _unflatten(self._fields, (self.max_size,))
+        self._row_bytes = {path: (t.numel() // self.max_size) * t.element_size() for path, t in self._fields.items()}
         self.initialized = True
 
     def add(self, data: DataType) -> None:
         """:72-112 — ring write with wrap-around split (b2rl_ring_write, one call per field)."""
         leaves, n = self._prepare(data)
+        self._add_leaves(leaves, n)
+
+    def _add_leaves(self, leaves: dict, n: int) -> None:
         if self._storage is None:
             self._init(leaves)
         if n > self.max_size:
@@ -144,8 +157,8 @@ class ReplayBuffer:
             dst = self._fields[path]
             if v.dtype != dst.dtype:
                 v = v.to(dst.dtype)
-            row_bytes = dst[0].numel() * dst.element_size()
-            assert v[0].numel() * v.element_size() == row_bytes, f"shape mismatch for {path}"
+            row_bytes = self._row_bytes[path]
+            assert v.numel() * v.element_size() == row_bytes * n, f"shape mismatch for {path}"
             _lib.check(self._lib.b2rl_ring_write(dst.data_ptr(), v.data_ptr(), row_bytes, self._cursor, n,
                                                  self.max_size, stream))
         self._cursor = (self._cursor + n) % self.max_size
@@ -155,16 +168,19 @@ class ReplayBuffer:
     # -- gather ---------------------------------------------------------------------------------
     def _gather(self, idx: torch.Tensor) -> TensorDict:
         """storage[idx] -> fresh tensors of shape idx.shape + feature shape (b2rl_gather_rows)."""
-        idx_dev = idx.to(self._dev, dtype=torch.int64, non_blocking=True).contiguous()
+        idx_dev = idx
+        if idx.device != self._dev or idx.dtype != torch.int64:
+            idx_dev = idx.to(self._dev, dtype=torch.int64, non_blocking=True)
+        if not idx_dev.is_contiguous():
+            idx_dev = idx_dev.contiguous()
         flat = idx_dev.reshape(-1)
         nrows = flat.numel()
         stream = _lib.stream_ptr(self._dev)
         out = {}
         for path, src in self._fields.items():
             dst = torch.empty((nrows, *src.shape[1:]), dtype=src.dtype, device=self._dev)
-            row_bytes = src[0].numel() * src.element_size()
-            _lib.check(self._lib.b2rl_gather_rows(dst.data_ptr(), src.data_ptr(), flat.data_ptr(), row_bytes,
-                                                  nrows, stream))
+            _lib.check(self._lib.b2rl_gather_rows(dst.data_ptr(), src.data_ptr(), flat.data_ptr(),
+                                                  self._row_bytes[path], nrows, stream))
             out[path] = dst.reshape(*idx_dev.shape, *src.shape[1:])
         return _unflatten(out, tuple(idx_dev.shape))
 
@@ -182,6 +198,7 @@ class ReplayBuffer:
         self._cursor = 0
         self._storage = None
         self._fields = {}
+        self._row_bytes = {}
         self.initialized = False
 
 
@@ -233,10 +250,11 @@ class MultiStepReplayBuffer(ReplayBuffer):
                 f"No done/termination key found in transition. Expected keys: {expected_keys}")
             self.done_key = done_key
 
-        out = first.clone()
         n = len(window)
         if n == 1:
-            return out
+            return first.clone()
+        # entries of `out` are replaced below, never written in place: share the untouched tensors
+        out = _shallow(first)
         stream = _lib.stream_ptr(self._dev)
         rewards = [w[self.reward_key].to(torch.float32).contiguous() for w in window]
         dones = [w[self.done_key].to(torch.float32).contiguous() for w in window]
@@ -311,7 +329,7 @@ class PrioritizedReplayBuffer(ReplayBuffer):
     def add(self, data: DataType) -> None:
         """:296-309 — ring write, then the n new leaves get max_priority**alpha."""
         leaves, n = self._prepare(data)
-        ReplayBuffer.add(self, _unflatten(leaves, (n,)))
+        self._add_leaves(leaves, n)
         p_alpha = float(self.max_priority) ** self.alpha
         _lib.check(self._lib.b2rl_tree_set_range(self.sum_tree.data_ptr, self.min_tree.data_ptr, self._cap,
                                                  self.tree_ptr, n, self.max_size, p_alpha,

@@ -67,6 +67,7 @@ class LearnEngine:
         self._noise_count = ctypes.c_int64(0)
         _lib.check(self.lib.b2rl_noise_count(ctypes.byref(layout.desc), ctypes.byref(self._noise_count)))
         self.philox_seed = 0xB200
+        self._host_out: dict = {}
         self.philox_offset = 0
 
     # -- scratch -------------------------------------------------------------------------------
@@ -76,6 +77,13 @@ class LearnEngine:
     # priority write-back): everything that reads or writes this engine's buffers first joins.
     _bwd_stream = None
     _opt_done = None
+    _readback = None
+
+    def readback(self):
+        """(loss: float, priorities: np.ndarray[B]) of the last ``rainbow_learn(host_readback=True)``."""
+        host, ev, B = self._readback
+        ev.synchronize()
+        return float(host[B]), host[:B].numpy().copy()
 
     def join(self) -> None:
         """Make the current stream wait for an overlapped backward/optimiser tail, if one is pending."""
@@ -193,7 +201,7 @@ class LearnEngine:
 
     def rainbow_learn(self, passes: list, *, B: int, support: torch.Tensor, weights, weights_mode: int, hp: dict,
                       noise_normals=None, want_proj: bool = False, row_idx=None, overlap: bool = False,
-                      after_loss=None, side_streams: int | None = None):
+                      after_loss=None, side_streams: int | None = None, host_readback: bool = False):
         """``passes`` = [(batch, gamma, driver_shapes)], one per ``_dqn_loss`` call of the reference
         (1-step and/or n-step; two entries when combined_reward).  Returns device tensors
         (loss_scalar[1], loss_elem[B], priorities[B], proj).
@@ -201,12 +209,16 @@ class LearnEngine:
         ``after_loss(priorities)`` (optional) is called once the loss / priorities of the last pass are
         enqueued — before the backward — so the caller can enqueue the tree write-back there.
         ``overlap`` (single pass only): backward + optimiser + noise reset go to the engine's own
-        stream; the caller's stream only carries sample, forward, loss and ``after_loss``."""
+        stream; the caller's stream only carries sample, forward, loss and ``after_loss``.
+        ``host_readback``: the scalar loss and the priorities are copied to pinned host memory as soon
+        as they exist — before the backward is enqueued — and ``readback()`` waits for that copy only,
+        so a caller that needs Python numbers (the reference's ``learn`` return value) does not wait
+        for the rest of the step."""
         self.join()
         desc = ctypes.byref(self.layout.desc)
         loss_elem = torch.empty(B, dtype=torch.float32, device=self.device)
-        priorities = torch.empty(B, dtype=torch.float32, device=self.device)
-        loss_scalar = torch.empty(1, dtype=torch.float32, device=self.device)
+        out = torch.empty(B + 1, dtype=torch.float32, device=self.device)     # priorities | scalar loss (one D2H)
+        priorities, loss_scalar = out[:B], out[B:]
         proj = torch.empty((B, self.layout.desc.n_atoms), dtype=torch.float32, device=self.device) if want_proj else None
         self.step += 1
         keepalive = []
@@ -230,8 +242,16 @@ class LearnEngine:
             if i + 1 < len(passes):
                 _lib.check(self.lib.b2rl_rainbow_backward(desc, ctypes.byref(cfg), ctypes.byref(bufs),
                                                           _lib.stream_ptr(self.device)))
-        keepalive.append([loss_elem, priorities, loss_scalar, proj, support, weights])
+        keepalive.append([loss_elem, out, proj, support, weights])
         self._keepalive = keepalive         # everything the tail reads stays allocated until the next join
+        if host_readback:
+            host = self._host_out.get(B)
+            if host is None:
+                host = self._host_out[B] = torch.empty(B + 1, dtype=torch.float32).pin_memory()
+            host.copy_(out, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self._readback = (host, ev, B)
 
         def tail():
             stream = _lib.stream_ptr(self.device)
