@@ -10,7 +10,9 @@ def main(path):
             'launch__occupancy_limit_registers', 'launch__waves_per_multiprocessor',
             'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
             'smsp__inst_executed.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
-            'launch__shared_mem_per_block_dynamic', 'lts__t_bytes.sum', 'sm__inst_executed_pipe_tensor.sum']
+            'launch__shared_mem_per_block_dynamic', 'lts__t_bytes.sum',
+            'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
+            'dram__throughput.avg.pct_of_peak_sustained_elapsed']
     for r in rows[2:]:
         print(r[hdr.index('Kernel Name')][:90], r[hdr.index('Grid Size')])
         for w in want:
