@@ -521,7 +521,8 @@ static inline size_t conv_tc_wsplit_floats(const b2rl_layer &l) {
 // returns B2RL_OK, or 1 when the shape is outside what the tensor-core kernel handles (caller falls
 // back to the FFMA engine).  wsplit: scratch for the pre-split weights (conv_tc_wsplit_floats).
 static int launch_conv_fwd_tc(const b2rl_layer &l, const Operand &A, const float *W, const float *bias, float *out,
-                              float *pre_out, int64_t rows, float *wsplit, size_t wsplit_cap, cudaStream_t s) {
+                              float *pre_out, int64_t rows, float *wsplit, size_t wsplit_cap, cudaStream_t s,
+                              bool reuse_split = false) {   // reuse_split: wsplit still holds this layer's split weights
     const int KK = l.ksize * l.ksize, K = l.in_c * KK, P = l.out_h * l.out_w;
     const int n_pad = (l.out_c + 15) / 16 * 16, k_pad = (K + kTcBK - 1) / kTcBK * kTcBK;
     if (n_pad > 256 || k_pad > 8192 || rows * (int64_t)P > INT32_MAX) return 1;
@@ -535,7 +536,7 @@ static int launch_conv_fwd_tc(const b2rl_layer &l, const Operand &A, const float
     if (reinterpret_cast<uintptr_t>(wsplit) % 16 != 0) return 1;          // bulk copies need 16-byte aligned sources
     float *w_hi = wsplit, *w_lo = wsplit + (size_t)n_pad * k_pad;
     uint32_t *koff = reinterpret_cast<uint32_t *>(wsplit + (size_t)2 * n_pad * k_pad);
-    {
+    if (!reuse_split) {
         const int total = n_pad * k_pad;
         weight_split_kernel<<<(total + 255) / 256, 256, 0, s>>>(W, l.out_c, K, n_pad, k_pad, w_hi, w_lo, KK, l.ksize, l.in_h * l.in_w,
                                                                 l.in_w, koff);

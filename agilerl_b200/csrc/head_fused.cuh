@@ -3,7 +3,7 @@
 // The head of RainbowQNetwork / QNetwork is a handful of tiny (Noisy)Linear -> LayerNorm -> act
 // layers (agilerl/networks/custom_modules.py:127-162, utils/evolvable_networks.py:527-644):
 // 27k MAC per row for the north-star net.  As separate GEMM launches each of them costs a kernel's
-// ramp-up/tail (5-10 us) for microseconds of math; here one CTA takes a tile of 16 rows through
+// ramp-up/tail (5-10 us) for microseconds of math; here one CTA takes a tile of 4 rows through
 // every layer of both chains, activations staying in shared memory, weights streamed from L2
 // (they are a few hundred KB at most and shared by all CTAs).  It writes exactly the buffers the
 // unfused path writes (z, stats, pre, a per layer), so backward and the loss kernels are unchanged.

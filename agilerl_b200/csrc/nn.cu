@@ -218,7 +218,7 @@ static int validate_net(const b2rl_net_desc &net) {
 // NoisyLinear: W_eff = mu + sigma * eps   (custom_components.py:97-99; mul then add, no FMA)
 // ------------------------------------------------------------------------------------------
 struct Seg { float *dst; const float *mu; const float *sigma; const float *eps; int64_t n; };
-struct SegTable { Seg s[2 * (B2RL_MAX_ENC + 2 * B2RL_MAX_HEAD)]; int n; };
+struct SegTable { Seg s[4 * (B2RL_MAX_ENC + 2 * B2RL_MAX_HEAD)]; int n; };    // room for two networks
 
 __global__ void compose_kernel(SegTable t) {
     const Seg sg = t.s[blockIdx.y];
@@ -241,18 +241,24 @@ static void for_each_layer(const b2rl_net_desc &net, F &&f) {
     for (int i = 0; i < net.n_adv; ++i) f(net.adv[i]);
 }
 
+// W_eff of every noisy layer of up to two parameter sets (online + target network) in one launch
 static int compose_weights(const b2rl_net_desc &net, const float *params, const float *eps, float *weff,
-                           cudaStream_t s) {
+                           cudaStream_t s, const float *params2 = nullptr, const float *eps2 = nullptr,
+                           float *weff2 = nullptr) {
     SegTable t;
     t.n = 0;
     int64_t maxn = 0;
-    for_each_layer(net, [&](const b2rl_layer &l) {
-        if (!l.noisy) return;
-        const int64_t nw = layer_w_elems(l);
-        t.s[t.n++] = Seg{weff + l.w_off, params + l.w_off, params + l.ws_off, eps + l.we_off, nw};
-        t.s[t.n++] = Seg{weff + l.b_off, params + l.b_off, params + l.bs_off, eps + l.be_off, (int64_t)l.out_c};
-        if (nw > maxn) maxn = nw;
-    });
+    auto add = [&](const float *p, const float *e, float *w) {
+        for_each_layer(net, [&](const b2rl_layer &l) {
+            if (!l.noisy) return;
+            const int64_t nw = layer_w_elems(l);
+            t.s[t.n++] = Seg{w + l.w_off, p + l.w_off, p + l.ws_off, e + l.we_off, nw};
+            t.s[t.n++] = Seg{w + l.b_off, p + l.b_off, p + l.bs_off, e + l.be_off, (int64_t)l.out_c};
+            if (nw > maxn) maxn = nw;
+        });
+    };
+    add(params, eps, weff);
+    if (params2) add(params2, eps2, weff2);
     if (t.n == 0) return B2RL_OK;
     int bx = (int)((maxn + 255) / 256);
     if (bx > 64) bx = 64;
@@ -429,7 +435,8 @@ static int layer_forward(const b2rl_net_desc &net, const b2rl_layer &l, const fl
         int rc = 1;
         if (l.kind == B2RL_LAYER_CONV && tc_enabled() && l.ln == B2RL_LN_NONE)
             rc = launch_conv_fwd_tc(l, A, W, bias, out_ptr, lb.pre ? lb.pre + row0 * oe : nullptr, r, sc.partial, sc.floats,
-                                    s);   // tcgen05 3xTF32 (pre-split weights live in the split-K scratch)
+                                    s, run > 0);   // tcgen05 3xTF32 (pre-split weights live in the split-K scratch;
+                                                   // the second observation chunk reuses the first one's split)
         if (rc == 1 && l.kind == B2RL_LAYER_CONV)
             rc = dispatch_elem(A.elem_kind(), [&](auto ek) {
                 return launch_igemm<OpTraits<decltype(ek)::value, MAP_PIXEL, MAP_KERNEL, true, false>, OpW,
@@ -1255,8 +1262,9 @@ static int rainbow_loss(const b2rl_net_desc &net, const b2rl_learn_cfg &cfg, con
     const bool noise = cfg.use_noise != 0;
     int rc;
     if (noise) {
-        if ((rc = compose_weights(net, bufs.actor_params, bufs.actor_eps, ws.weff_actor, s)) != B2RL_OK) return rc;
-        if ((rc = compose_weights(net, bufs.target_params, bufs.target_eps, ws.weff_target, s)) != B2RL_OK) return rc;
+        if ((rc = compose_weights(net, bufs.actor_params, bufs.actor_eps, ws.weff_actor, s, bufs.target_params,
+                                  bufs.target_eps, ws.weff_target)) != B2RL_OK)
+            return rc;
     }
     Scratch sc{ws.partial, ws.partial_floats};
     // target network on next_obs (forward #2) on a side stream, concurrently with the online pass
