@@ -111,16 +111,21 @@ tree_set_kernel(double *__restrict__ st, double *__restrict__ mt, int64_t cap,
     }
 }
 
-// Fast path for a learn batch (n <= kFastMax distinct-or-not leaves, both trees, cap <= 2^24):
-// no global-memory round trip between levels.  A thread carries the value of the node on its own
-// leaf-to-root path in registers; the sibling at every level is either untouched by this batch —
-// then its value was prefetched from global memory up front, all levels at once, one latency — or
-// it lies on another thread's path, which published it the level before in a shared-memory hash
-// table (three tables in rotation: read l-1, fill l, clear l+1; one __syncthreads per level).
+// Fast path for a learn batch (n <= kFastMax leaves, both trees, cap <= 2^24): no global-memory round
+// trip and no hashing inside the level loop.
+//   1. last-writer-wins: a small hash set of leaf ids keeps, per id, the highest batch position.
+//   2. every surviving thread registers the nodes of its leaf-to-root path (node ids are unique across
+//      levels) in one shared-memory hash map node -> owning thread (first registrant wins; all threads
+//      through a node hold identical values), then looks up, for every level, the thread that owns its
+//      SIBLING (or none: then the sibling is untouched by this batch and its value was prefetched from
+//      global memory up front, all levels at once).  Two barriers for all 17+ levels.
+//   3. the level loop is then a thread-to-thread exchange through a double-buffered value array:
+//      read the partner's value, add / min with the own one (registers), publish, one barrier.
 // Same arithmetic as tree_set_kernel (left + right, Python min(left, right)), same last-writer rule.
 constexpr int kFastMax = 512;
 constexpr int kFastLevels = 24;
-constexpr int kFastEmpty = -1;
+constexpr unsigned long long kFastEmpty64 = ~0ull;
+constexpr int kFastDense = 2048;              // nodes below this id (the top 11 levels) use a direct-index owner table
 
 __device__ __forceinline__ uint32_t fast_hash(uint32_t key, int bits) { return (key * 2654435761u) >> (32 - bits); }
 
@@ -130,19 +135,18 @@ tree_set_fast_kernel(double *__restrict__ st, double *__restrict__ mt, int64_t c
                      const int64_t *__restrict__ idx, const double *__restrict__ pa, const float *__restrict__ pri,
                      int n, int tbits, double alpha, double floor_, double *max_priority) {
     extern __shared__ __align__(16) unsigned char tsm[];
-    const int T = 1 << tbits;
-    // [3][T] keys | [3][T] sum values | [3][T] min values | [T] last-writer position
-    int *keys = reinterpret_cast<int *>(tsm);
-    double *vs = reinterpret_cast<double *>(tsm + (size_t)3 * T * sizeof(int) + (size_t)T * sizeof(int));
-    double *vm = vs + (size_t)3 * T;
-    int *lastpos = keys + 3 * T;
+    const int T = 1 << tbits;                     // node map slots
+    // [T] u64 (node << 32 | owner) | [2][kFastMax] sum | [2][kFastMax] min | [kFastDense] int
+    unsigned long long *nmap = reinterpret_cast<unsigned long long *>(tsm);
+    double *vs = reinterpret_cast<double *>(tsm + (size_t)T * sizeof(unsigned long long));
+    double *vm = vs + 2 * kFastMax;
+    int *dense = reinterpret_cast<int *>(vm + 2 * kFastMax);      // [kFastDense] owner of the top-level nodes
     const int tid = threadIdx.x;
-    for (int i = tid; i < 3 * T; i += blockDim.x) keys[i] = kFastEmpty;
-    for (int i = tid; i < T; i += blockDim.x) lastpos[i] = -1;
-    __syncthreads();
+    for (int i = tid; i < T; i += blockDim.x) nmap[i] = kFastEmpty64;
+    for (int i = tid; i < kFastDense; i += blockDim.x) dense[i] = -1;
 
     const bool have = tid < n;
-    const int id = have ? (int)idx[tid] : 0;
+    const uint32_t id = have ? (uint32_t)idx[tid] : 0u;
     double v = 0.0, local_max = 0.0;
     if (have) {
         if (kFromPriority) {
@@ -151,17 +155,6 @@ tree_set_fast_kernel(double *__restrict__ st, double *__restrict__ mt, int64_t c
             local_max = p;
             v = pow(p, alpha);
         } else v = pa[tid];
-    }
-    // ---- last writer of every leaf (table 0 doubles as the leaf-id set for this phase)
-    int lslot = 0;
-    if (have) {
-        lslot = (int)fast_hash((uint32_t)id, tbits);
-        while (true) {
-            const int k = atomicCAS(&keys[lslot], kFastEmpty, id);
-            if (k == kFastEmpty || k == id) break;
-            lslot = (lslot + 1) & (T - 1);
-        }
-        atomicMax(&lastpos[lslot], tid);
     }
     if (kFromPriority && max_priority != nullptr) {
         // block max -> *max_priority = max(*max_priority, max_i p_i)  (replay_buffer.py:329)
@@ -179,56 +172,89 @@ tree_set_fast_kernel(double *__restrict__ st, double *__restrict__ mt, int64_t c
         }
     }
     __syncthreads();
-    const bool active = have && lastpos[lslot] == tid;
+    // ---- 1. last writer of every leaf: the map entry of the LEAF node keeps the highest position
+    //         (key in the high word, so atomicMax on the packed word orders by position within a key)
+    const uint32_t leaf = (uint32_t)cap + id;
+    int lslot = 0;
+    if (have) {
+        lslot = (int)fast_hash(leaf, tbits);
+        const unsigned long long mine = ((unsigned long long)leaf << 32) | (unsigned)tid;
+        while (true) {
+            const unsigned long long cur = atomicCAS(&nmap[lslot], kFastEmpty64, mine);
+            if (cur == kFastEmpty64) break;
+            if ((uint32_t)(cur >> 32) == leaf) { atomicMax(&nmap[lslot], mine); break; }
+            lslot = (lslot + 1) & (T - 1);
+        }
+    }
     __syncthreads();
-    for (int i = tid; i < T; i += blockDim.x) keys[i] = kFastEmpty;      // table 0 becomes the leaf level's table
+    const bool active = have && (uint32_t)(nmap[lslot] & 0xffffffffull) == (uint32_t)tid;
     // ---- prefetch the sibling of every node on this leaf's path (values before this batch)
-    uint32_t node = (uint32_t)cap + (uint32_t)id;
     double sib_s[kFastLevels], sib_m[kFastLevels];
 #pragma unroll
     for (int l = 0; l < kFastLevels; ++l) {
         sib_s[l] = 0.0; sib_m[l] = 0.0;
         if (active && l < levels) {
-            const uint32_t sb = (node >> l) ^ 1u;
+            const uint32_t sb = (leaf >> l) ^ 1u;
             sib_s[l] = st[sb];
             sib_m[l] = mt[sb];
         }
     }
-    __syncthreads();
-    double my_s = v, my_m = v;
-    auto publish = [&](int table, uint32_t key, double a, double b) {
-        int *kt = keys + table * T;
-        int slot = (int)fast_hash(key, tbits);
-        while (true) {
-            const int k = atomicCAS(&kt[slot], kFastEmpty, (int)key);
-            if (k == kFastEmpty || k == (int)key) break;
-            slot = (slot + 1) & (T - 1);
+    // ---- 2a. register the inner nodes of the path (the leaf entry already names this thread)
+    if (active) {
+#pragma unroll 4
+        for (int l = 1; l < levels; ++l) {
+            const uint32_t node = leaf >> l;
+            if (node < (uint32_t)kFastDense) {           // any registrant may own it: plain store, no contention
+                dense[node] = tid;
+                continue;
+            }
+            const unsigned long long mine = ((unsigned long long)node << 32) | (unsigned)tid;
+            int slot = (int)fast_hash(node, tbits);
+            while (true) {
+                const unsigned long long cur = atomicCAS(&nmap[slot], kFastEmpty64, mine);
+                if (cur == kFastEmpty64 || (uint32_t)(cur >> 32) == node) break;
+                slot = (slot + 1) & (T - 1);
+            }
         }
-        vs[table * T + slot] = a;          // threads sharing the node hold identical values
-        vm[table * T + slot] = b;
-    };
+    }
+    __syncthreads();
+    // ---- 2b. owner of the sibling at every level (-1: untouched by this batch)
+    int partner[kFastLevels];
+#pragma unroll
+    for (int l = 0; l < kFastLevels; ++l) {
+        partner[l] = -1;
+        if (active && l < levels) {
+            const uint32_t sb = (leaf >> l) ^ 1u;
+            if (l > 0 && sb < (uint32_t)kFastDense) {
+                partner[l] = dense[sb];
+                continue;
+            }
+            int slot = (int)fast_hash(sb, tbits);
+            while (true) {
+                const unsigned long long cur = nmap[slot];
+                if (cur == kFastEmpty64) break;
+                if ((uint32_t)(cur >> 32) == sb) { partner[l] = (int)(cur & 0xffffffffull); break; }
+                slot = (slot + 1) & (T - 1);
+            }
+        }
+    }
+    // ---- 3. level loop: thread-to-thread exchange
+    double my_s = v, my_m = v;
+    uint32_t node = leaf;
     if (active) {
         st[node] = v;
         mt[node] = v;
-        publish(0, node, v, v);
+        vs[tid] = v;
+        vm[tid] = v;
     }
     __syncthreads();
 #pragma unroll
     for (int l = 0; l < kFastLevels; ++l) {
         if (l < levels) {
-            const int rd = l % 3, wr = (l + 1) % 3, cl = (l + 2) % 3;
-            for (int i = tid; i < T; i += blockDim.x) keys[cl * T + i] = kFastEmpty;
+            const int rd = (l & 1) * kFastMax, wr = ((l + 1) & 1) * kFastMax;
             if (active) {
-                const uint32_t sb = node ^ 1u;
                 double o_s = sib_s[l], o_m = sib_m[l];
-                const int *kt = keys + rd * T;
-                int slot = (int)fast_hash(sb, tbits);
-                while (true) {
-                    const int k = kt[slot];
-                    if (k == (int)sb) { o_s = vs[rd * T + slot]; o_m = vm[rd * T + slot]; break; }
-                    if (k == kFastEmpty) break;
-                    slot = (slot + 1) & (T - 1);
-                }
+                if (partner[l] >= 0) { o_s = vs[rd + partner[l]]; o_m = vm[rd + partner[l]]; }
                 const bool left = (node & 1u) == 0;
                 const double ns = left ? __dadd_rn(my_s, o_s) : __dadd_rn(o_s, my_s);
                 const double nm = left ? dmin_py(my_m, o_m) : dmin_py(o_m, my_m);
@@ -236,7 +262,8 @@ tree_set_fast_kernel(double *__restrict__ st, double *__restrict__ mt, int64_t c
                 st[node] = ns;
                 mt[node] = nm;
                 my_s = ns; my_m = nm;
-                publish(wr, node, ns, nm);
+                vs[wr + tid] = ns;
+                vm[wr + tid] = nm;
             }
             __syncthreads();
         }
@@ -252,10 +279,15 @@ static int launch_tree_fast(double *st, double *mt, int64_t cap, const int64_t *
                             int64_t n, double alpha, double floor_, double *max_priority, cudaStream_t s) {
     int levels = 0;
     while (((int64_t)1 << levels) < cap) ++levels;
-    int tbits = 6;
-    while ((1 << tbits) < 2 * n) ++tbits;
+    // distinct path nodes <= sum over levels of min(n, nodes of the level): keep the map at most ~40 % full
+    int64_t distinct = 0;
+    for (int l = 0; l <= levels; ++l) distinct += n < ((int64_t)1 << l) ? n : ((int64_t)1 << l);
+    int tbits = 8;
+    while (((int64_t)1 << tbits) < distinct * 5 / 2) ++tbits;
     const int T = 1 << tbits;
-    const size_t smem = (size_t)4 * T * sizeof(int) + (size_t)6 * T * sizeof(double);
+    const size_t smem = (size_t)T * sizeof(unsigned long long) + (size_t)4 * kFastMax * sizeof(double) +
+                        (size_t)kFastDense * sizeof(int);
+    if (smem > 200 * 1024) return 1;
     const int threads = (int)((n + 31) / 32 * 32);
     auto kern = tree_set_fast_kernel<kFromPriority>;
     if (smem > 48 * 1024) B2RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -371,8 +403,11 @@ int b2rl_tree_set(double *sum_tree, double *min_tree, int64_t cap, const int64_t
     B2RL_CHECK_ARG(is_pow2(cap), "capacity must be positive and a power of 2.");
     B2RL_CHECK_ARG(n >= 0, "n must be >= 0");
     B2RL_CHECK_ARG(sum_tree || min_tree, "both trees are NULL");
-    if (tree_fast_ok(sum_tree, min_tree, cap, n))
-        return launch_tree_fast<false>(sum_tree, min_tree, cap, idx, p_alpha, nullptr, n, 0.0, 0.0, nullptr, as_stream(stream));
+    if (tree_fast_ok(sum_tree, min_tree, cap, n)) {
+        const int rcf = launch_tree_fast<false>(sum_tree, min_tree, cap, idx, p_alpha, nullptr, n, 0.0, 0.0, nullptr,
+                                                as_stream(stream));
+        if (rcf != 1) return rcf;
+    }
     for (int64_t off = 0; off < n; off += kTreeChunk) {   // chunks keep last-writer-wins order
         const int64_t m = n - off < kTreeChunk ? n - off : kTreeChunk;
         tree_set_kernel<false, false><<<1, kTreeThreads, 0, as_stream(stream)>>>(
@@ -386,9 +421,11 @@ int b2rl_tree_set_from_priorities(double *sum_tree, double *min_tree, int64_t ca
                                   const float *priority, int64_t n, double alpha, double floor_,
                                   double *max_priority, void *stream) {
     B2RL_CHECK_ARG(is_pow2(cap), "capacity must be positive and a power of 2.");
-    if (tree_fast_ok(sum_tree, min_tree, cap, n))
-        return launch_tree_fast<true>(sum_tree, min_tree, cap, idx, nullptr, priority, n, alpha, floor_, max_priority,
-                                      as_stream(stream));
+    if (tree_fast_ok(sum_tree, min_tree, cap, n)) {
+        const int rcf = launch_tree_fast<true>(sum_tree, min_tree, cap, idx, nullptr, priority, n, alpha, floor_,
+                                               max_priority, as_stream(stream));
+        if (rcf != 1) return rcf;
+    }
     for (int64_t off = 0; off < n; off += kTreeChunk) {
         const int64_t m = n - off < kTreeChunk ? n - off : kTreeChunk;
         tree_set_kernel<false, true><<<1, kTreeThreads, 0, as_stream(stream)>>>(
