@@ -209,6 +209,22 @@ __global__ void weight_split_kernel(const float *__restrict__ w, int N, int K, i
 
 __device__ __noinline__ float act_fwd_slow(int act, float v) { return act_fwd(act, v); }
 
+// opt a kernel into large dynamic shared memory once (the launchers cap their request at kTcSmemCap):
+// cudaFuncSetAttribute costs microseconds of host time per call, and there are ~10 conv launches per step
+constexpr int kTcSmemCap = 200 * 1024;
+template <typename Kern>
+static int ensure_big_smem(Kern kern) {
+    // keyed by the function's address: every instantiation shares the pointer TYPE, not the pointer
+    static const void *seen[64];
+    static int n_seen = 0;
+    const void *key = reinterpret_cast<const void *>(kern);
+    for (int i = 0; i < n_seen; ++i)
+        if (seen[i] == key) return B2RL_OK;
+    B2RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemCap));
+    if (n_seen < 64) seen[n_seen++] = key;
+    return B2RL_OK;
+}
+
 // Forward convolution.  Latency structure (the kernel is bound by the im2col gather, not by the
 // tensor pipe): a thread keeps the raw taps of the next D k-blocks in registers (for packed uint8
 // frames D = 8 covers a whole 8x8x4 receptive field: every DRAM round trip of a row is in flight at
@@ -561,7 +577,7 @@ static int launch_conv_fwd_tc(const b2rl_layer &l, const Operand &A, const float
               p.in_bstride % 2 == 0 && reinterpret_cast<uintptr_t>(A.ptr) % 8 == 0;
     const int grid = (p.M + kTcBM - 1) / kTcBM;
     auto launch = [&](auto kern) -> int {
-        B2RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        { const int rca = ensure_big_smem(kern); if (rca != B2RL_OK) return rca; }
         kern<<<grid, kTcThreads + 32, smem, s>>>(p);
         B2RL_LAUNCH_CHECK();
         return B2RL_OK;
@@ -677,7 +693,7 @@ static int launch_conv_dgrad_tc(const b2rl_layer &l, const float *g, const float
         if (rcp != 1) return rcp;
     }
     auto kern = conv_fwd_tc_kernel<EL_F32, false, false, 2, true>;
-    B2RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { const int rca = ensure_big_smem(kern); if (rca != B2RL_OK) return rca; }
     kern<<<dim3((unsigned)((p.M + kTcBM - 1) / kTcBM), S * S), kTcThreads + 32, smem, s>>>(p);
     B2RL_LAUNCH_CHECK();
     return B2RL_OK;
@@ -1014,7 +1030,7 @@ static int launch_conv_wgrad_tc(const b2rl_layer &l, const Operand &X, const flo
                      reinterpret_cast<uintptr_t>(X.ptr) % 4 == 0;
     dim3 grid(mt, (unsigned)splits);
     auto launch = [&](auto kern) -> int {
-        B2RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        { const int rca = ensure_big_smem(kern); if (rca != B2RL_OK) return rca; }
         kern<<<grid, kTcThreads + 32, smem, s>>>(p);
         B2RL_LAUNCH_CHECK();
         return B2RL_OK;

@@ -612,10 +612,14 @@ struct ProjCfg { float gamma, v_min, v_max, delta_z; };
 
 // Target distribution of a* and (canonical shapes) the C51 projection, sequential per row in the
 // reference's index_add_ order so the fp32 sums are bit-faithful (dqn_rainbow.py:318-360).
+// When v_on / adv_on are given (the online network's outputs on next_obs) the kernel first selects
+// a* = argmax_a E[Z_online(next_obs, a)] itself (dqn_rainbow.py:315; same code as rainbow_q_kernel)
+// and records it in a_star; otherwise it reads a_star.
 __global__ void rainbow_target_kernel(const float *__restrict__ v, const float *__restrict__ adv,
-                                      const int32_t *__restrict__ a_star, const float *__restrict__ reward,
+                                      int32_t *__restrict__ a_star, const float *__restrict__ reward,
                                       const float *__restrict__ done, const float *__restrict__ support, ProjCfg pc,
-                                      int A, int N, float *__restrict__ tdist, float *__restrict__ proj) {
+                                      int A, int N, float *__restrict__ tdist, float *__restrict__ proj,
+                                      const float *__restrict__ v_on, const float *__restrict__ adv_on) {
     extern __shared__ float sm[];
     float *x = sm;                 // A*N
     float *pr = sm + A * N;        // N   projected
@@ -624,8 +628,31 @@ __global__ void rainbow_target_kernel(const float *__restrict__ v, const float *
     int *Li = reinterpret_cast<int *>(wu + N);   // N
     int *Ui = Li + N;                            // N
     const int64_t row = blockIdx.x;
+    __shared__ int s_as;
+    if (v_on != nullptr) {                 // host guarantees A <= 3*N (q[] borrows the projection scratch)
+        float *q = pr;
+        dueling_to_smem(v_on + row * N, adv_on + row * (int64_t)A * N, A, N, x);
+        const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
+        for (int a = warp; a < A; a += nwarps) {
+            const float qa = softmax_clamp_row(x + a * N, N, support);
+            if (lane == 0) q[a] = qa;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int best = 0;
+            float bv = q[0];
+            for (int a = 1; a < A; ++a)
+                if (q[a] > bv) { bv = q[a]; best = a; }    // first maximum, like torch.argmax
+            s_as = best;
+            a_star[row] = best;
+        }
+        __syncthreads();
+    } else {
+        if (threadIdx.x == 0) s_as = a_star[row];
+        __syncthreads();
+    }
+    const int as = s_as;
     dueling_to_smem(v + row * N, adv + row * (int64_t)A * N, A, N, x);
-    const int as = a_star[row];
     float *p = x + as * N;
     if ((threadIdx.x >> 5) == 0) softmax_clamp_row(p, N, nullptr);
     __syncthreads();
@@ -1293,17 +1320,21 @@ static int rainbow_loss(const b2rl_net_desc &net, const b2rl_learn_cfg &cfg, con
     const size_t sm_q = sizeof(float) * ((size_t)A * N + A);
     const size_t sm_t = sizeof(float) * ((size_t)A * N + 3 * (size_t)N) + sizeof(int) * 2 * (size_t)N;
     if ((rc = head_smem_check(sm_t)) != B2RL_OK) return rc;
-    // next_actions = actor(next_obs).argmax(1)                              (dqn_rainbow.py:315)
-    rainbow_q_kernel<<<(int)B, 128, sm_q, s>>>(v_on, adv_on, bufs.support, A, N, nullptr, ws.a_star, nullptr);
-    B2RL_LAUNCH_CHECK();
+    // next_actions = actor(next_obs).argmax(1) (dqn_rainbow.py:315): selected inside the target kernel
+    const bool fuse_q = A <= 3 * N;
+    if (!fuse_q) {
+        rainbow_q_kernel<<<(int)B, 128, sm_q, s>>>(v_on, adv_on, bufs.support, A, N, nullptr, ws.a_star, nullptr);
+        B2RL_LAUNCH_CHECK();
+    }
+    const float *fq_v = fuse_q ? v_on : nullptr, *fq_a = fuse_q ? adv_on : nullptr;
     ProjCfg pc{(float)cfg.gamma, (float)cfg.v_min, (float)cfg.v_max, (float)cfg.delta_z};
     if (!cfg.driver_shapes) {
         rainbow_target_kernel<<<(int)B, 128, sm_t, s>>>(v_tg, adv_tg, ws.a_star, bufs.reward, bufs.done, bufs.support,
-                                                        pc, A, N, nullptr, ws.proj);
+                                                        pc, A, N, nullptr, ws.proj, fq_v, fq_a);
         B2RL_LAUNCH_CHECK();
     } else {
         rainbow_target_kernel<<<(int)B, 128, sm_t, s>>>(v_tg, adv_tg, ws.a_star, bufs.reward, bufs.done, bufs.support,
-                                                        pc, A, N, ws.tdist, nullptr);
+                                                        pc, A, N, ws.tdist, nullptr, fq_v, fq_a);
         B2RL_LAUNCH_CHECK();
         q2_cmat_kernel<<<N, 64, sizeof(float) * N, s>>>(bufs.reward, bufs.done, bufs.support, pc, B, N, ws.cmat);
         B2RL_LAUNCH_CHECK();

@@ -290,7 +290,11 @@ static int launch_tree_fast(double *st, double *mt, int64_t cap, const int64_t *
     if (smem > 200 * 1024) return 1;
     const int threads = (int)((n + 31) / 32 * 32);
     auto kern = tree_set_fast_kernel<kFromPriority>;
-    if (smem > 48 * 1024) B2RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static bool big_smem = false;              // per instantiation; the launcher never asks for more than 200 KB
+    if (!big_smem) {
+        B2RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        big_smem = true;
+    }
     kern<<<1, threads, smem, s>>>(st, mt, cap, levels, idx, pa, pri, (int)n, tbits, alpha, floor_, max_priority);
     B2RL_LAUNCH_CHECK();
     return B2RL_OK;
@@ -339,9 +343,16 @@ __global__ void per_sample_kernel(const double *__restrict__ st, const double *_
                                   const float *__restrict__ reward_ring, const float *__restrict__ done_ring,
                                   float *__restrict__ out_action, float *__restrict__ out_reward,
                                   float *__restrict__ out_done) {
+    // the top levels of the sum tree are walked by every sample: stage them once per CTA (one coalesced
+    // load instead of ten dependent L2 round trips per thread)
+    constexpr int kTop = 1024;
+    __shared__ double top[kTop];
+    const int ntop = (int)(2 * cap < kTop ? 2 * cap : kTop);
+    for (int k = threadIdx.x; k < ntop; k += blockDim.x) top[k] = st[k];
+    __syncthreads();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= B) return;
-    const double total = st[1];                                   // sum_tree.sum()
+    const double total = top[1];                                  // sum_tree.sum()
     const double segment = __ddiv_rn(total, (double)B);           // replay_buffer.py:369
     const double a = __dmul_rn(segment, (double)i);
     const double b = __dmul_rn(segment, (double)(i + 1));
@@ -354,7 +365,18 @@ __global__ void per_sample_kernel(const double *__restrict__ st, const double *_
         u = uniforms[i];
     }
     const double ub = __dadd_rn(__dmul_rn((double)u, __dsub_rn(b, a)), a);   // :377
-    const int64_t idx = retrieve_dev(st, cap, ub);
+    int64_t idx;
+    {
+        double u2 = ub;
+        int64_t node = 1;
+        while (node < cap) {  // segment_tree.py:148-155 — strict '>' tie rule (quirk Q6); same arithmetic as retrieve_dev
+            const int64_t left = 2 * node;
+            const double l = left < ntop ? top[left] : __ldg(st + left);
+            if (l > u2) node = left;
+            else { u2 = __dsub_rn(u2, l); node = left + 1; }
+        }
+        idx = node - cap;
+    }
     out_idx[i] = idx;
     if (out_w != nullptr) {                                        // :383-409
         const double p_min = __ddiv_rn(mt[1], total);
