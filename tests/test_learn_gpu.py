@@ -332,3 +332,45 @@ def test_conv_geometry_sweep_matches_oracle(name, obs, chan, kern, stride, u8):
         got = gv.view(k).cpu()
         scale = max(ref.abs().max().item(), 1e-6)
         assert (got - ref).abs().max().item() <= 2e-5 * scale + 1e-8, f"grad {k}: {(got - ref).abs().max().item()} vs {scale}"
+
+
+@pytest.mark.parametrize("B", [1, 7, 300])
+def test_odd_batch_sizes_match_oracle(B):
+    """Batch sizes that are not multiples of the head tile (4 rows), the warp or the conv M tile:
+    a single row, a prime, and one above a tile boundary — loss / priorities / gradients vs the oracle."""
+    from oracle import learn as olearn, nets as onets
+    from agilerl_b200.engine import LearnEngine, NetBuffers
+    from agilerl_b200.networks.spec import FlatLayout, rainbow_spec
+    obs, A = (3, 20, 20), 4
+    kw = dict(channel_size=(8, 16), kernel_size=(4, 3), stride_size=(2, 1), latent_dim=16, hidden_size=(32,),
+              obs_low=0.0, obs_high=255.0)
+    layout = FlatLayout(rainbow_spec(obs, A, obs_u8=True, **kw))
+    gen = torch.Generator().manual_seed(100 + B)
+    sd_a = _random_state(layout, gen)
+    sd_t = {k: v + 0.01 * torch.randn(v.shape, generator=gen) for k, v in sd_a.items()}
+    actor, target = NetBuffers(layout, "cuda"), NetBuffers(layout, "cuda")
+    actor.load_state_dict(sd_a); target.load_state_dict(sd_t)
+    eng = LearnEngine(layout, actor, target)
+    nexp = dict(obs=torch.randint(0, 256, (B, *obs), dtype=torch.uint8, generator=gen),
+                action=torch.randint(0, A, (B,), generator=gen).float(), reward=torch.randn(B, 1, generator=gen),
+                next_obs=torch.randint(0, 256, (B, *obs), dtype=torch.uint8, generator=gen),
+                done=(torch.rand(B, 1, generator=gen) < 0.2).float())
+    exp = dict(nexp, weights=torch.rand(B, generator=gen) + 0.5, idxs=torch.arange(B))
+    oa = olearn.OracleAgent(onets.rainbow_spec(obs, A, **kw), sd_a, sd_t, batch_size=B, lr=1e-4)
+    z = (torch.randn(eng.noise_count, generator=gen), torch.randn(eng.noise_count, generator=gen))
+    oloss, _, opri = oa.learn_rainbow(exp, nexp, per=True, noise_normals=z)
+    hp = dict(v_min=-10.0, v_max=10.0, delta_z=20.0 / 50, lr=1e-4, tau=1e-3, prior_eps=1e-6)
+    loss, _, pri, _ = eng.rainbow_learn([({k: v.cuda() for k, v in nexp.items()}, 0.99 ** 3, False)], B=B,
+                                        support=torch.linspace(-10.0, 10.0, 51).cuda(), weights=exp["weights"].cuda(),
+                                        weights_mode=1, hp=hp, noise_normals=z)
+    torch.cuda.synchronize()
+    assert abs(loss.item() - oloss) <= 1e-5 * max(1.0, abs(oloss)), (loss.item(), oloss)
+    np.testing.assert_allclose(pri.cpu().numpy(), np.asarray(opri).reshape(-1), rtol=1e-5, atol=1e-5)
+    total = torch.sqrt(sum((g.double() ** 2).sum() for g in oa.last_grads.values())).item()
+    coef = min(1.0, 10.0 / (total + 1e-6))                   # clip_grad_norm_ scales the stored gradients
+    gv = NetBuffers(layout, "cuda"); gv.params.copy_(eng.grads)
+    for k, ref in oa.last_grads.items():
+        got = gv.view(k).cpu()
+        ref = ref * coef
+        scale = max(ref.abs().max().item(), 1e-6)
+        assert (got - ref).abs().max().item() <= 2e-5 * scale + 1e-8, f"grad {k}"

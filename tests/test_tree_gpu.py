@@ -159,3 +159,25 @@ def test_tree_invariants_full_size_device_pow():
     for i, k in last.items():
         ref = float(pri_h[k]) ** 0.6
         assert abs(s[cap + i] - ref) <= 2 * np.spacing(ref)
+
+
+@pytest.mark.parametrize("cap", [2, 64, 4096, 131072])
+@pytest.mark.parametrize("n", [1, 2, 31, 33, 255, 256, 257, 511, 512, 513, 1500])
+def test_batched_update_duplicates_and_sizes_bit_exact(cap, n):
+    """Batch sizes around the warp / fast-path limits (<= 512: partner-map kernel, above: level-by-level
+    kernel), with heavy index collisions (small trees): leaves follow the last writer, every ancestor is
+    bit-identical to n sequential __setitem__ calls of the reference (segment_tree.py:86-108)."""
+    from oracle.segtree import CSegTree
+    rng = np.random.default_rng(cap * 1000 + n)
+    st, mt = _trees(cap)
+    os_, om = CSegTree(cap, "sum"), CSegTree(cap, "min")
+    for rnd in range(3):
+        idx = rng.integers(0, cap, n)
+        if rnd == 1:
+            idx[: n // 2] = idx[0]                      # one leaf hit many times
+        val = np.abs(rng.standard_normal(n)) + 1e-9
+        _set_both(st, mt, idx, val)
+        for i, v in zip(idx, val):
+            os_[int(i)] = float(v); om[int(i)] = float(v)
+        assert np.array_equal(st._t.cpu().numpy()[1:], os_.tree[1:])
+        assert np.array_equal(mt._t.cpu().numpy()[1:], om.tree[1:])
