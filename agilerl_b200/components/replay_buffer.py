@@ -140,6 +140,11 @@ class ReplayBuffer:
         }
         self._storage = _unflatten(self._fields, (self.max_size,))
         self._row_bytes = {path: (t.numel() // self.max_size) * t.element_size() for path, t in self._fields.items()}
+        # tables for the multi-field C entry points (b2rl_ring_write_multi / b2rl_gather_rows_multi)
+        self._field_order = list(self._fields)
+        nf = len(self._field_order)
+        self._field_ptrs = (ctypes.c_void_p * nf)(*[self._fields[p].data_ptr() for p in self._field_order])
+        self._field_row_bytes = (ctypes.c_int64 * nf)(*[self._row_bytes[p] for p in self._field_order])
         self.initialized = True
 
     def add(self, data: DataType) -> None:
@@ -152,15 +157,25 @@ class ReplayBuffer:
             self._init(leaves)
         if n > self.max_size:
             raise ValueError("cannot add more transitions than max_size in one call")
-        stream = _lib.stream_ptr(self._dev)
+        nf = len(leaves)
+        srcs = []
         for path, v in leaves.items():
             dst = self._fields[path]
             if v.dtype != dst.dtype:
                 v = v.to(dst.dtype)
-            row_bytes = self._row_bytes[path]
-            assert v.numel() * v.element_size() == row_bytes * n, f"shape mismatch for {path}"
-            _lib.check(self._lib.b2rl_ring_write(dst.data_ptr(), v.data_ptr(), row_bytes, self._cursor, n,
-                                                 self.max_size, stream))
+            assert v.numel() * v.element_size() == self._row_bytes[path] * n, f"shape mismatch for {path}"
+            srcs.append(v)
+        if nf <= 8 and list(leaves) == self._field_order:       # every field of the transition in one launch
+            arr = ctypes.c_void_p * nf
+            _lib.check(self._lib.b2rl_ring_write_multi(nf, self._field_ptrs, arr(*[v.data_ptr() for v in srcs]),
+                                                       self._field_row_bytes, self._cursor, n, self.max_size,
+                                                       _lib.stream_ptr(self._dev)))
+        else:
+            stream = _lib.stream_ptr(self._dev)
+            for (path, _), v in zip(leaves.items(), srcs):
+                _lib.check(self._lib.b2rl_ring_write(self._fields[path].data_ptr(), v.data_ptr(), self._row_bytes[path],
+                                                     self._cursor, n, self.max_size, stream))
+        self._keep_add = srcs
         self._cursor = (self._cursor + n) % self.max_size
         self._size = min(self._size + n, self.max_size)
         self.counter += n
@@ -177,10 +192,17 @@ class ReplayBuffer:
         nrows = flat.numel()
         stream = _lib.stream_ptr(self._dev)
         out = {}
-        for path, src in self._fields.items():
-            dst = torch.empty((nrows, *src.shape[1:]), dtype=src.dtype, device=self._dev)
-            _lib.check(self._lib.b2rl_gather_rows(dst.data_ptr(), src.data_ptr(), flat.data_ptr(),
-                                                  self._row_bytes[path], nrows, stream))
+        dsts = [torch.empty((nrows, *src.shape[1:]), dtype=src.dtype, device=self._dev) for src in self._fields.values()]
+        nf = len(dsts)
+        if nf <= 8:
+            arr = ctypes.c_void_p * nf
+            _lib.check(self._lib.b2rl_gather_rows_multi(nf, arr(*[d.data_ptr() for d in dsts]), self._field_ptrs,
+                                                        self._field_row_bytes, flat.data_ptr(), nrows, stream))
+        else:
+            for (path, src), dst in zip(self._fields.items(), dsts):
+                _lib.check(self._lib.b2rl_gather_rows(dst.data_ptr(), src.data_ptr(), flat.data_ptr(),
+                                                      self._row_bytes[path], nrows, stream))
+        for (path, src), dst in zip(self._fields.items(), dsts):
             out[path] = dst.reshape(*idx_dev.shape, *src.shape[1:])
         return _unflatten(out, tuple(idx_dev.shape))
 

@@ -80,6 +80,67 @@ __global__ void select_copy_kernel(uint8_t *__restrict__ dst, SrcPtrs srcs, cons
     }
 }
 
+// ---- all fields of a transition in one launch (blockIdx.y = field) -------------------------------
+constexpr int kMaxFields = 8;
+struct MultiField { void *dst; const void *src; int64_t row_bytes; int vec; };   // vec: 16 / 4 / 1 bytes per element
+struct MultiFields { MultiField f[kMaxFields]; };
+
+template <typename V>
+__device__ __forceinline__ void gather_field(V *__restrict__ dst, const V *__restrict__ storage,
+                                             const int64_t *__restrict__ idx, int64_t row_v, int64_t n) {
+    if (row_v >= 256) {
+        for (int64_t r = blockIdx.x; r < n; r += gridDim.x) {
+            const V *s = storage + idx[r] * row_v;
+            V *d = dst + r * row_v;
+            for (int64_t c = threadIdx.x; c < row_v; c += blockDim.x) d[c] = __ldg(s + c);
+        }
+    } else {
+        const int64_t total = n * row_v;
+        for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
+             e += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t r = e / row_v, c = e - r * row_v;
+            dst[e] = __ldg(storage + idx[r] * row_v + c);
+        }
+    }
+}
+__global__ void gather_rows_multi_kernel(MultiFields mf, const int64_t *__restrict__ idx, int64_t n) {
+    const MultiField f = mf.f[blockIdx.y];
+    if (f.vec == 16) gather_field(static_cast<uint4 *>(f.dst), static_cast<const uint4 *>(f.src), idx, f.row_bytes / 16, n);
+    else if (f.vec == 4) gather_field(static_cast<uint32_t *>(f.dst), static_cast<const uint32_t *>(f.src), idx, f.row_bytes / 4, n);
+    else gather_field(static_cast<uint8_t *>(f.dst), static_cast<const uint8_t *>(f.src), idx, f.row_bytes, n);
+}
+
+template <typename V>
+__device__ __forceinline__ void ring_write_field(V *__restrict__ storage, const V *__restrict__ src, int64_t row_v,
+                                                 int64_t start, int64_t n, int64_t max_size) {
+    const int64_t total = n * row_v;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / row_v, c = e - r * row_v;
+        storage[((start + r) % max_size) * row_v + c] = src[e];
+    }
+}
+__global__ void ring_write_multi_kernel(MultiFields mf, int64_t start, int64_t n, int64_t max_size) {
+    const MultiField f = mf.f[blockIdx.y];     // dst = ring storage, src = the n new rows
+    if (f.vec == 16) ring_write_field(static_cast<uint4 *>(f.dst), static_cast<const uint4 *>(f.src), f.row_bytes / 16, start, n, max_size);
+    else if (f.vec == 4) ring_write_field(static_cast<uint32_t *>(f.dst), static_cast<const uint32_t *>(f.src), f.row_bytes / 4, start, n, max_size);
+    else ring_write_field(static_cast<uint8_t *>(f.dst), static_cast<const uint8_t *>(f.src), f.row_bytes, start, n, max_size);
+}
+
+static int fill_fields(int n_fields, void *const *dst, const void *const *src, const int64_t *row_bytes, MultiFields &mf,
+                       int64_t &max_row_bytes) {
+    B2RL_CHECK_ARG(n_fields >= 1 && n_fields <= kMaxFields, "n_fields must be in [1, %d]", kMaxFields);
+    B2RL_CHECK_ARG(dst && src && row_bytes, "NULL field table");
+    max_row_bytes = 0;
+    for (int i = 0; i < n_fields; ++i) {
+        B2RL_CHECK_ARG(dst[i] && src[i] && row_bytes[i] > 0, "bad field %d", i);
+        const uintptr_t al = reinterpret_cast<uintptr_t>(dst[i]) | reinterpret_cast<uintptr_t>(src[i]) | (uintptr_t)row_bytes[i];
+        mf.f[i] = MultiField{dst[i], src[i], row_bytes[i], (al & 15) == 0 ? 16 : ((al & 3) == 0 ? 4 : 1)};
+        if (row_bytes[i] > max_row_bytes) max_row_bytes = row_bytes[i];
+    }
+    return B2RL_OK;
+}
+
 template <typename F>
 static int dispatch_width(const void *a, const void *b, int64_t row_bytes, F &&f) {
     const uintptr_t al = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | (uintptr_t)row_bytes;
@@ -135,6 +196,39 @@ int b2rl_gather_rows(void *dst, const void *storage, const int64_t *idx, int64_t
         B2RL_LAUNCH_CHECK();
         return B2RL_OK;
     });
+}
+
+int b2rl_ring_write_multi(int n_fields, void *const *storage, const void *const *src, const int64_t *row_bytes,
+                          int64_t start, int64_t n, int64_t max_size, void *stream) {
+    B2RL_CHECK_ARG(max_size > 0 && start >= 0 && start < max_size, "cursor out of range");
+    B2RL_CHECK_ARG(n >= 0 && n <= max_size, "cannot add more rows than max_size in one call");
+    MultiFields mf;
+    int64_t max_row = 0;
+    int rc = fill_fields(n_fields, storage, src, row_bytes, mf, max_row);
+    if (rc != B2RL_OK) return rc;
+    if (n == 0) return B2RL_OK;
+    int64_t blocks = (n * max_row / 16 + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
+    ring_write_multi_kernel<<<dim3((unsigned)blocks, n_fields), 256, 0, as_stream(stream)>>>(mf, start, n, max_size);
+    B2RL_LAUNCH_CHECK();
+    return B2RL_OK;
+}
+
+int b2rl_gather_rows_multi(int n_fields, void *const *dst, const void *const *storage, const int64_t *row_bytes,
+                           const int64_t *idx, int64_t n, void *stream) {
+    B2RL_CHECK_ARG(idx, "NULL index buffer");
+    MultiFields mf;
+    int64_t max_row = 0;
+    int rc = fill_fields(n_fields, dst, storage, row_bytes, mf, max_row);
+    if (rc != B2RL_OK) return rc;
+    if (n <= 0) return B2RL_OK;
+    int64_t blocks = max_row >= 256 * 16 ? n : (n * max_row / 16 + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
+    gather_rows_multi_kernel<<<dim3((unsigned)blocks, n_fields), 256, 0, as_stream(stream)>>>(mf, idx, n);
+    B2RL_LAUNCH_CHECK();
+    return B2RL_OK;
 }
 
 int b2rl_nstep_fold(const float *const *reward_steps, const float *const *done_steps, int n_step,

@@ -150,7 +150,10 @@ class LearnEngine:
 
     @staticmethod
     def _vec(t: torch.Tensor, device) -> torch.Tensor:
-        return t.to(device, dtype=torch.float32).reshape(-1).contiguous()
+        if t.dtype != torch.float32 or t.device != device:
+            t = t.to(device, dtype=torch.float32)
+        t = t.reshape(-1)
+        return t if t.is_contiguous() else t.contiguous()
 
     # -- learn ---------------------------------------------------------------------------------
     def _cfg(self, B, *, gamma, v_min=0.0, v_max=0.0, delta_z=1.0, weights_mode=0, driver_shapes=0, double=0,

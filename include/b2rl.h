@@ -106,6 +106,12 @@ int b2rl_ring_write(void *storage, const void *src, int64_t row_bytes, int64_t s
 /* dst[i] <- storage[idx[i]], i < n (idx int64 on device, values in [0, max_size)). */
 int b2rl_gather_rows(void *dst, const void *storage, const int64_t *idx, int64_t row_bytes,
                      int64_t n, void *stream);
+/* The same for up to 8 fields of a transition in one launch (host arrays of n_fields device pointers /
+ * row sizes): what ReplayBuffer.add and storage[indices] do over every key of the TensorDict. */
+int b2rl_ring_write_multi(int n_fields, void *const *storage, const void *const *src, const int64_t *row_bytes,
+                          int64_t start, int64_t n, int64_t max_size, void *stream);
+int b2rl_gather_rows_multi(int n_fields, void *const *dst, const void *const *storage, const int64_t *row_bytes,
+                           const int64_t *idx, int64_t n, void *stream);
 
 /* MultiStepReplayBuffer._get_n_step_info (replay_buffer.py:206-258) over a device window of n
  * per-env batches (oldest first): reward_out[e] = sum_i gamma^i r_i[e] (fp32 accumulate, gamma^i a
