@@ -174,6 +174,8 @@ struct ConvTcParams {
     int cls_s;                  // classes per dimension (the forward stride); output pixel = (yy*s + py, xx*s + px)
     int out_H, out_W;           // plane of the scattered output
     int64_t w_class_stride;     // floats between the pre-split weights of consecutive classes
+    long long *dbg;             // diagnostics (B2RL_TC_DBG=<cta>): clock64 stamps of one CTA's roles, else NULL
+    int dbg_cta;
 };
 
 static inline size_t conv_tc_smem_bytes(int n_pad, int k_pad, int a_parts = 2, int a_stages = 2, int b_stages = kTcBStages) {
@@ -267,6 +269,10 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const Conv
     uint64_t *full_b = full_a + SA;                                      // [SB] weight tile landed
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(gen + (tptr_a - sbase));
     const int KB = p.k_pad / kTcBK;
+    // diagnostics: time stamps of producer warp 0 (slots 0..) and of the MMA lane (slots 64..) of one CTA
+    const bool dbg_on = p.dbg != nullptr && (int)blockIdx.x == p.dbg_cta && blockIdx.y == 0;
+    auto stamp = [&](int slot) { if (dbg_on) p.dbg[slot] = clock64(); };
+    if (tid == 0) stamp(0);
 
     // ---- one-time setup ----------------------------------------------------------------------
     if (tid == 0) {
@@ -303,6 +309,7 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const Conv
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
+    if (tid == 0) stamp(1);
     const uint32_t tmem_d = *tmem_ptr;
     const uint32_t idesc = tc::make_idesc_tf32(kTcBM, p.n_pad);
     const uint32_t lbo_a = kTcBM * 16, lbo_b = (uint32_t)p.n_pad * 16;
@@ -323,7 +330,9 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const Conv
                 __syncwarp();
             }
             tc::mbar_wait(&full_b[sb], (uint32_t)((kb / SB) & 1));
+            if ((tid & 31) == 0 && kb < 16) stamp(64 + 3 * kb);
             tc::mbar_wait(&full_a[s], (uint32_t)((kb / SA) & 1));
+            if ((tid & 31) == 0 && kb < 16) stamp(65 + 3 * kb);
             tc::tc_fence_after();
             // descriptors of consecutive k-steps differ only in the 14-bit start-address field
             const uint64_t dah0 = tc::make_desc(a_hi(s), lbo_a, 128), dal0 = tc::make_desc(a_lo(s), lbo_a, 128);
@@ -337,6 +346,7 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const Conv
                 }
                 tc::mma_commit(&mma_bar[s]);
             }
+            if ((tid & 31) == 0 && kb < 16) stamp(66 + 3 * kb);
             __syncwarp();
         }
     }
@@ -406,10 +416,12 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const Conv
         for (int d = 0; d < D; ++d)
             if (d < KB) gather(d, raw[d]);
     }
+    if (tid == 0) stamp(2);
 
     auto step = [&](int kb, uint32_t (&cur)[RAWN]) {
         const int s = kb % SA;
         if (kb >= SA) wait_mma(kb - SA);     // A stage s is free again
+        if (tid == 0 && kb < 16) stamp(3 + 3 * kb);
         // ---- convert + hi/lo split + 16-byte smem stores of the gathered taps
         const uint32_t ah = a_hi(s) + row_off + (uint32_t)(half * CH) * lbo_a, al = a_lo(s) + row_off + (uint32_t)(half * CH) * lbo_a;
         const int k0 = kb * kTcBK + half * (CH * 4);
@@ -439,10 +451,12 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const Conv
             tc::sts128(ah + (uint32_t)c * lbo_a, hi[0], hi[1], hi[2], hi[3]);
             if (!EXACT_A) tc::sts128(al + (uint32_t)c * lbo_a, lo[0], lo[1], lo[2], lo[3]);
         }
+        if (tid == 0 && kb < 16) stamp(4 + 3 * kb);
         if (kb + D < KB) gather(kb + D, cur);   // refill this register slot D k-blocks ahead
         tc::fence_async_smem();                  // generic-proxy smem writes -> visible to the async (tensor) proxy
         __syncwarp();
         if ((tid & 31) == 0) tc::mbar_arrive(&full_a[s]);
+        if (tid == 0 && kb < 16) stamp(5 + 3 * kb);
     };
     for (int kb0 = 0; kb0 < KB; kb0 += D) {
 #pragma unroll
@@ -451,6 +465,7 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const Conv
     }
     // ---- the last commit covers every earlier MMA of the issuing thread
     if (KB > 0) wait_mma(KB - 1);
+    if (tid == 0) stamp(60);
     tc::tc_fence_after();
 
     // ---- epilogue: warp w owns TMEM lanes 32*(w%4)..+31 (its rows) and the 16-column groups of parity w/4
@@ -504,6 +519,7 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const Conv
             }
         }
     }
+    if (tid == 0) stamp(61);
     }   // producer warps
     tc::tc_fence_before();
     __syncthreads();
@@ -526,6 +542,22 @@ static bool tc_persist_enabled() {
         v = (e && e[0] == '1') ? 1 : 0;
     }
     return v == 1;
+}
+
+// B2RL_TC_DBG=<cta index>: the forward kernel records clock64 stamps of that CTA (b2rl_debug_read)
+static int tc_debug_cta() {
+    static int v = -2;
+    if (v == -2) v = getenv("B2RL_TC_DBG") ? atoi(getenv("B2RL_TC_DBG")) : -1;
+    return v;
+}
+static long long *tc_debug_buffer() {
+    static long long *buf = nullptr;
+    if (tc_debug_cta() < 0) return nullptr;
+    if (!buf) {
+        if (cudaMalloc(&buf, 128 * sizeof(long long)) != cudaSuccess) return nullptr;
+        cudaMemset(buf, 0, 128 * sizeof(long long));
+    }
+    return buf;
 }
 
 static inline size_t conv_tc_wsplit_floats(const b2rl_layer &l) {
@@ -566,6 +598,7 @@ static int launch_conv_fwd_tc(const b2rl_layer &l, const Operand &A, const float
     p.KK = KK; p.KS = l.ksize; p.HW = l.in_h * l.in_w; p.W = l.in_w;
     p.act = l.act; p.normalize = A.normalize; p.low = A.normalize ? A.low : 0.f; p.high = A.normalize ? A.high : 1.f;
     p.pad = 0; p.IH = l.in_h; p.cls_s = 1; p.out_H = l.out_h; p.out_W = l.out_w; p.w_class_stride = 0;
+    p.dbg = tc_debug_buffer(); p.dbg_cta = tc_debug_cta();
     // 4 consecutive taps are 4 contiguous, 4-byte aligned bytes when the kernel width, the column
     // stride, the row pitch and the plane / image sizes are all multiples of 4
     bool vec;
@@ -687,6 +720,7 @@ static int launch_conv_dgrad_tc(const b2rl_layer &l, const float *g, const float
     p.act = B2RL_ACT_NONE; p.normalize = 0; p.low = 0.f; p.high = 1.f;
     p.pad = T - 1; p.IH = l.out_h; p.cls_s = S; p.out_H = l.in_h; p.out_W = l.in_w;
     p.w_class_stride = (int64_t)cls_floats;
+    p.dbg = nullptr; p.dbg_cta = -1;
     if (tc_persist_enabled()) {
         const int rcp = launch_conv_persist(conv_fwd_tc_persist_kernel<EL_F32, false, false, 2, true, 2>, p, S * S,
                                             conv_tc_persist_smem_bytes(n_pad, k_pad, 2, 2), s);

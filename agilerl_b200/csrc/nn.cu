@@ -1538,6 +1538,15 @@ int b2rl_dqn_learn(const b2rl_net_desc *net_host, const b2rl_learn_cfg *cfg_host
 }
 
 
+int b2rl_debug_read(long long *out_host, int n) {
+    long long *buf = tc_debug_buffer();
+    B2RL_CHECK_ARG(out_host && n >= 1 && n <= 128, "bad debug read");
+    B2RL_CHECK_ARG(buf != nullptr, "diagnostics are off (set B2RL_TC_DBG=<cta>)");
+    B2RL_CUDA(cudaDeviceSynchronize());
+    B2RL_CUDA(cudaMemcpy(out_host, buf, sizeof(long long) * n, cudaMemcpyDeviceToHost));
+    return B2RL_OK;
+}
+
 int b2rl_encoder_layer_forward(const b2rl_net_desc *net_host, int layer, const float *params, const void *input,
                                const int64_t *row_idx, int64_t rows, float *out, void *workspace,
                                size_t workspace_bytes, void *stream) {

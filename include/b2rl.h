@@ -192,6 +192,11 @@ int b2rl_net_forward_q(const b2rl_net_desc *net_host, const float *params, const
                        const int64_t *row_idx, int64_t rows, float *q_out, int64_t *argmax_out,
                        void *workspace, size_t workspace_bytes, void *stream);
 
+/* Diagnostics: with B2RL_TC_DBG=<cta> in the environment the tensor-core forward convolution records
+ * clock64() stamps of that CTA's producer warp 0 (slots 0..63) and MMA lane (slots 64..127); this copies the
+ * first n (<= 128) to the host after a device synchronize.  Fails when diagnostics are off. */
+int b2rl_debug_read(long long *out_host, int n);
+
 /* Forward of ONE encoder layer (profiling / roofline hook: lets bench.py time the dominant
  * contraction alone with CUDA events).  layer 0 reads observations (obs/row_idx as above), layer
  * i>0 reads `input` = the previous layer's [rows, ...] fp32 activations.  out: rows x out elems. */
