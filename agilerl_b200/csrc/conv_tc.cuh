@@ -151,7 +151,8 @@ constexpr int kTcBM = 128;      // pixels per CTA (UMMA M)
 constexpr int kTcBK = 32;       // k per stage (4 MMA k-steps of 8)
 constexpr int kTcStages = 2;    // operand stages of the weight-gradient kernel (both tiles thread-built)
 constexpr int kTcBStages = 4;   // forward: B-operand ring (bulk-copied by the TMA unit, two k-blocks ahead)
-constexpr int kTcThreads = 256; // two threads per im2col row (16 k each per stage)
+constexpr int kTcThreads = 256; // producers: two threads per im2col row (16 k each per stage)
+constexpr int kTcFwdThreads = kTcThreads + 64;   // forward kernel: + MMA warp + weight-copy warp
 
 struct ConvTcParams {
     const void *x;              // input: uint8 frames / fp32 activations (NCHW)
@@ -180,7 +181,7 @@ struct ConvTcParams {
 
 static inline size_t conv_tc_smem_bytes(int n_pad, int k_pad, int a_parts = 2, int a_stages = 2, int b_stages = kTcBStages) {
     const size_t a = (size_t)kTcBM * kTcBK * 4, b = (size_t)n_pad * kTcBK * 4;
-    return a_stages * a_parts * a + b_stages * 2 * b + (size_t)k_pad * 4 + 256 * 4 + (size_t)n_pad * 4 + 192 + 1024;
+    return a_stages * a_parts * a + b_stages * 2 * b + (size_t)k_pad * 4 + 256 * 4 + (size_t)n_pad * 4 + 256 + 1024;
 }
 
 // Split W [N, K] into tf32 hi / lo and store it in the order the conv kernel's B tiles use:
@@ -242,7 +243,7 @@ static int ensure_big_smem(Kern kern) {
 // SB: slots of the weight-tile ring; tiles are requested SB-2 k-blocks ahead (a bulk copy takes on the
 // order of a microsecond to land — more than one k-block of work)
 template <int ELEM, bool EXACT_A, bool VEC, int D, bool PAD = false, int SA = 2, int SB = kTcBStages>
-__global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const ConvTcParams p) {
+__global__ void __launch_bounds__(kTcFwdThreads) conv_fwd_tc_kernel(const ConvTcParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     constexpr int RAWN = (ELEM == EL_U8 && VEC) ? 4 : 16;      // raw words per thread per k-block
     constexpr int CH = kTcBK / 4 / 2;                          // 4-tap chunks per thread per k-block (4)
@@ -262,11 +263,12 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const Conv
     const uint32_t lut_a = koff_a + (uint32_t)p.k_pad * 4;
     const uint32_t bias_a = lut_a + 256 * 4;
     const uint32_t bars_a = (bias_a + (uint32_t)p.n_pad * 4 + 15u) & ~15u;
-    const uint32_t tptr_a = bars_a + 8 * (2 * SA + SB);
+    const uint32_t tptr_a = bars_a + 8 * (2 * SA + 2 * SB);
     uint8_t *gen = smem_raw + (sbase - tc::smem_u32(smem_raw));        // generic alias of sbase (barriers only)
     uint64_t *mma_bar = reinterpret_cast<uint64_t *>(gen + (bars_a - sbase));   // [SA] MMA group done
     uint64_t *full_a = mma_bar + SA;                                     // [SA] im2col tile written
     uint64_t *full_b = full_a + SA;                                      // [SB] weight tile landed
+    uint64_t *empty_b = full_b + SB;                                     // [SB] weight tile consumed (MMAs retired)
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(gen + (tptr_a - sbase));
     const int KB = p.k_pad / kTcBK;
     // diagnostics: time stamps of producer warp 0 (slots 0..) and of the MMA lane (slots 64..) of one CTA
@@ -280,7 +282,10 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const Conv
             tc::mbar_init(&mma_bar[s], 1);
             tc::mbar_init(&full_a[s], kTcThreads / 32);      // one elected arrive per producer warp
         }
-        for (int s = 0; s < SB; ++s) tc::mbar_init(&full_b[s], 1);
+        for (int s = 0; s < SB; ++s) {
+            tc::mbar_init(&full_b[s], 1);
+            tc::mbar_init(&empty_b[s], 1);
+        }
         tc::fence_barrier_init();
     }
     // MMA group j (k-block j) has retired: its A stage and its B ring slot may be overwritten
@@ -292,14 +297,14 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const Conv
         tc::bulk_g2s(b_hi(sb), p.w_hi + wo, b_bytes, &full_b[sb]);
         tc::bulk_g2s(b_lo(sb), p.w_lo + wo, b_bytes, &full_b[sb]);
     };
-    for (int k = tid; k < p.k_pad; k += kTcThreads + 32)
+    for (int k = tid; k < p.k_pad; k += kTcFwdThreads)
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(koff_a + 4u * k), "r"(__ldg(p.koff + k)) : "memory");
     if (ELEM == EL_U8 && !EXACT_A)
-        for (int i = tid; i < 256; i += kTcThreads + 32) {
+        for (int i = tid; i < 256; i += kTcFwdThreads) {
             const float v = p.normalize ? __fdiv_rn((float)i - p.low, p.high - p.low) : (float)i;
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(lut_a + 4u * i), "f"(v) : "memory");
         }
-    for (int n = tid; n < p.n_pad; n += kTcThreads + 32) {
+    for (int n = tid; n < p.n_pad; n += kTcFwdThreads) {
         const float v = (n < p.N && p.bias) ? p.bias[n] : 0.f;
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_a + 4u * n), "f"(v) : "memory");
     }
@@ -314,21 +319,28 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const Conv
     const uint32_t idesc = tc::make_idesc_tf32(kTcBM, p.n_pad);
     const uint32_t lbo_a = kTcBM * 16, lbo_b = (uint32_t)p.n_pad * 16;
 
-    if (warp == kTcThreads / 32) {
-        // ---- MMA warp.  The whole warp runs the loop converged (waits, descriptor arithmetic stay in the
-        // uniform datapath); one elected lane issues the copies, the MMAs and the commit.
+    if (warp == kTcThreads / 32 + 1) {
+        // ---- weight-copy warp: keeps the TMA ring SB-2 k-blocks ahead, so that requesting a tile (an
+        // expect_tx and two bulk copies, a few hundred cycles of issue latency) is off the MMA lane's path
         if (tc::elect_one()) {
             for (int j = 0; j < SB - 2 && j < KB; ++j) issue_b(j);
         }
         __syncwarp();
+        for (int kb = 0; kb + SB - 2 < KB; ++kb) {
+            // ring slot (kb+SB-2)%SB was last read by MMA group kb-2.  Its own "consumed" barrier, not the
+            // A-stage barrier: the next completion on this slot needs the copy issued right here, so this
+            // warp can never fall a whole phase behind the barrier it polls.
+            if (kb >= 2) tc::mbar_wait(&empty_b[(kb - 2) % SB], (uint32_t)(((kb - 2) / SB) & 1));
+            if (tc::elect_one()) issue_b(kb + SB - 2);
+            __syncwarp();
+        }
+    }
+    if (warp == kTcThreads / 32) {
+        // ---- MMA warp.  The whole warp runs the loop converged (waits, descriptor arithmetic stay in the
+        // uniform datapath); one elected lane issues the copies, the MMAs and the commit.
         const uint64_t da_step = (uint64_t)((2 * lbo_a) >> 4), db_step = (uint64_t)((2 * lbo_b) >> 4);
         for (int kb = 0; kb < KB; ++kb) {
             const int s = kb % SA, sb = kb & (SB - 1);
-            if (kb + SB - 2 < KB) {
-                if (kb >= 2) wait_mma(kb - 2);          // ring slot (kb+SB-2)%SB was last read by MMA group kb-2
-                if (tc::elect_one()) issue_b(kb + SB - 2);
-                __syncwarp();
-            }
             tc::mbar_wait(&full_b[sb], (uint32_t)((kb / SB) & 1));
             if ((tid & 31) == 0 && kb < 16) stamp(64 + 3 * kb);
             tc::mbar_wait(&full_a[s], (uint32_t)((kb / SA) & 1));
@@ -345,6 +357,7 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const Conv
                     tc::mma_tf32(tmem_d, dah0 + j * da_step, dbl0 + j * db_step, idesc, 1u);
                 }
                 tc::mma_commit(&mma_bar[s]);
+                tc::mma_commit(&empty_b[sb]);
             }
             if ((tid & 31) == 0 && kb < 16) stamp(66 + 3 * kb);
             __syncwarp();
@@ -394,11 +407,12 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_fwd_tc_kernel(const Conv
                 dst[c * 4 + 2] = __float_as_uint(b.x); dst[c * 4 + 3] = __float_as_uint(b.y);
             }
         } else if (ELEM == EL_U8 && VEC) {
+            // offsets first, loads second: the shared-memory reads pipeline instead of each one gating its load
 #pragma unroll
-            for (int c = 0; c < CH; ++c) {
-                const uint32_t off = tc::lds32(koff_a + 4u * (k0 + c * 4));
-                dst[c] = __ldg(reinterpret_cast<const uint32_t *>(row_u8 + off));   // 4 packed taps
-            }
+            for (int c = 0; c < CH; ++c) dst[c] = tc::lds32(koff_a + 4u * (k0 + c * 4));
+#pragma unroll
+            for (int c = 0; c < CH; ++c)
+                dst[c] = __ldg(reinterpret_cast<const uint32_t *>(row_u8 + dst[c]));   // 4 packed taps
         } else {
 #pragma unroll
             for (int j = 0; j < CH * 4; ++j) {
@@ -611,7 +625,7 @@ static int launch_conv_fwd_tc(const b2rl_layer &l, const Operand &A, const float
     const int grid = (p.M + kTcBM - 1) / kTcBM;
     auto launch = [&](auto kern) -> int {
         { const int rca = ensure_big_smem(kern); if (rca != B2RL_OK) return rca; }
-        kern<<<grid, kTcThreads + 32, smem, s>>>(p);
+        kern<<<grid, kTcFwdThreads, smem, s>>>(p);
         B2RL_LAUNCH_CHECK();
         return B2RL_OK;
     };
@@ -728,7 +742,7 @@ static int launch_conv_dgrad_tc(const b2rl_layer &l, const float *g, const float
     }
     auto kern = conv_fwd_tc_kernel<EL_F32, false, false, 2, true>;
     { const int rca = ensure_big_smem(kern); if (rca != B2RL_OK) return rca; }
-    kern<<<dim3((unsigned)((p.M + kTcBM - 1) / kTcBM), S * S), kTcThreads + 32, smem, s>>>(p);
+    kern<<<dim3((unsigned)((p.M + kTcBM - 1) / kTcBM), S * S), kTcFwdThreads, smem, s>>>(p);
     B2RL_LAUNCH_CHECK();
     return B2RL_OK;
 }
