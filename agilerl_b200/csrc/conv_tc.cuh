@@ -184,8 +184,11 @@ static inline size_t conv_tc_smem_bytes(int n_pad, int k_pad, int a_parts = 2, i
     return a_stages * a_parts * a + b_stages * 2 * b + (size_t)k_pad * 4 + 256 * 4 + (size_t)n_pad * 4 + 256 + 1024;
 }
 
-// Split W [N, K] into tf32 hi / lo and store it in the order the conv kernel's B tiles use:
-//   [k-block][chunk c = (k%32)/4][n/8][n%8][k%4]   (n_pad * 32 floats per k-block, zero padded)
+// Split W [N, K] into tf32 hi / lo and store it in the order the conv kernel's B tiles use: one
+// [2*n_pad rows x 32 k] tile per k-block whose rows 0..n_pad-1 are the hi parts and n_pad..2*n_pad-1 the
+// lo parts, so that ONE tcgen05.mma with N = 2*n_pad multiplies an im2col k-step with both:
+//   [k-block][chunk c = (k%32)/4][part (hi, lo)][n/8][n%8][k%4]   (2 * n_pad * 32 floats per k-block, zero padded)
+// (w_hl is the whole array; the unused w_lo argument is kept for the call sites)
 __global__ void weight_split_kernel(const float *__restrict__ w, int N, int K, int n_pad, int k_pad,
                                     float *__restrict__ w_hi, float *__restrict__ w_lo, int KK, int KS, int HW, int W,
                                     uint32_t *__restrict__ koff) {
@@ -195,9 +198,9 @@ __global__ void weight_split_kernel(const float *__restrict__ w, int N, int K, i
         const float v = (n < N && k < K) ? w[(int64_t)n * K + k] : 0.f;
         const float hi = tc::tf32_rn(v);
         const int kb = k / kTcBK, kin = k - kb * kTcBK;
-        const int64_t o = (int64_t)kb * n_pad * kTcBK + (int64_t)(kin >> 2) * n_pad * 4 + (n >> 3) * 32 + (n & 7) * 4 + (kin & 3);
+        const int64_t o = (int64_t)kb * 2 * n_pad * kTcBK + (int64_t)(kin >> 2) * 2 * n_pad * 4 + (n >> 3) * 32 + (n & 7) * 4 + (kin & 3);
         w_hi[o] = hi;
-        w_lo[o] = v - hi;
+        w_hi[o + (int64_t)n_pad * 4] = v - hi;
         if (n == 0 && koff) {      // input offset of tap k = (ci, ky, kx); padded taps read offset 0 against zero weights
             uint32_t off = 0;
             if (k < K) {
@@ -293,9 +296,8 @@ __global__ void __launch_bounds__(kTcFwdThreads) conv_fwd_tc_kernel(const ConvTc
     auto issue_b = [&](int kb) {       // elected thread: weight tile of k-block kb -> its ring slot
         const int sb = kb & (SB - 1);
         tc::mbar_expect_tx(&full_b[sb], 2 * b_bytes);
-        const int64_t wo = (PAD ? (int64_t)blockIdx.y * p.w_class_stride : 0) + (int64_t)kb * p.n_pad * kTcBK;
-        tc::bulk_g2s(b_hi(sb), p.w_hi + wo, b_bytes, &full_b[sb]);
-        tc::bulk_g2s(b_lo(sb), p.w_lo + wo, b_bytes, &full_b[sb]);
+        const int64_t wo = (PAD ? (int64_t)blockIdx.y * p.w_class_stride : 0) + (int64_t)kb * 2 * p.n_pad * kTcBK;
+        tc::bulk_g2s(b_hi(sb), p.w_hi + wo, 2 * b_bytes, &full_b[sb]);          // hi|lo tile, one copy
     };
     for (int k = tid; k < p.k_pad; k += kTcFwdThreads)
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(koff_a + 4u * k), "r"(__ldg(p.koff + k)) : "memory");
@@ -308,16 +310,17 @@ __global__ void __launch_bounds__(kTcFwdThreads) conv_fwd_tc_kernel(const ConvTc
         const float v = (n < p.N && p.bias) ? p.bias[n] : 0.f;
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_a + 4u * n), "f"(v) : "memory");
     }
-    uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < p.n_pad) tmem_cols <<= 1;
+    uint32_t tmem_cols = 32;                                   // D = [A.W_hi | A.W_lo]: 2*n_pad columns
+    while ((int)tmem_cols < 2 * p.n_pad) tmem_cols <<= 1;
     if (warp == 0) tc::tmem_alloc(tmem_ptr, tmem_cols);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     if (tid == 0) stamp(1);
     const uint32_t tmem_d = *tmem_ptr;
-    const uint32_t idesc = tc::make_idesc_tf32(kTcBM, p.n_pad);
-    const uint32_t lbo_a = kTcBM * 16, lbo_b = (uint32_t)p.n_pad * 16;
+    const uint32_t idesc2 = tc::make_idesc_tf32(kTcBM, 2 * p.n_pad);      // A_hi x [W_hi; W_lo]
+    const uint32_t idesc1 = tc::make_idesc_tf32(kTcBM, p.n_pad);          // A_lo x W_hi
+    const uint32_t lbo_a = kTcBM * 16, lbo_b = (uint32_t)p.n_pad * 2 * 16;   // a 4-tap chunk holds hi rows, then lo rows
 
     if (warp == kTcThreads / 32 + 1) {
         // ---- weight-copy warp: keeps the TMA ring SB-2 k-blocks ahead, so that requesting a tile (an
@@ -348,13 +351,13 @@ __global__ void __launch_bounds__(kTcFwdThreads) conv_fwd_tc_kernel(const ConvTc
             tc::tc_fence_after();
             // descriptors of consecutive k-steps differ only in the 14-bit start-address field
             const uint64_t dah0 = tc::make_desc(a_hi(s), lbo_a, 128), dal0 = tc::make_desc(a_lo(s), lbo_a, 128);
-            const uint64_t dbh0 = tc::make_desc(b_hi(sb), lbo_b, 128), dbl0 = tc::make_desc(b_lo(sb), lbo_b, 128);
+            const uint64_t db0 = tc::make_desc(b_hi(sb), lbo_b, 128);
             if (tc::elect_one()) {
 #pragma unroll
                 for (int j = 0; j < kTcBK / 8; ++j) {      // one MMA k-step = 8 tf32 = 2 core-matrix columns
-                    tc::mma_tf32(tmem_d, dah0 + j * da_step, dbh0 + j * db_step, idesc, (kb | j) ? 1u : 0u);
-                    if (!EXACT_A) tc::mma_tf32(tmem_d, dal0 + j * da_step, dbh0 + j * db_step, idesc, 1u);
-                    tc::mma_tf32(tmem_d, dah0 + j * da_step, dbl0 + j * db_step, idesc, 1u);
+                    // columns [0, n_pad) += A_hi.W_hi (+ A_lo.W_hi), columns [n_pad, 2 n_pad) += A_hi.W_lo
+                    tc::mma_tf32(tmem_d, dah0 + j * da_step, db0 + j * db_step, idesc2, (kb | j) ? 1u : 0u);
+                    if (!EXACT_A) tc::mma_tf32(tmem_d, dal0 + j * da_step, db0 + j * db_step, idesc1, 1u);
                 }
                 tc::mma_commit(&mma_bar[s]);
                 tc::mma_commit(&empty_b[sb]);
@@ -502,8 +505,11 @@ __global__ void __launch_bounds__(kTcFwdThreads) conv_fwd_tc_kernel(const ConvTc
         const float scale = (EXACT_A && p.normalize) ? 1.0f / (p.high - p.low) : 1.0f;
         const int oP = (int)out_P;
         for (int c0 = (warp >> 2) * 16; c0 < p.n_pad; c0 += 32) {
-            uint32_t r[16];
+            uint32_t r[16], r2[16];
             tc::tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            tc::tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.n_pad + c0), r2);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
             if (e_ok) {
                 const int nv = min(16, p.N - c0);
                 float v[16];
@@ -587,7 +593,7 @@ static int launch_conv_fwd_tc(const b2rl_layer &l, const Operand &A, const float
                               bool reuse_split = false) {   // reuse_split: wsplit still holds this layer's split weights
     const int KK = l.ksize * l.ksize, K = l.in_c * KK, P = l.out_h * l.out_w;
     const int n_pad = (l.out_c + 15) / 16 * 16, k_pad = (K + kTcBK - 1) / kTcBK * kTcBK;
-    if (n_pad > 256 || k_pad > 8192 || rows * (int64_t)P > INT32_MAX) return 1;
+    if (n_pad > 128 || k_pad > 8192 || rows * (int64_t)P > INT32_MAX) return 1;    // one MMA spans 2*n_pad <= 256 columns
     const bool exact = A.u8 && (!A.normalize || (A.low == floorf(A.low) && fabsf(A.low) <= 1024.f));
     static const int sa_exact = getenv("B2RL_TC_SA") ? atoi(getenv("B2RL_TC_SA")) : 2;
     static const int sb_exact = getenv("B2RL_TC_SB") ? atoi(getenv("B2RL_TC_SB")) : 4;
@@ -596,7 +602,7 @@ static int launch_conv_fwd_tc(const b2rl_layer &l, const Operand &A, const float
     const size_t smem = conv_tc_smem_bytes(n_pad, k_pad, exact ? 1 : 2, deep ? 3 : 2, wide_b ? 8 : kTcBStages);
     if (smem > 200 * 1024 || wsplit == nullptr || conv_tc_wsplit_floats(l) > wsplit_cap) return 1;
     if (reinterpret_cast<uintptr_t>(wsplit) % 16 != 0) return 1;          // bulk copies need 16-byte aligned sources
-    float *w_hi = wsplit, *w_lo = wsplit + (size_t)n_pad * k_pad;
+    float *w_hi = wsplit, *w_lo = nullptr;                 // one interleaved hi|lo array
     uint32_t *koff = reinterpret_cast<uint32_t *>(wsplit + (size_t)2 * n_pad * k_pad);
     if (!reuse_split) {
         const int total = n_pad * k_pad;
@@ -676,7 +682,7 @@ __global__ void dgrad_weight_split_kernel(const float *__restrict__ w, int Cout,
                                           float *__restrict__ w_lo, uint32_t *__restrict__ koff) {
     const int cls = blockIdx.y, py = cls / S, px = cls % S;
     const int K = Cout * T * T, total = n_pad * k_pad;
-    float *hi_c = w_hi + (int64_t)cls * total, *lo_c = w_lo + (int64_t)cls * total;
+    float *hl_c = w_hi + (int64_t)cls * 2 * total;          // [2*n_pad x k_pad] hi|lo tiles of this class
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         const int k = e / n_pad, n = e - k * n_pad;          // k = (co, a', b'), n = ci
         float v = 0.f;
@@ -690,9 +696,9 @@ __global__ void dgrad_weight_split_kernel(const float *__restrict__ w, int Cout,
         }
         const float hi = tc::tf32_rn(v);
         const int kb = k / kTcBK, kin = k - kb * kTcBK;
-        const int64_t o = (int64_t)kb * n_pad * kTcBK + (int64_t)(kin >> 2) * n_pad * 4 + (n >> 3) * 32 + (n & 7) * 4 + (kin & 3);
-        hi_c[o] = hi;
-        lo_c[o] = v - hi;
+        const int64_t o = (int64_t)kb * 2 * n_pad * kTcBK + (int64_t)(kin >> 2) * 2 * n_pad * 4 + (n >> 3) * 32 + (n & 7) * 4 + (kin & 3);
+        hl_c[o] = hi;
+        hl_c[o + (int64_t)n_pad * 4] = v - hi;
         if (n == 0 && cls == 0)
             koff[k] = k < K ? ((uint32_t)(co * in_plane + a * in_w + b) | ((uint32_t)a << 24) | ((uint32_t)b << 28)) : 0u;
     }
@@ -714,13 +720,13 @@ static int launch_conv_dgrad_tc(const b2rl_layer &l, const float *g, const float
     const int n_pad = (l.in_c + 15) / 16 * 16, k_pad = (K + kTcBK - 1) / kTcBK * kTcBK;
     const int Yc = (l.in_h + S - 1) / S, Xc = (l.in_w + S - 1) / S;
     const int64_t M = rows * Yc * Xc;
-    if (n_pad > 256 || k_pad > 8192 || M > INT32_MAX || T > 15 || S * S > 64) return 1;
+    if (n_pad > 128 || k_pad > 8192 || M > INT32_MAX || T > 15 || S * S > 64) return 1;
     if ((int64_t)l.out_c * l.out_h * l.out_w >= (1 << 24)) return 1;        // offset field of the tap table
     const size_t smem = conv_tc_smem_bytes(n_pad, k_pad, 2);
     if (smem > 200 * 1024 || scratch == nullptr || conv_dgrad_tc_scratch_floats(l) > scratch_cap) return 1;
     if (reinterpret_cast<uintptr_t>(scratch) % 16 != 0) return 1;
     const size_t cls_floats = (size_t)n_pad * k_pad;
-    float *w_hi = scratch, *w_lo = scratch + (size_t)S * S * cls_floats;
+    float *w_hi = scratch, *w_lo = nullptr;                // per class: one interleaved hi|lo array of 2*cls_floats
     uint32_t *koff = reinterpret_cast<uint32_t *>(scratch + (size_t)2 * S * S * cls_floats);
     dgrad_weight_split_kernel<<<dim3((unsigned)((cls_floats + 255) / 256), S * S), 256, 0, s>>>(
         W, l.out_c, l.in_c, l.ksize, S, T, n_pad, k_pad, l.out_h * l.out_w, l.out_w, w_hi, w_lo, koff);
@@ -733,7 +739,7 @@ static int launch_conv_dgrad_tc(const b2rl_layer &l, const float *g, const float
     p.KK = T * T; p.KS = T; p.HW = l.out_h * l.out_w; p.W = l.out_w;
     p.act = B2RL_ACT_NONE; p.normalize = 0; p.low = 0.f; p.high = 1.f;
     p.pad = T - 1; p.IH = l.out_h; p.cls_s = S; p.out_H = l.in_h; p.out_W = l.in_w;
-    p.w_class_stride = (int64_t)cls_floats;
+    p.w_class_stride = (int64_t)2 * cls_floats;
     p.dbg = nullptr; p.dbg_cta = -1;
     if (tc_persist_enabled()) {
         const int rcp = launch_conv_persist(conv_fwd_tc_persist_kernel<EL_F32, false, false, 2, true, 2>, p, S * S,

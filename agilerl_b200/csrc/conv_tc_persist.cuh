@@ -83,15 +83,15 @@ __global__ void __launch_bounds__(kPsThreads) conv_fwd_tc_persist_kernel(const C
         const float v = (n < p.N && p.bias) ? p.bias[n] : 0.f;
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_a + 4u * n), "f"(v) : "memory");
     }
-    uint32_t acc_cols = 32;                                    // columns of one accumulator
-    while ((int)acc_cols < p.n_pad) acc_cols <<= 1;
+    uint32_t acc_cols = 32;                                    // columns of one accumulator: [A.W_hi | A.W_lo]
+    while ((int)acc_cols < 2 * p.n_pad) acc_cols <<= 1;
     if (warp == 0) tc::tmem_alloc(tmem_ptr, 2 * acc_cols);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_d = *tmem_ptr;
-    const uint32_t idesc = tc::make_idesc_tf32(kTcBM, p.n_pad);
-    const uint32_t lbo_a = kTcBM * 16, lbo_b = (uint32_t)p.n_pad * 16;
+    const uint32_t idesc2 = tc::make_idesc_tf32(kTcBM, 2 * p.n_pad), idesc1 = tc::make_idesc_tf32(kTcBM, p.n_pad);
+    const uint32_t lbo_a = kTcBM * 16, lbo_b = (uint32_t)p.n_pad * 2 * 16;
     // k-block g used A stage g % SA for the (g / SA)-th time
     auto wait_mma = [&](int g) { tc::mbar_wait(&mma_bar[g % SA], (uint32_t)((g / SA) & 1)); };
 
@@ -100,12 +100,11 @@ __global__ void __launch_bounds__(kPsThreads) conv_fwd_tc_persist_kernel(const C
         int bg = 0, b_it = 0, b_kb = 0;                    // cursor of the weight-tile copies
         auto issue_b_next = [&]() {
             const int sb = bg & (kTcBStages - 1);
-            int64_t wo = (int64_t)b_kb * p.n_pad * kTcBK;
+            int64_t wo = (int64_t)b_kb * 2 * p.n_pad * kTcBK;
             if (PAD) wo += (int64_t)(((int)blockIdx.x + b_it * (int)gridDim.x) / mtiles) * p.w_class_stride;
             if (tc::elect_one()) {
                 tc::mbar_expect_tx(&full_b[sb], 2 * b_bytes);
-                tc::bulk_g2s(b_hi(sb), p.w_hi + wo, b_bytes, &full_b[sb]);
-                tc::bulk_g2s(b_lo(sb), p.w_lo + wo, b_bytes, &full_b[sb]);
+                tc::bulk_g2s(b_hi(sb), p.w_hi + wo, 2 * b_bytes, &full_b[sb]);      // hi|lo tile, one copy
             }
             __syncwarp();
             ++bg;
@@ -130,13 +129,12 @@ __global__ void __launch_bounds__(kPsThreads) conv_fwd_tc_persist_kernel(const C
                 tc::mbar_wait(&full_a[s], (uint32_t)((g / SA) & 1));
                 tc::tc_fence_after();
                 const uint64_t dah0 = tc::make_desc(a_hi(s), lbo_a, 128), dal0 = tc::make_desc(a_lo(s), lbo_a, 128);
-                const uint64_t dbh0 = tc::make_desc(b_hi(sb), lbo_b, 128), dbl0 = tc::make_desc(b_lo(sb), lbo_b, 128);
+                const uint64_t db0 = tc::make_desc(b_hi(sb), lbo_b, 128);
                 if (tc::elect_one()) {
 #pragma unroll
                     for (int j = 0; j < kTcBK / 8; ++j) {      // one MMA k-step = 8 tf32 = 2 core-matrix columns
-                        tc::mma_tf32(tacc, dah0 + j * da_step, dbh0 + j * db_step, idesc, (kb | j) ? 1u : 0u);
-                        if (!EXACT_A) tc::mma_tf32(tacc, dal0 + j * da_step, dbh0 + j * db_step, idesc, 1u);
-                        tc::mma_tf32(tacc, dah0 + j * da_step, dbl0 + j * db_step, idesc, 1u);
+                        tc::mma_tf32(tacc, dah0 + j * da_step, db0 + j * db_step, idesc2, (kb | j) ? 1u : 0u);
+                        if (!EXACT_A) tc::mma_tf32(tacc, dal0 + j * da_step, db0 + j * db_step, idesc1, 1u);
                     }
                     tc::mma_commit(&mma_bar[s]);
                 }
@@ -288,8 +286,11 @@ __global__ void __launch_bounds__(kPsThreads) conv_fwd_tc_persist_kernel(const C
             tc::mbar_wait(&acc_full[buf], (uint32_t)((it >> 1) & 1));
             tc::tc_fence_after();
             for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
-                uint32_t r[16];
+                uint32_t r[16], r2[16];
                 tc::tmem_ld16(tmem_d + (uint32_t)buf * acc_cols + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+                tc::tmem_ld16(tmem_d + (uint32_t)buf * acc_cols + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.n_pad + c0), r2);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
                 if (e_ok) {
                     const int nv = min(16, p.N - c0);
                     float v[16];
