@@ -344,10 +344,82 @@ def gen_tournament():
     print("  tournament: oracle == reference")
 
 
+def gen_ddpg_td3():
+    """SURVEY §8(f) rank 1 groundwork: DDPG / TD3 learn() of BASELINE config 3's shapes (17-dim obs, 6-dim
+    action) — four consecutive learn calls (actor + targets move on calls 2 and 4), oracle == reference
+    bit for bit; the fixture keeps the initial state dicts, the batches, the RNG seeds of the in-place
+    target-policy noise, and the reference's losses + final parameters."""
+    from agilerl.algorithms.ddpg import DDPG
+    from agilerl.algorithms.td3 import TD3
+    from oracle import ddpg_td3 as od
+    obs_space = spaces.Box(-1, 1, (17,), np.float32)
+    act_space = spaces.Box(-1, 1, (6,), np.float32)
+    B, steps = 32, 4
+
+    def batch(seed):
+        g = torch.Generator().manual_seed(seed)
+        return dict(obs=torch.randn(B, 17, generator=g), action=torch.rand(B, 6, generator=g) * 2 - 1,
+                    reward=torch.randn(B, 1, generator=g), next_obs=torch.randn(B, 17, generator=g),
+                    done=(torch.rand(B, 1, generator=g) < 0.2).float())
+
+    for name, cls, twin in (("ddpg", DDPG, False), ("td3", TD3, True)):
+        torch.manual_seed(7)
+        ref = cls(obs_space, act_space, batch_size=B, device="cpu")
+        crit = [ref.critic] if not twin else [ref.critic_1, ref.critic_2]
+        crit_t = [ref.critic_target] if not twin else [ref.critic_target_1, ref.critic_target_2]
+        a_hidden = list(ref.actor.head_net.net_config["hidden_size"])
+        c_hidden = list(crit[0].head_net.net_config["hidden_size"])
+        a_specs = od.actor_specs(17, 6, head_hidden=a_hidden, encoder_layer_norm=ref.actor.encoder.net_config["layer_norm"])
+        c_specs = od.critic_specs(17, 6, head_hidden=c_hidden)
+        out = {"B": B, "steps": steps, "twin": int(twin), "a_hidden": np.array(a_hidden), "c_hidden": np.array(c_hidden),
+               "gamma": ref.gamma, "tau": ref.tau, "lr_actor": ref.lr_actor, "lr_critic": ref.lr_critic,
+               "policy_freq": ref.policy_freq}
+        out.update({f"actor0/{k}": v for k, v in sd_np(ref.actor.state_dict()).items()})
+        out.update({f"actor_target0/{k}": v for k, v in sd_np(ref.actor_target.state_dict()).items()})
+        for i, (c, t) in enumerate(zip(crit, crit_t)):
+            out.update({f"critic{i}_0/{k}": v for k, v in sd_np(c.state_dict()).items()})
+            out.update({f"critic_target{i}_0/{k}": v for k, v in sd_np(t.state_dict()).items()})
+        orc = od.OracleDDPG(a_specs, c_specs, ref.actor.state_dict(), ref.actor_target.state_dict(),
+                            [c.state_dict() for c in crit], [c.state_dict() for c in crit_t], gamma=ref.gamma, tau=ref.tau,
+                            lr_actor=ref.lr_actor, lr_critic=ref.lr_critic, policy_freq=ref.policy_freq, twin=twin)
+        for st in range(steps):
+            e_ref, e_orc = batch(40 + st), batch(40 + st)
+            for k, v in e_ref.items():
+                out[f"s{st}_{k}"] = v.numpy().copy()
+            out[f"s{st}_seed"] = 500 + st
+            torch.manual_seed(500 + st)
+            ra, rc = ref.learn(TensorDict(e_ref, batch_size=[B]))
+            torch.manual_seed(500 + st)
+            oa, oc = orc.learn(e_orc)
+            assert ra == oa and rc == oc, (name, st, ra, oa, rc, oc)
+            out[f"s{st}_noise"] = e_ref["action"].numpy().copy()          # the batch's action tensor now holds the noise
+            out[f"s{st}_actor_loss"] = np.nan if ra is None else ra
+            out[f"s{st}_critic_loss"] = rc
+        for k, v in ref.actor.state_dict().items():
+            assert torch.equal(v, orc.actor[k].data), (name, k)
+        for c, ocr in zip(crit, orc.critics):
+            for k, v in c.state_dict().items():
+                assert torch.equal(v, ocr[k].data), (name, k)
+        for c, oct_ in zip(crit_t, orc.critic_targets):
+            for k, v in c.state_dict().items():
+                assert torch.equal(v, oct_[k]), (name, k)
+        out.update({f"actor1/{k}": v for k, v in sd_np(ref.actor.state_dict()).items()})
+        out.update({f"actor_target1/{k}": v for k, v in sd_np(ref.actor_target.state_dict()).items()})
+        for i, (c, t) in enumerate(zip(crit, crit_t)):
+            out.update({f"critic{i}_1/{k}": v for k, v in sd_np(c.state_dict()).items()})
+            out.update({f"critic_target{i}_1/{k}": v for k, v in sd_np(t.state_dict()).items()})
+        save(f"{name}_vector.npz", **out)
+        print(f"  {name}: oracle == reference over {steps} learn calls (losses, every parameter, targets)")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)   # deterministic CPU reductions while generating
+    if len(sys.argv) > 1 and sys.argv[1] == "ddpg_td3":
+        gen_ddpg_td3()
+        sys.exit(0)
     gen_tree()
     gen_replay()
     gen_rainbow()
     gen_dqn()
     gen_tournament()
+    gen_ddpg_td3()
