@@ -125,7 +125,12 @@ class TensorDict(TensorDictBase):
             self._data[index] = _as_tensor(value)
             return
         if isinstance(value, (TensorDict, Mapping)):
-            for k in self._data:
+            for k in value.keys():              # like tensordict: only the entries the source carries are written
+                if k not in self._data and isinstance(index, int) and isinstance(value[k], torch.Tensor):
+                    # a key the destination lacks is created (zero-filled) over the full batch shape
+                    v = value[k]
+                    feat = tuple(v.shape[len(self._batch_size) - 1:])
+                    self._data[k] = torch.zeros((*self._batch_size, *feat), dtype=v.dtype, device=v.device)
                 self._data[k][index] = value[k]
         else:
             for k in self._data:

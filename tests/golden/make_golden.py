@@ -412,10 +412,47 @@ def gen_ddpg_td3():
         print(f"  {name}: oracle == reference over {steps} learn calls (losses, every parameter, targets)")
 
 
+def gen_gae():
+    """SURVEY §8(f) rank 2 groundwork: RolloutBuffer.compute_returns_and_advantages at BASELINE config 4's
+    shape (256 vector envs, 8-dim obs), GAE and Monte-Carlo modes; oracle (oracle/gae.py) == reference bit
+    for bit, fixture keeps rewards / dones / values / bootstrap inputs and the reference's outputs."""
+    from agilerl.components.rollout_buffer import RolloutBuffer
+    from oracle import gae
+    T, E = 64, 256
+    obs_space = spaces.Box(-1, 1, (8,), np.float32)
+    act_space = spaces.Discrete(4)
+    out = {"T": T, "E": E, "gamma": 0.99, "gae_lambda": 0.95}
+    for mode, use_gae in (("gae", True), ("mc", False)):
+        rng = np.random.default_rng(11 + int(use_gae))
+        buf = RolloutBuffer(capacity=T, num_envs=E, observation_space=obs_space, action_space=act_space, device="cpu",
+                            gae_lambda=0.95, gamma=0.99, use_gae=use_gae)
+        for t in range(T):
+            buf.add(obs=rng.standard_normal((E, 8)).astype(np.float32), action=rng.integers(0, 4, E),
+                    reward=rng.standard_normal(E).astype(np.float32), done=rng.random(E) < 0.05,
+                    value=rng.standard_normal(E).astype(np.float32), log_prob=rng.standard_normal(E).astype(np.float32))
+        lv = rng.standard_normal(E).astype(np.float32)
+        ld = (rng.random(E) < 0.05).astype(np.float32)
+        buf.compute_returns_and_advantages(lv, ld)
+        R = buf.buffer["rewards"][:T].numpy().reshape(T, E)
+        D = buf.buffer["dones"][:T].numpy().reshape(T, E)
+        V = buf.buffer["values"][:T].numpy().reshape(T, E)
+        ra = buf.buffer["advantages"][:T].numpy().reshape(T, E)
+        rr = buf.buffer["returns"][:T].numpy().reshape(T, E)
+        oa, orr = gae.compute_returns_and_advantages(R, D, V, lv, ld, 0.99, 0.95, use_gae)
+        assert np.array_equal(ra, oa) and np.array_equal(rr, orr), mode
+        out.update({f"{mode}_rewards": R, f"{mode}_dones": D.astype(np.uint8), f"{mode}_values": V, f"{mode}_last_value": lv,
+                    f"{mode}_last_done": ld, f"{mode}_advantages": ra, f"{mode}_returns": rr})
+    save("gae_rollout.npz", **out)
+    print("  gae: oracle == reference (GAE and Monte-Carlo)")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)   # deterministic CPU reductions while generating
     if len(sys.argv) > 1 and sys.argv[1] == "ddpg_td3":
         gen_ddpg_td3()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "gae":
+        gen_gae()
         sys.exit(0)
     gen_tree()
     gen_replay()
@@ -423,3 +460,4 @@ if __name__ == "__main__":
     gen_dqn()
     gen_tournament()
     gen_ddpg_td3()
+    gen_gae()
