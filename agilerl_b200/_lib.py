@@ -66,6 +66,8 @@ class LearnBufs(Structure):
 _SIGS = {
     "b2rl_version": ([], c_int),
     "b2rl_debug_read": ([c_void_p, c_int], c_int),
+    "b2rl_gae_scan": ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_double, c_double, c_int,
+                       c_void_p, c_void_p, c_void_p], c_int),
     "b2rl_device_sm_count": ([c_int, POINTER(c_int)], c_int),
     "b2rl_tree_init": ([c_void_p, c_void_p, c_int64, c_void_p], c_int),
     "b2rl_tree_set": ([c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p], c_int),

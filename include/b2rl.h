@@ -192,6 +192,16 @@ int b2rl_net_forward_q(const b2rl_net_desc *net_host, const float *params, const
                        const int64_t *row_idx, int64_t rows, float *q_out, int64_t *argmax_out,
                        void *workspace, size_t workspace_bytes, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * PPO return / advantage recurrence — RolloutBuffer.compute_returns_and_advantages
+ * (agilerl/components/rollout_buffer.py:413-481).  rewards / values float32 [T, E], dones bool (1 byte) [T, E],
+ * last_value / last_done float32 [E]; advantages / returns float32 [T, E] out.  use_gae = 0: Monte-Carlo returns.
+ * Bit-identical to the reference's NumPy loop (float64 carry, float32 stores).
+ * ------------------------------------------------------------------------------------------ */
+int b2rl_gae_scan(const float *rewards, const uint8_t *dones, const float *values, const float *last_value,
+                  const float *last_done, int64_t T, int64_t E, double gamma, double gae_lambda, int use_gae,
+                  float *advantages, float *returns, void *stream);
+
 /* Diagnostics: with B2RL_TC_DBG=<cta> in the environment the tensor-core forward convolution records
  * clock64() stamps of that CTA's producer warp 0 (slots 0..63) and MMA lane (slots 64..127); this copies the
  * first n (<= 128) to the host after a device synchronize.  Fails when diagnostics are off. */
