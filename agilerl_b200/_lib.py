@@ -82,6 +82,8 @@ _SIGS = {
     "b2rl_per_sample_fused": ([c_void_p, c_void_p, c_int64, c_void_p, c_uint64, c_uint64, c_int64, c_double, c_int64,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p], c_int),
+    "b2rl_philox_uniforms": ([c_uint64, c_uint64, c_int64, c_void_p, c_void_p], c_int),
+    "b2rl_philox_normals": ([c_uint64, c_uint64, c_int64, c_void_p, c_void_p], c_int),
     "b2rl_ring_write": ([c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p], c_int),
     "b2rl_gather_rows": ([c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p], c_int),
     "b2rl_ring_write_multi": ([c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p], c_int),

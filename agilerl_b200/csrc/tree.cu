@@ -394,6 +394,19 @@ __global__ void per_sample_kernel(const double *__restrict__ st, const double *_
 
 static bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
 
+// what per_sample_kernel<true> / noise_reset_kernel<true> draw, written out (parity tests feed them to the oracle)
+__global__ void philox_dump_kernel(uint64_t seed, uint64_t offset, int64_t n, int normal, float *__restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (normal) {
+        out[i] = philox_normal(seed, offset + (uint64_t)i, 0x4E4F4953ull /* "NOIS" */);
+    } else {
+        uint32_t r[4];
+        philox4x32_10(seed, offset + (uint64_t)i, 0x50455253ull /* "PERS" */, r);
+        out[i] = (float)(r[0] >> 8) * (1.0f / 16777216.0f);
+    }
+}
+
 }  // namespace b2rl
 
 using namespace b2rl;
@@ -407,6 +420,21 @@ const char *b2rl_last_error(void) { return b2rl::last_error(); }
 int b2rl_device_sm_count(int device, int *out_host) {
     B2RL_CHECK_ARG(out_host != nullptr, "out_host is NULL");
     B2RL_CUDA(cudaDeviceGetAttribute(out_host, cudaDevAttrMultiProcessorCount, device));
+    return B2RL_OK;
+}
+
+int b2rl_philox_uniforms(uint64_t seed, uint64_t offset, int64_t n, float *out, void *stream) {
+    B2RL_CHECK_ARG(n >= 0 && (out || n == 0), "bad arguments");
+    if (n == 0) return B2RL_OK;
+    philox_dump_kernel<<<(int)((n + 255) / 256), 256, 0, as_stream(stream)>>>(seed, offset, n, 0, out);
+    B2RL_LAUNCH_CHECK();
+    return B2RL_OK;
+}
+int b2rl_philox_normals(uint64_t seed, uint64_t offset, int64_t n, float *out, void *stream) {
+    B2RL_CHECK_ARG(n >= 0 && (out || n == 0), "bad arguments");
+    if (n == 0) return B2RL_OK;
+    philox_dump_kernel<<<(int)((n + 255) / 256), 256, 0, as_stream(stream)>>>(seed, offset, n, 1, out);
+    B2RL_LAUNCH_CHECK();
     return B2RL_OK;
 }
 

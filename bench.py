@@ -55,6 +55,9 @@ def peaks():
 
 
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region: an NVML polling thread (5 ms period, so
+    even a 10 ms region is covered); falls back to `nvidia-smi -lms 20` when pynvml cannot be initialised."""
+    NAMES = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -62,18 +65,64 @@ class ClockSampler:
     def __init__(self, index: int):
         self.index = index
         self.proc = None
+        self.thread = None
+        self.samples: list = []
+        self.reasons: set = set()
+        self.max_mhz = None
+        self._stop = False
+        self.how = None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid)
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+
+    def _poll(self, nv, h):
+        while not self._stop:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                for bit, name in self.NAMES.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        import threading
+        try:
+            nv, h = self._nvml_handle()
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, args=(nv, h), daemon=True)
+            self.thread.start()
+            self.how = "nvml thread, 5 ms"
+            return
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.how = "nvidia-smi -lms 20"
         except OSError:
             self.proc = None
 
     def stop(self) -> dict:
+        if self.thread is not None:
+            self._stop = True
+            self.thread.join(timeout=1.0)
+            sm = self.samples
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(self.reasons), "samples": len(sm), "how": self.how}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
@@ -94,7 +143,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "how": self.how}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -183,28 +232,36 @@ def api_population_step(agents, mem, nmem, support, host_tr):
     return out
 
 
-def time_region(fn, steps, dist_on, finish=None):
-    """``finish`` joins work left on side streams (overlapped learn tails) into the timed stream
-    before the closing event, so the region covers every kernel of the K steps."""
+REPEATS = int(os.environ.get("B2RL_BENCH_REPEATS", "5"))
+
+
+def time_region(fn, steps, dist_on, finish=None, repeats=None):
+    """EXACTLY ``steps`` steps between a barrier + synchronize on both sides, CUDA events on the launching
+    stream, MAX over ranks — repeated ``repeats`` times; returns (median ms, [ms of every repeat]).
+    ``finish`` joins work left on side streams (overlapped learn tails) into the timed stream before the
+    closing event, so the region covers every kernel of the K steps."""
     import torch.distributed as dist
-    if dist_on:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        fn()
-    if finish is not None:
-        finish()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    if dist_on:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        dist.barrier()
-    return ms
+    out = []
+    for _ in range(repeats or REPEATS):
+        if dist_on:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        if finish is not None:
+            finish()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist_on:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            dist.barrier()
+        out.append(ms)
+    return statistics.median(out), out
 
 
 def conv1_roofline(eng, nmem, device):
@@ -232,18 +289,33 @@ def conv1_roofline(eng, nmem, device):
         if it >= 5:
             times.append(e0.elapsed_time(e1))
     ms = statistics.mean(times)
-    return flops, alg_bytes, ms
+    desc = {"kernel": "conv_fwd_tc_kernel<uint8, exact-A> (+ weight_split_kernel): conv1 forward (4->32, k8 s4) of B=256 "
+                      "frames gathered from the replay ring, tcgen05.mma kind::tf32 (2xTF32 weight split, fp32 TMEM "
+                      "accumulate)",
+            "operand": "tf32", "peak_vs_bf16": 0.5, "mmas_per_product": 2,
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (cold L2):
+            # profiles/r1_conv_fwd_tcgen05_v2.txt (7.2 MB of frames read; the 13 MB fp32 output stays in L2)
+            "traffic": 7405824,
+            "note": "uint8 frames read once + fp32 activations written once + weights; fp32-equivalent FLOPs 2*M*N*K, "
+                    "each costing 2 tf32 MMAs; the kernel is issue/latency-bound on building the im2col tile with CUDA "
+                    "cores (DESIGN.md section 5), not on HBM or the tensor pipe"}
+    return flops, alg_bytes, ms, desc
 
 
 # ---------------------------------------------------------------------------------------------------
+FRAME_SLOTS = 4096      # distinct frame rows the CPU arm keeps in host RAM (0.46 GB); see cpu_reference
+
+
 def cpu_reference(steps, warmup, cores):
-    """The reference's CPU implementation of one gradient step, as restated by the oracle
-    (pure-Python list segment trees like the reference + torch-CPU learn): bounded sample."""
+    """The reference's CPU implementation of one gradient step, as restated by the oracle (pure-Python list
+    segment trees like the reference + torch-CPU learn) on the STATED configuration: replay of BUFFER =
+    100 000 transitions — trees of capacity 2^17 with every one of the 100 000 leaves set, indices sampled over
+    the full range, 17-level descents and write-backs.  Only the frame payload is bounded: row i's frames are
+    those of slot i mod 4096 (0.46 GB of host RAM instead of 11.3 GB; the gather still copies B full rows)."""
     from oracle import learn as olearn, nets as onets, replay as oreplay
     from oracle.segtree import PySegTree
     torch.set_num_threads(cores)
     torch.manual_seed(0)
-    n_buf = 4096                              # bounded replay (frames for 4096 slots = 0.46 GB of host RAM)
     spec = onets.rainbow_spec(OBS, N_ACT)
     from agilerl_b200.networks.init import init_state_dict
     from agilerl_b200.networks.spec import FlatLayout, rainbow_spec
@@ -255,14 +327,41 @@ def cpu_reference(steps, warmup, cores):
             sd[k] = torch.zeros(e.shape)
     agent = olearn.OracleAgent(spec, sd, sd, batch_size=B, lr=LR, v_min=V_MIN, v_max=V_MAX)
     agent.reset_noise()
-    mem = oreplay.OraclePER(n_buf, ALPHA, tree_cls=PySegTree)
-    nmem = oreplay.OracleReplay(n_buf)
+
+    class WindowedFrames:
+        """gather(idx) over the full index space; frames come from slot idx mod FRAME_SLOTS."""
+        def gather(self, idx):
+            return {k: v[idx % FRAME_SLOTS] for k, v in self.storage.items()}
+
+    class PER(WindowedFrames, oreplay.OraclePER):
+        pass
+
+    class NStep(WindowedFrames, oreplay.OracleReplay):
+        pass
+
     g = torch.Generator().manual_seed(0)
+    mem, nmem = PER(BUFFER, ALPHA, tree_cls=PySegTree), NStep(BUFFER)
     for buf in (mem, nmem):
-        buf.add(dict(obs=torch.randint(0, 256, (n_buf, *OBS), dtype=torch.uint8, generator=g),
-                     action=torch.randint(0, N_ACT, (n_buf,), generator=g).float(),
-                     next_obs=torch.randint(0, 256, (n_buf, *OBS), dtype=torch.uint8, generator=g),
-                     reward=torch.randn(n_buf, generator=g), done=(torch.rand(n_buf, generator=g) < 0.01).float()))
+        buf.storage = dict(obs=torch.randint(0, 256, (FRAME_SLOTS, *OBS), dtype=torch.uint8, generator=g),
+                           action=torch.randint(0, N_ACT, (FRAME_SLOTS, 1), generator=g).float(),
+                           next_obs=torch.randint(0, 256, (FRAME_SLOTS, *OBS), dtype=torch.uint8, generator=g),
+                           reward=torch.randn(FRAME_SLOTS, 1, generator=g),
+                           done=(torch.rand(FRAME_SLOTS, 1, generator=g) < 0.01).float())
+        buf.size = buf.counter = BUFFER
+    # priorities |N(0,1)| + 1e-6 on all 100 000 leaves (BASELINE.md section 4), trees built bottom-up in fp64
+    cap = mem.sum_tree.capacity
+    assert cap == 1 << 17
+    pa = np.zeros(cap)
+    pri = np.abs(torch.randn(BUFFER, generator=g).numpy().astype(np.float64)) + 1e-6
+    pa[:BUFFER] = np.maximum(pri, 1e-5) ** ALPHA
+    sums, mins = [pa], [np.where(np.arange(cap) < BUFFER, pa, np.inf)]
+    while len(sums[-1]) > 1:
+        sums.append(sums[-1][0::2] + sums[-1][1::2])
+        mins.append(np.minimum(mins[-1][0::2], mins[-1][1::2]))
+    mem.sum_tree.tree = [0.0] + np.concatenate(sums[::-1]).tolist()
+    mem.min_tree.tree = [float("inf")] + np.concatenate(mins[::-1]).tolist()
+    mem.max_priority = float(pri.max())
+
     def one_step():
         t0 = time.perf_counter()
         exp = mem.sample(B, BETA)
@@ -291,6 +390,58 @@ def cpu_reference(steps, warmup, cores):
     return times, best
 
 
+CPU_SAMPLE = ("gradient steps of ONE agent of the 8 (B=256; replay of 100 000 transitions: trees of capacity 2^17 with all "
+              "leaves set, full index space; frame payload of row i taken from slot i mod 4096 to bound host RAM), "
+              "pure-Python segment trees + torch-CPU learn at the fastest probed torch thread count (oracle restatement "
+              "of the reference; a Python reference cannot be installed on the box)")
+
+
+def config_for(world: int) -> dict:
+    n_local = POP // world
+    return {"workload": "Rainbow-DQN learn step, synthetic 84x84x4 uint8, batch 256, PER+3-step+C51, pop=8 "
+                        "(BASELINE configs[1])", "pop": POP, "batch": B, "buffer": BUFFER, "n_actions": N_ACT,
+            "atoms": N_ATOMS, "net": "conv[32,32] k[8,4] s[4,2] -> 2592 -> latent 32 -> noisy dueling head [64]",
+            "shapes": "canonical ([B] weights, [B,1] reward/done); quirks Q1/Q2 off",
+            "parallelism": f"pop{POP}/dp{world} ({n_local} agents per GPU, no data-path collective)",
+            "l2": "inputs larger than L2: 11.3 GB replay ring per rank, fresh random rows every step"}
+
+
+def tournament_generation(agents, world, rank, device):
+    """One generation of TournamentSelection.select on the sharded population (hpo/tournament.py:41-119 with
+    the checkpoint transport of utils/utils.py:756-782 replaced by NCCL): one all-gather of (fitness, index),
+    identical plan on every rank (asserted), winners moved point to point.  Timed with CUDA events, max over
+    ranks; OUTSIDE the timed learn region."""
+    import torch.distributed as dist
+    from agilerl_b200.hpo import TournamentSelection
+    n_local = len(agents)
+    for a in agents:
+        a.synchronize()
+        a.fitness = [float((a.index * 37) % 11)]          # synthetic evaluation scores, distinct per agent
+    ts = TournamentSelection(2, True, POP, 1, seed=1)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    elite, new_pop = ts.select(agents)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) * 1e3
+    elite_pos, slots = ts.last_plan
+    plans = [None] * world
+    dist.all_gather_object(plans, [elite_pos, [list(x) for x in slots]])
+    assert all(p == plans[0] for p in plans), "ranks derived different tournament plans"
+    moved = sum(1 for slot, (parent, _) in enumerate(slots) if slot // n_local != parent // n_local)
+    eng = agents[0].engine
+    per_agent = 4 * (2 * eng.actor.params.numel() + 2 * eng.actor.eps.numel() + 2 * eng.exp_avg.numel())
+    t = torch.tensor([e0.elapsed_time(e1), wall], device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    assert len(new_pop) == n_local and all(a is not None for a in new_pop)
+    return {"ms_device": float(t[0].item()), "ms_wall": float(t[1].item()), "bytes_allgather": world * n_local * 16,
+            "bytes_p2p": moved * per_agent, "moved_agents": moved, "plans_identical": True,
+            "elite_index": int(slots[0][1])}, new_pop
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -304,27 +455,21 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = os.cpu_count() or 1
-    common_cfg = {"workload": "Rainbow-DQN learn step, synthetic 84x84x4 uint8, batch 256, PER+3-step+C51, pop=8 "
-                              "(BASELINE configs[1])", "pop": POP, "batch": B, "buffer": BUFFER, "n_actions": N_ACT,
-                  "atoms": N_ATOMS, "net": "conv[32,32] k[8,4] s[4,2] -> 2592 -> latent 32 -> noisy dueling head [64]",
-                  "shapes": "canonical ([B] weights, [B,1] reward/done); quirks Q1/Q2 off"}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        steps = max(1, min(args.steps, 10))     # bounded sample: ~1-3 s of CPU per gradient step
-        warm = max(1, min(args.warmup, 2))
-        times, cores = cpu_reference(steps, warm, cores)
-        per_step = statistics.mean(times)
+        # a "step" of this arm = a bounded sample of the population step: ONE agent's gradient step (1/8)
+        times, cores = cpu_reference(args.steps, args.warmup, cores)
+        per_step = statistics.median(times)
         val = 1.0 / per_step                     # gradient-steps/s of ONE agent == population rate on one host
         line = {"metric": "population gradient-steps/sec (Rainbow-DQN pop=8)", "value": val, "unit": "steps/s",
-                "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": per_step * 1e3 * POP,
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3 * POP,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "impl": "reference", "config": dict(common_cfg, parallelism="host cores, agents sequential"),
+                "impl": "reference", "config": config_for(max(1, args.gpus)),
                 "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": "port",
-                                 "sample": f"{steps} gradient steps of one agent, B=256, replay bounded to 4096 slots, "
-                                           "pure-Python segment trees + torch-CPU learn (oracle restatement of the "
-                                           "reference; the reference itself cannot be installed on the box)"},
+                                 "sample": f"{args.steps} timed " + CPU_SAMPLE,
+                                 "ms_p10_p50_p90": [float(np.percentile(times, q)) * 1e3 for q in (10, 50, 90)]},
                 "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -357,8 +502,8 @@ def main():
         sampler.start()
     l0 = lib.b2rl_launch_count()
     join_all = lambda: [a.synchronize() for a in engines]
-    ms = time_region(step_fn, args.steps, dist_on, finish=join_all)
-    launches = (lib.b2rl_launch_count() - l0)
+    ms, ms_all = time_region(step_fn, args.steps, dist_on, finish=join_all)
+    launches = (lib.b2rl_launch_count() - l0) // len(ms_all)
     clocks = sampler.stop() if rank == 0 else None
     value = POP * args.steps / (ms / 1e3)
 
@@ -377,11 +522,17 @@ def main():
         api_fn = lambda: api_population_step(engines, mem, nmem, support, host_tr)
         for _ in range(max(args.warmup, 3)):
             api_fn()
-        ms_e2e = time_region(api_fn, args.steps, dist_on)
+        ms_e2e, ms_e2e_all = time_region(api_fn, args.steps, dist_on, repeats=3)
         h2d = sum(v.numel() * v.element_size() for v in host_tr.values()) + B * 4 + B * 8      # + uniforms + p_alpha
         d2h = 4 + B * 4
         e2e = {"value": POP * args.steps / (ms_e2e / 1e3), "unit": "steps/s", "ms_per_step": ms_e2e / args.steps,
-               "h2d_bytes_per_step": h2d * n_local, "d2h_bytes_per_step": d2h * n_local}
+               "h2d_bytes_per_step": h2d * n_local, "d2h_bytes_per_step": d2h * n_local,
+               "ms_repeats": [round(x, 3) for x in ms_e2e_all]}
+
+    # ---- per-generation exchange (N > 1): one tournament on the sharded population -------------
+    tournament = None
+    if dist_on:
+        tournament, engines = tournament_generation(engines, world, rank, device)
 
     if rank != 0:
         if dist_on:
@@ -389,14 +540,18 @@ def main():
         return
 
     hbm_peak, tf_peak, peak_kind = peaks()
-    flops, kbytes, kms = conv1_roofline(engines[0].engine, nmem, device)
+    flops, kbytes, kms, kdesc = conv1_roofline(engines[0].engine, nmem, device)
     achieved_tf = flops / (kms / 1e3) / 1e12
+    # tensor roof of this kernel: fp32-equivalent FLOPs, each multiply-add costing `mmas_per_product` tensor-core
+    # products of the operand type used (peak of that type = measured cuBLAS bf16 peak x the nominal type ratio)
+    type_peak = tf_peak * kdesc["peak_vs_bf16"]
+    tensor_peak_eq = type_peak / kdesc["mmas_per_product"]
     line = {
         "metric": "population gradient-steps/sec (Rainbow-DQN pop=8)", "value": value, "unit": "steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(common_cfg, parallelism=f"pop{POP}/dp{world} ({n_local} agents per GPU, no data-path collective)",
-                       l2="inputs larger than L2: 11.3 GB replay ring per rank, fresh random rows every step"),
+        "config": config_for(world),
+        "timing": {"repeats": len(ms_all), "stat": "median", "ms_repeats": [round(x, 3) for x in ms_all]},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "step_hbm": {"alg_bytes_per_grad_step": ALG_BYTES_PER_STEP,
@@ -404,30 +559,29 @@ def main():
                      "frac_of_peak": ALG_BYTES_PER_STEP * value / world / 1e9 / hbm_peak, "peak_gbs": hbm_peak,
                      "peak": peak_kind},
         # conv1 forward: 1.68 GFLOP over 20.4 MB of algorithmic traffic = 82 FLOP/B, left of the B200 ridge
-        # (measured 1678 TFLOP/s / 6.59 TB/s = 255 FLOP/B): the roof that bounds it is HBM
-        "roofline": {"kernel": "conv_fwd_tc_kernel<uint8, exact-A> (+ weight_split_kernel): conv1 forward (4->32, k8 s4) "
-                               "of B=256 frames gathered from the replay ring, tcgen05.mma kind::tf32 (2xTF32 weight "
-                               "split, fp32 TMEM accumulate)",
+        # (measured 1678 TFLOP/s / 6.59 TB/s = 255 FLOP/B): the roof that bounds it is HBM; the tensor roof is
+        # reported beside it
+        "roofline": {"kernel": kdesc["kernel"],
                      "bound": "hbm", "achieved": kbytes / (kms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                      "frac": kbytes / (kms * 1e-3) / 1e9 / hbm_peak,
-                     # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (cold L2):
-                     # profiles/r1_conv_fwd_tcgen05_v2.txt (7.2 MB of frames read; the 13 MB fp32 output stays in L2)
-                     "traffic": 7405824, "peak_kind": peak_kind + " (copy bandwidth, burst)",
+                     "traffic": kdesc["traffic"], "peak_kind": peak_kind + " (copy bandwidth, burst)",
                      "alg_bytes_per_launch": kbytes, "flops_per_launch": flops, "ms_per_launch": kms,
-                     "tflops": achieved_tf, "tflops_frac_of_bf16_peak": achieved_tf / tf_peak,
-                     "note": "uint8 frames read once + fp32 activations written once + weights; fp32-equivalent FLOPs "
-                             "2*M*N*K, each costing 2 tf32 MMAs; the kernel is issue/latency-bound on building the im2col "
-                             "tile with CUDA cores (DESIGN.md section 5), not on HBM or the tensor pipe"},
+                     "tensor": {"achieved": achieved_tf, "unit": "TFLOP/s fp32-equivalent", "peak": tensor_peak_eq,
+                                "frac": achieved_tf / tensor_peak_eq, "operand": kdesc["operand"],
+                                "mmas_per_product": kdesc["mmas_per_product"],
+                                "peak_kind": f"{peak_kind} bf16 cuBLAS peak x {kdesc['peak_vs_bf16']} (nominal "
+                                             f"{kdesc['operand']}:bf16 ratio) / {kdesc['mmas_per_product']}"},
+                     "note": kdesc["note"]},
     }
     if e2e is not None:
         line["e2e"] = e2e
+    if tournament is not None:
+        line["tournament"] = tournament
     if not args.no_cpu_baseline and world == 1:
-        t, used = cpu_reference(3, 1, cores)
-        per = statistics.mean(t)
+        t, used = cpu_reference(5, 1, cores)
+        per = statistics.median(t)
         line["cpu_baseline"] = {"value": 1.0 / per, "unit": "steps/s", "cores": used, "kind": "port",
-                                "sample": "3 gradient steps of one agent (B=256, replay bounded to 4096 slots) at the "
-                                          "fastest probed torch thread count, oracle restatement of the reference: "
-                                          "pure-Python segment trees + torch-CPU learn"}
+                                "sample": "5 timed " + CPU_SAMPLE}
     print(json.dumps(line))
     if dist_on:
         torch.distributed.destroy_process_group()

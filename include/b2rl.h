@@ -95,6 +95,12 @@ int b2rl_per_sample_fused(const double *sum_tree, const double *min_tree, int64_
                           float *out_w, float *out_action, float *out_reward, float *out_done,
                           void *stream);
 
+/* Read-back of the device random streams (parity tests hand them to the oracle): the B float32 uniforms
+ * b2rl_per_sample_philox / b2rl_per_sample_fused(uniforms = NULL) consume at (seed, offset), and the
+ * standard normals b2rl_noise_reset_philox consumes at (seed, offset) in b2rl_noise_reset_from_normals' layout. */
+int b2rl_philox_uniforms(uint64_t seed, uint64_t offset, int64_t n, float *out, void *stream);
+int b2rl_philox_normals(uint64_t seed, uint64_t offset, int64_t n, float *out, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Ring storage — ReplayBuffer.add / storage[indices] (replay_buffer.py:72-112, :126, :204, :345).
  * One call per field (SoA); rows are opaque byte strings of row_bytes.
