@@ -68,6 +68,9 @@ _SIGS = {
     "b2rl_debug_read": ([c_void_p, c_int], c_int),
     "b2rl_gae_scan": ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_double, c_double, c_int,
                        c_void_p, c_void_p, c_void_p], c_int),
+    "b2rl_advantage_normalize": ([c_void_p, c_int64, c_void_p, c_void_p], c_int),
+    "b2rl_gae_scan_normalize": ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_double, c_double,
+                                 c_int, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
     "b2rl_device_sm_count": ([c_int, POINTER(c_int)], c_int),
     "b2rl_tree_init": ([c_void_p, c_void_p, c_int64, c_void_p], c_int),
     "b2rl_tree_set": ([c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p], c_int),
@@ -97,6 +100,8 @@ _SIGS = {
     "b2rl_noise_count": ([POINTER(NetDesc), POINTER(c_int64)], c_int),
     "b2rl_net_forward_q": ([POINTER(NetDesc), c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64,
                             c_void_p, c_void_p, c_void_p, c_size_t, c_void_p], c_int),
+    "b2rl_net_forward_dist": ([POINTER(NetDesc), c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p,
+                               c_void_p, c_size_t, c_void_p], c_int),
     "b2rl_encoder_layer_forward": ([POINTER(NetDesc), c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                     c_size_t, c_void_p], c_int),
     "b2rl_launch_count": ([], ctypes.c_ulonglong),

@@ -37,6 +37,9 @@ class EvolvableAlgorithm:
         self.fitness: list = []
         self.steps: list = [0]
         self.registry = MutationRegistry(hp_config)
+        # the reference's clone() deep-copies ``registry`` (copy_attributes, core/base.py:432-492); here the
+        # constructor rebuilds it, so the hyper-parameter config travels as a constructor argument
+        self.hp_config = self.registry.hp_config
         self.training = True
 
     @property
@@ -173,10 +176,24 @@ class EvolvableAlgorithm:
             net = type(getattr(self, n))(**d["init_dict"])
             net.load_state_dict(d["state_dict"])
             setattr(self, n, net)
+        # every saved constructor attribute comes back (the reference setattr's the whole checkpoint,
+        # core/base.py:1003-1049): mutated lr / batch_size / learn_step / beta / tau / gamma / n_step / v_min / v_max ...
+        for k, v in ckpt.get("init", {}).items():
+            if k in ("device", "accelerator", "observation_space", "action_space", "index", "net_config"):
+                continue
+            if k == "hp_config":
+                if v is not None:
+                    self.hp_config = self.registry.hp_config = v
+                continue
+            setattr(self, k, v)
+        self._after_hyperparameter_restore()
         self._after_network_swap()
-        self.optimizer.load_state_dict(ckpt["optimizer"])
+        self.optimizer.load_state_dict(ckpt["optimizer"], strict=True)
         self.scores, self.fitness, self.steps, self.mut = ckpt["scores"], ckpt["fitness"], ckpt["steps"], ckpt["mut"]
         self.index = ckpt["index"]
+
+    def _after_hyperparameter_restore(self) -> None:
+        """Derived attributes that depend on restored scalars (e.g. the C51 support)."""
 
     def _after_network_swap(self) -> None:
         pass

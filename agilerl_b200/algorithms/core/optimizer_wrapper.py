@@ -34,10 +34,18 @@ class OptimizerWrapper:
         e = self.engine
         return {"step": e.step, "exp_avg": e.exp_avg.clone(), "exp_avg_sq": e.exp_avg_sq.clone(), "lr": self.lr}
 
-    def load_state_dict(self, sd: dict) -> None:
+    def load_state_dict(self, sd: dict, strict: bool = False) -> None:
         e = self.engine
         if sd["exp_avg"].numel() != e.exp_avg.numel():
+            msg = (f"optimizer state of {sd['exp_avg'].numel()} elements does not fit a network of "
+                   f"{e.exp_avg.numel()} parameters")
+            if strict:
+                raise ValueError(msg)
+            import warnings
+            warnings.warn(msg + ": Adam moments start fresh", stacklevel=2)
             return                                   # architecture changed: fresh moments (reinit_optimizers)
+        if "lr" in sd and sd["lr"] is not None:
+            self.lr = sd["lr"]
         e.step = int(sd["step"])
         e.exp_avg.copy_(sd["exp_avg"].to(e.exp_avg.device))
         e.exp_avg_sq.copy_(sd["exp_avg_sq"].to(e.exp_avg.device))

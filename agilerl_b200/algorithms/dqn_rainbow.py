@@ -115,6 +115,10 @@ class RainbowDQN(RLAlgorithm):
     def _after_network_swap(self) -> None:
         self._bind_engine()
 
+    def _after_hyperparameter_restore(self) -> None:
+        self.support = torch.linspace(self.v_min, self.v_max, self.num_atoms).to(self._dev)
+        self.delta_z = (self.v_max - self.v_min) / (self.num_atoms - 1)
+
     def _copy_networks_to(self, clone) -> None:
         clone.actor, clone.actor_target = self.actor.clone(), self.actor_target.clone()
         clone._bind_engine(keep_state=self.optimizer.state_dict())

@@ -608,6 +608,34 @@ __global__ void rainbow_q_kernel(const float *__restrict__ v, const float *__res
         for (int a = threadIdx.x; a < A; a += blockDim.x) q_out[row * A + a] = q[a];
 }
 
+// RainbowQNetwork.forward(q=False, log=...) (custom_modules.py:153-160): per-atom distributions [rows, A, N] —
+// softmax + clamp(min=1e-3), or log_softmax when log_mode (no clamp, like the reference).
+__global__ void rainbow_dist_kernel(const float *__restrict__ v, const float *__restrict__ adv, int A, int N,
+                                    int log_mode, float *__restrict__ out) {
+    extern __shared__ float sm[];
+    float *x = sm;            // A*N
+    const int64_t row = blockIdx.x;
+    dueling_to_smem(v + row * N, adv + row * (int64_t)A * N, A, N, x);
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
+    for (int a = warp; a < A; a += nwarps) {
+        float *xr = x + a * N;
+        if (!log_mode) {
+            softmax_clamp_row(xr, N, nullptr);
+        } else {
+            float m = -INFINITY;
+            for (int n = lane; n < N; n += 32) m = fmaxf(m, xr[n]);
+            m = warp_max(m);
+            float sum = 0.f;
+            for (int n = lane; n < N; n += 32) sum += expf(xr[n] - m);
+            sum = warp_sum(sum);
+            const float lse = logf(sum);
+            for (int n = lane; n < N; n += 32) xr[n] = xr[n] - m - lse;
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < A * N; k += blockDim.x) out[row * (int64_t)A * N + k] = x[k];
+}
+
 struct ProjCfg { float gamma, v_min, v_max, delta_z; };
 
 // Target distribution of a* and (canonical shapes) the C51 projection, sequential per row in the
@@ -1411,14 +1439,16 @@ int b2rl_noise_reset_philox(const b2rl_net_desc *net_host, float *eps, uint64_t 
     return noise_reset(*net_host, eps, nullptr, seed, offset, as_stream(stream));
 }
 
-int b2rl_net_forward_q(const b2rl_net_desc *net_host, const float *params, const float *eps, int use_noise,
-                       const float *support, const void *obs, const int64_t *row_idx, int64_t rows, float *q_out,
-                       int64_t *argmax_out, void *workspace, size_t workspace_bytes, void *stream) {
+// mode 0: expected Q-values (+ argmax); 1: per-atom distributions; 2: per-atom log-probabilities
+static int net_forward(const b2rl_net_desc *net_host, const float *params, const float *eps, int use_noise,
+                       const float *support, const void *obs, const int64_t *row_idx, int64_t rows, int mode,
+                       float *out, int64_t *argmax_out, void *workspace, size_t workspace_bytes, void *stream) {
     B2RL_CHECK_ARG(net_host && params && obs, "NULL argument");
     int rc = validate_net(*net_host);
     if (rc != B2RL_OK) return rc;
     if (rows <= 0) return B2RL_OK;
     const b2rl_net_desc &net = *net_host;
+    B2RL_CHECK_ARG(mode == 0 || net.kind == B2RL_NET_RAINBOW, "per-atom distributions exist for rainbow networks only");
     FwdWS ws;
     carve_fwd(net, rows, workspace, ws);
     B2RL_CHECK_ARG(workspace && workspace_bytes >= ws.bytes, "workspace too small: need %zu bytes, got %zu", ws.bytes,
@@ -1436,15 +1466,34 @@ int b2rl_net_forward_q(const b2rl_net_desc *net_host, const float *params, const
     if (net.kind == B2RL_NET_RAINBOW) {
         const size_t sm_q = sizeof(float) * ((size_t)A * N + A);
         if ((rc = head_smem_check(sm_q)) != B2RL_OK) return rc;
-        B2RL_CHECK_ARG(support, "support is NULL");
-        rainbow_q_kernel<<<(int)rows, 128, sm_q, s>>>(ws.pass.val[net.n_val - 1].a, ws.pass.adv[net.n_adv - 1].a, support,
-                                                      A, N, q_out, nullptr, argmax_out);
+        const float *v = ws.pass.val[net.n_val - 1].a, *adv = ws.pass.adv[net.n_adv - 1].a;
+        if (mode == 0) {
+            B2RL_CHECK_ARG(support, "support is NULL");
+            rainbow_q_kernel<<<(int)rows, 128, sm_q, s>>>(v, adv, support, A, N, out, nullptr, argmax_out);
+        } else {
+            B2RL_CHECK_ARG(out, "output is NULL");
+            rainbow_dist_kernel<<<(int)rows, 128, sm_q, s>>>(v, adv, A, N, mode == 2, out);
+        }
         B2RL_LAUNCH_CHECK();
         return B2RL_OK;
     }
-    q_argmax_kernel<<<(int)((rows + 127) / 128), 128, 0, s>>>(ws.pass.val[net.n_val - 1].a, A, rows, q_out, argmax_out);
+    q_argmax_kernel<<<(int)((rows + 127) / 128), 128, 0, s>>>(ws.pass.val[net.n_val - 1].a, A, rows, out, argmax_out);
     B2RL_LAUNCH_CHECK();
     return B2RL_OK;
+}
+
+int b2rl_net_forward_q(const b2rl_net_desc *net_host, const float *params, const float *eps, int use_noise,
+                       const float *support, const void *obs, const int64_t *row_idx, int64_t rows, float *q_out,
+                       int64_t *argmax_out, void *workspace, size_t workspace_bytes, void *stream) {
+    return net_forward(net_host, params, eps, use_noise, support, obs, row_idx, rows, 0, q_out, argmax_out, workspace,
+                       workspace_bytes, stream);
+}
+
+int b2rl_net_forward_dist(const b2rl_net_desc *net_host, const float *params, const float *eps, int use_noise,
+                          const void *obs, const int64_t *row_idx, int64_t rows, int log_probs, float *dist_out,
+                          void *workspace, size_t workspace_bytes, void *stream) {
+    return net_forward(net_host, params, eps, use_noise, nullptr, obs, row_idx, rows, log_probs ? 2 : 1, dist_out, nullptr,
+                       workspace, workspace_bytes, stream);
 }
 
 

@@ -141,6 +141,19 @@ class LearnEngine:
             None if am is None else am.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(self.device)))
         return (q, am) if want_argmax else q
 
+    def distributions(self, net: NetBuffers, obs: torch.Tensor, use_noise: bool, log: bool = False) -> torch.Tensor:
+        """RainbowQNetwork.forward(obs, q=False, log=log): [rows, n_actions, n_atoms] (q_networks.py:265-284)."""
+        self.join()
+        desc = self.layout.desc
+        obs = self._obs(obs)
+        rows = obs.shape[0]
+        out = torch.empty((rows, desc.n_actions, desc.n_atoms), dtype=torch.float32, device=self.device)
+        ws = self.workspace(rows, False)
+        _lib.check(self.lib.b2rl_net_forward_dist(
+            ctypes.byref(desc), net.params.data_ptr(), net.eps.data_ptr(), int(use_noise), obs.data_ptr(), None, rows,
+            int(log), out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(self.device)))
+        return out
+
     def _obs(self, obs: torch.Tensor) -> torch.Tensor:
         _lib.require_cuda_tensor(obs, "observation batch")
         want = torch.uint8 if self.layout.desc.obs_u8 else torch.float32

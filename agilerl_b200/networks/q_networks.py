@@ -122,8 +122,11 @@ class RainbowQNetwork(_ForwardMixin, EvolvableNetwork):
         return NetSpec("rainbow", self._encoder_spec(), val, adv, self.num_actions, self.num_atoms, low, high, u8)
 
     def forward(self, obs, q: bool = True, log: bool = False) -> torch.Tensor:
-        if not q or log:
-            raise NotImplementedError("per-atom distributions are produced inside the fused loss kernels only")
+        """q_networks.py:265-284: expected Q-values [rows, A] (q=True), per-atom distributions [rows, A, N]
+        (q=False: softmax + clamp 1e-3) or log-probabilities (log=True, which takes precedence like
+        custom_modules.py:154-156)."""
+        if log or not q:
+            return self._engine().distributions(self.buffers, self._prep_obs(obs), use_noise=self.training, log=log)
         return self._engine().q_values(self.buffers, self._prep_obs(obs), self.support, use_noise=self.training)
 
     __call__ = forward

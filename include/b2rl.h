@@ -198,15 +198,31 @@ int b2rl_net_forward_q(const b2rl_net_desc *net_host, const float *params, const
                        const int64_t *row_idx, int64_t rows, float *q_out, int64_t *argmax_out,
                        void *workspace, size_t workspace_bytes, void *stream);
 
+/* RainbowQNetwork.forward(obs, q=False, log=log_probs) (q_networks.py:265-284 -> custom_modules.py:127-162):
+ * per-atom distributions, dist_out: rows x n_actions x n_atoms — softmax then clamp(min=1e-3), or log_softmax
+ * (unclamped) when log_probs != 0. */
+int b2rl_net_forward_dist(const b2rl_net_desc *net_host, const float *params, const float *eps, int use_noise,
+                          const void *obs, const int64_t *row_idx, int64_t rows, int log_probs, float *dist_out,
+                          void *workspace, size_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * PPO return / advantage recurrence — RolloutBuffer.compute_returns_and_advantages
  * (agilerl/components/rollout_buffer.py:413-481).  rewards / values float32 [T, E], dones bool (1 byte) [T, E],
- * last_value / last_done float32 [E]; advantages / returns float32 [T, E] out.  use_gae = 0: Monte-Carlo returns.
+ * last_value float64 [E] (the reference widens it: last_value.astype(float)), last_done float32 [E]; advantages / returns float32 [T, E] out.  use_gae = 0: Monte-Carlo returns.
  * Bit-identical to the reference's NumPy loop (float64 carry, float32 stores).
  * ------------------------------------------------------------------------------------------ */
-int b2rl_gae_scan(const float *rewards, const uint8_t *dones, const float *values, const float *last_value,
+int b2rl_gae_scan(const float *rewards, const uint8_t *dones, const float *values, const double *last_value,
                   const float *last_done, int64_t T, int64_t E, double gamma, double gae_lambda, int use_gae,
                   float *advantages, float *returns, void *stream);
+/* PPO's global advantage normalisation (agilerl/algorithms/ppo.py:831-834, :935-944): out = (a - mean(a)) /
+ * (std(a) + 1e-8), unbiased std; reductions in float64, fixed order (deterministic; within 1e-6 of torch's float32
+ * statistics).  n = T*E elements, one launch. */
+int b2rl_advantage_normalize(const float *advantages, int64_t n, float *out, void *stream);
+/* Both in ONE launch when E <= 1024 (one CTA: thread e scans environment e, then the CTA normalises): returns,
+ * raw advantages and normalised advantages of a rollout without leaving the device. */
+int b2rl_gae_scan_normalize(const float *rewards, const uint8_t *dones, const float *values, const double *last_value,
+                            const float *last_done, int64_t T, int64_t E, double gamma, double gae_lambda, int use_gae,
+                            float *advantages, float *returns, float *adv_norm, void *stream);
 
 /* Diagnostics: with B2RL_TC_DBG=<cta> in the environment the tensor-core forward convolution records
  * clock64() stamps of that CTA's producer warp 0 (slots 0..63) and MMA lane (slots 64..127); this copies the

@@ -39,3 +39,13 @@ def compute_returns_and_advantages(rewards: np.ndarray, dones: np.ndarray, value
             returns[t] = last_returns = rewards[t] + gamma * last_returns * (1.0 - dones[t].astype(float))
         advantages = returns - values
     return advantages, returns
+
+
+def normalize_advantages(advantages: np.ndarray) -> np.ndarray:
+    """PPO's global advantage normalisation, agilerl/algorithms/ppo.py:831-834 (flat path) and :935-944
+    (recurrent path): ``(a - a.mean()) / (a.std() + 1e-8)`` with torch's float32 reductions and Bessel-corrected
+    ``std`` — the literal torch expression on CPU."""
+    import torch
+    flat = torch.from_numpy(np.ascontiguousarray(advantages, dtype=np.float32)).reshape(-1)
+    out = (flat - flat.mean()) / (flat.std() + 1e-8)
+    return out.reshape(advantages.shape).numpy()

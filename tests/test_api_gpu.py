@@ -271,3 +271,55 @@ def test_overlapped_learn_tail_is_bit_identical_to_sequential():
     assert torch.equal(s0, s1) and torch.equal(m0, m1)
     for a, b in zip(p0, p1):
         assert torch.equal(a, b)
+
+
+def test_clone_keeps_hyperparameter_config_and_rl_hp_mutation_acts_on_clones(tmp_path):
+    """the cloned agent must carry the HyperparameterConfig, otherwise every
+    rl_hyperparam_mutation after the first tournament is a silent no-op; the sharded move (export_state /
+    from_state) and checkpoints carry it too."""
+    from agilerl_b200.algorithms import RainbowDQN
+    from agilerl_b200.algorithms.core.registry import HyperparameterConfig, RLParameter
+    from agilerl_b200.hpo import Mutations
+    obs_space, act_space = _spaces()
+    hp = HyperparameterConfig(lr=RLParameter(min=1e-5, max=1e-2), batch_size=RLParameter(min=8, max=32, dtype=int))
+    agent = RainbowDQN(obs_space, act_space, index=3, hp_config=hp, net_config=dict(NET), batch_size=16, v_min=-10.0,
+                       v_max=10.0)
+    c = agent.clone(index=4).clone(index=5)                       # two generations of tournament clones
+    assert bool(c.registry.hp_config) and sorted(c.registry.hp_config.names()) == ["batch_size", "lr"]
+    assert c.registry.hp_config is not agent.registry.hp_config   # deep copy, like copy_attributes
+    mut = Mutations(0, 0, 0, 0, 0, 1.0, rand_seed=1)
+    seen = set()
+    for _ in range(8):
+        before = (c.lr, c.batch_size)
+        c = mut.rl_hyperparam_mutation(c)
+        assert c.mut in ("lr", "batch_size")
+        assert (c.lr, c.batch_size) != before
+        seen.add(c.mut)
+        c = c.clone()
+    assert seen == {"lr", "batch_size"}
+    assert c.optimizer.lr == c.lr
+    moved = type(c).from_state(*c.export_state(), like=agent)
+    assert sorted(moved.registry.hp_config.names()) == ["batch_size", "lr"] and moved.lr == c.lr
+    # checkpoint round trip restores mutated hyper-parameters, the derived support and the architecture
+    c.actor.encoder.add_channel(hidden_layer=0, numb_new_channels=8)
+    c.actor_target = type(c.actor)(**c.actor.init_dict)
+    c.actor_target.load_state_dict(c.actor.state_dict())
+    c.reinit_optimizers()
+    c.beta, c.tau, c.v_min, c.v_max = 0.7, 5e-3, -5.0, 5.0
+    c._after_hyperparameter_restore()
+    c.engine.exp_avg.fill_(0.5); c.engine.step = 11
+    path = str(tmp_path / "agent.pt")
+    c.save_checkpoint(path)
+    fresh = RainbowDQN(obs_space, act_space, index=0, net_config=dict(NET), batch_size=16, v_min=-10.0, v_max=10.0)
+    fresh.load_checkpoint(path)
+    assert (fresh.lr, fresh.batch_size, fresh.beta, fresh.tau, fresh.v_min, fresh.v_max) == \
+           (c.lr, c.batch_size, 0.7, 5e-3, -5.0, 5.0)
+    assert torch.equal(fresh.support.cpu(), torch.linspace(-5.0, 5.0, 51)) and fresh.delta_z == 10.0 / 50
+    assert list(fresh.actor.encoder.channel_size) == list(c.actor.encoder.channel_size)
+    assert fresh.engine.step == 11 and float(fresh.engine.exp_avg.mean()) == 0.5 and fresh.optimizer.lr == c.lr
+    assert sorted(fresh.registry.hp_config.names()) == ["batch_size", "lr"]
+    for k, v in c.actor.state_dict().items():
+        assert torch.equal(v, fresh.actor.state_dict()[k]), k
+    with pytest.raises(ValueError):                               # optimiser state of another architecture is not dropped silently
+        other = RainbowDQN(obs_space, act_space, net_config=dict(NET), batch_size=16, v_min=-10.0, v_max=10.0)
+        other.optimizer.load_state_dict(c.optimizer.state_dict(), strict=True)

@@ -47,3 +47,31 @@ def test_requires_cuda_tensors():
     with pytest.raises(_lib.B2RLError):
         compute_returns_and_advantages(torch.zeros(2, 2), torch.zeros(2, 2, dtype=torch.bool), torch.zeros(2, 2),
                                        np.zeros(2, np.float32), np.zeros(2, np.float32))
+
+
+@pytest.mark.parametrize("T,E", [(8, 256), (128, 256), (3, 5), (1, 2), (16, 1500)])
+@pytest.mark.parametrize("use_gae", [True, False])
+def test_fused_scan_and_advantage_normalisation(T, E, use_gae):
+    """b2rl_gae_scan_normalize (one launch for E <= 1024; BASELINE config 4 = 256 envs x learn_step 2048 -> T = 8):
+    advantages / returns bit-exact against the oracle's NumPy loop; normalised advantages within 1e-6 of the
+    reference's torch expression (ppo.py:831-834) — the device carries both reductions in float64, fixed order,
+    torch sums float32 in cascade order, so bit equality is not the bar here (stated in csrc/gae.cu)."""
+    from oracle import gae
+    from agilerl_b200.components.rollout import compute_returns_and_normalized_advantages, normalize_advantages
+    rng = np.random.default_rng(7 * T + E + int(use_gae))
+    R = rng.standard_normal((T, E)).astype(np.float32)
+    V = rng.standard_normal((T, E)).astype(np.float32)
+    D = rng.random((T, E)) < 0.03
+    lv = rng.standard_normal(E)                                   # float64 bootstrap values keep all their bits
+    ld = (rng.random(E) < 0.03).astype(np.float32)
+    oa, orr = gae.compute_returns_and_advantages(R, D, V, lv, ld, 0.99, 0.95, use_gae)
+    adv, ret, nrm = compute_returns_and_normalized_advantages(torch.from_numpy(R).cuda(), torch.from_numpy(D).cuda(),
+                                                              torch.from_numpy(V).cuda(), lv, ld, 0.99, 0.95, use_gae)
+    np.testing.assert_array_equal(adv.cpu().numpy(), oa)
+    np.testing.assert_array_equal(ret.cpu().numpy(), orr)
+    want = gae.normalize_advantages(oa)
+    scale = max(1.0, float(np.abs(want).max()))
+    np.testing.assert_allclose(nrm.cpu().numpy(), want, rtol=2e-6, atol=2e-6 * scale)
+    again = normalize_advantages(adv)                             # stand-alone launch == fused launch, bit for bit
+    assert torch.equal(again, nrm)
+    assert torch.equal(normalize_advantages(adv), again)          # deterministic run to run

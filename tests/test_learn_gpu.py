@@ -80,6 +80,27 @@ def test_forward_q_values_match_oracle():
     np.testing.assert_allclose(q_eval.cpu().numpy(), q_ref_eval.numpy(), rtol=1e-5, atol=1e-5)
 
 
+def test_forward_distributions_match_oracle():
+    """RainbowQNetwork.forward(q=False) / (log=True): per-atom distributions and log-probabilities
+    (custom_modules.py:153-160) vs the oracle, train-mode noise and eval mode."""
+    from oracle import nets as onets
+    g = load_golden("rainbow_small_canonical.npz")
+    eng, layout = _engine(_small_spec(), g)
+    ospec = onets.rainbow_spec((3, 20, 20), 4, (8, 16), (4, 3), (2, 1), 16, (32,))
+    ospec.support = torch.linspace(-10.0, 10.0, 51)
+    obs = torch.from_numpy(g["exp_obs"])
+    x = onets.preprocess(ospec, obs)
+    for noise in (True, False):
+        ref = onets.rainbow_forward(_sd(g, "actor0"), ospec, x, q=False, train_noise=noise)
+        got = eng.distributions(eng.actor, obs.cuda(), use_noise=noise)
+        assert got.shape == (obs.shape[0], 4, 51)
+        np.testing.assert_allclose(got.cpu().numpy(), ref.numpy(), rtol=1e-5, atol=1e-6)
+        assert float(got.min()) >= 1e-3                                   # clamp, quirk Q8
+        ref_log = onets.rainbow_forward(_sd(g, "actor0"), ospec, x, q=False, log=True, train_noise=noise)
+        got_log = eng.distributions(eng.actor, obs.cuda(), use_noise=noise, log=True)
+        np.testing.assert_allclose(got_log.cpu().numpy(), ref_log.numpy(), rtol=1e-5, atol=1e-5)
+
+
 def test_rainbow_learn_golden_canonical_full_state():
     g = load_golden("rainbow_small_canonical.npz")
     eng, layout, (loss, loss_elem, pri, proj) = _run_rainbow(g, _small_spec())
