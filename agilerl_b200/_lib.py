@@ -60,6 +60,14 @@ class LearnBufs(Structure):
         ("reward", c_void_p), ("done", c_void_p), ("weights", c_void_p), ("support", c_void_p),
         ("loss_elem", c_void_p), ("priorities", c_void_p), ("loss_scalar", c_void_p),
         ("proj_dist", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+        ("step_state", c_void_p),
+    ]
+
+
+class StepState(Structure):
+    _fields_ = [
+        ("beta", c_double), ("size", c_int64), ("sample_offset", c_uint64), ("noise_offset", c_uint64 * 2),
+        ("lr", c_double), ("bias_correction1", c_double), ("bias_correction2", c_double),
     ]
 
 
@@ -85,6 +93,15 @@ _SIGS = {
     "b2rl_per_sample_fused": ([c_void_p, c_void_p, c_int64, c_void_p, c_uint64, c_uint64, c_int64, c_double, c_int64,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p], c_int),
+    "b2rl_per_sample_fused_state": ([c_void_p, c_void_p, c_int64, c_uint64, c_void_p, c_int64, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
+    "b2rl_noise_reset_state": ([POINTER(NetDesc), c_void_p, c_uint64, c_void_p, c_int, c_void_p], c_int),
+    "b2rl_step_state_write": ([POINTER(StepState), c_void_p, c_void_p], c_int),
+    "b2rl_graph_begin": ([c_void_p], c_int),
+    "b2rl_graph_end": ([c_void_p, POINTER(c_void_p)], c_int),
+    "b2rl_graph_launch": ([c_void_p, POINTER(StepState), c_void_p], c_int),
+    "b2rl_graph_kernel_count": ([c_void_p, POINTER(c_int)], c_int),
+    "b2rl_graph_destroy": ([c_void_p], c_int),
     "b2rl_philox_uniforms": ([c_uint64, c_uint64, c_int64, c_void_p, c_void_p], c_int),
     "b2rl_philox_normals": ([c_uint64, c_uint64, c_int64, c_void_p, c_void_p], c_int),
     "b2rl_ring_write": ([c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p], c_int),

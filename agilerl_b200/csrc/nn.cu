@@ -1183,7 +1183,12 @@ __global__ void sqnorm_kernel(const float *__restrict__ g, int64_t n, float *__r
 
 __global__ void adam_polyak_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m,
                                    float *__restrict__ v, float *__restrict__ tgt, int64_t n,
-                                   const float *__restrict__ partials, int nparts, AdamCfg c) {
+                                   const float *__restrict__ partials, int nparts, AdamCfg c,
+                                   const b2rl_step_state *__restrict__ state) {
+    if (state) {        // graph-replayed step: this step's scalars, same double arithmetic as the host path
+        c.neg_step = (float)(-__ddiv_rn(state->lr, state->bias_correction1));
+        c.bc2_sqrt = (float)__dsqrt_rn(state->bias_correction2);
+    }
     __shared__ float coef_s;
     if (threadIdx.x < 32) {                                 // every block combines the partial norms in the same order
         float coef = 1.f;
@@ -1225,7 +1230,9 @@ __device__ __forceinline__ float scale_noise(float x) {    // x.sign() * x.abs()
 }
 
 template <bool kPhilox>
-__global__ void noise_reset_kernel(NoiseTable t, const float *__restrict__ normals, uint64_t seed, uint64_t offset) {
+__global__ void noise_reset_kernel(NoiseTable t, const float *__restrict__ normals, uint64_t seed, uint64_t offset,
+                                   const b2rl_step_state *__restrict__ state = nullptr, int which = 0) {
+    if (state) offset = state->noise_offset[which];
     const NoiseSeg sg = t.s[blockIdx.y];
     const int64_t n = (int64_t)sg.in * sg.out;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
@@ -1256,7 +1263,7 @@ static int64_t build_noise_table(const b2rl_net_desc &net, float *eps, NoiseTabl
 }
 
 static int noise_reset(const b2rl_net_desc &net, float *eps, const float *normals, uint64_t seed, uint64_t offset,
-                       cudaStream_t s) {
+                       cudaStream_t s, const b2rl_step_state *state = nullptr, int which = 0) {
     NoiseTable t;
     build_noise_table(net, eps, t);
     if (t.n == 0) return B2RL_OK;
@@ -1268,7 +1275,7 @@ static int noise_reset(const b2rl_net_desc &net, float *eps, const float *normal
     int bx = (int)((maxn + 255) / 256);
     if (bx > 64) bx = 64;
     if (normals) noise_reset_kernel<false><<<dim3(bx, t.n), 256, 0, s>>>(t, normals, 0, 0);
-    else noise_reset_kernel<true><<<dim3(bx, t.n), 256, 0, s>>>(t, nullptr, seed, offset);
+    else noise_reset_kernel<true><<<dim3(bx, t.n), 256, 0, s>>>(t, nullptr, seed, offset, state, which);
     B2RL_LAUNCH_CHECK();
     return B2RL_OK;
 }
@@ -1305,7 +1312,7 @@ static int optim_step(const b2rl_net_desc &net, const b2rl_learn_cfg &cfg, const
     int blocks = (int)((n + 255) / 256);
     if (blocks > sm_count() * 4) blocks = sm_count() * 4;
     adam_polyak_kernel<<<blocks, 256, 0, s>>>(bufs.actor_params, bufs.grads, bufs.exp_avg, bufs.exp_avg_sq,
-                                              bufs.target_params, n, ws.norm_partials, kNormBlocks, c);
+                                              bufs.target_params, n, ws.norm_partials, kNormBlocks, c, bufs.step_state);
     B2RL_LAUNCH_CHECK();
     return B2RL_OK;
 }
@@ -1480,6 +1487,12 @@ static int net_forward(const b2rl_net_desc *net_host, const float *params, const
     q_argmax_kernel<<<(int)((rows + 127) / 128), 128, 0, s>>>(ws.pass.val[net.n_val - 1].a, A, rows, out, argmax_out);
     B2RL_LAUNCH_CHECK();
     return B2RL_OK;
+}
+
+int b2rl_noise_reset_state(const b2rl_net_desc *net_host, float *eps, uint64_t seed, const b2rl_step_state *state,
+                           int which, void *stream) {
+    B2RL_CHECK_ARG(net_host && eps && state && (which == 0 || which == 1), "bad arguments");
+    return noise_reset(*net_host, eps, nullptr, seed, 0, as_stream(stream), state, which);
 }
 
 int b2rl_net_forward_q(const b2rl_net_desc *net_host, const float *params, const float *eps, int use_noise,

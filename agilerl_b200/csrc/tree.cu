@@ -342,7 +342,8 @@ __global__ void per_sample_kernel(const double *__restrict__ st, const double *_
                                   float *__restrict__ out_w, const float *__restrict__ action_ring,
                                   const float *__restrict__ reward_ring, const float *__restrict__ done_ring,
                                   float *__restrict__ out_action, float *__restrict__ out_reward,
-                                  float *__restrict__ out_done) {
+                                  float *__restrict__ out_done, const b2rl_step_state *__restrict__ state = nullptr) {
+    if (state) { beta = state->beta; size = state->size; offset = state->sample_offset; }   // graph-replayed step
     // the top levels of the sum tree are walked by every sample: stage them once per CTA (one coalesced
     // load instead of ten dependent L2 round trips per thread)
     constexpr int kTop = 1024;
@@ -559,6 +560,20 @@ int b2rl_per_sample_fused(const double *sum_tree, const double *min_tree, int64_
         per_sample_kernel<true><<<(int)((B + 63) / 64), 64, 0, as_stream(stream)>>>(
             sum_tree, min_tree, cap, nullptr, seed, offset, B, beta, size, out_idx, out_w, action_ring, reward_ring,
             done_ring, out_action, out_reward, out_done);
+    B2RL_LAUNCH_CHECK();
+    return B2RL_OK;
+}
+
+int b2rl_per_sample_fused_state(const double *sum_tree, const double *min_tree, int64_t cap, uint64_t seed,
+                                const b2rl_step_state *state, int64_t B, const float *action_ring,
+                                const float *reward_ring, const float *done_ring, int64_t *out_idx, float *out_w,
+                                float *out_action, float *out_reward, float *out_done, void *stream) {
+    B2RL_CHECK_ARG(is_pow2(cap), "capacity must be positive and a power of 2.");
+    B2RL_CHECK_ARG(B > 0 && out_idx && state, "bad sample arguments");
+    B2RL_CHECK_ARG(action_ring && reward_ring && done_ring && out_action && out_reward && out_done, "NULL ring field");
+    per_sample_kernel<true><<<(int)((B + 63) / 64), 64, 0, as_stream(stream)>>>(
+        sum_tree, min_tree, cap, nullptr, seed, 0, B, 0.0, 0, out_idx, out_w, action_ring, reward_ring, done_ring,
+        out_action, out_reward, out_done, state);
     B2RL_LAUNCH_CHECK();
     return B2RL_OK;
 }

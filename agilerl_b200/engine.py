@@ -51,6 +51,84 @@ class NetBuffers:
 import os as _os
 
 _SIDE = int(_os.environ["B2RL_SIDE_STREAMS"]) if "B2RL_SIDE_STREAMS" in _os.environ else None
+_GRAPH = _os.environ.get("B2RL_GRAPH", "1") != "0"      # CUDA-graph replay of the fused step (0: always eager)
+
+
+class _FusedPlan:
+    """Static buffers and the two captured graphs of one fused-step configuration of an engine."""
+
+    def __init__(self, eng, per, nmem, B, support, hp, gamma_n, weights_mode, side_streams):
+        dev = eng.device
+        self.eng, self.per, self.nmem, self.B = eng, per, nmem, B
+        self.support, self.hp, self.gamma_n = support, dict(hp), gamma_n
+        self.weights_mode, self.side_streams = weights_mode, side_streams
+        self.idx = torch.empty(B, dtype=torch.int64, device=dev)
+        self.w, self.a, self.r, self.d = (torch.empty(B, dtype=torch.float32, device=dev) for _ in range(4))
+        self.loss_elem = torch.empty(B, dtype=torch.float32, device=dev)
+        self.out = torch.empty(B + 1, dtype=torch.float32, device=dev)          # priorities | scalar loss
+        self.state_host = _lib.StepState()
+        self.state_dev = torch.zeros(ctypes.sizeof(_lib.StepState), dtype=torch.uint8, device=dev)
+        self.front = self.tail = None
+        self.fwd_done, self.done = torch.cuda.Event(), torch.cuda.Event()
+        self.kernels = 0
+
+    def capture(self) -> None:
+        eng, per, nmem, B = self.eng, self.per, self.nmem, self.B
+        lib = eng.lib
+        desc = ctypes.byref(eng.layout.desc)
+        f = nmem._fields
+        dk = nmem.done_key or "done"
+        batch = dict(obs=f[("obs",)], next_obs=f[(nmem.ns_key,)], action=self.a, reward=self.r, done=self.d)
+        hp = self.hp
+        cfg = eng._cfg(B, gamma=self.gamma_n, v_min=hp["v_min"], v_max=hp["v_max"], delta_z=hp["delta_z"],
+                       weights_mode=self.weights_mode, driver_shapes=0, clip=1, lr=hp["lr"], tau=hp["tau"],
+                       prior_eps=hp["prior_eps"], accumulate=0, use_noise=1, step=1, side_streams=self.side_streams)
+        bufs, keep = eng._bufs(B, batch, self.w, self.support, self.loss_elem, self.out[:B], self.out[B:], None, self.idx)
+        bufs.step_state = self.state_dev.data_ptr()
+        self._keep = (keep, cfg, bufs)
+        cap = torch.cuda.Stream(device=eng.device)
+        cap.wait_stream(torch.cuda.current_stream(eng.device))
+        s = cap.cuda_stream
+        gh = ctypes.c_void_p()
+        # ---- front: state write -> sample -> forwards/projection/loss -> priority write-back
+        _lib.check(lib.b2rl_graph_begin(s))
+        try:
+            _lib.check(lib.b2rl_step_state_write(ctypes.byref(self.state_host), self.state_dev.data_ptr(), s))
+            _lib.check(lib.b2rl_per_sample_fused_state(
+                per.sum_tree.data_ptr, per.min_tree.data_ptr, per._cap, per._philox_seed, self.state_dev.data_ptr(), B,
+                f[("action",)].data_ptr(), f[(nmem.reward_key,)].data_ptr(), f[(dk,)].data_ptr(), self.idx.data_ptr(),
+                self.w.data_ptr(), self.a.data_ptr(), self.r.data_ptr(), self.d.data_ptr(), s))
+            _lib.check(lib.b2rl_rainbow_loss(desc, ctypes.byref(cfg), ctypes.byref(bufs), s))
+            _lib.check(lib.b2rl_tree_set_from_priorities(
+                per.sum_tree.data_ptr, per.min_tree.data_ptr, per._cap, self.idx.data_ptr(), self.out.data_ptr(), B,
+                float(per.alpha), 1e-5, per._max_priority_dev.data_ptr(), s))
+        finally:
+            _lib.check(lib.b2rl_graph_end(s, ctypes.byref(gh)))
+        self.front = gh.value
+        # ---- tail: backward -> clip/Adam/Polyak -> noise reset (actor, then target: dqn_rainbow.py:484-485)
+        gt = ctypes.c_void_p()
+        _lib.check(lib.b2rl_graph_begin(s))
+        try:
+            _lib.check(lib.b2rl_rainbow_backward(desc, ctypes.byref(cfg), ctypes.byref(bufs), s))
+            _lib.check(lib.b2rl_optim_step(desc, ctypes.byref(cfg), ctypes.byref(bufs), s))
+            _lib.check(lib.b2rl_noise_reset_state(desc, eng.actor.eps.data_ptr(), eng.philox_seed,
+                                                  self.state_dev.data_ptr(), 0, s))
+            _lib.check(lib.b2rl_noise_reset_state(desc, eng.target.eps.data_ptr(), eng.philox_seed,
+                                                  self.state_dev.data_ptr(), 1, s))
+        finally:
+            _lib.check(lib.b2rl_graph_end(s, ctypes.byref(gt)))
+        self.tail = gt.value
+        n = ctypes.c_int(0)
+        for g in (self.front, self.tail):
+            _lib.check(lib.b2rl_graph_kernel_count(g, ctypes.byref(n)))
+            self.kernels += n.value
+
+    def destroy(self) -> None:
+        lib = self.eng.lib
+        for g in (self.front, self.tail):
+            if g:
+                lib.b2rl_graph_destroy(g)
+        self.front = self.tail = None
 
 
 class LearnEngine:
@@ -69,6 +147,14 @@ class LearnEngine:
         self.philox_seed = 0xB200
         self._host_out: dict = {}
         self.philox_offset = 0
+        self._plans: dict = {}
+
+    def __del__(self):
+        try:
+            for plan in self._plans.values():
+                plan.destroy()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
 
     # -- scratch -------------------------------------------------------------------------------
     # -- two-stream learn ----------------------------------------------------------------------
@@ -309,10 +395,60 @@ class LearnEngine:
         self._keepalive = keep
         return loss_scalar
 
+    # -- fused HBM-resident step, CUDA-graph replay ----------------------------------------------
+    def _plan_key(self, per, nmem, B, support, hp, gamma_n, weights_mode, side_streams):
+        f = nmem._fields
+        return (id(per), id(nmem), B, weights_mode, side_streams, float(gamma_n), support.data_ptr(),
+                float(hp["v_min"]), float(hp["v_max"]), float(hp["delta_z"]), float(hp["tau"]), float(hp["prior_eps"]),
+                per.sum_tree.data_ptr, per.min_tree.data_ptr, per._cap, float(per.alpha), per._philox_seed,
+                f[("obs",)].data_ptr(), f[(nmem.ns_key,)].data_ptr(), f[("action",)].data_ptr())
+
+    def _fused_graph_step(self, per, nmem, *, B, beta, support, hp, gamma_n, weights_mode, overlap, side_streams):
+        """``rainbow_fused_step`` with the whole chain replayed from two CUDA graphs per (agent, replay pair, B):
+        *front* = step-state write -> PER sample -> 3 forwards -> projection / loss -> priority write-back (the part
+        the next agent's sampler depends on) and *tail* = backward -> clip/Adam/Polyak -> noise reset x2.  The first
+        call of a plan runs eagerly (it also creates the library's side streams and kernel attributes), the second
+        captures, every later one replays.  The replay reads this step's scalars (beta, len(memory), Philox
+        offsets, Adam's lr and bias corrections) from a device block its first node rewrites — same arithmetic,
+        same random streams and bit-identical results as the eager path (tests/test_graph_gpu.py)."""
+        key = self._plan_key(per, nmem, B, support, hp, gamma_n, weights_mode, side_streams)
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = self._plans[key] = _FusedPlan(self, per, nmem, B, support, hp, gamma_n, weights_mode, side_streams)
+            return None                                   # caller runs this step eagerly
+        st = plan.state_host
+        st.beta, st.size = float(beta), int(per._size)
+        st.sample_offset = per._philox_offset
+        st.noise_offset[0] = self.philox_offset
+        st.noise_offset[1] = self.philox_offset + self.noise_count
+        self.step += 1
+        st.lr = float(hp["lr"])
+        st.bias_correction1 = 1.0 - 0.9 ** self.step
+        st.bias_correction2 = 1.0 - 0.999 ** self.step
+        per._philox_offset += B
+        self.philox_offset += 2 * self.noise_count
+        if plan.front is None:
+            plan.capture()
+        lib, cur = self.lib, _lib.stream_ptr(self.device)
+        _lib.check(lib.b2rl_graph_launch(plan.front, ctypes.byref(st), cur))
+        per._dev_dirty = True
+        if overlap:
+            fwd_done = plan.fwd_done
+            fwd_done.record(torch.cuda.current_stream(self.device))
+            if self._bwd_stream is None:
+                self._bwd_stream = torch.cuda.Stream(device=self.device)
+            self._bwd_stream.wait_event(fwd_done)
+            _lib.check(lib.b2rl_graph_launch(plan.tail, None, self._bwd_stream.cuda_stream))
+            plan.done.record(self._bwd_stream)
+            self._opt_done = plan.done
+        else:
+            _lib.check(lib.b2rl_graph_launch(plan.tail, None, cur))
+        return plan.out[B:], plan.idx, plan.out[:B]
+
     # -- fused HBM-resident step ---------------------------------------------------------------
     def rainbow_fused_step(self, per, n_step_memory, *, B: int, beta: float, support: torch.Tensor, hp: dict,
                            gamma_n: float, weights_mode: int = 1, uniforms=None, noise_normals=None,
-                           overlap: bool = False, side_streams: int | None = None):
+                           overlap: bool = False, side_streams: int | None = None, graph: bool | None = None):
         """One gradient step with the replay resident in HBM and no host round trip:
         sample (tree descent + IS weights + n-step scalars, one kernel) -> learn with the encoder
         reading frames from the ring through the sampled indices -> priorities written back into
@@ -323,6 +459,17 @@ class LearnEngine:
         sharing the buffer) sees exactly the tree the sequential loop would show it, while this
         agent's backward + optimiser still run on its own stream."""
         self.join()
+        if graph is None:
+            graph = _GRAPH
+        if graph and uniforms is None and noise_normals is None and per.device_rng and self.noise_count > 0:
+            if _SIDE is not None:
+                side_streams = _SIDE
+            elif side_streams is None:
+                side_streams = 1 if overlap else 3
+            out = self._fused_graph_step(per, n_step_memory, B=B, beta=beta, support=support, hp=hp, gamma_n=gamma_n,
+                                         weights_mode=weights_mode, overlap=overlap, side_streams=side_streams)
+            if out is not None:
+                return out
         idx, w, a, r, d = per.sample_fused(B, beta, n_step_memory, uniforms)
         f = n_step_memory._fields
         batch = dict(obs=f[("obs",)], next_obs=f[(n_step_memory.ns_key,)], action=a, reward=r, done=d)

@@ -37,6 +37,18 @@ unsigned long long b2rl_launch_count(void);
 /* Device properties the host side sizes grids with (SM count, etc.). */
 int b2rl_device_sm_count(int device, int *out_host);
 
+/* Per-step scalars of a CUDA-graph-replayed gradient step: everything the host changes from one step to the next
+ * (the driver-annealed beta, len(memory), Philox offsets, Adam's bias corrections / lr).  A captured step reads them
+ * from a DEVICE copy of this struct; b2rl_graph_launch rewrites that copy through the graph's first node, so the
+ * host's double arithmetic (CPython's `1 - beta**step`, `lr / bias_correction1`) stays the source of the values. */
+typedef struct b2rl_step_state {
+    double beta;                        /* PER importance exponent (train_off_policy.py:346-351 anneals it) */
+    int64_t size;                       /* len(memory) */
+    uint64_t sample_offset;             /* Philox offset of the B sampling uniforms */
+    uint64_t noise_offset[2];           /* Philox offsets of the actor / target noise reset */
+    double lr, bias_correction1, bias_correction2;   /* torch.optim.Adam scalars of this step */
+} b2rl_step_state;
+
 /* ------------------------------------------------------------------------------------------
  * Priority trees — agilerl/components/segment_tree.py (SumSegmentTree / MinSegmentTree).
  * Layout: array heap of 2*cap fp64 per tree, node i has children 2i, 2i+1, leaf j at cap+j,
@@ -94,6 +106,11 @@ int b2rl_per_sample_fused(const double *sum_tree, const double *min_tree, int64_
                           const float *reward_ring, const float *done_ring, int64_t *out_idx,
                           float *out_w, float *out_action, float *out_reward, float *out_done,
                           void *stream);
+/* Same, with beta / size / the Philox offset read on device from *state (graph-replayed steps; Philox only). */
+int b2rl_per_sample_fused_state(const double *sum_tree, const double *min_tree, int64_t cap, uint64_t seed,
+                                const b2rl_step_state *state, int64_t B, const float *action_ring,
+                                const float *reward_ring, const float *done_ring, int64_t *out_idx, float *out_w,
+                                float *out_action, float *out_reward, float *out_done, void *stream);
 
 /* Read-back of the device random streams (parity tests hand them to the oracle): the B float32 uniforms
  * b2rl_per_sample_philox / b2rl_per_sample_fused(uniforms = NULL) consume at (seed, offset), and the
@@ -185,6 +202,9 @@ int b2rl_noise_reset_from_normals(const b2rl_net_desc *net_host, float *eps, con
 /* Same with normals drawn on device: Philox4x32-10(seed, subsequence = layer, offset). */
 int b2rl_noise_reset_philox(const b2rl_net_desc *net_host, float *eps, uint64_t seed,
                             uint64_t offset, void *stream);
+/* Same, offset = state->noise_offset[which] read on device (which: 0 actor, 1 target). */
+int b2rl_noise_reset_state(const b2rl_net_desc *net_host, float *eps, uint64_t seed, const b2rl_step_state *state,
+                           int which, void *stream);
 /* Number of standard normals one reset consumes. */
 int b2rl_noise_count(const b2rl_net_desc *net_host, int64_t *out_host);
 
@@ -278,6 +298,8 @@ typedef struct b2rl_learn_bufs {
     float *loss_scalar;                      /* out: 1, the scalar loss that was back-propagated */
     float *proj_dist;                        /* out (nullable): B x n_atoms projected target */
     void *workspace; size_t workspace_bytes;
+    const b2rl_step_state *step_state;       /* nullable DEVICE pointer: when set, b2rl_optim_step takes lr and the bias
+                                                corrections from it instead of cfg (graph-replayed steps) */
 } b2rl_learn_bufs;
 
 /* RainbowDQN._dqn_loss (dqn_rainbow.py:284-367): three forwards, C51 projection, cross-entropy;
@@ -297,6 +319,24 @@ int b2rl_dqn_learn(const b2rl_net_desc *net_host, const b2rl_learn_cfg *cfg_host
 /* Whole Rainbow learn step for the common case (one loss pass): loss + backward + optim. */
 int b2rl_rainbow_learn(const b2rl_net_desc *net_host, const b2rl_learn_cfg *cfg_host,
                        const b2rl_learn_bufs *bufs_host, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * CUDA graphs: the ~40 dependent launches of a gradient step captured once and replayed per step.
+ * b2rl_graph_begin puts `stream` into capture (relaxed mode; library-owned side streams fork from and join back
+ * into it); every b2rl_* call made on it until b2rl_graph_end is recorded instead of executed.  If the captured
+ * work starts with b2rl_step_state_write, b2rl_graph_launch patches that node's by-value argument with
+ * *state_host before launching, which is how a replay sees this step's scalars.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct b2rl_graph b2rl_graph;
+/* *state_dev <- *state_host (one tiny kernel; the struct travels by value in the launch). */
+int b2rl_step_state_write(const b2rl_step_state *state_host, b2rl_step_state *state_dev, void *stream);
+int b2rl_graph_begin(void *stream);
+int b2rl_graph_end(void *stream, b2rl_graph **out_host);
+/* state_host may be NULL when the graph holds no b2rl_step_state_write node. */
+int b2rl_graph_launch(b2rl_graph *g, const b2rl_step_state *state_host, void *stream);
+/* kernel nodes in the graph (what one replay adds to b2rl_launch_count) */
+int b2rl_graph_kernel_count(const b2rl_graph *g, int *out_host);
+int b2rl_graph_destroy(b2rl_graph *g);
 
 #ifdef __cplusplus
 }

@@ -67,7 +67,7 @@ def ring():
         mem.add(TensorDict(small, batch_size=[n]))      # the PER buffer's own frames are never read on this path
     cg = torch.Generator().manual_seed(7)
     pri = torch.randn(ROWS, generator=cg).abs() + 1e-6
-    pri[TOP:] *= (TOP / (ROWS - TOP))                   # equal mass below and above the 2^32-byte line
+    pri[TOP:] *= (TOP / (ROWS - TOP)) ** (1.0 / ALPHA)  # equal p**alpha mass below and above the 2^32-byte line
     pri = pri.numpy().astype(np.float32)
     omem = oreplay.OraclePER(ROWS, ALPHA)
     omem.size = ROWS
