@@ -583,7 +583,7 @@ static long long *tc_debug_buffer() {
 static inline size_t conv_tc_wsplit_floats(const b2rl_layer &l) {
     const int K = l.in_c * l.ksize * l.ksize;
     const int n_pad = (l.out_c + 15) / 16 * 16, k_pad = (K + kTcBK - 1) / kTcBK * kTcBK;
-    return (size_t)2 * n_pad * k_pad + k_pad;      // hi, lo, tap offsets
+    return (size_t)2 * n_pad * k_pad + k_pad + 4 * n_pad + 64;      // hi, lo, tap offsets (+ room for the int8 digit path's scales)
 }
 
 // returns B2RL_OK, or 1 when the shape is outside what the tensor-core kernel handles (caller falls

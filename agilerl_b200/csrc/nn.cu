@@ -19,6 +19,7 @@
 #include <type_traits>
 
 #include "conv_tc.cuh"
+#include "conv_i8.cuh"
 #include "head_fused.cuh"
 #include "gemm.cuh"
 #include <cstdlib>
@@ -394,8 +395,23 @@ static int layer_forward(const b2rl_net_desc &net, const b2rl_layer &l, const fl
                          int64_t rows, const LayerBuf &lb, const Scratch &sc, cudaStream_t s) {
     const int64_t oe = layer_out_elems(l);
     const bool first = x_prev == nullptr;
-    const int n_runs = first ? n_chunks : 1;
+    int n_runs = first ? n_chunks : 1;
     int64_t row0 = 0;
+    // uint8 frames with integer bounds: integer tensor path, every chunk in ONE launch (conv_i8.cuh)
+    if (first && tc_enabled() && n_chunks >= 1 && n_chunks <= kI8MaxSegs &&
+        conv_i8_ok(l, net.obs_u8 != 0, net.normalize != 0, net.obs_low, net.obs_high, chunks[0].ptr, 1) &&
+        (n_chunks == 1 || reinterpret_cast<uintptr_t>(chunks[1].ptr) % 4 == 0)) {
+        ConvI8Job jobs[kI8MaxSegs];
+        int64_t r0 = 0;
+        for (int i = 0; i < n_chunks; ++i) {
+            jobs[i] = ConvI8Job{chunks[i].ptr, chunks[i].gather, chunks[i].rows, 1, {lb.a + r0 * oe, nullptr}};
+            r0 += chunks[i].rows;
+        }
+        const float *Ws[2] = {W, W}, *bs[2] = {bias, bias};
+        const int rc8 = launch_conv_fwd_i8(l, net.normalize != 0, net.obs_low, net.obs_high, Ws, bs, 1, jobs, n_chunks,
+                                           sc.partial, sc.floats * sizeof(float), s);
+        if (rc8 != 1) return rc8;
+    }
     for (int run = 0; run < n_runs; ++run) {
         const int64_t r = first ? chunks[run].rows : rows;
         Operand A, Bm;
@@ -473,9 +489,10 @@ static inline const float *eff_b(const b2rl_layer &l, const float *params, const
 
 static int forward_pass(const b2rl_net_desc &net, const float *params, const float *weff, bool use_noise,
                         const ObsChunk *chunks, int n_chunks, int64_t rows, PassBufs &pb, const Scratch &sc,
-                        cudaStream_t s) {
+                        cudaStream_t s, bool first_done = false) {     // first_done: pb.enc[0].a already holds layer 0's output
     const float *x = nullptr;
     for (int i = 0; i < net.n_enc; ++i) {
+        if (i == 0 && first_done) { x = pb.enc[0].a; continue; }
         const b2rl_layer &l = net.enc[i];
         int rc = layer_forward(net, l, eff_w(l, params, weff, use_noise), eff_b(l, params, weff, use_noise), params, x,
                                chunks, n_chunks, rows, pb.enc[i], sc, s);
@@ -1332,6 +1349,27 @@ static int rainbow_loss(const b2rl_net_desc &net, const b2rl_learn_cfg &cfg, con
     // target network on next_obs (forward #2) on a side stream, concurrently with the online pass
     static const bool fork_env = !(getenv("B2RL_NO_FORK") && getenv("B2RL_NO_FORK")[0] == '1');
     const bool fork_on = fork_env && (cfg.side_streams & 1);
+    // First layer over uint8 frames: the online and the target network both read next_obs (dqn_rainbow.py:306-318), so
+    // one launch gathers every frame once — next_obs against [W_online | W_target] (256 accumulator columns), obs
+    // against W_online — before the target chain forks off (conv_i8.cuh).
+    bool shared_first = false;
+    {
+        const b2rl_layer &l0 = net.enc[0];
+        if (tc_enabled() && !l0.noisy &&
+            conv_i8_ok(l0, net.obs_u8 != 0, net.normalize != 0, net.obs_low, net.obs_high, bufs.next_obs, 2) &&
+            reinterpret_cast<uintptr_t>(bufs.obs) % 4 == 0) {
+            const int64_t oe = layer_out_elems(l0);
+            ConvI8Job jobs[2] = {
+                ConvI8Job{bufs.next_obs, bufs.row_idx, B, 2, {ws.online.enc[0].a, ws.target.enc[0].a}},
+                ConvI8Job{bufs.obs, bufs.row_idx, B, 1, {ws.online.enc[0].a + B * oe, nullptr}}};
+            const float *Ws[2] = {bufs.actor_params + l0.w_off, bufs.target_params + l0.w_off};
+            const float *bs[2] = {bufs.actor_params + l0.b_off, bufs.target_params + l0.b_off};
+            rc = launch_conv_fwd_i8(l0, net.normalize != 0, net.obs_low, net.obs_high, Ws, bs, 2, jobs, 2, ws.partial,
+                                    ws.partial_floats * sizeof(float), s);
+            if (rc == B2RL_OK) shared_first = true;
+            else if (rc != 1) return rc;
+        }
+    }
     ForkJoin *fj = nullptr;
     cudaStream_t st = s;
     if (fork_on) {
@@ -1342,12 +1380,14 @@ static int rainbow_loss(const b2rl_net_desc &net, const b2rl_learn_cfg &cfg, con
     }
     ObsChunk tg_chunk{bufs.next_obs, bufs.row_idx, B};
     Scratch sc_tg{ws.partial_tg, ws.partial_tg_floats};
-    if ((rc = forward_pass(net, bufs.target_params, ws.weff_target, noise, &tg_chunk, 1, B, ws.target, sc_tg, st)) != B2RL_OK)
+    if ((rc = forward_pass(net, bufs.target_params, ws.weff_target, noise, &tg_chunk, 1, B, ws.target, sc_tg, st,
+                           shared_first)) != B2RL_OK)
         return rc;
     if (fork_on) B2RL_CUDA(cudaEventRecord(fj->join, fj->side));
     // online network on [next_obs ; obs]  (forwards #1 and #3 of _dqn_loss share weights and noise)
     ObsChunk on_chunks[2] = {{bufs.next_obs, bufs.row_idx, B}, {bufs.obs, bufs.row_idx, B}};
-    if ((rc = forward_pass(net, bufs.actor_params, ws.weff_actor, noise, on_chunks, 2, 2 * B, ws.online, sc, s)) != B2RL_OK)
+    if ((rc = forward_pass(net, bufs.actor_params, ws.weff_actor, noise, on_chunks, 2, 2 * B, ws.online, sc, s,
+                           shared_first)) != B2RL_OK)
         return rc;
     if (fork_on) B2RL_CUDA(cudaStreamWaitEvent(s, fj->join, 0));
     const float *v_on = ws.online.val[net.n_val - 1].a, *adv_on = ws.online.adv[net.n_adv - 1].a;

@@ -395,3 +395,47 @@ def test_odd_batch_sizes_match_oracle(B):
         ref = ref * coef
         scale = max(ref.abs().max().item(), 1e-6)
         assert (got - ref).abs().max().item() <= 2e-5 * scale + 1e-8, f"grad {k}"
+
+
+@pytest.mark.parametrize("cin,hw,k,s,cout,rows", [
+    (4, 84, 8, 4, 32, 37),       # the north-star first layer; 37 images: last tile ragged
+    (1, 36, 4, 4, 16, 5),        # one k-step, 16 channels
+    (3, 40, 8, 4, 24, 9),        # Cout not a multiple of 16 (padded digit planes), K = 192
+    (4, 64, 8, 8, 64, 3),        # 64 channels: 256 accumulator columns for one weight set
+])
+def test_first_layer_int8_digit_conv_matches_float64(cin, hw, k, s, cout, rows):
+    """conv_fwd_i8_kernel (tcgen05 kind::i8 over raw frame bytes, weights as four int8 digit planes) through the
+    layer hook, against a float64 convolution of (x - low) / (high - low): <= 2e-6 of the output scale — tighter
+    than the fp32 reference itself — for gathered ring rows, a ragged last tile and padded channel counts."""
+    import ctypes
+    from agilerl_b200 import _lib
+    from agilerl_b200.networks.spec import FlatLayout, rainbow_spec
+    g = torch.Generator().manual_seed(cin * 1000 + cout)
+    spec = rainbow_spec((cin, hw, hw), 3, channel_size=(cout,), kernel_size=(k,), stride_size=(s,), latent_dim=16,
+                        hidden_size=(16,), obs_low=0.0, obs_high=255.0, obs_u8=True)
+    layout = FlatLayout(spec)
+    desc = layout.desc
+    L = desc.enc[0]
+    params = torch.zeros(layout.n_params)
+    w = torch.randn(cout, cin, k, k, generator=g) * (1.0 / (cin * k * k) ** 0.5)
+    w[0] *= 1e-3                                      # a channel far below the others: per-channel scales matter
+    w[1, :, :, : k // 2] = 0.0
+    b = torch.randn(cout, generator=g) * 0.1
+    params[L.w_off:L.w_off + w.numel()] = w.reshape(-1)
+    params[L.b_off:L.b_off + cout] = b
+    ring = torch.randint(0, 256, (64, cin, hw, hw), dtype=torch.uint8, generator=g)
+    idx = torch.randint(0, 64, (rows,), generator=g)
+    ref = torch.nn.functional.conv2d(ring[idx].double() / 255.0, w.double(), b.double(), stride=s).relu()
+    out = torch.empty(ref.shape, dtype=torch.float32, device="cuda")
+    ws = torch.empty(16 << 20, dtype=torch.uint8, device="cuda")
+    pd, rd, id_ = params.cuda(), ring.cuda(), idx.cuda()
+    lib = _lib.load()
+    n0 = lib.b2rl_launch_count()
+    _lib.check(lib.b2rl_encoder_layer_forward(ctypes.byref(desc), 0, pd.data_ptr(), rd.data_ptr(), id_.data_ptr(), rows,
+                                              out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(torch.device("cuda:0"))))
+    torch.cuda.synchronize()
+    assert lib.b2rl_launch_count() - n0 == 2, "expected the digit-split + int8 convolution launches"
+    err = (out.cpu().double() - ref).abs().max().item()
+    assert err <= 2e-6 * max(1.0, ref.abs().max().item()), err
+    # low-magnitude channel: relative accuracy is kept by the per-channel scale
+    assert (out.cpu().double()[:, 0] - ref[:, 0]).abs().max().item() <= 2e-6 * max(1e-3, ref[:, 0].abs().max().item())
