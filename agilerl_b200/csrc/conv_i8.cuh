@@ -32,7 +32,6 @@
 
 namespace b2rl {
 
-constexpr int kI8Threads = 256 + 32;   // 8 gather/epilogue warps + the MMA warp
 constexpr int kI8MaxSegs = 2;
 
 struct ConvI8Seg {
@@ -50,18 +49,16 @@ struct ConvI8Params {
     const int8_t *wd;          // digit planes of both weight sets in the smem tile layout: rows = net*4*n_pad + digit*n_pad + n
     const float *scale;        // [nets_total * n_pad]   2^(e_c - 30) / (high - low)
     const float *bias[2];      // [Cout] per weight set
-    const uint32_t *koff4;     // [k_pad / 4] input offset of every group of 4 consecutive taps
     int64_t in_bstride;        // Cin*H*W
     int N, n_pad, k_pad;       // Cout, Cout rounded up to 16, Cin*k*k rounded up to 32
     int nets_total;            // weight sets resident in wd (1 or 2)
     int P, OW, sy, sx;         // output pixels per image, output width, in-row stride (s*W), in-col stride (s)
     int act;
-    float low;                 // integer lower bound: D is computed on raw bytes, low * sum_k w is folded into the bias term
+    int Cin, HW, W;            // input channels, plane size, row pitch (the gather walks kernel rows with running pointers)
 };
 
 static inline size_t conv_i8_smem_bytes(int n_pad, int k_pad, int nets_total) {
-    return (size_t)kTcBM * k_pad + (size_t)nets_total * 4 * n_pad * k_pad + (size_t)k_pad + 2 * (size_t)nets_total * n_pad * 4 +
-           256 + 1024;
+    return 2 * (size_t)kTcBM * k_pad + (size_t)nets_total * 4 * n_pad * k_pad + 2 * (size_t)nets_total * n_pad * 4 + 256 + 1024;
 }
 // scratch the launcher needs (bytes): digit planes + scales + low-correction + tap-group offsets
 static inline size_t conv_i8_scratch_bytes(int n_pad, int k_pad, int nets_total) {
@@ -72,8 +69,7 @@ static inline size_t conv_i8_scratch_bytes(int n_pad, int k_pad, int nets_total)
 // weight, stored where the conv kernel's bulk copy expects them.  Channel n of set `net` is row net*4*n_pad + d*n_pad + n.
 __global__ void weight_digits_kernel(const float *__restrict__ w0, const float *__restrict__ w1, int N, int K, int n_pad,
                                      int k_pad, int nets_total, double inv_range, float low, int8_t *__restrict__ wd,
-                                     float *__restrict__ scale, float *__restrict__ lowcorr, int KK, int KS, int HW, int W,
-                                     uint32_t *__restrict__ koff4) {
+                                     float *__restrict__ scale, float *__restrict__ lowcorr) {
     const int n = blockIdx.x, net = blockIdx.y;
     const float *w = net == 0 ? w0 : w1;
     __shared__ float red[32];
@@ -121,17 +117,6 @@ __global__ void weight_digits_kernel(const float *__restrict__ w0, const float *
         scale[net * n_pad + n] = sc;
         lowcorr[net * n_pad + n] = (float)(-(double)low * t * ldexp(1.0, e - 30) * inv_range);
     }
-    if (n == 0 && net == 0 && koff4)
-        for (int g = threadIdx.x; g < k_pad / 4; g += blockDim.x) {
-            const int k = g * 4;
-            uint32_t off = 0;                                         // padded taps read offset 0 against zero digits
-            if (k < K) {
-                const int ci = k / KK, rem = k - ci * KK;
-                const int ky = rem / KS, kx = rem - ky * KS;
-                off = (uint32_t)(ci * HW + ky * W + kx);
-            }
-            koff4[g] = off;
-        }
 }
 
 namespace tc {
@@ -162,47 +147,61 @@ __device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, u
 }
 }  // namespace tc
 
-// CPT = 16-tap chunks per gather thread (k_pad / 16 / 2): compile-time so the raw words stay in registers.
-template <int CPT>
-__global__ void __launch_bounds__(kI8Threads, (CPT <= 8 ? 3 : 2)) conv_fwd_i8_kernel(const ConvI8Params p) {
+// Persistent, warp-specialised kernel: one CTA per SM walks its tiles (128 output pixels each) through a three-stage
+// pipeline whose stages run concurrently on different warps —
+//   gather warps (8)   : frame bytes -> A stage s (two stages), running pointers instead of an offset table:
+//                        per 16 taps four 4-byte loads, two pointer bumps, one 16-byte store;
+//   MMA warp (1)       : k_pad/32 tcgen05.mma kind::i8 into TMEM accumulator s (two accumulators), commits free the
+//                        A stage and hand the accumulator over;
+//   epilogue warps (8) : TMEM -> digit recombination -> scale, bias, activation -> coalesced NCHW stores.
+// The digit planes of every weight set are copied into shared memory ONCE per CTA.  KS = kernel size (4 or 8, so
+// a kernel row is one or two aligned 4-byte groups), CPT = 16-tap chunks per gather thread (k_pad / 32).
+constexpr int kI8GatherWarps = 8, kI8EpiWarps = 8;
+constexpr int kI8ThreadsP = (kI8GatherWarps + 1 + kI8EpiWarps) * 32;
+
+template <int KS, int CPT>
+__global__ void __launch_bounds__(kI8ThreadsP, 1) conv_fwd_i8_kernel(const ConvI8Params p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    const int tid = threadIdx.x, warp = tid >> 5;
-    // which segment (input rows x weight sets) this CTA belongs to
-    int si = 0;
-    if (p.n_seg > 1 && (int)blockIdx.x >= p.seg[1].cta0) si = 1;
-    const ConvI8Seg &sg = p.seg[si];
-    const int nets = sg.nets;
-    const int cta = (int)blockIdx.x - sg.cta0;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rows_b = p.nets_total * 4 * p.n_pad;                       // rows of the resident B tile
+    const int acc_cols = rows_b;                                         // columns of one accumulator buffer
     const uint32_t a_bytes = (uint32_t)kTcBM * p.k_pad, b_bytes = (uint32_t)rows_b * p.k_pad;
     const uint32_t sbase = (tc::smem_u32(smem_raw) + 127u) & ~127u;
-    const uint32_t a_s = sbase, b_s = sbase + a_bytes;
-    const uint32_t koff_a = b_s + b_bytes;                              // k_pad/4 words
-    const uint32_t scale_a = koff_a + (uint32_t)p.k_pad;                // nets_total*n_pad floats
+    const uint32_t a_s = sbase, b_s = sbase + 2 * a_bytes;
+    const uint32_t scale_a = b_s + b_bytes;                             // nets_total*n_pad floats (16-byte aligned)
     const uint32_t bias_a = scale_a + (uint32_t)p.nets_total * p.n_pad * 4;
     const uint32_t bars_a = (bias_a + (uint32_t)p.nets_total * p.n_pad * 4 + 15u) & ~15u;
     uint8_t *gen = smem_raw + (sbase - tc::smem_u32(smem_raw));
-    uint64_t *full_a = reinterpret_cast<uint64_t *>(gen + (bars_a - sbase));   // im2col tile written (8 warp arrivals)
-    uint64_t *full_b = full_a + 1;                                              // digit planes landed (tx count)
-    uint64_t *mma_done = full_a + 2;
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(full_a + 3);
+    uint64_t *full_a = reinterpret_cast<uint64_t *>(gen + (bars_a - sbase));   // [2] im2col stage written (8 warp arrivals)
+    uint64_t *empty_a = full_a + 2;                                             // [2] stage consumed (MMA commit)
+    uint64_t *acc_full = full_a + 4;                                            // [2] accumulator complete (MMA commit)
+    uint64_t *acc_empty = full_a + 6;                                           // [2] accumulator drained (8 warp arrivals)
+    uint64_t *full_b = full_a + 8;                                              // digit planes landed (tx count)
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(full_a + 9);
     const uint32_t lbo_a = kTcBM * 16, lbo_b = (uint32_t)rows_b * 16;
+    // tiles of this CTA: t = blockIdx.x + i * gridDim.x over [segment 0 tiles | segment 1 tiles]
+    const int tiles0 = (p.seg[0].M + kTcBM - 1) / kTcBM;
+    const int tiles1 = p.n_seg > 1 ? (p.seg[1].M + kTcBM - 1) / kTcBM : 0;
+    const int n_tiles = tiles0 + tiles1;
+    const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
     if (tid == 0) {
-        tc::mbar_init(full_a, 8);
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(&full_a[s], kI8GatherWarps);
+            tc::mbar_init(&empty_a[s], 1);
+            tc::mbar_init(&acc_full[s], 1);
+            tc::mbar_init(&acc_empty[s], kI8EpiWarps);
+        }
         tc::mbar_init(full_b, 1);
-        tc::mbar_init(mma_done, 1);
         tc::fence_barrier_init();
     }
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < nets * 4 * p.n_pad) tmem_cols <<= 1;
-    if (warp == 8) tc::tmem_alloc(tmem_ptr, tmem_cols);
-    for (int g = tid; g < p.k_pad / 4; g += kI8Threads)
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(koff_a + 4u * g), "r"(__ldg(p.koff4 + g)) : "memory");
-    for (int n = tid; n < p.nets_total * p.n_pad; n += kI8Threads) {
+    while ((int)tmem_cols < 2 * acc_cols) tmem_cols <<= 1;
+    if (warp == kI8GatherWarps) tc::tmem_alloc(tmem_ptr, tmem_cols);
+    for (int n = tid; n < p.nets_total * p.n_pad; n += kI8ThreadsP) {
         const int net = n / p.n_pad, c = n - net * p.n_pad;
         const float *bp = p.bias[net];
-        // bias + the low-bound correction of this channel (scale table holds [scale | lowcorr])
+        // bias + the low-bound correction of this channel (the scale table holds [scale | lowcorr])
         const float bv = ((c < p.N && bp) ? bp[c] : 0.f) + __ldg(p.scale + p.nets_total * p.n_pad + n);
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(scale_a + 4u * n), "f"(__ldg(p.scale + n)) : "memory");
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_a + 4u * n), "f"(bv) : "memory");
@@ -212,115 +211,156 @@ __global__ void __launch_bounds__(kI8Threads, (CPT <= 8 ? 3 : 2)) conv_fwd_i8_ke
     tc::tc_fence_after();
     const uint32_t tmem_d = *tmem_ptr;
 
-    if (warp == 8) {
-        // ---- MMA warp: one bulk copy brings every digit plane, then k_pad/32 MMAs over the resident tiles
+    if (warp == kI8GatherWarps) {
+        // ================================ MMA warp ================================
         if (tc::elect_one()) {
-            if (nets == p.nets_total) {
-                tc::mbar_expect_tx(full_b, b_bytes);
-                tc::bulk_g2s(b_s, p.wd, b_bytes, full_b);
-            } else {        // first weight set only: its rows are the leading part of every 16-tap column of the tile
-                const uint32_t part = (uint32_t)nets * 4 * p.n_pad * 16;
-                const int cols = p.k_pad / 16;
-                tc::mbar_expect_tx(full_b, part * cols);
-                for (int c = 0; c < cols; ++c) tc::bulk_g2s(b_s + c * lbo_b, p.wd + (size_t)c * lbo_b, part, full_b);
-            }
+            tc::mbar_expect_tx(full_b, b_bytes);
+            tc::bulk_g2s(b_s, p.wd, b_bytes, full_b);
         }
         __syncwarp();
         tc::mbar_wait(full_b, 0);
-        tc::mbar_wait(full_a, 0);
-        tc::tc_fence_after();
-        const uint32_t idesc = tc::make_idesc_i8(kTcBM, nets * 4 * p.n_pad);
-        const uint64_t da0 = tc::make_desc(a_s, lbo_a, 128), db0 = tc::make_desc(b_s, lbo_b, 128);
+        const uint64_t db0 = tc::make_desc(b_s, lbo_b, 128);
         const uint64_t da_step = (uint64_t)((2 * lbo_a) >> 4), db_step = (uint64_t)((2 * lbo_b) >> 4);
-        if (tc::elect_one()) {
-            const int steps = p.k_pad / 32;                          // one MMA k-step = 32 taps = 2 core-matrix columns
-            for (int j = 0; j < steps; ++j) tc::mma_i8(tmem_d, da0 + j * da_step, db0 + j * db_step, idesc, j ? 1u : 0u);
-            tc::mma_commit(mma_done);
+        for (int i = 0; i < my_tiles; ++i) {
+            const int t = (int)blockIdx.x + i * (int)gridDim.x;
+            const int nets = t < tiles0 ? p.seg[0].nets : p.seg[1].nets;
+            const int s = i & 1;
+            const uint32_t ph = (uint32_t)((i >> 1) & 1);
+            tc::mbar_wait(&acc_empty[s], ph ^ 1u);                   // epilogue has drained accumulator s (passes at first use)
+            tc::mbar_wait(&full_a[s], ph);
+            tc::tc_fence_after();
+            const uint32_t idesc = tc::make_idesc_i8(kTcBM, nets * 4 * p.n_pad);   // first weight set = leading rows of every column
+            const uint64_t da0 = tc::make_desc(a_s + (uint32_t)s * a_bytes, lbo_a, 128);
+            const uint32_t d_addr = tmem_d + (uint32_t)(s * acc_cols);
+            if (tc::elect_one()) {
+#pragma unroll
+                for (int j = 0; j < CPT; ++j)                         // one MMA k-step = 32 taps = 2 core-matrix columns
+                    tc::mma_i8(d_addr, da0 + j * da_step, db0 + j * db_step, idesc, j ? 1u : 0u);
+                tc::mma_commit(&empty_a[s]);
+                tc::mma_commit(&acc_full[s]);
+            }
+            __syncwarp();
         }
-        __syncwarp();
-    } else {
-        // ---- gather warps: thread = (im2col row, half of the taps); the raw frame bytes ARE the operand
+    } else if (warp < kI8GatherWarps) {
+        // ================================ gather warps ================================
+        // thread = (im2col row, half of the taps): channels [half*Cin/2, (half+1)*Cin/2), every kernel row of them
         const int row = tid & (kTcBM - 1), half = tid >> 7;
-        const int m = cta * kTcBM + row;
-        const bool row_ok = m < sg.M;
-        int64_t rowbase = sg.gather ? sg.gather[0] * p.in_bstride : 0;     // rows beyond M read a valid address
-        if (row_ok) {
-            const int b = m / p.P, pix = m - b * p.P;
-            const int oy = pix / p.OW, ox = pix - oy * p.OW;
-            const int64_t bb = sg.gather ? sg.gather[b] : (int64_t)b;
-            rowbase = bb * p.in_bstride + (int64_t)(oy * p.sy + ox * p.sx);
+        const uint32_t row_off = (uint32_t)(row >> 3) * 128 + (uint32_t)(row & 7) * 16 + (uint32_t)(half * CPT) * lbo_a;
+        const int64_t half_off = (int64_t)half * (p.Cin / 2) * p.HW;
+        const int64_t step_row = p.W, step_chan = (int64_t)p.HW - (int64_t)(KS - 1) * p.W;
+        for (int i = 0; i < my_tiles; ++i) {
+            const int t = (int)blockIdx.x + i * (int)gridDim.x;
+            const ConvI8Seg &sg = t < tiles0 ? p.seg[0] : p.seg[1];
+            const int m = (t < tiles0 ? t : t - tiles0) * kTcBM + row;
+            int64_t rowbase = sg.gather ? __ldg(sg.gather) * p.in_bstride : 0;     // rows beyond M read a valid address
+            if (m < sg.M) {
+                const int b = m / p.P, pix = m - b * p.P;
+                const int oy = pix / p.OW, ox = pix - oy * p.OW;
+                const int64_t bb = sg.gather ? __ldg(sg.gather + b) : (int64_t)b;
+                rowbase = bb * p.in_bstride + (int64_t)(oy * p.sy + ox * p.sx);
+            }
+            const uint8_t *ptr = sg.x + rowbase + half_off;
+            uint32_t raw[CPT][4];
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+#pragma unroll
+                for (int rr = 0; rr < 16 / KS; ++rr) {               // kernel rows inside this 16-tap chunk
+                    const int r = c * (16 / KS) + rr;                // compile-time row counter of this thread
+#pragma unroll
+                    for (int gx = 0; gx < KS / 4; ++gx)
+                        raw[c][rr * (KS / 4) + gx] = __ldg(reinterpret_cast<const uint32_t *>(ptr + 4 * gx));
+                    ptr += (r % KS == KS - 1) ? step_chan : step_row;
+                }
+            }
+            const int s = i & 1;
+            const uint32_t ph = (uint32_t)((i >> 1) & 1);
+            tc::mbar_wait(&empty_a[s], ph ^ 1u);                     // MMAs that read stage s two tiles ago have retired
+            const uint32_t dst = a_s + (uint32_t)s * a_bytes + row_off;
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) tc::sts128u(dst + (uint32_t)c * lbo_a, raw[c][0], raw[c][1], raw[c][2], raw[c][3]);
+            tc::fence_async_smem();              // generic-proxy smem writes -> visible to the async (tensor) proxy
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&full_a[s]);
         }
-        const uint8_t *rp = sg.x + rowbase;
-        uint32_t raw[CPT][4];
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-            const uint32_t g0 = (uint32_t)(half * CPT + c) * 4;
-            uint32_t off[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) off[j] = tc::lds32(koff_a + 4u * (g0 + j));
-#pragma unroll
-            for (int j = 0; j < 4; ++j) raw[c][j] = __ldg(reinterpret_cast<const uint32_t *>(rp + off[j]));
-        }
-        const uint32_t row_off = (uint32_t)(row >> 3) * 128 + (uint32_t)(row & 7) * 16;
-#pragma unroll
-        for (int c = 0; c < CPT; ++c)
-            tc::sts128u(a_s + (uint32_t)(half * CPT + c) * lbo_a + row_off, raw[c][0], raw[c][1], raw[c][2], raw[c][3]);
-        tc::fence_async_smem();                  // generic-proxy smem writes -> visible to the async (tensor) proxy
-        __syncwarp();
-        if ((tid & 31) == 0) tc::mbar_arrive(full_a);
-
-        // ---- epilogue: warp w owns TMEM lanes 32*(w%4)..+31 (its rows) and channel groups of parity w/4
-        tc::mbar_wait(mma_done, 0);
-        tc::tc_fence_after();
-        const int q = warp & 3;
-        const int er = q * 32 + (tid & 31);
-        const int em = cta * kTcBM + er;
-        const bool e_ok = em < sg.M;
-        int b_img = 0, pix = 0;
-        if (e_ok) { b_img = em / p.P; pix = em - b_img * p.P; }
+    } else {
+        // ================================ epilogue warps ================================
+        // warp owns TMEM lanes 32*(warp%4)..+31 (its 32 pixel rows) and every second group of 8 channels
+        const int q = warp & 3, sub = (warp - (kI8GatherWarps + 1)) >> 2;
         const bool relu = p.act == B2RL_ACT_RELU, ident = p.act == B2RL_ACT_NONE;
-        const int oP = p.P;
-        for (int net = 0; net < nets; ++net) {
-            float *outp = sg.out[net];
-            for (int c0 = (warp >> 2) * 8; c0 < p.n_pad; c0 += 16) {      // 8 channels x 4 digit planes per pass
+        const bool int_combine = p.k_pad <= 256;                      // (D2 << 8) + D3 stays inside int32 up to 256 taps
+        const int64_t oP = p.P;
+        for (int i = 0; i < my_tiles; ++i) {
+            const int t = (int)blockIdx.x + i * (int)gridDim.x;
+            const ConvI8Seg &sg = t < tiles0 ? p.seg[0] : p.seg[1];
+            const int em = (t < tiles0 ? t : t - tiles0) * kTcBM + q * 32 + lane;
+            const bool e_ok = em < sg.M;
+            int b_img = 0, pix = 0;
+            if (e_ok) { b_img = em / p.P; pix = em - b_img * p.P; }
+            const int s = i & 1;
+            const uint32_t ph = (uint32_t)((i >> 1) & 1);
+            tc::mbar_wait(&acc_full[s], ph);
+            tc::tc_fence_after();
+            const uint32_t lane_addr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * acc_cols);
+            const int passes = sg.nets * (p.n_pad / 16);              // (net, 16-channel block): this warp takes 8 of the 16
+            for (int ps = 0; ps < passes; ++ps) {
+                const int net = ps / (p.n_pad / 16), c0 = (ps - net * (p.n_pad / 16)) * 16 + sub * 8;
                 uint32_t d0[8], d1[8], d2[8], d3[8];
                 const uint32_t col = (uint32_t)(net * 4 * p.n_pad + c0);
-                const uint32_t lane_addr = tmem_d + ((uint32_t)(q * 32) << 16);
                 tc::tmem_ld8(lane_addr + col, d0);
                 tc::tmem_ld8(lane_addr + col + (uint32_t)p.n_pad, d1);
                 tc::tmem_ld8(lane_addr + col + 2u * (uint32_t)p.n_pad, d2);
                 tc::tmem_ld8(lane_addr + col + 3u * (uint32_t)p.n_pad, d3);
                 tc::tmem_ld_wait();
+                if (ps == passes - 1) {                               // every TMEM read of this tile has landed in registers
+                    tc::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&acc_empty[s]);
+                }
+                float sc[8], bi[8];
+                {
+                    const uint32_t so = scale_a + 4u * (uint32_t)(net * p.n_pad + c0), bo = bias_a + 4u * (uint32_t)(net * p.n_pad + c0);
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(sc[0]), "=f"(sc[1]), "=f"(sc[2]), "=f"(sc[3]) : "r"(so));
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(sc[4]), "=f"(sc[5]), "=f"(sc[6]), "=f"(sc[7]) : "r"(so + 16u));
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bi[0]), "=f"(bi[1]), "=f"(bi[2]), "=f"(bi[3]) : "r"(bo));
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bi[4]), "=f"(bi[5]), "=f"(bi[6]), "=f"(bi[7]) : "r"(bo + 16u));
+                }
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float tsum;
+                    if (int_combine) {        // exact integer pairs, two conversions instead of four
+                        const int hi = ((int)d0[j] << 8) + (int)d1[j], lo = ((int)d2[j] << 8) + (int)d3[j];
+                        tsum = fmaf((float)hi, 65536.f, (float)lo);
+                    } else {                  // smallest digit plane first
+                        tsum = fmaf((float)(int)d2[j], 256.f, (float)(int)d3[j]);
+                        tsum = fmaf((float)(int)d1[j], 65536.f, tsum);
+                        tsum = fmaf((float)(int)d0[j], 16777216.f, tsum);
+                    }
+                    v[j] = fmaf(tsum, sc[j], bi[j]);
+                }
+                if (relu) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+                } else if (!ident) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = act_fwd_slow(p.act, v[j]);
+                }
                 if (e_ok) {
-                    const int nv = min(8, p.N - c0);
-                    float v[8];
+                    float *o = sg.out[net] + ((int64_t)b_img * p.N + c0) * oP + pix;
+                    if (c0 + 8 <= p.N) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        // smallest digit plane first: every partial sum is exact or rounded once at its own magnitude
-                        float t = fmaf((float)(int)d2[j], 256.f, (float)(int)d3[j]);
-                        t = fmaf((float)(int)d1[j], 65536.f, t);
-                        t = fmaf((float)(int)d0[j], 16777216.f, t);
-                        const float sc = __uint_as_float(tc::lds32(scale_a + 4u * (net * p.n_pad + c0 + j)));
-                        v[j] = fmaf(t, sc, __uint_as_float(tc::lds32(bias_a + 4u * (net * p.n_pad + c0 + j))));
+                        for (int j = 0; j < 8; ++j) { *o = v[j]; o += oP; }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { if (c0 + j < p.N) *o = v[j]; o += oP; }
                     }
-                    if (relu) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-                    } else if (!ident) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = act_fwd_slow(p.act, v[j]);
-                    }
-                    float *o = outp + ((int64_t)b_img * p.N + c0) * oP + pix;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (j < nv) o[j * oP] = v[j];
                 }
             }
         }
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 8) tc::tmem_dealloc(tmem_d, tmem_cols);
+    if (warp == kI8GatherWarps) tc::tmem_dealloc(tmem_d, tmem_cols);
 }
 
 static bool i8_enabled() {
@@ -339,14 +379,14 @@ static bool conv_i8_ok(const b2rl_layer &l, bool obs_u8, bool normalize, float l
     if (!i8_enabled() || !obs_u8 || l.kind != B2RL_LAYER_CONV || l.ln != B2RL_LN_NONE) return false;
     if (l.act == B2RL_ACT_GELU) return false;                         // no pre-activation copy on this path
     if (normalize && !(low == floorf(low) && high == floorf(high) && high > low && fabsf(low) <= 1024.f)) return false;
-    const int K = l.in_c * l.ksize * l.ksize, k_pad = (K + 31) / 32 * 32, n_pad = (l.out_c + 15) / 16 * 16;
-    if (nets_total * 4 * n_pad > 256 || (k_pad / 16) % 2 != 0) return false;
-    const int cpt = k_pad / 32;
+    if (!(l.ksize == 4 || l.ksize == 8) || l.in_c % 2 != 0) return false;   // kernel rows = aligned 4-byte groups; two tap halves
+    const int K = l.in_c * l.ksize * l.ksize, n_pad = (l.out_c + 15) / 16 * 16;
+    if (K % 32 != 0 || nets_total * 4 * n_pad > 256) return false;   // two accumulators of nets*4*n_pad columns in TMEM
+    const int cpt = K / 32;
     if (!(cpt == 1 || cpt == 2 || cpt == 4 || cpt == 8 || cpt == 16)) return false;
-    if (conv_i8_smem_bytes(n_pad, k_pad, nets_total) > 100 * 1024) return false;
-    const bool vec = l.ksize % 4 == 0 && l.stride % 4 == 0 && l.in_w % 4 == 0 && (l.in_h * l.in_w) % 4 == 0 &&
-                     reinterpret_cast<uintptr_t>(x) % 4 == 0 && K % 4 == 0;
-    return vec;
+    if (conv_i8_smem_bytes(n_pad, K, nets_total) > 200 * 1024) return false;
+    // frames: 4 consecutive taps of a kernel row are 4 contiguous, 4-byte aligned bytes
+    return l.stride % 4 == 0 && l.in_w % 4 == 0 && (l.in_h * l.in_w) % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 4 == 0;
 }
 
 struct ConvI8Job {                 // one segment as the host describes it
@@ -367,47 +407,46 @@ static int launch_conv_fwd_i8(const b2rl_layer &l, bool normalize, float low, fl
     if (reinterpret_cast<uintptr_t>(scratch) % 16 != 0 || n_jobs < 1 || n_jobs > kI8MaxSegs) return 1;
     int8_t *wd = static_cast<int8_t *>(scratch);
     float *scale = reinterpret_cast<float *>(wd + (size_t)nets_total * 4 * n_pad * k_pad);   // [scale | lowcorr]
-    uint32_t *koff4 = reinterpret_cast<uint32_t *>(scale + 2 * (size_t)nets_total * n_pad);
     const double inv_range = normalize ? 1.0 / ((double)high - (double)low) : 1.0;
     const float lo = normalize ? low : 0.f;
     if (!reuse_digits) {
         weight_digits_kernel<<<dim3(n_pad, nets_total), 128, 0, s>>>(W[0], nets_total > 1 ? W[1] : W[0], l.out_c, K, n_pad, k_pad,
                                                                     nets_total, inv_range, lo, wd, scale,
-                                                                    scale + (size_t)nets_total * n_pad, KK, l.ksize,
-                                                                    l.in_h * l.in_w, l.in_w, koff4);
+                                                                    scale + (size_t)nets_total * n_pad);
         B2RL_LAUNCH_CHECK();
     }
     ConvI8Params p;
     memset(&p, 0, sizeof(p));
-    int cta = 0;
+    int tiles = 0;
     for (int i = 0; i < n_jobs; ++i) {
         if (jobs[i].rows * (int64_t)P > INT32_MAX) return 1;
         ConvI8Seg &sg = p.seg[i];
         sg.x = static_cast<const uint8_t *>(jobs[i].x); sg.gather = jobs[i].gather;
         sg.out[0] = jobs[i].out[0]; sg.out[1] = jobs[i].out[1];
-        sg.M = (int)(jobs[i].rows * P); sg.nets = jobs[i].nets; sg.cta0 = cta;
-        cta += (sg.M + kTcBM - 1) / kTcBM;
+        sg.M = (int)(jobs[i].rows * P); sg.nets = jobs[i].nets; sg.cta0 = tiles;
+        tiles += (sg.M + kTcBM - 1) / kTcBM;
     }
     p.n_seg = n_jobs;
-    p.wd = wd; p.scale = scale; p.bias[0] = bias[0]; p.bias[1] = nets_total > 1 ? bias[1] : bias[0]; p.koff4 = koff4;
+    p.wd = wd; p.scale = scale; p.bias[0] = bias[0]; p.bias[1] = nets_total > 1 ? bias[1] : bias[0];
     p.in_bstride = (int64_t)l.in_c * l.in_h * l.in_w;
     p.N = l.out_c; p.n_pad = n_pad; p.k_pad = k_pad; p.nets_total = nets_total;
-    p.P = P; p.OW = l.out_w; p.sy = l.stride * l.in_w; p.sx = l.stride; p.act = l.act; p.low = lo;
+    p.P = P; p.OW = l.out_w; p.sy = l.stride * l.in_w; p.sx = l.stride; p.act = l.act;
+    p.Cin = l.in_c; p.HW = l.in_h * l.in_w; p.W = l.in_w;
     const size_t smem = conv_i8_smem_bytes(n_pad, k_pad, nets_total);
+    const int grid = tiles < sm_count() ? tiles : sm_count();          // persistent: one CTA per SM walks its tiles
+    if (grid <= 0) return B2RL_OK;
     auto launch = [&](auto kern) -> int {
         { const int rca = ensure_big_smem(kern); if (rca != B2RL_OK) return rca; }
-        kern<<<cta, kI8Threads, smem, s>>>(p);
+        kern<<<grid, kI8ThreadsP, smem, s>>>(p);
         B2RL_LAUNCH_CHECK();
         return B2RL_OK;
     };
-    switch (k_pad / 32) {
-        case 1: return launch(conv_fwd_i8_kernel<1>);
-        case 2: return launch(conv_fwd_i8_kernel<2>);
-        case 4: return launch(conv_fwd_i8_kernel<4>);
-        case 8: return launch(conv_fwd_i8_kernel<8>);
-        case 16: return launch(conv_fwd_i8_kernel<16>);
-        default: return 1;
-    }
+    const int cpt = k_pad / 32;
+#define B2RL_I8_CASE(KS_, CPT_) if (l.ksize == KS_ && cpt == CPT_) return launch(conv_fwd_i8_kernel<KS_, CPT_>)
+    B2RL_I8_CASE(8, 2); B2RL_I8_CASE(8, 4); B2RL_I8_CASE(8, 8); B2RL_I8_CASE(8, 16);
+    B2RL_I8_CASE(4, 1); B2RL_I8_CASE(4, 2); B2RL_I8_CASE(4, 4); B2RL_I8_CASE(4, 8); B2RL_I8_CASE(4, 16);
+#undef B2RL_I8_CASE
+    return 1;
 }
 
 }  // namespace b2rl

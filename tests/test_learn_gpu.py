@@ -398,10 +398,13 @@ def test_odd_batch_sizes_match_oracle(B):
 
 
 @pytest.mark.parametrize("cin,hw,k,s,cout,rows", [
-    (4, 84, 8, 4, 32, 37),       # the north-star first layer; 37 images: last tile ragged
-    (1, 36, 4, 4, 16, 5),        # one k-step, 16 channels
-    (3, 40, 8, 4, 24, 9),        # Cout not a multiple of 16 (padded digit planes), K = 192
+    (4, 84, 8, 4, 32, 37),       # the north-star first layer; 37 images: ragged last tile, 116 tiles < 148 SMs
+    (4, 84, 8, 4, 32, 300),      # 938 tiles: every CTA of the persistent kernel walks 6-7 tiles through both stages
+    (2, 36, 4, 4, 16, 5),        # k4: one 4-byte group per kernel row, a single k-step, 16 channels
+    (4, 40, 8, 4, 24, 9),        # Cout not a multiple of 16 (padded digit planes)
     (4, 64, 8, 8, 64, 3),        # 64 channels: 256 accumulator columns for one weight set
+    (8, 36, 8, 4, 16, 6),        # K = 512: float digit recombination (the integer pairing needs K <= 256)
+    (3, 40, 8, 4, 24, 4),        # odd channel count: outside the integer path, falls back to the tf32 kernel
 ])
 def test_first_layer_int8_digit_conv_matches_float64(cin, hw, k, s, cout, rows):
     """conv_fwd_i8_kernel (tcgen05 kind::i8 over raw frame bytes, weights as four int8 digit planes) through the
