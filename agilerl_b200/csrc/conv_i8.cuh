@@ -243,12 +243,13 @@ __global__ void __launch_bounds__(kI8ThreadsP, 1) conv_fwd_i8_kernel(const ConvI
         }
     } else if (warp < kI8GatherWarps) {
         // ================================ gather warps ================================
-        // thread = (im2col row, half of the taps): channels [half*Cin/2, (half+1)*Cin/2), every kernel row of them
+        // thread = (im2col row, half of the taps): channels [half*Cin/2, (half+1)*Cin/2), every kernel row of them.
+        // The loads of tile i+1 are issued BEFORE tile i's registers are stored: two tiles of DRAM latency in flight.
         const int row = tid & (kTcBM - 1), half = tid >> 7;
         const uint32_t row_off = (uint32_t)(row >> 3) * 128 + (uint32_t)(row & 7) * 16 + (uint32_t)(half * CPT) * lbo_a;
         const int64_t half_off = (int64_t)half * (p.Cin / 2) * p.HW;
         const int64_t step_row = p.W, step_chan = (int64_t)p.HW - (int64_t)(KS - 1) * p.W;
-        for (int i = 0; i < my_tiles; ++i) {
+        auto issue = [&](int i, uint32_t (&raw)[CPT][4]) {
             const int t = (int)blockIdx.x + i * (int)gridDim.x;
             const ConvI8Seg &sg = t < tiles0 ? p.seg[0] : p.seg[1];
             const int m = (t < tiles0 ? t : t - tiles0) * kTcBM + row;
@@ -260,7 +261,6 @@ __global__ void __launch_bounds__(kI8ThreadsP, 1) conv_fwd_i8_kernel(const ConvI
                 rowbase = bb * p.in_bstride + (int64_t)(oy * p.sy + ox * p.sx);
             }
             const uint8_t *ptr = sg.x + rowbase + half_off;
-            uint32_t raw[CPT][4];
 #pragma unroll
             for (int c = 0; c < CPT; ++c) {
 #pragma unroll
@@ -272,6 +272,8 @@ __global__ void __launch_bounds__(kI8ThreadsP, 1) conv_fwd_i8_kernel(const ConvI
                     ptr += (r % KS == KS - 1) ? step_chan : step_row;
                 }
             }
+        };
+        auto store = [&](int i, uint32_t (&raw)[CPT][4]) {
             const int s = i & 1;
             const uint32_t ph = (uint32_t)((i >> 1) & 1);
             tc::mbar_wait(&empty_a[s], ph ^ 1u);                     // MMAs that read stage s two tiles ago have retired
@@ -281,6 +283,14 @@ __global__ void __launch_bounds__(kI8ThreadsP, 1) conv_fwd_i8_kernel(const ConvI
             tc::fence_async_smem();              // generic-proxy smem writes -> visible to the async (tensor) proxy
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&full_a[s]);
+        };
+        uint32_t ra[CPT][4], rb[CPT][4];
+        if (my_tiles > 0) issue(0, ra);
+        for (int i = 0; i < my_tiles; i += 2) {
+            if (i + 1 < my_tiles) issue(i + 1, rb);
+            store(i, ra);
+            if (i + 2 < my_tiles) issue(i + 2, ra);
+            if (i + 1 < my_tiles) store(i + 1, rb);
         }
     } else {
         // ================================ epilogue warps ================================
@@ -289,6 +299,8 @@ __global__ void __launch_bounds__(kI8ThreadsP, 1) conv_fwd_i8_kernel(const ConvI
         const bool relu = p.act == B2RL_ACT_RELU, ident = p.act == B2RL_ACT_NONE;
         const bool int_combine = p.k_pad <= 256;                      // (D2 << 8) + D3 stays inside int32 up to 256 taps
         const int64_t oP = p.P;
+        const int blocks = p.n_pad / 16;
+        const bool full_n = (p.N % 16) == 0;
         for (int i = 0; i < my_tiles; ++i) {
             const int t = (int)blockIdx.x + i * (int)gridDim.x;
             const ConvI8Seg &sg = t < tiles0 ? p.seg[0] : p.seg[1];
@@ -296,63 +308,65 @@ __global__ void __launch_bounds__(kI8ThreadsP, 1) conv_fwd_i8_kernel(const ConvI
             const bool e_ok = em < sg.M;
             int b_img = 0, pix = 0;
             if (e_ok) { b_img = em / p.P; pix = em - b_img * p.P; }
+            const int64_t o_row = ((int64_t)b_img * p.N + sub * 8) * oP + pix;       // channel sub*8 of this pixel
             const int s = i & 1;
             const uint32_t ph = (uint32_t)((i >> 1) & 1);
             tc::mbar_wait(&acc_full[s], ph);
             tc::tc_fence_after();
-            const uint32_t lane_addr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * acc_cols);
-            const int passes = sg.nets * (p.n_pad / 16);              // (net, 16-channel block): this warp takes 8 of the 16
-            for (int ps = 0; ps < passes; ++ps) {
-                const int net = ps / (p.n_pad / 16), c0 = (ps - net * (p.n_pad / 16)) * 16 + sub * 8;
-                uint32_t d0[8], d1[8], d2[8], d3[8];
-                const uint32_t col = (uint32_t)(net * 4 * p.n_pad + c0);
-                tc::tmem_ld8(lane_addr + col, d0);
-                tc::tmem_ld8(lane_addr + col + (uint32_t)p.n_pad, d1);
-                tc::tmem_ld8(lane_addr + col + 2u * (uint32_t)p.n_pad, d2);
-                tc::tmem_ld8(lane_addr + col + 3u * (uint32_t)p.n_pad, d3);
-                tc::tmem_ld_wait();
-                if (ps == passes - 1) {                               // every TMEM read of this tile has landed in registers
-                    tc::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(&acc_empty[s]);
-                }
-                float sc[8], bi[8];
-                {
-                    const uint32_t so = scale_a + 4u * (uint32_t)(net * p.n_pad + c0), bo = bias_a + 4u * (uint32_t)(net * p.n_pad + c0);
+            const uint32_t lane_addr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * acc_cols + sub * 8);
+            const int nets = sg.nets;
+            for (int net = 0; net < nets; ++net) {
+                float *o_net = sg.out[net] + o_row;
+                uint32_t col = lane_addr + (uint32_t)(net * 4 * p.n_pad);
+                uint32_t so = scale_a + 4u * (uint32_t)(net * p.n_pad + sub * 8), bo = bias_a + 4u * (uint32_t)(net * p.n_pad + sub * 8);
+                for (int blk = 0; blk < blocks; ++blk, col += 16u, so += 64u, bo += 64u, o_net += 16 * oP) {
+                    uint32_t d0[8], d1[8], d2[8], d3[8];
+                    tc::tmem_ld8(col, d0);
+                    tc::tmem_ld8(col + (uint32_t)p.n_pad, d1);
+                    tc::tmem_ld8(col + 2u * (uint32_t)p.n_pad, d2);
+                    tc::tmem_ld8(col + 3u * (uint32_t)p.n_pad, d3);
+                    tc::tmem_ld_wait();
+                    if (net == nets - 1 && blk == blocks - 1) {       // every TMEM read of this tile has landed in registers
+                        tc::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(&acc_empty[s]);
+                    }
+                    float sc[8], bi[8];
                     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(sc[0]), "=f"(sc[1]), "=f"(sc[2]), "=f"(sc[3]) : "r"(so));
                     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(sc[4]), "=f"(sc[5]), "=f"(sc[6]), "=f"(sc[7]) : "r"(so + 16u));
                     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bi[0]), "=f"(bi[1]), "=f"(bi[2]), "=f"(bi[3]) : "r"(bo));
                     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bi[4]), "=f"(bi[5]), "=f"(bi[6]), "=f"(bi[7]) : "r"(bo + 16u));
-                }
-                float v[8];
+                    float v[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float tsum;
-                    if (int_combine) {        // exact integer pairs, two conversions instead of four
-                        const int hi = ((int)d0[j] << 8) + (int)d1[j], lo = ((int)d2[j] << 8) + (int)d3[j];
-                        tsum = fmaf((float)hi, 65536.f, (float)lo);
-                    } else {                  // smallest digit plane first
-                        tsum = fmaf((float)(int)d2[j], 256.f, (float)(int)d3[j]);
-                        tsum = fmaf((float)(int)d1[j], 65536.f, tsum);
-                        tsum = fmaf((float)(int)d0[j], 16777216.f, tsum);
+                    for (int j = 0; j < 8; ++j) {
+                        float tsum;
+                        if (int_combine) {        // exact integer pairs, two conversions instead of four
+                            const int hi = ((int)d0[j] << 8) + (int)d1[j], lo = ((int)d2[j] << 8) + (int)d3[j];
+                            tsum = fmaf((float)hi, 65536.f, (float)lo);
+                        } else {                  // smallest digit plane first
+                            tsum = fmaf((float)(int)d2[j], 256.f, (float)(int)d3[j]);
+                            tsum = fmaf((float)(int)d1[j], 65536.f, tsum);
+                            tsum = fmaf((float)(int)d0[j], 16777216.f, tsum);
+                        }
+                        v[j] = fmaf(tsum, sc[j], bi[j]);
                     }
-                    v[j] = fmaf(tsum, sc[j], bi[j]);
-                }
-                if (relu) {
+                    if (relu) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-                } else if (!ident) {
+                        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+                    } else if (!ident) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = act_fwd_slow(p.act, v[j]);
-                }
-                if (e_ok) {
-                    float *o = sg.out[net] + ((int64_t)b_img * p.N + c0) * oP + pix;
-                    if (c0 + 8 <= p.N) {
+                        for (int j = 0; j < 8; ++j) v[j] = act_fwd_slow(p.act, v[j]);
+                    }
+                    if (e_ok) {
+                        float *o = o_net;
+                        if (full_n) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) { *o = v[j]; o += oP; }
-                    } else {
+                            for (int j = 0; j < 8; ++j) { *o = v[j]; o += oP; }
+                        } else {
+                            const int c0 = blk * 16 + sub * 8;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) { if (c0 + j < p.N) *o = v[j]; o += oP; }
+                            for (int j = 0; j < 8; ++j) { if (c0 + j < p.N) *o = v[j]; o += oP; }
+                        }
                     }
                 }
             }

@@ -44,6 +44,7 @@ LR, TAU, PRIOR_EPS = 1e-4, 1e-3, 1e-6
 NUM_ENVS = 4                                  # env-steps ingested per e2e step
 ALG_BYTES_PER_STEP = 22_954_544
 ALG_FLOPS_PER_STEP = 12_067_307_520
+TRAFFIC_CONV1 = None                           # filled from the committed ncu capture (profiles/)
 
 
 def peaks():
@@ -289,16 +290,16 @@ def conv1_roofline(eng, nmem, device):
         if it >= 5:
             times.append(e0.elapsed_time(e1))
     ms = statistics.mean(times)
-    desc = {"kernel": "conv_fwd_tc_kernel<uint8, exact-A> (+ weight_split_kernel): conv1 forward (4->32, k8 s4) of B=256 "
-                      "frames gathered from the replay ring, tcgen05.mma kind::tf32 (2xTF32 weight split, fp32 TMEM "
-                      "accumulate)",
-            "operand": "tf32", "peak_vs_bf16": 0.5, "mmas_per_product": 2,
-            # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (cold L2):
-            # profiles/r1_conv_fwd_tcgen05_v2.txt (7.2 MB of frames read; the 13 MB fp32 output stays in L2)
-            "traffic": 7405824,
-            "note": "uint8 frames read once + fp32 activations written once + weights; fp32-equivalent FLOPs 2*M*N*K, "
-                    "each costing 2 tf32 MMAs; the kernel is issue/latency-bound on building the im2col tile with CUDA "
-                    "cores (DESIGN.md section 5), not on HBM or the tensor pipe"}
+    desc = {"kernel": "conv_fwd_i8_kernel<8, 8> (+ weight_digits_kernel): conv1 forward (4->32, k8 s4) of B=256 frames gathered "
+                      "from the replay ring; persistent warp-specialised kernel, tcgen05.mma kind::i8 over the raw frame bytes "
+                      "against four int8 digit planes of the fp32 weights (exact int32 accumulation in TMEM), fp32 "
+                      "recombination + bias + ReLU in the epilogue",
+            "operand": "int8", "peak_vs_bf16": 2.0, "mmas_per_product": 4,
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (cold L2): profiles/r2_conv1_i8_*.txt
+            "traffic": TRAFFIC_CONV1,
+            "note": "uint8 frames read once + fp32 activations written once + weights; fp32-equivalent FLOPs 2*M*N*K, each "
+                    "multiply-add costing 4 int8 tensor-core products (one per weight digit plane); nominal int8 dense rate = "
+                    "2x bf16"}
     return flops, alg_bytes, ms, desc
 
 
