@@ -120,7 +120,7 @@ _SIGS = {
     "b2rl_net_forward_dist": ([POINTER(NetDesc), c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p,
                                c_void_p, c_size_t, c_void_p], c_int),
     "b2rl_encoder_layer_forward": ([POINTER(NetDesc), c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
-                                    c_size_t, c_void_p], c_int),
+                                    c_size_t, c_int, c_void_p], c_int),
     "b2rl_launch_count": ([], ctypes.c_ulonglong),
     "b2rl_rainbow_loss": ([POINTER(NetDesc), POINTER(LearnCfg), POINTER(LearnBufs), c_void_p], c_int),
     "b2rl_rainbow_backward": ([POINTER(NetDesc), POINTER(LearnCfg), POINTER(LearnBufs), c_void_p], c_int),

@@ -392,7 +392,7 @@ using OpW = OpTraits<EL_F32, MAP_STRIDE, MAP_STRIDE, true, false>;     // weight
 
 static int layer_forward(const b2rl_net_desc &net, const b2rl_layer &l, const float *W, const float *bias,
                          const float *params, const float *x_prev, const ObsChunk *chunks, int n_chunks,
-                         int64_t rows, const LayerBuf &lb, const Scratch &sc, cudaStream_t s) {
+                         int64_t rows, const LayerBuf &lb, const Scratch &sc, cudaStream_t s, bool reuse_split = false) {
     const int64_t oe = layer_out_elems(l);
     const bool first = x_prev == nullptr;
     int n_runs = first ? n_chunks : 1;
@@ -409,7 +409,7 @@ static int layer_forward(const b2rl_net_desc &net, const b2rl_layer &l, const fl
         }
         const float *Ws[2] = {W, W}, *bs[2] = {bias, bias};
         const int rc8 = launch_conv_fwd_i8(l, net.normalize != 0, net.obs_low, net.obs_high, Ws, bs, 1, jobs, n_chunks,
-                                           sc.partial, sc.floats * sizeof(float), s);
+                                           sc.partial, sc.floats * sizeof(float), s, reuse_split);
         if (rc8 != 1) return rc8;
     }
     for (int run = 0; run < n_runs; ++run) {
@@ -451,7 +451,7 @@ static int layer_forward(const b2rl_net_desc &net, const b2rl_layer &l, const fl
         int rc = 1;
         if (l.kind == B2RL_LAYER_CONV && tc_enabled() && l.ln == B2RL_LN_NONE)
             rc = launch_conv_fwd_tc(l, A, W, bias, out_ptr, lb.pre ? lb.pre + row0 * oe : nullptr, r, sc.partial, sc.floats,
-                                    s, run > 0);   // tcgen05 3xTF32 (pre-split weights live in the split-K scratch;
+                                    s, run > 0 || reuse_split);   // tcgen05 3xTF32 (pre-split weights live in the split-K scratch;
                                                    // the second observation chunk reuses the first one's split)
         if (rc == 1 && l.kind == B2RL_LAYER_CONV)
             rc = dispatch_elem(A.elem_kind(), [&](auto ek) {
@@ -1651,7 +1651,7 @@ int b2rl_debug_read(long long *out_host, int n) {
 
 int b2rl_encoder_layer_forward(const b2rl_net_desc *net_host, int layer, const float *params, const void *input,
                                const int64_t *row_idx, int64_t rows, float *out, void *workspace,
-                               size_t workspace_bytes, void *stream) {
+                               size_t workspace_bytes, int reuse_split, void *stream) {
     B2RL_CHECK_ARG(net_host && params && input && out, "NULL argument");
     B2RL_CHECK_ARG(layer >= 0 && layer < net_host->n_enc, "layer out of range");
     const b2rl_layer &l = net_host->enc[layer];
@@ -1662,7 +1662,7 @@ int b2rl_encoder_layer_forward(const b2rl_net_desc *net_host, int layer, const f
     ObsChunk ch{input, row_idx, rows};
     return layer_forward(*net_host, l, params + l.w_off, params + l.b_off, params,
                          layer == 0 ? nullptr : static_cast<const float *>(input), &ch, 1, rows, lb, sc,
-                         as_stream(stream));
+                         as_stream(stream), reuse_split != 0);
 }
 
 }  // extern "C"

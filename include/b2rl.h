@@ -251,10 +251,12 @@ int b2rl_debug_read(long long *out_host, int n);
 
 /* Forward of ONE encoder layer (profiling / roofline hook: lets bench.py time the dominant
  * contraction alone with CUDA events).  layer 0 reads observations (obs/row_idx as above), layer
- * i>0 reads `input` = the previous layer's [rows, ...] fp32 activations.  out: rows x out elems. */
+ * i>0 reads `input` = the previous layer's [rows, ...] fp32 activations.  out: rows x out elems.
+ * reuse_split != 0: the workspace still holds this layer's pre-split weights (digit planes / tf32 hi-lo tiles) from the
+ * previous call with the same parameters — only the convolution kernel itself is launched. */
 int b2rl_encoder_layer_forward(const b2rl_net_desc *net_host, int layer, const float *params,
                                const void *input, const int64_t *row_idx, int64_t rows, float *out,
-                               void *workspace, size_t workspace_bytes, void *stream);
+                               void *workspace, size_t workspace_bytes, int reuse_split, void *stream);
 
 /* Scalars of one learn step (doubles are the Python floats of the reference, rounded to f32
  * inside the kernels exactly where torch rounds them). */

@@ -435,7 +435,7 @@ def test_first_layer_int8_digit_conv_matches_float64(cin, hw, k, s, cout, rows):
     lib = _lib.load()
     n0 = lib.b2rl_launch_count()
     _lib.check(lib.b2rl_encoder_layer_forward(ctypes.byref(desc), 0, pd.data_ptr(), rd.data_ptr(), id_.data_ptr(), rows,
-                                              out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(torch.device("cuda:0"))))
+                                              out.data_ptr(), ws.data_ptr(), ws.numel(), 0, _lib.stream_ptr(torch.device("cuda:0"))))
     torch.cuda.synchronize()
     assert lib.b2rl_launch_count() - n0 == 2, "expected the digit-split + int8 convolution launches"
     err = (out.cpu().double() - ref).abs().max().item()
