@@ -97,11 +97,13 @@ _SIGS = {
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
     "b2rl_noise_reset_state": ([POINTER(NetDesc), c_void_p, c_uint64, c_void_p, c_int, c_void_p], c_int),
     "b2rl_step_state_write": ([POINTER(StepState), c_void_p, c_void_p], c_int),
+    "b2rl_copy_d2h": ([c_void_p, c_void_p, c_size_t, c_void_p], c_int),
     "b2rl_graph_begin": ([c_void_p], c_int),
     "b2rl_graph_end": ([c_void_p, POINTER(c_void_p)], c_int),
     "b2rl_graph_launch": ([c_void_p, POINTER(StepState), c_void_p], c_int),
     "b2rl_graph_kernel_count": ([c_void_p, POINTER(c_int)], c_int),
     "b2rl_graph_destroy": ([c_void_p], c_int),
+    "b2rl_host_priority_pow": ([c_void_p, c_int64, c_double, c_double, c_void_p, POINTER(c_double)], c_int),
     "b2rl_philox_uniforms": ([c_uint64, c_uint64, c_int64, c_void_p, c_void_p], c_int),
     "b2rl_philox_normals": ([c_uint64, c_uint64, c_int64, c_void_p, c_void_p], c_int),
     "b2rl_ring_write": ([c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p], c_int),

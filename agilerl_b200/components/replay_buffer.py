@@ -75,6 +75,35 @@ def _as_collection(data) -> Any:
     raise TypeError(f"Cannot store data of type {type(data)} in a replay buffer")
 
 
+class _PinnedRing:
+    """A few pinned host blocks used round-robin as the source of asynchronous H2D copies.  A slot is handed
+    out again only after the copy that last read it has completed (its event), so callers may overwrite their
+    own host arrays as soon as ``add`` / ``update_priorities`` return — the blocking ``.to(device)`` semantics
+    of the reference without blocking on the stream."""
+
+    def __init__(self, slots: int = 8):
+        self.slots = slots
+        self.bufs: list = [None] * slots
+        self.events: list = [None] * slots
+        self.i = 0
+
+    def take(self, nbytes: int) -> tuple[torch.Tensor, int]:
+        k = self.i
+        self.i = (k + 1) % self.slots
+        if self.events[k] is not None:
+            self.events[k].synchronize()
+        buf = self.bufs[k]
+        if buf is None or buf.numel() < nbytes:
+            buf = self.bufs[k] = torch.empty(max(nbytes, 4096), dtype=torch.uint8).pin_memory()
+        return buf, k
+
+    def sent(self, k: int, device) -> None:
+        ev = self.events[k]
+        if ev is None:
+            ev = self.events[k] = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+
+
 class ReplayBuffer:
     """Circular replay buffer resident in HBM (replay_buffer.py:12-138)."""
 
@@ -92,6 +121,36 @@ class ReplayBuffer:
         self._fields: dict[tuple, torch.Tensor] = {}
         self._row_bytes: dict[tuple, int] = {}
         self._lib = _lib.load()
+        self._ring = _PinnedRing()
+        self._stage_plans: dict = {}
+
+    # -- host -> device staging -----------------------------------------------------------------
+    def _to_device(self, data):
+        """Every host leaf of a transition through ONE pinned staging block and ONE H2D copy (the reference does
+        ``data.to(device)``: a blocking copy per leaf).  Leaves already on the device pass through."""
+        leaves = list(_leaf_items(data))
+        host = [(path, v) for path, v in leaves if isinstance(v, torch.Tensor) and v.device.type == "cpu"]
+        if not host or len(host) != len(leaves):
+            return data.to(self._dev)
+        key = tuple((path, tuple(v.shape), v.dtype) for path, v in host)
+        plan = self._stage_plans.get(key)
+        if plan is None:
+            off, plan_l = 0, []
+            for path, v in host:
+                nb = v.numel() * v.element_size()
+                plan_l.append((path, off, nb, v.dtype, tuple(v.shape)))
+                off = (off + nb + 255) & ~255
+            plan = self._stage_plans[key] = (plan_l, max(off, 256))
+        plan_l, total = plan
+        stage, slot = self._ring.take(total)
+        for (path, off, nb, dt, shape), (_, v) in zip(plan_l, host):
+            stage[off:off + nb].view(dt).view(shape).copy_(v)
+        dev = torch.empty(total, dtype=torch.uint8, device=self._dev)
+        dev.copy_(stage[:total], non_blocking=True)
+        self._ring.sent(slot, self._dev)
+        out = {path: dev[off:off + nb].view(dt).view(shape) for path, off, nb, dt, shape in plan_l}
+        bs = tuple(data.batch_size) if hasattr(data, "batch_size") else ()
+        return _unflatten(out, bs)
 
     # -- properties (replay_buffer.py:39-58) ---------------------------------------------------
     @property
@@ -116,6 +175,8 @@ class ReplayBuffer:
     # -- ingest ---------------------------------------------------------------------------------
     def _prepare(self, data) -> tuple[dict[tuple, torch.Tensor], int]:
         data = _as_collection(data)
+        if any(isinstance(v, torch.Tensor) and v.device.type == "cpu" for _, v in _leaf_items(data)):
+            data = self._to_device(data)
         leaves = {}
         n = None
         for path, v in _leaf_items(data):
@@ -239,7 +300,7 @@ class MultiStepReplayBuffer(ReplayBuffer):
 
     def add(self, data: DataType):
         """:173-194 — returns the oldest transition of the window (or None while filling)."""
-        data = _as_collection(data).to(self._dev)
+        data = self._to_device(_as_collection(data))
         self.n_step_buffer.append(data)
         if len(self.n_step_buffer) < self.n_step:
             return None
@@ -367,8 +428,15 @@ class PrioritizedReplayBuffer(ReplayBuffer):
         self.max_priority = max(self.max_priority, priority)
 
     def _uniforms(self, batch_size: int) -> torch.Tensor:
-        # B x torch.rand(1).item() (replay_buffer.py:377) == torch.rand(B) on the CPU generator
-        return torch.rand(batch_size).to(self._dev, non_blocking=True)
+        # B x torch.rand(1).item() (replay_buffer.py:377) == torch.rand(B) on the CPU generator; drawn straight
+        # into a pinned block so the H2D copy is asynchronous
+        stage, slot = self._ring.take(batch_size * 4)
+        host = stage[:batch_size * 4].view(torch.float32)
+        torch.rand(batch_size, out=host)
+        dev = torch.empty(batch_size, dtype=torch.float32, device=self._dev)
+        dev.copy_(host, non_blocking=True)
+        self._ring.sent(slot, self._dev)
+        return dev
 
     def _sample(self, batch_size: int, beta: float | None):
         idx = torch.empty(batch_size, dtype=torch.int64, device=self._dev)
@@ -411,22 +479,30 @@ class PrioritizedReplayBuffer(ReplayBuffer):
         return samples
 
     def update_priorities(self, indices, priorities) -> None:
-        """:411-428 — floor at 1e-5, leaf = p**alpha in CPython doubles (host, bit-exact),
-        batched last-writer-wins tree update on device (b2rl_tree_set)."""
+        """:411-428 — floor at 1e-5, leaf = p**alpha in host doubles with the C library's ``pow`` (what CPython's
+        ``**`` evaluates: bit-identical leaves, tests/test_host_pow_cpu.py), one asynchronous H2D from pinned
+        memory, batched last-writer-wins tree update on device (b2rl_tree_set)."""
         if isinstance(priorities, torch.Tensor):
-            pri = priorities.detach().reshape(-1).cpu().tolist()
+            pri = priorities.detach().reshape(-1).to(device="cpu", dtype=torch.float32).numpy()
         else:
-            pri = np.asarray(priorities).reshape(-1).tolist()
+            pri = np.ascontiguousarray(np.asarray(priorities).reshape(-1), dtype=np.float32)
         if isinstance(indices, torch.Tensor):
-            idx_dev = indices.detach().reshape(-1).to(self._dev, dtype=torch.int64)
+            idx_dev = indices.detach().reshape(-1)
+            if idx_dev.device != self._dev or idx_dev.dtype != torch.int64:
+                idx_dev = idx_dev.to(self._dev, dtype=torch.int64)
         else:
             idx_dev = torch.as_tensor(np.asarray(indices).reshape(-1), dtype=torch.int64).to(self._dev)
-        n = min(idx_dev.numel(), len(pri))
-        alpha = self.alpha
-        floored = [p if p > 1e-5 else 1e-5 for p in pri[:n]]        # max(priority.item(), 1e-5)
-        p_alpha = torch.tensor([p ** alpha for p in floored], dtype=torch.float64)
-        self.max_priority = max(self.max_priority, max(floored)) if n else self.max_priority
-        pa_dev = p_alpha.to(self._dev, non_blocking=True)
+        n = min(idx_dev.numel(), pri.size)
+        if n == 0:
+            return
+        stage, slot = self._ring.take(n * 8)
+        mx = ctypes.c_double(self.max_priority)
+        _lib.check(self._lib.b2rl_host_priority_pow(pri.ctypes.data, n, float(self.alpha), 1e-5, stage.data_ptr(),
+                                                    ctypes.byref(mx)))
+        self.max_priority = mx.value
+        pa_dev = torch.empty(n, dtype=torch.float64, device=self._dev)
+        pa_dev.copy_(stage[:n * 8].view(torch.float64), non_blocking=True)
+        self._ring.sent(slot, self._dev)
         _lib.check(self._lib.b2rl_tree_set(self.sum_tree.data_ptr, self.min_tree.data_ptr, self._cap,
                                            idx_dev.data_ptr(), pa_dev.data_ptr(), n, _lib.stream_ptr(self._dev)))
         self._keep = (idx_dev, pa_dev)

@@ -34,6 +34,12 @@ int b2rl_step_state_write(const b2rl_step_state *state_host, b2rl_step_state *st
     return B2RL_OK;
 }
 
+int b2rl_copy_d2h(void *dst_pinned_host, const void *src, size_t bytes, void *stream) {
+    B2RL_CHECK_ARG(dst_pinned_host && src, "NULL argument");
+    B2RL_CUDA(cudaMemcpyAsync(dst_pinned_host, src, bytes, cudaMemcpyDeviceToHost, as_stream(stream)));
+    return B2RL_OK;
+}
+
 int b2rl_graph_begin(void *stream) {
     B2RL_CHECK_ARG(stream != nullptr, "graph capture needs a non-default stream");
     B2RL_CUDA(cudaStreamBeginCapture(as_stream(stream), cudaStreamCaptureModeRelaxed));

@@ -4,6 +4,8 @@
 // (:100-107 write, :126/:204/:345 gather) and the Python loop of _get_n_step_info (:236-256).
 // Pure byte movement: 128-bit coalesced loads/stores when rows are 16-byte multiples (uint8
 // 4x84x84 frames are 28224 B = 1764 x 16 B), scalar path otherwise.
+#include <math.h>
+
 #include "common.cuh"
 
 namespace b2rl {
@@ -261,6 +263,23 @@ int b2rl_select_copy(void *dst, const void *const *srcs_host, int n_srcs, const 
     if (blocks > sm_count() * 4) blocks = sm_count() * 4;
     select_copy_kernel<<<blocks, 256, 0, as_stream(stream)>>>(static_cast<uint8_t *>(dst), sp, which, bytes);
     B2RL_LAUNCH_CHECK();
+    return B2RL_OK;
+}
+
+/* HOST arithmetic of PrioritizedReplayBuffer.update_priorities (replay_buffer.py:411-428, :311-329): for every
+ * float32 priority p: q = max((double)p, floor); out[i] = q ** alpha with glibc pow — the function CPython's float
+ * `**` calls, so the leaves are bit-identical to the reference's — and the running maximum of q. */
+int b2rl_host_priority_pow(const float *priority_host, int64_t n, double alpha, double floor_, double *out_host,
+                           double *max_host) {
+    B2RL_CHECK_ARG(n >= 0 && (n == 0 || (priority_host && out_host)), "bad arguments");
+    double mx = max_host ? *max_host : 0.0;
+    for (int64_t i = 0; i < n; ++i) {
+        const double p = (double)priority_host[i];
+        const double q = p > floor_ ? p : floor_;
+        out_host[i] = pow(q, alpha);
+        if (q > mx) mx = q;
+    }
+    if (max_host) *max_host = mx;
     return B2RL_OK;
 }
 

@@ -131,6 +131,68 @@ class _FusedPlan:
         self.front = self.tail = None
 
 
+class _ApiPlan:
+    """Captured graphs of ``rainbow_learn`` on ONE set of batch buffers (keyed by their device addresses).
+
+    ``agent.learn(experiences, ...)`` receives fresh tensors every step, but in a steady training loop the
+    caching allocator hands the sampler the same blocks again and again: when every pointer of a call matches a
+    plan, the step is two graph launches (forwards + projection + loss + D2H of loss/priorities; backward + optimiser
+    + noise reset) instead of ~45 eager launches; any other call runs eagerly.  Nothing is copied, nothing is
+    assumed about the tensors beyond their addresses."""
+
+    def __init__(self, eng, B):
+        dev = eng.device
+        self.eng, self.B = eng, B
+        self.loss_elem = torch.empty(B, dtype=torch.float32, device=dev)
+        self.out = torch.empty(B + 1, dtype=torch.float32, device=dev)
+        self.host = torch.empty(B + 1, dtype=torch.float32).pin_memory()
+        self.state_host = _lib.StepState()
+        self.state_dev = torch.zeros(ctypes.sizeof(_lib.StepState), dtype=torch.uint8, device=dev)
+        self.front = self.tail = None
+        self.seen = 0
+        self.rb_ev, self.fwd_done, self.done = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+
+    def capture(self, batch, gamma, driver, weights, weights_mode, support, hp, side_streams) -> None:
+        eng, B = self.eng, self.B
+        lib = eng.lib
+        desc = ctypes.byref(eng.layout.desc)
+        cfg = eng._cfg(B, gamma=gamma, v_min=hp["v_min"], v_max=hp["v_max"], delta_z=hp["delta_z"], weights_mode=weights_mode,
+                       driver_shapes=int(driver), clip=1, lr=hp["lr"], tau=hp["tau"], prior_eps=hp["prior_eps"], accumulate=0,
+                       use_noise=1, step=1, side_streams=side_streams)
+        bufs, keep = eng._bufs(B, batch, weights, support, self.loss_elem, self.out[:B], self.out[B:], None, None)
+        bufs.step_state = self.state_dev.data_ptr()
+        self._keep = (cfg, bufs)
+        cap = torch.cuda.Stream(device=eng.device)
+        cap.wait_stream(torch.cuda.current_stream(eng.device))
+        s = cap.cuda_stream
+        gh, gt = ctypes.c_void_p(), ctypes.c_void_p()
+        _lib.check(lib.b2rl_graph_begin(s))
+        try:
+            _lib.check(lib.b2rl_step_state_write(ctypes.byref(self.state_host), self.state_dev.data_ptr(), s))
+            _lib.check(lib.b2rl_rainbow_loss(desc, ctypes.byref(cfg), ctypes.byref(bufs), s))
+            _lib.check(lib.b2rl_copy_d2h(self.host.data_ptr(), self.out.data_ptr(), (B + 1) * 4, s))
+        finally:
+            _lib.check(lib.b2rl_graph_end(s, ctypes.byref(gh)))
+        _lib.check(lib.b2rl_graph_begin(s))
+        try:
+            _lib.check(lib.b2rl_rainbow_backward(desc, ctypes.byref(cfg), ctypes.byref(bufs), s))
+            _lib.check(lib.b2rl_optim_step(desc, ctypes.byref(cfg), ctypes.byref(bufs), s))
+            _lib.check(lib.b2rl_noise_reset_state(desc, eng.actor.eps.data_ptr(), eng.philox_seed,
+                                                  self.state_dev.data_ptr(), 0, s))
+            _lib.check(lib.b2rl_noise_reset_state(desc, eng.target.eps.data_ptr(), eng.philox_seed,
+                                                  self.state_dev.data_ptr(), 1, s))
+        finally:
+            _lib.check(lib.b2rl_graph_end(s, ctypes.byref(gt)))
+        self.front, self.tail = gh.value, gt.value
+
+    def destroy(self) -> None:
+        lib = self.eng.lib
+        for g in (self.front, self.tail):
+            if g:
+                lib.b2rl_graph_destroy(g)
+        self.front = self.tail = None
+
+
 class LearnEngine:
     def __init__(self, layout: FlatLayout, actor: NetBuffers, target: NetBuffers):
         self.layout, self.actor, self.target = layout, actor, target
@@ -148,10 +210,11 @@ class LearnEngine:
         self._host_out: dict = {}
         self.philox_offset = 0
         self._plans: dict = {}
+        self._api_plans: dict = {}
 
     def __del__(self):
         try:
-            for plan in self._plans.values():
+            for plan in list(self._plans.values()) + list(self._api_plans.values()):
                 plan.destroy()
         except Exception:  # noqa: BLE001 - interpreter shutdown
             pass
@@ -317,6 +380,12 @@ class LearnEngine:
         so a caller that needs Python numbers (the reference's ``learn`` return value) does not wait
         for the rest of the step."""
         self.join()
+        if (_GRAPH and host_readback and noise_normals is None and len(passes) == 1 and not want_proj and row_idx is None
+                and after_loss is None and self.noise_count > 0):
+            done = self._api_graph_learn(passes[0], B=B, support=support, weights=weights, weights_mode=weights_mode, hp=hp,
+                                         side_streams=side_streams)
+            if done:
+                return None
         desc = ctypes.byref(self.layout.desc)
         loss_elem = torch.empty(B, dtype=torch.float32, device=self.device)
         out = torch.empty(B + 1, dtype=torch.float32, device=self.device)     # priorities | scalar loss (one D2H)
@@ -381,6 +450,63 @@ class LearnEngine:
                 after_loss(priorities)
             tail()
         return loss_scalar, loss_elem, priorities, proj
+
+    def _api_graph_learn(self, one_pass, *, B, support, weights, weights_mode, hp, side_streams) -> bool:
+        """Graph replay of ``rainbow_learn`` when this exact set of device buffers has been seen before (see
+        ``_ApiPlan``).  Returns False when the call has to run eagerly (first sightings, host tensors, odd dtypes)."""
+        batch, gamma, driver = one_pass
+        want = torch.uint8 if self.layout.desc.obs_u8 else torch.float32
+        ts = [batch["obs"], batch["next_obs"], batch["action"], batch["reward"], batch["done"]]
+        if weights is not None:
+            ts.append(weights)
+        for i, t in enumerate(ts):
+            if not (isinstance(t, torch.Tensor) and t.device == self.device and t.is_contiguous()
+                    and t.dtype == (want if i < 2 else torch.float32)):
+                return False
+        for t in ts[2:5]:
+            if t.numel() != B:
+                return False
+        if ts[0].numel() != B * self.layout.desc.obs_elems or ts[1].numel() != ts[0].numel():
+            return False
+        if weights is not None and weights.numel() != B:
+            return False
+        if _SIDE is not None:
+            side_streams = _SIDE
+        elif side_streams is None:
+            side_streams = 1
+        key = (B, weights_mode, side_streams, float(gamma), bool(driver), support.data_ptr(), float(hp["v_min"]),
+               float(hp["v_max"]), float(hp["delta_z"]), float(hp["tau"]), float(hp["prior_eps"]),
+               *(t.data_ptr() for t in ts))
+        plan = self._api_plans.get(key)
+        if plan is None:
+            if len(self._api_plans) >= 16:                   # addresses keep changing: stop trying to cache them
+                return False
+            self._api_plans[key] = _ApiPlan(self, B)
+            return False
+        plan.seen += 1
+        st = plan.state_host
+        self.step += 1
+        st.lr = float(hp["lr"])
+        st.bias_correction1 = 1.0 - 0.9 ** self.step
+        st.bias_correction2 = 1.0 - 0.999 ** self.step
+        st.noise_offset[0] = self.philox_offset
+        st.noise_offset[1] = self.philox_offset + self.noise_count
+        self.philox_offset += 2 * self.noise_count
+        if plan.front is None:
+            plan.capture(batch, gamma, driver, weights, weights_mode, support, hp, side_streams)
+        lib, cur = self.lib, torch.cuda.current_stream(self.device)
+        _lib.check(lib.b2rl_graph_launch(plan.front, ctypes.byref(st), cur.cuda_stream))
+        plan.rb_ev.record(cur)
+        self._readback = (plan.host, plan.rb_ev, B)
+        # backward + optimiser + noise reset under the caller's next calls (sampling, ingest, the next agent)
+        if self._bwd_stream is None:
+            self._bwd_stream = torch.cuda.Stream(device=self.device)
+        self._bwd_stream.wait_event(plan.rb_ev)
+        _lib.check(lib.b2rl_graph_launch(plan.tail, None, self._bwd_stream.cuda_stream))
+        plan.done.record(self._bwd_stream)
+        self._opt_done = plan.done
+        self._keepalive = (ts, support)          # the tail reads the batch: keep it allocated until the next join
+        return True
 
     def dqn_learn(self, batch: dict, *, B: int, hp: dict, double: bool):
         self.join()

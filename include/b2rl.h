@@ -136,6 +136,13 @@ int b2rl_ring_write_multi(int n_fields, void *const *storage, const void *const 
 int b2rl_gather_rows_multi(int n_fields, void *const *dst, const void *const *storage, const int64_t *row_bytes,
                            const int64_t *idx, int64_t n, void *stream);
 
+/* HOST helper (no device work): PrioritizedReplayBuffer.update_priorities' per-priority arithmetic
+ * (replay_buffer.py:411-428, :311-329) — q = max((double)p, floor); out[i] = pow(q, alpha) with the C library's pow,
+ * which is what CPython's `priority ** alpha` evaluates, so the leaves are bit-identical to the reference's; *max_host
+ * (in/out, nullable) accumulates max(q) (max_priority, :329). */
+int b2rl_host_priority_pow(const float *priority_host, int64_t n, double alpha, double floor_, double *out_host,
+                           double *max_host);
+
 /* MultiStepReplayBuffer._get_n_step_info (replay_buffer.py:206-258) over a device window of n
  * per-env batches (oldest first): reward_out[e] = sum_i gamma^i r_i[e] (fp32 accumulate, gamma^i a
  * double rounded to f32 like torch scalar mul), stop after the first step i>=1 where ANY env is
@@ -332,6 +339,8 @@ int b2rl_rainbow_learn(const b2rl_net_desc *net_host, const b2rl_learn_cfg *cfg_
 typedef struct b2rl_graph b2rl_graph;
 /* *state_dev <- *state_host (one tiny kernel; the struct travels by value in the launch). */
 int b2rl_step_state_write(const b2rl_step_state *state_host, b2rl_step_state *state_dev, void *stream);
+/* Asynchronous device -> pinned-host copy on `stream` (capturable: the loss / priority read-back of a replayed step). */
+int b2rl_copy_d2h(void *dst_pinned_host, const void *src, size_t bytes, void *stream);
 int b2rl_graph_begin(void *stream);
 int b2rl_graph_end(void *stream, b2rl_graph **out_host);
 /* state_host may be NULL when the graph holds no b2rl_step_state_write node. */

@@ -115,3 +115,55 @@ def test_graph_path_counts_its_kernels_and_matches_population_helper():
     torch.cuda.synchronize()
     plan = next(iter(eng._plans.values()))
     assert n1 - n0 == plan.kernels and plan.kernels > 0
+
+
+def test_api_learn_graph_replay_matches_eager_bit_for_bit():
+    """``agent.learn`` replays two captured graphs when it is handed the same device buffers again (the steady
+    state of a training loop under torch's caching allocator): losses, priorities, parameters, moments and noise are
+    identical to the eager launch sequence; a call on other buffers falls back to eager and stays correct."""
+    import agilerl_b200.engine as E
+    from agilerl_b200.algorithms import RainbowDQN
+    from agilerl_b200.compat import spaces
+
+    def run(graph):
+        E._GRAPH = graph
+        try:
+            torch.manual_seed(0)
+            net = {"encoder_config": {"channel_size": [8, 16], "kernel_size": [4, 3], "stride_size": [2, 1]},
+                   "head_config": {"hidden_size": [32]}, "latent_dim": 16}
+            agent = RainbowDQN(spaces.Box(0, 255, OBS, np.uint8), spaces.Discrete(A), index=2, net_config=net, batch_size=B,
+                               v_min=-10.0, v_max=10.0, lr=1e-3)
+            g = torch.Generator().manual_seed(9)
+            exp = dict(obs=torch.empty((B, *OBS), dtype=torch.uint8, device="cuda"), next_obs=torch.empty((B, *OBS), dtype=torch.uint8, device="cuda"),
+                       action=torch.empty(B, 1, device="cuda"), reward=torch.empty(B, 1, device="cuda"), done=torch.empty(B, 1, device="cuda"),
+                       weights=torch.empty(B, device="cuda"), idxs=torch.arange(B, device="cuda"))
+            other = {k: v.clone() for k, v in exp.items()}
+            trace = []
+            for step in range(7):
+                tgt = other if step == 5 else exp                      # one call on different buffers (eager fallback)
+                tgt["obs"].copy_(torch.randint(0, 256, (B, *OBS), dtype=torch.uint8, generator=g))
+                tgt["next_obs"].copy_(torch.randint(0, 256, (B, *OBS), dtype=torch.uint8, generator=g))
+                tgt["action"].copy_(torch.randint(0, A, (B, 1), generator=g).float())
+                tgt["reward"].copy_(torch.randn(B, 1, generator=g))
+                tgt["done"].copy_((torch.rand(B, 1, generator=g) < 0.1).float())
+                tgt["weights"].copy_(torch.rand(B, generator=g) + 0.5)
+                if step == 3:
+                    agent.lr = 5e-4                                    # an lr mutation between steps
+                loss, idxs, pri = agent.learn(tgt, n_experiences=tgt, per=True)
+                trace.append((loss, pri.copy()))
+            agent.synchronize()
+            torch.cuda.synchronize()
+            e = agent.engine
+            replays = sum(p.seen for p in e._api_plans.values())
+            return trace, [e.actor.params.clone(), e.target.params.clone(), e.actor.eps.clone(), e.target.eps.clone(),
+                           e.exp_avg.clone(), e.exp_avg_sq.clone()], replays
+        finally:
+            E._GRAPH = True
+
+    t_e, s_e, r_e = run(False)
+    t_g, s_g, r_g = run(True)
+    assert r_e == 0 and r_g >= 4, (r_e, r_g)
+    for k, ((le, pe), (lg, pg)) in enumerate(zip(t_e, t_g)):
+        assert le == lg and np.array_equal(pe, pg), f"loss / priorities differ at step {k}"
+    for k, (a, b) in enumerate(zip(s_e, s_g)):
+        assert torch.equal(a, b), f"state tensor {k} differs"
