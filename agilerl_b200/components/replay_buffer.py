@@ -432,7 +432,7 @@ class PrioritizedReplayBuffer(ReplayBuffer):
         # into a pinned block so the H2D copy is asynchronous
         stage, slot = self._ring.take(batch_size * 4)
         host = stage[:batch_size * 4].view(torch.float32)
-        torch.rand(batch_size, out=host)
+        host.copy_(torch.rand(batch_size))
         dev = torch.empty(batch_size, dtype=torch.float32, device=self._dev)
         dev.copy_(host, non_blocking=True)
         self._ring.sent(slot, self._dev)

@@ -277,21 +277,30 @@ def conv1_roofline(eng, nmem, device):
     frames = nmem._fields[("obs",)]
     flops = 2.0 * B * L.out_h * L.out_w * L.out_c * L.in_c * L.ksize * L.ksize
     alg_bytes = B * desc.obs_elems + out.numel() * 4 + (L.out_c * L.in_c * L.ksize * L.ksize + L.out_c) * 4
-    times = []
     stream = _lib.stream_ptr(torch.device(device))
-    for it in range(25):
-        idx = torch.randint(0, BUFFER, (B,), device=device)
+
+    def launch(idx, reuse):
+        _lib.check(lib.b2rl_encoder_layer_forward(ctypes.byref(desc), 0, eng.actor.params.data_ptr(), frames.data_ptr(),
+                                                  idx.data_ptr(), B, out.data_ptr(), ws.data_ptr(), ws.numel(), int(reuse),
+                                                  stream))
+    # the first call splits the weights into digit planes (weight_digits_kernel: once per step in the real loop); the
+    # timed launches are the convolution kernel alone, 20 back to back between one pair of events (each on B fresh
+    # random rows of the 2.8 GB frame ring, so nothing is L2-resident), which amortises the event/launch latency
+    # that would otherwise dominate a ~10 us kernel
+    per_batch = 20
+    idxs = [torch.randint(0, BUFFER, (B,), device=device) for _ in range(per_batch)]
+    launch(idxs[0], False)
+    torch.cuda.synchronize()
+    times = []
+    for it in range(8):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        # it == 0 splits the weights into digit planes (weight_digits_kernel, once per step in the real loop); the timed
-        # launches are the convolution kernel alone
-        _lib.check(lib.b2rl_encoder_layer_forward(ctypes.byref(desc), 0, eng.actor.params.data_ptr(), frames.data_ptr(),
-                                                  idx.data_ptr(), B, out.data_ptr(), ws.data_ptr(), ws.numel(), int(it > 0),
-                                                  stream))
+        for idx in idxs:
+            launch(idx, True)
         e1.record()
         torch.cuda.synchronize()
-        if it >= 5:
-            times.append(e0.elapsed_time(e1))
+        if it >= 2:
+            times.append(e0.elapsed_time(e1) / per_batch)
     ms = statistics.mean(times)
     desc = {"kernel": "conv_fwd_i8_kernel<8, 8> (digit planes split once per step by weight_digits_kernel, not in the timed launch): conv1 forward (4->32, k8 s4) of B=256 frames gathered "
                       "from the replay ring; persistent warp-specialised kernel, tcgen05.mma kind::i8 over the raw frame bytes "
@@ -446,6 +455,83 @@ def tournament_generation(agents, world, rank, device):
             "elite_index": int(slots[0][1])}, new_pop
 
 
+def ppo_workload(args):
+    """BASELINE configs[3]: PPO, 256 vector envs x 8-dim observations, pop = 8 — the rollout post-processing the
+    reference runs on the host after every collection (RolloutBuffer.compute_returns_and_advantages,
+    rollout_buffer.py:413-481: D2H, a NumPy loop over T, H2D) plus the global advantage normalisation of
+    PPO.learn (ppo.py:831-834).  One "step" = that post-processing for every agent of the population
+    (b2rl_gae_scan_normalize: one launch per agent).  T = learn_step / num_envs = 2048 / 256 = 8 (reference
+    defaults); B2RL_PPO_T overrides the horizon."""
+    from agilerl_b200 import _lib
+    from agilerl_b200.components.rollout import compute_returns_and_normalized_advantages
+    from oracle import gae as ogae
+    E, T = 256, int(os.environ.get("B2RL_PPO_T", "8"))
+    device = "cuda:0"
+    torch.cuda.set_device(0)
+    lib = _lib.load(require_cuda=True)
+    rng = np.random.default_rng(0)
+    host = [dict(r=rng.standard_normal((T, E)).astype(np.float32), v=rng.standard_normal((T, E)).astype(np.float32),
+                 d=rng.random((T, E)) < 0.02, lv=rng.standard_normal(E).astype(np.float32),
+                 ld=(rng.random(E) < 0.02).astype(np.float32)) for _ in range(POP)]
+    dev = [{k: torch.from_numpy(np.ascontiguousarray(x)).to(device) for k, x in h.items()} for h in host]
+    pin = [{k: torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for k, x in h.items()} for h in host]
+
+    def dev_step():
+        for a in dev:
+            compute_returns_and_normalized_advantages(a["r"], a["d"], a["v"], a["lv"], a["ld"], 0.99, 0.95, True)
+
+    def e2e_step():
+        outs = []
+        for a in pin:
+            adv, ret, nrm = compute_returns_and_normalized_advantages(
+                a["r"].to(device, non_blocking=True), a["d"].to(device, non_blocking=True), a["v"].to(device, non_blocking=True),
+                a["lv"].to(device, non_blocking=True), a["ld"].to(device, non_blocking=True), 0.99, 0.95, True)
+            outs.append((ret.cpu(), nrm.cpu()))                 # the minibatch loop reads returns + normalised advantages
+        return outs
+
+    for _ in range(max(args.warmup, 3)):
+        dev_step(); e2e_step()
+    l0 = lib.b2rl_launch_count()
+    ms, ms_all = time_region(dev_step, args.steps, False)
+    launches = (lib.b2rl_launch_count() - l0) // len(ms_all)
+    ms_e2e, _ = time_region(e2e_step, args.steps, False, repeats=3)
+    value = POP * args.steps / (ms / 1e3)
+    # the oracle: the reference's NumPy loop + torch normalisation on the host (its own path: the data is already there)
+    t0 = time.perf_counter()
+    n_cpu = 0
+    while time.perf_counter() - t0 < 2.0:
+        for h in host:
+            adv, ret = ogae.compute_returns_and_advantages(h["r"], h["d"], h["v"], h["lv"], h["ld"], 0.99, 0.95, True)
+            ogae.normalize_advantages(adv)
+            n_cpu += 1
+    cpu_val = n_cpu / (time.perf_counter() - t0)
+    hbm_peak, _, peak_kind = peaks()
+    alg = T * E * (4 + 1 + 4 + 4 + 4) + T * E * 4 * 3          # scan: r, d, v in, adv, ret out; normalisation: 2 reads + 1 write
+    per_launch_ms = ms / args.steps / POP
+    line = {"metric": "PPO rollout post-processing (GAE scan + advantage normalisation), rollouts/sec, pop=8",
+            "value": value, "unit": "rollouts/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"PPO GAE + advantage normalisation, {E} vector envs x T={T} steps per rollout, pop={POP} "
+                                   "(BASELINE configs[3])", "pop": POP, "envs": E, "T": T,
+                       "l2": "inputs are a few KB: latency-bound by T dependent float64 steps, not by HBM"},
+            "timing": {"repeats": len(ms_all), "stat": "median", "ms_repeats": [round(x, 4) for x in ms_all]},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "gae_fused_kernel (one CTA: thread e walks environment e backwards in float64, the CTA then "
+                                   "normalises the T x E advantages)", "bound": "hbm",
+                         "achieved": alg / (per_launch_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": alg / (per_launch_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                         "alg_bytes_per_launch": alg, "ms_per_launch": per_launch_ms,
+                         "note": "timed inside the population loop incl. the host call; a serial recurrence of T dependent fp64 "
+                                 "steps per environment — latency-bound by construction (SURVEY 8f-2)"},
+            "e2e": {"value": POP * args.steps / (ms_e2e / 1e3), "unit": "rollouts/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": POP * (T * E * 9 + E * 8), "d2h_bytes_per_step": POP * T * E * 8},
+            "cpu_baseline": {"value": cpu_val, "unit": "rollouts/s", "cores": 1, "kind": "port",
+                             "sample": "2 s of oracle.gae (the reference's NumPy loop, bit-exact restatement) + torch normalisation "
+                                       "per rollout, host arrays in place (no copies counted)"}}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -454,7 +540,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="rainbow", choices=["rainbow", "ppo"],
+                    help="rainbow: BASELINE configs[1] (the metric line the driver reads); ppo: configs[3] post-processing")
     args = ap.parse_args()
+    if args.workload == "ppo":
+        return ppo_workload(args)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
