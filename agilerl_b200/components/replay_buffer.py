@@ -75,6 +75,10 @@ def _as_collection(data) -> Any:
     raise TypeError(f"Cannot store data of type {type(data)} in a replay buffer")
 
 
+import os as _os
+_NOSYNC = _os.environ.get("B2RL_RING_NOSYNC") == "1"     # diagnostics only
+
+
 class _PinnedRing:
     """A few pinned host blocks used round-robin as the source of asynchronous H2D copies.  A slot is handed
     out again only after the copy that last read it has completed (its event), so callers may overwrite their
@@ -90,7 +94,7 @@ class _PinnedRing:
     def take(self, nbytes: int) -> tuple[torch.Tensor, int]:
         k = self.i
         self.i = (k + 1) % self.slots
-        if self.events[k] is not None:
+        if self.events[k] is not None and not _NOSYNC:
             self.events[k].synchronize()
         buf = self.bufs[k]
         if buf is None or buf.numel() < nbytes:
@@ -143,8 +147,13 @@ class ReplayBuffer:
             plan = self._stage_plans[key] = (plan_l, max(off, 256))
         plan_l, total = plan
         stage, slot = self._ring.take(total)
+        base = stage.data_ptr()
         for (path, off, nb, dt, shape), (_, v) in zip(plan_l, host):
-            stage[off:off + nb].view(dt).view(shape).copy_(v)
+            # plain memcpy: a torch CPU copy of a frame stack is large enough to wake torch's whole intra-op thread
+            # pool, whose workers then spin on every core of the box for their block time (measured: 5x slower loop)
+            if not v.is_contiguous():
+                v = v.contiguous()
+            ctypes.memmove(base + off, v.data_ptr(), nb)
         dev = torch.empty(total, dtype=torch.uint8, device=self._dev)
         dev.copy_(stage[:total], non_blocking=True)
         self._ring.sent(slot, self._dev)
@@ -432,7 +441,8 @@ class PrioritizedReplayBuffer(ReplayBuffer):
         # into a pinned block so the H2D copy is asynchronous
         stage, slot = self._ring.take(batch_size * 4)
         host = stage[:batch_size * 4].view(torch.float32)
-        host.copy_(torch.rand(batch_size))
+        u = torch.rand(batch_size)
+        ctypes.memmove(stage.data_ptr(), u.data_ptr(), batch_size * 4)
         dev = torch.empty(batch_size, dtype=torch.float32, device=self._dev)
         dev.copy_(host, non_blocking=True)
         self._ring.sent(slot, self._dev)

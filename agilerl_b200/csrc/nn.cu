@@ -138,6 +138,7 @@ struct LearnWS {
     size_t partial_bw_floats;
     float *norm_partials;           // kNormBlocks
     float *wsum;                    // 1
+    unsigned int *ticket;           // last-CTA counter of the fused loss tail
     size_t bytes;
 };
 
@@ -163,6 +164,7 @@ static void carve_learn(const b2rl_net_desc &net, int64_t B, bool two_sided_onli
     ws.partial_bw = b.take<float>(ws.partial_bw_floats);
     ws.norm_partials = b.take<float>(kNormBlocks);
     ws.wsum = b.take<float>(4);
+    ws.ticket = b.take<unsigned int>(4);
     ws.bytes = b.off + 256;
 }
 
@@ -660,12 +662,12 @@ struct ProjCfg { float gamma, v_min, v_max, delta_z; };
 // When v_on / adv_on are given (the online network's outputs on next_obs) the kernel first selects
 // a* = argmax_a E[Z_online(next_obs, a)] itself (dqn_rainbow.py:315; same code as rainbow_q_kernel)
 // and records it in a_star; otherwise it reads a_star.
-__global__ void rainbow_target_kernel(const float *__restrict__ v, const float *__restrict__ adv,
+// returns the shared-memory row holding the projected distribution of this row (valid when proj != NULL)
+__device__ __forceinline__ float *rainbow_target_row(float *sm, const float *__restrict__ v, const float *__restrict__ adv,
                                       int32_t *__restrict__ a_star, const float *__restrict__ reward,
                                       const float *__restrict__ done, const float *__restrict__ support, ProjCfg pc,
                                       int A, int N, float *__restrict__ tdist, float *__restrict__ proj,
                                       const float *__restrict__ v_on, const float *__restrict__ adv_on) {
-    extern __shared__ float sm[];
     float *x = sm;                 // A*N
     float *pr = sm + A * N;        // N   projected
     float *wl = pr + N;            // N
@@ -703,7 +705,7 @@ __global__ void rainbow_target_kernel(const float *__restrict__ v, const float *
     __syncthreads();
     if (tdist)
         for (int n = threadIdx.x; n < N; n += blockDim.x) tdist[row * N + n] = p[n];
-    if (!proj) return;
+    if (!proj) return pr;
     const float r = reward[row], d = done[row];
     const float g = __fmul_rn(__fsub_rn(1.0f, d), pc.gamma);              // (1 - dones) * gamma
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
@@ -713,9 +715,12 @@ __global__ void rainbow_target_kernel(const float *__restrict__ v, const float *
         int L = (int)floorf(b), U = (int)ceilf(b);
         if (U > 0 && U == L) L -= 1;                                        // quirk Q9 order
         if ((N - 1) > L && U == L) U += 1;
-        Li[n] = L; Ui[n] = U;
         wl[n] = __fsub_rn((float)U, b);
         wu[n] = __fsub_rn(b, (float)L);
+        // delta_z is a rounded float: b can exceed N-1 by an ulp (U == N).  The reference's index_add_ would then
+        // raise; here the stray mass stays in the last atom instead of landing in the neighbouring scratch row
+        Li[n] = L < 0 ? 0 : (L > N - 1 ? N - 1 : L);
+        Ui[n] = U < 0 ? 0 : (U > N - 1 ? N - 1 : U);
         pr[n] = 0.f;
     }
     __syncthreads();
@@ -725,6 +730,16 @@ __global__ void rainbow_target_kernel(const float *__restrict__ v, const float *
     }
     __syncthreads();
     for (int n = threadIdx.x; n < N; n += blockDim.x) proj[row * N + n] = pr[n];
+    return pr;
+}
+
+__global__ void rainbow_target_kernel(const float *__restrict__ v, const float *__restrict__ adv,
+                                      int32_t *__restrict__ a_star, const float *__restrict__ reward,
+                                      const float *__restrict__ done, const float *__restrict__ support, ProjCfg pc,
+                                      int A, int N, float *__restrict__ tdist, float *__restrict__ proj,
+                                      const float *__restrict__ v_on, const float *__restrict__ adv_on) {
+    extern __shared__ float sm[];
+    rainbow_target_row(sm, v, adv, a_star, reward, done, support, pc, A, N, tdist, proj, v_on, adv_on);
 }
 
 // Driver-shape (quirk Q2) projection: reward/done arrive [B,1,1], the reference's broadcasting
@@ -769,12 +784,12 @@ __global__ void q2_project_kernel(const float *__restrict__ tdist, const float *
 // loss_i = -sum_n proj[i][n] * log_softmax(x[a_i])[n]                      (dqn_rainbow.py:362-367)
 // d loss_i / d x[a_i][n] = softmax[n] * sum_m proj[i][m] - proj[i][n]
 // dueling backward: dv[n] = dx[n];  dadv[a][n] = [a==a_i] dx[n] - dx[n]/A
-__global__ void rainbow_loss_kernel(const float *__restrict__ v, const float *__restrict__ adv,
-                                    const float *__restrict__ action, const float *__restrict__ proj,
+// projrow: this row's projected distribution (global or shared memory)
+__device__ __forceinline__ void rainbow_loss_row(float *sm, const float *__restrict__ v, const float *__restrict__ adv,
+                                    const float *__restrict__ action, const float *projrow,
                                     const float *__restrict__ weights, int weights_mode, int64_t B, int A, int N,
                                     int accumulate, float *__restrict__ loss_elem, float *__restrict__ dv,
                                     float *__restrict__ dadv) {
-    extern __shared__ float sm[];
     float *x = sm;              // N (action row only)
     float *red = sm + N;        // 32
     const int64_t row = blockIdx.x;
@@ -803,7 +818,7 @@ __global__ void rainbow_loss_kernel(const float *__restrict__ v, const float *__
     float l = 0.f, ps = 0.f;
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
         const float lp = x[n] - mx - lse;
-        const float pj = proj[row * N + n];
+        const float pj = projrow[n];
         l -= pj * lp;
         ps += pj;
     }
@@ -821,10 +836,65 @@ __global__ void rainbow_loss_kernel(const float *__restrict__ v, const float *__
     if (threadIdx.x == 0) loss_elem[row] = accumulate ? loss_elem[row] + l : l;
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
         const float sm_n = expf(x[n] - mx) / s;
-        const float dx = gs * (sm_n * ps - proj[row * N + n]);
+        const float dx = gs * (sm_n * ps - projrow[n]);
         dv[row * N + n] = dx;
         const float sh = dx / (float)A;
         for (int a = 0; a < A; ++a) dadv[row * (int64_t)A * N + a * N + n] = (a == ai ? dx : 0.f) - sh;
+    }
+}
+
+__global__ void rainbow_loss_kernel(const float *__restrict__ v, const float *__restrict__ adv,
+                                    const float *__restrict__ action, const float *__restrict__ proj,
+                                    const float *__restrict__ weights, int weights_mode, int64_t B, int A, int N,
+                                    int accumulate, float *__restrict__ loss_elem, float *__restrict__ dv,
+                                    float *__restrict__ dadv) {
+    extern __shared__ float sm[];
+    rainbow_loss_row(sm, v, adv, action, proj + (int64_t)blockIdx.x * N, weights, weights_mode, B, A, N, accumulate, loss_elem,
+                     dv, dadv);
+}
+
+// The loss tail of _dqn_loss for canonical shapes in ONE launch (dqn_rainbow.py:315-367, :434, :487-488): CTA = batch
+// row — a* selection + target distribution + C51 projection, then the cross-entropy of the online row against the
+// projection still sitting in shared memory (+ dL/dlogits), then the LAST CTA to finish (ticket counter) reduces the
+// per-sample losses to the scalar loss in a fixed order and writes the priorities.
+__global__ void rainbow_tail_kernel(const float *__restrict__ v_tg, const float *__restrict__ adv_tg,
+                                    int32_t *__restrict__ a_star, const float *__restrict__ reward,
+                                    const float *__restrict__ done, const float *__restrict__ support, ProjCfg pc, int A,
+                                    int N, float *__restrict__ proj, const float *__restrict__ v_nx,
+                                    const float *__restrict__ adv_nx, const float *__restrict__ v_ob,
+                                    const float *__restrict__ adv_ob, const float *__restrict__ action,
+                                    const float *__restrict__ weights, int weights_mode, int64_t B, int accumulate,
+                                    float *__restrict__ loss_elem, float *__restrict__ dv, float *__restrict__ dadv,
+                                    float prior_eps, float *__restrict__ loss_scalar, float *__restrict__ priorities,
+                                    unsigned int *__restrict__ ticket) {
+    extern __shared__ float sm[];
+    float *pr = rainbow_target_row(sm, v_tg, adv_tg, a_star, reward, done, support, pc, A, N, nullptr, proj, v_nx, adv_nx);
+    __syncthreads();
+    // the loss part reuses the dueling scratch x[0 .. N + 32) — pr (behind the A*N floats) stays intact
+    rainbow_loss_row(sm, v_ob, adv_ob, action, pr, weights, weights_mode, B, A, N, accumulate, loss_elem, dv, dadv);
+    __shared__ unsigned int s_ticket;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+    __threadfence();
+    float *red = sm;
+    float a = 0.f, w = 0.f;
+    for (int64_t i = threadIdx.x; i < B; i += blockDim.x) {
+        const float l = __ldcg(loss_elem + i);
+        if (weights_mode == 1) a += l * weights[i];
+        else a += l;
+        if (weights_mode == 2) w += weights[i];
+        if (priorities) priorities[i] = l + prior_eps;
+    }
+    a = block_reduce_sum(a, red);
+    w = block_reduce_sum(w, red);
+    if (threadIdx.x == 0) {
+        float L = a / (float)B;
+        if (weights_mode == 2) L *= w / (float)B;
+        *loss_scalar = L;
+        *ticket = 0u;
     }
 }
 
@@ -1403,6 +1473,16 @@ static int rainbow_loss(const b2rl_net_desc &net, const b2rl_learn_cfg &cfg, con
     }
     const float *fq_v = fuse_q ? v_on : nullptr, *fq_a = fuse_q ? adv_on : nullptr;
     ProjCfg pc{(float)cfg.gamma, (float)cfg.v_min, (float)cfg.v_max, (float)cfg.delta_z};
+    static const bool fuse_tail_env = !(getenv("B2RL_NO_TAIL_FUSE") && getenv("B2RL_NO_TAIL_FUSE")[0] == '1');
+    if (!cfg.driver_shapes && fuse_q && fuse_tail_env && A * N >= N + 32) {
+        B2RL_CUDA(cudaMemsetAsync(ws.ticket, 0, sizeof(unsigned int), s));
+        rainbow_tail_kernel<<<(int)B, 128, sm_t, s>>>(
+            v_tg, adv_tg, ws.a_star, bufs.reward, bufs.done, bufs.support, pc, A, N, ws.proj, v_on, adv_on, v_on + B * N,
+            adv_on + B * (int64_t)A * N, bufs.action, bufs.weights, cfg.weights_mode, B, cfg.accumulate, bufs.loss_elem,
+            ws.online.val[net.n_val - 1].g, ws.online.adv[net.n_adv - 1].g, (float)cfg.prior_eps, bufs.loss_scalar,
+            bufs.priorities, ws.ticket);
+        B2RL_LAUNCH_CHECK();
+    } else {
     if (!cfg.driver_shapes) {
         rainbow_target_kernel<<<(int)B, 128, sm_t, s>>>(v_tg, adv_tg, ws.a_star, bufs.reward, bufs.done, bufs.support,
                                                         pc, A, N, nullptr, ws.proj, fq_v, fq_a);
@@ -1424,6 +1504,7 @@ static int rainbow_loss(const b2rl_net_desc &net, const b2rl_learn_cfg &cfg, con
     rainbow_scalar_kernel<<<1, 256, 0, s>>>(bufs.loss_elem, bufs.weights, cfg.weights_mode, B, (float)cfg.prior_eps,
                                             bufs.loss_scalar, bufs.priorities);
     B2RL_LAUNCH_CHECK();
+    }
     if (bufs.proj_dist)
         B2RL_CUDA(cudaMemcpyAsync(bufs.proj_dist, ws.proj, sizeof(float) * B * N, cudaMemcpyDeviceToDevice, s));
     return B2RL_OK;
