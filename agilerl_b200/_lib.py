@@ -64,6 +64,27 @@ class LearnBufs(Structure):
     ]
 
 
+class DdpgCfg(Structure):
+    _fields_ = [
+        ("batch", c_int64), ("twin", c_int32), ("policy_update", c_int32),
+        ("gamma", c_double), ("tau", c_double), ("noise_clip", c_double), ("policy_noise", c_double),
+        ("lr_actor", c_double), ("lr_critic", c_double), ("beta1", c_double), ("beta2", c_double), ("adam_eps", c_double),
+        ("bc1_actor", c_double), ("bc2_actor", c_double), ("bc1_critic", c_double), ("bc2_critic", c_double),
+        ("noise_seed", c_uint64), ("noise_offset", c_uint64),
+    ]
+
+
+class DdpgBufs(Structure):
+    _fields_ = [
+        ("actor", c_void_p), ("actor_target", c_void_p), ("actor_grads", c_void_p), ("actor_m", c_void_p), ("actor_v", c_void_p),
+        ("critic", c_void_p * 2), ("critic_target", c_void_p * 2), ("critic_grads", c_void_p * 2), ("critic_m", c_void_p * 2),
+        ("critic_v", c_void_p * 2),
+        ("obs", c_void_p), ("next_obs", c_void_p), ("action", c_void_p), ("reward", c_void_p), ("done", c_void_p),
+        ("noise", c_void_p), ("action_low", c_void_p), ("action_high", c_void_p),
+        ("critic_loss", c_void_p), ("actor_loss", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+    ]
+
+
 class StepState(Structure):
     _fields_ = [
         ("beta", c_double), ("size", c_int64), ("sample_offset", c_uint64), ("noise_offset", c_uint64 * 2),
@@ -103,6 +124,10 @@ _SIGS = {
     "b2rl_graph_launch": ([c_void_p, POINTER(StepState), c_void_p], c_int),
     "b2rl_graph_kernel_count": ([c_void_p, POINTER(c_int)], c_int),
     "b2rl_graph_destroy": ([c_void_p], c_int),
+    "b2rl_ddpg_workspace_bytes": ([POINTER(NetDesc), POINTER(NetDesc), c_int64, POINTER(c_size_t)], c_int),
+    "b2rl_ddpg_learn": ([POINTER(NetDesc), POINTER(NetDesc), POINTER(DdpgCfg), POINTER(DdpgBufs), c_void_p], c_int),
+    "b2rl_actor_workspace_bytes": ([POINTER(NetDesc), c_int64, POINTER(c_size_t)], c_int),
+    "b2rl_actor_forward": ([POINTER(NetDesc), c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p], c_int),
     "b2rl_host_priority_pow": ([c_void_p, c_int64, c_double, c_double, c_void_p, POINTER(c_double)], c_int),
     "b2rl_philox_uniforms": ([c_uint64, c_uint64, c_int64, c_void_p, c_void_p], c_int),
     "b2rl_philox_normals": ([c_uint64, c_uint64, c_int64, c_void_p, c_void_p], c_int),

@@ -1,4 +1,5 @@
 from .dqn import DQN
 from .dqn_rainbow import RainbowDQN
+from .td3 import DDPG, TD3
 
-__all__ = ["DQN", "RainbowDQN"]
+__all__ = ["DQN", "RainbowDQN", "DDPG", "TD3"]

@@ -1747,3 +1747,5 @@ int b2rl_encoder_layer_forward(const b2rl_net_desc *net_host, int layer, const f
 }
 
 }  // extern "C"
+
+#include "ddpg.cuh"

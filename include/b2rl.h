@@ -330,6 +330,45 @@ int b2rl_rainbow_learn(const b2rl_net_desc *net_host, const b2rl_learn_cfg *cfg_
                        const b2rl_learn_bufs *bufs_host, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * DDPG / TD3 learn() — agilerl/algorithms/ddpg.py:422-500, td3.py:459-551 (BASELINE configs[2]).
+ * Networks are b2rl_net_desc chains: actor = enc[] (MLP encoder) -> val[] (head, Tanh output, n_actions = action dim);
+ * critic = enc[] -> cat(latent, action) -> val[] (val[0].in_c = latent + action dim, output 1)
+ * (networks/actors.py:78-210, networks/q_networks.py:302-443).  One flat parameter buffer per network.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct b2rl_ddpg_cfg {
+    int64_t batch;
+    int32_t twin;                       /* 1: TD3 (two critics, min target, summed MSE), 0: DDPG */
+    int32_t policy_update;              /* this call also steps the actor and soft-updates every target
+                                           (learn_counter % policy_freq == 0, td3.py:520) */
+    double gamma, tau, noise_clip, policy_noise;
+    double lr_actor, lr_critic, beta1, beta2, adam_eps;
+    double bc1_actor, bc2_actor, bc1_critic, bc2_critic;   /* 1 - beta^step of each optimiser */
+    uint64_t noise_seed, noise_offset;  /* Philox stream of the target-policy noise when bufs.noise == NULL */
+} b2rl_ddpg_cfg;
+
+typedef struct b2rl_ddpg_bufs {
+    float *actor, *actor_target, *actor_grads, *actor_m, *actor_v;
+    float *critic[2], *critic_target[2], *critic_grads[2], *critic_m[2], *critic_v[2];
+    const float *obs, *next_obs;        /* [B, obs_dim] float32 */
+    float *action;                      /* [B, act_dim] IN/OUT: overwritten with the raw target-policy noise
+                                           (actions.data.normal_(0, policy_noise), td3.py:497 — the reference's quirk) */
+    const float *reward, *done;         /* [B] */
+    const float *noise;                 /* nullable [B, act_dim]: injected N(0, policy_noise) draws (parity tests) */
+    const float *action_low, *action_high;   /* [act_dim] */
+    float *critic_loss, *actor_loss;    /* out: scalars (actor_loss written on policy steps only) */
+    void *workspace; size_t workspace_bytes;
+} b2rl_ddpg_bufs;
+
+int b2rl_ddpg_workspace_bytes(const b2rl_net_desc *actor_host, const b2rl_net_desc *critic_host, int64_t batch,
+                              size_t *out_host);
+int b2rl_ddpg_learn(const b2rl_net_desc *actor_host, const b2rl_net_desc *critic_host, const b2rl_ddpg_cfg *cfg_host,
+                    const b2rl_ddpg_bufs *bufs_host, void *stream);
+/* DeterministicActor.forward (actors.py:188-210): out [rows, act_dim]. */
+int b2rl_actor_workspace_bytes(const b2rl_net_desc *actor_host, int64_t rows, size_t *out_host);
+int b2rl_actor_forward(const b2rl_net_desc *actor_host, const float *params, const float *obs, int64_t rows, float *out,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * CUDA graphs: the ~40 dependent launches of a gradient step captured once and replayed per step.
  * b2rl_graph_begin puts `stream` into capture (relaxed mode; library-owned side streams fork from and join back
  * into it); every b2rl_* call made on it until b2rl_graph_end is recorded instead of executed.  If the captured
