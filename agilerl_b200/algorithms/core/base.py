@@ -108,6 +108,7 @@ class EvolvableAlgorithm:
         self._copy_networks_to(clone)
         skip = set(self._ctor_params()) | set(self._evolvable_attrs()) | {"registry", "optimizer", "engine", "_dev",
                                                                           "_index", "support"}
+        skip |= set(getattr(self, "_clone_skip", ()))       # per-class device state rebuilt by _copy_networks_to
         for k, v in self.__dict__.items():
             if k in skip or k.startswith("_engine"):
                 continue

@@ -61,6 +61,8 @@ class _AdamState:
 class _DeterministicPG(RLAlgorithm):
     _twin = False
     _name = "DDPG"
+    _clone_skip = ("_ws", "_keep", "_low_dev", "_high_dev", "actor_optimizer", "critic_optimizer", "critic_1_optimizer",
+                   "critic_2_optimizer", "action_low", "action_high")
 
     def __init__(self, observation_space, action_space, O_U_noise: bool = True, vect_noise_dim: int = 1,
                  expl_noise: float = 0.1, mean_noise: float = 0.0, theta: float = 0.15, dt: float = 1e-2, index: int = 0,
@@ -238,6 +240,12 @@ class _DeterministicPG(RLAlgorithm):
     def learn(self, experiences, noise_clip: float = 0.5, policy_noise: float = 0.2, noise: torch.Tensor | None = None):
         """td3.py:462-551 / ddpg.py:422-494.  ``noise`` (optional, [B, act_dim]) injects the N(0, policy_noise) draws
         instead of the device Philox stream (parity tests).  Returns ``(actor_loss | None, critic_loss)``."""
+        out, policy_update = self.learn_device(experiences, noise_clip, policy_noise, noise)
+        host = out.tolist()                                   # the reference returns Python floats (.item())
+        return (host[1] if policy_update else None), host[0]
+
+    def learn_device(self, experiences, noise_clip: float = 0.5, policy_noise: float = 0.2, noise: torch.Tensor | None = None):
+        """``learn`` without the host read-back: returns (device tensor [critic_loss, actor_loss], policy_update)."""
         lib = _lib.load()
         f32 = lambda t: t if (t.dtype == torch.float32 and t.device == self._dev and t.is_contiguous()) else \
             t.to(self._dev, dtype=torch.float32).contiguous()
@@ -290,8 +298,7 @@ class _DeterministicPG(RLAlgorithm):
         _lib.check(lib.b2rl_ddpg_learn(ctypes.byref(self.actor.layout.desc), ctypes.byref(critics[0].layout.desc),
                                        ctypes.byref(cfg), ctypes.byref(bufs), _lib.stream_ptr(self._dev)))
         self._keep = (obs, next_obs, reward, done, nz, out)
-        host = out.tolist()                                   # the reference returns Python floats (.item())
-        return (host[1] if policy_update else None), host[0]
+        return out, policy_update
 
     def soft_update(self, net, target) -> None:
         """td3.py:553-565."""

@@ -284,6 +284,20 @@ class ReplayBuffer:
             samples["idxs"] = indices.to(self._dev)
         return samples
 
+    def sample_device(self, batch_size: int, return_idx: bool = False) -> TensorDict:
+        """``sample`` for the HBM-resident loop: the B distinct uniform indices are drawn on device (Philox,
+        b2rl_sample_uniform_distinct) instead of ``torch.randperm(size)`` on the host — no host round trip, not the
+        reference's RNG stream."""
+        idx = torch.empty(batch_size, dtype=torch.int64, device=self._dev)
+        off = getattr(self, "_uniform_offset", 0)
+        _lib.check(self._lib.b2rl_sample_uniform_distinct(getattr(self, "_uniform_seed", 0x5A11), off, self._size, batch_size,
+                                                          idx.data_ptr(), _lib.stream_ptr(self._dev)))
+        self._uniform_offset = off + 64 * batch_size
+        samples = self._gather(idx)
+        if return_idx:
+            samples["idxs"] = idx
+        return samples
+
     def clear(self) -> None:
         """:133-138."""
         self._size = 0

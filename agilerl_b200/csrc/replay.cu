@@ -155,6 +155,52 @@ static int dispatch_width(const void *a, const void *b, int64_t row_bytes, F &&f
 
 using namespace b2rl;
 
+namespace b2rl {
+// B DISTINCT indices uniform over [0, N) — what randperm(N)[:B] yields as a set (ReplayBuffer.sample,
+// replay_buffer.py:114-131, quirk Q12) — without generating the permutation: every slot draws from its own Philox
+// counter stream and redraws while its value is already owned by another slot.  Ownership is decided by
+// (round, slot) priority through atomicMin, so the result does not depend on thread timing.
+__global__ void sample_distinct_kernel(uint64_t seed, uint64_t offset, int64_t N, int B, int tbits, int64_t *__restrict__ out) {
+    extern __shared__ unsigned long long tab[];          // [T] keys (index + 1; 0 = empty)
+    const int T = 1 << tbits;
+    unsigned int *owner = reinterpret_cast<unsigned int *>(tab + T);   // [T] (round << 16 | slot) of the winning claim
+    for (int i = threadIdx.x; i < T; i += blockDim.x) { tab[i] = 0ull; owner[i] = 0xFFFFFFFFu; }
+    __syncthreads();
+    const int i = threadIdx.x;
+    bool done = i >= B;
+    __shared__ int pending;
+    for (unsigned int round = 0; round < 64; ++round) {
+        if (threadIdx.x == 0) pending = 0;
+        __syncthreads();
+        int slot = -1;
+        long long idx = -1;
+        if (!done) {
+            uint32_t r[4];
+            philox4x32_10(seed, offset + (uint64_t)i + (uint64_t)round * (uint64_t)B, 0x554E4946ull /* "UNIF" */, r);
+            const unsigned long long u = ((unsigned long long)r[0] << 32) | r[1];
+            idx = (long long)__umul64hi(u, (unsigned long long)N);           // floor(u * N / 2^64)
+            const unsigned long long key = (unsigned long long)idx + 1ull;
+            unsigned int h = (unsigned int)((key * 0x9E3779B97F4A7C15ull) >> (64 - tbits));
+            while (true) {
+                const unsigned long long prev = atomicCAS(&tab[h], 0ull, key);
+                if (prev == 0ull || prev == key) break;
+                h = (h + 1) & (T - 1);
+            }
+            slot = (int)h;
+            atomicMin(&owner[slot], (round << 16) | (unsigned int)i);
+        }
+        __syncthreads();
+        if (!done) {
+            if (owner[slot] == ((round << 16) | (unsigned int)i)) { out[i] = idx; done = true; }
+            else atomicAdd(&pending, 1);
+        }
+        __syncthreads();
+        if (pending == 0) break;
+        __syncthreads();
+    }
+}
+}  // namespace b2rl
+
 extern "C" {
 
 int b2rl_ring_write(void *storage, const void *src, int64_t row_bytes, int64_t start, int64_t n,
@@ -262,6 +308,18 @@ int b2rl_select_copy(void *dst, const void *const *srcs_host, int n_srcs, const 
     if (blocks < 1) blocks = 1;
     if (blocks > sm_count() * 4) blocks = sm_count() * 4;
     select_copy_kernel<<<blocks, 256, 0, as_stream(stream)>>>(static_cast<uint8_t *>(dst), sp, which, bytes);
+    B2RL_LAUNCH_CHECK();
+    return B2RL_OK;
+}
+
+int b2rl_sample_uniform_distinct(uint64_t seed, uint64_t offset, int64_t N, int64_t B, int64_t *out_idx, void *stream) {
+    B2RL_CHECK_ARG(out_idx && N >= 1 && B >= 1 && B <= N && B <= 1024, "need 1 <= B <= min(N, 1024)");
+    int tbits = 4;
+    while ((1 << tbits) < 4 * B) ++tbits;
+    const size_t smem = (size_t)(1 << tbits) * (sizeof(unsigned long long) + sizeof(unsigned int));
+    int threads = 32;
+    while (threads < B) threads <<= 1;
+    b2rl::sample_distinct_kernel<<<1, threads, smem, b2rl::as_stream(stream)>>>(seed, offset, N, (int)B, tbits, out_idx);
     B2RL_LAUNCH_CHECK();
     return B2RL_OK;
 }

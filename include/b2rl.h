@@ -136,6 +136,11 @@ int b2rl_ring_write_multi(int n_fields, void *const *storage, const void *const 
 int b2rl_gather_rows_multi(int n_fields, void *const *dst, const void *const *storage, const int64_t *row_bytes,
                            const int64_t *idx, int64_t n, void *stream);
 
+/* ReplayBuffer.sample's index draw on device (replay_buffer.py:114-131, quirk Q12: uniform WITHOUT replacement):
+ * B distinct indices uniform over [0, N) from Philox(seed, offset), B <= 1024, deterministic.  The API path keeps
+ * torch.randperm on the host (same RNG stream as the reference); this serves the HBM-resident loop. */
+int b2rl_sample_uniform_distinct(uint64_t seed, uint64_t offset, int64_t N, int64_t B, int64_t *out_idx, void *stream);
+
 /* HOST helper (no device work): PrioritizedReplayBuffer.update_priorities' per-priority arithmetic
  * (replay_buffer.py:411-428, :311-329) — q = max((double)p, floor); out[i] = pow(q, alpha) with the C library's pow,
  * which is what CPython's `priority ** alpha` evaluates, so the leaves are bit-identical to the reference's; *max_host

@@ -128,6 +128,10 @@ def test_td3_api_surface_clone_and_actions():
     for k, v in agent.critic_1.state_dict().items():
         assert torch.equal(v, c.critic_1.state_dict()[k])
     assert torch.equal(agent.critic_1_optimizer.exp_avg, c.critic_1_optimizer.exp_avg) and c.critic_2_optimizer.step == 2
+    same = agent.clone()                                                         # same index: same Philox stream and position
     ea, ec = exp["action"].clone(), exp["action"].clone()
-    la, lc = agent.learn(dict(exp, action=ea)), c.learn(dict(exp, action=ec))
-    assert la == lc and torch.equal(ea, ec)                                      # same Philox stream position, same result
+    la, lc = agent.learn(dict(exp, action=ea)), same.learn(dict(exp, action=ec))
+    assert la == lc and torch.equal(ea, ec) and not torch.equal(ea, exp["action"])
+    e7 = exp["action"].clone()
+    c.learn(dict(exp, action=e7))
+    assert not torch.equal(e7, ea)                                               # another index draws another noise stream

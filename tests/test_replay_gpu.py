@@ -146,3 +146,30 @@ def test_full_size_gather_round_trip():
     out = rb._gather(idx)
     assert torch.equal(out["obs"].cpu(), frames[idx])
     assert torch.equal(out["reward"].cpu(), rew[idx].unsqueeze(1))
+
+
+def test_device_uniform_sampling_is_distinct_uniform_and_deterministic():
+    """b2rl_sample_uniform_distinct (the HBM-resident counterpart of randperm(size)[:B], replay_buffer.py:125): B
+    distinct in-range indices, identical for identical (seed, offset), different across offsets, and uniform over
+    the range (chi-square over 16 bins of 200 x 512 draws)."""
+    import ctypes
+    from agilerl_b200 import _lib
+    lib = _lib.load()
+    s = _lib.stream_ptr(torch.device("cuda:0"))
+
+    def draw(N, B, off):
+        out = torch.empty(B, dtype=torch.int64, device="cuda")
+        _lib.check(lib.b2rl_sample_uniform_distinct(77, off, N, B, out.data_ptr(), s))
+        return out.cpu().numpy()
+    for N, B in [(1_000_000, 512), (600, 512), (1024, 1024), (7, 7), (5, 1)]:
+        a = draw(N, B, 0)
+        assert len(set(a.tolist())) == B and a.min() >= 0 and a.max() < N
+        assert np.array_equal(a, draw(N, B, 0))
+        if N > B:
+            assert not np.array_equal(a, draw(N, B, 64 * B))
+    counts = np.zeros(16)
+    for k in range(200):
+        counts += np.bincount(draw(1_000_000, 512, 64 * 512 * k) * 16 // 1_000_000, minlength=16)
+    exp = 200 * 512 / 16
+    chi2 = float(((counts - exp) ** 2 / exp).sum())
+    assert chi2 < 45.0, chi2            # 15 degrees of freedom: P(chi2 > 45) < 1e-4
