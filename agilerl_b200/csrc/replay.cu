@@ -315,7 +315,7 @@ int b2rl_select_copy(void *dst, const void *const *srcs_host, int n_srcs, const 
 int b2rl_sample_uniform_distinct(uint64_t seed, uint64_t offset, int64_t N, int64_t B, int64_t *out_idx, void *stream) {
     B2RL_CHECK_ARG(out_idx && N >= 1 && B >= 1 && B <= N && B <= 1024, "need 1 <= B <= min(N, 1024)");
     int tbits = 4;
-    while ((1 << tbits) < 4 * B) ++tbits;
+    while ((1 << tbits) < 2 * B) ++tbits;       // load factor <= 0.5; 24 KB of shared memory at B = 1024
     const size_t smem = (size_t)(1 << tbits) * (sizeof(unsigned long long) + sizeof(unsigned int));
     int threads = 32;
     while (threads < B) threads <<= 1;

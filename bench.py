@@ -420,39 +420,44 @@ def config_for(world: int) -> dict:
 
 
 def tournament_generation(agents, world, rank, device):
-    """One generation of TournamentSelection.select on the sharded population (hpo/tournament.py:41-119 with
-    the checkpoint transport of utils/utils.py:756-782 replaced by NCCL): one all-gather of (fitness, index),
-    identical plan on every rank (asserted), winners moved point to point.  Timed with CUDA events, max over
-    ranks; OUTSIDE the timed learn region."""
+    """Two generations of TournamentSelection.select on the sharded population (hpo/tournament.py:41-119 with the
+    checkpoint transport of utils/utils.py:756-782 replaced by NCCL): per generation one all-gather of (fitness,
+    index), identical plan on every rank (asserted), winners moved point to point.  The first generation pays
+    NCCL's lazy point-to-point channel set-up; the second is the steady state.  Timed with CUDA events + wall
+    clock, max over ranks; OUTSIDE the timed learn region."""
     import torch.distributed as dist
     from agilerl_b200.hpo import TournamentSelection
     n_local = len(agents)
-    for a in agents:
-        a.synchronize()
-        a.fitness = [float((a.index * 37) % 11)]          # synthetic evaluation scores, distinct per agent
     ts = TournamentSelection(2, True, POP, 1, seed=1)
-    dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record()
-    elite, new_pop = ts.select(agents)
-    e1.record()
-    torch.cuda.synchronize()
-    wall = (time.perf_counter() - t0) * 1e3
-    elite_pos, slots = ts.last_plan
-    plans = [None] * world
-    dist.all_gather_object(plans, [elite_pos, [list(x) for x in slots]])
-    assert all(p == plans[0] for p in plans), "ranks derived different tournament plans"
-    moved = sum(1 for slot, (parent, _) in enumerate(slots) if slot // n_local != parent // n_local)
-    eng = agents[0].engine
-    per_agent = 4 * (2 * eng.actor.params.numel() + 2 * eng.actor.eps.numel() + 2 * eng.exp_avg.numel())
-    t = torch.tensor([e0.elapsed_time(e1), wall], device=device)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    assert len(new_pop) == n_local and all(a is not None for a in new_pop)
-    return {"ms_device": float(t[0].item()), "ms_wall": float(t[1].item()), "bytes_allgather": world * n_local * 16,
-            "bytes_p2p": moved * per_agent, "moved_agents": moved, "plans_identical": True,
-            "elite_index": int(slots[0][1])}, new_pop
+    gens = []
+    for gen in range(2):
+        for a in agents:
+            a.synchronize()
+            a.fitness = [float(((a.index + 3 * gen) * 37) % 11)]      # synthetic evaluation scores
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        elite, agents = ts.select(agents)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        elite_pos, slots = ts.last_plan
+        plans = [None] * world
+        dist.all_gather_object(plans, [elite_pos, [list(x) for x in slots]])
+        assert all(p == plans[0] for p in plans), "ranks derived different tournament plans"
+        assert len(agents) == n_local and all(a is not None for a in agents)
+        moved = sum(1 for slot, (parent, _) in enumerate(slots) if slot // n_local != parent // n_local)
+        eng = agents[0].engine
+        per_agent = 4 * (2 * eng.actor.params.numel() + 2 * eng.actor.eps.numel() + 2 * eng.exp_avg.numel())
+        t = torch.tensor([e0.elapsed_time(e1), wall], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gens.append({"ms_device": float(t[0].item()), "ms_wall": float(t[1].item()), "moved_agents": moved,
+                     "bytes_p2p": moved * per_agent, "elite_index": int(slots[0][1])})
+    out = dict(gens[1], bytes_allgather=world * n_local * 16, plans_identical=True, generations=gens,
+               note="ms of generation 2 (steady state); generation 1 includes NCCL's lazy p2p channel set-up")
+    return out, agents
 
 
 def ppo_workload(args):
