@@ -724,9 +724,16 @@ __device__ __forceinline__ float *rainbow_target_row(float *sm, const float *__r
         pr[n] = 0.f;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int n = 0; n < N; ++n) pr[Li[n]] = __fadd_rn(pr[Li[n]], __fmul_rn(p[n], wl[n]));
-        for (int n = 0; n < N; ++n) pr[Ui[n]] = __fadd_rn(pr[Ui[n]], __fmul_rn(p[n], wu[n]));
+    // index_add_ order kept per destination bin, bins in parallel: bin m receives its l-contributions in ascending n,
+    // then its u-contributions in ascending n — the same fp32 additions in the same order as the reference's two
+    // sequential index_add_ calls (dqn_rainbow.py:350-360), without one thread walking all 2N updates
+    for (int m = threadIdx.x; m < N; m += blockDim.x) {
+        float acc = 0.f;
+        for (int n = 0; n < N; ++n)
+            if (Li[n] == m) acc = __fadd_rn(acc, __fmul_rn(p[n], wl[n]));
+        for (int n = 0; n < N; ++n)
+            if (Ui[n] == m) acc = __fadd_rn(acc, __fmul_rn(p[n], wu[n]));
+        pr[m] = acc;
     }
     __syncthreads();
     for (int n = threadIdx.x; n < N; n += blockDim.x) proj[row * N + n] = pr[n];

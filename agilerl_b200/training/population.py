@@ -49,3 +49,41 @@ def population_learn(pop, memory, n_step_memory, overlap: bool = True, join: boo
         for agent in pop:
             agent.synchronize()
     return losses
+
+
+def share_transitions(transition, device=None, group=None):
+    """The reference trains the WHOLE population against one replay buffer (train_off_policy.py:327-345,
+    docs/off_policy/index.rst:103): every agent's environment steps land in it.  With the population sharded one
+    process per GPU each rank only sees its own agents' steps, so before ingest the ranks exchange them: every
+    leaf of the transition is packed into one byte block, ONE all-gather moves the blocks (NCCL on the device,
+    gloo on the host), and the result is the transition of all ranks concatenated along the environment
+    dimension in rank order — identical on every rank, so every rank's buffer holds the population's experience
+    exactly as a single process stepping ``world_size * num_envs`` environments would.  Without an initialised
+    process group (or world size 1) the transition is returned unchanged."""
+    import torch.distributed as dist
+    from ..compat import TensorDict
+    from ..components.replay_buffer import _leaf_items, _unflatten
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return transition
+    world = dist.get_world_size(group)
+    use_cuda = dist.get_backend(group) != "gloo"
+    dev = torch.device(device) if (device is not None and use_cuda) else (
+        torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu"))
+    leaves = [(p, v if isinstance(v, torch.Tensor) else torch.as_tensor(v)) for p, v in _leaf_items(transition)]
+    plan, off = [], 0
+    for path, v in leaves:
+        nb = v.numel() * v.element_size()
+        plan.append((path, off, nb, v.dtype, tuple(v.shape)))
+        off = (off + nb + 255) & ~255
+    total = max(off, 256)
+    block = torch.zeros(total, dtype=torch.uint8, device=dev)
+    for (path, o, nb, dt, shape), (_, v) in zip(plan, leaves):
+        block[o:o + nb].view(dt).view(shape).copy_(v.contiguous(), non_blocking=True)
+    gathered = torch.empty(world * total, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(gathered, block, group=group)          # the single exchange of an environment step
+    out = {}
+    for path, o, nb, dt, shape in plan:
+        parts = [gathered[r * total + o:r * total + o + nb].view(dt).view(shape) for r in range(world)]
+        out[path] = torch.cat(parts, dim=0)
+    n = next(iter(out.values())).shape[0]
+    return _unflatten(out, (n,))

@@ -4,7 +4,9 @@ driver; it cannot be imported in the build image — gymnasium / accelerate / te
 absent — so this module restates its loop for the algorithms of this path, minus W&B / accelerate /
 checkpoint plumbing).  One addition: ``fused=True`` routes PER + n-step learning through the
 HBM-resident fused step (``RainbowDQN.learn_from_buffers``) instead of sample -> learn ->
-update_priorities through host-visible tensors.
+update_priorities through host-visible tensors; ``share_experience=True`` (population sharded one process per GPU)
+all-gathers every environment step across the ranks before ingest, so each rank's buffer holds the whole
+population's experience like the reference's single shared buffer (``training.population.share_transitions``).
 """
 from __future__ import annotations
 
@@ -17,6 +19,7 @@ from ..algorithms import DQN, RainbowDQN
 from ..algorithms.dqn_rainbow import obs_channels_to_first
 from ..components import MultiStepReplayBuffer, PrioritizedReplayBuffer, ReplayBuffer, Sampler, Transition
 from ..utils.utils import tournament_selection_and_mutation
+from .population import share_transitions
 
 
 def train_off_policy(env, env_name: str, algo: str, pop: list, memory: ReplayBuffer, INIT_HP: dict | None = None,
@@ -28,7 +31,7 @@ def train_off_policy(env, env_name: str, algo: str, pop: list, memory: ReplayBuf
                      checkpoint: int | None = None, checkpoint_path: str | None = None, overwrite_checkpoints: bool = False,
                      save_elite: bool = False, elite_path: str | None = None, wb: bool = False, verbose: bool = True,
                      accelerator=None, wandb_api_key: str | None = None, wandb_kwargs: dict | None = None,
-                     fused: bool = False):
+                     fused: bool = False, share_experience: bool = False):
     assert isinstance(algo, str), "'algo' must be the name of the algorithm as a string."
     assert isinstance(max_steps, int), "Number of steps must be an integer."
     assert isinstance(evo_steps, int), "Evolution frequency must be an integer."
@@ -107,6 +110,8 @@ def train_off_policy(env, env_name: str, algo: str, pop: list, memory: ReplayBuf
                     transition = Transition(obs=np.asarray(obs)[None], action=np.asarray([action]),
                                             reward=np.asarray([reward]), next_obs=np.asarray(next_obs)[None],
                                             done=done, batch_size=[1]).to_tensordict()
+                if share_experience:                                    # sharded population: every rank ingests every rank's steps
+                    transition = share_transitions(transition, getattr(memory, "_dev", None))
                 if n_step_memory is not None:
                     one_step = n_step_memory.add(transition)
                     if one_step is not None:

@@ -92,3 +92,37 @@ def test_plan_is_rank_invariant_and_ranks_by_mean_fitness():
     # winners are never the worst-ranked of their draws: with tournament_size 3 the worst agent
     # (position 1) can only win if drawn three times
     assert sum(1 for p, _ in a[1] if p == 1) <= 1
+
+
+def _share_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from agilerl_b200.compat import TensorDict
+    from agilerl_b200.training.population import share_transitions
+    E = 3
+    g = torch.Generator().manual_seed(100 + rank)
+    td = TensorDict({"obs": torch.randint(0, 256, (E, 4, 6, 6), dtype=torch.uint8, generator=g),
+                     "action": torch.randint(0, 5, (E,), generator=g).float(), "reward": torch.randn(E, generator=g),
+                     "next_obs": torch.randint(0, 256, (E, 4, 6, 6), dtype=torch.uint8, generator=g),
+                     "done": (torch.rand(E, generator=g) < 0.5).float()}, batch_size=[E])
+    allr = share_transitions(td)
+    out[rank] = {k: v.clone() for k, v in allr.items()} | {"_own": {k: v.clone() for k, v in td.items()},
+                                                         "_bs": tuple(allr.batch_size)}
+    dist.destroy_process_group()
+
+
+def test_cross_rank_experience_sharing_world2_gloo():
+    """share_transitions: one all-gather per environment step; every rank ends up with the transitions of ALL ranks
+    concatenated along the environment dimension in rank order (the reference's single shared buffer,
+    train_off_policy.py:327-345), dtypes and shapes preserved."""
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_share_worker, args=(world, port, out), nprocs=world, join=True)
+    r0, r1 = out[0], out[1]
+    assert r0["_bs"] == (6,) and r1["_bs"] == (6,)
+    for k in ("obs", "action", "reward", "next_obs", "done"):
+        want = torch.cat([r0["_own"][k], r1["_own"][k]], dim=0)
+        assert r0[k].dtype == want.dtype and torch.equal(r0[k], want) and torch.equal(r1[k], want), k
