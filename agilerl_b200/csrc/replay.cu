@@ -169,7 +169,7 @@ __global__ void sample_distinct_kernel(uint64_t seed, uint64_t offset, int64_t N
     const int i = threadIdx.x;
     bool done = i >= B;
     __shared__ int pending;
-    for (unsigned int round = 0; round < 64; ++round) {
+    for (unsigned int round = 0; round < 4096; ++round) {
         if (threadIdx.x == 0) pending = 0;
         __syncthreads();
         int slot = -1;
@@ -199,6 +199,38 @@ __global__ void sample_distinct_kernel(uint64_t seed, uint64_t offset, int64_t N
         __syncthreads();
     }
 }
+// Dense case (B > N / 2, hence N < 2048): a full random permutation — every index gets a 64-bit Philox key, a bitonic
+// sort orders (key, index) pairs in shared memory, the first B indices are the sample.
+__global__ void sample_shuffle_kernel(uint64_t seed, uint64_t offset, int N, int B, int P, int64_t *__restrict__ out) {
+    extern __shared__ unsigned long long keys[];         // [P] keys, then [P] payloads
+    unsigned long long *val = keys + P;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        unsigned long long k = ~0ull;
+        if (i < N) {
+            uint32_t r[4];
+            philox4x32_10(seed, offset + (uint64_t)i, 0x53484646ull /* "SHFF" */, r);
+            k = (((unsigned long long)r[0] << 32) | r[1]) >> 1;         // < 2^63: padding keys sort last
+        }
+        keys[i] = k; val[i] = (unsigned long long)i;
+    }
+    __syncthreads();
+    for (int size = 2; size <= P; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < P; i += blockDim.x) {
+                const int j = i ^ stride;
+                if (j > i) {
+                    const bool up = (i & size) == 0;
+                    const unsigned long long ki = keys[i], kj = keys[j];
+                    // ties broken by index so the order is total and deterministic
+                    const bool gt = ki > kj || (ki == kj && val[i] > val[j]);
+                    if (gt == up) { keys[i] = kj; keys[j] = ki; const unsigned long long t = val[i]; val[i] = val[j]; val[j] = t; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < B; i += blockDim.x) out[i] = (int64_t)val[i];
+}
+
 }  // namespace b2rl
 
 extern "C" {
@@ -314,6 +346,14 @@ int b2rl_select_copy(void *dst, const void *const *srcs_host, int n_srcs, const 
 
 int b2rl_sample_uniform_distinct(uint64_t seed, uint64_t offset, int64_t N, int64_t B, int64_t *out_idx, void *stream) {
     B2RL_CHECK_ARG(out_idx && N >= 1 && B >= 1 && B <= N && B <= 1024, "need 1 <= B <= min(N, 1024)");
+    if (2 * B > N) {      // dense draw (N <= 2047): rejection would crawl; sort all N indices by random keys instead
+        int P = 1;
+        while (P < N) P <<= 1;
+        b2rl::sample_shuffle_kernel<<<1, 1024, (size_t)P * 2 * sizeof(unsigned long long), b2rl::as_stream(stream)>>>(
+            seed, offset, (int)N, (int)B, P, out_idx);
+        B2RL_LAUNCH_CHECK();
+        return B2RL_OK;
+    }
     int tbits = 4;
     while ((1 << tbits) < 2 * B) ++tbits;       // load factor <= 0.5; 24 KB of shared memory at B = 1024
     const size_t smem = (size_t)(1 << tbits) * (sizeof(unsigned long long) + sizeof(unsigned int));
