@@ -136,12 +136,12 @@ class Mutations:
         return individual
 
     def _permutate_activation(self, network):
-        """mutation.py _permutate_activation: pick a different activation from the selection."""
+        """mutation.py:710-731: a different activation from the selection (one draw from ``self.rng``)."""
+        possible = list(self.activation_selection)
         current = network.activation
-        choices = [a for a in self.activation_selection if a != current]
-        if not choices:
-            return network
-        network.change_activation(str(self.rng.choice(choices)), output=False)
+        if len(possible) > 1 and current in possible:
+            possible.remove(current)
+        network.change_activation(str(self.rng.choice(possible, size=1)[0]), output=False)
         return network
 
     def activation_mutation(self, individual):
@@ -173,21 +173,26 @@ class Mutations:
         return individual
 
     def _gaussian_parameter_mutation(self, network):
-        """mutation.py:733-827, applied in place to the 2-D weight views of the flat buffer."""
+        """mutation.py:733-827, bit for bit.  The reference walks ``state_dict()`` — parameters AND the 2-D NoisyLinear
+        epsilon buffers, in module order — picks keys / rows / columns / branch with ``self.rng`` and draws the noise from
+        torch's global CPU generator; duplicate (row, col) pairs resolve to the last writer like a CPU ``index_put_``.
+        Mutations are off the hot path: each chosen matrix is mutated on a host copy with exactly those torch calls and
+        written back into the flat HBM buffer."""
         mut_strength, frac = self.mutation_sd, 0.1
         super_strength, super_prob = 10, 0.05
         reset_prob, mag_limit = super_prob + 0.05, 1000000
-        views = {k: v for k, v in network.named_parameters()}
-        keys = [k for k, v in views.items() if "norm" not in k and "lstm" not in k and v.ndim == 2]
+        entries = network.layout.entries
+        keys = [k for k, e in entries.items() if "lstm" not in k and "norm" not in k and len(e.shape) == 2]
         how_many = int(self.rng.integers(1, len(keys) + 1))
         for key in self.rng.choice(keys, how_many, replace=False):
-            W = views[str(key)]
+            view = network.buffers.view(str(key))
+            W = view.cpu()
             n_mut = int(np.ceil(frac * W.shape[0] * W.shape[1]))
             if n_mut < 1:
                 continue
-            rows = torch.tensor(self.rng.integers(0, W.shape[0], size=n_mut), dtype=torch.long, device=W.device)
-            cols = torch.tensor(self.rng.integers(0, W.shape[1], size=n_mut), dtype=torch.long, device=W.device)
-            r = torch.tensor(self.rng.uniform(0, 1, size=n_mut), dtype=W.dtype, device=W.device)
+            rows = torch.tensor(self.rng.integers(0, W.shape[0], size=n_mut), dtype=torch.long)
+            cols = torch.tensor(self.rng.integers(0, W.shape[1], size=n_mut), dtype=torch.long)
+            r = torch.tensor(self.rng.uniform(0, 1, size=n_mut), dtype=W.dtype)
             cur = W[rows, cols]
             new = cur.clone()
             m_super, m_reset = r < super_prob, (r >= super_prob) & (r < reset_prob)
@@ -196,10 +201,11 @@ class Mutations:
                 std = (super_strength * cur[m_super]).abs()
                 new[m_super] = cur[m_super] + torch.normal(mean=torch.zeros_like(std), std=std)
             if m_reset.sum() > 0:
-                k = int(m_reset.sum())
-                new[m_reset] = torch.normal(mean=torch.zeros(k, device=W.device), std=torch.ones(k, device=W.device))
+                k = m_reset.sum()
+                new[m_reset] = torch.normal(mean=torch.zeros(k), std=torch.ones(k))
             if m_norm.sum() > 0:
                 std = (mut_strength * cur[m_norm]).abs()
                 new[m_norm] = cur[m_norm] + torch.normal(mean=torch.zeros_like(std), std=std)
             W[rows, cols] = new.clamp(min=-mag_limit, max=mag_limit)
+            view.copy_(W)
         return network

@@ -446,8 +446,84 @@ def gen_gae():
     print("  gae: oracle == reference (GAE and Monte-Carlo)")
 
 
+def gen_mutations():
+    """Mutations (agilerl/hpo/mutation.py) on the UNMODIFIED reference: everything its seeded generators decide —
+    which mutation each member of a population gets (``self.rng.choice``, :335-339), what
+    ``_gaussian_parameter_mutation`` does to a network's state_dict (:733-827: numpy Generator for keys / rows /
+    columns / branch, torch's global generator for the noise), the ``rl_hyperparam_mutation`` sequence (:413-452 ->
+    registry.py:135-186, 234-241: torch.randperm + torch.rand) and the activation picked by
+    ``_permutate_activation``.  (Architecture mutations draw from each module's own unseeded generator in the
+    reference — only the METHOD choice, made by ``Mutations.rng``, is reproducible and recorded.)"""
+    from agilerl.algorithms.core.registry import HyperparameterConfig, RLParameter
+    from agilerl.hpo.mutation import Mutations
+    out = {}
+    obs_space, act_space = spaces.Box(0, 255, (3, 20, 20), np.uint8), spaces.Discrete(4)
+    net_config = {"encoder_config": {"channel_size": [8, 16], "kernel_size": [4, 3], "stride_size": [2, 1]},
+                  "head_config": {"hidden_size": [32]}, "latent_dim": 16}
+    # (a) mutation choice per population member
+    for c, (probs, seed) in enumerate([((0.2, 0.2, 0.2, 0.2, 0.2), 42), ((0.4, 0.0, 0.3, 0.0, 0.3), 7), ((0, 1, 1, 1, 1), 3)]):
+        m = Mutations(no_mutation=probs[0], architecture=probs[1], new_layer_prob=0.5, parameters=probs[2],
+                      activation=probs[3], rl_hp=probs[4], rand_seed=seed)
+        names = [f.__name__ for f in m.rng.choice(m.mut_options, 12, p=m.mut_proba)]
+        pre = [f.__name__ for f in m.rng.choice(m.pretraining_mut_options, 12, p=m.pretraining_mut_proba)]
+        out[f"choice{c}_probs"], out[f"choice{c}_seed"] = np.array(probs, np.float64), seed
+        out[f"choice{c}_names"], out[f"choice{c}_pre"] = np.array(names), np.array(pre)
+    # (b) Gaussian parameter mutation of a RainbowQNetwork state_dict
+    for c, seed in enumerate((11, 12)):
+        torch.manual_seed(100 + seed)
+        agent = RainbowDQN(obs_space, act_space, net_config=dict(net_config), batch_size=8, v_min=-10.0, v_max=10.0)
+        m = Mutations(0, 0, 0.5, 1, 0, 0, mutation_sd=0.1, rand_seed=seed)
+        before = sd_np(agent.actor.state_dict())
+        torch.manual_seed(500 + seed)
+        m._gaussian_parameter_mutation(agent.actor)
+        after = sd_np(agent.actor.state_dict())
+        out[f"gauss{c}_seed"] = seed
+        for k, v in before.items():
+            out[f"gauss{c}_before/{k}"] = v
+        for k, v in after.items():
+            out[f"gauss{c}_after/{k}"] = v
+        n_changed = sum(int((before[k] != after[k]).sum()) for k in before)
+        print(f"  gaussian mutation seed {seed}: {n_changed} weights changed")
+    # (c) RL hyper-parameter mutation sequence
+    hp = HyperparameterConfig(lr=RLParameter(min=1e-5, max=1e-2), batch_size=RLParameter(min=8, max=64, dtype=int),
+                              learn_step=RLParameter(min=1, max=16, dtype=int, grow_factor=1.5, shrink_factor=0.75))
+    torch.manual_seed(0)
+    agent = RainbowDQN(obs_space, act_space, hp_config=hp, net_config=dict(net_config), batch_size=16, lr=1e-3, learn_step=4,
+                       v_min=-10.0, v_max=10.0)
+    m = Mutations(0, 0, 0.5, 0, 0, 1, rand_seed=5)
+    torch.manual_seed(900)
+    seq = []
+    for _ in range(12):
+        agent = m.rl_hyperparam_mutation(agent)
+        seq.append((agent.mut, float(agent.lr), int(agent.batch_size), int(agent.learn_step)))
+    out["rlhp_mut"] = np.array([s[0] for s in seq])
+    out["rlhp_vals"] = np.array([[s[1], s[2], s[3]] for s in seq], np.float64)
+    # (d) activation picks
+    m = Mutations(0, 0, 0.5, 0, 1, 0, activation_selection=["ReLU", "ELU", "GELU"], rand_seed=9)
+    acts = []
+    for _ in range(8):
+        agent = m.activation_mutation(agent)
+        acts.append(agent.actor.activation)
+    out["act_seq"] = np.array(acts)
+    # (e) architecture: the method Mutations.rng samples for a RainbowQNetwork (names only)
+    m = Mutations(0, 1, 0.5, 0, 0, 0, rand_seed=21)
+    torch.manual_seed(1)
+    agent = RainbowDQN(obs_space, act_space, net_config=dict(net_config), batch_size=8, v_min=-10.0, v_max=10.0)
+    out["arch_methods"] = np.array(list(agent.actor.mutation_methods))
+    out["arch_probs"] = np.array(agent.actor.get_mutation_probs(m.new_layer_prob), np.float64)
+    picks = []
+    for _ in range(16):
+        picks.append(agent.actor.sample_mutation_method(m.new_layer_prob, m.rng))
+    out["arch_picks"] = np.array([p if isinstance(p, str) else getattr(p, "__name__", str(p)) for p in picks])
+    save("mutations.npz", **out)
+    print("  mutations: reference outputs recorded")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)   # deterministic CPU reductions while generating
+    if len(sys.argv) > 1 and sys.argv[1] == "mutations":
+        gen_mutations()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "ddpg_td3":
         gen_ddpg_td3()
         sys.exit(0)
@@ -461,3 +537,4 @@ if __name__ == "__main__":
     gen_tournament()
     gen_ddpg_td3()
     gen_gae()
+    gen_mutations()
