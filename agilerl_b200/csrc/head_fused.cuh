@@ -173,6 +173,34 @@ static inline size_t head2_smem_floats(const HeadDesc &hd) {
 
 static_assert(kHeadThreads / 32 == kHead2Rows, "one warp per row in the normalise / store phase");
 
+// y[q][o] = b[o] + sum_i x[q][i] * W[o][i] for RPT rows held by this thread: bias first, then ascending i
+template <int RPT>
+__device__ __forceinline__ void head2_linear(const HeadLayer &L, const float *__restrict__ ws, int wp,
+                                             const float *__restrict__ xr, float *__restrict__ yr, int pitch, int ol,
+                                             int lanes_o) {
+    for (int o = ol; o < L.out; o += lanes_o) {
+        float acc[RPT];
+        const float bv = L.b ? __ldg(L.b + o) : 0.f;
+#pragma unroll
+        for (int q = 0; q < RPT; ++q) acc[q] = bv;
+        const float *wr = ws + (size_t)o * wp;
+#pragma unroll 2
+        for (int i = 0; i < L.in; i += 4) {
+            const float4 w = *reinterpret_cast<const float4 *>(wr + i);
+#pragma unroll
+            for (int q = 0; q < RPT; ++q) {
+                const float4 x = *reinterpret_cast<const float4 *>(xr + q * pitch + i);
+                acc[q] = fmaf(x.x, w.x, acc[q]);
+                acc[q] = fmaf(x.y, w.y, acc[q]);
+                acc[q] = fmaf(x.z, w.z, acc[q]);
+                acc[q] = fmaf(x.w, w.w, acc[q]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < RPT; ++q) yr[q * pitch + o] = acc[q];
+    }
+}
+
 __global__ void __launch_bounds__(kHeadThreads) head_fwd2_kernel(const HeadDesc hd, const float *__restrict__ latent,
                                                                  int64_t rows) {
     extern __shared__ __align__(16) float hsm[];
@@ -224,30 +252,13 @@ __global__ void __launch_bounds__(kHeadThreads) head_fwd2_kernel(const HeadDesc 
             const int rpt = R / rg;                                   // rows per thread: 8, 4, 2 or 1
             const int ol = tid % lanes_o, g = tid / lanes_o;
             if (g < rg) {
-                for (int o = ol; o < L.out; o += lanes_o) {
-                    float acc[R];
-                    const float bv = L.b ? __ldg(L.b + o) : 0.f;
-#pragma unroll
-                    for (int q = 0; q < R; ++q) acc[q] = bv;
-                    const float *wr = ws + (size_t)o * wp;
-                    const float *xr = xb + (size_t)(g * rpt) * pitch;
-                    for (int i = 0; i < L.in; i += 4) {
-                        const float4 w = *reinterpret_cast<const float4 *>(wr + i);
-#pragma unroll
-                        for (int q = 0; q < R; ++q) {
-                            if (q < rpt) {
-                                const float4 x = *reinterpret_cast<const float4 *>(xr + q * pitch + i);
-                                // bias first, then ascending i: the summation order of a row-major dot product
-                                acc[q] = fmaf(x.x, w.x, acc[q]);
-                                acc[q] = fmaf(x.y, w.y, acc[q]);
-                                acc[q] = fmaf(x.z, w.z, acc[q]);
-                                acc[q] = fmaf(x.w, w.w, acc[q]);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < R; ++q)
-                        if (q < rpt) yb[(g * rpt + q) * pitch + o] = acc[q];
+                const float *xr = xb + (size_t)(g * rpt) * pitch;
+                float *yr = yb + (size_t)(g * rpt) * pitch;
+                switch (rpt) {       // compile-time row counts: the accumulators stay in registers, the loops unroll
+                    case 8: head2_linear<8>(L, ws, wp, xr, yr, pitch, ol, lanes_o); break;
+                    case 4: head2_linear<4>(L, ws, wp, xr, yr, pitch, ol, lanes_o); break;
+                    case 2: head2_linear<2>(L, ws, wp, xr, yr, pitch, ol, lanes_o); break;
+                    default: head2_linear<1>(L, ws, wp, xr, yr, pitch, ol, lanes_o); break;
                 }
             }
             __syncthreads();
