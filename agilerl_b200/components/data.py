@@ -49,3 +49,12 @@ class Transition:
             self.done = self.done.unsqueeze(-1)
         if self.reward.ndim == 0:
             self.reward = self.reward.unsqueeze(-1)
+
+
+class ReplayDataset:
+    """agilerl/components/data.py:96-118 — the accelerate DataLoader bridge of the reference's distributed replay.
+    The population is sharded one process per GPU here (no accelerate), so the class only exists for the
+    ``from agilerl.components.data import ReplayDataset`` line of the unchanged driver."""
+
+    def __init__(self, buffer, batch_size: int = 256) -> None:
+        raise NotImplementedError("accelerate-sharded replay is replaced by one-agent-per-GPU sharding (DESIGN.md section 6)")
