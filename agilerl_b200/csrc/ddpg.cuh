@@ -65,10 +65,6 @@ static int chain_forward(const Chain &c, const float *params, const float *x, in
         h.a = bufs[i].a; h.z = bufs[i].z; h.pre = bufs[i].pre; h.stats = bufs[i].stats;
         h.in = l.in_c; h.out = l.out_c; h.ln = l.ln; h.act = l.act;
     }
-    {
-        const int rc2 = launch_head_fwd2(hd, x, rows, s);      // weights staged in shared memory when they fit
-        if (rc2 != 1) return rc2;
-    }
     const size_t smem = sizeof(float) * ((size_t)2 * kHeadRows * head_pitch(hd.maxdim) + (kHeadThreads / 32) * kHeadRows);
     B2RL_CHECK_ARG(smem <= 160 * 1024, "chain too wide for the fused forward kernel");
     head_fwd_kernel<<<(int)((rows + kHeadRows - 1) / kHeadRows), kHeadThreads, smem, s>>>(hd, x, rows);

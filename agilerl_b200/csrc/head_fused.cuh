@@ -8,8 +8,6 @@
 // (they are a few hundred KB at most and shared by all CTAs).  It writes exactly the buffers the
 // unfused path writes (z, stats, pre, a per layer), so backward and the loss kernels are unchanged.
 #pragma once
-#include <cstdlib>
-
 #include "common.cuh"
 
 namespace b2rl {
@@ -142,172 +140,6 @@ __global__ void __launch_bounds__(kHeadThreads) head_fwd_kernel(const HeadDesc h
             __syncthreads();
         }
     }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Forward, weights staged in shared memory (the default when the head fits: every network of this repo does).
-// The tile kernel above re-reads its weights from L2 inside every inner loop and is bound by that latency
-// (ncu: long_scoreboard 6.8 / issue, 19 us for 14 MFLOP).  Here a CTA first pulls EVERY layer's weight matrix of
-// both chains into shared memory with 16-byte cp.async copies (rows padded by 4 floats so that a warp's 16-byte
-// reads of 32 different rows are bank-conflict free), then walks 8 rows through all layers out of shared memory:
-// thread = (output neuron, row group), the row group's accumulators in registers, one 16-byte weight read feeding
-// 4 x rows FMAs.  Same outputs (z / stats / pre / a per layer) as the tile kernel.
-// ------------------------------------------------------------------------------------------------
-constexpr int kHead2Rows = 8;
-
-__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-// floats of shared memory the staged kernel needs (0: a layer's rows are not 16-byte copyable)
-static inline size_t head2_smem_floats(const HeadDesc &hd) {
-    size_t w = 0;
-    for (int i = 0; i < hd.n_val + hd.n_adv; ++i) {
-        const HeadLayer &L = hd.l[i];
-        if ((L.in & 3) != 0 || (reinterpret_cast<uintptr_t>(L.w) & 15) != 0) return 0;
-        w += (size_t)L.out * (L.in + 4);
-    }
-    return w + (size_t)2 * kHead2Rows * head_pitch(hd.maxdim) + 64;
-}
-
-static_assert(kHeadThreads / 32 == kHead2Rows, "one warp per row in the normalise / store phase");
-
-// y[q][o] = b[o] + sum_i x[q][i] * W[o][i] for RPT rows held by this thread: bias first, then ascending i
-template <int RPT>
-__device__ __forceinline__ void head2_linear(const HeadLayer &L, const float *__restrict__ ws, int wp,
-                                             const float *__restrict__ xr, float *__restrict__ yr, int pitch, int ol,
-                                             int lanes_o) {
-    for (int o = ol; o < L.out; o += lanes_o) {
-        float acc[RPT];
-        const float bv = L.b ? __ldg(L.b + o) : 0.f;
-#pragma unroll
-        for (int q = 0; q < RPT; ++q) acc[q] = bv;
-        const float *wr = ws + (size_t)o * wp;
-#pragma unroll 2
-        for (int i = 0; i < L.in; i += 4) {
-            const float4 w = *reinterpret_cast<const float4 *>(wr + i);
-#pragma unroll
-            for (int q = 0; q < RPT; ++q) {
-                const float4 x = *reinterpret_cast<const float4 *>(xr + q * pitch + i);
-                acc[q] = fmaf(x.x, w.x, acc[q]);
-                acc[q] = fmaf(x.y, w.y, acc[q]);
-                acc[q] = fmaf(x.z, w.z, acc[q]);
-                acc[q] = fmaf(x.w, w.w, acc[q]);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < RPT; ++q) yr[q * pitch + o] = acc[q];
-    }
-}
-
-__global__ void __launch_bounds__(kHeadThreads) head_fwd2_kernel(const HeadDesc hd, const float *__restrict__ latent,
-                                                                 int64_t rows) {
-    extern __shared__ __align__(16) float hsm[];
-    constexpr int R = kHead2Rows;
-    const int pitch = head_pitch(hd.maxdim);
-    float *xb = hsm;                                  // [R][pitch] layer input
-    float *yb = hsm + R * pitch;                      // [R][pitch] layer output (pre-LN)
-    float *wbase = yb + R * pitch;                    // every layer's [out][in + 4]
-    const int tid = threadIdx.x;
-    const int nl = hd.n_val + hd.n_adv;
-    const int64_t row0 = (int64_t)blockIdx.x * R;
-    // ---- stage all weights (asynchronously), then the latent rows
-    {
-        size_t off = 0;
-        for (int li = 0; li < nl; ++li) {
-            const HeadLayer &L = hd.l[li];
-            const int in4 = L.in >> 2, wp = L.in + 4;
-            const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(wbase + off);
-            for (int e = tid; e < L.out * in4; e += kHeadThreads) {
-                const int o = e / in4, c = e - o * in4;
-                cp_async16(dst0 + (uint32_t)(o * wp + c * 4) * 4u, L.w + (int64_t)o * L.in + c * 4);
-            }
-            off += (size_t)L.out * wp;
-        }
-    }
-    cp_async_wait_all();
-    __syncthreads();
-
-    size_t woff = 0;
-    for (int chain = 0; chain < 2; ++chain) {
-        const int l0 = chain == 0 ? 0 : hd.n_val, l1 = chain == 0 ? hd.n_val : nl;
-        if (l0 == l1) continue;
-        __syncthreads();
-        for (int e = tid; e < R * hd.latent; e += kHeadThreads) {
-            const int q = e / hd.latent, i = e - q * hd.latent;
-            xb[q * pitch + i] = (row0 + q < rows) ? latent[(row0 + q) * hd.latent + i] : 0.f;
-        }
-        __syncthreads();
-        for (int li = l0; li < l1; ++li) {
-            const HeadLayer L = hd.l[li];
-            const int wp = L.in + 4;
-            const float *ws = wbase + woff;
-            woff += (size_t)L.out * wp;
-            // thread = (output lane, row group): lanes_o = smallest power of two >= out (32..256)
-            int lanes_o = 32;
-            while (lanes_o < L.out && lanes_o < kHeadThreads) lanes_o <<= 1;
-            int rg = kHeadThreads / lanes_o;
-            if (rg > R) rg = R;
-            const int rpt = R / rg;                                   // rows per thread: 8, 4, 2 or 1
-            const int ol = tid % lanes_o, g = tid / lanes_o;
-            if (g < rg) {
-                const float *xr = xb + (size_t)(g * rpt) * pitch;
-                float *yr = yb + (size_t)(g * rpt) * pitch;
-                switch (rpt) {       // compile-time row counts: the accumulators stay in registers, the loops unroll
-                    case 8: head2_linear<8>(L, ws, wp, xr, yr, pitch, ol, lanes_o); break;
-                    case 4: head2_linear<4>(L, ws, wp, xr, yr, pitch, ol, lanes_o); break;
-                    case 2: head2_linear<2>(L, ws, wp, xr, yr, pitch, ol, lanes_o); break;
-                    default: head2_linear<1>(L, ws, wp, xr, yr, pitch, ol, lanes_o); break;
-                }
-            }
-            __syncthreads();
-            // ---- LayerNorm statistics: 32 threads per row (one warp), two passes, shuffle tree
-            const int q = tid >> 5, lane = tid & 31;              // 8 warps == 8 rows
-            const int64_t row = row0 + q;
-            const bool rok = row < rows;
-            float mean = 0.f, rstd = 1.f;
-            if (L.ln != B2RL_LN_NONE) {
-                float sacc = 0.f;
-                for (int o = lane; o < L.out; o += 32) sacc += yb[q * pitch + o];
-                mean = warp_sum(sacc) / (float)L.out;
-                float v = 0.f;
-                for (int o = lane; o < L.out; o += 32) { const float d = yb[q * pitch + o] - mean; v += d * d; }
-                rstd = 1.0f / sqrtf(warp_sum(v) / (float)L.out + 1e-5f);
-                if (lane == 0 && rok && L.stats) { L.stats[row * 2] = mean; L.stats[row * 2 + 1] = rstd; }
-            }
-            // ---- normalise / activate, write global + next layer's input (warp q owns row q: coalesced rows)
-            for (int o = lane; o < L.out; o += 32) {
-                float y = yb[q * pitch + o];
-                if (L.ln != B2RL_LN_NONE) {
-                    if (rok && L.z) L.z[row * L.out + o] = y;
-                    y = (y - mean) * rstd;
-                    if (L.lnw) y = y * L.lnw[o] + L.lnb[o];
-                }
-                if (rok && L.pre) L.pre[row * L.out + o] = y;
-                y = act_fwd(L.act, y);
-                if (rok) L.a[row * L.out + o] = y;
-                xb[q * pitch + o] = y;
-            }
-            __syncthreads();
-        }
-    }
-}
-
-// launch the staged kernel when the head fits (returns 1 when it does not: caller uses the tile kernel)
-static int launch_head_fwd2(const HeadDesc &hd, const float *latent, int64_t rows, cudaStream_t s) {
-    static const bool on = !(getenv("B2RL_HEAD2") && getenv("B2RL_HEAD2")[0] == '0');
-    if (!on) return 1;
-    const size_t fl = head2_smem_floats(hd);
-    if (fl == 0 || fl * sizeof(float) > 200 * 1024) return 1;
-    static bool attr_set = false;
-    if (!attr_set) {
-        B2RL_CUDA(cudaFuncSetAttribute(head_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
-    head_fwd2_kernel<<<(int)((rows + kHead2Rows - 1) / kHead2Rows), kHeadThreads, fl * sizeof(float), s>>>(hd, latent, rows);
-    B2RL_LAUNCH_CHECK();
-    return B2RL_OK;
 }
 
 }  // namespace b2rl

@@ -523,10 +523,6 @@ static int forward_pass(const b2rl_net_desc &net, const float *params, const flo
         for (int i = 0; i < net.n_adv && ok; ++i) fill(net.adv[i], pb.adv[i], hd.l[net.n_val + i]);
         hd.maxdim = maxdim;
         const size_t smem = sizeof(float) * ((size_t)2 * kHeadRows * head_pitch(maxdim) + (kHeadThreads / 32) * kHeadRows);
-        if (ok) {
-            const int rc2 = launch_head_fwd2(hd, latent, rows, s);
-            if (rc2 != 1) return rc2;
-        }
         if (ok && smem <= 160 * 1024) {
             static bool attr_set = false;
             if (!attr_set) {
