@@ -136,6 +136,8 @@ _SIGS = {
     "b2rl_gather_rows": ([c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p], c_int),
     "b2rl_ring_write_multi": ([c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p], c_int),
     "b2rl_gather_rows_multi": ([c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p], c_int),
+    "b2rl_nstep_ingest": ([c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_double, c_int64,
+                           c_int64, c_void_p], c_int),
     "b2rl_nstep_fold": ([POINTER(c_void_p), POINTER(c_void_p), c_int, c_int64, c_double, c_void_p, c_void_p,
                          c_void_p], c_int),
     "b2rl_select_copy": ([c_void_p, POINTER(c_void_p), c_int, c_void_p, c_int64, c_void_p], c_int),

@@ -65,6 +65,13 @@ def _shallow(td):
     return td.clone(False)                       # real tensordict: non-recursive clone shares the leaves
 
 
+def _numel(shape) -> int:
+    n = 1
+    for d in shape:
+        n *= int(d)
+    return n
+
+
 def _as_collection(data) -> Any:
     if is_tensor_collection(data):
         return data
@@ -317,6 +324,7 @@ class MultiStepReplayBuffer(ReplayBuffer):
         self.n_step = n_step
         self.gamma = gamma
         self.n_step_buffer: deque = deque(maxlen=n_step)
+        self._window_ptrs: deque = deque(maxlen=n_step)
         self.reward_key = "reward"
         self.done_key = None
         self.ns_key = "next_obs"
@@ -325,11 +333,57 @@ class MultiStepReplayBuffer(ReplayBuffer):
         """:173-194 — returns the oldest transition of the window (or None while filling)."""
         data = self._to_device(_as_collection(data))
         self.n_step_buffer.append(data)
+        self._window_ptrs.append(self._leaf_ptrs(data))
         if len(self.n_step_buffer) < self.n_step:
             return None
-        n_step_data = self._get_n_step_info()
-        super().add(n_step_data)
+        if not self._ingest_fused():
+            n_step_data = self._get_n_step_info()
+            super().add(n_step_data)
         return self.n_step_buffer[0]
+
+    # -- fused ingest: fold + select + ring write in one launch -------------------------------------
+    def _leaf_ptrs(self, data):
+        """(path -> (data_ptr, shape, dtype)) of a window entry, taken once when it enters the window."""
+        out = {}
+        for path, v in _leaf_items(data):
+            if not (isinstance(v, torch.Tensor) and v.device == self._dev and v.is_contiguous()):
+                return None
+            out[path] = (v.data_ptr(), tuple(v.shape), v.dtype)
+        return out
+
+    def _ingest_fused(self) -> bool:
+        """One ``b2rl_nstep_ingest`` launch instead of fold + two select-copies + a multi-field ring write with their
+        temporaries.  Needs an initialised storage whose fields the window entries match leaf for leaf (flat float32
+        reward / done of one element per env); anything else takes the general path."""
+        if self._storage is None or self.n_step < 2 or self.done_key is None:
+            return False
+        win = list(self._window_ptrs)
+        order = self._field_order
+        nf, n = len(order), self.n_step
+        if nf > 8 or any(w is None or list(w) != order for w in win):
+            return False
+        E = win[0][order[0]][1][0]
+        rk, dk, nk = (self.reward_key,), (self.done_key,), (self.ns_key,)
+        if rk not in win[0] or dk not in win[0] or nk not in win[0] or E > self.max_size:
+            return False
+        for w in win:
+            for path in order:
+                ptr, shape, dt = w[path]
+                dst = self._fields[path]
+                if dt != dst.dtype or shape[0] != E or _numel(shape[1:]) != _numel(dst.shape[1:]):
+                    return False
+            if w[rk][2] != torch.float32 or w[dk][2] != torch.float32 or _numel(w[rk][1]) != E or _numel(w[dk][1]) != E:
+                return False
+        src = (ctypes.c_void_p * (nf * n))(*[win[k][path][0] for path in order for k in range(n)])
+        role = (ctypes.c_int32 * nf)(*[2 if path == rk else (1 if path in (dk, nk) else 0) for path in order])
+        rew = (ctypes.c_void_p * n)(*[w[rk][0] for w in win])
+        don = (ctypes.c_void_p * n)(*[w[dk][0] for w in win])
+        _lib.check(self._lib.b2rl_nstep_ingest(nf, self._field_ptrs, src, self._field_row_bytes, role, rew, don, n, E,
+                                               float(self.gamma), self._cursor, self.max_size, _lib.stream_ptr(self._dev)))
+        self._cursor = (self._cursor + E) % self.max_size
+        self._size = min(self._size + E, self.max_size)
+        self.counter += E
+        return True
 
     def sample_from_indices(self, idxs: torch.Tensor) -> TensorDict:
         """:196-204 — ``storage[idxs]`` (keeps the idxs shape, e.g. [B,1] -> fields [B,1,...])."""

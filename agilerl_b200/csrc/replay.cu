@@ -43,6 +43,7 @@ __global__ void gather_rows_kernel(V *__restrict__ dst, const V *__restrict__ st
 }
 
 constexpr int kMaxNStep = 16;
+constexpr int kMaxFields = 8;
 struct StepPtrs {
     const float *reward[kMaxNStep];
     const float *done[kMaxNStep];
@@ -82,8 +83,55 @@ __global__ void select_copy_kernel(uint8_t *__restrict__ dst, SrcPtrs srcs, cons
     }
 }
 
+// ---- n-step roll + ring write in ONE launch (MultiStepReplayBuffer.add, replay_buffer.py:173-194 + :206-258 + :72-112) ----
+// The window's n per-env batches stay where ingest put them; every field of the n-step transition goes straight into
+// its ring rows: obs / action (and any other key) from the oldest step, next_obs / done from the step the fold
+// stopped at, reward folded like nstep_fold_kernel (fp32, gamma**k rounded to f32, quirk Q3).  blockIdx.y = field.
+struct IngestField { uint8_t *ring; const uint8_t *src[kMaxNStep]; int64_t row_bytes; int role; };   // 0 first, 1 last, 2 reward
+struct IngestArgs {
+    IngestField f[kMaxFields];
+    const float *reward[kMaxNStep];
+    const float *done[kMaxNStep];
+    float scale[kMaxNStep];
+    int n_step;
+    int64_t num_envs, cursor, max_size;
+};
+__global__ void nstep_ingest_kernel(IngestArgs a) {
+    int last = 0;
+    for (int k = 1; k < a.n_step; ++k) {           // every CTA derives the stopping step itself (a few hundred flags)
+        int any = 0;
+        for (int64_t e = threadIdx.x; e < a.num_envs; e += blockDim.x) any |= (a.done[k][e] != 0.f);
+        last = k;
+        if (__syncthreads_or(any)) break;
+    }
+    const IngestField f = a.f[blockIdx.y];
+    if (f.role == 2) {
+        for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < a.num_envs; e += (int64_t)gridDim.x * blockDim.x) {
+            float r = a.reward[0][e];
+            for (int k = 1; k <= last; ++k) r = __fadd_rn(r, __fmul_rn(a.reward[k][e], a.scale[k]));
+            *reinterpret_cast<float *>(f.ring + ((a.cursor + e) % a.max_size) * f.row_bytes) = r;
+        }
+        return;
+    }
+    const uint8_t *src = f.src[f.role == 1 ? last : 0];
+    const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(f.ring) | (uintptr_t)f.row_bytes) & 15) == 0;
+    if (vec) {
+        const int64_t rv = f.row_bytes / 16, total = a.num_envs * rv;
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t e = i / rv, c = i - e * rv;
+            reinterpret_cast<uint4 *>(f.ring + ((a.cursor + e) % a.max_size) * f.row_bytes)[c] =
+                __ldg(reinterpret_cast<const uint4 *>(src + e * f.row_bytes) + c);
+        }
+    } else {
+        const int64_t total = a.num_envs * f.row_bytes;
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t e = i / f.row_bytes, c = i - e * f.row_bytes;
+            f.ring[((a.cursor + e) % a.max_size) * f.row_bytes + c] = src[e * f.row_bytes + c];
+        }
+    }
+}
+
 // ---- all fields of a transition in one launch (blockIdx.y = field) -------------------------------
-constexpr int kMaxFields = 8;
 struct MultiField { void *dst; const void *src; int64_t row_bytes; int vec; };   // vec: 16 / 4 / 1 bytes per element
 struct MultiFields { MultiField f[kMaxFields]; };
 
@@ -340,6 +388,36 @@ int b2rl_select_copy(void *dst, const void *const *srcs_host, int n_srcs, const 
     if (blocks < 1) blocks = 1;
     if (blocks > sm_count() * 4) blocks = sm_count() * 4;
     select_copy_kernel<<<blocks, 256, 0, as_stream(stream)>>>(static_cast<uint8_t *>(dst), sp, which, bytes);
+    B2RL_LAUNCH_CHECK();
+    return B2RL_OK;
+}
+
+int b2rl_nstep_ingest(int n_fields, void *const *ring, const void *const *src, const int64_t *row_bytes, const int32_t *role,
+                      const float *const *reward_steps, const float *const *done_steps, int n_step, int64_t num_envs,
+                      double gamma, int64_t cursor, int64_t max_size, void *stream) {
+    B2RL_CHECK_ARG(n_fields >= 1 && n_fields <= b2rl::kMaxFields && n_step >= 1 && n_step <= b2rl::kMaxNStep, "bad field / step count");
+    B2RL_CHECK_ARG(ring && src && row_bytes && role && reward_steps && done_steps && num_envs >= 1 && num_envs <= max_size,
+                   "bad arguments");
+    b2rl::IngestArgs a;
+    int64_t max_bytes = 0;
+    for (int i = 0; i < n_fields; ++i) {
+        a.f[i].ring = static_cast<uint8_t *>(ring[i]);
+        a.f[i].row_bytes = row_bytes[i];
+        a.f[i].role = role[i];
+        for (int k = 0; k < n_step; ++k) a.f[i].src[k] = static_cast<const uint8_t *>(src[i * n_step + k]);
+        if (role[i] == 2) B2RL_CHECK_ARG(row_bytes[i] == 4, "the reward field must be one float32 per row");
+        if (row_bytes[i] * num_envs > max_bytes) max_bytes = row_bytes[i] * num_envs;
+    }
+    double g = 1.0;
+    for (int k = 0; k < n_step; ++k) {
+        a.reward[k] = reward_steps[k]; a.done[k] = done_steps[k];
+        a.scale[k] = (float)g;                      // gamma ** k as a Python double, rounded where torch rounds it
+        g = pow(gamma, (double)(k + 1));
+    }
+    a.n_step = n_step; a.num_envs = num_envs; a.cursor = cursor; a.max_size = max_size;
+    int bx = (int)((max_bytes / 16 + 255) / 256);
+    bx = bx < 1 ? 1 : (bx > 296 ? 296 : bx);
+    b2rl::nstep_ingest_kernel<<<dim3(bx, n_fields), 256, 0, b2rl::as_stream(stream)>>>(a);
     B2RL_LAUNCH_CHECK();
     return B2RL_OK;
 }

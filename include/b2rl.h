@@ -156,6 +156,16 @@ int b2rl_nstep_fold(const float *const *reward_steps, const float *const *done_s
                     int64_t num_envs, double gamma, float *reward_out, int32_t *last_step_out,
                     void *stream);
 
+/* MultiStepReplayBuffer.add in ONE launch (replay_buffer.py:173-194 -> :206-258 -> :72-112): fold the window of n_step
+ * per-env batches and write the resulting n-step transition straight into the ring rows [cursor, cursor+num_envs) (mod
+ * max_size).  Field i: ring[i] (storage base), src[i*n_step + k] (step k's [num_envs, ...] batch of that field),
+ * row_bytes[i], role[i] = 0 take step 0 (obs, action ...), 1 take the step the fold stopped at (next_obs, done),
+ * 2 the folded float32 reward.  reward_steps / done_steps: float32 [num_envs] per step.  All arrays HOST arrays of
+ * device pointers. */
+int b2rl_nstep_ingest(int n_fields, void *const *ring, const void *const *src, const int64_t *row_bytes, const int32_t *role,
+                      const float *const *reward_steps, const float *const *done_steps, int n_step, int64_t num_envs,
+                      double gamma, int64_t cursor, int64_t max_size, void *stream);
+
 /* dst[0:bytes] <- srcs[*which][0:bytes]: carries next_obs/done of the step the fold stopped
  * at (replay_buffer.py:249-250) without a host round trip.  srcs_host: HOST array of n_srcs
  * device pointers; which: DEVICE int32. */
