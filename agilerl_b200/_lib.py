@@ -229,6 +229,12 @@ def as_device(device) -> torch.device:
             f"agilerl_b200 runs on CUDA devices only (got device={device!r}); there is no CPU fallback."
         )
     load(require_cuda=True)
+    cur = torch.cuda.current_device()
     if d.index is None:
-        d = torch.device("cuda", torch.cuda.current_device())
+        d = torch.device("cuda", cur)
+    elif d.index != cur:
+        # the library keeps per-process side streams / kernel attributes for ONE device and launches on the current
+        # one: a buffer or agent elsewhere would fail later with an invalid resource handle
+        raise B2RLError(f"device {d} is not the current CUDA device (cuda:{cur}): agilerl_b200 drives one GPU per process; "
+                        "call torch.cuda.set_device first")
     return d

@@ -701,7 +701,12 @@ def main():
         sampler.start()
     l0 = lib.b2rl_launch_count()
     join_all = lambda: [a.synchronize() for a in engines]
+    prof = os.environ.get("B2RL_PROFILE_REGION") == "1"      # `ncu --profile-from-start off`: only the timed region
+    if prof:
+        torch.cuda.profiler.start()
     ms, ms_all = time_region(step_fn, args.steps, dist_on, finish=join_all)
+    if prof:
+        torch.cuda.profiler.stop()
     launches = (lib.b2rl_launch_count() - l0) // len(ms_all)
     clocks = sampler.stop() if rank == 0 else None
     value = POP * args.steps / (ms / 1e3)
