@@ -546,23 +546,6 @@ __global__ void __launch_bounds__(kTcFwdThreads) conv_fwd_tc_kernel(const ConvTc
     if (warp == 0) tc::tmem_dealloc(tmem_d, tmem_cols);
 }
 
-}  // namespace b2rl
-#include "conv_tc_persist.cuh"
-namespace b2rl {
-
-// B2RL_TC_PERSIST=1 selects the persistent kernels of conv_tc_persist.cuh.  Measured on B200 (r1):
-// they tie with the one-tile-per-CTA kernels on a quiet GPU (conv1 forward 24 us both) and lose a few
-// percent when other streams share the SMs (fewer, longer-lived CTAs), so they are off by default.
-// Likewise B2RL_TC_SA=3 (three A stages) and B2RL_TC_SB=8 (weight tiles six k-blocks ahead) trade
-// residency (3 -> 2 CTAs per SM) for pipeline depth and measured slower.
-static bool tc_persist_enabled() {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("B2RL_TC_PERSIST");
-        v = (e && e[0] == '1') ? 1 : 0;
-    }
-    return v == 1;
-}
 
 // B2RL_TC_DBG=<cta index>: the forward kernel records clock64 stamps of that CTA (b2rl_debug_read)
 static int tc_debug_cta() {
@@ -595,11 +578,7 @@ static int launch_conv_fwd_tc(const b2rl_layer &l, const Operand &A, const float
     const int n_pad = (l.out_c + 15) / 16 * 16, k_pad = (K + kTcBK - 1) / kTcBK * kTcBK;
     if (n_pad > 128 || k_pad > 8192 || rows * (int64_t)P > INT32_MAX) return 1;    // one MMA spans 2*n_pad <= 256 columns
     const bool exact = A.u8 && (!A.normalize || (A.low == floorf(A.low) && fabsf(A.low) <= 1024.f));
-    static const int sa_exact = getenv("B2RL_TC_SA") ? atoi(getenv("B2RL_TC_SA")) : 2;
-    static const int sb_exact = getenv("B2RL_TC_SB") ? atoi(getenv("B2RL_TC_SB")) : 4;
-    const bool deep = exact && sa_exact == 3;
-    const bool wide_b = exact && !deep && sb_exact == 8 && k_pad / kTcBK > 4;
-    const size_t smem = conv_tc_smem_bytes(n_pad, k_pad, exact ? 1 : 2, deep ? 3 : 2, wide_b ? 8 : kTcBStages);
+    const size_t smem = conv_tc_smem_bytes(n_pad, k_pad, exact ? 1 : 2, 2, kTcBStages);
     if (smem > 200 * 1024 || wsplit == nullptr || conv_tc_wsplit_floats(l) > wsplit_cap) return 1;
     if (reinterpret_cast<uintptr_t>(wsplit) % 16 != 0) return 1;          // bulk copies need 16-byte aligned sources
     float *w_hi = wsplit, *w_lo = nullptr;                 // one interleaved hi|lo array
@@ -635,29 +614,8 @@ static int launch_conv_fwd_tc(const b2rl_layer &l, const Operand &A, const float
         B2RL_LAUNCH_CHECK();
         return B2RL_OK;
     };
-    if (tc_persist_enabled()) {
-        static const int sa_p = getenv("B2RL_TC_PSA") ? atoi(getenv("B2RL_TC_PSA")) : 4;
-        const size_t smem_p = conv_tc_persist_smem_bytes(n_pad, k_pad, exact ? 1 : 2, 2);
-        int rcp = 1;
-        if (A.elem_kind() == EL_U8 && exact && vec) {
-            if (sa_p == 8)
-                rcp = launch_conv_persist(conv_fwd_tc_persist_kernel<EL_U8, true, true, 8, false, 8>, p, 1,
-                                          conv_tc_persist_smem_bytes(n_pad, k_pad, 1, 8), s);
-            else if (sa_p == 4)
-                rcp = launch_conv_persist(conv_fwd_tc_persist_kernel<EL_U8, true, true, 8, false, 4>, p, 1,
-                                          conv_tc_persist_smem_bytes(n_pad, k_pad, 1, 4), s);
-            else
-                rcp = launch_conv_persist(conv_fwd_tc_persist_kernel<EL_U8, true, true, 8, false, 2>, p, 1, smem_p, s);
-        }
-        else if (A.elem_kind() == EL_F32 && vec)
-            rcp = launch_conv_persist(conv_fwd_tc_persist_kernel<EL_F32, false, true, 2, false, 2>, p, 1, smem_p, s);
-        if (rcp != 1) return rcp;
-    }
     switch (A.elem_kind()) {
         case EL_U8:
-            if (exact && vec && deep) return launch(conv_fwd_tc_kernel<EL_U8, true, true, 8, false, 3>);
-            if (exact && vec && wide_b) return launch(conv_fwd_tc_kernel<EL_U8, true, true, 8, false, 2, 8>);
-            if (exact && wide_b) return launch(conv_fwd_tc_kernel<EL_U8, true, false, 2, false, 2, 8>);
             if (exact) return vec ? launch(conv_fwd_tc_kernel<EL_U8, true, true, 8>) : launch(conv_fwd_tc_kernel<EL_U8, true, false, 2>);
             return vec ? launch(conv_fwd_tc_kernel<EL_U8, false, true, 8>) : launch(conv_fwd_tc_kernel<EL_U8, false, false, 2>);
         case EL_F32_NORM:
@@ -741,11 +699,6 @@ static int launch_conv_dgrad_tc(const b2rl_layer &l, const float *g, const float
     p.pad = T - 1; p.IH = l.out_h; p.cls_s = S; p.out_H = l.in_h; p.out_W = l.in_w;
     p.w_class_stride = (int64_t)2 * cls_floats;
     p.dbg = nullptr; p.dbg_cta = -1;
-    if (tc_persist_enabled()) {
-        const int rcp = launch_conv_persist(conv_fwd_tc_persist_kernel<EL_F32, false, false, 2, true, 2>, p, S * S,
-                                            conv_tc_persist_smem_bytes(n_pad, k_pad, 2, 2), s);
-        if (rcp != 1) return rcp;
-    }
     auto kern = conv_fwd_tc_kernel<EL_F32, false, false, 2, true>;
     { const int rca = ensure_big_smem(kern); if (rca != B2RL_OK) return rca; }
     kern<<<dim3((unsigned)((p.M + kTcBM - 1) / kTcBM), S * S), kTcFwdThreads, smem, s>>>(p);
