@@ -44,7 +44,10 @@ LR, TAU, PRIOR_EPS = 1e-4, 1e-3, 1e-6
 NUM_ENVS = 4                                  # env-steps ingested per e2e step
 ALG_BYTES_PER_STEP = 22_954_544
 ALG_FLOPS_PER_STEP = 12_067_307_520
-TRAFFIC_CONV1 = None                           # filled from the committed ncu capture (profiles/)
+# dram__bytes_read.sum + dram__bytes_write.sum of one conv_fwd_i8_kernel<8,8> launch (profiles/r2_conv1_i8_single.txt,
+# ncu --set full): 7.29 MB read (the 7.2 MB of uint8 frames + weights) + 0 written -- the 13.1 MB of fp32 activations stay
+# in the 126 MB L2 for the next layer, so DRAM traffic is BELOW the algorithmic bytes, i.e. no re-reads.
+TRAFFIC_CONV1 = 7287808
 
 
 def peaks():
