@@ -151,7 +151,12 @@ _SIGS = {
                                c_void_p, c_size_t, c_void_p], c_int),
     "b2rl_encoder_layer_forward": ([POINTER(NetDesc), c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                     c_size_t, c_int, c_void_p], c_int),
+    "b2rl_encoder_layer_wgrad": ([POINTER(NetDesc), c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                  c_size_t, c_void_p], c_int),
+    "b2rl_encoder_layer_dgrad": ([POINTER(NetDesc), c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_size_t,
+                                  c_void_p], c_int),
     "b2rl_launch_count": ([], ctypes.c_ulonglong),
+    "b2rl_conv_path_count": ([ctypes.c_int], ctypes.c_ulonglong),
     "b2rl_rainbow_loss": ([POINTER(NetDesc), POINTER(LearnCfg), POINTER(LearnBufs), c_void_p], c_int),
     "b2rl_rainbow_backward": ([POINTER(NetDesc), POINTER(LearnCfg), POINTER(LearnBufs), c_void_p], c_int),
     "b2rl_optim_step": ([POINTER(NetDesc), POINTER(LearnCfg), POINTER(LearnBufs), c_void_p], c_int),

@@ -28,6 +28,7 @@ void set_error(const char *fmt, ...);
         }                                                                                \
     } while (0)
 
+extern unsigned long long g_conv_path[3];  // forward convolutions per path (b2rl_conv_path_count)
 extern unsigned long long g_launches;   // kernels launched by this library (bench.py's gpu_launches)
 #define B2RL_LAUNCH_CHECK()                 \
     do {                                    \

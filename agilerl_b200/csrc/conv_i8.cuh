@@ -453,6 +453,7 @@ static int launch_conv_fwd_i8(const b2rl_layer &l, bool normalize, float low, fl
         { const int rca = ensure_big_smem(kern); if (rca != B2RL_OK) return rca; }
         kern<<<grid, kI8ThreadsP, smem, s>>>(p);
         B2RL_LAUNCH_CHECK();
+        ++g_conv_path[1];
         return B2RL_OK;
     };
     const int cpt = k_pad / 32;

@@ -612,6 +612,7 @@ static int launch_conv_fwd_tc(const b2rl_layer &l, const Operand &A, const float
         { const int rca = ensure_big_smem(kern); if (rca != B2RL_OK) return rca; }
         kern<<<grid, kTcFwdThreads, smem, s>>>(p);
         B2RL_LAUNCH_CHECK();
+        ++g_conv_path[0];
         return B2RL_OK;
     };
     switch (A.elem_kind()) {

@@ -20,6 +20,9 @@
 
 #include "conv_tc.cuh"
 #include "conv_i8.cuh"
+#include "conv_st.cuh"
+#include "conv_wst.cuh"
+#include "conv_dst.cuh"
 #include "head_fused.cuh"
 #include "gemm.cuh"
 #include <cstdlib>
@@ -115,7 +118,9 @@ static size_t max_partial_floats(const b2rl_net_desc &net, int64_t rows, int64_t
             size_t n = conv_tc_wsplit_floats(net.enc[i]);
             if (n > m) m = n;
             if (brows) { n = conv_wgrad_tc_partial_floats(net.enc[i], brows, sm_count()); if (n > m) m = n; }
+            if (brows) { n = conv_wgrad_st_partial_floats(net.enc[i], sm_count()); if (n > m) m = n; }
             if (brows && i > 0) { n = conv_dgrad_tc_scratch_floats(net.enc[i]); if (n > m) m = n; }
+            if (brows && i > 0) { n = conv_dst_scratch_floats(net.enc[i]); if (n > m) m = n; }
         }
     return m;
 }
@@ -451,7 +456,10 @@ static int layer_forward(const b2rl_net_desc &net, const b2rl_layer &l, const fl
             epi.pre_out = lb.pre ? lb.pre + row0 * oe : nullptr;
         }
         int rc = 1;
-        if (l.kind == B2RL_LAYER_CONV && tc_enabled() && l.ln == B2RL_LN_NONE)
+        // fp32 activations of an earlier layer: receptive fields staged in shared memory by the TMA unit (conv_st.cuh)
+        if (l.kind == B2RL_LAYER_CONV && tc_enabled() && l.ln == B2RL_LN_NONE && !first && lb.pre == nullptr)
+            rc = launch_conv_fwd_st(l, x_prev, W, bias, out_ptr, r, sc.partial, sc.floats, s, reuse_split);
+        if (rc == 1 && l.kind == B2RL_LAYER_CONV && tc_enabled() && l.ln == B2RL_LN_NONE)
             rc = launch_conv_fwd_tc(l, A, W, bias, out_ptr, lb.pre ? lb.pre + row0 * oe : nullptr, r, sc.partial, sc.floats,
                                     s, run > 0 || reuse_split);   // tcgen05 3xTF32 (pre-split weights live in the split-K scratch;
                                                    // the second observation chunk reuses the first one's split)
@@ -1055,7 +1063,9 @@ static int layer_backward(const b2rl_net_desc &net, const b2rl_layer &l, const f
             A.ones_row = Kc;
             Bm.ptr = g_out; Bm.row = map_stride(P); Bm.red = map_pixel(P, l.out_w, (int64_t)l.out_c * P, l.out_w, 1);
             rc = 1;
-            if (tc_enabled())   // tcgen05 3xTF32 (im2col operand MN-major, split over pixels)
+            if (tc_enabled())   // staged operands, MN-major im2col tile (conv_wst.cuh)
+                rc = launch_conv_wgrad_st(l, A, g_out, gw, gb, acc_w, B, scw->partial, scw->floats, sw);
+            if (rc == 1 && tc_enabled())   // tcgen05 3xTF32, gathered operands, split over pixels
                 rc = launch_conv_wgrad_tc(l, A, g_out, gw, gb, acc_w, B, scw->partial, scw->floats, sw);
             if (rc == 1) rc = dispatch_elem(A.elem_kind(), [&](auto ek) {
                 return launch_igemm<OpTraits<decltype(ek)::value, MAP_KERNEL, MAP_PIXEL, true, true>,
@@ -1091,6 +1101,8 @@ static int layer_backward(const b2rl_net_desc &net, const b2rl_layer &l, const f
             const int P = l.out_h * l.out_w, KK = l.ksize * l.ksize;
             const int Kc = l.in_c * KK;
             if (!accumulate_gin && tc_enabled()) {     // parity-class convolutions on tcgen05 (no atomics)
+                const int rc_st = launch_conv_dgrad_st(l, g_out, W, g_in, B, sc.partial, sc.floats, s);
+                if (rc_st != 1) return rc_st;
                 const int rc_tc = launch_conv_dgrad_tc(l, g_out, W, g_in, B, sc.partial, sc.floats, s);
                 if (rc_tc != 1) return rc_tc;
             }
@@ -1751,6 +1763,36 @@ int b2rl_encoder_layer_forward(const b2rl_net_desc *net_host, int layer, const f
     return layer_forward(*net_host, l, params + l.w_off, params + l.b_off, params,
                          layer == 0 ? nullptr : static_cast<const float *>(input), &ch, 1, rows, lb, sc,
                          as_stream(stream), reuse_split != 0);
+}
+
+int b2rl_encoder_layer_wgrad(const b2rl_net_desc *net_host, int layer, const void *input, const int64_t *row_idx,
+                             int64_t rows, const float *g_out, float *grads, void *workspace, size_t workspace_bytes,
+                             void *stream) {
+    B2RL_CHECK_ARG(net_host && input && g_out && grads, "NULL argument");
+    B2RL_CHECK_ARG(layer >= 0 && layer < net_host->n_enc, "layer out of range");
+    b2rl_layer l = net_host->enc[layer];
+    B2RL_CHECK_ARG(l.ln == B2RL_LN_NONE && !l.noisy, "profiling hook handles plain conv/linear layers");
+    l.act = B2RL_ACT_NONE;                                 // g_out is the gradient at the layer's pre-activation output
+    LayerBuf lb;
+    Scratch sc{static_cast<float *>(workspace), workspace_bytes / sizeof(float)};
+    ObsChunk ch{input, row_idx, rows};
+    return layer_backward(*net_host, l, nullptr, nullptr, layer == 0 ? nullptr : static_cast<const float *>(input),
+                          layer == 0 ? &ch : nullptr, lb, 0, const_cast<float *>(g_out), nullptr, false, grads, nullptr, 0, rows,
+                          sc, as_stream(stream));
+}
+
+int b2rl_encoder_layer_dgrad(const b2rl_net_desc *net_host, int layer, const float *params, const float *g_out, int64_t rows,
+                             float *g_in, void *workspace, size_t workspace_bytes, void *stream) {
+    B2RL_CHECK_ARG(net_host && params && g_out && g_in, "NULL argument");
+    B2RL_CHECK_ARG(layer >= 1 && layer < net_host->n_enc, "layer out of range (the first layer has no input gradient)");
+    b2rl_layer l = net_host->enc[layer];
+    B2RL_CHECK_ARG(l.kind == B2RL_LAYER_CONV && l.ln == B2RL_LN_NONE && !l.noisy, "profiling hook handles plain conv layers");
+    Scratch sc{static_cast<float *>(workspace), workspace_bytes / sizeof(float)};
+    cudaStream_t s = as_stream(stream);
+    int rc = launch_conv_dgrad_st(l, g_out, params + l.w_off, g_in, rows, sc.partial, sc.floats, s);
+    if (rc == 1) rc = launch_conv_dgrad_tc(l, g_out, params + l.w_off, g_in, rows, sc.partial, sc.floats, s);
+    if (rc == 1) { set_error("layer outside the tensor-core input-gradient kernels"); return B2RL_EUNSUPPORTED; }
+    return rc;
 }
 
 }  // extern "C"

@@ -14,6 +14,7 @@
 namespace b2rl {
 
 unsigned long long g_launches = 0;
+unsigned long long g_conv_path[3] = {0, 0, 0};
 static thread_local char g_err[512] = "";
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -416,6 +417,7 @@ extern "C" {
 
 int b2rl_version(void) { return 100; }
 unsigned long long b2rl_launch_count(void) { return b2rl::g_launches; }
+unsigned long long b2rl_conv_path_count(int path) { return (path >= 0 && path < 3) ? b2rl::g_conv_path[path] : 0ull; }
 const char *b2rl_last_error(void) { return b2rl::last_error(); }
 
 int b2rl_device_sm_count(int device, int *out_host) {

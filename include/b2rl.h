@@ -34,6 +34,10 @@ int b2rl_version(void);
 const char *b2rl_last_error(void);
 /* Number of CUDA kernels this library has launched in this process (bench.py: gpu_launches). */
 unsigned long long b2rl_launch_count(void);
+/* How many convolution launches took each forward path so far (tests assert the intended kernel ran, not a fallback):
+ * path 0 = gather tf32 kernel (conv_tc.cuh), 1 = int8 digit planes over uint8 frames (conv_i8.cuh),
+ * 2 = TMA-staged receptive fields (conv_st.cuh); anything else returns 0. */
+unsigned long long b2rl_conv_path_count(int path);
 /* Device properties the host side sizes grids with (SM count, etc.). */
 int b2rl_device_sm_count(int device, int *out_host);
 
@@ -279,6 +283,18 @@ int b2rl_debug_read(long long *out_host, int n);
 int b2rl_encoder_layer_forward(const b2rl_net_desc *net_host, int layer, const float *params,
                                const void *input, const int64_t *row_idx, int64_t rows, float *out,
                                void *workspace, size_t workspace_bytes, int reuse_split, void *stream);
+
+/* Test / profiling hook: weight and bias gradient of encoder layer `layer` alone.  g_out [rows, out...] is the gradient at the
+ * layer's pre-activation output; input as in b2rl_encoder_layer_forward; the gradients are written (not accumulated) at the
+ * layer's w_off / b_off of the flat buffer `grads` [n_params]. */
+int b2rl_encoder_layer_wgrad(const b2rl_net_desc *net_host, int layer, const void *input, const int64_t *row_idx,
+                             int64_t rows, const float *g_out, float *grads, void *workspace, size_t workspace_bytes,
+                             void *stream);
+
+/* Test / profiling hook: input gradient of convolutional encoder layer `layer` >= 1 alone: g_in [rows, in_c, in_h, in_w]
+ * (overwritten) from g_out, the gradient at the layer's pre-activation output. */
+int b2rl_encoder_layer_dgrad(const b2rl_net_desc *net_host, int layer, const float *params, const float *g_out, int64_t rows,
+                             float *g_in, void *workspace, size_t workspace_bytes, void *stream);
 
 /* Scalars of one learn step (doubles are the Python floats of the reference, rounded to f32
  * inside the kernels exactly where torch rounds them). */

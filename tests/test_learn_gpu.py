@@ -442,3 +442,153 @@ def test_first_layer_int8_digit_conv_matches_float64(cin, hw, k, s, cout, rows):
     assert err <= 2e-6 * max(1.0, ref.abs().max().item()), err
     # low-magnitude channel: relative accuracy is kept by the per-channel scale
     assert (out.cpu().double()[:, 0] - ref[:, 0]).abs().max().item() <= 2e-6 * max(1e-3, ref[:, 0].abs().max().item())
+
+
+@pytest.mark.parametrize("obs_hw,c0,k0,s0,cout,k,s,rows,staged", [
+    (84, 32, 8, 4, 32, 4, 2, 256, True),     # the north-star second layer at the benchmark batch: 296 tiles of 71 pixels
+    (84, 32, 8, 4, 32, 4, 2, 512, True),     # online pass over [next_obs | obs]: four tiles per CTA, slab refilled per channel
+    (84, 32, 8, 4, 32, 4, 2, 1, True),       # one image: fewer tiles than CTAs
+    (84, 32, 8, 4, 32, 4, 2, 37, True),      # ragged last tile
+    (34, 8, 4, 2, 16, 8, 2, 9, True),        # k8: four k-blocks per channel, two 4-tap chunks per kernel row
+    (50, 16, 4, 2, 48, 4, 4, 5, True),       # stride 4 (16-byte aligned taps), Cout 48
+    (26, 2, 4, 2, 8, 4, 2, 300, True),       # K = 32: two k-blocks, one weight group; tiles span several 5x5 images
+    (44, 4, 4, 2, 8, 4, 2, 3, False),        # input width 21: rows not 16-byte multiples -> gather kernel
+])
+def test_inner_conv_layer_staged_matches_float64(obs_hw, c0, k0, s0, cout, k, s, rows, staged):
+    """conv_fwd_st_kernel (receptive fields bulk-copied into shared memory, 3xTF32 on tcgen05) through the layer hook,
+    against a float64 convolution: <= 1e-5 of the output scale (tcgen05 accumulates in fp32 with truncation, K/8 k-steps of
+    three products each: a bias of up to ~2^-24 of the running sum per accumulation, the same for the gather kernel);
+    the path counter proves which kernel ran."""
+    import ctypes
+    from agilerl_b200 import _lib
+    from agilerl_b200.networks.spec import FlatLayout, rainbow_spec
+    g = torch.Generator().manual_seed(obs_hw * 100 + cout + rows)
+    spec = rainbow_spec((4, obs_hw, obs_hw), 3, channel_size=(c0, cout), kernel_size=(k0, k), stride_size=(s0, s),
+                        latent_dim=16, hidden_size=(16,), obs_low=0.0, obs_high=255.0, obs_u8=True)
+    layout = FlatLayout(spec)
+    desc = layout.desc
+    L = desc.enc[1]
+    hw = (obs_hw - k0) // s0 + 1
+    assert (L.in_c, L.in_h, L.in_w) == (c0, hw, hw)
+    params = torch.zeros(layout.n_params)
+    w = torch.randn(cout, c0, k, k, generator=g) * (1.0 / (c0 * k * k) ** 0.5)
+    b = torch.randn(cout, generator=g) * 0.1
+    params[L.w_off:L.w_off + w.numel()] = w.reshape(-1)
+    params[L.b_off:L.b_off + cout] = b
+    x = torch.randn(rows, c0, hw, hw, generator=g).relu()            # post-ReLU activations of the layer before
+    x[0, 0, 0, :4] = torch.tensor([1e-3, 1.0, 30.0, 3.0])             # mixed magnitudes inside one 4-tap chunk
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), b.double(), stride=s).relu()
+    out = torch.full(ref.shape, float("nan"), dtype=torch.float32, device="cuda")
+    ws = torch.empty(16 << 20, dtype=torch.uint8, device="cuda")
+    pd, xd = params.cuda(), x.cuda()
+    lib = _lib.load()
+    n_st, n_tc = lib.b2rl_conv_path_count(2), lib.b2rl_conv_path_count(0)
+    _lib.check(lib.b2rl_encoder_layer_forward(ctypes.byref(desc), 1, pd.data_ptr(), xd.data_ptr(), None, rows,
+                                              out.data_ptr(), ws.data_ptr(), ws.numel(), 0, _lib.stream_ptr(torch.device("cuda:0"))))
+    torch.cuda.synchronize()
+    assert lib.b2rl_conv_path_count(2) - n_st == (1 if staged else 0)
+    assert lib.b2rl_conv_path_count(0) - n_tc == (0 if staged else 1)
+    got = out.cpu().double()
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs().max().item()
+    assert err <= 1e-5 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("first,obs_hw,c0,k0,s0,cout,k,s,rows,staged", [
+    (False, 84, 32, 8, 4, 32, 4, 2, 256, True),   # north-star second layer: K = 512 taps (4 tap tiles), 81 pixels per image
+    (False, 84, 32, 8, 4, 32, 4, 2, 37, True),    # ragged last tile, fewer tiles than CTAs
+    (True, 84, 32, 8, 4, 32, 4, 2, 256, True),    # north-star first layer: uint8 frames of gathered ring rows, exact operand
+    (True, 84, 32, 8, 4, 32, 4, 2, 5, True),
+    (False, 34, 8, 4, 2, 16, 8, 2, 9, True),      # k8 over fp32, Cout 16
+    (False, 50, 16, 4, 2, 48, 4, 4, 5, False),    # Cout 48: 128 G threads do not divide -> gather kernel
+    (False, 26, 2, 4, 2, 8, 4, 2, 300, True),     # K = 32: a quarter of one tap tile
+    (True, 36, 16, 4, 4, 8, 4, 2, 6, True),       # first layer k4 s4: K = 64
+])
+def test_conv_weight_gradient_staged_matches_float64(first, obs_hw, c0, k0, s0, cout, k, s, rows, staged):
+    """conv_wgrad_st_kernel (MN-major im2col tile, staged operands) through b2rl_rainbow_backward's layer step is exercised
+    by the learn tests; here the layer's dW / db alone against float64 autograd, both operand kinds."""
+    import ctypes
+    from agilerl_b200 import _lib
+    from agilerl_b200.networks.spec import FlatLayout, rainbow_spec
+    g = torch.Generator().manual_seed(obs_hw * 7 + cout + rows + int(first))
+    spec = rainbow_spec((4, obs_hw, obs_hw), 3, channel_size=(c0, cout), kernel_size=(k0, k), stride_size=(s0, s),
+                        latent_dim=16, hidden_size=(16,), obs_low=0.0, obs_high=255.0, obs_u8=True)
+    layout = FlatLayout(spec)
+    desc = layout.desc
+    li = 0 if first else 1
+    L = desc.enc[li]
+    if first:
+        ring = torch.randint(0, 256, (64, L.in_c, L.in_h, L.in_w), dtype=torch.uint8, generator=g)
+        idx = torch.randint(0, 64, (rows,), generator=g)
+        x64 = ring[idx].double() / 255.0
+        x_dev, idx_dev = ring.cuda(), idx.cuda()
+    else:
+        x = torch.randn(rows, L.in_c, L.in_h, L.in_w, generator=g).relu()
+        x64 = x.double()
+        x_dev, idx_dev = x.cuda(), None
+    gout = torch.randn(rows, L.out_c, L.out_h, L.out_w, generator=g) * 0.1
+    gout[:, 0] *= 1e-3
+    w64 = torch.zeros(L.out_c, L.in_c, L.ksize, L.ksize, dtype=torch.float64, requires_grad=True)
+    b64 = torch.zeros(L.out_c, dtype=torch.float64, requires_grad=True)
+    out = torch.nn.functional.conv2d(x64, w64, b64, stride=L.stride)
+    out.backward(gout.double())
+    grads = torch.full((layout.n_params,), float("nan"), dtype=torch.float32, device="cuda")
+    ws = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+    gdev = gout.cuda()
+    lib = _lib.load()
+    n_st = lib.b2rl_conv_path_count(2)
+    _lib.check(lib.b2rl_encoder_layer_wgrad(ctypes.byref(desc), li, x_dev.data_ptr(),
+                                            idx_dev.data_ptr() if idx_dev is not None else None, rows, gdev.data_ptr(),
+                                            grads.data_ptr(), ws.data_ptr(), ws.numel(),
+                                            _lib.stream_ptr(torch.device("cuda:0"))))
+    torch.cuda.synchronize()
+    assert lib.b2rl_conv_path_count(2) - n_st == (1 if staged else 0)
+    gh = grads.cpu().double()
+    got_w, got_b = gh[L.w_off:L.w_off + w64.numel()].reshape(w64.shape), gh[L.b_off:L.b_off + L.out_c]
+    assert torch.isfinite(got_w).all() and torch.isfinite(got_b).all()
+    sw, sb = max(w64.grad.abs().max().item(), 1e-6), max(b64.grad.abs().max().item(), 1e-6)
+    assert (got_w - w64.grad).abs().max().item() <= 5e-6 * sw, ((got_w - w64.grad).abs().max().item(), sw)
+    assert (got_b - b64.grad).abs().max().item() <= 5e-6 * sb
+    # the low-magnitude channel keeps its relative accuracy
+    s0_ = max(w64.grad[0].abs().max().item(), 1e-9)
+    assert (got_w[0] - w64.grad[0]).abs().max().item() <= 2e-5 * s0_
+
+
+@pytest.mark.parametrize("obs_hw,c0,k0,s0,cout,k,s,rows,staged", [
+    (84, 32, 8, 4, 32, 4, 2, 256, True),     # north-star second layer: 25 600 positions x (4 classes x 32 channels)
+    (84, 32, 8, 4, 32, 4, 2, 3, True),       # fewer tiles than CTAs
+    (84, 32, 8, 4, 32, 4, 2, 77, True),      # ragged
+    (50, 16, 4, 2, 8, 4, 2, 5, True),        # 24x24 input, 16 input channels (64 columns), 8 output channels (K = 32)
+    (42, 8, 4, 2, 16, 4, 2, 6, True),        # 20x20 -> 9x9, Cin 8 padded to 16
+    (34, 8, 4, 2, 16, 8, 2, 9, False),       # k8 s2: T = 4, per-class kernel
+])
+def test_conv_input_gradient_staged_matches_float64(obs_hw, c0, k0, s0, cout, k, s, rows, staged):
+    """conv_dgrad_st_kernel (the four parity classes as extra columns of one product) against float64 autograd."""
+    import ctypes
+    from agilerl_b200 import _lib
+    from agilerl_b200.networks.spec import FlatLayout, rainbow_spec
+    g = torch.Generator().manual_seed(obs_hw * 3 + cout + rows)
+    spec = rainbow_spec((4, obs_hw, obs_hw), 3, channel_size=(c0, cout), kernel_size=(k0, k), stride_size=(s0, s),
+                        latent_dim=16, hidden_size=(16,), obs_low=0.0, obs_high=255.0, obs_u8=True)
+    layout = FlatLayout(spec)
+    desc = layout.desc
+    L = desc.enc[1]
+    params = torch.zeros(layout.n_params)
+    w = torch.randn(cout, c0, k, k, generator=g) * (1.0 / (cout * k * k) ** 0.5)
+    params[L.w_off:L.w_off + w.numel()] = w.reshape(-1)
+    gout = torch.randn(rows, L.out_c, L.out_h, L.out_w, generator=g)
+    x64 = torch.zeros(rows, L.in_c, L.in_h, L.in_w, dtype=torch.float64, requires_grad=True)
+    torch.nn.functional.conv2d(x64, w.double(), None, stride=s).backward(gout.double())
+    gin = torch.full(x64.shape, float("nan"), dtype=torch.float32, device="cuda")
+    ws = torch.empty(16 << 20, dtype=torch.uint8, device="cuda")
+    pd, gd = params.cuda(), gout.cuda()
+    lib = _lib.load()
+    n_st = lib.b2rl_conv_path_count(2)
+    _lib.check(lib.b2rl_encoder_layer_dgrad(ctypes.byref(desc), 1, pd.data_ptr(), gd.data_ptr(), rows, gin.data_ptr(),
+                                            ws.data_ptr(), ws.numel(), _lib.stream_ptr(torch.device("cuda:0"))))
+    torch.cuda.synchronize()
+    assert lib.b2rl_conv_path_count(2) - n_st == (1 if staged else 0)
+    got = gin.cpu().double()
+    assert torch.isfinite(got).all()
+    err = (got - x64.grad).abs().max().item()
+    assert err <= 5e-6 * max(1.0, x64.grad.abs().max().item()), err
