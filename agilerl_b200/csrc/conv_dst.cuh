@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(kStThreads, 1) conv_dgrad_st_kernel(const Conv
 // dL/d(layer input) [rows, Cin, in_h, in_w] (overwritten).  returns B2RL_OK, or 1 when the layer is outside this kernel.
 static int launch_conv_dgrad_st(const b2rl_layer &l, const float *g, const float *W, float *g_in, int64_t rows, float *scratch,
                                 size_t scratch_cap, cudaStream_t s) {
-    if (!st_enabled()) return 1;
+    if (!st_enabled('d')) return 1;
     if (l.ksize != 4 || l.stride != 2 || l.in_w % 2 != 0) return 1;
     const int ncp = (l.in_c + 15) / 16 * 16, NT = 4 * ncp, k_pad = 4 * l.out_c;
     const int Yc = (l.in_h + 1) / 2, Xc = (l.in_w + 1) / 2, Pc = Yc * Xc, Pg = l.out_h * l.out_w;

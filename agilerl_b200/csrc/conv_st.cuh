@@ -80,8 +80,8 @@ __global__ void __launch_bounds__(kStThreads, 1) conv_fwd_st_kernel(const ConvSt
     uint64_t *acc_full = empty_a + kStStages;                                   // [2] accumulator complete
     uint64_t *acc_empty = acc_full + 2;                                         // [2] accumulator drained
     uint64_t *b_full = acc_empty + 2;                                           // [NBG] weight group landed
-    uint64_t *slab_full = b_full + kStMaxBGroups;                               // [Cin] channel rows of this tile landed
-    uint64_t *slab_empty = slab_full + kStMaxCin;                               // [Cin] channel released by the producers
+    uint64_t *slab_full = b_full + kStMaxBGroups;                               // [NBG] rows of a 64-tap channel group landed
+    uint64_t *slab_empty = slab_full + kStMaxCin;                               // [NBG] group released by the producers
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(slab_empty + kStMaxCin);
     const uint32_t lbo_a = (uint32_t)p.rows_p * 16, lbo_b = (uint32_t)p.n_pad * 2 * 16;
     const int my_tiles = ((int)blockIdx.x < p.n_tiles) ? (p.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -96,9 +96,10 @@ __global__ void __launch_bounds__(kStThreads, 1) conv_fwd_st_kernel(const ConvSt
             tc::mbar_init(&acc_empty[s], kStEpiWarps);
         }
         for (int g = 0; g < NBG; ++g) tc::mbar_init(&b_full[g], 1);
-        for (int c = 0; c < p.Cin; ++c) {
-            tc::mbar_init(&slab_full[c], 1);
-            tc::mbar_init(&slab_empty[c], (uint32_t)p.n_prod);
+        for (int g = 0; g < NBG; ++g) {
+            const int c_lo = (g * 4 * kStBK) / KK, c_end = ((g + 1) * 4 * kStBK + KK - 1) / KK;      // channels of the group
+            tc::mbar_init(&slab_full[g], (uint32_t)((c_end < p.Cin ? c_end : p.Cin) - c_lo));          // one arrival per channel copy lane
+            tc::mbar_init(&slab_empty[g], (uint32_t)p.n_prod);
         }
         tc::fence_barrier_init();
     }
@@ -135,14 +136,15 @@ __global__ void __launch_bounds__(kStThreads, 1) conv_fwd_st_kernel(const ConvSt
                 rows_tot += n_in;
             }
             for (int c = lane; c < p.Cin; c += 32) {
-                if (i > 0) tc::mbar_wait(&slab_empty[c], (uint32_t)((i - 1) & 1));
-                tc::mbar_expect_tx(&slab_full[c], (uint32_t)rows_tot * row_bytes);
+                const int grp = (c * KK) / (4 * kStBK);                   // 64-tap group this channel belongs to
+                if (i > 0) tc::mbar_wait(&slab_empty[grp], (uint32_t)((i - 1) & 1));
+                tc::mbar_expect_tx(&slab_full[grp], (uint32_t)rows_tot * row_bytes);
                 uint32_t dst = slab_s + (uint32_t)c * chan_stride;
                 for (int b = b_first; b <= b_last; ++b) {
                     int oy_lo, n_in;
                     st_segment(b, m0, m1, p.P, p.OW, p.S, KS, oy_lo, n_in);
                     const float *src = p.x + (((int64_t)b * p.Cin + c) * p.H + (int64_t)oy_lo * p.S) * p.W;
-                    tc::bulk_g2s(dst, src, (uint32_t)n_in * row_bytes, &slab_full[c]);
+                    tc::bulk_g2s(dst, src, (uint32_t)n_in * row_bytes, &slab_full[grp]);
                     dst += (uint32_t)n_in * row_bytes;
                 }
             }
@@ -205,29 +207,38 @@ __global__ void __launch_bounds__(kStThreads, 1) conv_fwd_st_kernel(const ConvSt
                 }
                 const uint32_t src_row = slab_s + (uint32_t)(rowbase + (oy - oy_lo) * p.S) * row_bytes + (uint32_t)(ox * p.S) * 4u;
                 const uint32_t tph = (uint32_t)(i & 1);
-                for (int kb = 0; kb < KB; ++kb) {
-                    int c, ky, kx0;
-                    if (KS == 4) { c = kb; ky = q; kx0 = 0; }
-                    else { c = kb >> 2; ky = ((kb & 3) << 1) + (q >> 1); kx0 = (q & 1) * 4; }
-                    if ((kb * kStBK) % KK == 0) tc::mbar_wait(&slab_full[c], tph);
-                    const uint32_t addr = src_row + (uint32_t)c * chan_stride + (uint32_t)ky * row_bytes + (uint32_t)kx0 * 4u;
-                    float v[4];
-                    tc::lds64(addr, v[0], v[1]);
-                    tc::lds64(addr + 8u, v[2], v[3]);
-                    float hi[4], lo[4];
+                for (int g = 0; g < NBG; ++g) {
+                    tc::mbar_wait(&slab_full[g], tph);                     // one poll per 64 taps
+                    const int nk = KB - 4 * g < 4 ? KB - 4 * g : 4;
+                    // all loads of the group first: their latency overlaps the previous k-block's fence
+                    float v[4][4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) { hi[j] = tc::tf32_rn(v[j]); lo[j] = v[j] - hi[j]; }
-                    tc::mbar_wait(&empty_a[stage], sph);
-                    const uint32_t dst = a_s + (uint32_t)stage * a_stage + dst_off;
-                    tc::sts128(dst, hi[0], hi[1], hi[2], hi[3]);
-                    tc::sts128(dst + a_part, lo[0], lo[1], lo[2], lo[3]);
-                    tc::fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        tc::mbar_arrive(&full_a[stage]);
-                        if (((kb + 1) * kStBK) % KK == 0) tc::mbar_arrive(&slab_empty[c]);
+                    for (int kk = 0; kk < 4; ++kk) {
+                        if (kk >= nk) break;
+                        const int kb = 4 * g + kk;
+                        int c, ky, kx0;
+                        if (KS == 4) { c = kb; ky = q; kx0 = 0; }
+                        else { c = kb >> 2; ky = ((kb & 3) << 1) + (q >> 1); kx0 = (q & 1) * 4; }
+                        const uint32_t addr = src_row + (uint32_t)c * chan_stride + (uint32_t)ky * row_bytes + (uint32_t)kx0 * 4u;
+                        tc::lds64(addr, v[kk][0], v[kk][1]);
+                        tc::lds64(addr + 8u, v[kk][2], v[kk][3]);
                     }
-                    if (++stage == kStStages) { stage = 0; sph ^= 1u; }
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        if (kk >= nk) break;
+                        float hi[4], lo[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { hi[j] = tc::tf32_rn_fast(v[kk][j]); lo[j] = v[kk][j] - hi[j]; }
+                        if (!tc::mbar_test(&empty_a[stage], sph)) tc::mbar_wait(&empty_a[stage], sph);
+                        const uint32_t dst = a_s + (uint32_t)stage * a_stage + dst_off;
+                        tc::sts128(dst, hi[0], hi[1], hi[2], hi[3]);
+                        tc::sts128(dst + a_part, lo[0], lo[1], lo[2], lo[3]);
+                        tc::fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(&full_a[stage]);
+                        if (++stage == kStStages) { stage = 0; sph ^= 1u; }
+                    }
+                    if (lane == 0) tc::mbar_arrive(&slab_empty[g]);
                 }
             }
         }
@@ -288,20 +299,27 @@ __global__ void __launch_bounds__(kStThreads, 1) conv_fwd_st_kernel(const ConvSt
     if (warp == kStProdWarps) tc::tmem_dealloc(tmem_d, tmem_cols);
 }
 
-static bool st_enabled() {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("B2RL_DISABLE_ST");
-        v = (e && e[0] == '1') ? 0 : 1;
+// B2RL_ST selects which layers' passes take the staged kernels: a string of the letters f (forward), w (weight gradient),
+// d (input gradient); default "d" — measured on B200 at the benchmark shapes the staged input gradient is 2.3x faster than
+// the per-class gather kernel, while the staged forward / weight-gradient kernels (16-tap stages: one mbarrier round trip
+// and one proxy fence per 4 taps of a row) are still slower than the gather kernels they would replace.
+static int &st_mask() {
+    static int mask = -1;
+    if (mask < 0) {
+        const char *e = getenv("B2RL_ST");
+        if (!e) e = "d";
+        mask = 0;
+        for (; *e; ++e) mask |= (*e == 'f') ? 1 : (*e == 'w') ? 2 : (*e == 'd') ? 4 : 0;
     }
-    return v == 1;
+    return mask;
 }
+static bool st_enabled(char which) { return (st_mask() & (which == 'f' ? 1 : which == 'w' ? 2 : 4)) != 0; }
 
 // returns B2RL_OK, or 1 when the layer is outside what this kernel handles (caller falls back to conv_tc.cuh's gather kernel).
 // wsplit as in launch_conv_fwd_tc (same split layout, so the two paths may share it).
 static int launch_conv_fwd_st(const b2rl_layer &l, const float *x, const float *W, const float *bias, float *out, int64_t rows,
                               float *wsplit, size_t wsplit_cap, cudaStream_t s, bool reuse_split = false) {
-    if (!st_enabled()) return 1;
+    if (!st_enabled('f')) return 1;
     const int KS = l.ksize, KK = KS * KS, K = l.in_c * KK, P = l.out_h * l.out_w;
     const int n_pad = (l.out_c + 15) / 16 * 16, k_pad = (K + kTcBK - 1) / kTcBK * kTcBK;
     if (!(KS == 4 || KS == 8) || K != k_pad || n_pad > 64 || l.in_c > kStMaxCin || k_pad / kStBK > 4 * kStMaxBGroups) return 1;

@@ -411,7 +411,7 @@ static inline size_t conv_wgrad_st_partial_floats(const b2rl_layer &l, int sms) 
 // returns B2RL_OK, or 1 when the layer is outside what this kernel handles (caller: conv_tc.cuh's wgrad kernel)
 static int launch_conv_wgrad_st(const b2rl_layer &l, const Operand &X, const float *g, float *dw, float *db, int accumulate,
                                 int64_t rows, float *partial, size_t partial_cap, cudaStream_t s) {
-    if (!st_enabled()) return 1;
+    if (!st_enabled('w')) return 1;
     const int KS = l.ksize, KK = KS * KS, Kc = l.in_c * KK, P = l.out_h * l.out_w;
     const int n_pad = (l.out_c + 15) / 16 * 16, sms = sm_count();
     const bool u8 = X.u8;

@@ -1765,6 +1765,12 @@ int b2rl_encoder_layer_forward(const b2rl_net_desc *net_host, int layer, const f
                          as_stream(stream), reuse_split != 0);
 }
 
+int b2rl_conv_staged_paths(int mask) {
+    const int prev = st_mask();
+    if (mask >= 0) st_mask() = mask & 7;
+    return prev;
+}
+
 int b2rl_encoder_layer_wgrad(const b2rl_net_desc *net_host, int layer, const void *input, const int64_t *row_idx,
                              int64_t rows, const float *g_out, float *grads, void *workspace, size_t workspace_bytes,
                              void *stream) {

@@ -38,6 +38,10 @@ unsigned long long b2rl_launch_count(void);
  * path 0 = gather tf32 kernel (conv_tc.cuh), 1 = int8 digit planes over uint8 frames (conv_i8.cuh),
  * 2 = TMA-staged receptive fields (conv_st.cuh); anything else returns 0. */
 unsigned long long b2rl_conv_path_count(int path);
+/* Which convolution passes take the TMA-staged kernels (conv_st / conv_wst / conv_dst): bit 0 forward, bit 1 weight
+ * gradient, bit 2 input gradient.  mask >= 0 sets it, mask < 0 only queries; returns the previous mask.  The default comes
+ * from the environment variable B2RL_ST (letters f, w, d; "d" when unset). */
+int b2rl_conv_staged_paths(int mask);
 /* Device properties the host side sizes grids with (SM count, etc.). */
 int b2rl_device_sm_count(int device, int *out_host);
 

@@ -483,9 +483,13 @@ def test_inner_conv_layer_staged_matches_float64(obs_hw, c0, k0, s0, cout, k, s,
     pd, xd = params.cuda(), x.cuda()
     lib = _lib.load()
     n_st, n_tc = lib.b2rl_conv_path_count(2), lib.b2rl_conv_path_count(0)
-    _lib.check(lib.b2rl_encoder_layer_forward(ctypes.byref(desc), 1, pd.data_ptr(), xd.data_ptr(), None, rows,
-                                              out.data_ptr(), ws.data_ptr(), ws.numel(), 0, _lib.stream_ptr(torch.device("cuda:0"))))
-    torch.cuda.synchronize()
+    prev = lib.b2rl_conv_staged_paths(7)
+    try:
+        _lib.check(lib.b2rl_encoder_layer_forward(ctypes.byref(desc), 1, pd.data_ptr(), xd.data_ptr(), None, rows,
+                                                  out.data_ptr(), ws.data_ptr(), ws.numel(), 0, _lib.stream_ptr(torch.device("cuda:0"))))
+        torch.cuda.synchronize()
+    finally:
+        lib.b2rl_conv_staged_paths(prev)
     assert lib.b2rl_conv_path_count(2) - n_st == (1 if staged else 0)
     assert lib.b2rl_conv_path_count(0) - n_tc == (0 if staged else 1)
     got = out.cpu().double()
@@ -537,11 +541,15 @@ def test_conv_weight_gradient_staged_matches_float64(first, obs_hw, c0, k0, s0, 
     gdev = gout.cuda()
     lib = _lib.load()
     n_st = lib.b2rl_conv_path_count(2)
-    _lib.check(lib.b2rl_encoder_layer_wgrad(ctypes.byref(desc), li, x_dev.data_ptr(),
-                                            idx_dev.data_ptr() if idx_dev is not None else None, rows, gdev.data_ptr(),
-                                            grads.data_ptr(), ws.data_ptr(), ws.numel(),
-                                            _lib.stream_ptr(torch.device("cuda:0"))))
-    torch.cuda.synchronize()
+    prev = lib.b2rl_conv_staged_paths(7)
+    try:
+        _lib.check(lib.b2rl_encoder_layer_wgrad(ctypes.byref(desc), li, x_dev.data_ptr(),
+                                                idx_dev.data_ptr() if idx_dev is not None else None, rows, gdev.data_ptr(),
+                                                grads.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                _lib.stream_ptr(torch.device("cuda:0"))))
+        torch.cuda.synchronize()
+    finally:
+        lib.b2rl_conv_staged_paths(prev)
     assert lib.b2rl_conv_path_count(2) - n_st == (1 if staged else 0)
     gh = grads.cpu().double()
     got_w, got_b = gh[L.w_off:L.w_off + w64.numel()].reshape(w64.shape), gh[L.b_off:L.b_off + L.out_c]
@@ -584,9 +592,13 @@ def test_conv_input_gradient_staged_matches_float64(obs_hw, c0, k0, s0, cout, k,
     pd, gd = params.cuda(), gout.cuda()
     lib = _lib.load()
     n_st = lib.b2rl_conv_path_count(2)
-    _lib.check(lib.b2rl_encoder_layer_dgrad(ctypes.byref(desc), 1, pd.data_ptr(), gd.data_ptr(), rows, gin.data_ptr(),
-                                            ws.data_ptr(), ws.numel(), _lib.stream_ptr(torch.device("cuda:0"))))
-    torch.cuda.synchronize()
+    prev = lib.b2rl_conv_staged_paths(7)
+    try:
+        _lib.check(lib.b2rl_encoder_layer_dgrad(ctypes.byref(desc), 1, pd.data_ptr(), gd.data_ptr(), rows, gin.data_ptr(),
+                                                ws.data_ptr(), ws.numel(), _lib.stream_ptr(torch.device("cuda:0"))))
+        torch.cuda.synchronize()
+    finally:
+        lib.b2rl_conv_staged_paths(prev)
     assert lib.b2rl_conv_path_count(2) - n_st == (1 if staged else 0)
     got = gin.cpu().double()
     assert torch.isfinite(got).all()
