@@ -21,6 +21,8 @@
 namespace b2rl {
 
 constexpr int kDsMaxSeg = 4;
+constexpr int kDsEpiWarps = 8;                                   // the epilogue moves 4x the columns of the forward kernel's
+constexpr int kDsThreads = (kStProdWarps + 2 + kDsEpiWarps) * 32;
 
 struct ConvDstParams {
     const float *g;              // [rows, Cout, OH, OW]
@@ -62,7 +64,7 @@ static inline size_t conv_dst_smem_bytes(int NT, int k_pad, int rows_p, int nseg
            8 * (2 * kStStages + 4 + kStMaxBGroups + 4) + 16 + 128;
 }
 
-__global__ void __launch_bounds__(kStThreads, 1) conv_dgrad_st_kernel(const ConvDstParams p) {
+__global__ void __launch_bounds__(kDsThreads, 1) conv_dgrad_st_kernel(const ConvDstParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int KB = p.k_pad / kStBK, NBG = (KB + 3) >> 2;
@@ -92,7 +94,7 @@ __global__ void __launch_bounds__(kStThreads, 1) conv_dgrad_st_kernel(const Conv
         }
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(&acc_full[s], 1);
-            tc::mbar_init(&acc_empty[s], kStEpiWarps);
+            tc::mbar_init(&acc_empty[s], kDsEpiWarps);
             tc::mbar_init(&slab_full[s], 1);
             tc::mbar_init(&slab_empty[s], (uint32_t)p.n_prod);
         }
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(kStThreads, 1) conv_dgrad_st_kernel(const Conv
                     v[3] = m11 ? __uint_as_float(tc::lds32(addr + ow4 + 4u)) : 0.f;
                     float hi[4], lo[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) { hi[j] = tc::tf32_rn(v[j]); lo[j] = v[j] - hi[j]; }
+                    for (int j = 0; j < 4; ++j) { hi[j] = tc::tf32_rn_fast(v[j]); lo[j] = v[j] - hi[j]; }
                     tc::mbar_wait(&empty_a[stage], sph);
                     const uint32_t dst = a_s + (uint32_t)stage * a_stage + dst_off;
                     tc::sts128(dst, hi[0], hi[1], hi[2], hi[3]);
@@ -215,7 +217,7 @@ __global__ void __launch_bounds__(kStThreads, 1) conv_dgrad_st_kernel(const Conv
         }
     } else {
         // ================================ epilogue warps ================================
-        const int q = warp & 3;
+        const int q = warp & 3, chalf = (warp - (kStProdWarps + 2)) >> 2;       // TMEM lane quarter, half of the channel groups
         const int64_t plane = (int64_t)p.IH * p.IW;
         for (int i = 0; i < my_tiles; ++i) {
             int m0, m1;
@@ -231,7 +233,7 @@ __global__ void __launch_bounds__(kStThreads, 1) conv_dgrad_st_kernel(const Conv
             const bool warp_has_rows = m0 + q * 32 < m1;
             const bool pair_ok = 2 * xx + 1 < p.IW;
             float *o_base = p.dx + (int64_t)b * p.Cin * plane + (int64_t)(2 * yy) * p.IW + 2 * xx;
-            for (int c0 = 0; c0 < p.ncp && warp_has_rows; c0 += 8) {
+            for (int c0 = chalf * 8; c0 < p.ncp && warp_has_rows; c0 += 16) {
                 float v[4][8];
 #pragma unroll
                 for (int cls = 0; cls < 4; ++cls) {
@@ -242,7 +244,7 @@ __global__ void __launch_bounds__(kStThreads, 1) conv_dgrad_st_kernel(const Conv
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[cls][j] = __uint_as_float(rh[j]) + __uint_as_float(rl[j]);
                 }
-                if (c0 + 8 >= p.ncp) {
+                if (c0 + 16 >= p.ncp) {
                     tc::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
@@ -321,7 +323,7 @@ static int launch_conv_dgrad_st(const b2rl_layer &l, const float *g, const float
         attr_set = true;
     }
     const int grid = n_tiles < sms ? n_tiles : sms;
-    conv_dgrad_st_kernel<<<grid, kStThreads, smem, s>>>(p);
+    conv_dgrad_st_kernel<<<grid, kDsThreads, smem, s>>>(p);
     B2RL_LAUNCH_CHECK();
     ++g_conv_path[2];
     return B2RL_OK;

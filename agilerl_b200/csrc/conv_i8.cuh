@@ -55,10 +55,27 @@ struct ConvI8Params {
     int P, OW, sy, sx;         // output pixels per image, output width, in-row stride (s*W), in-col stride (s)
     int act;
     int Cin, HW, W;            // input channels, plane size, row pitch (the gather walks kernel rows with running pointers)
+    // staged mode (slab != 0): the rows of every channel a tile needs are bulk-copied into shared memory by a copy warp
+    // (16-byte aligned supersets, three tiles in flight) and the gather warps read them with LDS
+    int slab, KS, S;
+    int nseg_max;              // images a tile may touch
+    uint32_t chan_bytes;       // slab bytes per channel (all segments of a tile)
 };
 
-static inline size_t conv_i8_smem_bytes(int n_pad, int k_pad, int nets_total) {
-    return 2 * (size_t)kTcBM * k_pad + (size_t)nets_total * 4 * n_pad * k_pad + 2 * (size_t)nets_total * n_pad * 4 + 256 + 1024;
+constexpr int kI8Slabs = 3;
+static inline size_t conv_i8_smem_bytes(int n_pad, int k_pad, int nets_total, int Cin = 0, uint32_t chan_bytes = 0) {
+    return 2 * (size_t)kTcBM * k_pad + (size_t)nets_total * 4 * n_pad * k_pad + 2 * (size_t)nets_total * n_pad * 4 + 256 + 1024 +
+           (size_t)kI8Slabs * Cin * chan_bytes;
+}
+// image `bimg` of tile [m0, m1): first output row it needs and the byte range [st, en) of every channel plane
+__host__ __device__ __forceinline__ void i8_segment(int bimg, int m0, int m1, int P, int OW, int S, int KS, int W, int &oy_lo,
+                                                    uint32_t &st, uint32_t &en) {
+    const int p_lo = m0 - bimg * P > 0 ? m0 - bimg * P : 0;
+    const int p_hi = m1 - bimg * P < P ? m1 - bimg * P : P;
+    oy_lo = p_lo / OW;
+    const int n_in = ((p_hi - 1) / OW - oy_lo) * S + KS;
+    st = (uint32_t)(oy_lo * S * W);
+    en = st + (uint32_t)(n_in * W);
 }
 // scratch the launcher needs (bytes): digit planes + scales + low-correction + tap-group offsets
 static inline size_t conv_i8_scratch_bytes(int n_pad, int k_pad, int nets_total) {
@@ -157,7 +174,7 @@ __device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, u
 // The digit planes of every weight set are copied into shared memory ONCE per CTA.  KS = kernel size (4 or 8, so
 // a kernel row is one or two aligned 4-byte groups), CPT = 16-tap chunks per gather thread (k_pad / 32).
 constexpr int kI8GatherWarps = 8, kI8EpiWarps = 8;
-constexpr int kI8ThreadsP = (kI8GatherWarps + 1 + kI8EpiWarps) * 32;
+constexpr int kI8ThreadsP = (kI8GatherWarps + 1 + kI8EpiWarps + 1) * 32;      // + the slab copy warp (idle when slab == 0)
 
 template <int KS, int CPT>
 __global__ void __launch_bounds__(kI8ThreadsP, 1) conv_fwd_i8_kernel(const ConvI8Params p) {
@@ -178,6 +195,10 @@ __global__ void __launch_bounds__(kI8ThreadsP, 1) conv_fwd_i8_kernel(const ConvI
     uint64_t *acc_empty = full_a + 6;                                           // [2] accumulator drained (8 warp arrivals)
     uint64_t *full_b = full_a + 8;                                              // digit planes landed (tx count)
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(full_a + 9);
+    uint64_t *slab_full = full_a + 10;                                          // [kI8Slabs] rows of a tile landed (tx count)
+    uint64_t *slab_empty = slab_full + kI8Slabs;                                // [kI8Slabs] released by the 8 gather warps
+    const uint32_t slab_s = (bars_a + 8u * (10 + 2 * kI8Slabs) + 15u) & ~15u;
+    const uint32_t slab_buf = (uint32_t)p.Cin * p.chan_bytes;
     const uint32_t lbo_a = kTcBM * 16, lbo_b = (uint32_t)rows_b * 16;
     // tiles of this CTA: t = blockIdx.x + i * gridDim.x over [segment 0 tiles | segment 1 tiles]
     const int tiles0 = (p.seg[0].M + kTcBM - 1) / kTcBM;
@@ -193,6 +214,10 @@ __global__ void __launch_bounds__(kI8ThreadsP, 1) conv_fwd_i8_kernel(const ConvI
             tc::mbar_init(&acc_empty[s], kI8EpiWarps);
         }
         tc::mbar_init(full_b, 1);
+        for (int s = 0; s < kI8Slabs; ++s) {
+            tc::mbar_init(&slab_full[s], 1);
+            tc::mbar_init(&slab_empty[s], kI8GatherWarps);
+        }
         tc::fence_barrier_init();
     }
     uint32_t tmem_cols = 32;
@@ -252,7 +277,39 @@ __global__ void __launch_bounds__(kI8ThreadsP, 1) conv_fwd_i8_kernel(const ConvI
         auto issue = [&](int i, uint32_t (&raw)[CPT][4]) {
             const int t = (int)blockIdx.x + i * (int)gridDim.x;
             const ConvI8Seg &sg = t < tiles0 ? p.seg[0] : p.seg[1];
-            const int m = (t < tiles0 ? t : t - tiles0) * kTcBM + row;
+            const int m0 = (t < tiles0 ? t : t - tiles0) * kTcBM;
+            const int m = m0 + row;
+            if (p.slab) {
+                // ---- staged: this row's receptive field inside slab i % kI8Slabs
+                const int m1 = m0 + kTcBM < sg.M ? m0 + kTcBM : sg.M;
+                const int mm = m < m1 ? m : m1 - 1;                  // rows beyond the tile repeat its last one
+                const int b = mm / p.P, pix = mm - b * p.P;
+                const int oy = pix / p.OW, ox = pix - oy * p.OW;
+                uint32_t off = 0;
+                int oy_lo = 0;
+                for (int bb = m0 / p.P; bb <= b; ++bb) {
+                    uint32_t st, en;
+                    i8_segment(bb, m0, m1, p.P, p.OW, p.S, p.KS, p.W, oy_lo, st, en);
+                    if (bb < b) off += ((en + 15u) & ~15u) - (st & ~15u);
+                    else off += st & 15u;
+                }
+                const int buf = i % kI8Slabs;
+                uint32_t ptr = slab_s + (uint32_t)buf * slab_buf + (uint32_t)(half * (p.Cin / 2)) * p.chan_bytes + off +
+                               (uint32_t)((oy - oy_lo) * p.S * p.W + ox * p.S);
+                const uint32_t s_row = (uint32_t)p.W, s_chan = p.chan_bytes - (uint32_t)((KS - 1) * p.W);
+                tc::mbar_wait(&slab_full[buf], (uint32_t)((i / kI8Slabs) & 1));
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) {
+#pragma unroll
+                    for (int rr = 0; rr < 16 / KS; ++rr) {
+                        const int r = c * (16 / KS) + rr;
+#pragma unroll
+                        for (int gx = 0; gx < KS / 4; ++gx) raw[c][rr * (KS / 4) + gx] = tc::lds32(ptr + 4u * gx);
+                        ptr += (r % KS == KS - 1) ? s_chan : s_row;
+                    }
+                }
+                return;
+            }
             int64_t rowbase = sg.gather ? __ldg(sg.gather) * p.in_bstride : 0;     // rows beyond M read a valid address
             if (m < sg.M) {
                 const int b = m / p.P, pix = m - b * p.P;
@@ -282,7 +339,10 @@ __global__ void __launch_bounds__(kI8ThreadsP, 1) conv_fwd_i8_kernel(const ConvI
             for (int c = 0; c < CPT; ++c) tc::sts128u(dst + (uint32_t)c * lbo_a, raw[c][0], raw[c][1], raw[c][2], raw[c][3]);
             tc::fence_async_smem();              // generic-proxy smem writes -> visible to the async (tensor) proxy
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&full_a[s]);
+            if (lane == 0) {
+                tc::mbar_arrive(&full_a[s]);
+                if (p.slab) tc::mbar_arrive(&slab_empty[i % kI8Slabs]);      // this tile's slab has been read into registers
+            }
         };
         uint32_t ra[CPT][4], rb[CPT][4];
         if (my_tiles > 0) issue(0, ra);
@@ -291,6 +351,43 @@ __global__ void __launch_bounds__(kI8ThreadsP, 1) conv_fwd_i8_kernel(const ConvI
             store(i, ra);
             if (i + 2 < my_tiles) issue(i + 2, ra);
             if (i + 1 < my_tiles) store(i + 1, rb);
+        }
+    } else if (warp == kI8GatherWarps + 1 + kI8EpiWarps) {
+        // ================================ slab copy warp ================================
+        // lane = (image of the tile, channel): one bulk copy of the channel rows the tile touches
+        if (p.slab) {
+            for (int i = 0; i < my_tiles; ++i) {
+                const int t = (int)blockIdx.x + i * (int)gridDim.x;
+                const ConvI8Seg &sg = t < tiles0 ? p.seg[0] : p.seg[1];
+                const int m0 = (t < tiles0 ? t : t - tiles0) * kTcBM;
+                const int m1 = m0 + kTcBM < sg.M ? m0 + kTcBM : sg.M;
+                const int b_first = m0 / p.P, nseg = (m1 - 1) / p.P - b_first + 1;
+                const int buf = i % kI8Slabs;
+                if (i >= kI8Slabs) tc::mbar_wait(&slab_empty[buf], (uint32_t)((i / kI8Slabs - 1) & 1));
+                const int sgi = lane / p.Cin, c = lane - sgi * p.Cin;
+                uint32_t bytes = 0, dst_off = 0, a0 = 0;
+                if (sgi < nseg) {
+                    for (int bb = b_first; bb <= b_first + sgi; ++bb) {
+                        int oy_lo;
+                        uint32_t st, en;
+                        i8_segment(bb, m0, m1, p.P, p.OW, p.S, p.KS, p.W, oy_lo, st, en);
+                        a0 = st & ~15u;
+                        bytes = ((en + 15u) & ~15u) - a0;
+                        if (bb < b_first + sgi) dst_off += bytes;
+                    }
+                }
+                uint32_t total = bytes;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+                if (lane == 0) tc::mbar_expect_tx(&slab_full[buf], total);
+                __syncwarp();
+                if (sgi < nseg) {
+                    const int64_t bb = sg.gather ? __ldg(sg.gather + b_first + sgi) : (int64_t)(b_first + sgi);
+                    tc::bulk_g2s(slab_s + (uint32_t)buf * slab_buf + (uint32_t)c * p.chan_bytes + dst_off,
+                                 sg.x + bb * p.in_bstride + (int64_t)c * p.HW + a0, bytes, &slab_full[buf]);
+                }
+                __syncwarp();
+            }
         }
     } else {
         // ================================ epilogue warps ================================
@@ -446,7 +543,38 @@ static int launch_conv_fwd_i8(const b2rl_layer &l, bool normalize, float low, fl
     p.N = l.out_c; p.n_pad = n_pad; p.k_pad = k_pad; p.nets_total = nets_total;
     p.P = P; p.OW = l.out_w; p.sy = l.stride * l.in_w; p.sx = l.stride; p.act = l.act;
     p.Cin = l.in_c; p.HW = l.in_h * l.in_w; p.W = l.in_w;
-    const size_t smem = conv_i8_smem_bytes(n_pad, k_pad, nets_total);
+    // staged input, OFF by default (B2RL_I8_SLAB=1 turns it on): measured on B200 at B = 256 the bulk-copied slabs are
+    // slower than the register gather (16.3 us vs 14.6 us per launch) — the kernel is bound by its per-tile hand-offs,
+    // not by the gather's DRAM latency.  Needs planes and images 16-byte aligned, one copy lane per (image, channel).
+    p.slab = 0; p.KS = l.ksize; p.S = l.stride; p.nseg_max = 0; p.chan_bytes = 0;
+    {
+        static int want = -1;
+        if (want < 0) { const char *e = getenv("B2RL_I8_SLAB"); want = (e && e[0] == '1') ? 1 : 0; }
+        bool ok = want == 1 && (l.in_h * l.in_w) % 16 == 0;
+        int nseg_max = 0;
+        uint32_t chan_bytes = 0;
+        for (int i = 0; i < n_jobs && ok; ++i) {
+            if (reinterpret_cast<uintptr_t>(jobs[i].x) % 16 != 0) ok = false;
+            const int M = p.seg[i].M;
+            for (int m0 = 0; m0 < M; m0 += kTcBM) {
+                const int m1 = m0 + kTcBM < M ? m0 + kTcBM : M;
+                const int b_first = m0 / P, b_last = (m1 - 1) / P;
+                if (b_last - b_first + 1 > nseg_max) nseg_max = b_last - b_first + 1;
+                uint32_t tot = 0;
+                for (int b = b_first; b <= b_last; ++b) {
+                    int oy_lo;
+                    uint32_t st, en;
+                    i8_segment(b, m0, m1, P, l.out_w, l.stride, l.ksize, l.in_w, oy_lo, st, en);
+                    tot += ((en + 15u) & ~15u) - (st & ~15u);
+                }
+                if (tot > chan_bytes) chan_bytes = tot;
+            }
+        }
+        if (ok && nseg_max * l.in_c <= 32 && conv_i8_smem_bytes(n_pad, k_pad, nets_total, l.in_c, chan_bytes) <= 200 * 1024) {
+            p.slab = 1; p.nseg_max = nseg_max; p.chan_bytes = chan_bytes;
+        }
+    }
+    const size_t smem = conv_i8_smem_bytes(n_pad, k_pad, nets_total, p.slab ? l.in_c : 0, p.chan_bytes);
     const int grid = tiles < sm_count() ? tiles : sm_count();          // persistent: one CTA per SM walks its tiles
     if (grid <= 0) return B2RL_OK;
     auto launch = [&](auto kern) -> int {

@@ -40,6 +40,8 @@ struct ConvStParams {
     int R, rows_p, n_prod, n_tiles;
     int rtot_max;                // input rows per channel the slab holds
     int act;
+    int dbg;                     // timing experiments (B2RL_ST_DBG): 1 = producers do not wait for the slab, 2 = no slab copies at all,
+                                 // 4 = producers skip the proxy fence (results are garbage in every case)
 };
 
 // rows of image `bimg` a tile [m0, m1) of output pixels needs: first output row and number of input rows
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(kStThreads, 1) conv_fwd_st_kernel(const ConvSt
                 st_segment(b, m0, m1, p.P, p.OW, p.S, KS, oy_lo, n_in);
                 rows_tot += n_in;
             }
-            for (int c = lane; c < p.Cin; c += 32) {
+            for (int c = lane; c < p.Cin && !(p.dbg & 2); c += 32) {
                 const int grp = (c * KK) / (4 * kStBK);                   // 64-tap group this channel belongs to
                 if (i > 0) tc::mbar_wait(&slab_empty[grp], (uint32_t)((i - 1) & 1));
                 tc::mbar_expect_tx(&slab_full[grp], (uint32_t)rows_tot * row_bytes);
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(kStThreads, 1) conv_fwd_st_kernel(const ConvSt
             const uint32_t d_addr = tmem_d + (uint32_t)(acc * 2 * p.n_pad);
             for (int kb = 0; kb < KB; ++kb) {
                 if (i == 0 && (kb & 3) == 0) tc::mbar_wait(&b_full[kb >> 2], 0);
-                tc::mbar_wait(&full_a[stage], sph);
+                if (!(p.dbg & 8)) tc::mbar_wait(&full_a[stage], sph);
                 tc::tc_fence_after();
                 const uint32_t a_addr = a_s + (uint32_t)stage * a_stage;
                 const uint64_t dah0 = tc::make_desc(a_addr, lbo_a, 128), dal0 = tc::make_desc(a_addr + a_part, lbo_a, 128);
@@ -175,6 +177,7 @@ __global__ void __launch_bounds__(kStThreads, 1) conv_fwd_st_kernel(const ConvSt
                 if (tc::elect_one()) {
 #pragma unroll
                     for (int j = 0; j < kStBK / 8; ++j) {
+                        if (p.dbg & 16) break;
                         tc::mma_tf32(d_addr, dah0 + j * da_step, db0 + j * db_step, idesc2, (kb | j) ? 1u : 0u);
                         tc::mma_tf32(d_addr, dal0 + j * da_step, db0 + j * db_step, idesc1, 1u);
                     }
@@ -208,7 +211,7 @@ __global__ void __launch_bounds__(kStThreads, 1) conv_fwd_st_kernel(const ConvSt
                 const uint32_t src_row = slab_s + (uint32_t)(rowbase + (oy - oy_lo) * p.S) * row_bytes + (uint32_t)(ox * p.S) * 4u;
                 const uint32_t tph = (uint32_t)(i & 1);
                 for (int g = 0; g < NBG; ++g) {
-                    tc::mbar_wait(&slab_full[g], tph);                     // one poll per 64 taps
+                    if (!(p.dbg & 3)) tc::mbar_wait(&slab_full[g], tph);   // one poll per 64 taps
                     const int nk = KB - 4 * g < 4 ? KB - 4 * g : 4;
                     // all loads of the group first: their latency overlaps the previous k-block's fence
                     float v[4][4];
@@ -229,11 +232,11 @@ __global__ void __launch_bounds__(kStThreads, 1) conv_fwd_st_kernel(const ConvSt
                         float hi[4], lo[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) { hi[j] = tc::tf32_rn_fast(v[kk][j]); lo[j] = v[kk][j] - hi[j]; }
-                        if (!tc::mbar_test(&empty_a[stage], sph)) tc::mbar_wait(&empty_a[stage], sph);
+                        if (!(p.dbg & 8) && !tc::mbar_test(&empty_a[stage], sph)) tc::mbar_wait(&empty_a[stage], sph);
                         const uint32_t dst = a_s + (uint32_t)stage * a_stage + dst_off;
                         tc::sts128(dst, hi[0], hi[1], hi[2], hi[3]);
                         tc::sts128(dst + a_part, lo[0], lo[1], lo[2], lo[3]);
-                        tc::fence_async_smem();
+                        if (!(p.dbg & 4)) tc::fence_async_smem();
                         __syncwarp();
                         if (lane == 0) tc::mbar_arrive(&full_a[stage]);
                         if (++stage == kStStages) { stage = 0; sph ^= 1u; }
@@ -369,6 +372,7 @@ static int launch_conv_fwd_st(const b2rl_layer &l, const float *x, const float *
     p.P = P; p.OW = l.out_w; p.S = l.stride; p.Cin = l.in_c; p.H = l.in_h; p.W = l.in_w;
     p.R = R; p.rows_p = rows_p; p.n_prod = (rows_p / 32) * (kStBK / 4); p.n_tiles = n_tiles;
     p.rtot_max = rtot_max; p.act = l.act;
+    { const char *e = getenv("B2RL_ST_DBG"); p.dbg = e ? atoi(e) : 0; }
     const int grid = n_tiles < sms ? n_tiles : sms;
     auto launch = [&](auto kern) -> int {
         static bool attr_set[2] = {false, false};

@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(kTcFwdThreads) conv_fwd_tc_kernel(const ConvTc
                 else v = __uint_as_float(cur[kk]);
                 if (tail) v = (k0 + kk < p.K) ? v : 0.f;
                 if (EXACT_A) { hi[j] = v; lo[j] = 0.f; }
-                else { hi[j] = tc::tf32_rn(v); lo[j] = v - hi[j]; }
+                else { hi[j] = tc::tf32_rn_fast(v); lo[j] = v - hi[j]; }
             }
             tc::sts128(ah + (uint32_t)c * lbo_a, hi[0], hi[1], hi[2], hi[3]);
             if (!EXACT_A) tc::sts128(al + (uint32_t)c * lbo_a, lo[0], lo[1], lo[2], lo[3]);
@@ -916,7 +916,7 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_wgrad_tc_kernel(const Co
                     if (EXACT_A) {
                         asm volatile("st.shared.f32 [%0], %1;" ::"r"(a_hi(s) + o), "f"(v) : "memory");
                     } else {
-                        const float hi = tc::tf32_rn(v), lo = v - hi;
+                        const float hi = tc::tf32_rn_fast(v), lo = v - hi;
                         asm volatile("st.shared.f32 [%0], %1;" ::"r"(a_hi(s) + o), "f"(hi) : "memory");
                         asm volatile("st.shared.f32 [%0], %1;" ::"r"(a_lo(s) + o), "f"(lo) : "memory");
                     }
@@ -926,7 +926,7 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_wgrad_tc_kernel(const Co
             {
                 float hi[4], lo[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) { hi[j] = tc::tf32_rn(gv[j]); lo[j] = gv[j] - hi[j]; bsum += gv[j]; }
+                for (int j = 0; j < 4; ++j) { hi[j] = tc::tf32_rn_fast(gv[j]); lo[j] = gv[j] - hi[j]; bsum += gv[j]; }
                 const uint32_t o = (uint32_t)q * lbo_b + (uint32_t)(n >> 3) * 128 + (uint32_t)(n & 7) * 16;
                 if (n < p.n_pad) {          // n_pad may be 16: rows beyond it belong to the next K chunk
                     tc::sts128(b_hi(s) + o, hi[0], hi[1], hi[2], hi[3]);
@@ -939,7 +939,7 @@ __global__ void __launch_bounds__(kTcThreads + 32) conv_wgrad_tc_kernel(const Co
                     for (int j = 0; j < 4; ++j) {
                         const float v = (n2 < p.N && px0 + j < pix1) ? __ldg(p.g + ((int64_t)b * p.N + n2) * p.P + pp) : 0.f;
                         if (++pp == p.P) { pp = 0; ++b; }
-                        hi[j] = tc::tf32_rn(v); lo[j] = v - hi[j];
+                        hi[j] = tc::tf32_rn_fast(v); lo[j] = v - hi[j];
                     }
                     const uint32_t o2 = (uint32_t)q * lbo_b + (uint32_t)(n2 >> 3) * 128 + (uint32_t)(n2 & 7) * 16;
                     tc::sts128(b_hi(s) + o2, hi[0], hi[1], hi[2], hi[3]);

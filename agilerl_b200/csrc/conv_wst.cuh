@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_wgrad_st_kernel(const Conv
                         } else {
                             float hi[4], lo[4];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) { hi[j] = tc::tf32_rn(v[h][j]); lo[j] = v[h][j] - hi[j]; }
+                            for (int j = 0; j < 4; ++j) { hi[j] = tc::tf32_rn_fast(v[h][j]); lo[j] = v[h][j] - hi[j]; }
                             tc::sts128(d, hi[0], hi[1], hi[2], hi[3]);
                             tc::sts128(d + kWsAPart, lo[0], lo[1], lo[2], lo[3]);
                         }
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) conv_wgrad_st_kernel(const Conv
                 }
                 float h[4], l[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) { h[j] = tc::tf32_rn(v[j]); l[j] = v[j] - h[j]; bsum += v[j]; }
+                for (int j = 0; j < 4; ++j) { h[j] = tc::tf32_rn_fast(v[j]); l[j] = v[j] - h[j]; bsum += v[j]; }
                 const uint32_t o = gt_s + (uint32_t)buf * gt_buf + (uint32_t)pb * 2u * gt_part + (uint32_t)q * lbo_b +
                                    (uint32_t)(co >> 3) * 128u + (uint32_t)(co & 7) * 16u;
                 tc::sts128(o, h[0], h[1], h[2], h[3]);
