@@ -158,6 +158,7 @@ _SIGS = {
     "b2rl_launch_count": ([], ctypes.c_ulonglong),
     "b2rl_conv_path_count": ([ctypes.c_int], ctypes.c_ulonglong),
     "b2rl_conv_staged_paths": ([ctypes.c_int], ctypes.c_int),
+    "b2rl_rainbow_prep": ([POINTER(NetDesc), POINTER(LearnCfg), POINTER(LearnBufs), c_void_p], c_int),
     "b2rl_rainbow_loss": ([POINTER(NetDesc), POINTER(LearnCfg), POINTER(LearnBufs), c_void_p], c_int),
     "b2rl_rainbow_backward": ([POINTER(NetDesc), POINTER(LearnCfg), POINTER(LearnBufs), c_void_p], c_int),
     "b2rl_optim_step": ([POINTER(NetDesc), POINTER(LearnCfg), POINTER(LearnBufs), c_void_p], c_int),

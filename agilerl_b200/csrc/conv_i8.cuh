@@ -508,6 +508,25 @@ struct ConvI8Job {                 // one segment as the host describes it
     float *out[2];
 };
 
+// the digit planes + scales of `nets_total` weight sets into `scratch` (layout of launch_conv_fwd_i8, which may then be
+// called with reuse_digits = true on the same scratch)
+static int launch_weight_digits(const b2rl_layer &l, bool normalize, float low, float high, const float *const W[2], int nets_total,
+                                void *scratch, size_t scratch_bytes, cudaStream_t s) {
+    const int K = l.in_c * l.ksize * l.ksize;
+    const int n_pad = (l.out_c + 15) / 16 * 16, k_pad = (K + 31) / 32 * 32;
+    if (scratch == nullptr || conv_i8_scratch_bytes(n_pad, k_pad, nets_total) > scratch_bytes ||
+        reinterpret_cast<uintptr_t>(scratch) % 16 != 0)
+        return B2RL_EINVAL;
+    int8_t *wd = static_cast<int8_t *>(scratch);
+    float *scale = reinterpret_cast<float *>(wd + (size_t)nets_total * 4 * n_pad * k_pad);
+    const double inv_range = normalize ? 1.0 / ((double)high - (double)low) : 1.0;
+    weight_digits_kernel<<<dim3(n_pad, nets_total), 128, 0, s>>>(W[0], nets_total > 1 ? W[1] : W[0], l.out_c, K, n_pad, k_pad, nets_total,
+                                                                inv_range, normalize ? low : 0.f, wd, scale,
+                                                                scale + (size_t)nets_total * n_pad);
+    B2RL_LAUNCH_CHECK();
+    return B2RL_OK;
+}
+
 // scratch: conv_i8_scratch_bytes(...) bytes, 16-byte aligned.  W[net], bias[net]: fp32 parameters of each weight set.
 static int launch_conv_fwd_i8(const b2rl_layer &l, bool normalize, float low, float high, const float *const W[2],
                               const float *const bias[2], int nets_total, const ConvI8Job *jobs, int n_jobs, void *scratch,

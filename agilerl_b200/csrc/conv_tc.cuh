@@ -586,6 +586,20 @@ static inline size_t conv_tc_wsplit_floats(const b2rl_layer &l) {
     return (size_t)2 * n_pad * k_pad + k_pad + 4 * n_pad + 64;      // hi, lo, tap offsets (+ room for the int8 digit path's scales)
 }
 
+// tf32 hi/lo split (+ tap offsets) of one convolution's weights into `wsplit` — what launch_conv_fwd_tc / _st produce
+// themselves unless called with reuse_split
+static int launch_weight_split(const b2rl_layer &l, const float *W, float *wsplit, size_t wsplit_cap, cudaStream_t s) {
+    const int KK = l.ksize * l.ksize, K = l.in_c * KK;
+    const int n_pad = (l.out_c + 15) / 16 * 16, k_pad = (K + kTcBK - 1) / kTcBK * kTcBK;
+    if (wsplit == nullptr || conv_tc_wsplit_floats(l) > wsplit_cap || reinterpret_cast<uintptr_t>(wsplit) % 16 != 0) return B2RL_EINVAL;
+    uint32_t *koff = reinterpret_cast<uint32_t *>(wsplit + (size_t)2 * n_pad * k_pad);
+    const int total = n_pad * k_pad;
+    weight_split_kernel<<<(total + 255) / 256, 256, 0, s>>>(W, l.out_c, K, n_pad, k_pad, wsplit, nullptr, KK, l.ksize, l.in_h * l.in_w,
+                                                            l.in_w, koff);
+    B2RL_LAUNCH_CHECK();
+    return B2RL_OK;
+}
+
 // returns B2RL_OK, or 1 when the shape is outside what the tensor-core kernel handles (caller falls
 // back to the FFMA engine).  wsplit: scratch for the pre-split weights (conv_tc_wsplit_floats).
 static int launch_conv_fwd_tc(const b2rl_layer &l, const Operand &A, const float *W, const float *bias, float *out,

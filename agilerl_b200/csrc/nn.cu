@@ -144,6 +144,13 @@ struct LearnWS {
     float *norm_partials;           // kNormBlocks
     float *wsum;                    // 1
     unsigned int *ticket;           // last-CTA counter of the fused loss tail
+    // parameter-only preparation of a step (b2rl_rainbow_prep): digit planes of the first layer for both networks,
+    // pre-split weights of the later convolutions per network — kept apart from the split-K scratch so that they can be
+    // produced on a side stream while the sampler runs
+    void *prep0;
+    size_t prep0_bytes;
+    float *prep_split[2][B2RL_MAX_ENC];
+    size_t prep_split_floats[B2RL_MAX_ENC];
     size_t bytes;
 };
 
@@ -170,6 +177,20 @@ static void carve_learn(const b2rl_net_desc &net, int64_t B, bool two_sided_onli
     ws.norm_partials = b.take<float>(kNormBlocks);
     ws.wsum = b.take<float>(4);
     ws.ticket = b.take<unsigned int>(4);
+    ws.prep0 = nullptr; ws.prep0_bytes = 0;
+    for (int i = 0; i < B2RL_MAX_ENC; ++i) { ws.prep_split[0][i] = ws.prep_split[1][i] = nullptr; ws.prep_split_floats[i] = 0; }
+    if (net.n_enc >= 1 && net.enc[0].kind == B2RL_LAYER_CONV) {
+        const b2rl_layer &l0 = net.enc[0];
+        const int K = l0.in_c * l0.ksize * l0.ksize;
+        ws.prep0_bytes = conv_i8_scratch_bytes((l0.out_c + 15) / 16 * 16, (K + 31) / 32 * 32, 2);
+        ws.prep0 = b.take<unsigned char>(ws.prep0_bytes);
+    }
+    for (int i = 1; i < net.n_enc; ++i)
+        if (net.enc[i].kind == B2RL_LAYER_CONV) {
+            ws.prep_split_floats[i] = conv_tc_wsplit_floats(net.enc[i]);
+            ws.prep_split[0][i] = b.take<float>(ws.prep_split_floats[i]);
+            ws.prep_split[1][i] = b.take<float>(ws.prep_split_floats[i]);
+        }
     ws.bytes = b.off + 256;
 }
 
@@ -179,6 +200,8 @@ struct ForkJoin {
     cudaStream_t side = nullptr;       // target-network forward (highest priority)
     cudaStream_t side_bw = nullptr;    // weight gradients of the backward (default priority)
     cudaEvent_t fork = nullptr, join = nullptr, bw = nullptr;
+    cudaStream_t prep = nullptr;       // parameter-only preparation of a step, concurrent with the sampler
+    cudaEvent_t prep_fork = nullptr, prep_done = nullptr;
 };
 static int fork_join(ForkJoin **out) {
     static ForkJoin fj;
@@ -192,6 +215,9 @@ static int fork_join(ForkJoin **out) {
         B2RL_CUDA(cudaEventCreateWithFlags(&fj.join, cudaEventDisableTiming));
         B2RL_CUDA(cudaStreamCreateWithFlags(&fj.side_bw, cudaStreamNonBlocking));
         B2RL_CUDA(cudaEventCreateWithFlags(&fj.bw, cudaEventDisableTiming));
+        B2RL_CUDA(cudaStreamCreateWithPriority(&fj.prep, cudaStreamNonBlocking, hi));
+        B2RL_CUDA(cudaEventCreateWithFlags(&fj.prep_fork, cudaEventDisableTiming));
+        B2RL_CUDA(cudaEventCreateWithFlags(&fj.prep_done, cudaEventDisableTiming));
     }
     *out = &fj;
     return B2RL_OK;
@@ -399,7 +425,8 @@ using OpW = OpTraits<EL_F32, MAP_STRIDE, MAP_STRIDE, true, false>;     // weight
 
 static int layer_forward(const b2rl_net_desc &net, const b2rl_layer &l, const float *W, const float *bias,
                          const float *params, const float *x_prev, const ObsChunk *chunks, int n_chunks,
-                         int64_t rows, const LayerBuf &lb, const Scratch &sc, cudaStream_t s, bool reuse_split = false) {
+                         int64_t rows, const LayerBuf &lb, const Scratch &sc, cudaStream_t s, bool reuse_split = false,
+                         float *presplit = nullptr, size_t presplit_floats = 0) {   // presplit: this layer's weights already split there
     const int64_t oe = layer_out_elems(l);
     const bool first = x_prev == nullptr;
     int n_runs = first ? n_chunks : 1;
@@ -457,11 +484,14 @@ static int layer_forward(const b2rl_net_desc &net, const b2rl_layer &l, const fl
         }
         int rc = 1;
         // fp32 activations of an earlier layer: receptive fields staged in shared memory by the TMA unit (conv_st.cuh)
+        const bool pre_ok = presplit != nullptr && !first;
+        float *wsp = pre_ok ? presplit : sc.partial;
+        const size_t wsp_cap = pre_ok ? presplit_floats : sc.floats;
         if (l.kind == B2RL_LAYER_CONV && tc_enabled() && l.ln == B2RL_LN_NONE && !first && lb.pre == nullptr)
-            rc = launch_conv_fwd_st(l, x_prev, W, bias, out_ptr, r, sc.partial, sc.floats, s, reuse_split);
+            rc = launch_conv_fwd_st(l, x_prev, W, bias, out_ptr, r, wsp, wsp_cap, s, reuse_split || pre_ok);
         if (rc == 1 && l.kind == B2RL_LAYER_CONV && tc_enabled() && l.ln == B2RL_LN_NONE)
-            rc = launch_conv_fwd_tc(l, A, W, bias, out_ptr, lb.pre ? lb.pre + row0 * oe : nullptr, r, sc.partial, sc.floats,
-                                    s, run > 0 || reuse_split);   // tcgen05 3xTF32 (pre-split weights live in the split-K scratch;
+            rc = launch_conv_fwd_tc(l, A, W, bias, out_ptr, lb.pre ? lb.pre + row0 * oe : nullptr, r, wsp, wsp_cap,
+                                    s, run > 0 || reuse_split || pre_ok);   // tcgen05 3xTF32 (pre-split weights live in the split-K scratch;
                                                    // the second observation chunk reuses the first one's split)
         if (rc == 1 && l.kind == B2RL_LAYER_CONV)
             rc = dispatch_elem(A.elem_kind(), [&](auto ek) {
@@ -499,13 +529,15 @@ static inline const float *eff_b(const b2rl_layer &l, const float *params, const
 
 static int forward_pass(const b2rl_net_desc &net, const float *params, const float *weff, bool use_noise,
                         const ObsChunk *chunks, int n_chunks, int64_t rows, PassBufs &pb, const Scratch &sc,
-                        cudaStream_t s, bool first_done = false) {     // first_done: pb.enc[0].a already holds layer 0's output
+                        cudaStream_t s, bool first_done = false,      // first_done: pb.enc[0].a already holds layer 0's output
+                        float *const *presplit = nullptr, const size_t *presplit_floats = nullptr) {
     const float *x = nullptr;
     for (int i = 0; i < net.n_enc; ++i) {
         if (i == 0 && first_done) { x = pb.enc[0].a; continue; }
         const b2rl_layer &l = net.enc[i];
         int rc = layer_forward(net, l, eff_w(l, params, weff, use_noise), eff_b(l, params, weff, use_noise), params, x,
-                               chunks, n_chunks, rows, pb.enc[i], sc, s);
+                               chunks, n_chunks, rows, pb.enc[i], sc, s, false, presplit ? presplit[i] : nullptr,
+                               presplit ? presplit_floats[i] : 0);
         if (rc != B2RL_OK) return rc;
         x = pb.enc[i].a;
     }
@@ -1423,13 +1455,59 @@ static int optim_step(const b2rl_net_desc &net, const b2rl_learn_cfg &cfg, const
     return B2RL_OK;
 }
 
+// Everything of a loss pass that depends on the parameters only — W = mu + sigma * eps of the noisy layers, the int8 digit
+// planes of the first layer (both networks), the tf32 hi/lo split of the later convolutions — on a library-owned side stream
+// forked from `s`, so that it runs under the sampler that precedes the loss; rainbow_loss(prepped) joins it.
+static bool prep_first_i8(const b2rl_net_desc &net, const b2rl_learn_bufs &bufs) {
+    const b2rl_layer &l0 = net.enc[0];
+    return tc_enabled() && !l0.noisy &&
+           conv_i8_ok(l0, net.obs_u8 != 0, net.normalize != 0, net.obs_low, net.obs_high, bufs.next_obs, 2) &&
+           reinterpret_cast<uintptr_t>(bufs.obs) % 4 == 0;
+}
+static int rainbow_prep(const b2rl_net_desc &net, const b2rl_learn_cfg &cfg, const b2rl_learn_bufs &bufs, LearnWS &ws,
+                        cudaStream_t s) {
+    ForkJoin *fj = nullptr;
+    int rc;
+    if ((rc = fork_join(&fj)) != B2RL_OK) return rc;
+    B2RL_CUDA(cudaEventRecord(fj->prep_fork, s));
+    B2RL_CUDA(cudaStreamWaitEvent(fj->prep, fj->prep_fork, 0));
+    cudaStream_t sp = fj->prep;
+    if (cfg.use_noise) {
+        if ((rc = compose_weights(net, bufs.actor_params, bufs.actor_eps, ws.weff_actor, sp, bufs.target_params,
+                                  bufs.target_eps, ws.weff_target)) != B2RL_OK)
+            return rc;
+    }
+    if (prep_first_i8(net, bufs) && ws.prep0) {
+        const b2rl_layer &l0 = net.enc[0];
+        const float *Ws[2] = {bufs.actor_params + l0.w_off, bufs.target_params + l0.w_off};
+        if ((rc = launch_weight_digits(l0, net.normalize != 0, net.obs_low, net.obs_high, Ws, 2, ws.prep0, ws.prep0_bytes, sp)) != B2RL_OK)
+            return rc;
+    }
+    for (int i = 1; i < net.n_enc; ++i) {
+        const b2rl_layer &l = net.enc[i];
+        if (l.kind != B2RL_LAYER_CONV || l.noisy || !tc_enabled() || ws.prep_split[0][i] == nullptr) continue;
+        for (int which = 0; which < 2; ++which) {
+            const float *W = (which == 0 ? bufs.actor_params : bufs.target_params) + l.w_off;
+            if ((rc = launch_weight_split(l, W, ws.prep_split[which][i], ws.prep_split_floats[i], sp)) != B2RL_OK) return rc;
+        }
+    }
+    B2RL_CUDA(cudaEventRecord(fj->prep_done, sp));
+    return B2RL_OK;
+}
+
 static int rainbow_loss(const b2rl_net_desc &net, const b2rl_learn_cfg &cfg, const b2rl_learn_bufs &bufs, LearnWS &ws,
                         cudaStream_t s) {
     const int64_t B = cfg.batch;
     const int A = net.n_actions, N = net.n_atoms;
     const bool noise = cfg.use_noise != 0;
+    const bool prepped = (cfg.reserved_ & 1) != 0;          // b2rl_rainbow_prep was enqueued for this pass
     int rc;
-    if (noise) {
+    if (prepped) {
+        ForkJoin *fjp = nullptr;
+        if ((rc = fork_join(&fjp)) != B2RL_OK) return rc;
+        B2RL_CUDA(cudaStreamWaitEvent(s, fjp->prep_done, 0));
+    }
+    if (noise && !prepped) {
         if ((rc = compose_weights(net, bufs.actor_params, bufs.actor_eps, ws.weff_actor, s, bufs.target_params,
                                   bufs.target_eps, ws.weff_target)) != B2RL_OK)
             return rc;
@@ -1453,8 +1531,12 @@ static int rainbow_loss(const b2rl_net_desc &net, const b2rl_learn_cfg &cfg, con
                 ConvI8Job{bufs.obs, bufs.row_idx, B, 1, {ws.online.enc[0].a + B * oe, nullptr}}};
             const float *Ws[2] = {bufs.actor_params + l0.w_off, bufs.target_params + l0.w_off};
             const float *bs[2] = {bufs.actor_params + l0.b_off, bufs.target_params + l0.b_off};
-            rc = launch_conv_fwd_i8(l0, net.normalize != 0, net.obs_low, net.obs_high, Ws, bs, 2, jobs, 2, ws.partial,
-                                    ws.partial_floats * sizeof(float), s);
+            if (prepped && ws.prep0)
+                rc = launch_conv_fwd_i8(l0, net.normalize != 0, net.obs_low, net.obs_high, Ws, bs, 2, jobs, 2, ws.prep0,
+                                        ws.prep0_bytes, s, true);
+            else
+                rc = launch_conv_fwd_i8(l0, net.normalize != 0, net.obs_low, net.obs_high, Ws, bs, 2, jobs, 2, ws.partial,
+                                        ws.partial_floats * sizeof(float), s);
             if (rc == B2RL_OK) shared_first = true;
             else if (rc != 1) return rc;
         }
@@ -1470,13 +1552,13 @@ static int rainbow_loss(const b2rl_net_desc &net, const b2rl_learn_cfg &cfg, con
     ObsChunk tg_chunk{bufs.next_obs, bufs.row_idx, B};
     Scratch sc_tg{ws.partial_tg, ws.partial_tg_floats};
     if ((rc = forward_pass(net, bufs.target_params, ws.weff_target, noise, &tg_chunk, 1, B, ws.target, sc_tg, st,
-                           shared_first)) != B2RL_OK)
+                           shared_first, prepped ? ws.prep_split[1] : nullptr, ws.prep_split_floats)) != B2RL_OK)
         return rc;
     if (fork_on) B2RL_CUDA(cudaEventRecord(fj->join, fj->side));
     // online network on [next_obs ; obs]  (forwards #1 and #3 of _dqn_loss share weights and noise)
     ObsChunk on_chunks[2] = {{bufs.next_obs, bufs.row_idx, B}, {bufs.obs, bufs.row_idx, B}};
     if ((rc = forward_pass(net, bufs.actor_params, ws.weff_actor, noise, on_chunks, 2, 2 * B, ws.online, sc, s,
-                           shared_first)) != B2RL_OK)
+                           shared_first, prepped ? ws.prep_split[0] : nullptr, ws.prep_split_floats)) != B2RL_OK)
         return rc;
     if (fork_on) B2RL_CUDA(cudaStreamWaitEvent(s, fj->join, 0));
     const float *v_on = ws.online.val[net.n_val - 1].a, *adv_on = ws.online.adv[net.n_adv - 1].a;
@@ -1658,6 +1740,15 @@ int b2rl_rainbow_loss(const b2rl_net_desc *net_host, const b2rl_learn_cfg *cfg_h
     B2RL_CHECK_ARG(net_host->kind == B2RL_NET_RAINBOW, "not a rainbow network");
     B2RL_CHECK_ARG(bufs_host->support && bufs_host->loss_elem && bufs_host->loss_scalar, "NULL rainbow buffer");
     return rainbow_loss(*net_host, *cfg_host, *bufs_host, ws, as_stream(stream));
+}
+
+int b2rl_rainbow_prep(const b2rl_net_desc *net_host, const b2rl_learn_cfg *cfg_host, const b2rl_learn_bufs *bufs_host,
+                      void *stream) {
+    LearnWS ws;
+    int rc = check_learn_args(net_host, cfg_host, bufs_host, ws);
+    if (rc != B2RL_OK) return rc;
+    B2RL_CHECK_ARG(net_host->kind == B2RL_NET_RAINBOW, "not a rainbow network");
+    return rainbow_prep(*net_host, *cfg_host, *bufs_host, ws, as_stream(stream));
 }
 
 int b2rl_rainbow_backward(const b2rl_net_desc *net_host, const b2rl_learn_cfg *cfg_host,

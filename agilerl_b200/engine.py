@@ -52,6 +52,7 @@ import os as _os
 
 _SIDE = int(_os.environ["B2RL_SIDE_STREAMS"]) if "B2RL_SIDE_STREAMS" in _os.environ else None
 _GRAPH = _os.environ.get("B2RL_GRAPH", "1") != "0"      # CUDA-graph replay of the fused step (0: always eager)
+_PREP = _os.environ.get("B2RL_PREP", "1") != "0"        # parameter-only work of a captured step on a side stream under the sampler
 
 
 class _FusedPlan:
@@ -94,6 +95,9 @@ class _FusedPlan:
         _lib.check(lib.b2rl_graph_begin(s))
         try:
             _lib.check(lib.b2rl_step_state_write(ctypes.byref(self.state_host), self.state_dev.data_ptr(), s))
+            if _PREP:      # parameter-only work of the loss pass on a side stream, under the sampler
+                _lib.check(lib.b2rl_rainbow_prep(desc, ctypes.byref(cfg), ctypes.byref(bufs), s))
+                cfg.reserved_ = 1
             _lib.check(lib.b2rl_per_sample_fused_state(
                 per.sum_tree.data_ptr, per.min_tree.data_ptr, per._cap, per._philox_seed, self.state_dev.data_ptr(), B,
                 f[("action",)].data_ptr(), f[(nmem.reward_key,)].data_ptr(), f[(dk,)].data_ptr(), self.idx.data_ptr(),

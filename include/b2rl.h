@@ -324,7 +324,7 @@ typedef struct b2rl_learn_cfg {
                                            b2rl_rainbow_backward the weight gradients, on library-owned
                                            side streams (joined before the call's work is complete in the
                                            caller's stream order); 0: everything on `stream` */
-    int32_t reserved_;
+    int32_t reserved_;                  /* bit 0: b2rl_rainbow_prep was enqueued for this pass (rainbow loss only) */
 } b2rl_learn_cfg;
 
 /* Device buffers of one learn step (all fp32 unless stated). */
@@ -350,6 +350,13 @@ typedef struct b2rl_learn_bufs {
  * writes per-sample loss, leaves dL/dlogits staged in the workspace.  Does not touch grads. */
 int b2rl_rainbow_loss(const b2rl_net_desc *net_host, const b2rl_learn_cfg *cfg_host,
                       const b2rl_learn_bufs *bufs_host, void *stream);
+/* Optional: enqueue everything of the next b2rl_rainbow_loss that depends on the parameters only (noisy-layer weight
+ * composition, the first layer's int8 digit planes for both networks, the tf32 split of the later convolutions) on a
+ * library-owned side stream forked from `stream`, so that it overlaps whatever the caller enqueues next on `stream`
+ * (the sampler).  The following b2rl_rainbow_loss on the same stream must then be called with cfg.reserved_ = 1: it joins
+ * the side stream and skips those launches.  Same workspace, same buffers as the loss call. */
+int b2rl_rainbow_prep(const b2rl_net_desc *net_host, const b2rl_learn_cfg *cfg_host, const b2rl_learn_bufs *bufs_host,
+                      void *stream);
 /* Back-propagate mean(loss*w) of the staged loss(es) into `grads` (loss.backward()).
  * n_passes = 1, or 2 when combined_reward staged two losses. */
 int b2rl_rainbow_backward(const b2rl_net_desc *net_host, const b2rl_learn_cfg *cfg_host,
