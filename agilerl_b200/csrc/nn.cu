@@ -23,6 +23,7 @@
 #include "conv_st.cuh"
 #include "conv_wst.cuh"
 #include "conv_dst.cuh"
+#include "conv_wi8.cuh"
 #include "head_fused.cuh"
 #include "gemm.cuh"
 #include <cstdlib>
@@ -119,6 +120,11 @@ static size_t max_partial_floats(const b2rl_net_desc &net, int64_t rows, int64_t
             if (n > m) m = n;
             if (brows) { n = conv_wgrad_tc_partial_floats(net.enc[i], brows, sm_count()); if (n > m) m = n; }
             if (brows) { n = conv_wgrad_st_partial_floats(net.enc[i], sm_count()); if (n > m) m = n; }
+            if (brows && i == 0) {
+                n = conv_wi8_scratch_bytes((net.enc[i].out_c + 15) / 16 * 16, net.enc[i].in_c * net.enc[i].ksize * net.enc[i].ksize,
+                                           net.enc[i].out_c) / sizeof(float) + 64;
+                if (n > m) m = n;
+            }
             if (brows && i > 0) { n = conv_dgrad_tc_scratch_floats(net.enc[i]); if (n > m) m = n; }
             if (brows && i > 0) { n = conv_dst_scratch_floats(net.enc[i]); if (n > m) m = n; }
         }
@@ -1095,7 +1101,9 @@ static int layer_backward(const b2rl_net_desc &net, const b2rl_layer &l, const f
             A.ones_row = Kc;
             Bm.ptr = g_out; Bm.row = map_stride(P); Bm.red = map_pixel(P, l.out_w, (int64_t)l.out_c * P, l.out_w, 1);
             rc = 1;
-            if (tc_enabled())   // staged operands, MN-major im2col tile (conv_wst.cuh)
+            if (tc_enabled() && obs)   // uint8 frames: integer tensor path, frame bytes as the MN-major operand (conv_wi8.cuh)
+                rc = launch_conv_wgrad_i8(l, A, g_out, gw, gb, acc_w, B, scw->partial, scw->floats * sizeof(float), sw);
+            if (rc == 1 && tc_enabled())   // staged operands (conv_wst.cuh)
                 rc = launch_conv_wgrad_st(l, A, g_out, gw, gb, acc_w, B, scw->partial, scw->floats, sw);
             if (rc == 1 && tc_enabled())   // tcgen05 3xTF32, gathered operands, split over pixels
                 rc = launch_conv_wgrad_tc(l, A, g_out, gw, gb, acc_w, B, scw->partial, scw->floats, sw);

@@ -509,8 +509,9 @@ def test_inner_conv_layer_staged_matches_float64(obs_hw, c0, k0, s0, cout, k, s,
     (True, 36, 16, 4, 4, 8, 4, 2, 6, True),       # first layer k4 s4: K = 64
 ])
 def test_conv_weight_gradient_staged_matches_float64(first, obs_hw, c0, k0, s0, cout, k, s, rows, staged):
-    """conv_wgrad_st_kernel (MN-major im2col tile, staged operands) through b2rl_rainbow_backward's layer step is exercised
-    by the learn tests; here the layer's dW / db alone against float64 autograd, both operand kinds."""
+    """The layer's dW / db alone against float64 autograd: conv_wgrad_st_kernel (staged operands, transposed im2col reads) for
+    fp32 activations, conv_wgrad_i8_kernel (frame bytes as the MN-major operand, G as five int8 digit planes, int64
+    accumulation) for the first layer's uint8 frames."""
     import ctypes
     from agilerl_b200 import _lib
     from agilerl_b200.networks.spec import FlatLayout, rainbow_spec
@@ -540,7 +541,7 @@ def test_conv_weight_gradient_staged_matches_float64(first, obs_hw, c0, k0, s0, 
     ws = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
     gdev = gout.cuda()
     lib = _lib.load()
-    n_st = lib.b2rl_conv_path_count(2)
+    n_st, n_i8 = lib.b2rl_conv_path_count(2), lib.b2rl_conv_path_count(1)
     prev = lib.b2rl_conv_staged_paths(7)
     try:
         _lib.check(lib.b2rl_encoder_layer_wgrad(ctypes.byref(desc), li, x_dev.data_ptr(),
@@ -550,7 +551,10 @@ def test_conv_weight_gradient_staged_matches_float64(first, obs_hw, c0, k0, s0, 
         torch.cuda.synchronize()
     finally:
         lib.b2rl_conv_staged_paths(prev)
-    assert lib.b2rl_conv_path_count(2) - n_st == (1 if staged else 0)
+    if first:      # uint8 frames: the integer-tensor weight gradient (conv_wi8.cuh) takes the layer
+        assert lib.b2rl_conv_path_count(1) - n_i8 == 1 and lib.b2rl_conv_path_count(2) == n_st
+    else:
+        assert lib.b2rl_conv_path_count(2) - n_st == (1 if staged else 0)
     gh = grads.cpu().double()
     got_w, got_b = gh[L.w_off:L.w_off + w64.numel()].reshape(w64.shape), gh[L.b_off:L.b_off + L.out_c]
     assert torch.isfinite(got_w).all() and torch.isfinite(got_b).all()
@@ -604,3 +608,45 @@ def test_conv_input_gradient_staged_matches_float64(obs_hw, c0, k0, s0, cout, k,
     assert torch.isfinite(got).all()
     err = (got - x64.grad).abs().max().item()
     assert err <= 5e-6 * max(1.0, x64.grad.abs().max().item()), err
+
+
+def test_first_layer_weight_gradient_low_bound_zero_and_tiny_channels():
+    """The integer weight gradient with a non-zero integer lower bound (the -low * sum(G) correction), an all-zero
+    gradient channel and a channel six orders of magnitude below the others (per-channel scales)."""
+    import ctypes
+    from agilerl_b200 import _lib
+    from agilerl_b200.networks.spec import FlatLayout, rainbow_spec
+    g = torch.Generator().manual_seed(7)
+    spec = rainbow_spec((4, 84, 84), 3, channel_size=(32, 32), kernel_size=(8, 4), stride_size=(4, 2), latent_dim=16,
+                        hidden_size=(16,), obs_low=-3.0, obs_high=252.0, obs_u8=True)
+    layout = FlatLayout(spec)
+    desc = layout.desc
+    L = desc.enc[0]
+    rows = 33
+    ring = torch.randint(0, 256, (48, L.in_c, L.in_h, L.in_w), dtype=torch.uint8, generator=g)
+    idx = torch.randint(0, 48, (rows,), generator=g)
+    x64 = (ring[idx].double() + 3.0) / 255.0
+    gout = torch.randn(rows, L.out_c, L.out_h, L.out_w, generator=g) * 0.05
+    gout[:, 3] = 0.0                                     # an all-zero channel
+    gout[:, 5] *= 1e-6
+    w64 = torch.zeros(L.out_c, L.in_c, L.ksize, L.ksize, dtype=torch.float64, requires_grad=True)
+    b64 = torch.zeros(L.out_c, dtype=torch.float64, requires_grad=True)
+    torch.nn.functional.conv2d(x64, w64, b64, stride=L.stride).backward(gout.double())
+    lib = _lib.load()
+    grads = torch.full((layout.n_params,), float("nan"), dtype=torch.float32, device="cuda")
+    ws = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+    n_i8 = lib.b2rl_conv_path_count(1)
+    ring_d, idx_d, gout_d = ring.cuda(), idx.cuda(), gout.cuda()
+    _lib.check(lib.b2rl_encoder_layer_wgrad(ctypes.byref(desc), 0, ring_d.data_ptr(), idx_d.data_ptr(), rows,
+                                            gout_d.data_ptr(), grads.data_ptr(), ws.data_ptr(), ws.numel(),
+                                            _lib.stream_ptr(torch.device("cuda:0"))))
+    torch.cuda.synchronize()
+    assert lib.b2rl_conv_path_count(1) - n_i8 == 1
+    gh = grads.cpu().double()
+    got_w, got_b = gh[L.w_off:L.w_off + w64.numel()].reshape(w64.shape), gh[L.b_off:L.b_off + L.out_c]
+    sw = w64.grad.abs().max().item()
+    assert (got_w - w64.grad).abs().max().item() <= 2e-6 * sw
+    assert (got_b - b64.grad).abs().max().item() <= 2e-6 * b64.grad.abs().max().item()
+    assert got_w[3].abs().max().item() == 0.0 and got_b[3].item() == 0.0
+    s5 = w64.grad[5].abs().max().item()
+    assert (got_w[5] - w64.grad[5]).abs().max().item() <= 2e-6 * s5          # per-channel scale keeps small channels exact

@@ -24,12 +24,14 @@ __global__ void probe(const float *A, const float *B, float *D, int mode) {
         const int m = e / 32, k = e % 32;
         if (mode == 0) *reinterpret_cast<__nv_bfloat16 *>(As + (m / 8) * 512 + (k / 8) * 128 + (k % 8) * 16 + (m % 8) * 2) = __float2bfloat16(A[e]);
         else if (mode == 1) *reinterpret_cast<__nv_bfloat16 *>(As + (k / 8) * 2048 + (m / 8) * 128 + (m % 8) * 16 + (k % 8) * 2) = __float2bfloat16(A[e]);
-        else *reinterpret_cast<float *>(As + (k / 4) * 2048 + (m / 8) * 128 + (m % 8) * 16 + (k % 4) * 4) = A[e];
+        else if (mode == 2) *reinterpret_cast<float *>(As + (k / 4) * 2048 + (m / 8) * 128 + (m % 8) * 16 + (k % 4) * 4) = A[e];
+        else As[(m / 16) * 512 + (k / 8) * 128 + (k % 8) * 16 + (m % 16)] = (uint8_t)(int)(A[e] + 6.f);       // u8 0..12
     }
     for (int e = tid; e < 32 * 32; e += blockDim.x) {
         const int n = e / 32, k = e % 32;
         if (mode < 2) *reinterpret_cast<__nv_bfloat16 *>(Bs + (k / 8) * 512 + (n / 8) * 128 + (n % 8) * 16 + (k % 8) * 2) = __float2bfloat16(B[e]);
-        else *reinterpret_cast<float *>(Bs + (n / 4) * 512 + (k / 8) * 128 + (k % 8) * 16 + (n % 4) * 4) = B[e];
+        else if (mode == 2) *reinterpret_cast<float *>(Bs + (n / 4) * 512 + (k / 8) * 128 + (k % 8) * 16 + (n % 4) * 4) = B[e];
+        else Bs[(k / 16) * 512 + (n / 8) * 128 + (n % 8) * 16 + (k % 16)] = (uint8_t)(int8_t)(int)B[e];
     }
     if (tid == 0) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar))); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (warp == 0) {
@@ -49,6 +51,11 @@ __global__ void probe(const float *A, const float *B, float *D, int mode) {
                 const uint64_t db = make_desc(base + 16384 + ks * 2 * 512, 512, 128);
                 asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"((uint32_t)ks) : "memory");
             }
+        } else if (mode == 3) {
+            const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | (1u << 15) | ((32u >> 3) << 17) | ((128u >> 4) << 24);   // S32, U8 x S8, A MN-major
+            const uint64_t da = make_desc(base, 128, 512);       // one MMA: K = 32 = 4 k-groups of 8 at LBO = 128; 8 m-chunks of 16 at SBO = 512
+            const uint64_t db = make_desc(base + 16384, 512, 128);
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(0u) : "memory");
         } else {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
             for (int ks = 0; ks < 4; ++ks) {        // K = 8 per MMA
@@ -71,7 +78,7 @@ __global__ void probe(const float *A, const float *B, float *D, int mode) {
               "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
             : "r"(tmem_d + ((uint32_t)(warp * 32) << 16)));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        for (int j = 0; j < 32; ++j) D[(warp * 32 + lane) * 32 + j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 32; ++j) D[(warp * 32 + lane) * 32 + j] = mode == 3 ? (float)(int)r[j] : __uint_as_float(r[j]);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -86,15 +93,16 @@ int main() {
     cudaMalloc(&dA, sizeof(hA)); cudaMalloc(&dB, sizeof(hB)); cudaMalloc(&dD, sizeof(hD));
     cudaMemcpy(dA, hA, sizeof(hA), cudaMemcpyHostToDevice); cudaMemcpy(dB, hB, sizeof(hB), cudaMemcpyHostToDevice);
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    for (int mode = 0; mode < 3; ++mode) {
+    for (int mode = 0; mode < 4; ++mode) {
         cudaMemset(dD, 0xFF, sizeof(hD));
         probe<<<1, 128, 40 * 1024>>>(dA, dB, dD, mode);
         cudaError_t e = cudaDeviceSynchronize();
         cudaMemcpy(hD, dD, sizeof(hD), cudaMemcpyDeviceToHost);
         float err = 0;
+        if (mode == 3) for (int m = 0; m < 128; ++m) for (int n = 0; n < 32; ++n) { float s2 = 0; for (int k = 0; k < 32; ++k) s2 += (hA[m * 32 + k] + 6.f) * hB[n * 32 + k]; ref[m * 32 + n] = s2; }
         for (int i = 0; i < 128 * 32; ++i) { float d = hD[i] - ref[i]; if (d < 0) d = -d; if (d != d) d = 1e30f; if (d > err) err = d; }
         printf("mode %d (%s): %s max err %g, D[0][0..3] = %g %g %g %g (ref %g %g %g %g)\n", mode,
-               mode == 0 ? "bf16 A MN-major" : mode == 1 ? "bf16 A K-major" : "tf32 B MN-major", cudaGetErrorString(e), err, hD[0], hD[1], hD[2], hD[3], ref[0], ref[1], ref[2], ref[3]);
+               mode == 0 ? "bf16 A MN-major" : mode == 1 ? "bf16 A K-major" : mode == 2 ? "tf32 B MN-major" : "i8: u8 A MN-major x s8 B K-major", cudaGetErrorString(e), err, hD[0], hD[1], hD[2], hD[3], ref[0], ref[1], ref[2], ref[3]);
     }
     return 0;
 }
