@@ -32,17 +32,26 @@ static inline size_t conv_wi8_scratch_bytes(int n_pad, int Kc, int N) {
 }
 
 // block (co, slot): max |G| over the images b = slot, slot + kWi8Slots, ... of channel co -> maxbuf[co][slot];
-// the blocks also zero the int64 accumulators the weight-gradient kernel adds into.
-__global__ void chan_absmax_zero_kernel(const float *__restrict__ g, int64_t rows, int N, int P, uint32_t *__restrict__ maxbuf,
-                                        long long *__restrict__ acc, int64_t acc_n) {
+// the blocks also zero the int64 accumulators the weight-gradient kernel adds into, and — when `a` is given — apply the
+// layer's activation backward to G in place first (the act_bwd_kernel launch this replaces reads the same planes).
+__global__ void chan_absmax_zero_kernel(float *__restrict__ g, const float *__restrict__ a, const float *__restrict__ pre, int act,
+                                        int64_t rows, int N, int P, uint32_t *__restrict__ maxbuf, long long *__restrict__ acc,
+                                        int64_t acc_n) {
     __shared__ float red[8];
     const int co = blockIdx.x, slot = blockIdx.y;
     const int64_t nb = (int64_t)gridDim.x * gridDim.y, bid = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
     for (int64_t i = bid * blockDim.x + threadIdx.x; i < acc_n; i += nb * blockDim.x) acc[i] = 0;
     float mx = 0.f;
     for (int64_t b = slot; b < rows; b += kWi8Slots) {
-        const float *p = g + (b * N + co) * P;
-        for (int i = threadIdx.x; i < P; i += blockDim.x) mx = fmaxf(mx, fabsf(p[i]));
+        const int64_t base = (b * N + co) * P;
+        for (int i = threadIdx.x; i < P; i += blockDim.x) {
+            float v = g[base + i];
+            if (a) {
+                v *= act_bwd(act, pre ? pre[base + i] : 0.f, a[base + i]);
+                g[base + i] = v;
+            }
+            mx = fmaxf(mx, fabsf(v));
+        }
     }
     mx = warp_max(mx);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
@@ -204,7 +213,7 @@ __global__ void __launch_bounds__(kWi8Threads, 1) conv_wgrad_i8_kernel(const Con
         // warp = 16-pixel chunk of the tile, lane = output channel (+32 per pass): 16 values of G -> five int8 digits each
         const int gw = warp - (kI8GatherWarps + 1);                         // 0..7
         const bool vec_ok = (p.P % 4) == 0 && (reinterpret_cast<uintptr_t>(p.g) % 16) == 0;
-        long long bsum[2] = {0, 0};                                         // sum of q of this thread's channels (n_pad <= 64)
+        double bsum[2] = {0.0, 0.0};                                        // sum of q of this thread's channels: integers below 2^53
         for (int i = 0; i < my_tiles; ++i) {
             const int t = (int)blockIdx.x + i * (int)gridDim.x;
             const int m0 = t * kTcBM + gw * 16;
@@ -237,18 +246,29 @@ __global__ void __launch_bounds__(kWi8Threads, 1) conv_wgrad_i8_kernel(const Con
                 uint32_t dw[kWi8Digits][4];
 #pragma unroll
                 for (int d = 0; d < kWi8Digits; ++d) dw[d][0] = dw[d][1] = dw[d][2] = dw[d][3] = 0u;
-                long long qs = 0;
+                double qs = 0.0;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    long long q = __double2ll_rn((double)v[j] * up);          // |q| <= 2^37
-                    qs += q;
-#pragma unroll
-                    for (int d = kWi8Digits - 1; d >= 1; --d) {               // balanced digits, least significant first
-                        const int lowb = (int)(((q + 128) & 255) - 128);
-                        dw[d][j >> 2] |= (uint32_t)(lowb & 255) << (8 * (j & 3));
-                        q = (q - lowb) >> 8;
-                    }
-                    dw[0][j >> 2] |= (uint32_t)((int)q & 255) << (8 * (j & 3));
+                    // q = rint(v * up), |q| <= 2^37, split as A * 2^16 + B (0 <= B < 2^16) so that the balanced base-256 digits
+                    // come out of 32-bit integer arithmetic: d4, d3 from B (carry c2 in {0, 1}), d2, d1, d0 from A + c2
+                    const double qd = rint((double)v[j] * up);
+                    qs += qd;
+                    const int A = __double2int_rd(qd * 1.52587890625e-05);
+                    int t = __double2int_rn(qd - (double)A * 65536.0);
+                    const int d4 = ((t + 128) & 255) - 128;
+                    t = (t - d4) >> 8;
+                    const int d3 = ((t + 128) & 255) - 128;
+                    int u = A + ((t - d3) >> 8);
+                    const int d2 = ((u + 128) & 255) - 128;
+                    u = (u - d2) >> 8;
+                    const int d1 = ((u + 128) & 255) - 128;
+                    const int d0 = (u - d1) >> 8;
+                    const int sh = 8 * (j & 3);
+                    dw[4][j >> 2] |= (uint32_t)(d4 & 255) << sh;
+                    dw[3][j >> 2] |= (uint32_t)(d3 & 255) << sh;
+                    dw[2][j >> 2] |= (uint32_t)(d2 & 255) << sh;
+                    dw[1][j >> 2] |= (uint32_t)(d1 & 255) << sh;
+                    dw[0][j >> 2] |= (uint32_t)(d0 & 255) << sh;
                 }
                 bsum[pass & 1] += qs;
                 if (pass == 0) tc::mbar_wait(&empty[s], ph ^ 1u);               // the MMAs that read stage s two tiles ago have retired
@@ -264,7 +284,8 @@ __global__ void __launch_bounds__(kWi8Threads, 1) conv_wgrad_i8_kernel(const Con
         {
             int pass = 0;
             for (int co = lane; co < p.N; co += 32, ++pass)
-                if (bsum[pass & 1] != 0) atomicAdd(reinterpret_cast<unsigned long long *>(p.accb + co), (unsigned long long)bsum[pass & 1]);
+                if (bsum[pass & 1] != 0.0)
+                    atomicAdd(reinterpret_cast<unsigned long long *>(p.accb + co), (unsigned long long)__double2ll_rn(bsum[pass & 1]));
         }
         // ---- epilogue: TMEM lanes 32*(warp%4).. = taps; digit columns -> int64 -> atomics
         if (my_tiles > 0) {
@@ -324,33 +345,47 @@ __global__ void wgrad_i8_finish_kernel(const long long *__restrict__ acc, const 
     }
 }
 
-// returns B2RL_OK, or 1 when the layer is outside this path (caller: the tf32 weight-gradient kernels)
-static int launch_conv_wgrad_i8(const b2rl_layer &l, const Operand &X, const float *g, float *dw, float *db, int accumulate,
-                                int64_t rows, void *scratch, size_t scratch_bytes, cudaStream_t s) {
+// can launch_conv_wgrad_i8 take this layer?  (pure host check: the caller may then leave the activation backward to it)
+static bool conv_wgrad_i8_ok(const b2rl_layer &l, const Operand &X, int64_t rows, const void *scratch, size_t scratch_bytes) {
     static int want = -1;
     if (want < 0) { const char *e = getenv("B2RL_WGRAD_I8"); want = (e && e[0] == '0') ? 0 : 1; }
-    if (!want || !X.u8) return 1;
-    if (!conv_i8_ok(l, true, X.normalize != 0, X.low, X.high, X.ptr, 1)) return 1;
+    if (!want || !X.u8) return false;
+    if (!conv_i8_ok(l, true, X.normalize != 0, X.low, X.high, X.ptr, 1)) return false;
     const int KK = l.ksize * l.ksize, Kc = l.in_c * KK, P = l.out_h * l.out_w;
     const int n_pad = (l.out_c + 15) / 16 * 16, k_pad = (Kc + 31) / 32 * 32;
     const int MT = (Kc + kTcBM - 1) / kTcBM;
-    if (kWi8Digits * n_pad > 256 || MT * kWi8Digits * n_pad > 512 || n_pad > 64 || k_pad != Kc) return 1;
+    if (kWi8Digits * n_pad > 256 || MT * kWi8Digits * n_pad > 512 || n_pad > 64 || k_pad != Kc) return false;
+    const int cpt = k_pad / 32;
+    if (!(l.ksize == 8 ? (cpt == 2 || cpt == 4 || cpt == 8) : (cpt == 1 || cpt == 2 || cpt == 4 || cpt == 8))) return false;
     // int64 totals: pixels * 255 * 2^37 must stay below 2^63
-    if (rows * (int64_t)P > INT32_MAX || rows * (int64_t)P * 255 >= ((int64_t)1 << 26)) return 1;
-    const size_t smem = conv_wi8_smem_bytes(n_pad, k_pad);
-    if (smem > 200 * 1024) return 1;
+    if (rows < 1 || rows * (int64_t)P > INT32_MAX || rows * (int64_t)P * 255 >= ((int64_t)1 << 26)) return false;
+    if (conv_wi8_smem_bytes(n_pad, k_pad) > 200 * 1024) return false;
     if (scratch == nullptr || conv_wi8_scratch_bytes(n_pad, Kc, l.out_c) > scratch_bytes || reinterpret_cast<uintptr_t>(scratch) % 16 != 0)
-        return 1;
-    const int M = (int)(rows * P);
-    const int n_tiles = (M + kTcBM - 1) / kTcBM;
+        return false;
+    const int n_tiles = (int)((rows * P + kTcBM - 1) / kTcBM);
     const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
     // a CTA's int32 accumulators see tiles_per_cta * 128 pixels of |x * digit| <= 255 * 128
     const int64_t tiles_per_cta = (n_tiles + grid - 1) / grid;
-    if (tiles_per_cta * kTcBM * 255 * 128 >= ((int64_t)1 << 31)) return 1;
+    return tiles_per_cta * kTcBM * 255 * 128 < ((int64_t)1 << 31);
+}
+
+// g is dL/d(layer output); with act_a != NULL it is the gradient BEFORE the layer's activation backward, which the first
+// kernel then applies in place (g becomes what act_bwd_kernel would have left).  Call only when conv_wgrad_i8_ok.
+static int launch_conv_wgrad_i8(const b2rl_layer &l, const Operand &X, float *g, float *dw, float *db, int accumulate,
+                                int64_t rows, void *scratch, size_t scratch_bytes, cudaStream_t s, const float *act_a = nullptr,
+                                const float *act_pre = nullptr, int act = 0) {
+    if (!conv_wgrad_i8_ok(l, X, rows, scratch, scratch_bytes)) return 1;
+    const int KK = l.ksize * l.ksize, Kc = l.in_c * KK, P = l.out_h * l.out_w;
+    const int n_pad = (l.out_c + 15) / 16 * 16, k_pad = (Kc + 31) / 32 * 32;
+    const size_t smem = conv_wi8_smem_bytes(n_pad, k_pad);
+    const int M = (int)(rows * P);
+    const int n_tiles = (M + kTcBM - 1) / kTcBM;
+    const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
     uint32_t *maxbuf = static_cast<uint32_t *>(scratch);
     long long *acc = reinterpret_cast<long long *>(maxbuf + (size_t)n_pad * kWi8Slots);
     long long *accb = acc + (size_t)Kc * l.out_c;
-    chan_absmax_zero_kernel<<<dim3(l.out_c, kWi8Slots), 128, 0, s>>>(g, rows, l.out_c, P, maxbuf, acc, (int64_t)Kc * l.out_c + n_pad);
+    chan_absmax_zero_kernel<<<dim3(l.out_c, kWi8Slots), 128, 0, s>>>(g, act_a, act_pre, act, rows, l.out_c, P, maxbuf, acc,
+                                                                     (int64_t)Kc * l.out_c + n_pad);
     B2RL_LAUNCH_CHECK();
     ConvWi8Params p;
     p.x = static_cast<const uint8_t *>(X.ptr); p.gather = X.red.gather; p.g = g; p.maxbuf = maxbuf; p.acc = acc; p.accb = accb;

@@ -1045,8 +1045,18 @@ static int layer_backward(const b2rl_net_desc &net, const b2rl_layer &l, const f
     const int64_t oe = layer_out_elems(l);
     const float *a = lb.a + row_off * oe;
     const float *pre = lb.pre ? lb.pre + row_off * oe : nullptr;
+    // first convolution over uint8 frames: the integer weight-gradient path also applies the activation backward
+    // (its channel-maximum pass reads the same planes), one launch less on the chain
+    bool act_in_wgrad = false;
+    Operand obs_op;
+    if (obs && l.kind == B2RL_LAYER_CONV && l.ln == B2RL_LN_NONE && tc_enabled() && !(side && g_in)) {
+        obs_op.ptr = obs->ptr; obs_op.u8 = net.obs_u8; obs_op.normalize = net.normalize; obs_op.low = net.obs_low; obs_op.high = net.obs_high;
+        act_in_wgrad = conv_wgrad_i8_ok(l, obs_op, B, sc.partial, sc.floats * sizeof(float));
+    }
     // (1) through activation (+LayerNorm)
-    if (l.ln != B2RL_LN_NONE) {
+    if (act_in_wgrad) {
+        // nothing here
+    } else if (l.ln != B2RL_LN_NONE) {
         const float *z = lb.z + row_off * oe;
         const float *st = lb.stats + row_off * 2;
         if (l.ln == B2RL_LN_AFFINE) {
@@ -1102,7 +1112,9 @@ static int layer_backward(const b2rl_net_desc &net, const b2rl_layer &l, const f
             Bm.ptr = g_out; Bm.row = map_stride(P); Bm.red = map_pixel(P, l.out_w, (int64_t)l.out_c * P, l.out_w, 1);
             rc = 1;
             if (tc_enabled() && obs)   // uint8 frames: integer tensor path, frame bytes as the MN-major operand (conv_wi8.cuh)
-                rc = launch_conv_wgrad_i8(l, A, g_out, gw, gb, acc_w, B, scw->partial, scw->floats * sizeof(float), sw);
+                rc = launch_conv_wgrad_i8(l, A, g_out, gw, gb, acc_w, B, scw->partial, scw->floats * sizeof(float), sw,
+                                          (act_in_wgrad && l.act != B2RL_ACT_NONE) ? a : nullptr, pre, l.act);
+            if (rc == 1 && act_in_wgrad) { set_error("integer weight-gradient path refused a layer it had accepted"); return B2RL_ECUDA; }
             if (rc == 1 && tc_enabled())   // staged operands (conv_wst.cuh)
                 rc = launch_conv_wgrad_st(l, A, g_out, gw, gb, acc_w, B, scw->partial, scw->floats, sw);
             if (rc == 1 && tc_enabled())   // tcgen05 3xTF32, gathered operands, split over pixels
