@@ -122,7 +122,7 @@ static size_t max_partial_floats(const b2rl_net_desc &net, int64_t rows, int64_t
             if (brows) { n = conv_wgrad_st_partial_floats(net.enc[i], sm_count()); if (n > m) m = n; }
             if (brows && i == 0) {
                 n = conv_wi8_scratch_bytes((net.enc[i].out_c + 15) / 16 * 16, net.enc[i].in_c * net.enc[i].ksize * net.enc[i].ksize,
-                                           net.enc[i].out_c) / sizeof(float) + 64;
+                                           net.enc[i].out_c, sm_count()) / sizeof(float) + 64;
                 if (n > m) m = n;
             }
             if (brows && i > 0) { n = conv_dgrad_tc_scratch_floats(net.enc[i]); if (n > m) m = n; }
