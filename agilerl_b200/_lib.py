@@ -104,6 +104,8 @@ _SIGS = {
     "b2rl_tree_init": ([c_void_p, c_void_p, c_int64, c_void_p], c_int),
     "b2rl_tree_set": ([c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p], c_int),
     "b2rl_tree_set_range": ([c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_double, c_void_p], c_int),
+    "b2rl_tree_set_range_devmax": ([c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_double, c_void_p, c_double,
+                                    c_void_p], c_int),
     "b2rl_tree_set_from_priorities": ([c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_double,
                                        c_double, c_void_p, c_void_p], c_int),
     "b2rl_tree_retrieve": ([c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p], c_int),

@@ -484,16 +484,34 @@ class PrioritizedReplayBuffer(ReplayBuffer):
 
     @max_priority.setter
     def max_priority(self, value: float) -> None:
+        # an assigned value is THE maximum: the device scalar stops being authoritative (it is re-seeded from the host
+        # value before the next device-side fold, see _own_max_on_device) and cannot resurrect an older maximum
         self._max_priority = float(value)
+        self._dev_dirty = False
+
+    def _own_max_on_device(self) -> None:
+        """Call before enqueuing a device-side fold into ``_max_priority_dev`` (update_priorities_device, the captured
+        step): seeds the device scalar with the host value unless the device copy is already the authoritative one."""
+        if not self._dev_dirty:
+            self._max_priority_dev.fill_(self._max_priority)
+            self._dev_dirty = True
 
     def add(self, data: DataType) -> None:
-        """:296-309 — ring write, then the n new leaves get max_priority**alpha."""
+        """:296-309 — ring write, then the n new leaves get max_priority**alpha.  While the device path owns the running
+        maximum (after update_priorities_device) the leaf value is formed on the device from max(host, device) — no host
+        read of the device scalar per env step; the Python attribute reconciles lazily when it is read."""
         leaves, n = self._prepare(data)
         self._add_leaves(leaves, n)
-        p_alpha = float(self.max_priority) ** self.alpha
-        _lib.check(self._lib.b2rl_tree_set_range(self.sum_tree.data_ptr, self.min_tree.data_ptr, self._cap,
-                                                 self.tree_ptr, n, self.max_size, p_alpha,
-                                                 _lib.stream_ptr(self._dev)))
+        if self._dev_dirty:
+            _lib.check(self._lib.b2rl_tree_set_range_devmax(self.sum_tree.data_ptr, self.min_tree.data_ptr, self._cap,
+                                                            self.tree_ptr, n, self.max_size, float(self._max_priority),
+                                                            self._max_priority_dev.data_ptr(), float(self.alpha),
+                                                            _lib.stream_ptr(self._dev)))
+        else:
+            p_alpha = float(self._max_priority) ** self.alpha
+            _lib.check(self._lib.b2rl_tree_set_range(self.sum_tree.data_ptr, self.min_tree.data_ptr, self._cap,
+                                                     self.tree_ptr, n, self.max_size, p_alpha,
+                                                     _lib.stream_ptr(self._dev)))
         self.tree_ptr = (self.tree_ptr + n) % self.max_size
 
     def _update_priority(self, idx: int, priority: float) -> None:
@@ -617,8 +635,8 @@ class PrioritizedReplayBuffer(ReplayBuffer):
         idx = indices.reshape(-1)
         pri = priorities.reshape(-1)
         assert idx.is_cuda and pri.is_cuda and idx.dtype == torch.int64 and pri.dtype == torch.float32
+        self._own_max_on_device()
         _lib.check(self._lib.b2rl_tree_set_from_priorities(
             self.sum_tree.data_ptr, self.min_tree.data_ptr, self._cap, idx.data_ptr(), pri.data_ptr(), idx.numel(),
             float(self.alpha), 1e-5, self._max_priority_dev.data_ptr(), _lib.stream_ptr(self._dev)))
-        self._dev_dirty = True
 

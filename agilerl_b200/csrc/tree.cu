@@ -74,8 +74,10 @@ tree_set_kernel(double *__restrict__ st, double *__restrict__ mt, int64_t cap,
             last = (i + max_size >= n);  // a later lap over the ring overwrites this slot
         }
         double v;
-        if (kRange) v = range_val;
-        else if (kFromPriority) {
+        if (kRange) {
+            // max_priority given: range_val is the HOST maximum of raw priorities; the leaf is pow(max(host, device), alpha)
+            v = max_priority ? pow(fmax(range_val, *max_priority), alpha) : range_val;
+        } else if (kFromPriority) {
             double p = (double)pri[i];
             p = p < floor_ ? floor_ : p;          // max(priority, 1e-5), replay_buffer.py:425
             local_max = p > local_max ? p : local_max;
@@ -311,7 +313,9 @@ __global__ void tree_level_kernel(double *st, double *mt, int64_t first, int64_t
     }
 }
 __global__ void tree_range_leaves_kernel(double *st, double *mt, int64_t cap, int64_t tree_ptr,
-                                         int64_t n, int64_t max_size, double v) {
+                                         int64_t n, int64_t max_size, double v, const double *max_dev = nullptr,
+                                         double alpha = 0.0) {
+    if (max_dev) v = pow(fmax(v, *max_dev), alpha);
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     for (; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t id = (tree_ptr + i) % max_size;
@@ -488,8 +492,8 @@ int b2rl_tree_set_from_priorities(double *sum_tree, double *min_tree, int64_t ca
     return B2RL_OK;
 }
 
-int b2rl_tree_set_range(double *sum_tree, double *min_tree, int64_t cap, int64_t tree_ptr, int64_t n,
-                        int64_t max_size, double p_alpha, void *stream) {
+static int tree_set_range_impl(double *sum_tree, double *min_tree, int64_t cap, int64_t tree_ptr, int64_t n,
+                               int64_t max_size, double value, const double *max_dev, double alpha, void *stream) {
     B2RL_CHECK_ARG(is_pow2(cap), "capacity must be positive and a power of 2.");
     B2RL_CHECK_ARG(max_size > 0 && max_size <= cap, "max_size must be in (0, cap]");
     B2RL_CHECK_ARG(tree_ptr >= 0 && tree_ptr < max_size, "tree_ptr out of range");
@@ -497,13 +501,14 @@ int b2rl_tree_set_range(double *sum_tree, double *min_tree, int64_t cap, int64_t
     cudaStream_t s = as_stream(stream);
     if (n <= kTreeChunk) {
         tree_set_kernel<true, false><<<1, kTreeThreads, 0, s>>>(sum_tree, min_tree, cap, nullptr, nullptr, nullptr,
-                                                                 n, tree_ptr, max_size, p_alpha, 0.0, 0.0, nullptr);
+                                                                 n, tree_ptr, max_size, value, alpha, 0.0,
+                                                                 const_cast<double *>(max_dev));
         B2RL_LAUNCH_CHECK();
         return B2RL_OK;
     }
     const int64_t m = n < max_size ? n : max_size;   // more than a lap rewrites every slot
     tree_range_leaves_kernel<<<(int)((m + 255) / 256 < 2048 ? (m + 255) / 256 : 2048), 256, 0, s>>>(
-        sum_tree, min_tree, cap, tree_ptr, m, max_size, p_alpha);
+        sum_tree, min_tree, cap, tree_ptr, m, max_size, value, max_dev, alpha);
     B2RL_LAUNCH_CHECK();
     for (int64_t count = cap / 2; count >= 1; count /= 2) {
         const int blocks = (int)((count + 255) / 256 < 2048 ? (count + 255) / 256 : 2048);
@@ -511,6 +516,18 @@ int b2rl_tree_set_range(double *sum_tree, double *min_tree, int64_t cap, int64_t
         B2RL_LAUNCH_CHECK();
     }
     return B2RL_OK;
+}
+
+int b2rl_tree_set_range(double *sum_tree, double *min_tree, int64_t cap, int64_t tree_ptr, int64_t n,
+                        int64_t max_size, double p_alpha, void *stream) {
+    return tree_set_range_impl(sum_tree, min_tree, cap, tree_ptr, n, max_size, p_alpha, nullptr, 0.0, stream);
+}
+
+int b2rl_tree_set_range_devmax(double *sum_tree, double *min_tree, int64_t cap, int64_t tree_ptr, int64_t n,
+                               int64_t max_size, double host_max, const double *max_priority_dev, double alpha,
+                               void *stream) {
+    B2RL_CHECK_ARG(max_priority_dev != nullptr, "max_priority_dev is NULL");
+    return tree_set_range_impl(sum_tree, min_tree, cap, tree_ptr, n, max_size, host_max, max_priority_dev, alpha, stream);
 }
 
 int b2rl_tree_retrieve(const double *sum_tree, int64_t cap, const double *upperbound, int64_t n,

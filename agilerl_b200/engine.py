@@ -560,8 +560,8 @@ class LearnEngine:
         if plan.front is None:
             plan.capture()
         lib, cur = self.lib, _lib.stream_ptr(self.device)
+        per._own_max_on_device()               # the captured write-back folds max(priority) into the device scalar
         _lib.check(lib.b2rl_graph_launch(plan.front, ctypes.byref(st), cur))
-        per._dev_dirty = True
         if overlap:
             fwd_done = plan.fwd_done
             fwd_done.record(torch.cuda.current_stream(self.device))

@@ -78,6 +78,12 @@ int b2rl_tree_set(double *sum_tree, double *min_tree, int64_t cap, const int64_t
  * starting at tree_ptr, wrapping modulo max_size (not cap — quirk Q7), all set to p_alpha. */
 int b2rl_tree_set_range(double *sum_tree, double *min_tree, int64_t cap, int64_t tree_ptr,
                         int64_t n, int64_t max_size, double p_alpha, void *stream);
+/* Same, for a loop that keeps its running maximum on the device (b2rl_tree_set_from_priorities folds into
+ * *max_priority_dev): leaf = pow(max(host_max, *max_priority_dev), alpha) computed on device — no host read of the
+ * device scalar between an update and the next add (device pow: <= 1 ulp from glibc, like the update it follows). */
+int b2rl_tree_set_range_devmax(double *sum_tree, double *min_tree, int64_t cap, int64_t tree_ptr, int64_t n,
+                               int64_t max_size, double host_max, const double *max_priority_dev, double alpha,
+                               void *stream);
 
 /* Device variant used by the fused path: leaf = pow(max(priority, floor), alpha) computed ON
  * DEVICE (<= 1 ulp from glibc pow: leaves are NOT guaranteed bit-identical to the reference;

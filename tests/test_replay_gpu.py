@@ -173,3 +173,32 @@ def test_device_uniform_sampling_is_distinct_uniform_and_deterministic():
     exp = 200 * 512 / 16
     chi2 = float(((counts - exp) ** 2 / exp).sum())
     assert chi2 < 45.0, chi2            # 15 degrees of freedom: P(chi2 > 45) < 1e-4
+
+
+@pytest.mark.gpu
+def test_max_priority_host_device_ownership():
+    """add() after a device-side priority update must not read the device scalar back, and an assigned
+    max_priority must not be overridden by a stale device maximum."""
+    from agilerl_b200.components import PrioritizedReplayBuffer, Transition
+    buf = PrioritizedReplayBuffer(64, alpha=0.6, device="cuda")
+
+    def tr(n):
+        return Transition(obs=torch.zeros(n, 3), action=torch.zeros(n), reward=torch.zeros(n), next_obs=torch.zeros(n, 3),
+                          done=torch.zeros(n), batch_size=[n]).to_tensordict()
+
+    buf.add(tr(8))
+    idx = torch.arange(4, device="cuda")
+    buf.update_priorities_device(idx, torch.tensor([0.5, 7.0, 2.0, 3.0], device="cuda"))
+    assert buf._dev_dirty
+    buf.add(tr(2))                                   # leaves 8, 9 = pow(max(1.0, 7.0), alpha) without a host read
+    assert buf._dev_dirty                            # ... and without reconciling
+    torch.cuda.synchronize()
+    leaves = torch.tensor(buf.sum_tree.tree[buf._cap + 8:buf._cap + 10], dtype=torch.float64)
+    assert torch.allclose(leaves, torch.full((2,), 7.0 ** 0.6, dtype=torch.float64), rtol=1e-15)
+    assert buf.max_priority == 7.0 and not buf._dev_dirty
+    buf.max_priority = 2.0                           # user override: the old device maximum must not come back
+    buf.update_priorities_device(idx[:1], torch.tensor([1.5], device="cuda"))
+    assert buf.max_priority == 2.0
+    buf.add(tr(1))
+    torch.cuda.synchronize()
+    assert abs(buf.sum_tree.tree[buf._cap + 10] - 2.0 ** 0.6) < 1e-15
