@@ -112,7 +112,7 @@ class _PinnedRing:
         ev = self.events[k]
         if ev is None:
             ev = self.events[k] = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(device))
+        ev.record()
 
 
 class ReplayBuffer:

@@ -241,7 +241,7 @@ class LearnEngine:
     def join(self) -> None:
         """Make the current stream wait for an overlapped backward/optimiser tail, if one is pending."""
         if self._opt_done is not None:
-            torch.cuda.current_stream(self.device).wait_event(self._opt_done)
+            self._opt_done.wait()                  # current stream of the (current) device waits
             self._opt_done = None
 
     def workspace(self, rows: int, backward: bool) -> torch.Tensor:
@@ -425,7 +425,7 @@ class LearnEngine:
                 host = self._host_out[B] = torch.empty(B + 1, dtype=torch.float32).pin_memory()
             host.copy_(out, non_blocking=True)
             ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(self.device))
+            ev.record()
             self._readback = (host, ev, B)
 
         def tail():
@@ -438,7 +438,7 @@ class LearnEngine:
 
         if overlap:
             fwd_done = torch.cuda.Event()
-            fwd_done.record(torch.cuda.current_stream(self.device))
+            fwd_done.record()
             if after_loss is not None:
                 after_loss(priorities)
             if self._bwd_stream is None:
@@ -498,9 +498,9 @@ class LearnEngine:
         self.philox_offset += 2 * self.noise_count
         if plan.front is None:
             plan.capture(batch, gamma, driver, weights, weights_mode, support, hp, side_streams)
-        lib, cur = self.lib, torch.cuda.current_stream(self.device)
-        _lib.check(lib.b2rl_graph_launch(plan.front, ctypes.byref(st), cur.cuda_stream))
-        plan.rb_ev.record(cur)
+        lib = self.lib
+        _lib.check(lib.b2rl_graph_launch(plan.front, ctypes.byref(st), _lib.stream_ptr(self.device)))
+        plan.rb_ev.record()
         self._readback = (plan.host, plan.rb_ev, B)
         # backward + optimiser + noise reset under the caller's next calls (sampling, ingest, the next agent)
         if self._bwd_stream is None:
@@ -564,7 +564,7 @@ class LearnEngine:
         _lib.check(lib.b2rl_graph_launch(plan.front, ctypes.byref(st), cur))
         if overlap:
             fwd_done = plan.fwd_done
-            fwd_done.record(torch.cuda.current_stream(self.device))
+            fwd_done.record()
             if self._bwd_stream is None:
                 self._bwd_stream = torch.cuda.Stream(device=self.device)
             self._bwd_stream.wait_event(fwd_done)
