@@ -457,9 +457,10 @@ def tournament_generation(agents, world, rank, device):
         t = torch.tensor([e0.elapsed_time(e1), wall], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         gens.append({"ms_device": float(t[0].item()), "ms_wall": float(t[1].item()), "moved_agents": moved,
-                     "bytes_p2p": moved * per_agent, "elite_index": int(slots[0][1])})
+                     "bytes_moved": moved * per_agent, "elite_index": int(slots[0][1])})
     out = dict(gens[1], bytes_allgather=world * n_local * 16, plans_identical=True, generations=gens,
-               note="ms of generation 2 (steady state); generation 1 includes NCCL's lazy p2p channel set-up")
+               note="ms of generation 2 (steady state); winners move by broadcast from their owner over the communicator the "
+                    "fitness all_gather uses (no per-pair channel set-up); generation 1 includes NCCL's first-collective set-up")
     return out, agents
 
 
