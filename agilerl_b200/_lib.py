@@ -119,6 +119,7 @@ _SIGS = {
     "b2rl_per_sample_fused_state": ([c_void_p, c_void_p, c_int64, c_uint64, c_void_p, c_int64, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
     "b2rl_noise_reset_state": ([POINTER(NetDesc), c_void_p, c_uint64, c_void_p, c_int, c_void_p], c_int),
+    "b2rl_noise_reset_state_pair": ([POINTER(NetDesc), c_void_p, c_void_p, c_uint64, c_void_p, c_void_p], c_int),
     "b2rl_step_state_write": ([POINTER(StepState), c_void_p, c_void_p], c_int),
     "b2rl_copy_d2h": ([c_void_p, c_void_p, c_size_t, c_void_p], c_int),
     "b2rl_graph_begin": ([c_void_p], c_int),

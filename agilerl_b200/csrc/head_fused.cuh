@@ -60,7 +60,9 @@ __global__ void __launch_bounds__(kHeadThreads) head_fwd_kernel(const HeadDesc h
     const int64_t row = row0 + r;
     const bool rok = row < rows;
 
-    for (int chain = 0; chain < 2; ++chain) {
+    // gridDim.y == 2: the value chain and the advantage chain of a row tile run in different CTAs (the chains are
+    // independent and each is a sequence of dependent weight-streaming rounds: half the serial length per CTA)
+    for (int chain = blockIdx.y; chain < 2; chain += gridDim.y) {
         const int l0 = chain == 0 ? 0 : hd.n_val, l1 = chain == 0 ? hd.n_val : hd.n_val + hd.n_adv;
         if (l0 == l1) continue;
         __syncthreads();

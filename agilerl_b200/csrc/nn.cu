@@ -575,7 +575,8 @@ static int forward_pass(const b2rl_net_desc &net, const float *params, const flo
                 B2RL_CUDA(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
                 attr_set = true;
             }
-            head_fwd_kernel<<<(int)((rows + kHeadRows - 1) / kHeadRows), kHeadThreads, smem, s>>>(hd, latent, rows);
+            head_fwd_kernel<<<dim3((unsigned)((rows + kHeadRows - 1) / kHeadRows), (net.n_val > 0 && net.n_adv > 0) ? 2 : 1),
+                              kHeadThreads, smem, s>>>(hd, latent, rows);
             B2RL_LAUNCH_CHECK();
             return B2RL_OK;
         }
@@ -1300,14 +1301,16 @@ static int backward_pass(const b2rl_net_desc &net, const float *params, const fl
     if (tsg.n > 0) {
         int bx = (int)((maxn + 255) / 256);
         if (bx > 64) bx = 64;
-        if (use_noise) {
+        if (use_noise) {            // sigma and mu gradients of every noisy layer in ONE launch (segments are independent)
+            for (int i = 0; i < tm.n; ++i) tsg.s[tsg.n++] = tm.s[i];
             noisy_grad_kernel<<<dim3(bx, tsg.n), 256, 0, s>>>(tsg, accumulate);
             B2RL_LAUNCH_CHECK();
-        } else if (!accumulate) {   // eval-mode noisy layers: W = mu, sigma gets no gradient
-            for (int i = 0; i < tsg.n; ++i) B2RL_CUDA(cudaMemsetAsync(tsg.s[i].dst, 0, sizeof(float) * tsg.s[i].n, s));
+        } else {
+            if (!accumulate)        // eval-mode noisy layers: W = mu, sigma gets no gradient
+                for (int i = 0; i < tsg.n; ++i) B2RL_CUDA(cudaMemsetAsync(tsg.s[i].dst, 0, sizeof(float) * tsg.s[i].n, s));
+            noisy_grad_kernel<<<dim3(bx, tm.n), 256, 0, s>>>(tm, accumulate);
+            B2RL_LAUNCH_CHECK();
         }
-        noisy_grad_kernel<<<dim3(bx, tm.n), 256, 0, s>>>(tm, accumulate);
-        B2RL_LAUNCH_CHECK();
     }
     return B2RL_OK;
 }
@@ -1379,8 +1382,8 @@ __global__ void adam_polyak_kernel(float *__restrict__ p, float *__restrict__ g,
 // ------------------------------------------------------------------------------------------
 // NoisyLinear.reset_noise (custom_components.py:116-131)
 // ------------------------------------------------------------------------------------------
-struct NoiseSeg { float *eps_w; float *eps_b; int in, out; int64_t z_off; };
-struct NoiseTable { NoiseSeg s[B2RL_MAX_ENC + 2 * B2RL_MAX_HEAD]; int n; };
+struct NoiseSeg { float *eps_w; float *eps_b; int in, out; int64_t z_off; int which; };
+struct NoiseTable { NoiseSeg s[2 * (B2RL_MAX_ENC + 2 * B2RL_MAX_HEAD)]; int n; };      // room for two networks in one launch
 
 __device__ __forceinline__ float scale_noise(float x) {    // x.sign() * x.abs().sqrt()
     const float r = __fsqrt_rn(fabsf(x));
@@ -1390,8 +1393,8 @@ __device__ __forceinline__ float scale_noise(float x) {    // x.sign() * x.abs()
 template <bool kPhilox>
 __global__ void noise_reset_kernel(NoiseTable t, const float *__restrict__ normals, uint64_t seed, uint64_t offset,
                                    const b2rl_step_state *__restrict__ state = nullptr, int which = 0) {
-    if (state) offset = state->noise_offset[which];
     const NoiseSeg sg = t.s[blockIdx.y];
+    if (state) offset = state->noise_offset[which >= 0 ? which : sg.which];     // which < 0: per segment (two networks, one launch)
     const int64_t n = (int64_t)sg.in * sg.out;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
         const int o = (int)(e / sg.in), i = (int)(e - (int64_t)o * sg.in);
@@ -1409,12 +1412,12 @@ __global__ void noise_reset_kernel(NoiseTable t, const float *__restrict__ norma
     }
 }
 
-static int64_t build_noise_table(const b2rl_net_desc &net, float *eps, NoiseTable &t) {
-    t.n = 0;
+static int64_t build_noise_table(const b2rl_net_desc &net, float *eps, NoiseTable &t, bool append = false, int which = 0) {
+    if (!append) t.n = 0;
     int64_t z = 0;
     for_each_layer(net, [&](const b2rl_layer &l) {
         if (!l.noisy) return;
-        t.s[t.n++] = NoiseSeg{eps ? eps + l.we_off : nullptr, eps ? eps + l.be_off : nullptr, l.in_c, l.out_c, z};
+        t.s[t.n++] = NoiseSeg{eps ? eps + l.we_off : nullptr, eps ? eps + l.be_off : nullptr, l.in_c, l.out_c, z, which};
         z += l.in_c + l.out_c;
     });
     return z;
@@ -1511,6 +1514,7 @@ static int rainbow_prep(const b2rl_net_desc &net, const b2rl_learn_cfg &cfg, con
             if ((rc = launch_weight_split(l, W, ws.prep_split[which][i], ws.prep_split_floats[i], sp)) != B2RL_OK) return rc;
         }
     }
+    B2RL_CUDA(cudaMemsetAsync(ws.ticket, 0, sizeof(unsigned int), sp));      // the loss tail's last-CTA counter
     B2RL_CUDA(cudaEventRecord(fj->prep_done, sp));
     return B2RL_OK;
 }
@@ -1596,7 +1600,7 @@ static int rainbow_loss(const b2rl_net_desc &net, const b2rl_learn_cfg &cfg, con
     ProjCfg pc{(float)cfg.gamma, (float)cfg.v_min, (float)cfg.v_max, (float)cfg.delta_z};
     static const bool fuse_tail_env = !(getenv("B2RL_NO_TAIL_FUSE") && getenv("B2RL_NO_TAIL_FUSE")[0] == '1');
     if (!cfg.driver_shapes && fuse_q && fuse_tail_env && A * N >= N + 32) {
-        B2RL_CUDA(cudaMemsetAsync(ws.ticket, 0, sizeof(unsigned int), s));
+        if (!prepped) B2RL_CUDA(cudaMemsetAsync(ws.ticket, 0, sizeof(unsigned int), s));
         rainbow_tail_kernel<<<(int)B, 128, sm_t, s>>>(
             v_tg, adv_tg, ws.a_star, bufs.reward, bufs.done, bufs.support, pc, A, N, ws.proj, v_on, adv_on, v_on + B * N,
             adv_on + B * (int64_t)A * N, bufs.action, bufs.weights, cfg.weights_mode, B, cfg.accumulate, bufs.loss_elem,
@@ -1735,6 +1739,25 @@ int b2rl_noise_reset_state(const b2rl_net_desc *net_host, float *eps, uint64_t s
                            int which, void *stream) {
     B2RL_CHECK_ARG(net_host && eps && state && (which == 0 || which == 1), "bad arguments");
     return noise_reset(*net_host, eps, nullptr, seed, 0, as_stream(stream), state, which);
+}
+
+int b2rl_noise_reset_state_pair(const b2rl_net_desc *net_host, float *eps_actor, float *eps_target, uint64_t seed,
+                                const b2rl_step_state *state, void *stream) {
+    B2RL_CHECK_ARG(net_host && eps_actor && eps_target && state, "bad arguments");
+    NoiseTable t;
+    build_noise_table(*net_host, eps_actor, t, false, 0);
+    build_noise_table(*net_host, eps_target, t, true, 1);
+    if (t.n == 0) return B2RL_OK;
+    int64_t maxn = 0;
+    for (int i = 0; i < t.n; ++i) {
+        const int64_t n = (int64_t)t.s[i].in * t.s[i].out;
+        if (n > maxn) maxn = n;
+    }
+    int bx = (int)((maxn + 255) / 256);
+    if (bx > 64) bx = 64;
+    noise_reset_kernel<true><<<dim3(bx, t.n), 256, 0, as_stream(stream)>>>(t, nullptr, seed, 0, state, -1);
+    B2RL_LAUNCH_CHECK();
+    return B2RL_OK;
 }
 
 int b2rl_net_forward_q(const b2rl_net_desc *net_host, const float *params, const float *eps, int use_noise,

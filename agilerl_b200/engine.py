@@ -115,10 +115,8 @@ class _FusedPlan:
         try:
             _lib.check(lib.b2rl_rainbow_backward(desc, ctypes.byref(cfg), ctypes.byref(bufs), s))
             _lib.check(lib.b2rl_optim_step(desc, ctypes.byref(cfg), ctypes.byref(bufs), s))
-            _lib.check(lib.b2rl_noise_reset_state(desc, eng.actor.eps.data_ptr(), eng.philox_seed,
-                                                  self.state_dev.data_ptr(), 0, s))
-            _lib.check(lib.b2rl_noise_reset_state(desc, eng.target.eps.data_ptr(), eng.philox_seed,
-                                                  self.state_dev.data_ptr(), 1, s))
+            _lib.check(lib.b2rl_noise_reset_state_pair(desc, eng.actor.eps.data_ptr(), eng.target.eps.data_ptr(),
+                                                       eng.philox_seed, self.state_dev.data_ptr(), s))
         finally:
             _lib.check(lib.b2rl_graph_end(s, ctypes.byref(gt)))
         self.tail = gt.value
@@ -181,10 +179,8 @@ class _ApiPlan:
         try:
             _lib.check(lib.b2rl_rainbow_backward(desc, ctypes.byref(cfg), ctypes.byref(bufs), s))
             _lib.check(lib.b2rl_optim_step(desc, ctypes.byref(cfg), ctypes.byref(bufs), s))
-            _lib.check(lib.b2rl_noise_reset_state(desc, eng.actor.eps.data_ptr(), eng.philox_seed,
-                                                  self.state_dev.data_ptr(), 0, s))
-            _lib.check(lib.b2rl_noise_reset_state(desc, eng.target.eps.data_ptr(), eng.philox_seed,
-                                                  self.state_dev.data_ptr(), 1, s))
+            _lib.check(lib.b2rl_noise_reset_state_pair(desc, eng.actor.eps.data_ptr(), eng.target.eps.data_ptr(),
+                                                       eng.philox_seed, self.state_dev.data_ptr(), s))
         finally:
             _lib.check(lib.b2rl_graph_end(s, ctypes.byref(gt)))
         self.front, self.tail = gh.value, gt.value

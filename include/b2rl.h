@@ -241,6 +241,10 @@ int b2rl_noise_reset_philox(const b2rl_net_desc *net_host, float *eps, uint64_t 
 /* Same, offset = state->noise_offset[which] read on device (which: 0 actor, 1 target). */
 int b2rl_noise_reset_state(const b2rl_net_desc *net_host, float *eps, uint64_t seed, const b2rl_step_state *state,
                            int which, void *stream);
+/* The two resets of a learn step (actor: noise_offset[0], target: noise_offset[1]; dqn_rainbow.py:484-485) in ONE launch —
+ * same values as two b2rl_noise_reset_state calls with which = 0 and 1. */
+int b2rl_noise_reset_state_pair(const b2rl_net_desc *net_host, float *eps_actor, float *eps_target, uint64_t seed,
+                                const b2rl_step_state *state, void *stream);
 /* Number of standard normals one reset consumes. */
 int b2rl_noise_count(const b2rl_net_desc *net_host, int64_t *out_host);
 
