@@ -80,7 +80,7 @@ static int chain_backward(const Chain &c, const float *params, const float *x, i
     int rc = head_kernels_ready();
     if (rc != B2RL_OK) return rc;
     HeadBwdDesc hd;
-    hd.n_val = c.n; hd.n_adv = 0; hd.latent = c.in_features; hd.g_latent = g_in; hd.accumulate = 0; hd.n_ln = 0;
+    hd.n_val = c.n; hd.n_adv = 0; hd.latent = c.in_features; hd.g_latent = g_in; hd.latent_a = nullptr; hd.latent_act = B2RL_ACT_NONE; hd.accumulate = 0; hd.n_ln = 0;
     hd.maxdim = chain_maxdim(c);
     const int n_tiles = (int)((B + kHeadRows - 1) / kHeadRows);
     int ctas = 0;

@@ -110,6 +110,10 @@ struct Epilogue {
     int accumulate = 0;          // out += v instead of out = v
     float *db = nullptr;         // EPI_WGRAD: column n == wcols goes to db[m]
     int wcols = 0;
+    // EPI_STORE of an input gradient: fold the activation backward of the layer BELOW into the store
+    // (out = v * act'(mask_a[o]); mask_a = that layer's output, same layout as out) — one launch less
+    const float *mask_a = nullptr;
+    int mask_act = B2RL_ACT_NONE;
 };
 
 template <int KIND_, int OMK_, int ONK_>
@@ -141,6 +145,7 @@ __device__ __forceinline__ void epi_apply(const Epilogue &e, int m, int n, int64
             if (e.bias) v += e.bias[n];
             if (e.pre_out) e.pre_out[o] = v;
             v = act_fwd(e.act, v);
+            if (e.mask_a) v *= act_bwd(e.mask_act, 0.f, e.mask_a[o]);
             e.out[o] = e.accumulate ? e.out[o] + v : v;
         }
     }

@@ -175,6 +175,8 @@ struct HeadBwdDesc {
     int n_ln;
     int n_val, n_adv, latent, maxdim;
     float *g_latent;            // out: dL/dlatent [B, latent]
+    const float *latent_a;      // nullable: output of the layer that produced the latent; its activation backward is
+    int latent_act;             //           folded into the g_latent store (g *= act'(latent_a))
     int accumulate;             // add into dlnw/dlnb instead of overwriting
 };
 
@@ -285,7 +287,11 @@ __global__ void __launch_bounds__(kHeadThreads) head_bwd_kernel(const HeadBwdDes
     }
     __syncthreads();
     for (int i = og; i < hd.latent; i += kHeadLanes)
-        if (rok) hd.g_latent[row * hd.latent + i] = lat[r * hd.latent + i];
+        if (rok) {
+            float v = lat[r * hd.latent + i];
+            if (hd.latent_a) v *= act_bwd(hd.latent_act, 0.f, hd.latent_a[row * hd.latent + i]);
+            hd.g_latent[row * hd.latent + i] = v;
+        }
 }
 
 constexpr int kHeadWgMaxIn = 512;                    // widest layer input the fused weight-gradient kernel takes

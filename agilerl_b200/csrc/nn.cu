@@ -1036,13 +1036,18 @@ static int fork_to(const WgradSide *side, cudaStream_t from) {
     return B2RL_OK;
 }
 
+// activations whose derivative is a function of the layer's OUTPUT alone (no pre-activation buffer needed)
+static inline bool act_needs_output_only(int act) { return act == B2RL_ACT_RELU || act == B2RL_ACT_ELU || act == B2RL_ACT_TANH; }
+
 static int layer_backward(const b2rl_net_desc &net, const b2rl_layer &l, const float *W, const float *params,
                           const float *x_in,            // input activations of this layer (backward rows)
                           const ObsChunk *obs,          // first layer: where the observations come from
                           const LayerBuf &lb, int64_t row_off,  // forward buffers + offset of the backward rows
                           float *g_out,                 // dL/d(layer output) for the B backward rows
                           float *g_in, bool accumulate_gin, float *grads, float *gweff, int accumulate_grads,
-                          int64_t B, const Scratch &sc, cudaStream_t s, const WgradSide *side = nullptr) {
+                          int64_t B, const Scratch &sc, cudaStream_t s, const WgradSide *side = nullptr,
+                          bool skip_own_act = false,     // the layer above (or the head) already applied this layer's activation backward
+                          int below_act = B2RL_ACT_NONE) {   // fold the activation backward of the layer below (output x_in) into g_in
     const int64_t oe = layer_out_elems(l);
     const float *a = lb.a + row_off * oe;
     const float *pre = lb.pre ? lb.pre + row_off * oe : nullptr;
@@ -1050,12 +1055,12 @@ static int layer_backward(const b2rl_net_desc &net, const b2rl_layer &l, const f
     // (its channel-maximum pass reads the same planes), one launch less on the chain
     bool act_in_wgrad = false;
     Operand obs_op;
-    if (obs && l.kind == B2RL_LAYER_CONV && l.ln == B2RL_LN_NONE && tc_enabled() && !(side && g_in)) {
+    if (obs && l.kind == B2RL_LAYER_CONV && l.ln == B2RL_LN_NONE && tc_enabled() && !(side && g_in) && !skip_own_act) {
         obs_op.ptr = obs->ptr; obs_op.u8 = net.obs_u8; obs_op.normalize = net.normalize; obs_op.low = net.obs_low; obs_op.high = net.obs_high;
         act_in_wgrad = conv_wgrad_i8_ok(l, obs_op, B, sc.partial, sc.floats * sizeof(float));
     }
     // (1) through activation (+LayerNorm)
-    if (act_in_wgrad) {
+    if (act_in_wgrad || skip_own_act) {
         // nothing here
     } else if (l.ln != B2RL_LN_NONE) {
         const float *z = lb.z + row_off * oe;
@@ -1173,6 +1178,7 @@ static int layer_backward(const b2rl_net_desc &net, const b2rl_layer &l, const f
             A.ptr = g_out; A.row = map_stride(l.out_c); A.red = map_stride(1);
             Bm.ptr = W; Bm.row = map_stride(1); Bm.red = map_stride(l.in_c);
             epi.out = g_in; epi.om = map_stride(l.in_c); epi.on = map_stride(1); epi.accumulate = accumulate_gin ? 1 : 0;
+            if (below_act != B2RL_ACT_NONE && !accumulate_gin && x_in) { epi.mask_a = x_in; epi.mask_act = below_act; }
             rc = launch_igemm<OpTraits<EL_F32, MAP_STRIDE, MAP_STRIDE, true, false>,
                               OpTraits<EL_F32, MAP_STRIDE, MAP_STRIDE, false, false>,
                               EpiTraits<EPI_STORE, MAP_STRIDE, MAP_STRIDE>>(A, Bm, epi, (int)B, l.in_c, l.out_c, sc.partial,
@@ -1192,10 +1198,14 @@ static int backward_pass(const b2rl_net_desc &net, const float *params, const fl
     float *g_latent = lat.g;
     // heads: two fused launches (dZ/dX chain, then every dW/db) when the tile fits in shared memory
     bool head_done = false;
+    bool top_act_fused = false;
+    const b2rl_layer &ltop = net.enc[net.n_enc - 1];
+    const bool top_fusable = net.n_enc >= 2 && ltop.ln == B2RL_LN_NONE && act_needs_output_only(ltop.act);
     if (tc_enabled() && B <= 2048 && net.n_val + net.n_adv <= kHeadMaxLayers) {
         HeadBwdDesc hd;
         hd.n_val = net.n_val; hd.n_adv = net.n_adv; hd.latent = net.val[0].in_c;
         hd.g_latent = g_latent; hd.accumulate = accumulate; hd.n_ln = 0;
+        hd.latent_a = nullptr; hd.latent_act = B2RL_ACT_NONE;
         const int n_tiles = (int)((B + kHeadRows - 1) / kHeadRows);
         int maxdim = hd.latent, ctas = 0;
         size_t part_used = 0;
@@ -1244,6 +1254,7 @@ static int backward_pass(const b2rl_net_desc &net, const float *params, const fl
                                                (int)(kHeadWgSmemFloats * sizeof(float))));
                 attr_set = true;
             }
+            if (top_fusable) { hd.latent_a = latent; hd.latent_act = ltop.act; top_act_fused = true; }
             head_bwd_kernel<<<n_tiles, kHeadThreads, smem, s>>>(hd, B);
             B2RL_LAUNCH_CHECK();
             cudaStream_t sw = s;
@@ -1272,12 +1283,20 @@ static int backward_pass(const b2rl_net_desc &net, const float *params, const fl
         }
     }
     // encoder
+    bool skip_act = top_act_fused;          // the fused head backward already went through the top layer's activation
     for (int i = net.n_enc - 1; i >= 0; --i) {
         const b2rl_layer &l = net.enc[i];
         const float *x_in = i == 0 ? nullptr : pb.enc[i - 1].a + row_off * layer_out_elems(net.enc[i - 1]);
         float *g_in = i == 0 ? nullptr : pb.enc[i - 1].g;
+        // a linear layer's input gradient can carry the activation backward of the layer below it (not the first layer:
+        // the integer weight-gradient path applies that one itself)
+        int below = B2RL_ACT_NONE;
+        if (i >= 2 && l.kind == B2RL_LAYER_LINEAR && net.enc[i - 1].ln == B2RL_LN_NONE && act_needs_output_only(net.enc[i - 1].act))
+            below = net.enc[i - 1].act;
         int rc = layer_backward(net, l, eff_w(l, params, weff, use_noise), params, x_in, i == 0 ? &obs : nullptr,
-                                pb.enc[i], row_off, pb.enc[i].g, g_in, false, grads, gweff, accumulate, B, sc, s, side);
+                                pb.enc[i], row_off, pb.enc[i].g, g_in, false, grads, gweff, accumulate, B, sc, s, side,
+                                skip_act, below);
+        skip_act = below != B2RL_ACT_NONE;
         if (rc != B2RL_OK) return rc;
     }
     if (side) {                                           // every weight gradient must have landed before the tail
