@@ -7,9 +7,12 @@
 // core AS BYTES, with no conversion: the K-major [pixels x taps] tile the forward gather builds is, read as an MN-major
 // operand, exactly the [taps x pixels] tile this product needs (kind::i8 takes MN-major A; tools/probes/umma_mn_probe2.cu).
 // The precision is carried by G: per output channel, G / 2^E (2^E > max|G_c|, from chan_absmax_zero_kernel) is rounded to a
-// 38-bit fixed-point integer and written as five balanced base-256 int8 digits (rows d * n_pad + co of the B tile);
-// ONE tcgen05.mma kind::i8 with N = 5 * n_pad multiplies 32 pixels of a 128-tap tile with all five digit planes into exact
-// int32 accumulators, which stay in TMEM across all pixel tiles of the persistent CTA (<= 768 pixels: |sum| < 2^25).
+// 38-bit fixed-point integer q, shifted by 2^39 so that it is non-negative, and written as its five BYTES (rows
+// d * n_pad + co of the B tile, u8 x u8 MMA): extracting them is byte permutes, no carry arithmetic.  A sixth group of
+// rows holds a row of ones, so the same MMA also produces sum_pix x per tap, which removes the shift again:
+// sum x q = sum x (q + 2^39) - 2^39 * sum x, exactly, in int64 (pixels beyond the tensor cancel the same way).
+// ONE tcgen05.mma kind::i8 with N = 5 * n_pad + 16 multiplies 32 pixels of a 128-tap tile with all planes into exact
+// int32 accumulators, which stay in TMEM across all pixel tiles of the persistent CTA (<= 768 pixels: sums < 2^26).
 // The epilogue recombines the digits in int64 and writes one [Cout][taps] int64 partial per CTA (integer sums: exact and
 // order-independent, so the result is deterministic); wgrad_i8_finish_kernel adds the partials and scales them into dW / db.
 // (A first version added into one shared accumulator with 64-bit atomics: 1.2 M atomics on 8 192 addresses were half of
@@ -24,7 +27,8 @@
 namespace b2rl {
 
 constexpr int kWi8Digits = 5;
-constexpr int kWi8Bits = 37;                 // |q| < 2^37: five balanced digits, int64 sums over 2^25 pixel-bytes stay below 2^63
+constexpr int kWi8Bits = 37;                 // |q| < 2^37; q + 2^39 has five bytes; int64 sums over 2^25 pixel-bytes stay below 2^63
+constexpr int kWi8OnesRows = 16;             // extra B rows: row 0 = ones (sum of the frame bytes per tap), 15 rows of zero padding
 constexpr int kWi8Slots = 64;                // per-channel partial maxima (one block each, no atomics, no initialisation)
 constexpr int kWi8Threads = (kI8GatherWarps + 1 + kI8EpiWarps) * 32;
 
@@ -86,14 +90,14 @@ struct ConvWi8Params {
 };
 
 static inline size_t conv_wi8_smem_bytes(int n_pad, int k_pad) {
-    return 2 * (size_t)kTcBM * k_pad + 2 * (size_t)kWi8Digits * n_pad * kTcBM + (size_t)n_pad * 8 + 256 + 1024;
+    return 2 * (size_t)kTcBM * k_pad + 2 * (size_t)(kWi8Digits * n_pad + kWi8OnesRows) * kTcBM + (size_t)n_pad * 8 + 256 + 1024;
 }
 
 template <int KS, int CPT>
 __global__ void __launch_bounds__(kWi8Threads, 1) conv_wgrad_i8_kernel(const ConvWi8Params p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int rows_b = kWi8Digits * p.n_pad;                               // rows of the digit tile = columns of an accumulator
+    const int rows_b = kWi8Digits * p.n_pad + kWi8OnesRows;                // rows of the digit tile = columns of an accumulator
     const int MT = (p.Kc + kTcBM - 1) / kTcBM;
     const uint32_t a_bytes = (uint32_t)kTcBM * p.k_pad, b_bytes = (uint32_t)rows_b * kTcBM;
     const uint32_t sbase = (tc::smem_u32(smem_raw) + 127u) & ~127u;
@@ -130,6 +134,14 @@ __global__ void __launch_bounds__(kWi8Threads, 1) conv_wgrad_i8_kernel(const Con
         const int e = wi8_exponent(m);
         up_tab[c] = e > -100000 ? ldexp(1.0, kWi8Bits - e) : 0.0;
     }
+    // the ones rows of both B stages (the quantiser warps never touch them): row kWi8Digits * n_pad = 1, the rest 0
+    for (int e = tid; e < 2 * 8 * kWi8OnesRows * 4; e += kWi8Threads) {          // [stage][pixel chunk][row][4 words]
+        const int w = e & 3, row = (e >> 2) % kWi8OnesRows, chunk = (e >> 2) / kWi8OnesRows % 8, stg = (e >> 2) / (kWi8OnesRows * 8);
+        const int n = kWi8Digits * p.n_pad + row;
+        const uint32_t a = b_s + (uint32_t)stg * b_bytes + (uint32_t)chunk * lbo_b + (uint32_t)(n >> 3) * 128u + (uint32_t)(n & 7) * 16u + 4u * w;
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(row == 0 ? 0x01010101u : 0u) : "memory");
+    }
+    tc::fence_async_smem();
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -139,7 +151,8 @@ __global__ void __launch_bounds__(kWi8Threads, 1) conv_wgrad_i8_kernel(const Con
         // ================================ MMA warp ================================
         // A: MN-major u8, (tap m, pixel k) at (m/16)*SBO + (k/8)*LBO + (k%8)*16 + m%16 with SBO = 2048, LBO = 128 — the
         // forward kernel's K-major [pixel][tap] image.  B: K-major s8 digit planes.
-        const uint32_t idesc = tc::make_idesc_i8(kTcBM, rows_b) | (1u << 15);
+        // c = S32, a = U8, b = U8 (the shifted digits are unsigned bytes), A MN-major
+        const uint32_t idesc = (2u << 4) | (0u << 7) | (0u << 10) | (1u << 15) | ((uint32_t)(rows_b >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
         for (int i = 0; i < my_tiles; ++i) {
             const int s = i & 1;
             const uint32_t ph = (uint32_t)((i >> 1) & 1);
@@ -245,32 +258,30 @@ __global__ void __launch_bounds__(kWi8Threads, 1) conv_wgrad_i8_kernel(const Con
                     }
                 }
                 const double up = up_tab[co];
-                uint32_t dw[kWi8Digits][4];
-#pragma unroll
-                for (int d = 0; d < kWi8Digits; ++d) dw[d][0] = dw[d][1] = dw[d][2] = dw[d][3] = 0u;
+                // q' = rint(v * up) + 2^39 in [2^39 - 2^37, 2^39 + 2^37]: A = q' >> 16 (24 bits), t = q' & 65535; the five digit
+                // bytes of a pixel are bytes 2, 1, 0 of A and bytes 1, 0 of t — gathered four pixels at a time with byte permutes
+                uint32_t Aw[16], tw[16];
                 double qs = 0.0;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    // q = rint(v * up), |q| <= 2^37, split as A * 2^16 + B (0 <= B < 2^16) so that the balanced base-256 digits
-                    // come out of 32-bit integer arithmetic: d4, d3 from B (carry c2 in {0, 1}), d2, d1, d0 from A + c2
-                    const double qd = rint((double)v[j] * up);
-                    qs += qd;
+                    const double qr = rint((double)v[j] * up);
+                    qs += qr;
+                    const double qd = qr + 549755813888.0;
                     const int A = __double2int_rd(qd * 1.52587890625e-05);
-                    int t = __double2int_rn(qd - (double)A * 65536.0);
-                    const int d4 = ((t + 128) & 255) - 128;
-                    t = (t - d4) >> 8;
-                    const int d3 = ((t + 128) & 255) - 128;
-                    int u = A + ((t - d3) >> 8);
-                    const int d2 = ((u + 128) & 255) - 128;
-                    u = (u - d2) >> 8;
-                    const int d1 = ((u + 128) & 255) - 128;
-                    const int d0 = (u - d1) >> 8;
-                    const int sh = 8 * (j & 3);
-                    dw[4][j >> 2] |= (uint32_t)(d4 & 255) << sh;
-                    dw[3][j >> 2] |= (uint32_t)(d3 & 255) << sh;
-                    dw[2][j >> 2] |= (uint32_t)(d2 & 255) << sh;
-                    dw[1][j >> 2] |= (uint32_t)(d1 & 255) << sh;
-                    dw[0][j >> 2] |= (uint32_t)(d0 & 255) << sh;
+                    Aw[j] = (uint32_t)A;
+                    tw[j] = (uint32_t)__double2int_rn(qd - (double)A * 65536.0);
+                }
+                uint32_t dw[kWi8Digits][4];
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const uint32_t a0 = Aw[4 * w], a1 = Aw[4 * w + 1], a2 = Aw[4 * w + 2], a3 = Aw[4 * w + 3];
+                    const uint32_t t0 = tw[4 * w], t1 = tw[4 * w + 1], t2 = tw[4 * w + 2], t3 = tw[4 * w + 3];
+                    // byte k of four registers -> one word: two permutes pick the byte of each pair, a third joins the pairs
+                    dw[0][w] = __byte_perm(__byte_perm(a0, a1, 0x0062), __byte_perm(a2, a3, 0x0062), 0x5410);
+                    dw[1][w] = __byte_perm(__byte_perm(a0, a1, 0x0051), __byte_perm(a2, a3, 0x0051), 0x5410);
+                    dw[2][w] = __byte_perm(__byte_perm(a0, a1, 0x0040), __byte_perm(a2, a3, 0x0040), 0x5410);
+                    dw[3][w] = __byte_perm(__byte_perm(t0, t1, 0x0051), __byte_perm(t2, t3, 0x0051), 0x5410);
+                    dw[4][w] = __byte_perm(__byte_perm(t0, t1, 0x0040), __byte_perm(t2, t3, 0x0040), 0x5410);
                 }
                 bsum[pass & 1] += qs;
                 if (pass == 0) tc::mbar_wait(&empty[s], ph ^ 1u);               // the MMAs that read stage s two tiles ago have retired
@@ -296,6 +307,10 @@ __global__ void __launch_bounds__(kWi8Threads, 1) conv_wgrad_i8_kernel(const Con
             const int q = warp & 3, half = gw >> 2;
             for (int tt = half; tt < MT; tt += 2) {
                 const int tap = tt * kTcBM + q * 32 + lane;
+                uint32_t ones[8];
+                tc::tmem_ld8(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(tt * rows_b + kWi8Digits * p.n_pad), ones);
+                tc::tmem_ld_wait();
+                const long long shift = (long long)(int)ones[0] << 39;          // 2^39 * sum_pix x of this tap
                 for (int c0 = 0; c0 < p.n_pad; c0 += 8) {
                     uint32_t r[kWi8Digits][8];
 #pragma unroll
@@ -309,7 +324,7 @@ __global__ void __launch_bounds__(kWi8Threads, 1) conv_wgrad_i8_kernel(const Con
                             long long tsum = 0;
 #pragma unroll
                             for (int d = 0; d < kWi8Digits; ++d) tsum = tsum * 256 + (long long)(int)r[d][j];
-                            p.part[((int64_t)blockIdx.x * p.N + c0 + j) * p.Kc + tap] = tsum;        // lanes = consecutive taps: coalesced
+                            p.part[((int64_t)blockIdx.x * p.N + c0 + j) * p.Kc + tap] = tsum - shift;   // lanes = consecutive taps: coalesced
                         }
                     }
                 }
@@ -370,7 +385,8 @@ static bool conv_wgrad_i8_ok(const b2rl_layer &l, const Operand &X, int64_t rows
     const int KK = l.ksize * l.ksize, Kc = l.in_c * KK, P = l.out_h * l.out_w;
     const int n_pad = (l.out_c + 15) / 16 * 16, k_pad = (Kc + 31) / 32 * 32;
     const int MT = (Kc + kTcBM - 1) / kTcBM;
-    if (kWi8Digits * n_pad > 256 || MT * kWi8Digits * n_pad > 512 || n_pad > 64 || k_pad != Kc) return false;
+    const int rows_b = kWi8Digits * n_pad + kWi8OnesRows;
+    if (rows_b > 256 || MT * rows_b > 512 || n_pad > 64 || k_pad != Kc) return false;
     const int cpt = k_pad / 32;
     if (!(l.ksize == 8 ? (cpt == 2 || cpt == 4 || cpt == 8) : (cpt == 1 || cpt == 2 || cpt == 4 || cpt == 8))) return false;
     // int64 totals: pixels * 255 * 2^37 must stay below 2^63
@@ -380,9 +396,10 @@ static bool conv_wgrad_i8_ok(const b2rl_layer &l, const Operand &X, int64_t rows
     const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
     if (scratch == nullptr || conv_wi8_scratch_bytes(n_pad, Kc, l.out_c, grid) > scratch_bytes || reinterpret_cast<uintptr_t>(scratch) % 16 != 0)
         return false;
-    // a CTA's int32 accumulators see tiles_per_cta * 128 pixels of |x * digit| <= 255 * 128
+    // a CTA's int32 accumulators see tiles_per_cta * 128 pixels of x * digit <= 255 * 255; its int64 partial
+    // tiles_per_cta * 128 * 255 * 2^40
     const int64_t tiles_per_cta = (n_tiles + grid - 1) / grid;
-    return tiles_per_cta * kTcBM * 255 * 128 < ((int64_t)1 << 31);
+    return tiles_per_cta * kTcBM * 255 * 255 < ((int64_t)1 << 31) && tiles_per_cta * kTcBM * 255 < ((int64_t)1 << 22);
 }
 
 // g is dL/d(layer output); with act_a != NULL it is the gradient BEFORE the layer's activation backward, which the first
