@@ -275,8 +275,25 @@ __global__ void __launch_bounds__(kDsThreads, 1) conv_dgrad_st_kernel(const Conv
 }
 
 // dL/d(layer input) [rows, Cin, in_h, in_w] (overwritten).  returns B2RL_OK, or 1 when the layer is outside this kernel.
+// the combined class weights of a layer this kernel can take, into `scratch` (conv_dst_scratch_floats): what
+// launch_conv_dgrad_st does itself unless it is handed the result (presplit)
+static bool conv_dgrad_st_shape_ok(const b2rl_layer &l) {
+    if (!st_enabled('d') || l.ksize != 4 || l.stride != 2 || l.in_w % 2 != 0) return false;
+    const int ncp = (l.in_c + 15) / 16 * 16, k_pad = 4 * l.out_c;
+    return 4 * ncp <= 128 && k_pad % kStBK == 0 && k_pad / kStBK <= 4 * kStMaxBGroups;
+}
+static int launch_dgrad_st_weight_split(const b2rl_layer &l, const float *W, float *scratch, size_t scratch_cap, cudaStream_t s) {
+    if (!conv_dgrad_st_shape_ok(l) || scratch == nullptr || conv_dst_scratch_floats(l) > scratch_cap ||
+        reinterpret_cast<uintptr_t>(scratch) % 16 != 0)
+        return 1;
+    const int ncp = (l.in_c + 15) / 16 * 16, total = 4 * ncp * 4 * l.out_c;
+    dgrad_st_weight_split_kernel<<<(total + 255) / 256, 256, 0, s>>>(W, l.out_c, l.in_c, ncp, scratch);
+    B2RL_LAUNCH_CHECK();
+    return B2RL_OK;
+}
+
 static int launch_conv_dgrad_st(const b2rl_layer &l, const float *g, const float *W, float *g_in, int64_t rows, float *scratch,
-                                size_t scratch_cap, cudaStream_t s) {
+                                size_t scratch_cap, cudaStream_t s, const float *presplit = nullptr) {
     if (!st_enabled('d')) return 1;
     if (l.ksize != 4 || l.stride != 2 || l.in_w % 2 != 0) return 1;
     const int ncp = (l.in_c + 15) / 16 * 16, NT = 4 * ncp, k_pad = 4 * l.out_c;
@@ -284,7 +301,8 @@ static int launch_conv_dgrad_st(const b2rl_layer &l, const float *g, const float
     if (NT > 128 || k_pad % kStBK != 0 || k_pad / kStBK > 4 * kStMaxBGroups) return 1;
     if (((int64_t)l.out_c * Pg) % 4 != 0 || reinterpret_cast<uintptr_t>(g) % 16 != 0 || reinterpret_cast<uintptr_t>(g_in) % 8 != 0) return 1;
     if (rows * (int64_t)Pc > INT32_MAX || rows < 1) return 1;
-    if (scratch == nullptr || conv_dst_scratch_floats(l) > scratch_cap || reinterpret_cast<uintptr_t>(scratch) % 16 != 0) return 1;
+    if (!presplit && (scratch == nullptr || conv_dst_scratch_floats(l) > scratch_cap || reinterpret_cast<uintptr_t>(scratch) % 16 != 0))
+        return 1;
     const int M = (int)(rows * Pc), sms = sm_count();
     const uint32_t img_bytes = (uint32_t)l.out_c * Pg * 4u;
     int R = 0, rows_p = 0, n_tiles = 0, nseg_max = 0;
@@ -306,13 +324,13 @@ static int launch_conv_dgrad_st(const b2rl_layer &l, const float *g, const float
         R = 0;
     }
     if (R == 0) return 1;
-    {
+    if (!presplit) {
         const int total = NT * k_pad;
         dgrad_st_weight_split_kernel<<<(total + 255) / 256, 256, 0, s>>>(W, l.out_c, l.in_c, ncp, scratch);
         B2RL_LAUNCH_CHECK();
     }
     ConvDstParams p;
-    p.g = g; p.w_hl = scratch; p.dx = g_in; p.M = M;
+    p.g = g; p.w_hl = presplit ? presplit : scratch; p.dx = g_in; p.M = M;
     p.Cout = l.out_c; p.OH = l.out_h; p.OW = l.out_w; p.Cin = l.in_c; p.IH = l.in_h; p.IW = l.in_w;
     p.Yc = Yc; p.Xc = Xc; p.ncp = ncp; p.NT = NT; p.k_pad = k_pad;
     p.R = R; p.rows_p = rows_p; p.n_prod = (rows_p / 32) * (kStBK / 4); p.n_tiles = n_tiles; p.nseg_max = nseg_max;

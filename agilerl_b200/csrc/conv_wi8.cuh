@@ -48,8 +48,24 @@ __global__ void chan_absmax_zero_kernel(float *__restrict__ g, const float *__re
     const int64_t nb = (int64_t)gridDim.x * gridDim.y, bid = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
     for (int64_t i = bid * blockDim.x + threadIdx.x; i < acc_n; i += nb * blockDim.x) acc[i] = 0;
     float mx = 0.f;
+    const bool vec = (P & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 && (!a || (reinterpret_cast<uintptr_t>(a) & 15) == 0) && !pre;
     for (int64_t b = slot; b < rows; b += kWi8Slots) {
         const int64_t base = (b * N + co) * P;
+        if (vec) {                                   // planes are multiples of 16 bytes: four elements per access
+            float4 *g4 = reinterpret_cast<float4 *>(g + base);
+            const float4 *a4 = a ? reinterpret_cast<const float4 *>(a + base) : nullptr;
+            for (int i = threadIdx.x; i < P / 4; i += blockDim.x) {
+                float4 v = g4[i];
+                if (a4) {
+                    const float4 y = a4[i];
+                    v.x *= act_bwd(act, 0.f, y.x); v.y *= act_bwd(act, 0.f, y.y);
+                    v.z *= act_bwd(act, 0.f, y.z); v.w *= act_bwd(act, 0.f, y.w);
+                    g4[i] = v;
+                }
+                mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+            }
+            continue;
+        }
         for (int i = threadIdx.x; i < P; i += blockDim.x) {
             float v = g[base + i];
             if (a) {

@@ -157,6 +157,8 @@ struct LearnWS {
     size_t prep0_bytes;
     float *prep_split[2][B2RL_MAX_ENC];
     size_t prep_split_floats[B2RL_MAX_ENC];
+    float *prep_dsplit[B2RL_MAX_ENC];       // input-gradient weight layout of the online network's convolutions (backward)
+    size_t prep_dsplit_floats[B2RL_MAX_ENC];
     size_t bytes;
 };
 
@@ -184,7 +186,10 @@ static void carve_learn(const b2rl_net_desc &net, int64_t B, bool two_sided_onli
     ws.wsum = b.take<float>(4);
     ws.ticket = b.take<unsigned int>(4);
     ws.prep0 = nullptr; ws.prep0_bytes = 0;
-    for (int i = 0; i < B2RL_MAX_ENC; ++i) { ws.prep_split[0][i] = ws.prep_split[1][i] = nullptr; ws.prep_split_floats[i] = 0; }
+    for (int i = 0; i < B2RL_MAX_ENC; ++i) {
+        ws.prep_split[0][i] = ws.prep_split[1][i] = nullptr; ws.prep_split_floats[i] = 0;
+        ws.prep_dsplit[i] = nullptr; ws.prep_dsplit_floats[i] = 0;
+    }
     if (net.n_enc >= 1 && net.enc[0].kind == B2RL_LAYER_CONV) {
         const b2rl_layer &l0 = net.enc[0];
         const int K = l0.in_c * l0.ksize * l0.ksize;
@@ -196,6 +201,8 @@ static void carve_learn(const b2rl_net_desc &net, int64_t B, bool two_sided_onli
             ws.prep_split_floats[i] = conv_tc_wsplit_floats(net.enc[i]);
             ws.prep_split[0][i] = b.take<float>(ws.prep_split_floats[i]);
             ws.prep_split[1][i] = b.take<float>(ws.prep_split_floats[i]);
+            ws.prep_dsplit_floats[i] = conv_dst_scratch_floats(net.enc[i]);
+            ws.prep_dsplit[i] = b.take<float>(ws.prep_dsplit_floats[i]);
         }
     ws.bytes = b.off + 256;
 }
@@ -1047,7 +1054,8 @@ static int layer_backward(const b2rl_net_desc &net, const b2rl_layer &l, const f
                           float *g_in, bool accumulate_gin, float *grads, float *gweff, int accumulate_grads,
                           int64_t B, const Scratch &sc, cudaStream_t s, const WgradSide *side = nullptr,
                           bool skip_own_act = false,     // the layer above (or the head) already applied this layer's activation backward
-                          int below_act = B2RL_ACT_NONE) {   // fold the activation backward of the layer below (output x_in) into g_in
+                          int below_act = B2RL_ACT_NONE,   // fold the activation backward of the layer below (output x_in) into g_in
+                          const float *dsplit = nullptr) {  // input-gradient weights already laid out (b2rl_rainbow_prep)
     const int64_t oe = layer_out_elems(l);
     const float *a = lb.a + row_off * oe;
     const float *pre = lb.pre ? lb.pre + row_off * oe : nullptr;
@@ -1159,7 +1167,7 @@ static int layer_backward(const b2rl_net_desc &net, const b2rl_layer &l, const f
             const int P = l.out_h * l.out_w, KK = l.ksize * l.ksize;
             const int Kc = l.in_c * KK;
             if (!accumulate_gin && tc_enabled()) {     // parity-class convolutions on tcgen05 (no atomics)
-                const int rc_st = launch_conv_dgrad_st(l, g_out, W, g_in, B, sc.partial, sc.floats, s);
+                const int rc_st = launch_conv_dgrad_st(l, g_out, W, g_in, B, sc.partial, sc.floats, s, dsplit);
                 if (rc_st != 1) return rc_st;
                 const int rc_tc = launch_conv_dgrad_tc(l, g_out, W, g_in, B, sc.partial, sc.floats, s);
                 if (rc_tc != 1) return rc_tc;
@@ -1192,7 +1200,7 @@ static int layer_backward(const b2rl_net_desc &net, const b2rl_layer &l, const f
 static int backward_pass(const b2rl_net_desc &net, const float *params, const float *weff, bool use_noise,
                          const float *eps, PassBufs &pb, int64_t row_off, int64_t B, const ObsChunk &obs, float *grads,
                          float *gweff, int accumulate, const Scratch &sc, cudaStream_t s,
-                         const WgradSide *side = nullptr) {
+                         const WgradSide *side = nullptr, float *const *dsplit = nullptr) {
     const LayerBuf &lat = pb.enc[net.n_enc - 1];
     const float *latent = lat.a + row_off * layer_out_elems(net.enc[net.n_enc - 1]);
     float *g_latent = lat.g;
@@ -1295,7 +1303,7 @@ static int backward_pass(const b2rl_net_desc &net, const float *params, const fl
             below = net.enc[i - 1].act;
         int rc = layer_backward(net, l, eff_w(l, params, weff, use_noise), params, x_in, i == 0 ? &obs : nullptr,
                                 pb.enc[i], row_off, pb.enc[i].g, g_in, false, grads, gweff, accumulate, B, sc, s, side,
-                                skip_act, below);
+                                skip_act, below, (dsplit && conv_dgrad_st_shape_ok(l)) ? dsplit[i] : nullptr);
         skip_act = below != B2RL_ACT_NONE;
         if (rc != B2RL_OK) return rc;
     }
@@ -1531,6 +1539,11 @@ static int rainbow_prep(const b2rl_net_desc &net, const b2rl_learn_cfg &cfg, con
         for (int which = 0; which < 2; ++which) {
             const float *W = (which == 0 ? bufs.actor_params : bufs.target_params) + l.w_off;
             if ((rc = launch_weight_split(l, W, ws.prep_split[which][i], ws.prep_split_floats[i], sp)) != B2RL_OK) return rc;
+        }
+        // the backward of this step (same parameters: the optimiser runs after it) takes its input-gradient weights from here
+        if (ws.prep_dsplit[i] && conv_dgrad_st_shape_ok(l)) {
+            rc = launch_dgrad_st_weight_split(l, bufs.actor_params + l.w_off, ws.prep_dsplit[i], ws.prep_dsplit_floats[i], sp);
+            if (rc != B2RL_OK && rc != 1) return rc;
         }
     }
     B2RL_CUDA(cudaMemsetAsync(ws.ticket, 0, sizeof(unsigned int), sp));      // the loss tail's last-CTA counter
@@ -1830,9 +1843,11 @@ int b2rl_rainbow_backward(const b2rl_net_desc *net_host, const b2rl_learn_cfg *c
         side_storage = WgradSide{fj->side_bw, Scratch{ws.partial_bw, ws.partial_bw_floats}, fj->bw};
         side = &side_storage;
     }
+    // cfg.reserved_ bit 0: this step's b2rl_rainbow_prep laid out the input-gradient weights as well
     return backward_pass(*net_host, bufs_host->actor_params, ws.weff_actor, cfg_host->use_noise != 0,
                          bufs_host->actor_eps, ws.online, cfg_host->batch, cfg_host->batch, obs, bufs_host->grads,
-                         ws.gweff, cfg_host->accumulate, sc, as_stream(stream), side);
+                         ws.gweff, cfg_host->accumulate, sc, as_stream(stream), side,
+                         (cfg_host->reserved_ & 1) ? ws.prep_dsplit : nullptr);
 }
 
 int b2rl_optim_step(const b2rl_net_desc *net_host, const b2rl_learn_cfg *cfg_host, const b2rl_learn_bufs *bufs_host,
