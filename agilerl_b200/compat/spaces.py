@@ -113,6 +113,18 @@ class Dict(Space):
     def items(self):
         return self.spaces.items()
 
+    def get(self, k, default=None):          # gymnasium's Dict is a Mapping
+        return self.spaces.get(k, default)
+
+    def __contains__(self, k):
+        return k in self.spaces
+
+    def __iter__(self):
+        return iter(self.spaces)
+
+    def __len__(self):
+        return len(self.spaces)
+
 
 class Tuple(Space):
     def __init__(self, spaces, seed=None):

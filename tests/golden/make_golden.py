@@ -519,6 +519,125 @@ def gen_mutations():
     print("  mutations: reference outputs recorded")
 
 
+def gen_maddpg():
+    """MADDPG.learn (maddpg.py:571-740) on BASELINE config 5's shapes (4 agents x 18-dim
+    observations, 5-dim actions) — three consecutive learn calls of the UNMODIFIED reference, oracle == reference bit
+    for bit (losses, every actor / critic / target parameter).  A NaN reward and a NaN done (an agent that was not
+    alive) ride in the second batch: maddpg.py:683-694."""
+    from agilerl.algorithms.maddpg import MADDPG
+    from oracle import maddpg as om
+    ids = [f"agent_{i}" for i in range(4)]
+    obs_dims, act_dims = [18, 18, 18, 18], [5, 5, 5, 5]
+    obs_spaces = [spaces.Box(-1, 1, (d,), np.float32) for d in obs_dims]
+    act_spaces = [spaces.Box(-1, 1, (d,), np.float32) for d in act_dims]
+    B, steps = 32, 3
+    torch.manual_seed(11)
+    ref = MADDPG(obs_spaces, act_spaces, agent_ids=ids, batch_size=B, device="cpu")
+    a_hidden = list(ref.actors[ids[0]].head_net.net_config["hidden_size"])
+    c_hidden = list(ref.critics[ids[0]].head_net.net_config["hidden_size"])
+    a_specs = {a: om.actor_specs(o, d, head_hidden=a_hidden) for a, o, d in zip(ids, obs_dims, act_dims)}
+    c_head = om.critic_head_spec(sum(act_dims), head_hidden=c_hidden)
+    out = {"B": B, "steps": steps, "agent_ids": np.array(ids), "obs_dims": np.array(obs_dims), "act_dims": np.array(act_dims),
+           "a_hidden": np.array(a_hidden), "c_hidden": np.array(c_hidden), "gamma": ref.gamma, "tau": ref.tau,
+           "lr_actor": ref.lr_actor, "lr_critic": ref.lr_critic}
+    groups = (("actor", ref.actors), ("actor_target", ref.actor_targets), ("critic", ref.critics),
+              ("critic_target", ref.critic_targets))
+    for gname, nets in groups:
+        for a in ids:
+            out.update({f"{gname}0/{a}/{k}": v for k, v in sd_np(nets[a].state_dict()).items()})
+    orc = om.OracleMADDPG(ids, a_specs, c_head, {a: ref.actors[a].state_dict() for a in ids},
+                          {a: ref.actor_targets[a].state_dict() for a in ids}, {a: ref.critics[a].state_dict() for a in ids},
+                          {a: ref.critic_targets[a].state_dict() for a in ids}, gamma=ref.gamma, tau=ref.tau,
+                          lr_actor=ref.lr_actor, lr_critic=ref.lr_critic)
+
+    def batch(seed, with_nan):
+        g = torch.Generator().manual_seed(seed)
+        st = {a: torch.randn(B, o, generator=g) for a, o in zip(ids, obs_dims)}
+        ac = {a: torch.rand(B, d, generator=g) * 2 - 1 for a, d in zip(ids, act_dims)}
+        rw = {a: torch.randn(B, 1, generator=g) for a in ids}
+        ns = {a: torch.randn(B, o, generator=g) for a, o in zip(ids, obs_dims)}
+        dn = {a: (torch.rand(B, 1, generator=g) < 0.2).float() for a in ids}
+        if with_nan:
+            rw[ids[1]][3, 0] = float("nan")
+            dn[ids[1]][3, 0] = float("nan")
+            dn[ids[2]][7, 0] = float("nan")
+        return st, ac, rw, ns, dn
+
+    for s_ in range(steps):
+        e_ref, e_orc = batch(70 + s_, s_ == 1), batch(70 + s_, s_ == 1)
+        for fname, fd in zip(("obs", "action", "reward", "next_obs", "done"), e_ref):
+            for a in ids:
+                out[f"s{s_}_{fname}/{a}"] = fd[a].numpy().copy()
+        r_loss = ref.learn(e_ref)
+        o_loss = orc.learn(e_orc)
+        for a in ids:
+            assert tuple(r_loss[a]) == tuple(o_loss[a]), (s_, a, r_loss[a], o_loss[a])
+            out[f"s{s_}_actor_loss/{a}"], out[f"s{s_}_critic_loss/{a}"] = r_loss[a]
+        if s_ == 0:
+            for k, v in orc.last_grads.items():
+                out[f"s0_grad/{k}"] = v.numpy().copy()
+    for gname, nets, onets_ in (("actor", ref.actors, orc.actors), ("actor_target", ref.actor_targets, orc.actor_targets),
+                               ("critic", ref.critics, orc.critics), ("critic_target", ref.critic_targets, orc.critic_targets)):
+        for a in ids:
+            for k, v in nets[a].state_dict().items():
+                assert torch.equal(v, onets_[a][k].data), (gname, a, k)
+            out.update({f"{gname}1/{a}/{k}": v for k, v in sd_np(nets[a].state_dict()).items()})
+    save("maddpg_vector.npz", **out)
+    print(f"  maddpg: oracle == reference over {steps} learn calls (losses, every parameter, targets)")
+
+
+def gen_ma_replay():
+    """MultiAgentReplayBuffer (multi_agent_replay_buffer.py:30-242) of the UNMODIFIED reference: vectorised and
+    single-env saves into a 50-slot buffer until it has wrapped, then seeded ``random.sample`` batches; the oracle
+    ring reproduces every sampled tensor bit for bit."""
+    import random
+    from agilerl.components.multi_agent_replay_buffer import MultiAgentReplayBuffer
+    from oracle import maddpg as om
+    ids = ["agent_0", "agent_1", "agent_2"]
+    fields = ["obs", "action", "reward", "next_obs", "done"]
+    dims = {"agent_0": (6, 2), "agent_1": (4, 3), "agent_2": (6, 2)}
+    cap, E = 50, 4
+    ref, orc = MultiAgentReplayBuffer(cap, fields, ids, device="cpu"), om.OracleMAReplay(cap, fields, ids)
+    rng = np.random.default_rng(5)
+    out = {"cap": cap, "E": E, "agent_ids": np.array(ids), "fields": np.array(fields),
+           "obs_dims": np.array([dims[a][0] for a in ids]), "act_dims": np.array([dims[a][1] for a in ids])}
+    n_steps = 0
+    for t in range(20):
+        vect = t % 5 != 4                      # every fifth step comes from a single (un-vectorised) environment
+        lead = (E,) if vect else ()
+        obs = {a: rng.standard_normal(lead + (dims[a][0],)).astype(np.float32) for a in ids}
+        act = {a: rng.uniform(-1, 1, lead + (dims[a][1],)).astype(np.float32) for a in ids}
+        rew = {a: (rng.standard_normal(E) if vect else float(rng.standard_normal())) for a in ids}
+        nobs = {a: rng.standard_normal(lead + (dims[a][0],)).astype(np.float32) for a in ids}
+        done = {a: ((rng.uniform(size=E) < 0.3) if vect else bool(rng.uniform() < 0.3)) for a in ids}
+        if t == 17:                            # an agent that was not alive: NaN reward / done (float arrays)
+            rew["agent_1"] = np.array(rew["agent_1"], dtype=np.float64); rew["agent_1"][1] = np.nan
+            done["agent_1"] = np.array(done["agent_1"], dtype=np.float64); done["agent_1"][1] = np.nan
+        ref.save_to_memory(obs, act, rew, nobs, done, is_vectorised=vect)
+        orc.save_to_memory(obs, act, rew, nobs, done, is_vectorised=vect)
+        out[f"t{t}_vect"] = int(vect)
+        for fname, fd in zip(fields, (obs, act, rew, nobs, done)):
+            for a in ids:
+                out[f"t{t}_{fname}/{a}"] = np.asarray(fd[a])
+        n_steps += 1
+        assert len(ref) == len(orc) and ref.counter == orc.counter
+    out["n_steps"], out["final_len"], out["final_counter"] = n_steps, len(ref), ref.counter
+    for c, (seed, B) in enumerate([(1, 8), (2, 16), (3, 50)]):
+        random.seed(seed)
+        r = ref.sample(B)
+        random.seed(seed)
+        o = orc.sample(B)
+        for fname, rd, od_ in zip(fields, r, o):
+            for a in ids:
+                assert rd[a].dtype == od_[a].dtype == torch.float32 and rd[a].shape == od_[a].shape, (fname, a)
+                assert torch.equal(torch.nan_to_num(rd[a], nan=-7.0), torch.nan_to_num(od_[a], nan=-7.0)), (c, fname, a)
+                out[f"sample{c}_{fname}/{a}"] = rd[a].numpy().copy()
+        out[f"sample{c}_seed"], out[f"sample{c}_B"] = seed, B
+    out["n_samples"] = 3
+    save("ma_replay.npz", **out)
+    print("  multi-agent replay: oracle == reference on every sampled leaf (3 seeded batches, wrapped buffer)")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)   # deterministic CPU reductions while generating
     if len(sys.argv) > 1 and sys.argv[1] == "mutations":
@@ -526,6 +645,10 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "ddpg_td3":
         gen_ddpg_td3()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "maddpg":
+        gen_maddpg()
+        gen_ma_replay()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "gae":
         gen_gae()
@@ -538,3 +661,5 @@ if __name__ == "__main__":
     gen_ddpg_td3()
     gen_gae()
     gen_mutations()
+    gen_maddpg()
+    gen_ma_replay()
