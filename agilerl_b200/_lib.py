@@ -85,6 +85,29 @@ class DdpgBufs(Structure):
     ]
 
 
+B2RL_MAX_AGENTS = 8
+
+
+class MaddpgCfg(Structure):
+    _fields_ = [
+        ("batch", c_int64), ("n_agents", c_int32), ("reserved_", c_int32),
+        ("gamma", c_double), ("tau", c_double),
+        ("lr_actor", c_double), ("lr_critic", c_double), ("beta1", c_double), ("beta2", c_double), ("adam_eps", c_double),
+        ("bc1_actor", c_double), ("bc2_actor", c_double), ("bc1_critic", c_double), ("bc2_critic", c_double),
+    ]
+
+
+class MaddpgBufs(Structure):
+    _fields_ = [
+        ("actor", c_void_p * B2RL_MAX_AGENTS), ("actor_target", c_void_p * B2RL_MAX_AGENTS),
+        ("actor_grads", c_void_p * B2RL_MAX_AGENTS), ("actor_m", c_void_p * B2RL_MAX_AGENTS), ("actor_v", c_void_p * B2RL_MAX_AGENTS),
+        ("critic", c_void_p * B2RL_MAX_AGENTS), ("critic_target", c_void_p * B2RL_MAX_AGENTS),
+        ("critic_grads", c_void_p * B2RL_MAX_AGENTS), ("critic_m", c_void_p * B2RL_MAX_AGENTS), ("critic_v", c_void_p * B2RL_MAX_AGENTS),
+        ("obs", c_void_p), ("next_obs", c_void_p), ("action", c_void_p), ("reward", c_void_p), ("done", c_void_p),
+        ("losses", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+    ]
+
+
 class StepState(Structure):
     _fields_ = [
         ("beta", c_double), ("size", c_int64), ("sample_offset", c_uint64), ("noise_offset", c_uint64 * 2),
@@ -129,6 +152,10 @@ _SIGS = {
     "b2rl_graph_destroy": ([c_void_p], c_int),
     "b2rl_ddpg_workspace_bytes": ([POINTER(NetDesc), POINTER(NetDesc), c_int64, POINTER(c_size_t)], c_int),
     "b2rl_ddpg_learn": ([POINTER(NetDesc), POINTER(NetDesc), POINTER(DdpgCfg), POINTER(DdpgBufs), c_void_p], c_int),
+    "b2rl_maddpg_workspace_bytes": ([c_void_p, c_void_p, c_int, c_int64, POINTER(c_size_t)], c_int),
+    "b2rl_maddpg_learn": ([c_void_p, c_void_p, POINTER(MaddpgCfg), POINTER(MaddpgBufs), c_void_p], c_int),
+    "b2rl_gaussian_mutate": ([c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_uint64,
+                              c_double, c_int64, c_void_p], c_int),
     "b2rl_actor_workspace_bytes": ([POINTER(NetDesc), c_int64, POINTER(c_size_t)], c_int),
     "b2rl_actor_forward": ([POINTER(NetDesc), c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p], c_int),
     "b2rl_sample_uniform_distinct": ([c_uint64, c_uint64, c_int64, c_int64, c_void_p, c_void_p], c_int),

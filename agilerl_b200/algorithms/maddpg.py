@@ -1,0 +1,315 @@
+"""``MADDPG`` — drop-in for agilerl/algorithms/maddpg.py:39-800 on the CUDA path (BASELINE configs[4]:
+4 agents x 18-dim observations, shared replay), for vector (1-D ``Box``) observations and continuous (``Box``) actions.
+
+Same constructor (maddpg.py:103-131) and attributes (``agent_ids, n_agents, possible_observation_spaces,
+possible_action_spaces, action_dims, actors, actor_targets, critics, critic_targets, actor_optimizers,
+critic_optimizers, batch_size, lr_actor, lr_critic, learn_step, gamma, tau, mut, O_U_noise, expl_noise, mean_noise,
+current_noise ...``); ``learn(experiences) -> {agent_id: (actor_loss, critic_loss)}`` (:571-628), ``get_action(obs,
+infos) -> (processed, raw)`` (:428-532), ``action_noise`` / ``reset_action_noise``, ``soft_update``, ``clone``.
+The body of ``learn`` — every agent's target action, centralised critic TD step, actor step through the updated critic
+and all soft updates — is ONE C call, ``b2rl_maddpg_learn`` (csrc/maddpg.cuh).
+
+The batch may be the reference's tuple of ``{agent_id: tensor}`` dicts or what ``MultiAgentReplayBuffer.sample``
+returns here (dicts carrying the already concatenated ``[B, sum]`` matrices: no ``torch.cat`` on the way in).
+
+Not implemented (raises): image / Dict sub-observations, discrete (Gumbel-softmax) actors, custom networks,
+``accelerator``, architecture mutations of the sub-networks."""
+from __future__ import annotations
+
+import copy
+import ctypes
+import warnings
+from collections import OrderedDict
+from typing import Any
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..compat import spaces
+from ..networks.actors import DeterministicActor, MultiInputContinuousQNetwork
+from .core.base import EvolvableAlgorithm
+from .core.registry import HyperparameterConfig, NetworkGroup, OptimizerConfig
+from .td3 import _AdamState
+
+
+def concatenate_spaces(space_list) -> spaces.Box:
+    """utils/algo_utils.py concatenate_spaces for 1-D Boxes."""
+    low = np.concatenate([np.asarray(s.low, np.float32).reshape(-1) for s in space_list])
+    high = np.concatenate([np.asarray(s.high, np.float32).reshape(-1) for s in space_list])
+    return spaces.Box(low, high, (int(low.shape[0]),), np.float32)
+
+
+class MADDPG(EvolvableAlgorithm):
+    def __init__(self, observation_spaces, action_spaces, agent_ids: list[str] | None = None, O_U_noise: bool = True,
+                 expl_noise: float = 0.1, vect_noise_dim: int = 1, mean_noise: float = 0.0, theta: float = 0.15,
+                 dt: float = 1e-2, index: int = 0, hp_config: HyperparameterConfig | None = None,
+                 net_config: dict[str, Any] | None = None, batch_size: int = 64, lr_actor: float = 0.001,
+                 lr_critic: float = 0.01, learn_step: int = 5, gamma: float = 0.95, tau: float = 0.01, mut: str | None = None,
+                 normalize_images: bool = True, actor_networks=None, critic_networks=None, device: str = "cuda",
+                 accelerator: Any | None = None, torch_compiler: str | None = None, wrap: bool = True) -> None:
+        super().__init__(index, hp_config, device, accelerator, torch_compiler, name="MADDPG")
+        if isinstance(observation_spaces, (spaces.Dict, dict)):
+            agent_ids = list(observation_spaces.keys()) if agent_ids is None else agent_ids
+            observation_spaces = [observation_spaces[a] for a in agent_ids]
+        if isinstance(action_spaces, (spaces.Dict, dict)):
+            action_spaces = [action_spaces[a] for a in agent_ids]
+        assert agent_ids is not None, "Agent IDs must be specified if observation spaces are passed as a list."
+        assert len(agent_ids) == len(observation_spaces) == len(action_spaces), \
+            "Number of agent IDs must match number of observation and action spaces."
+        assert learn_step >= 1, "Learn step must be greater than or equal to one."
+        assert isinstance(learn_step, int), "Learn step rate must be an integer."
+        assert isinstance(batch_size, int), "Batch size must be an integer."
+        assert batch_size >= 1, "Batch size must be greater than or equal to one."
+        assert isinstance(lr_actor, float), "Actor learning rate must be a float."
+        assert lr_actor > 0, "Actor learning rate must be greater than zero."
+        assert isinstance(lr_critic, float), "Critic learning rate must be a float."
+        assert lr_critic > 0, "Critic learning rate must be greater than zero."
+        assert isinstance(gamma, float), "Gamma must be a float."
+        assert isinstance(tau, float), "Tau must be a float."
+        assert tau > 0, "Tau must be greater than zero."
+        assert isinstance(wrap, bool), "Wrap models flag must be boolean value True or False."
+        if actor_networks is not None or critic_networks is not None:
+            raise NotImplementedError("custom actor / critic networks are not implemented for MADDPG on the CUDA path")
+        if len(agent_ids) > _lib.B2RL_MAX_AGENTS:
+            raise NotImplementedError(f"at most {_lib.B2RL_MAX_AGENTS} agents per MADDPG instance on the CUDA path")
+        for a, osp, asp in zip(agent_ids, observation_spaces, action_spaces):
+            if not (isinstance(osp, spaces.Box) and len(osp.shape) == 1):
+                raise NotImplementedError(f"{a}: only 1-D Box observations are implemented for MADDPG on the CUDA path")
+            if not (isinstance(asp, spaces.Box) and len(asp.shape) == 1):
+                raise NotImplementedError(f"{a}: only continuous (1-D Box) actions are implemented for MADDPG on the CUDA path")
+        self.agent_ids, self.n_agents = list(agent_ids), len(agent_ids)
+        self.observation_spaces, self.action_spaces = list(observation_spaces), list(action_spaces)
+        self.possible_observation_spaces = OrderedDict(zip(self.agent_ids, observation_spaces))
+        self.possible_action_spaces = OrderedDict(zip(self.agent_ids, action_spaces))
+        self.observation_space = spaces.Dict(self.possible_observation_spaces)
+        self.action_space = spaces.Dict(self.possible_action_spaces)
+        self.action_dims = {a: int(s.shape[0]) for a, s in self.possible_action_spaces.items()}
+        self.obs_dims = {a: int(s.shape[0]) for a, s in self.possible_observation_spaces.items()}
+        self.normalize_images = normalize_images
+        self.batch_size, self.lr_actor, self.lr_critic, self.learn_step = batch_size, lr_actor, lr_critic, learn_step
+        self.gamma, self.tau, self.mut, self.net_config = gamma, tau, mut, net_config
+        self.learn_counter = 0
+        self.O_U_noise, self.vect_noise_dim, self.theta, self.dt, self.sqdt = O_U_noise, vect_noise_dim, theta, dt, dt ** 0.5
+        mk = lambda v: v if isinstance(v, dict) else {a: v * torch.ones(vect_noise_dim, d) for a, d in self.action_dims.items()}
+        self.sample_gaussian = {a: torch.zeros(vect_noise_dim, d) for a, d in self.action_dims.items()}
+        self.expl_noise, self.mean_noise = mk(expl_noise), mk(mean_noise)
+        self.current_noise = {a: torch.zeros(vect_noise_dim, d) for a, d in self.action_dims.items()}
+
+        # networks (maddpg.py:272-350): per-agent actors; every critic sees all observations and all actions
+        net_config = {} if net_config is None else copy.deepcopy(net_config)
+        if any(k in net_config for k in self.agent_ids):
+            raise NotImplementedError("per-agent net_config dictionaries are not implemented on the CUDA path")
+        actor_cfg = dict(net_config)
+        head_config = actor_cfg.get("head_config")
+        if head_config is None:
+            head_config = dict(hidden_size=[64])
+        head_config = {k: v for k, v in head_config.items() if k != "output_activation"}
+        actor_cfg["head_config"] = head_config
+        latent_dim = int(actor_cfg.get("latent_dim", 32))
+        critic_head = copy.deepcopy(head_config)
+        all_act = concatenate_spaces(self.action_spaces)
+        mk_a = lambda a: DeterministicActor(self.possible_observation_spaces[a], self.possible_action_spaces[a],
+                                            device=self.device, **copy.deepcopy(actor_cfg))
+        mk_c = lambda: MultiInputContinuousQNetwork(self.observation_space, all_act, latent_dim=latent_dim,
+                                                    head_config=critic_head, device=self.device)
+        self.actors = OrderedDict((a, mk_a(a)) for a in self.agent_ids)
+        self.critics = OrderedDict((a, mk_c()) for a in self.agent_ids)
+        self.actor_targets = OrderedDict((a, mk_a(a)) for a in self.agent_ids)
+        self.critic_targets = OrderedDict((a, mk_c()) for a in self.agent_ids)
+        for a in self.agent_ids:
+            self.actors[a].encoder.disable_mutations()                                   # maddpg.py:324-326
+            self.actor_targets[a].load_state_dict(self.actors[a].state_dict())
+            self.critic_targets[a].load_state_dict(self.critics[a].state_dict())
+        self.register_network_group(NetworkGroup(eval_network="actors", shared_networks="actor_targets", policy=True))
+        self.register_network_group(NetworkGroup(eval_network="critics", shared_networks="critic_targets"))
+        self.registry.register_optimizer(OptimizerConfig(name="actor_optimizers", networks=["actors"], lr="lr_actor"))
+        self.registry.register_optimizer(OptimizerConfig(name="critic_optimizers", networks=["critics"], lr="lr_critic"))
+        self._bind_engine()
+
+    # -- engine state ------------------------------------------------------------------------------------
+    def _bind_engine(self, keep: dict | None = None) -> None:
+        self.actor_optimizers = OrderedDict((a, _AdamState(self.actors[a], self.lr_actor)) for a in self.agent_ids)
+        self.critic_optimizers = OrderedDict((a, _AdamState(self.critics[a], self.lr_critic)) for a in self.agent_ids)
+        if keep:
+            for a in self.agent_ids:
+                self.actor_optimizers[a].load_state_dict(keep["actors"][a])
+                self.critic_optimizers[a].load_state_dict(keep["critics"][a])
+        n = self.n_agents
+        self._actor_descs = (ctypes.POINTER(_lib.NetDesc) * n)(*[ctypes.pointer(self.actors[a].layout.desc) for a in self.agent_ids])
+        self._critic_descs = (ctypes.POINTER(_lib.NetDesc) * n)(*[ctypes.pointer(self.critics[a].layout.desc) for a in self.agent_ids])
+        self._ws: dict = {}
+
+    def _opt_state(self) -> dict:
+        return {"actors": {a: o.state_dict() for a, o in self.actor_optimizers.items()},
+                "critics": {a: o.state_dict() for a, o in self.critic_optimizers.items()}}
+
+    def reinit_optimizers(self, optimizer=None) -> None:
+        self._bind_engine()
+
+    def __setattr__(self, name, value):
+        object.__setattr__(self, name, value)
+        if name == "lr_actor":
+            for o in self.__dict__.get("actor_optimizers", {}).values():
+                o.lr = value
+        if name == "lr_critic":
+            for o in self.__dict__.get("critic_optimizers", {}).values():
+                o.lr = value
+
+    def clone(self, index: int | None = None, wrap: bool = True):
+        """core/base.py:855-917: same constructor arguments, then networks, optimiser state and the run-time attributes."""
+        kw = dict(observation_spaces=self.observation_spaces, action_spaces=self.action_spaces, agent_ids=list(self.agent_ids),
+                  O_U_noise=self.O_U_noise, vect_noise_dim=self.vect_noise_dim, theta=self.theta, dt=self.dt,
+                  index=self.index if index is None else index, hp_config=copy.deepcopy(self.registry.hp_config),
+                  net_config=copy.deepcopy(self.net_config), batch_size=self.batch_size, lr_actor=self.lr_actor,
+                  lr_critic=self.lr_critic, learn_step=self.learn_step, gamma=self.gamma, tau=self.tau, mut=self.mut,
+                  normalize_images=self.normalize_images, device=self.device)
+        c = type(self)(**kw)
+        for a in self.agent_ids:
+            for src, dst in ((self.actors, c.actors), (self.actor_targets, c.actor_targets), (self.critics, c.critics),
+                             (self.critic_targets, c.critic_targets)):
+                dst[a].buffers.copy_from(src[a].buffers)
+        c._bind_engine(keep=self._opt_state())
+        c.expl_noise = {a: v.clone() for a, v in self.expl_noise.items()}
+        c.mean_noise = {a: v.clone() for a, v in self.mean_noise.items()}
+        c.current_noise = {a: v.clone() for a, v in self.current_noise.items()}
+        c.scores, c.fitness, c.steps = list(self.scores), list(self.fitness), list(self.steps)
+        c.learn_counter = self.learn_counter
+        return c
+
+    # -- acting (maddpg.py:428-558) ------------------------------------------------------------------------
+    def preprocess_observation(self, observation: dict) -> dict:
+        out = {}
+        for a in self.agent_ids:
+            o = observation[a]
+            if not isinstance(o, torch.Tensor):
+                o = torch.as_tensor(np.asarray(o))
+            o = o.to(self._dev, dtype=torch.float32)
+            out[a] = o.unsqueeze(0) if o.ndim == 1 else o
+        return out
+
+    def get_action(self, obs: dict, infos: dict | None = None, *args, **kwargs):
+        if infos is not None and any(isinstance(v, dict) and v.get("env_defined_actions") is not None for v in infos.values()):
+            raise NotImplementedError("env_defined_actions are not implemented on the CUDA path")
+        states = self.preprocess_observation(obs)
+        processed, raw = OrderedDict(), OrderedDict()
+        for a in self.agent_ids:
+            actor = self.actors[a]
+            actions = actor(states[a]).cpu()
+            if self.training:
+                actions = torch.clamp(actions + self.action_noise(a), -1.0, 1.0)
+            processed[a] = DeterministicActor.rescale_action(actions, actor.action_low, actor.action_high,
+                                                             actor.output_activation).numpy()
+            raw[a] = actions.numpy()
+        return processed, raw
+
+    def action_noise(self, agent_id: str) -> torch.Tensor:
+        """maddpg.py:534-558 (torch's global CPU generator)."""
+        if self.O_U_noise:
+            noise = (self.current_noise[agent_id] + self.theta * (self.mean_noise[agent_id] - self.current_noise[agent_id]) * self.dt
+                     + self.expl_noise[agent_id] * self.sqdt * self.sample_gaussian[agent_id].normal_())
+            self.current_noise[agent_id] = noise
+        else:
+            torch.normal(self.mean_noise[agent_id], self.expl_noise[agent_id], out=self.sample_gaussian[agent_id])
+            noise = self.sample_gaussian[agent_id]
+        return noise
+
+    def reset_action_noise(self, indices) -> None:
+        for a in self.agent_ids:
+            for idx in indices:
+                self.current_noise[a][idx, :] = 0
+
+    # -- learning ------------------------------------------------------------------------------------------
+    def _workspace(self, B: int) -> torch.Tensor:
+        ws = self._ws.get(B)
+        if ws is None:
+            need = ctypes.c_size_t(0)
+            _lib.check(_lib.load().b2rl_maddpg_workspace_bytes(ctypes.cast(self._actor_descs, ctypes.c_void_p),
+                                                               ctypes.cast(self._critic_descs, ctypes.c_void_p), self.n_agents, B,
+                                                               ctypes.byref(need)))
+            ws = self._ws[B] = torch.empty(need.value, dtype=torch.uint8, device=self._dev)
+        return ws
+
+    def _packed(self, field, width: int) -> torch.Tensor:
+        """[B, sum] float32 matrix of a field: the replay's packed gather if it rides along, else the reference's
+        ``torch.cat(list(field.values()), dim=1)`` in agent order."""
+        m = getattr(field, "packed", None)
+        if m is None:
+            m = torch.cat([field[a].to(self._dev, dtype=torch.float32).reshape(field[a].shape[0], -1) for a in self.agent_ids], dim=1)
+        if m.dtype != torch.float32 or m.device != self._dev or not m.is_contiguous():
+            m = m.to(self._dev, dtype=torch.float32).contiguous()
+        assert m.ndim == 2 and m.shape[1] == width, f"expected [B, {width}], got {tuple(m.shape)}"
+        return m
+
+    def learn(self, experiences) -> dict:
+        """maddpg.py:571-628.  Returns ``{agent_id: (actor_loss, critic_loss)}`` as Python floats."""
+        out = self.learn_device(experiences)
+        host = out.tolist()
+        return {a: (host[i][0], host[i][1]) for i, a in enumerate(self.agent_ids)}
+
+    def learn_device(self, experiences) -> torch.Tensor:
+        """``learn`` without the host read-back: device tensor ``[n_agents, 2]`` (actor_loss, critic_loss)."""
+        states, actions, rewards, next_states, dones = experiences
+        n = self.n_agents
+        SO, SA = sum(self.obs_dims.values()), sum(self.action_dims.values())
+        obs, next_obs, act = self._packed(states, SO), self._packed(next_states, SO), self._packed(actions, SA)
+        B = obs.shape[0]
+        # reward / done travel as [n_agents, B] (the packed replay matrices are [B, n_agents])
+        rew = self._packed(rewards, n).t().contiguous()
+        done = self._packed(dones, n).t().contiguous()
+        assert next_obs.shape[0] == B and act.shape[0] == B and rew.shape == (n, B) and done.shape == (n, B)
+        lib = _lib.load()
+        cfg = _lib.MaddpgCfg()
+        cfg.batch, cfg.n_agents = B, n
+        cfg.gamma, cfg.tau = float(self.gamma), float(self.tau)
+        cfg.lr_actor, cfg.lr_critic, cfg.beta1, cfg.beta2, cfg.adam_eps = float(self.lr_actor), float(self.lr_critic), 0.9, 0.999, 1e-8
+        for o in list(self.actor_optimizers.values()) + list(self.critic_optimizers.values()):
+            o.step += 1
+        a_step = next(iter(self.actor_optimizers.values())).step
+        c_step = next(iter(self.critic_optimizers.values())).step
+        cfg.bc1_actor, cfg.bc2_actor = 1.0 - 0.9 ** a_step, 1.0 - 0.999 ** a_step
+        cfg.bc1_critic, cfg.bc2_critic = 1.0 - 0.9 ** c_step, 1.0 - 0.999 ** c_step
+        bufs = _lib.MaddpgBufs()
+        for i, a in enumerate(self.agent_ids):
+            ao, co = self.actor_optimizers[a], self.critic_optimizers[a]
+            bufs.actor[i], bufs.actor_target[i] = self.actors[a].buffers.params.data_ptr(), self.actor_targets[a].buffers.params.data_ptr()
+            bufs.actor_grads[i], bufs.actor_m[i], bufs.actor_v[i] = ao.grads.data_ptr(), ao.exp_avg.data_ptr(), ao.exp_avg_sq.data_ptr()
+            bufs.critic[i], bufs.critic_target[i] = self.critics[a].buffers.params.data_ptr(), self.critic_targets[a].buffers.params.data_ptr()
+            bufs.critic_grads[i], bufs.critic_m[i], bufs.critic_v[i] = co.grads.data_ptr(), co.exp_avg.data_ptr(), co.exp_avg_sq.data_ptr()
+        bufs.obs, bufs.next_obs, bufs.action = obs.data_ptr(), next_obs.data_ptr(), act.data_ptr()
+        bufs.reward, bufs.done = rew.data_ptr(), done.data_ptr()
+        out = torch.empty((n, 2), dtype=torch.float32, device=self._dev)
+        bufs.losses = out.data_ptr()
+        ws = self._workspace(B)
+        bufs.workspace, bufs.workspace_bytes = ws.data_ptr(), ws.numel()
+        _lib.check(lib.b2rl_maddpg_learn(ctypes.cast(self._actor_descs, ctypes.c_void_p),
+                                         ctypes.cast(self._critic_descs, ctypes.c_void_p), ctypes.byref(cfg), ctypes.byref(bufs),
+                                         _lib.stream_ptr(self._dev)))
+        self.learn_counter += 1
+        self._keep = (obs, next_obs, act, rew, done, out)
+        return out
+
+    def soft_update(self, net, target) -> None:
+        """maddpg.py:733-746."""
+        p, t = net.buffers.params, target.buffers.params
+        t.copy_(self.tau * p + (1.0 - self.tau) * t)
+
+    def test(self, env, swap_channels: bool = False, max_steps: int | None = None, loop: int = 3, sum_scores: bool = True) -> float:
+        """maddpg.py:748-800 for a PettingZoo-style parallel environment."""
+        self.set_training_mode(False)
+        rewards = []
+        for _ in range(loop):
+            obs, info = env.reset()
+            score, steps, finished = 0.0, 0, False
+            while not finished:
+                steps += 1
+                action, _ = self.get_action(obs, infos=info)
+                obs, reward, term, trunc, info = env.step({a: v[0] for a, v in action.items()} if self.vect_noise_dim == 1 else action)
+                score += float(np.sum([np.sum(r) for r in reward.values()]))
+                finished = all(bool(np.all(term[a])) or bool(np.all(trunc[a])) for a in term) or \
+                    (max_steps is not None and steps >= max_steps)
+            rewards.append(score)
+        fit = float(np.mean(rewards))
+        self.fitness.append(fit)
+        self.set_training_mode(True)
+        return fit

@@ -1972,3 +1972,4 @@ int b2rl_encoder_layer_dgrad(const b2rl_net_desc *net_host, int layer, const flo
 }  // extern "C"
 
 #include "ddpg.cuh"
+#include "maddpg.cuh"

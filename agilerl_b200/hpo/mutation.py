@@ -162,15 +162,74 @@ class Mutations:
         return individual
 
     def parameter_mutation(self, individual):
-        """mutation.py:521-584."""
+        """mutation.py:521-584.  A multi-agent policy is a dict of networks keyed by agent id (the reference's
+        ``ModuleDict`` branch, :545-547): every sub-agent's network is mutated in turn."""
         group = individual.registry.policy(return_group=True)
         policy = getattr(individual, group.eval_network)
-        self._gaussian_parameter_mutation(policy)
-        for shared in group.shared_networks or []:
-            getattr(individual, shared).load_state_dict(policy.state_dict(), strict=False)
+        mutate = self._gaussian_parameter_mutation_device if getattr(self, "device_parameter_mutation", False) else \
+            self._gaussian_parameter_mutation
+        if isinstance(policy, dict):
+            for agent_id, module in policy.items():
+                policy[agent_id] = mutate(module)
+            for shared in group.shared_networks or []:
+                for agent_id, module in getattr(individual, shared).items():
+                    module.load_state_dict(policy[agent_id].state_dict(), strict=False)
+        else:
+            mutate(policy)
+            for shared in group.shared_networks or []:
+                getattr(individual, shared).load_state_dict(policy.state_dict(), strict=False)
         individual.reinit_optimizers()
         individual.mut = "param"
         return individual
+
+    #: opt-in (attribute, the constructor keeps the reference's signature): run the Gaussian parameter mutation ON THE
+    #: DEVICE (SURVEY 8f-4).  Positions and branch uniforms still come from ``self.rng`` — the same keys, rows, columns
+    #: and branches as the reference — but the noise comes from the library's Philox stream instead of torch's CPU
+    #: generator, so weights are distributed like the reference's, not bit-identical to a seeded reference run.
+    device_parameter_mutation = False
+    _device_mutation_offset = 0
+
+    def _gaussian_parameter_mutation_device(self, network, normals: dict | None = None):
+        """mutation.py:733-827 with the ``index_put`` of the mutated 10 % of each chosen matrix done by
+        ``b2rl_gaussian_mutate`` in place on the flat HBM parameter buffer (no host copy of the weights).
+        ``normals`` ({key: float32 [n_mut]}, tests) injects the standard-normal draws."""
+        import ctypes
+
+        from .. import _lib
+        lib = _lib.load()
+        entries = network.layout.entries
+        keys = [k for k, e in entries.items() if "lstm" not in k and "norm" not in k and len(e.shape) == 2]
+        how_many = int(self.rng.integers(1, len(keys) + 1))
+        dev = network.buffers.params.device
+        for key in self.rng.choice(keys, how_many, replace=False):
+            key = str(key)
+            view = network.buffers.view(key)
+            n_rows, n_cols = int(view.shape[0]), int(view.shape[1])
+            n_mut = int(np.ceil(0.1 * n_rows * n_cols))
+            if n_mut < 1:
+                continue
+            rows = self.rng.integers(0, n_rows, size=n_mut)
+            cols = self.rng.integers(0, n_cols, size=n_mut)
+            u = self.rng.uniform(0, 1, size=n_mut).astype(np.float32)          # torch.tensor(rand_vals, dtype=W.dtype)
+            flat = rows.astype(np.int64) * n_cols + cols.astype(np.int64)
+            keep = np.zeros(n_mut, dtype=np.uint8)                             # index_put_: the last writer of a position wins
+            _, last_from_end = np.unique(flat[::-1], return_index=True)
+            keep[n_mut - 1 - last_from_end] = 1
+            host = torch.from_numpy(np.concatenate([rows.astype(np.int64), cols.astype(np.int64)]))
+            idx = host.to(dev)
+            u_d, keep_d = torch.from_numpy(u).to(dev), torch.from_numpy(keep).to(dev)
+            z = None
+            if normals is not None:
+                z = normals[key].to(dev, dtype=torch.float32).contiguous()
+                assert z.numel() == n_mut
+            _lib.check(lib.b2rl_gaussian_mutate(view.data_ptr(), n_rows, n_cols, idx.data_ptr(), idx[n_mut:].data_ptr(),
+                                                u_d.data_ptr(), keep_d.data_ptr(), z.data_ptr() if z is not None else None,
+                                                0x6D757461 + 7919 * int(getattr(self, "_device_mutation_seed", 0)),
+                                                self._device_mutation_offset, float(self.mutation_sd), n_mut,
+                                                _lib.stream_ptr(dev)))
+            self._device_mutation_offset += n_mut
+            self._keep_mut = (idx, u_d, keep_d, z)
+        return network
 
     def _gaussian_parameter_mutation(self, network):
         """mutation.py:733-827, bit for bit.  The reference walks ``state_dict()`` — parameters AND the 2-D NoisyLinear

@@ -122,3 +122,60 @@ class ContinuousQNetwork(EvolvableNetwork):
                        layer_norm=h.layer_norm, output_layernorm=h.output_layernorm, activation=h.activation,
                        output_activation=h.output_activation)
         return NetSpec("q", self._encoder_spec(), head, None, 1, 1, None, None, False)
+
+
+class MultiInputContinuousQNetwork:
+    """``ContinuousQNetwork`` over a ``Dict`` of vector observation spaces — MADDPG's centralised critic
+    (maddpg.py:329-337): ``EvolvableMultiInput`` with no feature nets reduces to ``final_dense`` Linear(sum obs -> latent)
+    + ReLU over the raw vectors concatenated in key order (modules/multi_input.py:404-465), then
+    ``cat(latent, actions)`` -> LayerNorm MLP head -> 1 (q_networks.py:424-425).  State-dict keys are the reference's
+    (``encoder.final_dense.weight``, ``head_net.model.value_linear_layer_1.weight`` ...).  A fixed architecture over one
+    flat HBM parameter buffer: forward / backward run inside ``b2rl_maddpg_learn``; architecture mutations of
+    multi-agent networks are not implemented on the CUDA path."""
+
+    def __init__(self, observation_space, action_space, latent_dim: int = 32, head_config: dict | None = None,
+                 device: str = "cuda", random_seed: int | None = None) -> None:
+        from ..engine import NetBuffers
+        from .init import init_state_dict
+        from .spec import DenseSpec, FlatLayout
+        if not isinstance(observation_space, spaces.Dict):
+            raise TypeError("observation_space must be a Dict of the agents' observation spaces")
+        for k, sp in observation_space.items():
+            if not (isinstance(sp, spaces.Box) and len(sp.shape) == 1):
+                raise NotImplementedError(f"sub-space {k!r}: only 1-D Box observations are implemented on the CUDA path")
+        if not (isinstance(action_space, spaces.Box) and len(action_space.shape) == 1):
+            raise NotImplementedError("the CUDA critic takes the concatenated continuous actions (1-D Box)")
+        self.observation_space, self.action_space = observation_space, action_space
+        self.device, self._dev = device, _lib.as_device(device)
+        self.latent_dim = int(latent_dim)
+        self.num_inputs = int(sum(sp.shape[0] for sp in observation_space.values()))
+        self.num_actions = int(action_space.shape[0])
+        head_config = dict(head_config) if head_config is not None else dict(hidden_size=[64])
+        self.head_config = head_config
+        self.hidden_size = list(head_config.get("hidden_size", [64]))
+        self.activation = head_config.get("activation", "ReLU")
+        self.layer_norm = bool(head_config.get("layer_norm", True))
+        self.random_seed = random_seed
+        head = MlpSpec("head_net.model.", "value", self.latent_dim + self.num_actions, 1, self.hidden_size, noisy=False,
+                       layer_norm=self.layer_norm, output_layernorm=False, activation=self.activation, output_activation=None)
+        spec = NetSpec("q", DenseSpec("encoder.final_dense", self.num_inputs, self.latent_dim, "ReLU"), head, None, 1, 1,
+                       None, None, False)
+        self.layout = FlatLayout(spec)
+        self.buffers = NetBuffers(self.layout, self._dev)
+        self.buffers.load_state_dict(init_state_dict(self.layout, output_vanish_heads=True), strict=False)
+
+    @property
+    def init_dict(self) -> dict:
+        return dict(observation_space=self.observation_space, action_space=self.action_space, latent_dim=self.latent_dim,
+                    head_config=copy.deepcopy(self.head_config), device=self.device, random_seed=self.random_seed)
+
+    def state_dict(self):
+        return self.buffers.state_dict()
+
+    def load_state_dict(self, sd, strict: bool = True) -> None:
+        self.buffers.load_state_dict(sd, strict=strict)
+
+    def clone(self):
+        c = type(self)(**self.init_dict)
+        c.buffers.copy_from(self.buffers)
+        return c

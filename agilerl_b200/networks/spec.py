@@ -42,6 +42,16 @@ class CnnSpec:
 
 
 @dataclass
+class DenseSpec:
+    """``EvolvableMultiInput`` over vector sub-spaces only (modules/multi_input.py:404-465): the raw vectors concatenated
+    in key order -> ``final_dense`` -> output activation.  One linear layer under the reference's key."""
+    key: str                        # "encoder.final_dense"
+    num_inputs: int
+    num_outputs: int
+    output_activation: str | None = "ReLU"
+
+
+@dataclass
 class NetSpec:
     kind: str                       # "rainbow" | "q"
     encoder: object
@@ -120,6 +130,10 @@ class FlatLayout:
             L.b_off = self._param(key + ".bias", (e.num_outputs,), "linear_bias")
             enc_layers.append(L)
             self.flattened_size = flat
+        elif isinstance(spec.encoder, DenseSpec):
+            e = spec.encoder
+            d.obs_elems = e.num_inputs
+            enc_layers = [self._linear(e.key, e.num_inputs, e.num_outputs, e.output_activation, _lib.LN_NONE, False)]
         else:
             d.obs_elems = spec.encoder.num_inputs
             enc_layers = self._mlp_layers(spec.encoder)

@@ -421,6 +421,54 @@ int b2rl_actor_forward(const b2rl_net_desc *actor_host, const float *params, con
                        void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * MADDPG learn() — agilerl/algorithms/maddpg.py:571-740 (BASELINE configs[4]: 4 agents x 18-dim
+ * observations, shared replay) for vector observations and continuous actions.
+ * actor_i = b2rl_net_desc chain enc[] (LayerNorm MLP encoder over agent i's observation) -> val[] (head, Tanh);
+ * critic_i = enc[] over the concatenation of EVERY agent's observation (EvolvableMultiInput's final_dense + ReLU,
+ * modules/multi_input.py:404-465) -> cat(latent, EVERY agent's action) -> val[] (-> 1).
+ * The batch arrives as row-major matrices with the agents' columns side by side in agent order — what the
+ * reference's torch.cat(..., dim=1) builds — so the replay gather can write them directly.
+ * ------------------------------------------------------------------------------------------ */
+#define B2RL_MAX_AGENTS 8
+typedef struct b2rl_maddpg_cfg {
+    int64_t batch;
+    int32_t n_agents;
+    int32_t reserved_;
+    double gamma, tau;
+    double lr_actor, lr_critic, beta1, beta2, adam_eps;
+    double bc1_actor, bc2_actor, bc1_critic, bc2_critic;   /* 1 - beta^step of the actor / critic optimisers */
+} b2rl_maddpg_cfg;
+
+typedef struct b2rl_maddpg_bufs {
+    float *actor[B2RL_MAX_AGENTS], *actor_target[B2RL_MAX_AGENTS], *actor_grads[B2RL_MAX_AGENTS], *actor_m[B2RL_MAX_AGENTS],
+          *actor_v[B2RL_MAX_AGENTS];
+    float *critic[B2RL_MAX_AGENTS], *critic_target[B2RL_MAX_AGENTS], *critic_grads[B2RL_MAX_AGENTS], *critic_m[B2RL_MAX_AGENTS],
+          *critic_v[B2RL_MAX_AGENTS];
+    const float *obs, *next_obs;        /* [B, sum of observation dims] */
+    const float *action;                /* [B, sum of action dims] */
+    const float *reward, *done;         /* [n_agents, B]; NaN reward -> 0, NaN done -> 1 (maddpg.py:683-694) */
+    float *losses;                      /* out [n_agents, 2]: actor_loss, critic_loss of each agent */
+    void *workspace; size_t workspace_bytes;
+} b2rl_maddpg_bufs;
+
+int b2rl_maddpg_workspace_bytes(const b2rl_net_desc *const *actors_host, const b2rl_net_desc *const *critics_host, int n_agents,
+                                int64_t batch, size_t *out_host);
+/* One learn call of every agent, then every soft update (fused into the optimiser launches: no target is read after its
+ * network stepped).  actors_host / critics_host: n_agents pointers to the (host) layer tables. */
+int b2rl_maddpg_learn(const b2rl_net_desc *const *actors_host, const b2rl_net_desc *const *critics_host,
+                      const b2rl_maddpg_cfg *cfg_host, const b2rl_maddpg_bufs *bufs_host, void *stream);
+
+/* Mutations._gaussian_parameter_mutation (hpo/mutation.py:733-827) applied on the device to one weight matrix
+ * [n_rows, n_cols] (row-major, leading dimension n_cols) of a flat parameter buffer: slot j rewrites
+ * W[rows[j]][cols[j]] — branch_uniforms[j] < 0.05: w + |10 w| z; < 0.1: z; else w + |mutation_sd w| z; clamp(+-1e6).
+ * rows / cols / branch_uniforms are the reference's host-drawn numpy values (device copies); keep (nullable, uint8)
+ * marks the last writer of each position (index_put_ semantics); normals (nullable) injects z, else the Philox
+ * stream (seed, offset + j). */
+int b2rl_gaussian_mutate(float *weights, int64_t n_rows, int64_t n_cols, const int64_t *rows, const int64_t *cols,
+                         const float *branch_uniforms, const uint8_t *keep, const float *normals, uint64_t seed, uint64_t offset,
+                         double mutation_sd, int64_t n, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * CUDA graphs: the ~40 dependent launches of a gradient step captured once and replayed per step.
  * b2rl_graph_begin puts `stream` into capture (relaxed mode; library-owned side streams fork from and join back
  * into it); every b2rl_* call made on it until b2rl_graph_end is recorded instead of executed.  If the captured

@@ -34,9 +34,10 @@ def test_struct_layouts_match_header():
     src = textwrap.dedent(f"""
         #include <stdio.h>
         #include "{ROOT}/include/b2rl.h"
-        int main(void) {{ printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(b2rl_layer), sizeof(b2rl_net_desc),
+        int main(void) {{ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(b2rl_layer), sizeof(b2rl_net_desc),
                            sizeof(b2rl_learn_cfg), sizeof(b2rl_learn_bufs), sizeof(b2rl_step_state),
-                           sizeof(b2rl_ddpg_cfg), sizeof(b2rl_ddpg_bufs)); return 0; }}
+                           sizeof(b2rl_ddpg_cfg), sizeof(b2rl_ddpg_bufs), sizeof(b2rl_maddpg_cfg),
+                           sizeof(b2rl_maddpg_bufs)); return 0; }}
     """)
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "s.c"); exe = os.path.join(d, "s")
@@ -45,7 +46,7 @@ def test_struct_layouts_match_header():
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     assert sizes == [ctypes.sizeof(_lib.Layer), ctypes.sizeof(_lib.NetDesc), ctypes.sizeof(_lib.LearnCfg),
                      ctypes.sizeof(_lib.LearnBufs), ctypes.sizeof(_lib.StepState), ctypes.sizeof(_lib.DdpgCfg),
-                     ctypes.sizeof(_lib.DdpgBufs)]
+                     ctypes.sizeof(_lib.DdpgBufs), ctypes.sizeof(_lib.MaddpgCfg), ctypes.sizeof(_lib.MaddpgBufs)]
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
