@@ -1,0 +1,221 @@
+"""CPU: the HOST side of the multi-agent path with Python stand-ins for the C-ABI entry points it calls
+(test-only: the product has no CPU path and raises without CUDA — tests/test_abi_cpu.py).  The stand-ins move bytes
+(``b2rl_ring_write_multi`` / ``b2rl_gather_rows_multi``), apply the mutation rule slot by slot (``b2rl_gaussian_mutate``)
+or record what they were handed (``b2rl_maddpg_learn``), which pins everything the host decides:
+
+* ``MultiAgentReplayBuffer``: field packing (agents side by side), staging offsets, ring cursor / deque-head mapping,
+  ``random.sample`` positions -> slots, binary-field casting, NaN passthrough — against the reference's golden samples;
+* ``MADDPG.learn``: the [B, sum] matrices, reward / done transposed to [n_agents, B], every network / optimiser pointer,
+  Adam bias corrections, the layer tables of actors and critics;
+* ``Mutations._gaussian_parameter_mutation_device``: keys / rows / columns / branches drawn like the reference, the
+  last-writer mask of duplicate positions."""
+import ctypes
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+FIELDS = ("obs", "action", "reward", "next_obs", "done")
+
+
+def _bytes(ptr, n):
+    return np.ctypeslib.as_array((ctypes.c_uint8 * n).from_address(ptr))
+
+
+def _f32(ptr, n):
+    return np.ctypeslib.as_array((ctypes.c_float * n).from_address(ptr))
+
+
+def _i64(ptr, n):
+    return np.ctypeslib.as_array((ctypes.c_int64 * n).from_address(ptr))
+
+
+class StandIn:
+    def __init__(self):
+        self.seen = {}
+
+    def b2rl_ring_write_multi(self, nf, dst, src, row_bytes, start, n, max_size, stream):
+        for f in range(nf):
+            rb = row_bytes[f]
+            d, s = _bytes(dst[f], rb * max_size), _bytes(src[f], rb * n)
+            for r in range(n):
+                slot = (start + r) % max_size
+                d[slot * rb:(slot + 1) * rb] = s[r * rb:(r + 1) * rb]
+        return 0
+
+    def b2rl_gather_rows_multi(self, nf, dst, src, row_bytes, idx, n, stream):
+        ix = _i64(idx, n)
+        for f in range(nf):
+            rb = row_bytes[f]
+            d = _bytes(dst[f], rb * n)
+            for r in range(n):
+                d[r * rb:(r + 1) * rb] = _bytes(src[f] + int(ix[r]) * rb, rb)
+        return 0
+
+    def b2rl_gaussian_mutate(self, W, nr, nc, rows, cols, u, keep, z, seed, off, sd, n, stream):
+        Wv, orig = _f32(W, nr * nc), _f32(W, nr * nc).copy()
+        r, c, uu, kk, zz = _i64(rows, n), _i64(cols, n), _f32(u, n), _bytes(keep, n), _f32(z, n)
+        for j in range(n):
+            if not kk[j]:
+                continue
+            w = np.float32(orig[r[j] * nc + c[j]])
+            if uu[j] < np.float32(0.05):
+                v = w + abs(np.float32(10) * w) * zz[j]
+            elif uu[j] < np.float32(0.1):
+                v = zz[j]
+            else:
+                v = w + abs(np.float32(sd) * w) * zz[j]
+            Wv[r[j] * nc + c[j]] = np.clip(np.float32(v), -1e6, 1e6)
+        return 0
+
+    def b2rl_maddpg_workspace_bytes(self, actors, critics, n, B, out):
+        out._obj.value = 4096
+        return 0
+
+    def b2rl_maddpg_learn(self, actors, critics, cfg, bufs, stream):
+        from agilerl_b200 import _lib
+        cfg, bufs = cfg._obj, bufs._obj
+        B, n = cfg.batch, cfg.n_agents
+        ap = ctypes.cast(actors, ctypes.POINTER(ctypes.POINTER(_lib.NetDesc)))
+        cp = ctypes.cast(critics, ctypes.POINTER(ctypes.POINTER(_lib.NetDesc)))
+        SO = sum(ap[i].contents.enc[0].in_c for i in range(n))
+        SA = sum(ap[i].contents.val[ap[i].contents.n_val - 1].out_c for i in range(n))
+        s = self.seen
+        s["cfg"] = {f[0]: getattr(cfg, f[0]) for f in cfg._fields_}
+        s["actor_layers"] = [[(l.in_c, l.out_c, l.ln, l.act) for l in list(ap[i].contents.enc)[:ap[i].contents.n_enc] +
+                              list(ap[i].contents.val)[:ap[i].contents.n_val]] for i in range(n)]
+        s["critic_layers"] = [[(l.in_c, l.out_c, l.ln, l.act) for l in list(cp[i].contents.enc)[:cp[i].contents.n_enc] +
+                               list(cp[i].contents.val)[:cp[i].contents.n_val]] for i in range(n)]
+        s["obs"], s["next_obs"] = _f32(bufs.obs, B * SO).reshape(B, SO).copy(), _f32(bufs.next_obs, B * SO).reshape(B, SO).copy()
+        s["act"] = _f32(bufs.action, B * SA).reshape(B, SA).copy()
+        s["rew"], s["done"] = _f32(bufs.reward, n * B).reshape(n, B).copy(), _f32(bufs.done, n * B).reshape(n, B).copy()
+        s["ptrs"] = [{k: getattr(bufs, k)[i] for k in ("actor", "actor_target", "actor_grads", "actor_m", "actor_v", "critic",
+                                                        "critic_target", "critic_grads", "critic_m", "critic_v")} for i in range(n)]
+        _f32(bufs.losses, 2 * n)[:] = np.arange(2 * n)
+        return 0
+
+
+@pytest.fixture
+def standin(monkeypatch):
+    from agilerl_b200 import _lib
+    from agilerl_b200.components import replay_buffer as rb
+    lib = StandIn()
+    monkeypatch.setattr(_lib, "as_device", lambda d: torch.device("cpu"))
+    monkeypatch.setattr(_lib, "load", lambda require_cuda=False: lib)
+    monkeypatch.setattr(_lib, "stream_ptr", lambda d=None: 0)
+    monkeypatch.setattr(_lib, "check", lambda rc: None)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    monkeypatch.setattr(rb._PinnedRing, "sent", lambda self, k, dev: None)
+    return lib
+
+
+def _sd(g, tag):
+    return {k[len(tag) + 1:]: torch.from_numpy(g[k].copy()) for k in g.files if k.startswith(tag + "/")}
+
+
+def test_replay_host_logic_reproduces_reference_samples(standin):
+    from agilerl_b200.components import MultiAgentReplayBuffer
+    g = load_golden("ma_replay.npz")
+    ids, fields = [str(a) for a in g["agent_ids"]], [str(f) for f in g["fields"]]
+    buf = MultiAgentReplayBuffer(int(g["cap"]), fields, ids, device="cuda")
+    for t in range(int(g["n_steps"])):
+        buf.save_to_memory(*[{a: g[f"t{t}_{f}/{a}"] for a in ids} for f in fields], is_vectorised=bool(int(g[f"t{t}_vect"])))
+    assert len(buf) == int(g["final_len"]) and buf.counter == int(g["final_counter"])
+    for c in range(int(g["n_samples"])):
+        random.seed(int(g[f"sample{c}_seed"]))
+        batch = buf.sample(int(g[f"sample{c}_B"]))
+        for f, d in zip(fields, batch):
+            assert d.packed.shape[0] == int(g[f"sample{c}_B"])
+            for a in ids:
+                np.testing.assert_array_equal(d[a].numpy(), g[f"sample{c}_{f}/{a}"], err_msg=f"{c} {f} {a}")
+
+
+def test_maddpg_learn_marshalling(standin):
+    from agilerl_b200.algorithms import MADDPG
+    from agilerl_b200.compat import spaces
+    from agilerl_b200.components import MultiAgentReplayBuffer
+    g = load_golden("maddpg_vector.npz")
+    ids = [str(a) for a in g["agent_ids"]]
+    agent = MADDPG([spaces.Box(-1.0, 1.0, (int(d),), np.float32) for d in g["obs_dims"]],
+                   [spaces.Box(-1.0, 1.0, (int(d),), np.float32) for d in g["act_dims"]], agent_ids=ids, batch_size=int(g["B"]))
+    a0 = ids[0]
+    assert list(agent.actors[a0].state_dict()) == list(_sd(g, f"actor0/{a0}"))           # the reference's keys, in order
+    assert list(agent.critics[a0].state_dict()) == list(_sd(g, f"critic0/{a0}"))
+    assert agent.gamma == float(g["gamma"]) and agent.tau == float(g["tau"]) and agent.lr_critic == float(g["lr_critic"])
+    batch = tuple({a: torch.from_numpy(g[f"s1_{f}/{a}"].copy()) for a in ids} for f in FIELDS)
+    losses = agent.learn(batch)
+    assert losses == {a: (2.0 * i, 2.0 * i + 1.0) for i, a in enumerate(ids)}            # [n_agents, 2] = (actor, critic)
+    s = standin.seen
+    LN_AFFINE, LN_PLAIN, RELU, TANH = 1, 2, 1, 4
+    assert s["actor_layers"][0] == [(18, 64, LN_AFFINE, RELU), (64, 64, LN_AFFINE, RELU), (64, 32, LN_PLAIN, RELU),
+                                    (32, 64, LN_AFFINE, RELU), (64, 5, 0, TANH)]
+    assert s["critic_layers"][0] == [(72, 32, 0, RELU), (52, 64, LN_AFFINE, RELU), (64, 1, 0, 0)]
+    cat = lambda f: np.concatenate([g[f"s1_{f}/{a}"] for a in ids], axis=1)
+    np.testing.assert_array_equal(s["obs"], cat("obs")); np.testing.assert_array_equal(s["next_obs"], cat("next_obs"))
+    np.testing.assert_array_equal(s["act"], cat("action"))
+    for i, a in enumerate(ids):
+        np.testing.assert_array_equal(s["rew"][i], g[f"s1_reward/{a}"][:, 0])             # NaN entries travel as NaN
+        np.testing.assert_array_equal(s["done"][i], g[f"s1_done/{a}"][:, 0])
+        p = s["ptrs"][i]
+        assert p["actor"] == agent.actors[a].buffers.params.data_ptr() and p["actor_target"] == agent.actor_targets[a].buffers.params.data_ptr()
+        assert p["critic"] == agent.critics[a].buffers.params.data_ptr() and p["critic_target"] == agent.critic_targets[a].buffers.params.data_ptr()
+        ao, co = agent.actor_optimizers[a], agent.critic_optimizers[a]
+        assert (p["actor_grads"], p["actor_m"], p["actor_v"]) == (ao.grads.data_ptr(), ao.exp_avg.data_ptr(), ao.exp_avg_sq.data_ptr())
+        assert (p["critic_grads"], p["critic_m"], p["critic_v"]) == (co.grads.data_ptr(), co.exp_avg.data_ptr(), co.exp_avg_sq.data_ptr())
+    assert s["cfg"]["bc1_actor"] == 1.0 - 0.9 ** 1 and s["cfg"]["bc2_critic"] == 1.0 - 0.999 ** 1
+    agent.learn(batch)
+    assert standin.seen["cfg"]["bc1_critic"] == 1.0 - 0.9 ** 2
+    # the replay's packed matrices go in as they are
+    buf = MultiAgentReplayBuffer(64, list(FIELDS), ids, device="cuda")
+    buf.save_to_memory(*tuple({a: g[f"s0_{f}/{a}"] for a in ids} for f in FIELDS), is_vectorised=True)
+    random.seed(5)
+    agent.learn(buf.sample(int(g["B"])))
+    random.seed(5)
+    pos = random.sample(range(int(g["B"])), int(g["B"]))
+    np.testing.assert_array_equal(standin.seen["obs"], np.concatenate([g[f"s0_obs/{a}"] for a in ids], axis=1)[pos])
+    np.testing.assert_array_equal(standin.seen["rew"], np.stack([g[f"s0_reward/{a}"][pos, 0] for a in ids]))
+    # clone: same networks, optimiser step counts travel
+    c = agent.clone(index=3)
+    assert c.index == 3 and c.actor_optimizers[a0].step == 3 and torch.equal(c.critics[a0].buffers.params, agent.critics[a0].buffers.params)
+
+
+def test_device_mutation_decisions_match_index_put_semantics(standin):
+    from agilerl_b200.engine import NetBuffers
+    from agilerl_b200.hpo import Mutations
+    from agilerl_b200.networks.spec import FlatLayout, MlpSpec, NetSpec
+    spec = NetSpec("q", MlpSpec("encoder.model.", "encoder", 18, 32, [64, 64]),
+                   MlpSpec("head_net.model.", "actor", 32, 5, [64], output_activation="Tanh"), None, 5, 1)
+
+    class Net:
+        pass
+
+    def mk():
+        n = Net()
+        n.layout = FlatLayout(spec)
+        n.buffers = NetBuffers(n.layout, "cpu")
+        n.buffers.params.copy_(torch.randn(n.buffers.params.numel(), generator=torch.Generator().manual_seed(0)))
+        return n
+    ours, ref = mk(), mk()
+    keys = [k for k, e in ours.layout.entries.items() if "norm" not in k and len(e.shape) == 2]
+    gz = torch.Generator().manual_seed(9)
+    normals = {k: torch.randn(int(np.ceil(0.1 * np.prod(ours.layout.entries[k].shape))), generator=gz) for k in keys}
+    Mutations(0, 0, 0.5, 1, 0, 0, rand_seed=3, device="cuda")._gaussian_parameter_mutation_device(ours, normals=normals)
+    rng = np.random.default_rng(3)                                   # mutation.py:760-822 restated with the same noise per slot
+    for key in rng.choice(keys, int(rng.integers(1, len(keys) + 1)), replace=False):
+        W = ref.buffers.view(str(key))
+        n_mut = int(np.ceil(0.1 * W.shape[0] * W.shape[1]))
+        rows, cols = torch.tensor(rng.integers(0, W.shape[0], size=n_mut)), torch.tensor(rng.integers(0, W.shape[1], size=n_mut))
+        r, z = torch.tensor(rng.uniform(0, 1, size=n_mut), dtype=W.dtype), normals[str(key)]
+        cur = W[rows, cols]
+        new = cur.clone()
+        ms, mr, mn = r < 0.05, (r >= 0.05) & (r < 0.1), r >= 0.1
+        new[ms] = cur[ms] + (10 * cur[ms]).abs() * z[ms]
+        new[mr] = z[mr]
+        new[mn] = cur[mn] + (0.1 * cur[mn]).abs() * z[mn]
+        Wc = W.clone()
+        Wc[rows, cols] = new.clamp(-1000000, 1000000)                # CPU index_put_: the last writer of a position wins
+        W.copy_(Wc)
+    assert torch.equal(ours.buffers.params, ref.buffers.params)
