@@ -90,7 +90,7 @@ B2RL_MAX_AGENTS = 8
 
 class MaddpgCfg(Structure):
     _fields_ = [
-        ("batch", c_int64), ("n_agents", c_int32), ("reserved_", c_int32),
+        ("batch", c_int64), ("n_agents", c_int32), ("serial", c_int32),
         ("gamma", c_double), ("tau", c_double),
         ("lr_actor", c_double), ("lr_critic", c_double), ("beta1", c_double), ("beta2", c_double), ("adam_eps", c_double),
         ("bc1_actor", c_double), ("bc2_actor", c_double), ("bc1_critic", c_double), ("bc2_critic", c_double),
@@ -104,7 +104,7 @@ class MaddpgBufs(Structure):
         ("critic", c_void_p * B2RL_MAX_AGENTS), ("critic_target", c_void_p * B2RL_MAX_AGENTS),
         ("critic_grads", c_void_p * B2RL_MAX_AGENTS), ("critic_m", c_void_p * B2RL_MAX_AGENTS), ("critic_v", c_void_p * B2RL_MAX_AGENTS),
         ("obs", c_void_p), ("next_obs", c_void_p), ("action", c_void_p), ("reward", c_void_p), ("done", c_void_p),
-        ("losses", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+        ("losses", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_size_t), ("step_state", c_void_p),
     ]
 
 

@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import copy
 import ctypes
+import os
 import warnings
 from collections import OrderedDict
 from typing import Any
@@ -31,6 +32,36 @@ from ..networks.actors import DeterministicActor, MultiInputContinuousQNetwork
 from .core.base import EvolvableAlgorithm
 from .core.registry import HyperparameterConfig, NetworkGroup, OptimizerConfig
 from .td3 import _AdamState
+
+
+_GRAPH = os.environ.get("B2RL_MADDPG_GRAPH", "1") != "0"      # CUDA-graph replay of learn() (0: always eager)
+_FAN = os.environ.get("B2RL_MADDPG_STREAMS", "1") != "0"      # the agents' steps on one side stream each (0: serial)
+
+
+class _LearnPlan:
+    """Static batch buffers + the captured graph of one ``b2rl_maddpg_learn`` call for a batch size: ~130 dependent
+    launches (four concurrent per-agent chains) replayed as ONE graph launch.  What changes between steps — Adam's bias
+    corrections — lives in a ``b2rl_step_state`` on the device, rewritten by the graph's first node from the host's
+    double arithmetic, so a replay is bit-identical to the eager call (tests/test_maddpg_gpu.py)."""
+
+    def __init__(self, agent, B: int):
+        dev, n = agent._dev, agent.n_agents
+        SO, SA = sum(agent.obs_dims.values()), sum(agent.action_dims.values())
+        mk = lambda w: torch.zeros((B, w), dtype=torch.float32, device=dev)
+        self.obs, self.action, self.reward, self.next_obs, self.done = mk(SO), mk(SA), mk(n), mk(SO), mk(n)
+        self.out = torch.zeros((n, 2), dtype=torch.float32, device=dev)
+        self.state_host = _lib.StepState()
+        self.state_dev = torch.zeros(ctypes.sizeof(_lib.StepState), dtype=torch.uint8, device=dev)
+        self.graph = None
+
+    def fields(self):
+        """The static buffers in the replay's field order (obs, action, reward, next_obs, done)."""
+        return [self.obs, self.action, self.reward, self.next_obs, self.done]
+
+    def destroy(self) -> None:
+        if self.graph:
+            _lib.load().b2rl_graph_destroy(self.graph)
+            self.graph = None
 
 
 def concatenate_spaces(space_list) -> spaces.Box:
@@ -139,6 +170,20 @@ class MADDPG(EvolvableAlgorithm):
         self._actor_descs = (ctypes.POINTER(_lib.NetDesc) * n)(*[ctypes.pointer(self.actors[a].layout.desc) for a in self.agent_ids])
         self._critic_descs = (ctypes.POINTER(_lib.NetDesc) * n)(*[ctypes.pointer(self.critics[a].layout.desc) for a in self.agent_ids])
         self._ws: dict = {}
+        self._drop_plans()
+        if "use_graph" not in self.__dict__:
+            self.use_graph, self.concurrent_agents = _GRAPH, _FAN
+
+    def _drop_plans(self) -> None:
+        for plan in self.__dict__.get("_plans", {}).values():
+            plan.destroy()
+        self._plans: dict = {}
+
+    def __del__(self):
+        try:
+            self._drop_plans()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
 
     def _opt_state(self) -> dict:
         return {"actors": {a: o.state_dict() for a, o in self.actor_optimizers.items()},
@@ -155,6 +200,8 @@ class MADDPG(EvolvableAlgorithm):
         if name == "lr_critic":
             for o in self.__dict__.get("critic_optimizers", {}).values():
                 o.lr = value
+        if name in ("lr_actor", "lr_critic", "gamma", "tau", "concurrent_agents") and self.__dict__.get("_plans"):
+            self._drop_plans()                     # these scalars are baked into a captured call
 
     def clone(self, index: int | None = None, wrap: bool = True):
         """core/base.py:855-917: same constructor arguments, then networks, optimiser state and the run-time attributes."""
@@ -170,6 +217,7 @@ class MADDPG(EvolvableAlgorithm):
                              (self.critic_targets, c.critic_targets)):
                 dst[a].buffers.copy_from(src[a].buffers)
         c._bind_engine(keep=self._opt_state())
+        c.use_graph, c.concurrent_agents = self.use_graph, self.concurrent_agents
         c.expl_noise = {a: v.clone() for a, v in self.expl_noise.items()}
         c.mean_noise = {a: v.clone() for a, v in self.mean_noise.items()}
         c.current_noise = {a: v.clone() for a, v in self.current_noise.items()}
@@ -247,26 +295,26 @@ class MADDPG(EvolvableAlgorithm):
         host = out.tolist()
         return {a: (host[i][0], host[i][1]) for i, a in enumerate(self.agent_ids)}
 
-    def learn_device(self, experiences) -> torch.Tensor:
-        """``learn`` without the host read-back: device tensor ``[n_agents, 2]`` (actor_loss, critic_loss)."""
-        states, actions, rewards, next_states, dones = experiences
+    def batch_buffers(self, B: int) -> list:
+        """The static ``[B, sum]`` matrices a captured learn call reads, in the replay's field order (obs, action, reward,
+        next_obs, done): ``MultiAgentReplayBuffer.sample_device(B, out=agent.batch_buffers(B))`` gathers straight into
+        them and ``learn_device`` then replays the graph without copying the batch."""
+        return self._plan(B).fields()
+
+    def _plan(self, B: int) -> _LearnPlan:
+        plan = self._plans.get(B)
+        if plan is None:
+            plan = self._plans[B] = _LearnPlan(self, B)
+        return plan
+
+    def _call_args(self, B, obs, next_obs, act, rew, done, out, state_dev=None):
         n = self.n_agents
-        SO, SA = sum(self.obs_dims.values()), sum(self.action_dims.values())
-        obs, next_obs, act = self._packed(states, SO), self._packed(next_states, SO), self._packed(actions, SA)
-        B = obs.shape[0]
-        # reward / done travel as [n_agents, B] (the packed replay matrices are [B, n_agents])
-        rew = self._packed(rewards, n).t().contiguous()
-        done = self._packed(dones, n).t().contiguous()
-        assert next_obs.shape[0] == B and act.shape[0] == B and rew.shape == (n, B) and done.shape == (n, B)
-        lib = _lib.load()
         cfg = _lib.MaddpgCfg()
-        cfg.batch, cfg.n_agents = B, n
+        cfg.batch, cfg.n_agents, cfg.serial = B, n, int(not self.concurrent_agents)
         cfg.gamma, cfg.tau = float(self.gamma), float(self.tau)
         cfg.lr_actor, cfg.lr_critic, cfg.beta1, cfg.beta2, cfg.adam_eps = float(self.lr_actor), float(self.lr_critic), 0.9, 0.999, 1e-8
-        for o in list(self.actor_optimizers.values()) + list(self.critic_optimizers.values()):
-            o.step += 1
-        a_step = next(iter(self.actor_optimizers.values())).step
-        c_step = next(iter(self.critic_optimizers.values())).step
+        a_step = max(next(iter(self.actor_optimizers.values())).step, 1)
+        c_step = max(next(iter(self.critic_optimizers.values())).step, 1)
         cfg.bc1_actor, cfg.bc2_actor = 1.0 - 0.9 ** a_step, 1.0 - 0.999 ** a_step
         cfg.bc1_critic, cfg.bc2_critic = 1.0 - 0.9 ** c_step, 1.0 - 0.999 ** c_step
         bufs = _lib.MaddpgBufs()
@@ -278,14 +326,61 @@ class MADDPG(EvolvableAlgorithm):
             bufs.critic_grads[i], bufs.critic_m[i], bufs.critic_v[i] = co.grads.data_ptr(), co.exp_avg.data_ptr(), co.exp_avg_sq.data_ptr()
         bufs.obs, bufs.next_obs, bufs.action = obs.data_ptr(), next_obs.data_ptr(), act.data_ptr()
         bufs.reward, bufs.done = rew.data_ptr(), done.data_ptr()
-        out = torch.empty((n, 2), dtype=torch.float32, device=self._dev)
         bufs.losses = out.data_ptr()
         ws = self._workspace(B)
         bufs.workspace, bufs.workspace_bytes = ws.data_ptr(), ws.numel()
+        bufs.step_state = state_dev.data_ptr() if state_dev is not None else None
+        return cfg, bufs
+
+    def _capture(self, plan: _LearnPlan, B: int) -> None:
+        lib = _lib.load()
+        cfg, bufs = self._call_args(B, plan.obs, plan.next_obs, plan.action, plan.reward, plan.done, plan.out, plan.state_dev)
+        plan._keep = (cfg, bufs)
+        cap = torch.cuda.Stream(device=self._dev)
+        cap.wait_stream(torch.cuda.current_stream(self._dev))
+        s = cap.cuda_stream
+        gh = ctypes.c_void_p()
+        _lib.check(lib.b2rl_graph_begin(s))
+        try:
+            _lib.check(lib.b2rl_step_state_write(ctypes.byref(plan.state_host), plan.state_dev.data_ptr(), s))
+            _lib.check(lib.b2rl_maddpg_learn(ctypes.cast(self._actor_descs, ctypes.c_void_p),
+                                             ctypes.cast(self._critic_descs, ctypes.c_void_p), ctypes.byref(cfg), ctypes.byref(bufs), s))
+        finally:
+            _lib.check(lib.b2rl_graph_end(s, ctypes.byref(gh)))
+        plan.graph = gh.value
+        torch.cuda.current_stream(self._dev).wait_stream(cap)
+
+    def learn_device(self, experiences) -> torch.Tensor:
+        """``learn`` without the host read-back: device tensor ``[n_agents, 2]`` (actor_loss, critic_loss).  With
+        ``use_graph`` the tensor is the plan's static result buffer: valid until the next learn call of this batch size."""
+        states, actions, rewards, next_states, dones = experiences
+        n = self.n_agents
+        SO, SA = sum(self.obs_dims.values()), sum(self.action_dims.values())
+        obs, next_obs, act = self._packed(states, SO), self._packed(next_states, SO), self._packed(actions, SA)
+        rew, done = self._packed(rewards, n), self._packed(dones, n)      # [B, n_agents]: the replay's own layout
+        B = obs.shape[0]
+        assert next_obs.shape[0] == B and act.shape[0] == B and rew.shape == (B, n) and done.shape == (B, n)
+        lib = _lib.load()
+        for o in list(self.actor_optimizers.values()) + list(self.critic_optimizers.values()):
+            o.step += 1
+        self.learn_counter += 1
+        if self.use_graph:
+            plan = self._plan(B)
+            for dst, src in zip(plan.fields(), (obs, act, rew, next_obs, done)):
+                if dst.data_ptr() != src.data_ptr():
+                    dst.copy_(src)
+            if plan.graph is None:
+                self._workspace(B)                                # also creates the library's side streams: not under capture
+                self._capture(plan, B)
+            step = next(iter(self.critic_optimizers.values())).step
+            plan.state_host.bias_correction1, plan.state_host.bias_correction2 = 1.0 - 0.9 ** step, 1.0 - 0.999 ** step
+            _lib.check(lib.b2rl_graph_launch(plan.graph, ctypes.byref(plan.state_host), _lib.stream_ptr(self._dev)))
+            return plan.out
+        out = torch.empty((n, 2), dtype=torch.float32, device=self._dev)
+        cfg, bufs = self._call_args(B, obs, next_obs, act, rew, done, out)
         _lib.check(lib.b2rl_maddpg_learn(ctypes.cast(self._actor_descs, ctypes.c_void_p),
                                          ctypes.cast(self._critic_descs, ctypes.c_void_p), ctypes.byref(cfg), ctypes.byref(bufs),
                                          _lib.stream_ptr(self._dev)))
-        self.learn_counter += 1
         self._keep = (obs, next_obs, act, rew, done, out)
         return out
 

@@ -145,10 +145,15 @@ class MultiAgentReplayBuffer:
             self.save_to_memory_single_env(*args)
 
     # -- sampling --------------------------------------------------------------------------------------
-    def _gather(self, slots: torch.Tensor) -> tuple:
+    def _gather(self, slots: torch.Tensor, out: list | None = None) -> tuple:
         B = slots.numel()
         nf = len(self._rings)
-        dsts = [torch.empty((B, w), dtype=torch.float32, device=self._dev) for w in self._widths]
+        if out is not None:
+            dsts = list(out)
+            assert len(dsts) == nf and all(d.shape == (B, w) and d.dtype == torch.float32 and d.is_contiguous() and d.device == self._dev
+                                          for d, w in zip(dsts, self._widths)), "out: one contiguous float32 [B, width] per field"
+        else:
+            dsts = [torch.empty((B, w), dtype=torch.float32, device=self._dev) for w in self._widths]
         arr = (ctypes.c_void_p * nf)(*[d.data_ptr() for d in dsts])
         _lib.check(self._lib.b2rl_gather_rows_multi(nf, arr, self._ring_ptrs, self._row_bytes, slots.data_ptr(), B,
                                                     _lib.stream_ptr(self._dev)))
@@ -177,12 +182,13 @@ class MultiAgentReplayBuffer:
         self._idx_stage.sent(slot, self._dev)
         return self._gather(slots)
 
-    def sample_device(self, batch_size: int) -> tuple:
+    def sample_device(self, batch_size: int, out: list | None = None) -> tuple:
         """``sample`` for the HBM-resident loop: distinct uniform positions drawn on the device (Philox,
-        b2rl_sample_uniform_distinct) — no host round trip, not the reference's RNG stream."""
+        b2rl_sample_uniform_distinct) — no host round trip, not the reference's RNG stream.  ``out``: one ``[B, width]``
+        float32 matrix per field to gather into (``MADDPG.batch_buffers``: the buffers a captured learn call reads)."""
         idx = torch.empty(batch_size, dtype=torch.int64, device=self._dev)
         off = getattr(self, "_uniform_offset", 0)
         _lib.check(self._lib.b2rl_sample_uniform_distinct(0x3A44, off, self._size, batch_size, idx.data_ptr(),
                                                           _lib.stream_ptr(self._dev)))
         self._uniform_offset = off + 64 * batch_size
-        return self._gather(idx)          # a uniform draw over the slots is a uniform draw over the positions
+        return self._gather(idx, out)     # a uniform draw over the slots is a uniform draw over the positions

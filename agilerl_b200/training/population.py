@@ -51,6 +51,37 @@ def population_learn(pop, memory, n_step_memory, overlap: bool = True, join: boo
     return losses
 
 
+_MEMBER_STREAMS: dict = {}
+
+
+def multi_agent_population_learn(pop, memory, batch_size: int | None = None, overlap: bool = True) -> list:
+    """One learn call of every member of a MADDPG population (all on one device) against the shared HBM replay
+    (train_multi_agent_off_policy: ``experiences = memory.sample(agent.batch_size); agent.learn(experiences)`` per
+    member).  The members share nothing that a learn call writes — the replay is only read — so each member's position
+    draw, gather (straight into the buffers its captured learn call reads) and graph launch go to the member's own
+    stream and overlap; the caller's stream waits for all of them before the function returns.  Returns the members'
+    ``[n_agents, 2]`` loss tensors on the device (no host sync)."""
+    if not pop:
+        return []
+    device = pop[0]._dev
+    if not overlap:
+        return [m.learn_device(memory.sample_device(batch_size or m.batch_size, out=m.batch_buffers(batch_size or m.batch_size)))
+                for m in pop]
+    cur = torch.cuda.current_stream(device)
+    streams = _MEMBER_STREAMS.setdefault(torch.device(device), [])
+    while len(streams) < len(pop):
+        streams.append(torch.cuda.Stream(device=device))
+    losses = []
+    for m, st in zip(pop, streams):
+        B = batch_size or m.batch_size
+        st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            losses.append(m.learn_device(memory.sample_device(B, out=m.batch_buffers(B))))
+    for st in streams[:len(pop)]:
+        cur.wait_stream(st)
+    return losses
+
+
 def share_transitions(transition, device=None, group=None):
     """The reference trains the WHOLE population against one replay buffer (train_off_policy.py:327-345,
     docs/off_policy/index.rst:103): every agent's environment steps land in it.  With the population sharded one

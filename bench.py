@@ -677,11 +677,11 @@ def maddpg_workload(args):
     torch.cuda.synchronize()
     assert len(mem) == N
 
-    def dev_step():
-        out = None
-        for agent in agents:
-            out = agent.learn_device(mem.sample_device(BT))
-        return out
+    from agilerl_b200.training.population import multi_agent_population_learn
+    overlap = [True]
+
+    def dev_step():                    # per member: position draw + gather into the buffers its captured learn call reads + graph
+        return multi_agent_population_learn(agents, mem, BT, overlap=overlap[0])[-1]
 
     def api_step():
         out = None
@@ -700,6 +700,21 @@ def maddpg_workload(args):
     launches = (lib.b2rl_launch_count() - l0) // len(ms_all)
     clocks = sampler.stop()
     value = POPM * args.steps / (ms / 1e3)
+    variants = {}                      # the same loop with members one after another / without the graph / without agent streams
+    for name, (ov, gr, fan) in {"members serial, graph+agent streams": (False, True, True),
+                                "members serial, eager+agent streams": (False, False, True),
+                                "members serial, eager, agents serial": (False, False, False),
+                                "members overlapped, graph, agents serial": (True, True, False)}.items():
+        overlap[0] = ov
+        for a in agents:
+            a.use_graph, a.concurrent_agents = gr, fan
+        dev_step(); dev_step()
+        ms_v, _ = time_region(dev_step, args.steps, False, repeats=3)
+        variants[name] = POPM * args.steps / (ms_v / 1e3)
+    overlap[0] = True
+    for a in agents:
+        a.use_graph, a.concurrent_agents = True, True
+    dev_step()
     e2e_steps = max(1, min(args.steps, 50))
     ms_e2e, ms_e2e_all = time_region(api_step, e2e_steps, False, repeats=3)
     # mutation sweep on the device: every member's four actors (index_put of 10 % of the chosen matrices)
@@ -740,7 +755,8 @@ def maddpg_workload(args):
                        "pop": POPM, "batch": BT, "buffer": N, "agents": NA,
                        "net": "actors: LayerNorm MLP [64,64]->32 -> head [64] Tanh; critics: final_dense 72->32 ReLU, "
                               "cat(latent, 20 actions) -> [64] -> 1",
-                       "l2": "69 MB replay (fits L2): the step is launch/latency-bound (132 dependent launches), not HBM-bound"},
+                       "l2": "69 MB replay (fits L2): the step is launch/latency-bound (128 kernels in four concurrent per-agent chains, "
+                             "replayed as one CUDA graph per member), not HBM-bound"},
             "timing": {"repeats": len(ms_all), "stat": "median", "ms_repeats": [round(x, 3) for x in ms_all]},
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"kernel": "whole b2rl_maddpg_learn call (fused chain forward / backward / weight-gradient kernels over "
@@ -751,6 +767,7 @@ def maddpg_workload(args):
             "e2e": {"value": POPM * e2e_steps / (ms_e2e / 1e3), "unit": "steps/s", "ms_per_step": ms_e2e / e2e_steps,
                     "h2d_bytes_per_step": POPM * BT * 8, "d2h_bytes_per_step": POPM * NA * 8, "steps": e2e_steps,
                     "ms_repeats": [round(x, 3) for x in ms_e2e_all]},
+            "variants_steps_per_s": variants,
             "mutation_sweep": {"ms": sweep_ms, "members": POPM, "networks": POPM * NA,
                                "what": "Mutations.parameter_mutation with device_parameter_mutation on every member"},
             "cpu_baseline": {"value": cpu_val, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "port",

@@ -433,7 +433,8 @@ int b2rl_actor_forward(const b2rl_net_desc *actor_host, const float *params, con
 typedef struct b2rl_maddpg_cfg {
     int64_t batch;
     int32_t n_agents;
-    int32_t reserved_;
+    int32_t serial;                     /* 1: the agents' steps one after another on the caller's stream; 0: concurrently
+                                           on one library side stream per agent (forked from / joined into `stream`) */
     double gamma, tau;
     double lr_actor, lr_critic, beta1, beta2, adam_eps;
     double bc1_actor, bc2_actor, bc1_critic, bc2_critic;   /* 1 - beta^step of the actor / critic optimisers */
@@ -446,9 +447,11 @@ typedef struct b2rl_maddpg_bufs {
           *critic_v[B2RL_MAX_AGENTS];
     const float *obs, *next_obs;        /* [B, sum of observation dims] */
     const float *action;                /* [B, sum of action dims] */
-    const float *reward, *done;         /* [n_agents, B]; NaN reward -> 0, NaN done -> 1 (maddpg.py:683-694) */
+    const float *reward, *done;         /* [B, n_agents]; NaN reward -> 0, NaN done -> 1 (maddpg.py:683-694) */
     float *losses;                      /* out [n_agents, 2]: actor_loss, critic_loss of each agent */
     void *workspace; size_t workspace_bytes;
+    const b2rl_step_state *step_state;  /* nullable (device): a captured call reads this step's Adam bias corrections
+                                           (bias_correction1 / 2; every optimiser steps once per call) from here */
 } b2rl_maddpg_bufs;
 
 int b2rl_maddpg_workspace_bytes(const b2rl_net_desc *const *actors_host, const b2rl_net_desc *const *critics_host, int n_agents,

@@ -90,6 +90,82 @@ def test_learn_matches_reference_golden():
             assert float(tight.float().mean()) >= 0.995, (tag, a, float(tight.float().mean()), float(d.max()))
 
 
+@pytest.mark.parametrize("mode", ["graph+streams", "eager+streams", "graph+serial"])
+def test_graph_replay_and_concurrent_agents_are_bit_identical_to_the_serial_eager_call(mode):
+    """The captured learn call (one graph launch, bias corrections from the device step state) and the per-agent side
+    streams change scheduling only: losses, every parameter, target and Adam moment equal the serial eager call's bit
+    for bit over three steps (Adam's bias corrections differ at every step)."""
+    g = load_golden("maddpg_vector.npz")
+    ids, ref = _agent(g)
+    ref.use_graph, ref.concurrent_agents = False, False
+    ids, alt = _agent(g)
+    alt.use_graph, alt.concurrent_agents = mode.startswith("graph"), mode.endswith("streams")
+    for st in range(int(g["steps"])):
+        l_ref, l_alt = ref.learn(_batch(g, st, ids)), alt.learn(_batch(g, st, ids))
+        for a in ids:
+            same = [x == y or (np.isnan(x) and np.isnan(y)) for x, y in zip(l_ref[a], l_alt[a])]
+            assert all(same), (mode, st, a, l_ref[a], l_alt[a])
+    if alt.use_graph:
+        assert alt._plans[int(g["B"])].graph is not None
+    for a in ids:
+        for x, y in ((ref.actors, alt.actors), (ref.actor_targets, alt.actor_targets), (ref.critics, alt.critics),
+                     (ref.critic_targets, alt.critic_targets)):
+            assert torch.equal(x[a].buffers.params, y[a].buffers.params), (mode, a)
+        assert torch.equal(ref.actor_optimizers[a].exp_avg_sq, alt.actor_optimizers[a].exp_avg_sq)
+        assert torch.equal(ref.critic_optimizers[a].exp_avg, alt.critic_optimizers[a].exp_avg)
+
+
+def test_replay_gathers_straight_into_the_captured_batch_buffers():
+    from agilerl_b200.components import MultiAgentReplayBuffer
+    g = load_golden("maddpg_vector.npz")
+    ids, a1 = _agent(g)
+    a2 = a1.clone()
+    a2.use_graph = False
+    B = 16
+    buf = MultiAgentReplayBuffer(64, list(FIELDS), ids, device="cuda")
+    buf.save_to_memory(*tuple({a: g[f"s0_{f}/{a}"] for a in ids} for f in FIELDS), is_vectorised=True)
+    for _ in range(2):
+        batch = buf.sample_device(B, out=a1.batch_buffers(B))
+        assert batch[0].packed.data_ptr() == a1.batch_buffers(B)[0].data_ptr()
+        plain = tuple({a: d[a].clone() for a in ids} for d in batch)
+        l1, l2 = a1.learn(batch), a2.learn(plain)
+        assert l1 == l2
+    for a in ids:
+        assert torch.equal(a1.critics[a].buffers.params, a2.critics[a].buffers.params)
+        assert torch.equal(a1.actor_targets[a].buffers.params, a2.actor_targets[a].buffers.params)
+
+
+def test_overlapped_population_learn_equals_member_by_member():
+    """training.population.multi_agent_population_learn: every member on its own stream (draw, gather, graph launch)
+    == the members one after another, bit for bit."""
+    from agilerl_b200.components import MultiAgentReplayBuffer
+    from agilerl_b200.training.population import multi_agent_population_learn
+    g = load_golden("maddpg_vector.npz")
+    ids, base = _agent(g)
+    B = 16
+
+    def run(overlap):
+        torch.manual_seed(0)
+        pop = [base.clone(index=k) for k in range(3)]
+        for k, m in enumerate(pop):                      # distinct members
+            for a in ids:
+                m.actors[a].buffers.params.mul_(1.0 + 0.01 * k)
+        buf = MultiAgentReplayBuffer(64, list(FIELDS), ids, device="cuda")
+        buf.save_to_memory(*tuple({a: g[f"s0_{f}/{a}"] for a in ids} for f in FIELDS), is_vectorised=True)
+        out = None
+        for _ in range(3):
+            out = multi_agent_population_learn(pop, buf, B, overlap=overlap)
+        torch.cuda.synchronize()
+        return pop, [o.clone() for o in out]
+    p1, l1 = run(True)
+    p2, l2 = run(False)
+    for m1, m2, x, y in zip(p1, p2, l1, l2):
+        assert torch.equal(x, y)
+        for a in ids:
+            assert torch.equal(m1.actors[a].buffers.params, m2.actors[a].buffers.params)
+            assert torch.equal(m1.critic_targets[a].buffers.params, m2.critic_targets[a].buffers.params)
+
+
 def test_packed_replay_batch_equals_dict_batch_bit_for_bit():
     """learn() fed by MultiAgentReplayBuffer.sample (packed [B, sum] matrices) == learn() fed by the reference-shaped
     dicts of per-agent tensors."""

@@ -5,7 +5,7 @@ or record what they were handed (``b2rl_maddpg_learn``), which pins everything t
 
 * ``MultiAgentReplayBuffer``: field packing (agents side by side), staging offsets, ring cursor / deque-head mapping,
   ``random.sample`` positions -> slots, binary-field casting, NaN passthrough — against the reference's golden samples;
-* ``MADDPG.learn``: the [B, sum] matrices, reward / done transposed to [n_agents, B], every network / optimiser pointer,
+* ``MADDPG.learn``: the [B, sum] matrices (reward / done as [B, n_agents]), every network / optimiser pointer,
   Adam bias corrections, the layer tables of actors and critics;
 * ``Mutations._gaussian_parameter_mutation_device``: keys / rows / columns / branches drawn like the reference, the
   last-writer mask of duplicate positions."""
@@ -91,7 +91,8 @@ class StandIn:
                                list(cp[i].contents.val)[:cp[i].contents.n_val]] for i in range(n)]
         s["obs"], s["next_obs"] = _f32(bufs.obs, B * SO).reshape(B, SO).copy(), _f32(bufs.next_obs, B * SO).reshape(B, SO).copy()
         s["act"] = _f32(bufs.action, B * SA).reshape(B, SA).copy()
-        s["rew"], s["done"] = _f32(bufs.reward, n * B).reshape(n, B).copy(), _f32(bufs.done, n * B).reshape(n, B).copy()
+        s["rew"], s["done"] = _f32(bufs.reward, n * B).reshape(B, n).copy(), _f32(bufs.done, n * B).reshape(B, n).copy()
+        s["step_state"] = bufs.step_state
         s["ptrs"] = [{k: getattr(bufs, k)[i] for k in ("actor", "actor_target", "actor_grads", "actor_m", "actor_v", "critic",
                                                         "critic_target", "critic_grads", "critic_m", "critic_v")} for i in range(n)]
         _f32(bufs.losses, 2 * n)[:] = np.arange(2 * n)
@@ -141,6 +142,7 @@ def test_maddpg_learn_marshalling(standin):
     ids = [str(a) for a in g["agent_ids"]]
     agent = MADDPG([spaces.Box(-1.0, 1.0, (int(d),), np.float32) for d in g["obs_dims"]],
                    [spaces.Box(-1.0, 1.0, (int(d),), np.float32) for d in g["act_dims"]], agent_ids=ids, batch_size=int(g["B"]))
+    agent.use_graph = False                      # the eager call: graph capture needs the real library
     a0 = ids[0]
     assert list(agent.actors[a0].state_dict()) == list(_sd(g, f"actor0/{a0}"))           # the reference's keys, in order
     assert list(agent.critics[a0].state_dict()) == list(_sd(g, f"critic0/{a0}"))
@@ -157,8 +159,8 @@ def test_maddpg_learn_marshalling(standin):
     np.testing.assert_array_equal(s["obs"], cat("obs")); np.testing.assert_array_equal(s["next_obs"], cat("next_obs"))
     np.testing.assert_array_equal(s["act"], cat("action"))
     for i, a in enumerate(ids):
-        np.testing.assert_array_equal(s["rew"][i], g[f"s1_reward/{a}"][:, 0])             # NaN entries travel as NaN
-        np.testing.assert_array_equal(s["done"][i], g[f"s1_done/{a}"][:, 0])
+        np.testing.assert_array_equal(s["rew"][:, i], g[f"s1_reward/{a}"][:, 0])          # [B, n_agents]; NaN travels as NaN
+        np.testing.assert_array_equal(s["done"][:, i], g[f"s1_done/{a}"][:, 0])
         p = s["ptrs"][i]
         assert p["actor"] == agent.actors[a].buffers.params.data_ptr() and p["actor_target"] == agent.actor_targets[a].buffers.params.data_ptr()
         assert p["critic"] == agent.critics[a].buffers.params.data_ptr() and p["critic_target"] == agent.critic_targets[a].buffers.params.data_ptr()
@@ -166,6 +168,7 @@ def test_maddpg_learn_marshalling(standin):
         assert (p["actor_grads"], p["actor_m"], p["actor_v"]) == (ao.grads.data_ptr(), ao.exp_avg.data_ptr(), ao.exp_avg_sq.data_ptr())
         assert (p["critic_grads"], p["critic_m"], p["critic_v"]) == (co.grads.data_ptr(), co.exp_avg.data_ptr(), co.exp_avg_sq.data_ptr())
     assert s["cfg"]["bc1_actor"] == 1.0 - 0.9 ** 1 and s["cfg"]["bc2_critic"] == 1.0 - 0.999 ** 1
+    assert s["cfg"]["serial"] == 0 and s["step_state"] is None                            # concurrent agents, eager scalars
     agent.learn(batch)
     assert standin.seen["cfg"]["bc1_critic"] == 1.0 - 0.9 ** 2
     # the replay's packed matrices go in as they are
@@ -176,7 +179,7 @@ def test_maddpg_learn_marshalling(standin):
     random.seed(5)
     pos = random.sample(range(int(g["B"])), int(g["B"]))
     np.testing.assert_array_equal(standin.seen["obs"], np.concatenate([g[f"s0_obs/{a}"] for a in ids], axis=1)[pos])
-    np.testing.assert_array_equal(standin.seen["rew"], np.stack([g[f"s0_reward/{a}"][pos, 0] for a in ids]))
+    np.testing.assert_array_equal(standin.seen["rew"], np.stack([g[f"s0_reward/{a}"][pos, 0] for a in ids], axis=1))
     # clone: same networks, optimiser step counts travel
     c = agent.clone(index=3)
     assert c.index == 3 and c.actor_optimizers[a0].step == 3 and torch.equal(c.critics[a0].buffers.params, agent.critics[a0].buffers.params)

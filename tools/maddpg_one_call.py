@@ -19,6 +19,7 @@ B = 64
 exp = ({a: torch.randn(B, 18, device="cuda", generator=g) for a in ids}, {a: torch.rand(B, 5, device="cuda", generator=g) * 2 - 1 for a in ids},
        {a: torch.randn(B, 1, device="cuda", generator=g) for a in ids}, {a: torch.randn(B, 18, device="cuda", generator=g) for a in ids},
        {a: (torch.rand(B, 1, device="cuda", generator=g) < 0.1).float() for a in ids})
+agent.use_graph = os.environ.get("GRAPH", "0") == "1"      # eager by default: ncu lists the kernels either way
 for _ in range(3):
     out = agent.learn_device(exp)
 torch.cuda.synchronize()
