@@ -12,6 +12,8 @@ _LEAF = {
     "agilerl.algorithms.dqn_rainbow": "agilerl_b200.algorithms.dqn_rainbow",
     "agilerl.algorithms.td3": "agilerl_b200.algorithms.td3",
     "agilerl.algorithms.ddpg": "agilerl_b200.algorithms.td3",
+    "agilerl.algorithms.maddpg": "agilerl_b200.algorithms.maddpg",
+    "agilerl.components.multi_agent_replay_buffer": "agilerl_b200.components.multi_agent_replay_buffer",
     "agilerl.hpo.tournament": "agilerl_b200.hpo.tournament",
     "agilerl.hpo.mutation": "agilerl_b200.hpo.mutation",
 }
@@ -49,9 +51,9 @@ def install(include_driver: bool | None = None) -> list[str]:
     ``agilerl.training``.
 
     Where the reference package is importable, only the replaced leaf modules (``agilerl.components.{replay_buffer,
-    segment_tree, sampler, data}``, ``agilerl.algorithms.{dqn, dqn_rainbow, td3, ddpg}``, ``agilerl.hpo.{tournament,
+    segment_tree, sampler, data, multi_agent_replay_buffer}``, ``agilerl.algorithms.{dqn, dqn_rainbow, td3, ddpg, maddpg}``, ``agilerl.hpo.{tournament,
     mutation}``) and the three packages that re-export them are aliased; every other name of those packages
-    (``agilerl.algorithms.PPO``, ``agilerl.components.MultiAgentReplayBuffer`` ...) still comes from the reference's own
+    (``agilerl.algorithms.PPO``, ``agilerl.components.RolloutBuffer`` ...) still comes from the reference's own
     files, loaded lazily, and ``agilerl.utils``, ``agilerl.training``, ``agilerl.networks``, ``agilerl.modules`` stay
     the reference's.  Where it is not importable a bare ``agilerl`` namespace is created and
     ``agilerl.training.train_off_policy`` maps to this package's restatement of the driver (``include_driver`` forces

@@ -51,12 +51,14 @@ class _LearnPlan:
         self.obs, self.action, self.reward, self.next_obs, self.done = mk(SO), mk(SA), mk(n), mk(SO), mk(n)
         self.out = torch.zeros((n, 2), dtype=torch.float32, device=dev)
         self.state_host = _lib.StepState()
+        self.state_ref = ctypes.byref(self.state_host)
         self.state_dev = torch.zeros(ctypes.sizeof(_lib.StepState), dtype=torch.uint8, device=dev)
         self.graph = None
+        self._fields = [self.obs, self.action, self.reward, self.next_obs, self.done]
 
     def fields(self):
         """The static buffers in the replay's field order (obs, action, reward, next_obs, done)."""
-        return [self.obs, self.action, self.reward, self.next_obs, self.done]
+        return self._fields
 
     def destroy(self) -> None:
         if self.graph:
@@ -170,6 +172,8 @@ class MADDPG(EvolvableAlgorithm):
         self._actor_descs = (ctypes.POINTER(_lib.NetDesc) * n)(*[ctypes.pointer(self.actors[a].layout.desc) for a in self.agent_ids])
         self._critic_descs = (ctypes.POINTER(_lib.NetDesc) * n)(*[ctypes.pointer(self.critics[a].layout.desc) for a in self.agent_ids])
         self._ws: dict = {}
+        self._all_opts = list(self.actor_optimizers.values()) + list(self.critic_optimizers.values())
+        self._lib = _lib.load()
         self._drop_plans()
         if "use_graph" not in self.__dict__:
             self.use_graph, self.concurrent_agents = _GRAPH, _FAN
@@ -354,6 +358,13 @@ class MADDPG(EvolvableAlgorithm):
         """``learn`` without the host read-back: device tensor ``[n_agents, 2]`` (actor_loss, critic_loss).  With
         ``use_graph`` the tensor is the plan's static result buffer: valid until the next learn call of this batch size."""
         states, actions, rewards, next_states, dones = experiences
+        if self.use_graph:          # the replay gathered straight into a captured call's buffers: nothing to check or copy
+            p = getattr(states, "packed", None)
+            plan = self._plans.get(p.shape[0]) if p is not None else None
+            if (plan is not None and plan.graph is not None and p is plan.obs and getattr(actions, "packed", None) is plan.action
+                    and getattr(rewards, "packed", None) is plan.reward and getattr(next_states, "packed", None) is plan.next_obs
+                    and getattr(dones, "packed", None) is plan.done):
+                return self._replay(plan)
         n = self.n_agents
         SO, SA = sum(self.obs_dims.values()), sum(self.action_dims.values())
         obs, next_obs, act = self._packed(states, SO), self._packed(next_states, SO), self._packed(actions, SA)
@@ -361,9 +372,6 @@ class MADDPG(EvolvableAlgorithm):
         B = obs.shape[0]
         assert next_obs.shape[0] == B and act.shape[0] == B and rew.shape == (B, n) and done.shape == (B, n)
         lib = _lib.load()
-        for o in list(self.actor_optimizers.values()) + list(self.critic_optimizers.values()):
-            o.step += 1
-        self.learn_counter += 1
         if self.use_graph:
             plan = self._plan(B)
             for dst, src in zip(plan.fields(), (obs, act, rew, next_obs, done)):
@@ -372,10 +380,10 @@ class MADDPG(EvolvableAlgorithm):
             if plan.graph is None:
                 self._workspace(B)                                # also creates the library's side streams: not under capture
                 self._capture(plan, B)
-            step = next(iter(self.critic_optimizers.values())).step
-            plan.state_host.bias_correction1, plan.state_host.bias_correction2 = 1.0 - 0.9 ** step, 1.0 - 0.999 ** step
-            _lib.check(lib.b2rl_graph_launch(plan.graph, ctypes.byref(plan.state_host), _lib.stream_ptr(self._dev)))
-            return plan.out
+            return self._replay(plan)
+        for o in self._all_opts:
+            o.step += 1
+        self.learn_counter += 1
         out = torch.empty((n, 2), dtype=torch.float32, device=self._dev)
         cfg, bufs = self._call_args(B, obs, next_obs, act, rew, done, out)
         _lib.check(lib.b2rl_maddpg_learn(ctypes.cast(self._actor_descs, ctypes.c_void_p),
@@ -383,6 +391,15 @@ class MADDPG(EvolvableAlgorithm):
                                          _lib.stream_ptr(self._dev)))
         self._keep = (obs, next_obs, act, rew, done, out)
         return out
+
+    def _replay(self, plan: _LearnPlan) -> torch.Tensor:
+        for o in self._all_opts:
+            o.step += 1
+        self.learn_counter += 1
+        step = self._all_opts[-1].step
+        plan.state_host.bias_correction1, plan.state_host.bias_correction2 = 1.0 - 0.9 ** step, 1.0 - 0.999 ** step
+        _lib.check(self._lib.b2rl_graph_launch(plan.graph, plan.state_ref, _lib.stream_ptr(self._dev)))
+        return plan.out
 
     def soft_update(self, net, target) -> None:
         """maddpg.py:733-746."""

@@ -61,6 +61,7 @@ class MultiAgentReplayBuffer:
         self._widths: list[int] = []
         self._stage = _PinnedRing()
         self._idx_stage = _PinnedRing()
+        self._out_cache: dict = {}
 
     def __len__(self) -> int:
         return self._size
@@ -145,28 +146,34 @@ class MultiAgentReplayBuffer:
             self.save_to_memory_single_env(*args)
 
     # -- sampling --------------------------------------------------------------------------------------
-    def _gather(self, slots: torch.Tensor, out: list | None = None) -> tuple:
+    def _gather(self, slots: torch.Tensor, out: list | None = None, packed_only: bool = False) -> tuple:
         B = slots.numel()
         nf = len(self._rings)
         if out is not None:
-            dsts = list(out)
-            assert len(dsts) == nf and all(d.shape == (B, w) and d.dtype == torch.float32 and d.is_contiguous() and d.device == self._dev
-                                          for d, w in zip(dsts, self._widths)), "out: one contiguous float32 [B, width] per field"
+            key = (id(out[0]), out[0].data_ptr(), B)
+            cached = self._out_cache.get(key)
+            if cached is None:
+                dsts = list(out)
+                assert len(dsts) == nf and all(d.shape == (B, w) and d.dtype == torch.float32 and d.is_contiguous() and d.device == self._dev
+                                              for d, w in zip(dsts, self._widths)), "out: one contiguous float32 [B, width] per field"
+                cached = self._out_cache[key] = (dsts, (ctypes.c_void_p * nf)(*[d.data_ptr() for d in dsts]))
+            dsts, arr = cached
         else:
             dsts = [torch.empty((B, w), dtype=torch.float32, device=self._dev) for w in self._widths]
-        arr = (ctypes.c_void_p * nf)(*[d.data_ptr() for d in dsts])
+            arr = (ctypes.c_void_p * nf)(*[d.data_ptr() for d in dsts])
         _lib.check(self._lib.b2rl_gather_rows_multi(nf, arr, self._ring_ptrs, self._row_bytes, slots.data_ptr(), B,
                                                     _lib.stream_ptr(self._dev)))
-        out = []
+        out_fields = []
         for fi, mat in enumerate(dsts):
             d = PackedField()
             d.packed = mat
-            for aid in self.agent_ids:
-                col0, wa = self._offsets[fi][aid]
-                d[aid] = mat[:, col0:col0 + wa].reshape(B, *self._shapes[fi][aid]) if len(self._shapes[fi][aid]) > 1 \
-                    else mat[:, col0:col0 + wa]
-            out.append(d)
-        return tuple(out)
+            if not packed_only:
+                for aid in self.agent_ids:
+                    col0, wa = self._offsets[fi][aid]
+                    d[aid] = mat[:, col0:col0 + wa].reshape(B, *self._shapes[fi][aid]) if len(self._shapes[fi][aid]) > 1 \
+                        else mat[:, col0:col0 + wa]
+            out_fields.append(d)
+        return tuple(out_fields)
 
     def sample(self, batch_size: int, *args: Any) -> tuple:
         """:157-169 — ``random.sample`` positions (global ``random`` stream) -> ring slots -> one gather launch."""
@@ -182,13 +189,14 @@ class MultiAgentReplayBuffer:
         self._idx_stage.sent(slot, self._dev)
         return self._gather(slots)
 
-    def sample_device(self, batch_size: int, out: list | None = None) -> tuple:
+    def sample_device(self, batch_size: int, out: list | None = None, packed_only: bool = False) -> tuple:
         """``sample`` for the HBM-resident loop: distinct uniform positions drawn on the device (Philox,
         b2rl_sample_uniform_distinct) — no host round trip, not the reference's RNG stream.  ``out``: one ``[B, width]``
-        float32 matrix per field to gather into (``MADDPG.batch_buffers``: the buffers a captured learn call reads)."""
+        float32 matrix per field to gather into (``MADDPG.batch_buffers``: the buffers a captured learn call reads);
+        ``packed_only`` skips the per-agent column views (the returned dicts then only carry ``.packed``)."""
         idx = torch.empty(batch_size, dtype=torch.int64, device=self._dev)
         off = getattr(self, "_uniform_offset", 0)
         _lib.check(self._lib.b2rl_sample_uniform_distinct(0x3A44, off, self._size, batch_size, idx.data_ptr(),
                                                           _lib.stream_ptr(self._dev)))
         self._uniform_offset = off + 64 * batch_size
-        return self._gather(idx, out)     # a uniform draw over the slots is a uniform draw over the positions
+        return self._gather(idx, out, packed_only)     # a uniform draw over the slots is a uniform draw over the positions

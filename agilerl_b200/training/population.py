@@ -65,8 +65,8 @@ def multi_agent_population_learn(pop, memory, batch_size: int | None = None, ove
         return []
     device = pop[0]._dev
     if not overlap:
-        return [m.learn_device(memory.sample_device(batch_size or m.batch_size, out=m.batch_buffers(batch_size or m.batch_size)))
-                for m in pop]
+        return [m.learn_device(memory.sample_device(batch_size or m.batch_size, out=m.batch_buffers(batch_size or m.batch_size),
+                                                    packed_only=True)) for m in pop]
     cur = torch.cuda.current_stream(device)
     streams = _MEMBER_STREAMS.setdefault(torch.device(device), [])
     while len(streams) < len(pop):
@@ -76,7 +76,7 @@ def multi_agent_population_learn(pop, memory, batch_size: int | None = None, ove
         B = batch_size or m.batch_size
         st.wait_stream(cur)
         with torch.cuda.stream(st):
-            losses.append(m.learn_device(memory.sample_device(B, out=m.batch_buffers(B))))
+            losses.append(m.learn_device(memory.sample_device(B, out=m.batch_buffers(B), packed_only=True)))
     for st in streams[:len(pop)]:
         cur.wait_stream(st)
     return losses

@@ -75,3 +75,24 @@ def test_driver_signature_matches(ref):
     rs = list(inspect.signature(ref["train"].train_off_policy).parameters)
     ms = list(inspect.signature(mine).parameters)
     assert ms[:len(rs)] == rs, (rs, ms)
+
+
+def test_multi_agent_surface_matches(ref):
+    """MADDPG / MultiAgentReplayBuffer: same constructor parameters in the same order with the same
+    defaults (``device`` aside), same public methods of the replay and the learner's hot-path methods."""
+    import agilerl.algorithms.maddpg as r_ma
+    import agilerl.components.multi_agent_replay_buffer as r_mb
+    import agilerl_b200.algorithms as a
+    import agilerl_b200.components as c
+    assert _ctor(a.MADDPG) == _ctor(r_ma.MADDPG)
+    assert _ctor(c.MultiAgentReplayBuffer) == _ctor(r_mb.MultiAgentReplayBuffer)
+    rs, ms = inspect.signature(r_ma.MADDPG.__init__).parameters, inspect.signature(a.MADDPG.__init__).parameters
+    for name, p in rs.items():
+        if name in ("self", "device") or p.default is inspect.Parameter.empty:
+            continue
+        assert ms[name].default == p.default, f"MADDPG.{name}: {ms[name].default} != {p.default}"
+    for name in ("save_to_memory", "save_to_memory_single_env", "save_to_memory_vect_envs", "sample"):
+        r_sig = list(inspect.signature(getattr(r_mb.MultiAgentReplayBuffer, name)).parameters)
+        m_sig = list(inspect.signature(getattr(c.MultiAgentReplayBuffer, name)).parameters)
+        assert m_sig[:len(r_sig)] == r_sig, (name, r_sig, m_sig)
+    assert {"learn", "get_action", "action_noise", "reset_action_noise", "soft_update", "test", "clone"} <= set(dir(a.MADDPG))
