@@ -1,4 +1,5 @@
-"""``Mutations`` — drop-in for agilerl/hpo/mutation.py:168-1207 for single-agent value-based agents.
+"""``Mutations`` — drop-in for agilerl/hpo/mutation.py:168-1207 for the single-agent learners of this package and, for
+parameter / hyper-parameter mutations, MADDPG (a policy that is a dict of per-agent networks).
 
 Five mutation kinds with the reference's relative probabilities and RNG use (``self.rng =
 np.random.default_rng(rand_seed)`` :303, ``rng.choice`` over the option list :335-339):
