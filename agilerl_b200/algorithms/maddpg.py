@@ -209,12 +209,9 @@ class MADDPG(EvolvableAlgorithm):
 
     def clone(self, index: int | None = None, wrap: bool = True):
         """core/base.py:855-917: same constructor arguments, then networks, optimiser state and the run-time attributes."""
-        kw = dict(observation_spaces=self.observation_spaces, action_spaces=self.action_spaces, agent_ids=list(self.agent_ids),
-                  O_U_noise=self.O_U_noise, vect_noise_dim=self.vect_noise_dim, theta=self.theta, dt=self.dt,
-                  index=self.index if index is None else index, hp_config=copy.deepcopy(self.registry.hp_config),
-                  net_config=copy.deepcopy(self.net_config), batch_size=self.batch_size, lr_actor=self.lr_actor,
-                  lr_critic=self.lr_critic, learn_step=self.learn_step, gamma=self.gamma, tau=self.tau, mut=self.mut,
-                  normalize_images=self.normalize_images, device=self.device)
+        kw = self._init_kwargs()
+        kw["index"] = self.index if index is None else index
+        kw["device"] = self.device
         c = type(self)(**kw)
         for a in self.agent_ids:
             for src, dst in ((self.actors, c.actors), (self.actor_targets, c.actor_targets), (self.critics, c.critics),
@@ -228,6 +225,44 @@ class MADDPG(EvolvableAlgorithm):
         c.scores, c.fitness, c.steps = list(self.scores), list(self.fitness), list(self.steps)
         c.learn_counter = self.learn_counter
         return c
+
+    # -- cross-rank move (population sharding: hpo/tournament.py::_select_sharded broadcasts a winner from its owner) ------
+    def _init_kwargs(self) -> dict:
+        return dict(observation_spaces=self.observation_spaces, action_spaces=self.action_spaces, agent_ids=list(self.agent_ids),
+                    O_U_noise=self.O_U_noise, vect_noise_dim=self.vect_noise_dim, theta=self.theta, dt=self.dt,
+                    hp_config=copy.deepcopy(self.registry.hp_config), net_config=copy.deepcopy(self.net_config),
+                    batch_size=self.batch_size, lr_actor=self.lr_actor, lr_critic=self.lr_critic, learn_step=self.learn_step,
+                    gamma=self.gamma, tau=self.tau, mut=self.mut, normalize_images=self.normalize_images)
+
+    def _state_tensors(self) -> list:
+        out = []
+        for a in self.agent_ids:
+            ao, co = self.actor_optimizers[a], self.critic_optimizers[a]
+            out += [self.actors[a].buffers.params, self.actor_targets[a].buffers.params, self.critics[a].buffers.params,
+                    self.critic_targets[a].buffers.params, ao.exp_avg, ao.exp_avg_sq, co.exp_avg, co.exp_avg_sq]
+        return out
+
+    def export_state(self):
+        """-> (picklable description, [device tensors]): every network's flat parameter buffer and both Adam moments of
+        every optimiser, 8 tensors per agent (≈ 0.5 MB for config 5)."""
+        meta = {"init": self._init_kwargs(),
+                "attrs": {"scores": list(self.scores), "fitness": list(self.fitness), "steps": list(self.steps), "index": self.index,
+                          "learn_counter": self.learn_counter, "opt_step": self._all_opts[-1].step,
+                          "expl_noise": self.expl_noise, "mean_noise": self.mean_noise, "current_noise": self.current_noise}}
+        return meta, self._state_tensors()
+
+    @classmethod
+    def from_state(cls, meta, tensors, like):
+        agent = cls(device=like.device, **meta["init"])
+        for dst, src in zip(agent._state_tensors(), tensors):
+            dst.copy_(src)
+        a = meta["attrs"]
+        agent.scores, agent.fitness, agent.steps, agent.index = a["scores"], a["fitness"], a["steps"], a["index"]
+        agent.learn_counter = a["learn_counter"]
+        for o in agent._all_opts:
+            o.step = a["opt_step"]
+        agent.expl_noise, agent.mean_noise, agent.current_noise = a["expl_noise"], a["mean_noise"], a["current_noise"]
+        return agent
 
     # -- acting (maddpg.py:428-558) ------------------------------------------------------------------------
     def preprocess_observation(self, observation: dict) -> dict:
@@ -354,9 +389,17 @@ class MADDPG(EvolvableAlgorithm):
         plan.graph = gh.value
         torch.cuda.current_stream(self._dev).wait_stream(cap)
 
-    def learn_device(self, experiences) -> torch.Tensor:
+    def graph_ready(self, B: int) -> bool:
+        """A captured learn call for batch size ``B`` exists (the next ``learn_device`` on ``batch_buffers(B)`` is one
+        graph launch and touches no torch state: it may be given an explicit stream)."""
+        plan = self._plans.get(B)
+        return bool(self.use_graph and plan is not None and plan.graph is not None)
+
+    def learn_device(self, experiences, stream: int | None = None) -> torch.Tensor:
         """``learn`` without the host read-back: device tensor ``[n_agents, 2]`` (actor_loss, critic_loss).  With
-        ``use_graph`` the tensor is the plan's static result buffer: valid until the next learn call of this batch size."""
+        ``use_graph`` the tensor is the plan's static result buffer: valid until the next learn call of this batch size.
+        ``stream`` (raw ``cudaStream_t``; only when ``graph_ready`` and the batch sits in ``batch_buffers``): launch there
+        instead of on torch's current stream."""
         states, actions, rewards, next_states, dones = experiences
         if self.use_graph:          # the replay gathered straight into a captured call's buffers: nothing to check or copy
             p = getattr(states, "packed", None)
@@ -364,7 +407,8 @@ class MADDPG(EvolvableAlgorithm):
             if (plan is not None and plan.graph is not None and p is plan.obs and getattr(actions, "packed", None) is plan.action
                     and getattr(rewards, "packed", None) is plan.reward and getattr(next_states, "packed", None) is plan.next_obs
                     and getattr(dones, "packed", None) is plan.done):
-                return self._replay(plan)
+                return self._replay(plan, stream)
+        assert stream is None, "an explicit stream is only valid for a captured call on batch_buffers()"
         n = self.n_agents
         SO, SA = sum(self.obs_dims.values()), sum(self.action_dims.values())
         obs, next_obs, act = self._packed(states, SO), self._packed(next_states, SO), self._packed(actions, SA)
@@ -392,13 +436,13 @@ class MADDPG(EvolvableAlgorithm):
         self._keep = (obs, next_obs, act, rew, done, out)
         return out
 
-    def _replay(self, plan: _LearnPlan) -> torch.Tensor:
+    def _replay(self, plan: _LearnPlan, stream: int | None = None) -> torch.Tensor:
         for o in self._all_opts:
             o.step += 1
         self.learn_counter += 1
         step = self._all_opts[-1].step
         plan.state_host.bias_correction1, plan.state_host.bias_correction2 = 1.0 - 0.9 ** step, 1.0 - 0.999 ** step
-        _lib.check(self._lib.b2rl_graph_launch(plan.graph, plan.state_ref, _lib.stream_ptr(self._dev)))
+        _lib.check(self._lib.b2rl_graph_launch(plan.graph, plan.state_ref, _lib.stream_ptr(self._dev) if stream is None else stream))
         return plan.out
 
     def soft_update(self, net, target) -> None:

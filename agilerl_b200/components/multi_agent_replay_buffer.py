@@ -62,6 +62,8 @@ class MultiAgentReplayBuffer:
         self._stage = _PinnedRing()
         self._idx_stage = _PinnedRing()
         self._out_cache: dict = {}
+        self._idx_cache: dict = {}
+        self._uniform_offset = 0
 
     def __len__(self) -> int:
         return self._size
@@ -146,7 +148,7 @@ class MultiAgentReplayBuffer:
             self.save_to_memory_single_env(*args)
 
     # -- sampling --------------------------------------------------------------------------------------
-    def _gather(self, slots: torch.Tensor, out: list | None = None, packed_only: bool = False) -> tuple:
+    def _gather(self, slots: torch.Tensor, out: list | None = None, packed_only: bool = False, stream: int | None = None) -> tuple:
         B = slots.numel()
         nf = len(self._rings)
         if out is not None:
@@ -162,7 +164,7 @@ class MultiAgentReplayBuffer:
             dsts = [torch.empty((B, w), dtype=torch.float32, device=self._dev) for w in self._widths]
             arr = (ctypes.c_void_p * nf)(*[d.data_ptr() for d in dsts])
         _lib.check(self._lib.b2rl_gather_rows_multi(nf, arr, self._ring_ptrs, self._row_bytes, slots.data_ptr(), B,
-                                                    _lib.stream_ptr(self._dev)))
+                                                    _lib.stream_ptr(self._dev) if stream is None else stream))
         out_fields = []
         for fi, mat in enumerate(dsts):
             d = PackedField()
@@ -189,14 +191,21 @@ class MultiAgentReplayBuffer:
         self._idx_stage.sent(slot, self._dev)
         return self._gather(slots)
 
-    def sample_device(self, batch_size: int, out: list | None = None, packed_only: bool = False) -> tuple:
+    def sample_device(self, batch_size: int, out: list | None = None, packed_only: bool = False, stream: int | None = None) -> tuple:
         """``sample`` for the HBM-resident loop: distinct uniform positions drawn on the device (Philox,
         b2rl_sample_uniform_distinct) — no host round trip, not the reference's RNG stream.  ``out``: one ``[B, width]``
         float32 matrix per field to gather into (``MADDPG.batch_buffers``: the buffers a captured learn call reads);
-        ``packed_only`` skips the per-agent column views (the returned dicts then only carry ``.packed``)."""
-        idx = torch.empty(batch_size, dtype=torch.int64, device=self._dev)
-        off = getattr(self, "_uniform_offset", 0)
-        _lib.check(self._lib.b2rl_sample_uniform_distinct(0x3A44, off, self._size, batch_size, idx.data_ptr(),
-                                                          _lib.stream_ptr(self._dev)))
+        ``packed_only`` skips the per-agent column views (the returned dicts then only carry ``.packed``); ``stream``: raw
+        ``cudaStream_t`` to enqueue on instead of torch's current stream (only with ``out``: nothing is allocated then)."""
+        if out is not None:                     # one persistent index vector per destination (a member's own buffers)
+            idx = self._idx_cache.get(id(out[0]))
+            if idx is None or idx.numel() != batch_size:
+                idx = self._idx_cache[id(out[0])] = torch.empty(batch_size, dtype=torch.int64, device=self._dev)
+        else:
+            assert stream is None, "an explicit stream needs caller-owned destination buffers (out=...)"
+            idx = torch.empty(batch_size, dtype=torch.int64, device=self._dev)
+        off = self._uniform_offset
+        sp = _lib.stream_ptr(self._dev) if stream is None else stream
+        _lib.check(self._lib.b2rl_sample_uniform_distinct(0x3A44, off, self._size, batch_size, idx.data_ptr(), sp))
         self._uniform_offset = off + 64 * batch_size
-        return self._gather(idx, out, packed_only)     # a uniform draw over the slots is a uniform draw over the positions
+        return self._gather(idx, out, packed_only, sp)     # a uniform draw over the slots is a uniform draw over the positions

@@ -109,6 +109,9 @@ class Mutations:
         """mutation.py:373-411 + _architecture_mutate_single :829-885."""
         registry = individual.registry
         policy = getattr(individual, registry.policy())
+        if isinstance(policy, dict):
+            raise NotImplementedError("architecture mutations of multi-agent networks (mutation.py:887-1010) are not implemented "
+                                      "on the CUDA path: use parameter / RL hyper-parameter mutations for MADDPG")
         if not policy.mutation_methods:
             individual.mut = "None"
             return individual

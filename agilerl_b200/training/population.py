@@ -75,8 +75,12 @@ def multi_agent_population_learn(pop, memory, batch_size: int | None = None, ove
     for m, st in zip(pop, streams):
         B = batch_size or m.batch_size
         st.wait_stream(cur)
-        with torch.cuda.stream(st):
-            losses.append(m.learn_device(memory.sample_device(B, out=m.batch_buffers(B), packed_only=True)))
+        if m.graph_ready(B):       # steady state: two C calls + one graph launch on the member's stream, no torch state touched
+            sp = st.cuda_stream
+            losses.append(m.learn_device(memory.sample_device(B, out=m.batch_buffers(B), packed_only=True, stream=sp), stream=sp))
+        else:                      # first call of this member / batch size: allocations and the capture follow torch's current stream
+            with torch.cuda.stream(st):
+                losses.append(m.learn_device(memory.sample_device(B, out=m.batch_buffers(B), packed_only=True)))
     for st in streams[:len(pop)]:
         cur.wait_stream(st)
     return losses

@@ -302,3 +302,28 @@ def test_parameter_mutation_on_device_keeps_targets_in_step_and_learns():
     assert all(np.isfinite(v) for pair in losses.values() for v in pair)
     acts, raw = mutated.get_action({a: np.zeros((1, int(d)), np.float32) for a, d in zip(ids, g["obs_dims"])})
     assert set(acts) == set(ids) and all(v.shape == (1, int(d)) for v, d in zip(acts.values(), g["act_dims"]))
+
+
+def test_tournament_selects_clones_and_moved_members_learn_identically():
+    """TournamentSelection over a MADDPG population (hpo/tournament.py:41-119) and the cross-rank move used by the sharded
+    tournament (export_state -> from_state): the rebuilt member continues bit-identically to the original."""
+    import pickle
+    from agilerl_b200.hpo import TournamentSelection
+    g = load_golden("maddpg_vector.npz")
+    ids, base = _agent(g)
+    pop = [base.clone(index=k) for k in range(4)]
+    for k, m in enumerate(pop):
+        m.fitness = [float(k)]
+        m.learn(_batch(g, 0, ids))
+    np.random.seed(0)
+    elite, new_pop = TournamentSelection(2, True, 4, 1).select(pop)
+    assert elite.index == 3 and len(new_pop) == 4 and all(type(m) is type(base) for m in new_pop)
+    assert torch.equal(new_pop[0].critics[ids[0]].buffers.params, pop[3].critics[ids[0]].buffers.params)     # elitism
+    src = pop[1]
+    meta, tensors = src.export_state()
+    moved = type(src).from_state(pickle.loads(pickle.dumps(meta)), [t.clone() for t in tensors], src)
+    l1, l2 = src.learn(_batch(g, 2, ids)), moved.learn(_batch(g, 2, ids))
+    assert l1 == l2
+    for a in ids:
+        assert torch.equal(src.actors[a].buffers.params, moved.actors[a].buffers.params)
+        assert torch.equal(src.critic_optimizers[a].exp_avg_sq, moved.critic_optimizers[a].exp_avg_sq)

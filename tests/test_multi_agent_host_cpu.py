@@ -183,6 +183,18 @@ def test_maddpg_learn_marshalling(standin):
     # clone: same networks, optimiser step counts travel
     c = agent.clone(index=3)
     assert c.index == 3 and c.actor_optimizers[a0].step == 3 and torch.equal(c.critics[a0].buffers.params, agent.critics[a0].buffers.params)
+    # cross-rank move (sharded tournament): pickled description + flat tensors rebuild the same member
+    import pickle
+    agent.fitness, agent.scores = [1.5, 2.5], [3.0]
+    meta, tensors = agent.export_state()
+    assert len(tensors) == 8 * len(ids)
+    moved = MADDPG.from_state(pickle.loads(pickle.dumps(meta)), [t.clone() for t in tensors], agent)
+    assert moved.index == agent.index and moved.fitness == [1.5, 2.5] and moved.critic_optimizers[a0].step == 3
+    assert moved.lr_critic == agent.lr_critic and moved.agent_ids == agent.agent_ids
+    for a in ids:
+        assert torch.equal(moved.actors[a].buffers.params, agent.actors[a].buffers.params)
+        assert torch.equal(moved.critic_targets[a].buffers.params, agent.critic_targets[a].buffers.params)
+        assert torch.equal(moved.actor_optimizers[a].exp_avg_sq, agent.actor_optimizers[a].exp_avg_sq)
 
 
 def test_device_mutation_decisions_match_index_put_semantics(standin):
