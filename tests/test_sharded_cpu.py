@@ -126,3 +126,63 @@ def test_cross_rank_experience_sharing_world2_gloo():
     for k in ("obs", "action", "reward", "next_obs", "done"):
         want = torch.cat([r0["_own"][k], r1["_own"][k]], dim=0)
         assert r0[k].dtype == want.dtype and torch.equal(r0[k], want) and torch.equal(r1[k], want), k
+
+
+def _maddpg_worker(rank, world, port, out):
+    """Real ``MADDPG`` members (host side only: the C entry points are never reached — construction, clone, export_state /
+    from_state and the tournament's collectives are pure host + tensor-copy work) through the sharded tournament."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from agilerl_b200 import _lib
+    _lib.as_device = lambda d: torch.device("cpu")                 # test-only: flat buffers as CPU tensors
+    _lib.load = lambda require_cuda=False: None
+    from agilerl_b200.algorithms import MADDPG
+    from agilerl_b200.compat import spaces
+    from agilerl_b200.hpo.tournament import TournamentSelection
+    ids = ["speaker_0", "listener_0"]
+    obs = [spaces.Box(-1.0, 1.0, (3,), np.float32), spaces.Box(-1.0, 1.0, (11,), np.float32)]
+    act = [spaces.Box(-1.0, 1.0, (3,), np.float32), spaces.Box(-1.0, 1.0, (5,), np.float32)]
+    n_local, pop_size = 2, 2 * world
+    fitness = {0: 1.0, 1: 9.0, 2: 5.0, 3: 3.0}
+    pop = []
+    for i in range(n_local):
+        gi = rank * n_local + i
+        torch.manual_seed(100 + gi)
+        m = MADDPG(obs, act, agent_ids=ids, index=gi, batch_size=8, lr_actor=1e-4 * (gi + 1))
+        m.fitness = [fitness[gi]]
+        for o in m._all_opts:
+            o.step = 10 + gi
+            o.exp_avg.fill_(float(gi))
+        pop.append(m)
+    marks = {m.index: float(m.actors["listener_0"].buffers.params.sum()) for m in pop}
+    ts = TournamentSelection(2, True, pop_size, 1, seed=7)
+    elite, new_pop = ts.select(pop)
+    out[rank] = {"plan": ts.last_plan, "marks": marks,
+                 "local": [(m.index, float(m.actors["listener_0"].buffers.params.sum()), m.lr_actor, m._all_opts[0].step,
+                            float(m.critic_optimizers["speaker_0"].exp_avg[0]), list(m.fitness), m.agent_ids) for m in new_pop]}
+    dist.destroy_process_group()
+
+
+def test_sharded_tournament_moves_maddpg_members_world2_gloo():
+    """BASELINE configs[4] shards the MADDPG population two members per GPU: a winner living on another rank travels as
+    its pickled description + 8 flat tensors per agent (parameters, targets, Adam moments) and arrives with its weights,
+    hyper-parameters, optimiser step and fitness history."""
+    world = 2
+    port = 33500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_maddpg_worker, args=(world, port, out), nprocs=world, join=True)
+    r0, r1 = out[0], out[1]
+    assert r0["plan"] == r1["plan"]
+    elite_pos, slots = r0["plan"]
+    assert elite_pos == 1 and slots[0] == (1, 1)
+    marks = {**r0["marks"], **r1["marks"]}
+    new = r0["local"] + r1["local"]
+    crossed = 0
+    for slot, ((parent, new_index), (idx, mark, lr_actor, step, m0, fit, ids)) in enumerate(zip(slots, new)):
+        assert idx == new_index and mark == marks[parent]                       # the parent's weights, wherever it lived
+        assert lr_actor == pytest.approx(1e-4 * (parent + 1)) and step == 10 + parent and m0 == float(parent)
+        assert fit == [{0: 1.0, 1: 9.0, 2: 5.0, 3: 3.0}[parent]] and ids == ["speaker_0", "listener_0"]
+        crossed += int(slot // 2 != parent // 2)
+    assert crossed >= 1                                                          # at least one member changed rank
