@@ -280,14 +280,20 @@ class MADDPG(EvolvableAlgorithm):
             raise NotImplementedError("env_defined_actions are not implemented on the CUDA path")
         states = self.preprocess_observation(obs)
         processed, raw = OrderedDict(), OrderedDict()
+        action_dict, actor = {}, None
         for a in self.agent_ids:
             actor = self.actors[a]
             actions = actor(states[a]).cpu()
             if self.training:
                 actions = torch.clamp(actions + self.action_noise(a), -1.0, 1.0)
-            processed[a] = DeterministicActor.rescale_action(actions, actor.action_low, actor.action_high,
+            action_dict[a] = actions
+        for a in self.agent_ids:
+            # kept quirk (maddpg.py:504-511): the rescaling loop reads ``actor`` — the variable the loop above left pointing
+            # at the LAST agent's network — so every agent's action is rescaled to the last agent's bounds (and agents
+            # whose action widths differ from the last one's raise, as in the reference)
+            processed[a] = DeterministicActor.rescale_action(action_dict[a], actor.action_low, actor.action_high,
                                                              actor.output_activation).numpy()
-            raw[a] = actions.numpy()
+            raw[a] = action_dict[a].numpy()
         return processed, raw
 
     def action_noise(self, agent_id: str) -> torch.Tensor:
@@ -450,22 +456,48 @@ class MADDPG(EvolvableAlgorithm):
         p, t = net.buffers.params, target.buffers.params
         t.copy_(self.tau * p + (1.0 - self.tau) * t)
 
-    def test(self, env, swap_channels: bool = False, max_steps: int | None = None, loop: int = 3, sum_scores: bool = True) -> float:
-        """maddpg.py:748-800 for a PettingZoo-style parallel environment."""
+    def test(self, env, swap_channels: bool = False, max_steps: int | None = None, loop: int = 3, sum_scores: bool = True):
+        """maddpg.py:756-875: mean score over ``loop`` episodes of a (vectorised) PettingZoo-style parallel environment;
+        NaN rewards (inactive agents) count as 0, NaN terminations as True; appends to ``fitness``."""
+        if swap_channels:
+            raise NotImplementedError("image observations are not implemented for MADDPG on the CUDA path")
         self.set_training_mode(False)
         rewards = []
+        is_vectorised = hasattr(env, "num_envs")
+        num_envs = env.num_envs if is_vectorised else 1
+        width = 1 if sum_scores else len(self.agent_ids)
         for _ in range(loop):
             obs, info = env.reset()
-            score, steps, finished = 0.0, 0, False
-            while not finished:
-                steps += 1
+            scores, completed = np.zeros((num_envs, width)), np.zeros((num_envs, width))
+            finished = np.zeros(num_envs)
+            step = 0
+            while not np.all(finished):
+                step += 1
                 action, _ = self.get_action(obs, infos=info)
-                obs, reward, term, trunc, info = env.step({a: v[0] for a, v in action.items()} if self.vect_noise_dim == 1 else action)
-                score += float(np.sum([np.sum(r) for r in reward.values()]))
-                finished = all(bool(np.all(term[a])) or bool(np.all(trunc[a])) for a in term) or \
-                    (max_steps is not None and steps >= max_steps)
-            rewards.append(score)
-        fit = float(np.mean(rewards))
-        self.fitness.append(fit)
-        self.set_training_mode(True)
-        return fit
+                if not is_vectorised:
+                    action = {agent: act[0] for agent, act in action.items()}
+                obs, reward, term, trunc, info = env.step(action)
+                agent_rewards = np.array(list(reward.values())).transpose()
+                agent_rewards = np.where(np.isnan(agent_rewards), 0, agent_rewards)
+                if sum_scores:
+                    inc = np.sum(agent_rewards, axis=-1)[:, np.newaxis] if is_vectorised else np.sum(agent_rewards, axis=-1)
+                else:
+                    inc = agent_rewards
+                scores += inc
+                dones = {}
+                for agent_id in self.agent_ids:
+                    terminated, truncated = term.get(agent_id, True), trunc.get(agent_id, False)
+                    terminated = np.where(np.isnan(terminated), True, terminated).astype(bool)
+                    truncated = np.where(np.isnan(truncated), False, truncated).astype(bool)
+                    dones[agent_id] = terminated | truncated
+                if not is_vectorised:
+                    dones = {agent: np.array([dones[agent_id]]) for agent in self.agent_ids}      # sic (maddpg.py:855-859)
+                for idx, agent_dones in enumerate(zip(*dones.values())):
+                    if (np.all(agent_dones) or (max_steps is not None and step == max_steps)) and not finished[idx]:
+                        completed[idx] = scores[idx]
+                        finished[idx] = 1
+            rewards.append(np.mean(completed, axis=0))
+        mean_fit = np.mean(rewards, axis=0)
+        mean_fit = mean_fit[0] if sum_scores else mean_fit
+        self.fitness.append(mean_fit)
+        return mean_fit

@@ -234,3 +234,153 @@ def test_device_mutation_decisions_match_index_put_semantics(standin):
         Wc[rows, cols] = new.clamp(-1000000, 1000000)                # CPU index_put_: the last writer of a position wins
         W.copy_(Wc)
     assert torch.equal(ours.buffers.params, ref.buffers.params)
+
+
+class _ParallelEnv:
+    """Deterministic PettingZoo-style parallel environment (optionally vectorised): rewards depend on the step and the
+    action, agent_1 is 'killed' (NaN reward / termination) for a while, episodes end at different steps per env."""
+
+    def __init__(self, ids, num_envs=None):
+        self.ids, self.t = ids, 0
+        if num_envs is not None:
+            self.num_envs = num_envs
+        self.n = num_envs or 1
+
+    def reset(self):
+        self.t = 0
+        shape = (self.n, 4) if hasattr(self, "num_envs") else (4,)
+        return {a: np.zeros(shape, np.float32) for a in self.ids}, {a: {} for a in self.ids}
+
+    def step(self, action):
+        self.t += 1
+        vec = hasattr(self, "num_envs")
+        base = np.arange(self.n, dtype=np.float64) + self.t
+        rew, term, trunc = {}, {}, {}
+        for k, a in enumerate(self.ids):
+            r = base * (k + 1) + float(np.sum(action[a])) * 0.01
+            d = (self.t >= 3 + np.arange(self.n)).astype(np.float64)
+            if k == 1 and self.t == 2:
+                r, d = np.full(self.n, np.nan), np.full(self.n, np.nan)
+            rew[a], term[a], trunc[a] = (r, d, np.zeros(self.n)) if vec else (float(r[0]), float(d[0]), False)
+        shape = (self.n, 4) if vec else (4,)
+        return {a: np.full(shape, self.t, np.float32) for a in self.ids}, rew, term, trunc, {a: {} for a in self.ids}
+
+
+@pytest.mark.parametrize("vect,sum_scores,max_steps", [(True, True, None), (True, False, 4), (False, True, None)])
+def test_maddpg_test_loop_matches_the_unmodified_reference(standin, vect, sum_scores, max_steps):
+    """``MADDPG.test`` (maddpg.py:756-875) against the reference's own method run through oracle/refshim on the same
+    environment with the same (stubbed) actions: identical fitness, NaN handling and episode bookkeeping."""
+    from oracle import refshim
+    if not refshim.available():
+        pytest.skip("/root/reference not present (GPU box)")
+    refshim.install()
+    import agilerl.algorithms.maddpg as r_ma
+    from agilerl_b200.algorithms import MADDPG
+    from agilerl_b200.compat import spaces
+    ids = ["agent_0", "agent_1", "agent_2"]
+    n = 3 if vect else None
+
+    def fake_get_action(self, obs, infos=None, **kw):
+        rows = n or 1
+        act = {a: np.full((rows, 2), 0.1 * (k + 1), np.float32) for k, a in enumerate(ids)}
+        return act, act
+    ours = MADDPG([spaces.Box(-1.0, 1.0, (4,), np.float32)] * 3, [spaces.Box(-1.0, 1.0, (2,), np.float32)] * 3, agent_ids=ids)
+    ours.get_action = fake_get_action.__get__(ours)
+    ref = r_ma.MADDPG.__new__(r_ma.MADDPG)                       # the method under test only needs these attributes
+    ref.agent_ids, ref.fitness = ids, []
+    ref.set_training_mode = lambda training: None
+    ref.get_action = fake_get_action.__get__(ref)
+    want = r_ma.MADDPG.test(ref, _ParallelEnv(ids, n), max_steps=max_steps, loop=2, sum_scores=sum_scores)
+    got = ours.test(_ParallelEnv(ids, n), max_steps=max_steps, loop=2, sum_scores=sum_scores)
+    np.testing.assert_array_equal(np.asarray(got), np.asarray(want))
+    np.testing.assert_array_equal(np.asarray(ours.fitness[-1]), np.asarray(ref.fitness[-1]))
+    assert ours.training is False
+
+
+@pytest.mark.parametrize("ou_noise", [True, False])
+def test_maddpg_get_action_noise_and_rescaling_match_the_unmodified_reference(standin, ou_noise):
+    """``get_action`` / ``action_noise`` (maddpg.py:428-558) around the actor forward: exploration noise from torch's global
+    generator (Ornstein-Uhlenbeck state carried across calls, or Gaussian), clamp to [-1, 1], rescale to the action bounds (kept quirk: the LAST agent's bounds for every agent, maddpg.py:504-511) —
+    the real reference object next to ours, our actors stubbed to return the reference actors' outputs."""
+    from oracle import refshim
+    if not refshim.available():
+        pytest.skip("/root/reference not present (GPU box)")
+    refshim.install()
+    import agilerl.algorithms.maddpg as r_ma
+    from gymnasium import spaces as r_spaces
+    from agilerl_b200.algorithms import MADDPG
+    from agilerl_b200.compat import spaces
+    ids = ["a", "b"]
+    mk = lambda sp: ([sp.Box(-1.0, 1.0, (6,), np.float32), sp.Box(-1.0, 1.0, (4,), np.float32)],
+                     [sp.Box(-2.0, 3.0, (3,), np.float32), sp.Box(-0.5, 1.5, (3,), np.float32)])
+    torch.manual_seed(5)
+    ref = r_ma.MADDPG(*mk(r_spaces), agent_ids=ids, O_U_noise=ou_noise, vect_noise_dim=4, expl_noise=0.3, device="cpu")
+    ours = MADDPG(*mk(spaces), agent_ids=ids, O_U_noise=ou_noise, vect_noise_dim=4, expl_noise=0.3)
+
+    class Stub:
+        def __init__(self, actor):
+            self.actor, self.action_low, self.action_high = actor, actor.action_low.cpu(), actor.action_high.cpu()
+            self.output_activation = actor.output_activation
+
+        def __call__(self, obs):
+            with torch.no_grad():
+                return self.actor(obs.cpu())
+    ours.actors = {a: Stub(ref.actors[a]) for a in ids}
+    g = torch.Generator().manual_seed(0)
+    for training in (True, True, False):
+        ref.set_training_mode(training); ours.set_training_mode(training)
+        obs = {"a": torch.randn(4, 6, generator=g).numpy(), "b": torch.randn(4, 4, generator=g).numpy()}
+        torch.manual_seed(77)
+        want_p, want_r = ref.get_action({k: v.copy() for k, v in obs.items()})
+        torch.manual_seed(77)
+        got_p, got_r = ours.get_action({k: v.copy() for k, v in obs.items()})
+        for a in ids:
+            np.testing.assert_array_equal(got_r[a], want_r[a], err_msg=f"raw {a} training={training}")
+            np.testing.assert_array_equal(got_p[a], want_p[a], err_msg=f"processed {a} training={training}")
+    ref.reset_action_noise([1, 3]); ours.reset_action_noise([1, 3])
+    for a in ids:
+        assert torch.equal(ours.current_noise[a], ref.current_noise[a])
+
+
+def test_rl_hyperparameter_and_parameter_mutations_on_a_maddpg_member(standin):
+    """mutation.py:413-452 / :521-584 on a multi-agent member: a learning-rate mutation restarts every optimiser of that
+    kind's owner (fresh Adam state, like ``reinit_optimizers``), a parameter mutation walks every sub-agent's actor and
+    reloads the targets; architecture mutations are refused loudly."""
+    from agilerl_b200.algorithms import MADDPG
+    from agilerl_b200.algorithms.core.registry import HyperparameterConfig, RLParameter
+    from agilerl_b200.compat import spaces
+    from agilerl_b200.hpo import Mutations
+    ids = ["a", "b"]
+    hp = HyperparameterConfig(lr_actor=RLParameter(min=1e-5, max=1e-2), lr_critic=RLParameter(min=1e-5, max=1e-2),
+                              batch_size=RLParameter(min=8, max=512, dtype=int))
+    m = MADDPG([spaces.Box(-1.0, 1.0, (6,), np.float32)] * 2, [spaces.Box(-1.0, 1.0, (3,), np.float32)] * 2, agent_ids=ids, hp_config=hp)
+    m.use_graph = False
+    for o in m._all_opts:
+        o.step = 5
+    c = m.clone(index=1)
+    assert c.registry.hp_config.names() == ["lr_actor", "lr_critic", "batch_size"] and c._all_opts[0].step == 5
+    mut = Mutations(0, 0, 0.5, 0, 0, 1, rand_seed=4, device="cuda")
+    seen = set()
+    for _ in range(12):
+        before = (c.lr_actor, c.lr_critic, c.batch_size)
+        [c] = mut.mutation([c])
+        seen.add(c.mut)
+        after = (c.lr_actor, c.lr_critic, c.batch_size)
+        assert c.mut in ("lr_actor", "lr_critic", "batch_size") and sum(x != y for x, y in zip(before, after)) <= 1
+        if c.mut.startswith("lr"):
+            assert all(o.step == 0 for o in c._all_opts)                        # reinit_optimizers: fresh Adam state
+            assert c.actor_optimizers["a"].lr == c.lr_actor and c.critic_optimizers["b"].lr == c.lr_critic
+    assert len(seen) >= 2
+    pm = Mutations(0, 0, 0.5, 1, 0, 0, rand_seed=2, device="cuda")
+    before = {a: c.actors[a].buffers.params.clone() for a in ids}
+    [c] = pm.mutation([c])
+    assert c.mut == "param"
+    for a in ids:
+        assert not torch.equal(c.actors[a].buffers.params, before[a])
+        assert torch.equal(c.actor_targets[a].buffers.params, c.actors[a].buffers.params)
+    with pytest.raises(NotImplementedError):
+        Mutations(0, 1, 0.5, 0, 0, 0, rand_seed=2, device="cuda").mutation([c])
+    am = Mutations(0, 0, 0.5, 0, 1, 0, rand_seed=2, device="cuda")
+    with pytest.warns(UserWarning):
+        [c] = am.mutation([c])
+    assert c.mut == "None"                                                      # mutation.py:473-480: not supported for MADDPG
