@@ -19,7 +19,6 @@ from __future__ import annotations
 import copy
 import ctypes
 import os
-import warnings
 from collections import OrderedDict
 from typing import Any
 

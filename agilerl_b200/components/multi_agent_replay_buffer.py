@@ -74,6 +74,8 @@ class MultiAgentReplayBuffer:
         for arg in args:
             shapes, offs, col = {}, {}, 0
             for aid in self.agent_ids:
+                if isinstance(arg[aid], (dict, tuple)):
+                    raise NotImplementedError("dict / tuple sub-observations are not implemented in the HBM multi-agent replay")
                 leaf = np.asarray(arg[aid])
                 shape = tuple(leaf.shape[1:]) if vect else tuple(leaf.shape)
                 w = int(np.prod(shape)) if shape else 1
@@ -84,11 +86,6 @@ class MultiAgentReplayBuffer:
         nf = len(self._rings)
         self._ring_ptrs = (ctypes.c_void_p * nf)(*[r.data_ptr() for r in self._rings])
         self._row_bytes = (ctypes.c_int64 * nf)(*[4 * w for w in self._widths])
-        self._stage_off, off = [], 0
-        for w in self._widths:
-            self._stage_off.append(off)
-            off = (off + 4 * w + 255) & ~255
-        self._stage_row = max(off, 256)        # bytes of one step's packed fields (every field 256-byte aligned)
 
     # -- ingest ----------------------------------------------------------------------------------------
     def _save(self, args, n: int, vect: bool) -> None:
