@@ -384,3 +384,75 @@ def test_rl_hyperparameter_and_parameter_mutations_on_a_maddpg_member(standin):
     with pytest.warns(UserWarning):
         [c] = am.mutation([c])
     assert c.mut == "None"                                                      # mutation.py:473-480: not supported for MADDPG
+
+
+# ---- the behaviours the reference's own buffer tests pin (tests/test_components/test_multi_agent_replay_buffer.py), on the
+# ---- HBM layout with the stand-in data movers --------------------------------------------------------------------------
+def _step(k, ids=("agent1", "agent2")):
+    return ({a: np.array([k, k + 1, k + 2]) for a in ids}, {a: np.array([10 * k, 10 * k + 1]) for a in ids},
+            {a: np.array([100 * k + i]) for i, a in enumerate(ids)})
+
+
+def test_buffer_attributes_length_and_counter(standin):
+    from agilerl_b200.components import MultiAgentReplayBuffer
+    fields, ids = ["state", "action", "reward"], ["agent1", "agent2"]
+    buf = MultiAgentReplayBuffer(100, fields, ids)
+    assert len(buf) == 0 and buf.memory_size == 100 and buf.field_names == fields and buf.agent_ids == ids
+    assert buf.counter == 0 and buf.device is None
+    for k in range(3):
+        buf.save_to_memory(*_step(k))
+    assert len(buf) == 3 and buf.counter == 3
+    for bad in (dict(memory_size=0), dict(field_names=[]), dict(agent_ids=[])):
+        kw = dict(memory_size=4, field_names=fields, agent_ids=ids) | bad
+        with pytest.raises(AssertionError):
+            MultiAgentReplayBuffer(**kw)
+
+
+def test_oldest_step_falls_out_when_full(standin):
+    from agilerl_b200.components import MultiAgentReplayBuffer
+    ids = ["agent1", "agent2"]
+    buf = MultiAgentReplayBuffer(2, ["state", "action", "reward"], ids)
+    for k in (1, 2, 3):
+        buf.save_to_memory(*_step(k))
+    assert len(buf) == 2 and buf.counter == 3
+    state, action, reward = buf.sample(2)
+    assert sorted(state["agent1"][:, 0].tolist()) == [2.0, 3.0]                 # step 1 is gone (deque(maxlen) semantics)
+    for row in range(2):                                                       # fields of one step stay together
+        k = int(state["agent1"][row, 0])
+        assert action["agent2"][row].tolist() == [10.0 * k, 10.0 * k + 1] and reward["agent2"][row].tolist() == [100.0 * k + 1]
+
+
+def test_vectorised_and_single_saves_mix_and_samples_stay_aligned(standin):
+    from agilerl_b200.components import MultiAgentReplayBuffer
+    ids = ["agent1", "agent2"]
+    buf = MultiAgentReplayBuffer(100, ["environments", "state"], ids, "cuda")
+    num_envs = 50
+    envs = {a: np.array([[e] for e in range(num_envs)]) for a in ids}
+    states = {a: np.array([[(e + 1) * (i + 1)] for e in range(num_envs)]) for i, a in enumerate(ids)}
+    buf.save_to_memory(envs, states, is_vectorised=True)
+    assert len(buf) == num_envs
+    buf.save_to_memory({a: np.array([77]) for a in ids}, {a: np.array([78 * (i + 1)]) for i, a in enumerate(ids)}, is_vectorised=False)
+    assert len(buf) == num_envs + 1
+    s_envs, s_states = buf.sample(batch_size=25)
+    for i, a in enumerate(ids):
+        assert s_envs[a].dtype == torch.float32 and s_envs[a].shape == (25, 1)
+        for row in range(25):
+            e = int(s_envs[a][row])
+            assert float(s_states[a][row]) == (e + 1) * (i + 1)
+
+
+def test_sampled_shapes_follow_the_leaves_including_images(standin):
+    from agilerl_b200.components import MultiAgentReplayBuffer
+    ids = ["agent1", "agent2"]
+    buf = MultiAgentReplayBuffer(10, ["state", "action", "reward"], ids)
+    rng = np.random.default_rng(0)
+    state = {a: rng.random((3, 16, 16)) for a in ids}
+    buf.save_to_memory(state, {a: np.array([4, 5]) for a in ids}, {a: 6.5 for a in ids})
+    s, a_, r = buf.sample(1)
+    assert s["agent1"].shape == (1, 3, 16, 16) and a_["agent1"].shape == (1, 2) and r["agent1"].shape == (1, 1)
+    np.testing.assert_array_equal(s["agent2"][0].numpy(), state["agent2"].astype(np.float32))      # float64 -> .float()
+    assert a_["agent2"].dtype == torch.float32 and float(r["agent1"]) == 6.5
+    with pytest.raises(NotImplementedError):
+        MultiAgentReplayBuffer(4, ["state"], ids).save_to_memory({a: {"x": np.zeros(2)} for a in ids})
+    with pytest.raises(TypeError):
+        buf.save_to_memory(state)                                                                  # a field is missing
