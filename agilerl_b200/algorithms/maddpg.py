@@ -263,6 +263,46 @@ class MADDPG(EvolvableAlgorithm):
         agent.expl_noise, agent.mean_noise, agent.current_noise = a["expl_noise"], a["mean_noise"], a["current_noise"]
         return agent
 
+    # -- checkpoints (core/base.py:919-1049 reduced to what this learner owns) ---------------------------------------
+    def save_checkpoint(self, path: str) -> None:
+        meta, tensors = self.export_state()
+        torch.save({"algo": self.algo, "meta": meta, "tensors": [t.detach().cpu() for t in tensors]}, path)
+
+    def load_checkpoint(self, path: str) -> None:
+        """Restore networks, targets, Adam moments / step counts, hyper-parameters and run-time attributes into THIS
+        member (same agents and network shapes; a mismatch raises)."""
+        ckpt = torch.load(path, map_location="cpu", weights_only=False)
+        meta, tensors = ckpt["meta"], ckpt["tensors"]
+        init = meta["init"]
+        if list(init["agent_ids"]) != self.agent_ids:
+            raise ValueError(f"checkpoint holds agents {init['agent_ids']}, this member {self.agent_ids}")
+        mine = self._state_tensors()
+        if len(mine) != len(tensors) or any(tuple(a.shape) != tuple(b.shape) for a, b in zip(mine, tensors)):
+            raise ValueError("checkpoint networks do not fit this member's architecture")
+        for k in ("batch_size", "lr_actor", "lr_critic", "learn_step", "gamma", "tau", "mut"):
+            setattr(self, k, init[k])
+        if init.get("hp_config") is not None:
+            self.hp_config = self.registry.hp_config = init["hp_config"]
+        for dst, src in zip(mine, tensors):
+            dst.copy_(src)
+        a = meta["attrs"]
+        self.scores, self.fitness, self.steps, self.index = a["scores"], a["fitness"], a["steps"], a["index"]
+        self.learn_counter = a["learn_counter"]
+        for o in self._all_opts:
+            o.step = a["opt_step"]
+        self.expl_noise, self.mean_noise, self.current_noise = a["expl_noise"], a["mean_noise"], a["current_noise"]
+
+    @classmethod
+    def load(cls, path: str, device: str = "cuda", accelerator=None):
+        """core/base.py ``EvolvableAlgorithm.load``: build the member from the checkpoint alone."""
+        ckpt = torch.load(path, map_location="cpu", weights_only=False)
+
+        class _Like:
+            pass
+        like = _Like()
+        like.device = device
+        return cls.from_state(ckpt["meta"], ckpt["tensors"], like)
+
     # -- acting (maddpg.py:428-558) ------------------------------------------------------------------------
     def preprocess_observation(self, observation: dict) -> dict:
         out = {}

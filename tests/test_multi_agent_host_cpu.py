@@ -195,6 +195,25 @@ def test_maddpg_learn_marshalling(standin):
         assert torch.equal(moved.actors[a].buffers.params, agent.actors[a].buffers.params)
         assert torch.equal(moved.critic_targets[a].buffers.params, agent.critic_targets[a].buffers.params)
         assert torch.equal(moved.actor_optimizers[a].exp_avg_sq, agent.actor_optimizers[a].exp_avg_sq)
+    # checkpoints: into an existing member (hyper-parameters included) and from the file alone
+    import os
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "member.pt")
+        agent.lr_critic = 0.004
+        agent.actor_optimizers[a0].exp_avg.fill_(0.25)
+        agent.save_checkpoint(path)
+        other = MADDPG(agent.observation_spaces, agent.action_spaces, agent_ids=ids, batch_size=int(g["B"]), index=9)
+        other.load_checkpoint(path)
+        fresh = MADDPG.load(path, device="cuda")
+        with pytest.raises(ValueError):                      # other agents: refused, not silently half-loaded
+            MADDPG(agent.observation_spaces[:3], agent.action_spaces[:3], agent_ids=ids[:3]).load_checkpoint(path)
+    for m in (other, fresh):
+        assert m.lr_critic == 0.004 and m.critic_optimizers[a0].lr == 0.004 and m.index == agent.index
+        assert m.actor_optimizers[a0].step == 3 and float(m.actor_optimizers[a0].exp_avg[0]) == 0.25
+        for a in ids:
+            assert torch.equal(m.critics[a].buffers.params, agent.critics[a].buffers.params)
+            assert torch.equal(m.actor_targets[a].buffers.params, agent.actor_targets[a].buffers.params)
 
 
 def test_device_mutation_decisions_match_index_put_semantics(standin):
@@ -456,3 +475,27 @@ def test_sampled_shapes_follow_the_leaves_including_images(standin):
         MultiAgentReplayBuffer(4, ["state"], ids).save_to_memory({a: {"x": np.zeros(2)} for a in ids})
     with pytest.raises(TypeError):
         buf.save_to_memory(state)                                                                  # a field is missing
+
+
+def test_create_population_builds_maddpg_members_with_the_references_defaults(standin):
+    """utils/utils.py:444-472: the INIT_HP -> constructor mapping (gamma 0.95, tau 0.01, lr 1e-4 / 1e-3 defaults of
+    create_population, ``vect_noise_dim = num_envs``)."""
+    from agilerl_b200.compat import spaces
+    from agilerl_b200.utils.utils import create_population
+    ids = ["a", "b"]
+    pop = create_population("MADDPG", [spaces.Box(-1.0, 1.0, (6,), np.float32)] * 2, [spaces.Box(-1.0, 1.0, (3,), np.float32)] * 2,
+                            None, {"AGENT_IDS": ids, "BATCH_SIZE": 32, "LEARN_STEP": 16}, population_size=3, num_envs=4, first_index=5)
+    assert [m.index for m in pop] == [5, 6, 7] and all(m.algo == "MADDPG" and m.agent_ids == ids for m in pop)
+    m = pop[0]
+    assert (m.batch_size, m.learn_step, m.gamma, m.tau, m.lr_actor, m.lr_critic) == (32, 16, 0.95, 0.01, 0.0001, 0.001)
+    assert m.vect_noise_dim == 4 and m.current_noise["a"].shape == (4, 3) and m.O_U_noise is True
+    with pytest.raises(NotImplementedError):
+        create_population("MADDPG", m.observation_spaces, m.action_spaces, None, {"AGENT_IDS": ids, "SHARE_ENCODERS": True})
+    with pytest.raises(NotImplementedError):
+        create_population("PPO", m.observation_spaces[0], m.action_spaces[0], None, {})
+    # the single-agent deterministic-policy learners go through the same helper (utils.py:320-352, 414-442)
+    osp, asp = spaces.Box(-np.inf, np.inf, (17,), np.float32), spaces.Box(-1.0, 1.0, (6,), np.float32)
+    [td3] = create_population("TD3", osp, asp, None, {"POLICY_FREQ": 3}, num_envs=2)
+    [ddpg] = create_population("DDPG", osp, asp, None, {"TAU": 0.002})
+    assert (td3.algo, td3.tau, td3.policy_freq, td3.gamma, td3.vect_noise_dim) == ("TD3", 0.005, 3, 0.99, 2)
+    assert (ddpg.algo, ddpg.tau, ddpg.policy_freq, ddpg.lr_critic) == ("DDPG", 0.002, 2, 0.001)
