@@ -18,7 +18,8 @@
 //   UPDATED critic; dQ/da_i columns -> actor backward + Adam (+ Polyak).
 // The per-agent steps (1)-(4) are independent of each other and run on one library side stream per agent.
 // Same regime as DDPG/TD3: chains of 18..72-wide layers, launch/latency-bound; every chain is one fused launch forward
-// and two backward (head_fused.cuh).  4 agents: 4 x 4 + 4 x 29 = 132 launches per learn call.
+// and two backward (head_fused.cuh).  4 agents: 128 kernels + 4 device copies per learn call
+// (profiles/r2_maddpg_launches_*.txt), replayed as one CUDA graph with a branch per agent (algorithms/maddpg.py).
 #pragma once
 
 namespace b2rl {
