@@ -7,7 +7,8 @@ does not.  Every fixture stores the inputs, any injected randomness, and the ref
 
 What is real and what is a stand-in: the reference's own code runs for segment trees, replay
 buffers, Transition, Sampler, NoisyLinear/MLP/CNN/RainbowQNetwork/QNetwork, RainbowDQN/DQN
-``learn`` and TournamentSelection.  ``tensordict`` and ``gymnasium.spaces`` are the stand-ins of
+``learn``, DDPG/TD3 ``learn``, MADDPG ``learn`` (DeterministicActor + the EvolvableMultiInput critics),
+MultiAgentReplayBuffer, RolloutBuffer's return/advantage loop, Mutations and TournamentSelection.  ``tensordict`` and ``gymnasium.spaces`` are the stand-ins of
 ``agilerl_b200.compat`` (the real packages are not in the image); torch is 2.11 (reference pins
 2.9).
 """
