@@ -1,0 +1,126 @@
+"""Helper of tests/test_reference_driver_cpu.py (run as a script in its own process): the UNCHANGED reference driver
+``/root/reference/agilerl/training/train_off_policy.py`` drives THIS package's classes, bound under the ``agilerl.*`` names
+by ``agilerl_b200.install()``, on BASELINE configs[0] (DQN, pop = 4, vector environment).
+
+No GPU here, so the C entry points the run reaches are Python stand-ins: the data movers copy bytes, the network forward
+returns deterministic pseudo Q-values, the learn call only counts and reports a loss.  What the run therefore proves is the
+drop-in claim at the call level — every method, argument convention, attribute and return type the reference's loop relies
+on (acting with epsilon and masks, ``Transition`` -> ``memory.add``, ``Sampler`` dispatch, ``agent.learn``, ``agent.test``,
+``tournament_selection_and_mutation`` from the reference's own ``utils``) is served by our classes.  Numerics are the GPU
+tests' business."""
+import ctypes
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from oracle import refshim  # noqa: E402
+
+refshim.install()
+import agilerl_b200  # noqa: E402
+from agilerl_b200 import _lib  # noqa: E402
+from agilerl_b200.components import replay_buffer as rb  # noqa: E402
+from test_multi_agent_host_cpu import StandIn, _f32  # noqa: E402
+
+calls = {"learn": 0, "forward_rows": 0, "adds": 0}
+
+
+class Lib(StandIn):
+    def b2rl_ring_write(self, dst, src, row_bytes, start, n, max_size, stream):
+        return self.b2rl_ring_write_multi(1, [dst], [src], [row_bytes], start, n, max_size, stream)
+
+    def b2rl_gather_rows(self, dst, src, idx, row_bytes, n, stream):
+        return self.b2rl_gather_rows_multi(1, [dst], [src], [row_bytes], idx, n, stream)
+
+    def b2rl_noise_count(self, desc, out):
+        out._obj.value = 0
+        return 0
+
+    def b2rl_net_workspace_bytes(self, desc, rows, backward, out):
+        out._obj.value = 256
+        return 0
+
+    def b2rl_net_forward_q(self, desc, params, eps, use_noise, support, obs, row_idx, rows, q_out, argmax_out, ws, wsb, stream):
+        d = desc._obj
+        n_act, elems = d.n_actions, d.obs_elems
+        x = _f32(obs, rows * elems).reshape(rows, elems)
+        q = _f32(q_out, rows * n_act).reshape(rows, n_act)
+        q[:] = np.sin(x.sum(axis=1, keepdims=True) * (np.arange(n_act) + 1.0))
+        calls["forward_rows"] += rows
+        return 0
+
+    def b2rl_dqn_learn(self, desc, cfg, bufs, stream):
+        b = bufs._obj
+        _f32(b.loss_scalar, 1)[0] = 0.25 + 0.001 * calls["learn"]
+        calls["learn"] += 1
+        return 0
+
+
+lib = Lib()
+_lib.as_device = lambda d: torch.device("cpu")
+_lib.load = lambda require_cuda=False: lib
+_lib.stream_ptr = lambda d=None: 0
+_lib.check = lambda rc: None
+_lib.require_cuda_tensor = lambda t, what="tensor": None
+torch.Tensor.pin_memory = lambda self: self
+rb._PinnedRing.sent = lambda self, k, dev: None
+
+agilerl_b200.install(include_driver=False)
+import inspect  # noqa: E402
+
+import agilerl.training.train_off_policy as T  # noqa: E402
+
+assert inspect.getsourcefile(T).startswith("/root/reference/"), inspect.getsourcefile(T)
+import agilerl_b200.algorithms as A  # noqa: E402
+import agilerl_b200.components as C  # noqa: E402
+import agilerl_b200.hpo as H  # noqa: E402
+
+assert T.DQN is A.DQN and T.ReplayBuffer is C.ReplayBuffer and T.Sampler is C.Sampler and T.Mutations is H.Mutations
+from agilerl_b200.compat import spaces  # noqa: E402
+from agilerl_b200.utils.utils import create_population  # noqa: E402
+
+
+class VecEnv:
+    def __init__(self, num_envs=2, seed=0):
+        self.num_envs, self.rng, self.t = num_envs, np.random.default_rng(seed), 0
+
+    def _obs(self):
+        return self.rng.standard_normal((self.num_envs, 4)).astype(np.float32)
+
+    def reset(self):
+        self.t = 0
+        return self._obs(), {}
+
+    def step(self, action):
+        assert np.asarray(action).shape == (self.num_envs,), np.asarray(action).shape
+        self.t += 1
+        return (self._obs(), self.rng.standard_normal(self.num_envs), np.array([self.t % 7 == 0] * self.num_envs),
+                np.zeros(self.num_envs, bool), {})
+
+
+obs_space, act_space = spaces.Box(-1, 1, (4,), np.float32), spaces.Discrete(2)
+INIT_HP = {"BATCH_SIZE": 16, "LEARN_STEP": 2, "DOUBLE": True}
+pop = create_population("DQN", obs_space, act_space, None, INIT_HP, population_size=4)
+memory = C.ReplayBuffer(512, device="cuda")
+orig_add = memory.add
+
+
+def counting_add(data):
+    calls["adds"] += 1
+    return orig_add(data)
+
+
+memory.add = counting_add
+pop, fits = T.train_off_policy(VecEnv(), "synthetic", "DQN", pop, memory, INIT_HP=INIT_HP, MUT_P={}, max_steps=120, evo_steps=40,
+                               eval_steps=10, eval_loop=1, tournament=H.TournamentSelection(2, True, 4, 1),
+                               mutation=H.Mutations(0.5, 0, 0.2, 0.25, 0, 0.25, rand_seed=0, device="cuda"), wb=False, verbose=False)
+print("RESULT " + json.dumps({"pop": len(pop), "generations": len(fits), "fit_width": [len(f) for f in fits],
+                              "steps": [int(a.steps[-1]) for a in pop], "types": sorted({type(a).__module__ for a in pop}),
+                              "calls": calls, "memory_len": len(memory), "muts": [str(a.mut) for a in pop],
+                              "fitness_len": [len(a.fitness) for a in pop]}))
