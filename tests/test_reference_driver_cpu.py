@@ -32,3 +32,21 @@ def test_unchanged_reference_driver_trains_our_dqn_population():
     # buffer holds a batch
     assert r["calls"]["adds"] == 240 and r["memory_len"] == 480
     assert 200 <= r["calls"]["learn"] <= 240 and r["calls"]["forward_rows"] > 480
+
+
+def test_unchanged_reference_driver_runs_the_north_star_flow_on_our_classes():
+    """Rainbow DQN + prioritized replay + 3-step returns on image observations (the flow of BASELINE configs[1]):
+    ``Transition`` -> ``n_step_memory.add`` -> ``memory.add``; ``sampler.sample(B, beta)`` -> ``n_step_sampler.sample(idxs)``
+    -> ``agent.learn(experiences, n_experiences, per=True)`` -> ``memory.update_priorities`` — the reference's loop, our
+    objects.  The priority trees of the run are real (the oracle's C segment tree on the buffers our classes own)."""
+    r = _run("_reference_driver_rainbow_standin.py")
+    c = r["calls"]
+    assert r["pop"] == 2 and r["types"] == ["agilerl_b200.algorithms.dqn_rainbow"] and r["generations"] == 2
+    assert all(s >= 80 for s in r["steps"]) and all(r["beta_grew"])                  # quirk Q16: the driver anneals beta
+    # one loss / backward / optimiser step, one proportional sample and one priority write-back per learn call
+    assert c["loss"] == c["backward"] == c["optim"] == c["per_sample"] == c["tree_set"] >= 60
+    assert c["noise_resets"] >= 2 * c["optim"]                                        # actor, then target (dqn_rainbow.py:484-485)
+    # every env step after the 3-step window filled lands in BOTH rings at the same slot (PER leaves follow tree_ptr)
+    assert r["per_len"] == r["nstep_len"] == r["tree_ptr"] and c["tree_set_range"] >= c["ingest"] >= 70
+    assert all(r["checks"].values()), r["checks"]
+    assert r["distinct_leaves"] > 1 and r["max_priority"] >= 1.0
