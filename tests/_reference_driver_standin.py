@@ -28,7 +28,8 @@ from agilerl_b200 import _lib  # noqa: E402
 from agilerl_b200.components import replay_buffer as rb  # noqa: E402
 from test_multi_agent_host_cpu import StandIn, _f32  # noqa: E402
 
-calls = {"learn": 0, "forward_rows": 0, "adds": 0}
+ALGO = sys.argv[1] if len(sys.argv) > 1 else "DQN"      # "DQN" (configs[0]) or "TD3" (the driver's deterministic-policy branch)
+calls = {"learn": 0, "forward_rows": 0, "adds": 0, "policy_updates": 0}
 
 
 class Lib(StandIn):
@@ -62,6 +63,36 @@ class Lib(StandIn):
         return 0
 
 
+    # ---- TD3 / DDPG: actor forward and the fused learn call ------------------------------------------------------
+    def b2rl_actor_workspace_bytes(self, desc, rows, out):
+        out._obj.value = 256
+        return 0
+
+    def b2rl_ddpg_workspace_bytes(self, actor, critic, batch, out):
+        out._obj.value = 256
+        return 0
+
+    def b2rl_actor_forward(self, desc, params, obs, rows, out, ws, wsb, stream):
+        d = desc._obj
+        a = d.val[d.n_val - 1].out_c
+        x = _f32(obs, rows * d.obs_elems).reshape(rows, d.obs_elems)
+        _f32(out, rows * a).reshape(rows, a)[:] = np.tanh(x.sum(axis=1, keepdims=True) * (np.arange(a) + 1.0) * 0.1)
+        calls["forward_rows"] += rows
+        return 0
+
+    def b2rl_ddpg_learn(self, actor, critic, cfg, bufs, stream):
+        c, b = cfg._obj, bufs._obj
+        B, A = c.batch, actor._obj.val[actor._obj.n_val - 1].out_c
+        assert c.twin == 1 and np.isfinite(_f32(b.action, B * A)).all() and np.isfinite(_f32(b.reward, B)).all()
+        _f32(b.action, B * A)[:] = 0.125                         # the kept quirk: the batch's action tensor receives the noise
+        _f32(b.critic_loss, 1)[0] = 0.5
+        if c.policy_update:
+            _f32(b.actor_loss, 1)[0] = -0.25
+            calls["policy_updates"] += 1
+        calls["learn"] += 1
+        return 0
+
+
 lib = Lib()
 _lib.as_device = lambda d: torch.device("cpu")
 _lib.load = lambda require_cuda=False: lib
@@ -81,7 +112,7 @@ import agilerl_b200.algorithms as A  # noqa: E402
 import agilerl_b200.components as C  # noqa: E402
 import agilerl_b200.hpo as H  # noqa: E402
 
-assert T.DQN is A.DQN and T.ReplayBuffer is C.ReplayBuffer and T.Sampler is C.Sampler and T.Mutations is H.Mutations
+assert T.DQN is A.DQN and T.TD3 is A.TD3 and T.ReplayBuffer is C.ReplayBuffer and T.Sampler is C.Sampler and T.Mutations is H.Mutations
 from agilerl_b200.compat import spaces  # noqa: E402
 from agilerl_b200.utils.utils import create_population  # noqa: E402
 
@@ -98,15 +129,19 @@ class VecEnv:
         return self._obs(), {}
 
     def step(self, action):
-        assert np.asarray(action).shape == (self.num_envs,), np.asarray(action).shape
+        want = (self.num_envs,) if ALGO == "DQN" else (self.num_envs, 3)
+        assert np.asarray(action).shape == want, np.asarray(action).shape
+        if ALGO != "DQN":
+            assert np.all(np.abs(action) <= 2.0 + 1e-6)           # rescaled to the action bounds [-2, 2] by the driver
         self.t += 1
         return (self._obs(), self.rng.standard_normal(self.num_envs), np.array([self.t % 7 == 0] * self.num_envs),
                 np.zeros(self.num_envs, bool), {})
 
 
-obs_space, act_space = spaces.Box(-1, 1, (4,), np.float32), spaces.Discrete(2)
-INIT_HP = {"BATCH_SIZE": 16, "LEARN_STEP": 2, "DOUBLE": True}
-pop = create_population("DQN", obs_space, act_space, None, INIT_HP, population_size=4)
+obs_space = spaces.Box(-1, 1, (4,), np.float32)
+act_space = spaces.Discrete(2) if ALGO == "DQN" else spaces.Box(-2.0, 2.0, (3,), np.float32)
+INIT_HP = {"BATCH_SIZE": 16, "LEARN_STEP": 2, "DOUBLE": True, "POLICY_FREQ": 2}
+pop = create_population(ALGO, obs_space, act_space, None, INIT_HP, population_size=4, num_envs=2)
 memory = C.ReplayBuffer(512, device="cuda")
 orig_add = memory.add
 
@@ -117,7 +152,7 @@ def counting_add(data):
 
 
 memory.add = counting_add
-pop, fits = T.train_off_policy(VecEnv(), "synthetic", "DQN", pop, memory, INIT_HP=INIT_HP, MUT_P={}, max_steps=120, evo_steps=40,
+pop, fits = T.train_off_policy(VecEnv(), "synthetic", ALGO, pop, memory, INIT_HP=INIT_HP, MUT_P={}, max_steps=120, evo_steps=40,
                                eval_steps=10, eval_loop=1, tournament=H.TournamentSelection(2, True, 4, 1),
                                mutation=H.Mutations(0.5, 0, 0.2, 0.25, 0, 0.25, rand_seed=0, device="cuda"), wb=False, verbose=False)
 print("RESULT " + json.dumps({"pop": len(pop), "generations": len(fits), "fit_width": [len(f) for f in fits],

@@ -15,8 +15,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference/agilerl"), reason="needs the reference source tree")
 
 
-def _run(script):
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", script)], capture_output=True, text=True, timeout=600)
+def _run(script, *args):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", script), *args], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-3000:])
     line = [l for l in out.stdout.splitlines() if l.startswith("RESULT ")]
     assert line, out.stdout[-1500:]
@@ -32,6 +32,16 @@ def test_unchanged_reference_driver_trains_our_dqn_population():
     # buffer holds a batch
     assert r["calls"]["adds"] == 240 and r["memory_len"] == 480
     assert 200 <= r["calls"]["learn"] <= 240 and r["calls"]["forward_rows"] > 480
+
+
+def test_unchanged_reference_driver_trains_our_td3_population():
+    """The driver's deterministic-policy branch (train_off_policy.py:281-293, :312-313, :325-326): raw action ->
+    ``DeterministicActor.rescale_action`` -> environment, ``reset_action_noise``, the raw action stored, ``learn`` returning
+    ``(actor_loss | None, critic_loss)`` with the actor stepping every ``policy_freq`` calls."""
+    r = _run("_reference_driver_standin.py", "TD3")
+    assert r["pop"] == 4 and r["types"] == ["agilerl_b200.algorithms.td3"] and r["generations"] == 3
+    assert all(s >= 120 for s in r["steps"]) and r["calls"]["adds"] == 240 and r["memory_len"] == 480
+    assert 200 <= r["calls"]["learn"] <= 240 and abs(2 * r["calls"]["policy_updates"] - r["calls"]["learn"]) <= 4
 
 
 def test_unchanged_reference_driver_runs_the_north_star_flow_on_our_classes():
