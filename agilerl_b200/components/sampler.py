@@ -7,6 +7,7 @@ from __future__ import annotations
 import warnings
 from typing import Any
 
+from .multi_agent_replay_buffer import MultiAgentReplayBuffer
 from .replay_buffer import MultiStepReplayBuffer, PrioritizedReplayBuffer, ReplayBuffer
 
 
@@ -29,8 +30,8 @@ class Sampler:
         elif self.n_step:
             self.sample = self.sample_n_step
         else:
-            if not isinstance(self.memory, ReplayBuffer):
-                warnings.warn("Memory is not an agilerl ReplayBuffer.", stacklevel=2)
+            if not isinstance(self.memory, (ReplayBuffer, MultiAgentReplayBuffer)):          # sampler.py:106-111
+                warnings.warn("Memory is not an agilerl ReplayBuffer or MultiAgentReplayBuffer.", stacklevel=2)
             self.sample = self.sample_standard
 
     def sample_standard(self, batch_size: int, return_idx: bool = False):

@@ -60,3 +60,16 @@ def test_unchanged_reference_driver_runs_the_north_star_flow_on_our_classes():
     assert r["per_len"] == r["nstep_len"] == r["tree_ptr"] and c["tree_set_range"] >= c["ingest"] >= 70
     assert all(r["checks"].values()), r["checks"]
     assert r["distinct_leaves"] > 1 and r["max_priority"] >= 1.0
+
+
+def test_unchanged_reference_multi_agent_driver_trains_our_maddpg_population():
+    """``train_multi_agent_off_policy.py`` (the reference's file) with our ``MADDPG`` members and HBM ``MultiAgentReplayBuffer``
+    (SURVEY 8f-4): vectorised parallel environment with an agent that is dead on some steps (NaN reward / termination), the
+    raw actions stored, the buffer wrapping, ``learn`` returning ``{agent_id: (actor_loss, critic_loss)}``, ``test``,
+    tournament and parameter mutation."""
+    r = _run("_reference_ma_driver_standin.py")
+    c = r["calls"]
+    assert r["pop"] == 3 and r["types"] == ["agilerl_b200.algorithms.maddpg"] and r["generations"] == 3
+    assert all(s >= 96 for s in r["steps"]) and all(n == 3 for n in r["fitness_len"]) and all(n > 0 for n in r["scores"])
+    assert c["saves"] == 144 and r["counter"] == 288 and r["memory_len"] == 200        # 2 envs per save; 200-slot ring wrapped
+    assert 130 <= c["learn"] <= 144 and c["forward_rows"] > 3 * 2 * c["saves"]          # 3 actors x 2 envs per acting step
