@@ -147,6 +147,12 @@ class TensorDict(TensorDictBase):
         td.device = self.device
         return td
 
+    @property
+    def dtype(self):
+        """The leaves' common dtype, ``None`` when they differ (tensordict's semantics)."""
+        kinds = {v.dtype for v in self._data.values() if v.dtype is not None}
+        return kinds.pop() if len(kinds) == 1 else None
+
     def to(self, *args, **kwargs) -> "TensorDict":
         dtype = kwargs.get("dtype")
         device = kwargs.get("device")

@@ -22,9 +22,12 @@ def to_torch_tensor(data, dtype: torch.dtype = torch.float32) -> torch.Tensor:
 
 def to_tensordict(data, dtype: torch.dtype = torch.float32) -> TensorDict:
     """data.py:15-44 (dict / tuple observations)."""
+    ok = (torch.Tensor, np.ndarray, Number)
     if isinstance(data, tuple):
+        assert all(isinstance(el, ok) for el in data), "Expected all elements of the tuple to be torch.Tensor or np.ndarray."
         data = TensorDict({f"tuple_obs_{i}": el for i, el in enumerate(data)})
     elif isinstance(data, dict):
+        assert all(isinstance(el, ok) for el in data.values()), "Expected all values of the dict to be torch.Tensor or np.ndarray."
         data = TensorDict(data)
     return data.to(dtype=dtype)
 

@@ -23,6 +23,7 @@ from __future__ import annotations
 
 import ctypes
 import random
+from collections import namedtuple
 from typing import Any
 
 import numpy as np
@@ -39,6 +40,36 @@ class PackedField(dict):
     packed: torch.Tensor | None = None
 
 
+class _MemoryView:
+    """Read-only stand-in for the reference's ``self.memory`` deque (``maxlen``, ``len``, ``memory[i]`` -> ``Experience`` of
+    ``{agent_id: np.ndarray}`` per field in the saved leaf shape and dtype).  Introspection only: every access copies one
+    ring row per field from the device; the hot path never touches it."""
+
+    def __init__(self, buf):
+        self._buf = buf
+        self.maxlen = buf.memory_size
+
+    def __len__(self) -> int:
+        return self._buf._size
+
+    def __getitem__(self, i: int):
+        b = self._buf
+        n = b._size
+        if not -n <= i < n:
+            raise IndexError("deque index out of range")
+        head = b._cursor if n == b.memory_size else 0
+        slot = (head + (i % n)) % b.memory_size
+        fields = []
+        for fi in range(len(b.field_names)):
+            row = b._rings[fi][slot].cpu().numpy()
+            fields.append({aid: row[c0:c0 + w].reshape(b._leaf_shapes[fi][aid]).astype(b._dtypes[fi][aid])
+                           for aid, (c0, w) in b._offsets[fi].items()})
+        return b.experience(*fields)
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
 class MultiAgentReplayBuffer:
     def __init__(self, memory_size: int, field_names: list[str], agent_ids: list[str], device: str | None = None) -> None:
         assert memory_size > 0, "Memory size must be greater than zero."
@@ -51,6 +82,7 @@ class MultiAgentReplayBuffer:
         self.agent_ids = agent_ids
         self.counter = 0
         self.device = device
+        self.experience = namedtuple("Experience", self.field_names)
         self._dev = _lib.as_device(device if device is not None else "cuda")     # raises: no CPU storage path
         self._lib = _lib.load()
         self._cursor = 0
@@ -68,17 +100,23 @@ class MultiAgentReplayBuffer:
     def __len__(self) -> int:
         return self._size
 
+    @property
+    def memory(self) -> _MemoryView:
+        return _MemoryView(self)
+
     # -- layout ----------------------------------------------------------------------------------------
     def _init(self, args, vect: bool) -> None:
-        self._shapes, self._offsets, self._widths = [], [], []
+        self._shapes, self._offsets, self._widths, self._leaf_shapes, self._dtypes = [], [], [], [], []
         for arg in args:
             shapes, offs, col = {}, {}, 0
+            self._leaf_shapes.append({}); self._dtypes.append({})
             for aid in self.agent_ids:
                 if isinstance(arg[aid], (dict, tuple)):
                     raise NotImplementedError("dict / tuple sub-observations are not implemented in the HBM multi-agent replay")
                 leaf = np.asarray(arg[aid])
                 shape = tuple(leaf.shape[1:]) if vect else tuple(leaf.shape)
                 w = int(np.prod(shape)) if shape else 1
+                self._leaf_shapes[-1][aid], self._dtypes[-1][aid] = shape, leaf.dtype        # what ``memory[i]`` hands back
                 shapes[aid], offs[aid] = (shape if shape else (1,)), (col, w)
                 col += w
             self._shapes.append(shapes); self._offsets.append(offs); self._widths.append(col)
@@ -128,9 +166,36 @@ class MultiAgentReplayBuffer:
         self._size = min(self._size + n, self.memory_size)
         self.counter += n
 
+    def _add(self, *args: dict[str, Any]) -> None:
+        """:103-110 — one step; does not move ``counter`` (the callers do)."""
+        self._save(args, 1, vect=False)
+        self.counter -= 1
+
     def save_to_memory_single_env(self, *args: dict[str, Any]) -> None:
         """:171-179."""
         self._save(args, 1, vect=False)
+
+    # -- host-side helpers of the reference's class surface (not used by the HBM path) --------------------------------
+    @staticmethod
+    def stack_transitions(transitions: list):
+        """:57-101 for array / scalar leaves: one array with a leading batch axis, 1-D results become columns."""
+        if isinstance(transitions[0], (dict, tuple)):
+            raise NotImplementedError("dict / tuple sub-observations are not implemented in the HBM multi-agent replay")
+        ts = np.array(transitions)
+        return np.expand_dims(ts, axis=1) if ts.ndim == 1 else ts
+
+    def _process_transition(self, experiences: list, np_array: bool = False) -> dict:
+        """:112-155 — ``Experience`` tuples -> ``{field: {agent_id: stacked array | float32 tensor}}`` (binary fields through
+        uint8 unless they hold a NaN).  ``sample`` does not go through here: it gathers the packed rings."""
+        out = {field: {} for field in self.field_names}
+        rows = [e for e in experiences if e is not None]
+        for field in self.field_names:
+            for aid in self.agent_ids:
+                ts = self.stack_transitions([getattr(e, field)[aid] for e in rows])
+                if field in BINARY_FIELDS and not np.isnan(ts).any():
+                    ts = ts.astype(np.uint8)
+                out[field][aid] = ts if np_array else torch.as_tensor(ts, device=self._dev).float()
+        return out
 
     def save_to_memory_vect_envs(self, *args: dict[str, Any]) -> None:
         """:213-224 — one step of every vectorised environment, in environment order."""

@@ -26,8 +26,12 @@ class Sampler:
         self.dataset = dataset
         self.dataloader = dataloader
         if self.per:
+            if not isinstance(self.memory, PrioritizedReplayBuffer):                           # sampler.py:92-97 (kept check)
+                warnings.warn("Memory is not an agilerl PrioritizedReplayBuffer.", stacklevel=2)
             self.sample = self.sample_per
         elif self.n_step:
+            if not isinstance(self.memory, MultiStepReplayBuffer):                             # sampler.py:99-104
+                warnings.warn("Memory is not an agilerl MultiStepReplayBuffer.", stacklevel=2)
             self.sample = self.sample_n_step
         else:
             if not isinstance(self.memory, (ReplayBuffer, MultiAgentReplayBuffer)):          # sampler.py:106-111
