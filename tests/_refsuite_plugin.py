@@ -116,6 +116,19 @@ class Lib(StandIn):
         return 0
 
 
+    # construction of the value-based agents only asks for the size of their noise vector
+    def b2rl_noise_count(self, desc, out):
+        d = desc._obj
+        out._obj.value = sum(layers[i].in_c + layers[i].out_c for layers, cnt in ((d.enc, d.n_enc), (d.val, d.n_val), (d.adv, d.n_adv))
+                             for i in range(cnt) if layers[i].noisy)
+        return 0
+
+
+    def _noop(self, *a):
+        return 0
+    b2rl_noise_reset_philox = b2rl_noise_reset_from_normals = _noop          # fresh noise at construction / clone
+
+
 class _Event:
     def record(self, *a): pass
     def synchronize(self): pass
@@ -132,3 +145,11 @@ torch.Tensor.pin_memory = lambda self: self
 torch.cuda.Event = _Event
 rb._PinnedRing.sent = lambda self, k, dev: None
 agilerl_b200.install(include_driver=False)
+
+# tests/test_hpo/test_tournament.py imports a helper of the LLM tests at module level (transformers / peft / accelerate): an
+# inert stand-in keeps the file importable; the LLM cases themselves are outside this package and fail as expected
+import types  # noqa: E402
+
+_grpo = types.ModuleType("tests.test_algorithms.test_llms.test_grpo")
+_grpo.create_module = lambda *a, **k: None
+sys.modules.setdefault("tests.test_algorithms.test_llms.test_grpo", _grpo)

@@ -23,12 +23,12 @@ REF_TESTS = "/root/reference/tests"
 pytestmark = pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason="needs the reference source tree")
 
 
-def _run(rel):
+def _run(rel, noconftest=True):
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "tests"), ROOT, os.environ.get("PYTHONPATH", "")]))
     with tempfile.TemporaryDirectory() as cwd:
-        out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(REF_TESTS, rel), "-p", "_refsuite_plugin", "--noconftest",
-                              "-q", "--no-header", "-p", "no:cacheprovider", "-rf"], capture_output=True, text=True, cwd=cwd, env=env,
-                             timeout=900)
+        cmd = [sys.executable, "-m", "pytest", os.path.join(REF_TESTS, rel), "-p", "_refsuite_plugin", "-q", "--no-header", "-p",
+               "no:cacheprovider", "-rf"] + (["--noconftest"] if noconftest else [])
+        out = subprocess.run(cmd, capture_output=True, text=True, cwd=cwd, env=env, timeout=900)
     text = out.stdout + out.stderr
     failed = set(re.findall(r"^FAILED \S+::(\S+)", text, flags=re.M))
     m = re.search(r"(\d+) passed", text)
@@ -70,3 +70,17 @@ def test_reference_multi_agent_buffer_tests_on_the_hbm_layout():
     assert failed == {"test_append_to_memory_deque", "test_add_experience_when_memory_full", "test_add_experiences_to_memory",
                       "test_add_single_experiences_to_memory", "test_sample_experiences_from_memory_dict"}, text[-2000:]
     assert passed == 11
+
+
+def test_reference_tournament_tests_on_our_selection():
+    """tests/test_hpo/test_tournament.py with the reference's own conftest and ``create_population``: construction,
+    ``_tournament`` / ``_elitism`` known answers and the selection over DQN / Rainbow populations pass; what does not:
+    the two single-agent sweeps stop at DDPG (the reference's ``create_population`` passes ``share_encoders=True``, not
+    implemented here), the two multi-agent sweeps use discrete-action MADDPG actors (not implemented), the rest is LLM."""
+    passed, failed, text = _run("test_hpo/test_tournament.py", noconftest=False)
+    llm = {f for f in failed if f.startswith("test_language_model_tournament[")}
+    assert failed - llm == {"test_returns_best_agent_and_new_population", "test_returns_best_agent_and_new_population_without_elitism",
+                            "test_returns_best_agent_and_new_population_multi_agent",
+                            "test_returns_best_agent_and_new_population_without_elitism_multi_agent"}, text[-2000:]
+    assert passed == 9 and len(llm) == 8
+    assert "share_encoders is not implemented" in text and "only continuous (1-D Box) actions are implemented for MADDPG" in text
