@@ -197,8 +197,6 @@ class Mutations:
         """mutation.py:733-827 with the ``index_put`` of the mutated 10 % of each chosen matrix done by
         ``b2rl_gaussian_mutate`` in place on the flat HBM parameter buffer (no host copy of the weights).
         ``normals`` ({key: float32 [n_mut]}, tests) injects the standard-normal draws."""
-        import ctypes
-
         from .. import _lib
         lib = _lib.load()
         entries = network.layout.entries
