@@ -94,8 +94,6 @@ class _DeterministicPG(RLAlgorithm):
         assert isinstance(policy_freq, int), "Policy frequency must be an integer."
         assert policy_freq >= 1, "Policy frequency must be greater than or equal to one."
         assert isinstance(wrap, bool), "Wrap models flag must be boolean value True or False."
-        if share_encoders:
-            raise NotImplementedError("share_encoders is not implemented on the CUDA path")
         self.batch_size, self.lr_actor, self.lr_critic, self.learn_step = batch_size, lr_actor, lr_critic, learn_step
         self.gamma, self.tau, self.mut, self.policy_freq, self.net_config = gamma, tau, mut, policy_freq, net_config
         self.O_U_noise, self.vect_noise_dim, self.share_encoders = O_U_noise, vect_noise_dim, share_encoders
@@ -146,6 +144,9 @@ class _DeterministicPG(RLAlgorithm):
             self.actor, self.actor_target = mk_a(), mk_a()
             critics, targets = [mk_c() for _ in range(n_c)], [mk_c() for _ in range(n_c)]
         self._set_critics(critics, targets)
+        if self.share_encoders:                                    # ddpg.py:289-296 / td3.py: before the targets are initialised
+            self.share_encoder_parameters()
+            self.register_mutation_hook(self.share_encoder_parameters)
         self.actor_target.load_state_dict(self.actor.state_dict())
         for c, t in zip(critics, targets):
             t.load_state_dict(c.state_dict())
@@ -164,6 +165,29 @@ class _DeterministicPG(RLAlgorithm):
 
     def _critics(self):
         return [getattr(self, n) for n in self._critic_names]
+
+    def share_encoder_parameters(self) -> None:
+        """ddpg.py:335-351 -> utils/algo_utils.py:161-184: the critics' (and target critics') ENCODER parameters become
+        detached copies of the actor's encoder — a snapshot taken here (construction, and again after every mutation through
+        the mutation hook) that no optimiser touches from then on.  The fused learn call updates every critic parameter, so
+        ``learn`` saves the critics' encoder block before the call and puts it back afterwards: identical to never having
+        stepped it (the critics' heads and the actor never read the encoder's own update), and the frozen values live in
+        the critics' own buffers, so clones, checkpoints and cross-rank moves carry them."""
+        src = self.actor
+        keys = [k for k, e in src.layout.entries.items() if k.startswith("encoder.") and e.buf == "param"]
+        for net in self._critics() + self._targets():
+            for k in keys:
+                if k not in net.layout.entries or net.layout.entries[k].shape != src.layout.entries[k].shape:
+                    raise KeyError(f"Found incompatible encoder architectures: {k} not found in shared network.")
+            for k in keys:
+                net.buffers.view(k).copy_(src.buffers.view(k))
+
+    @staticmethod
+    def _encoder_block(net) -> int:
+        """Length of the leading block of the flat parameter buffer that holds the encoder (FlatLayout lays the encoder out
+        first): everything before the first head parameter."""
+        offs = [e.offset for k, e in net.layout.entries.items() if e.buf == "param" and not k.startswith("encoder.")]
+        return min(offs) if offs else net.layout.n_params
 
     def _targets(self):
         return [getattr(self, n) for n in self._target_names]
@@ -295,9 +319,13 @@ class _DeterministicPG(RLAlgorithm):
         bufs.critic_loss, bufs.actor_loss = out[0:].data_ptr(), out[1:].data_ptr()
         ws = self._workspace(B)
         bufs.workspace, bufs.workspace_bytes = ws.data_ptr(), ws.numel()
+        frozen = critics[0].buffers.params[:self._encoder_block(critics[0])].clone() if self.share_encoders else None
         _lib.check(lib.b2rl_ddpg_learn(ctypes.byref(self.actor.layout.desc), ctypes.byref(critics[0].layout.desc),
                                        ctypes.byref(cfg), ctypes.byref(bufs), _lib.stream_ptr(self._dev)))
         self._keep = (obs, next_obs, reward, done, nz, out)
+        if frozen is not None:                                    # share_encoders: the critics' encoders stay what they were
+            for net in critics + targets:
+                net.buffers.params[:frozen.numel()].copy_(frozen)
         return out, policy_update
 
     def soft_update(self, net, target) -> None:

@@ -15,9 +15,8 @@ def create_population(algo: str, observation_space, action_space, net_config: di
     """utils/utils.py:218-474.  ``first_index`` numbers the agents of a population shard."""
     population = []
     algo_kwargs = algo_kwargs or {}
-    if algo in ("DDPG", "TD3", "MADDPG") and INIT_HP.get("SHARE_ENCODERS", False):
-        raise NotImplementedError("SHARE_ENCODERS (utils.py:343 passes True by default) is not implemented on the CUDA path: "
-                                  "actors and critics keep their own encoders")
+    if algo == "MADDPG" and INIT_HP.get("SHARE_ENCODERS", False):
+        raise NotImplementedError("SHARE_ENCODERS is not implemented for MADDPG on the CUDA path")
     noise = dict(O_U_noise=INIT_HP.get("O_U_NOISE", True), expl_noise=INIT_HP.get("EXPL_NOISE", 0.1), vect_noise_dim=num_envs,
                  mean_noise=INIT_HP.get("MEAN_NOISE", 0.0), theta=INIT_HP.get("THETA", 0.15), dt=INIT_HP.get("DT", 0.01))
     pg = dict(hp_config=hp_config, net_config=net_config, batch_size=INIT_HP.get("BATCH_SIZE", 64),
@@ -44,11 +43,13 @@ def create_population(algo: str, observation_space, action_space, net_config: di
         elif algo == "DDPG":                                                    # utils.py:320-352
             agent = DDPG(observation_space=observation_space, action_space=action_space, index=idx, gamma=INIT_HP.get("GAMMA", 0.99),
                          tau=INIT_HP.get("TAU", 0.001), policy_freq=INIT_HP.get("POLICY_FREQ", 2), actor_network=actor_network,
-                         critic_network=critic_network, share_encoders=False, **noise, **pg, **algo_kwargs)
+                         critic_network=critic_network, share_encoders=INIT_HP.get("SHARE_ENCODERS", True), **noise, **pg,
+                         **algo_kwargs)
         elif algo == "TD3":                                                     # utils.py:414-442
             agent = TD3(observation_space=observation_space, action_space=action_space, index=idx, gamma=INIT_HP.get("GAMMA", 0.99),
                         tau=INIT_HP.get("TAU", 0.005), policy_freq=INIT_HP.get("POLICY_FREQ", 2), actor_network=actor_network,
-                        critic_networks=critic_network, share_encoders=False, **noise, **pg, **algo_kwargs)
+                        critic_networks=critic_network, share_encoders=INIT_HP.get("SHARE_ENCODERS", True), **noise, **pg,
+                        **algo_kwargs)
         elif algo == "MADDPG":                                                  # utils.py:444-472
             agent = MADDPG(observation_spaces=observation_space, action_spaces=action_space, agent_ids=INIT_HP["AGENT_IDS"],
                            index=idx, gamma=INIT_HP.get("GAMMA", 0.95), tau=INIT_HP.get("TAU", 0.01),

@@ -499,3 +499,47 @@ def test_create_population_builds_maddpg_members_with_the_references_defaults(st
     [ddpg] = create_population("DDPG", osp, asp, None, {"TAU": 0.002})
     assert (td3.algo, td3.tau, td3.policy_freq, td3.gamma, td3.vect_noise_dim) == ("TD3", 0.005, 3, 0.99, 2)
     assert (ddpg.algo, ddpg.tau, ddpg.policy_freq, ddpg.lr_critic) == ("DDPG", 0.002, 2, 0.001)
+
+
+def test_share_encoders_pins_the_critics_encoders_through_learn(standin):
+    """ddpg.py:289-296, 335-351 (``share_encoder_parameters``): with ``share_encoders=True`` the critics and target critics
+    carry a detached copy of the actor's encoder taken at construction / after a mutation, outside every optimiser.  The
+    fused learn call updates whole parameter buffers, so ``learn`` restores the critics' encoder block afterwards.
+    (Restated from the reference's code: its ``tensordict.from_module / to_module`` cannot run in this image, so this
+    behaviour is not pinned by a golden run.)"""
+    from agilerl_b200.algorithms import TD3
+    from agilerl_b200.compat import spaces
+
+    def fake_learn(actor, critic, cfg, bufs, stream):          # a learn call that moves EVERY parameter of every network
+        b = bufs._obj
+        for ptr, n in ((b.actor, actor._obj.n_params), (b.actor_target, actor._obj.n_params)) + tuple(
+                (p, critic._obj.n_params) for i in range(2) for p in (b.critic[i], b.critic_target[i])):
+            _f32(ptr, n)[:] += 1.0
+        _f32(b.critic_loss, 1)[0] = 1.0
+        _f32(b.actor_loss, 1)[0] = -1.0
+        return 0
+    standin.b2rl_ddpg_learn = fake_learn
+    standin.b2rl_ddpg_workspace_bytes = lambda a, c, B, out: setattr(out._obj, "value", 64) or 0
+    osp, asp = spaces.Box(-np.inf, np.inf, (17,), np.float32), spaces.Box(-1.0, 1.0, (6,), np.float32)
+    agent = TD3(osp, asp, batch_size=8, share_encoders=True, policy_freq=1)
+    enc_keys = [k for k in agent.actor.state_dict() if k.startswith("encoder.")]
+    snap = {k: agent.actor.state_dict()[k].clone() for k in enc_keys}
+    nets = agent._critics() + agent._targets()
+    assert enc_keys and all(torch.equal(n.state_dict()[k], snap[k]) for n in nets for k in enc_keys)
+    heads0 = [{k: v.clone() for k, v in n.state_dict().items() if not k.startswith("encoder.")} for n in nets]
+    g = torch.Generator().manual_seed(0)
+    exp = dict(obs=torch.randn(8, 17, generator=g), action=torch.rand(8, 6, generator=g), reward=torch.randn(8, generator=g),
+               next_obs=torch.randn(8, 17, generator=g), done=torch.zeros(8))
+    agent.learn(exp)
+    assert all(not torch.equal(agent.actor.state_dict()[k], snap[k]) for k in enc_keys)            # the actor's encoder learns
+    for n, h0 in zip(nets, heads0):
+        assert all(torch.equal(n.state_dict()[k], snap[k]) for k in enc_keys)                       # the critics' stay pinned
+        assert all(not torch.equal(n.state_dict()[k], v) for k, v in h0.items())                    # their heads moved
+    clone = agent.clone(index=1)                                                                    # the pinned values travel
+    assert all(torch.equal(n.state_dict()[k], snap[k]) for n in clone._critics() + clone._targets() for k in enc_keys)
+    agent.mutation_hook()                                                                           # re-share after a mutation
+    assert all(torch.equal(n.state_dict()[k], agent.actor.state_dict()[k]) for n in nets for k in enc_keys)
+    plain = TD3(osp, asp, batch_size=8)                                                             # default: nothing is pinned
+    e0 = plain.critic_1.state_dict()[enc_keys[0]].clone()
+    plain.learn(dict(exp, action=torch.rand(8, 6, generator=g)))
+    assert not torch.equal(plain.critic_1.state_dict()[enc_keys[0]], e0)

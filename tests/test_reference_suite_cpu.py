@@ -74,13 +74,12 @@ def test_reference_multi_agent_buffer_tests_on_the_hbm_layout():
 
 def test_reference_tournament_tests_on_our_selection():
     """tests/test_hpo/test_tournament.py with the reference's own conftest and ``create_population``: construction,
-    ``_tournament`` / ``_elitism`` known answers and the selection over DQN / Rainbow populations pass; what does not:
-    the two single-agent sweeps stop at DDPG (the reference's ``create_population`` passes ``share_encoders=True``, not
-    implemented here), the two multi-agent sweeps use discrete-action MADDPG actors (not implemented), the rest is LLM."""
+    ``_tournament`` / ``_elitism`` known answers and the selection sweeps over DQN / Rainbow / DDPG / TD3 populations of OUR
+    agents (plus the reference's PPO / CQN) pass; what does not: the two multi-agent sweeps use discrete-action MADDPG actors
+    (not implemented), the rest is LLM."""
     passed, failed, text = _run("test_hpo/test_tournament.py", noconftest=False)
     llm = {f for f in failed if f.startswith("test_language_model_tournament[")}
-    assert failed - llm == {"test_returns_best_agent_and_new_population", "test_returns_best_agent_and_new_population_without_elitism",
-                            "test_returns_best_agent_and_new_population_multi_agent",
+    assert failed - llm == {"test_returns_best_agent_and_new_population_multi_agent",
                             "test_returns_best_agent_and_new_population_without_elitism_multi_agent"}, text[-2000:]
-    assert passed == 9 and len(llm) == 8
-    assert "share_encoders is not implemented" in text and "only continuous (1-D Box) actions are implemented for MADDPG" in text
+    assert passed == 11 and len(llm) == 8
+    assert "only continuous (1-D Box) actions are implemented for MADDPG" in text
