@@ -99,6 +99,16 @@ class EvolvableAlgorithm:
     def _evolvable_attrs(self) -> list[str]:
         return self.registry.all_registered()
 
+    def evolvable_attributes(self, networks_only: bool = False) -> dict:
+        """core/base.py:790-819: the registered evolvable networks by attribute name and, unless ``networks_only``, the
+        optimisers associated with them."""
+        out = {name: getattr(self, name) for name in self.registry.all_registered() if hasattr(self, name)}
+        if not networks_only:
+            for cfg in self.registry.optimizers:
+                if hasattr(self, cfg.name):
+                    out[cfg.name] = getattr(self, cfg.name)
+        return out
+
     def clone(self, index: int | None = None, wrap: bool = True):
         """core/base.py:855-917."""
         kwargs = self._init_kwargs()

@@ -113,6 +113,11 @@ class Dict(Space):
     def items(self):
         return self.spaces.items()
 
+    def __eq__(self, other):                 # gymnasium: equal when the sub-spaces are
+        return isinstance(other, Dict) and list(self.spaces.items()) == list(other.spaces.items())
+
+    __hash__ = None
+
     def get(self, k, default=None):          # gymnasium's Dict is a Mapping
         return self.spaces.get(k, default)
 
@@ -130,6 +135,11 @@ class Tuple(Space):
     def __init__(self, spaces, seed=None):
         super().__init__(None, None, seed)
         self.spaces = tuple(spaces)
+
+    def __eq__(self, other):
+        return isinstance(other, Tuple) and self.spaces == other.spaces
+
+    __hash__ = None
 
     def __getitem__(self, i):
         return self.spaces[i]

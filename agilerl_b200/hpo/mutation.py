@@ -26,6 +26,25 @@ def set_global_seed(seed: int | None) -> None:
     random.seed(seed)
 
 
+class MutationError(Exception):
+    """mutation.py:1206-1207."""
+
+
+def get_offspring_eval_modules(individual) -> tuple[dict, dict]:
+    """mutation.py:57-82: clones of every registered evaluation network, split into (policy, the rest)."""
+    policy, rest = {}, {}
+    for group in individual.registry.groups:
+        net = getattr(individual, group.eval_network)
+        offspring = {k: v.clone() for k, v in net.items()} if isinstance(net, dict) else net.clone()
+        (policy if group.policy else rest)[group.eval_network] = offspring
+    return policy, rest
+
+
+def get_exp_layer(offspring):
+    """mutation.py:85-101 serves the bandit learners, which are outside this package."""
+    raise TypeError(f"Bandit algorithm architecture {type(offspring)} not supported.")
+
+
 class Mutations:
     def __init__(self, no_mutation: float, architecture: float, new_layer_prob: float, parameters: float,
                  activation: float, rl_hp: float, mutation_sd: float = 0.1, activation_selection: list | None = None,
