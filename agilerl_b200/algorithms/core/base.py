@@ -81,6 +81,15 @@ class EvolvableAlgorithm:
     def set_training_mode(self, training: bool) -> None:
         self.training = training
 
+    def clean_up(self) -> None:
+        """core/base.py:1233-1240: drop the networks and optimisers (their HBM buffers go back to the allocator) — plus the
+        engine state built on them (flat gradient / Adam buffers, captured graphs)."""
+        for name in list(self.evolvable_attributes()):
+            if name in self.__dict__:
+                object.__delattr__(self, name)
+        for name in [k for k in self.__dict__ if k in ("engine", "_ws", "_keep", "_plans") or k.startswith("_engine")]:
+            object.__delattr__(self, name)
+
     # -- clone -----------------------------------------------------------------------------------
     @classmethod
     def _ctor_params(cls) -> list[str]:

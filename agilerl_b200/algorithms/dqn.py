@@ -74,7 +74,10 @@ class DQN(RLAlgorithm):
 
     def learn(self, experiences) -> float:
         """dqn.py:326-347 (update :274-324 + soft_update) as one fused launch sequence."""
-        loss = self.engine.dqn_learn(experiences, B=self.batch_size,
+        # the reference's update works on whatever rows the batch holds (dqn.py:274-324 has no ``range(batch_size)``
+        # indexing — that is Rainbow's quirk Q17): the batch, not ``self.batch_size``, sets the row count
+        rows = int(experiences["reward"].numel())
+        loss = self.engine.dqn_learn(experiences, B=rows,
                                      hp=dict(gamma=self.gamma, lr=self.lr, tau=self.tau), double=self.double)
         return loss.item()
 

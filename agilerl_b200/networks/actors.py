@@ -23,7 +23,8 @@ from .spec import MlpSpec, NetSpec
 
 
 def _mlp_only(observation_space) -> None:
-    if len(observation_space.shape) != 1:
+    shape = getattr(observation_space, "shape", None)
+    if not isinstance(observation_space, spaces.Box) or shape is None or len(shape) != 1:
         raise NotImplementedError("DDPG / TD3 on the CUDA path take vector observations (BASELINE configs[2]: 17-dim)")
 
 

@@ -153,3 +153,75 @@ import types  # noqa: E402
 _grpo = types.ModuleType("tests.test_algorithms.test_llms.test_grpo")
 _grpo.create_module = lambda *a, **k: None
 sys.modules.setdefault("tests.test_algorithms.test_llms.test_grpo", _grpo)
+
+
+# ---- the learners' entry points, for the reference's ALGORITHM tests (construct / act / learn / clone / test loop): the
+# ---- forwards return deterministic pseudo values that depend on the first parameter, the learn calls MOVE the parameter
+# ---- buffers (and soft-update the targets), so "learning changed the weights" / "the clone is a deep copy" assertions see
+# ---- what they would on the device.  Numerics are the GPU tests' business.
+_cls = type(_lib.load())
+
+
+def _obs_rows(d, obs, rows):
+    x = _bytes(obs, rows * d.obs_elems) if d.obs_u8 else _f32(obs, rows * d.obs_elems)
+    return x.reshape(rows, d.obs_elems)[:, :16].astype(np.float64).sum(axis=1, keepdims=True)
+
+def net_workspace_bytes(self, desc, rows, backward, out):
+    out._obj.value = 256; return 0
+def forward_q(self, desc, params, eps, use_noise, support, obs, row_idx, rows, q_out, argmax_out, ws, wsb, stream):
+    d = desc._obj
+    q = _f32(q_out, rows * d.n_actions).reshape(rows, d.n_actions)
+    q[:] = np.sin(_obs_rows(d, obs, rows) * (np.arange(d.n_actions) + 1.0) + float(_f32(params, 1)[0]))
+    if argmax_out: _i64(argmax_out, rows)[:] = q.argmax(axis=1)
+    return 0
+def forward_dist(self, desc, params, eps, use_noise, support, obs, rows, log_probs, dist_out, ws, wsb, stream):
+    d = desc._obj
+    out = _f32(dist_out, rows * d.n_actions * d.n_atoms)
+    out[:] = np.log(1.0 / d.n_atoms) if log_probs else 1.0 / d.n_atoms
+    return 0
+def rainbow_loss(self, desc, cfg, bufs, stream):
+    c, b = cfg._obj, bufs._obj
+    B = c.batch
+    if b.priorities:
+        pr = _f32(b.priorities, B)
+        if not c.accumulate: pr[:] = 0
+        pr += np.float32(0.5 + c.prior_eps)
+    if b.loss_elem: _f32(b.loss_elem, B)[:] = 0.5
+    if b.loss_scalar: _f32(b.loss_scalar, 1)[0] = 0.5
+    return 0
+def optim_step(self, desc, cfg, bufs, stream):
+    d, c, b = desc._obj, cfg._obj, bufs._obj
+    p, t = _f32(b.actor_params, d.n_params), _f32(b.target_params, d.n_params)
+    p += 0.01
+    t[:] = c.tau * p + (1 - c.tau) * t
+    return 0
+def dqn_learn(self, desc, cfg, bufs, stream):
+    optim_step(self, desc, cfg, bufs, stream)
+    _f32(bufs._obj.loss_scalar, 1)[0] = 0.25
+    return 0
+def ok(self, *a): return 0
+def actor_ws(self, desc, rows, out): out._obj.value = 256; return 0
+def ddpg_ws(self, a, c, B, out): out._obj.value = 256; return 0
+def actor_forward(self, desc, params, obs, rows, out, ws, wsb, stream):
+    d = desc._obj; a = d.val[d.n_val - 1].out_c
+    x = _f32(obs, rows * d.obs_elems).reshape(rows, d.obs_elems)
+    _f32(out, rows * a).reshape(rows, a)[:] = np.tanh(x.sum(axis=1, keepdims=True) * (np.arange(a) + 1.0) * 0.1 + float(_f32(params, 1)[0]))
+    return 0
+def ddpg_learn(self, actor, critic, cfg, bufs, stream):
+    c, b = cfg._obj, bufs._obj
+    na, nc = actor._obj.n_params, critic._obj.n_params
+    for i in range(2 if c.twin else 1):
+        p, t = _f32(b.critic[i], nc), _f32(b.critic_target[i], nc)
+        p += 0.01
+        if c.policy_update: t[:] = c.tau * p + (1 - c.tau) * t
+    if c.policy_update:
+        p, t = _f32(b.actor, na), _f32(b.actor_target, na)
+        p += 0.01; t[:] = c.tau * p + (1 - c.tau) * t
+        _f32(b.actor_loss, 1)[0] = -0.5
+    _f32(b.critic_loss, 1)[0] = 0.5
+    return 0
+for name, fn in dict(b2rl_net_workspace_bytes=net_workspace_bytes, b2rl_net_forward_q=forward_q, b2rl_net_forward_dist=forward_dist,
+                     b2rl_rainbow_loss=rainbow_loss, b2rl_rainbow_backward=ok, b2rl_optim_step=optim_step, b2rl_dqn_learn=dqn_learn,
+                     b2rl_noise_reset_state=ok, b2rl_noise_reset_state_pair=ok, b2rl_actor_workspace_bytes=actor_ws,
+                     b2rl_ddpg_workspace_bytes=ddpg_ws, b2rl_actor_forward=actor_forward, b2rl_ddpg_learn=ddpg_learn).items():
+    setattr(_cls, name, fn)

@@ -23,16 +23,39 @@ REF_TESTS = "/root/reference/tests"
 pytestmark = pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason="needs the reference source tree")
 
 
-def _run(rel, noconftest=True):
+def _run_one(rel, noconftest=True):
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "tests"), ROOT, os.environ.get("PYTHONPATH", "")]))
     with tempfile.TemporaryDirectory() as cwd:
         cmd = [sys.executable, "-m", "pytest", os.path.join(REF_TESTS, rel), "-p", "_refsuite_plugin", "-q", "--no-header", "-p",
                "no:cacheprovider", "-rf"] + (["--noconftest"] if noconftest else [])
-        out = subprocess.run(cmd, capture_output=True, text=True, cwd=cwd, env=env, timeout=900)
+        out = subprocess.run(cmd, capture_output=True, text=True, cwd=cwd, env=env, timeout=1500)
     text = out.stdout + out.stderr
     failed = set(re.findall(r"^FAILED \S+::(\S+)", text, flags=re.M))
     m = re.search(r"(\d+) passed", text)
     return (int(m.group(1)) if m else 0), failed, text
+
+
+_ALG = os.path.join("test_algorithms", "test_single_agent")
+_JOBS = {"test_components/test_segment_tree.py": True, "test_components/test_replay_buffer.py": True,
+         "test_components/test_replay_data.py": True, "test_components/test_sampler.py": True,
+         "test_components/test_multi_agent_replay_buffer.py": True, "test_hpo/test_tournament.py": False,
+         "test_hpo/test_mutation.py": False, os.path.join(_ALG, "test_dqn.py"): False,
+         os.path.join(_ALG, "test_dqn_rainbow.py"): False, os.path.join(_ALG, "test_td3.py"): False,
+         os.path.join(_ALG, "test_ddpg.py"): False}
+_FUTURES: dict = {}
+
+
+def _run(rel, noconftest=True):
+    """Every reference test file runs in its own process; all of them are started together on first use (they are
+    independent) and each test of this module picks up its own result."""
+    if not _FUTURES:
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(max_workers=max(2, min(6, (os.cpu_count() or 2))))
+        for job, nc in _JOBS.items():
+            _FUTURES[job] = pool.submit(_run_one, job, nc)
+    if rel not in _FUTURES:
+        return _run_one(rel, noconftest)
+    return _FUTURES[rel].result()
 
 
 def test_reference_segment_tree_tests_pass_on_our_trees():
@@ -98,3 +121,20 @@ def test_reference_mutation_tests_that_concern_our_learners_pass():
     ours = [l for l in text.splitlines() if l.startswith("E ") and "agilerl_b200" in l and "Error" in l
             and not any(tag in l for tag in ("NotImplementedError", "has no attribute '_", "B2RLError"))]
     assert not ours, ours[:5]
+
+
+@pytest.mark.parametrize("rel,at_least", [("test_dqn.py", 21), ("test_dqn_rainbow.py", 22), ("test_td3.py", 12), ("test_ddpg.py", 9)])
+def test_reference_algorithm_tests_construct_act_learn_clone(rel, at_least):
+    """tests/test_algorithms/test_single_agent/*: the cases on the spaces this package implements without accelerate —
+    construction and attributes, (masked / epsilon-greedy / noisy) acting, ``learn`` on 1-step / n-step / PER batches with
+    the reference's return types, ``soft_update``, the ``test`` loop, ``clone`` (deep copy, new index, after learning),
+    ``clean_up``.  The rest needs accelerate, dict / image spaces the learner does not implement, the reference's own
+    module classes as ``actor_network``, or expects the reference's ``device='cpu'`` default."""
+    passed, failed, text = _run(os.path.join("test_algorithms", "test_single_agent", rel), noconftest=False)
+    assert passed >= at_least, text[-3000:]
+    allowed = ("accelerate/DDP wrapping is replaced", "Dict/Tuple observation spaces", "take vector observations",
+               "but must be of type EvolvableModule", "assert 'cuda' == 'cpu'", "device=_Dummy", "does not require grad",
+               "normalize_images=False for image observations", "Regex pattern did not match", "DID NOT RAISE", "DID NOT WARN")
+    errors = [l for l in text.splitlines() if l.startswith("E  ") and ("Error" in l or "assert" in l)]
+    odd = [l for l in errors if not any(a in l for a in allowed)]
+    assert len(odd) <= 2, odd[:6]
