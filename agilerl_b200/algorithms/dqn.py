@@ -76,7 +76,8 @@ class DQN(RLAlgorithm):
         """dqn.py:326-347 (update :274-324 + soft_update) as one fused launch sequence."""
         # the reference's update works on whatever rows the batch holds (dqn.py:274-324 has no ``range(batch_size)``
         # indexing — that is Rainbow's quirk Q17): the batch, not ``self.batch_size``, sets the row count
-        rows = int(experiences["reward"].numel())
+        r = experiences["reward"]
+        rows = int(r.numel()) if isinstance(r, torch.Tensor) else int(np.asarray(r).size)
         loss = self.engine.dqn_learn(experiences, B=rows,
                                      hp=dict(gamma=self.gamma, lr=self.lr, tau=self.tau), double=self.double)
         return loss.item()
