@@ -65,6 +65,15 @@ class _LearnPlan:
             self.graph = None
 
 
+class _AgentOptimizers(OrderedDict):
+    """{agent_id: Adam state}; ``.optimizer`` is the mapping itself — the reference's ``OptimizerWrapper`` over a
+    ``ModuleDict`` exposes its per-agent optimisers under that name (optimizer_wrapper.py)."""
+
+    @property
+    def optimizer(self):
+        return self
+
+
 def concatenate_spaces(space_list) -> spaces.Box:
     """utils/algo_utils.py concatenate_spaces for 1-D Boxes."""
     low = np.concatenate([np.asarray(s.low, np.float32).reshape(-1) for s in space_list])
@@ -161,8 +170,8 @@ class MADDPG(EvolvableAlgorithm):
 
     # -- engine state ------------------------------------------------------------------------------------
     def _bind_engine(self, keep: dict | None = None) -> None:
-        self.actor_optimizers = OrderedDict((a, _AdamState(self.actors[a], self.lr_actor)) for a in self.agent_ids)
-        self.critic_optimizers = OrderedDict((a, _AdamState(self.critics[a], self.lr_critic)) for a in self.agent_ids)
+        self.actor_optimizers = _AgentOptimizers((a, _AdamState(self.actors[a], self.lr_actor)) for a in self.agent_ids)
+        self.critic_optimizers = _AgentOptimizers((a, _AdamState(self.critics[a], self.lr_critic)) for a in self.agent_ids)
         if keep:
             for a in self.agent_ids:
                 self.actor_optimizers[a].load_state_dict(keep["actors"][a])

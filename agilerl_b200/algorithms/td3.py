@@ -57,6 +57,9 @@ class _AdamState:
     def zero_grad(self) -> None:
         pass
 
+    def __repr__(self) -> str:                    # what ``str(torch.optim.Adam)`` shows of the hyper-parameters
+        return f"Adam (lr: {self.lr}, betas: (0.9, 0.999), eps: 1e-08, weight_decay: 0)"
+
 
 class _DeterministicPG(RLAlgorithm):
     _twin = False

@@ -220,7 +220,19 @@ def ddpg_learn(self, actor, critic, cfg, bufs, stream):
         _f32(b.actor_loss, 1)[0] = -0.5
     _f32(b.critic_loss, 1)[0] = 0.5
     return 0
-for name, fn in dict(b2rl_net_workspace_bytes=net_workspace_bytes, b2rl_net_forward_q=forward_q, b2rl_net_forward_dist=forward_dist,
+def maddpg_ws(self, actors, critics, n, B, out): out._obj.value = 256; return 0
+def maddpg_learn(self, actors, critics, cfg, bufs, stream):
+    c, b = cfg._obj, bufs._obj
+    ap = ctypes.cast(actors, ctypes.POINTER(ctypes.POINTER(_lib.NetDesc)))
+    cp = ctypes.cast(critics, ctypes.POINTER(ctypes.POINTER(_lib.NetDesc)))
+    for i in range(c.n_agents):
+        for ptr, tgt, n in ((b.actor[i], b.actor_target[i], ap[i].contents.n_params), (b.critic[i], b.critic_target[i], cp[i].contents.n_params)):
+            p, t = _f32(ptr, n), _f32(tgt, n)
+            p += 0.01
+            t[:] = c.tau * p + (1 - c.tau) * t
+    _f32(b.losses, 2 * c.n_agents)[:] = 0.5
+    return 0
+for name, fn in dict(b2rl_maddpg_workspace_bytes=maddpg_ws, b2rl_maddpg_learn=maddpg_learn, b2rl_net_workspace_bytes=net_workspace_bytes, b2rl_net_forward_q=forward_q, b2rl_net_forward_dist=forward_dist,
                      b2rl_rainbow_loss=rainbow_loss, b2rl_rainbow_backward=ok, b2rl_optim_step=optim_step, b2rl_dqn_learn=dqn_learn,
                      b2rl_noise_reset_state=ok, b2rl_noise_reset_state_pair=ok, b2rl_actor_workspace_bytes=actor_ws,
                      b2rl_ddpg_workspace_bytes=ddpg_ws, b2rl_actor_forward=actor_forward, b2rl_ddpg_learn=ddpg_learn).items():

