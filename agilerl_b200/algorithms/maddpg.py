@@ -13,7 +13,8 @@ The batch may be the reference's tuple of ``{agent_id: tensor}`` dicts or what `
 returns here (dicts carrying the already concatenated ``[B, sum]`` matrices: no ``torch.cat`` on the way in).
 
 Not implemented (raises): image / Dict sub-observations, discrete (Gumbel-softmax) actors, custom networks,
-``accelerator``, architecture mutations of the sub-networks."""
+``accelerator``, architecture mutations of the sub-networks.  ``env_defined_actions`` in the info dicts are honoured like the
+reference's (maddpg.py:518-529)."""
 from __future__ import annotations
 
 import copy
@@ -323,9 +324,51 @@ class MADDPG(EvolvableAlgorithm):
             out[a] = o.unsqueeze(0) if o.ndim == 1 else o
         return out
 
+    @staticmethod
+    def _key_in_nested_dict(nested: dict, target: str) -> bool:
+        """utils/algo_utils.py:490-507, literally: only the FIRST nested dict met is searched."""
+        for k, v in nested.items():
+            if k == target:
+                return True
+            if isinstance(v, dict):
+                return MADDPG._key_in_nested_dict(v, target)
+        return False
+
+    def extract_agent_masks(self, infos: dict | None = None):
+        """core/base.py:1544-1603 for continuous actions: ``env_defined_actions`` per agent (NaN where the agent acts itself)
+        and the boolean masks of the entries the environment dictates."""
+        if (infos is None or not self._key_in_nested_dict(infos, "env_defined_actions")
+                or all(not info for agent, info in infos.items() if agent in self.agent_ids)):
+            return None, None
+        env_defined = {agent: (info.get("env_defined_actions", None) if isinstance(info, dict) else None)
+                       for agent, info in infos.items() if agent in self.agent_ids}
+        masks = {}
+        for agent_id, val in list(env_defined.items()):
+            if val is None:                                   # environment not vectorised: this agent acts itself
+                val = np.full(self.action_dims[agent_id], np.nan)
+                env_defined[agent_id] = val
+            if isinstance(val, (int, float)):
+                val = np.array([val])
+                env_defined[agent_id] = val
+            masks[agent_id] = np.where(np.isnan(env_defined[agent_id]), 0, 1).astype(bool)
+        return env_defined, masks
+
+    @staticmethod
+    def _reconcile_shapes(reference: np.ndarray, other: np.ndarray):
+        """utils/algo_utils.py:1790-1819, continuous branch."""
+        if reference.shape == other.shape:
+            return reference, other
+        if np.prod(other.shape) == np.prod(reference.shape):
+            if other.ndim < reference.ndim:
+                other = np.expand_dims(other, 0)
+            else:
+                reference = np.expand_dims(reference, 0)
+        return reference, np.broadcast_to(other, reference.shape)
+
     def get_action(self, obs: dict, infos: dict | None = None, *args, **kwargs):
-        if infos is not None and any(isinstance(v, dict) and v.get("env_defined_actions") is not None for v in infos.values()):
-            raise NotImplementedError("env_defined_actions are not implemented on the CUDA path")
+        assert not self._key_in_nested_dict(obs, "action_mask"), \
+            "AgileRL requires action masks to be defined in the information dictionary."
+        env_defined_actions, agent_masks = self.extract_agent_masks(infos)
         states = self.preprocess_observation(obs)
         processed, raw = OrderedDict(), OrderedDict()
         action_dict, actor = {}, None
@@ -342,6 +385,15 @@ class MADDPG(EvolvableAlgorithm):
             processed[a] = DeterministicActor.rescale_action(action_dict[a], actor.action_low, actor.action_high,
                                                              actor.output_activation).numpy()
             raw[a] = action_dict[a].numpy()
+        if env_defined_actions is not None:
+            # maddpg.py:518-529 -> algo_utils.py:1822-1852: the environment's actions overwrite the PROCESSED actions where it
+            # defines them, and (kept quirk) that same dict is what comes back as the "raw" actions too
+            for a in self.agent_ids:
+                action, override = self._reconcile_shapes(processed[a], np.asarray(env_defined_actions[a]))
+                action, mask = self._reconcile_shapes(action, agent_masks[a])
+                action[mask] = override[mask]
+                processed[a] = action
+            raw = processed
         return processed, raw
 
     def action_noise(self, agent_id: str) -> torch.Tensor:

@@ -356,6 +356,21 @@ def test_maddpg_get_action_noise_and_rescaling_match_the_unmodified_reference(st
         for a in ids:
             np.testing.assert_array_equal(got_r[a], want_r[a], err_msg=f"raw {a} training={training}")
             np.testing.assert_array_equal(got_p[a], want_p[a], err_msg=f"processed {a} training={training}")
+    # actions dictated by the environment (maddpg.py:518-529): NaN rows are the agent's own, the rest overwrite — and the
+    # overwritten dict also comes back as the "raw" actions (kept quirk)
+    eda = np.full((4, 3), np.nan)
+    eda[1] = [0.5, -0.25, 1.0]
+    eda[3] = [-2.0, 3.0, 0.0]
+    infos = {"a": {"env_defined_actions": eda}, "b": {"env_defined_actions": np.full((4, 3), np.nan)}}
+    obs = {"a": torch.randn(4, 6, generator=g).numpy(), "b": torch.randn(4, 4, generator=g).numpy()}
+    torch.manual_seed(78)
+    want_p, want_r = ref.get_action({k: v.copy() for k, v in obs.items()}, infos={k: {kk: vv.copy() for kk, vv in v.items()} for k, v in infos.items()})
+    torch.manual_seed(78)
+    got_p, got_r = ours.get_action({k: v.copy() for k, v in obs.items()}, infos={k: {kk: vv.copy() for kk, vv in v.items()} for k, v in infos.items()})
+    for a in ids:
+        np.testing.assert_array_equal(got_p[a], want_p[a], err_msg=f"env-defined processed {a}")
+        np.testing.assert_array_equal(got_r[a], want_r[a], err_msg=f"env-defined raw {a}")
+    np.testing.assert_array_equal(got_p["a"][1], [0.5, -0.25, 1.0])
     ref.reset_action_noise([1, 3]); ours.reset_action_noise([1, 3])
     for a in ids:
         assert torch.equal(ours.current_noise[a], ref.current_noise[a])
