@@ -215,6 +215,23 @@ class _DeterministicPG(RLAlgorithm):
     def reinit_optimizers(self, optimizer=None) -> None:
         self._bind_engine()
 
+    # -- checkpoints: the base class knows ONE optimiser; these learners own two or three --------------------------------
+    def save_checkpoint(self, path: str) -> None:
+        super().save_checkpoint(path)
+        ckpt = torch.load(path, map_location="cpu", weights_only=False)
+        ckpt["optimizers"] = self._opt_state()
+        ckpt["learn_counter"] = self.learn_counter
+        torch.save(ckpt, path)
+
+    def load_checkpoint(self, path: str) -> None:
+        super().load_checkpoint(path)
+        ckpt = torch.load(path, map_location="cpu", weights_only=False)
+        if "optimizers" in ckpt:
+            self.actor_optimizer.load_state_dict(ckpt["optimizers"]["actor"], strict=True)
+            for name, sd in zip(self._opt_names, ckpt["optimizers"]["critics"]):
+                getattr(self, name).load_state_dict(sd, strict=True)
+        self.learn_counter = ckpt.get("learn_counter", self.learn_counter)
+
     def _after_network_swap(self) -> None:
         self._bind_engine()
 

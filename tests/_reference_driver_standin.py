@@ -152,10 +152,25 @@ def counting_add(data):
 
 
 memory.add = counting_add
+import glob  # noqa: E402
+import tempfile  # noqa: E402
+
+ckpt_dir = tempfile.mkdtemp()
 pop, fits = T.train_off_policy(VecEnv(), "synthetic", ALGO, pop, memory, INIT_HP=INIT_HP, MUT_P={}, max_steps=120, evo_steps=40,
                                eval_steps=10, eval_loop=1, tournament=H.TournamentSelection(2, True, 4, 1),
-                               mutation=H.Mutations(0.5, 0, 0.2, 0.25, 0, 0.25, rand_seed=0, device="cuda"), wb=False, verbose=False)
+                               mutation=H.Mutations(0.5, 0, 0.2, 0.25, 0, 0.25, rand_seed=0, device="cuda"), wb=False, verbose=False,
+                               checkpoint=40, checkpoint_path=os.path.join(ckpt_dir, "pop.pt"), overwrite_checkpoints=True,
+                               save_elite=True, elite_path=os.path.join(ckpt_dir, "elite.pt"))
+ckpts = sorted(os.path.basename(f) for f in glob.glob(os.path.join(ckpt_dir, "*")))
+restored = None
+if ALGO == "DQN":                      # the population checkpoints the reference's utils wrote load back into our agents
+    f = [c for c in ckpts if c.startswith("pop")][0]
+    before = pop[0].actor.state_dict()
+    twin = pop[0].clone()
+    twin.actor.buffers.params.zero_()
+    twin.load_checkpoint(os.path.join(ckpt_dir, f))
+    restored = bool(twin.actor.buffers.params.abs().sum() > 0)
 print("RESULT " + json.dumps({"pop": len(pop), "generations": len(fits), "fit_width": [len(f) for f in fits],
                               "steps": [int(a.steps[-1]) for a in pop], "types": sorted({type(a).__module__ for a in pop}),
                               "calls": calls, "memory_len": len(memory), "muts": [str(a.mut) for a in pop],
-                              "fitness_len": [len(a.fitness) for a in pop]}))
+                              "fitness_len": [len(a.fitness) for a in pop], "checkpoints": ckpts, "restored": restored}))

@@ -558,3 +558,26 @@ def test_share_encoders_pins_the_critics_encoders_through_learn(standin):
     e0 = plain.critic_1.state_dict()[enc_keys[0]].clone()
     plain.learn(dict(exp, action=torch.rand(8, 6, generator=g)))
     assert not torch.equal(plain.critic_1.state_dict()[enc_keys[0]], e0)
+
+
+def test_td3_checkpoint_carries_every_optimiser(standin, tmp_path):
+    """core/base.py:919-1049 for a learner with several optimisers: actor AND critic Adam moments / step counts, the
+    learn counter (policy_freq phase) and the mutated hyper-parameters come back."""
+    from agilerl_b200.algorithms import DDPG, TD3
+    from agilerl_b200.compat import spaces
+    osp, asp = spaces.Box(-np.inf, np.inf, (17,), np.float32), spaces.Box(-1.0, 1.0, (6,), np.float32)
+    for cls, crit in ((TD3, "critic_2"), (DDPG, "critic")):
+        a = cls(osp, asp, batch_size=8)
+        opt = getattr(a, crit + "_optimizer")
+        opt.exp_avg.fill_(0.5); opt.exp_avg_sq.fill_(0.25); opt.step = 7
+        a.actor_optimizer.step, a.learn_counter, a.lr_critic = 3, 5, 0.005
+        a.actor.buffers.params.add_(1.0)
+        path = str(tmp_path / f"{cls.__name__}.pt")
+        a.save_checkpoint(path)
+        b = cls(osp, asp, batch_size=8)
+        b.load_checkpoint(path)
+        bopt = getattr(b, crit + "_optimizer")
+        assert torch.equal(a.actor.buffers.params, b.actor.buffers.params)
+        assert torch.equal(getattr(a, crit).buffers.params, getattr(b, crit).buffers.params)
+        assert float(bopt.exp_avg[0]) == 0.5 and float(bopt.exp_avg_sq[0]) == 0.25 and bopt.step == 7 and bopt.lr == 0.005
+        assert b.actor_optimizer.step == 3 and b.learn_counter == 5 and b.lr_critic == 0.005

@@ -32,6 +32,8 @@ def test_unchanged_reference_driver_trains_our_dqn_population():
     # buffer holds a batch
     assert r["calls"]["adds"] == 240 and r["memory_len"] == 480
     assert 200 <= r["calls"]["learn"] <= 240 and r["calls"]["forward_rows"] > 480
+    # the reference's own ``save_population_checkpoint`` / elite saving wrote through our ``save_checkpoint``; it loads back
+    assert r["checkpoints"] == ["elite.pt", "pop_0.pt", "pop_1.pt", "pop_2.pt", "pop_3.pt"] and r["restored"] is True
 
 
 def test_unchanged_reference_driver_trains_our_td3_population():
