@@ -215,6 +215,46 @@ class _DeterministicPG(RLAlgorithm):
     def reinit_optimizers(self, optimizer=None) -> None:
         self._bind_engine()
 
+    # -- cross-rank move (population sharding: hpo/tournament.py::_select_sharded broadcasts a winner from its owner) ------
+    def _all_optimizers(self) -> list:
+        return [self.actor_optimizer] + [getattr(self, n) for n in self._opt_names]
+
+    def export_state(self):
+        """-> (picklable description, [device tensors]): every network's flat parameter buffer, then both Adam moments of
+        the actor's and of every critic's optimiser."""
+        nets = self._evolvable_attrs()
+        meta = {"init": {k: v for k, v in self._init_kwargs().items() if k not in ("device", "accelerator")},
+                "nets": {n: getattr(self, n).init_dict for n in nets},
+                "attrs": {"scores": list(self.scores), "fitness": list(self.fitness), "steps": list(self.steps), "mut": self.mut,
+                          "index": self.index, "learn_counter": self.learn_counter,
+                          "opt_steps": [o.step for o in self._all_optimizers()], "current_noise": self.current_noise}}
+        for n in nets:
+            meta["nets"][n].pop("device", None)
+        tensors = [getattr(self, n).buffers.params for n in nets]
+        for o in self._all_optimizers():
+            tensors += [o.exp_avg, o.exp_avg_sq]
+        return meta, tensors
+
+    @classmethod
+    def from_state(cls, meta, tensors, like):
+        agent = cls(device=like.device, **meta["init"])
+        nets = agent._evolvable_attrs()
+        for n in nets:                                  # the moved member's (possibly mutated) architectures
+            kw = dict(meta["nets"][n])
+            kw["device"] = like.device
+            setattr(agent, n, type(getattr(agent, n))(**kw))
+        agent._after_network_swap()
+        it = iter(tensors)
+        for n in nets:
+            getattr(agent, n).buffers.params.copy_(next(it))
+        a = meta["attrs"]
+        for o, step in zip(agent._all_optimizers(), a["opt_steps"]):
+            o.exp_avg.copy_(next(it)); o.exp_avg_sq.copy_(next(it))
+            o.step = step
+        agent.scores, agent.fitness, agent.steps, agent.mut = a["scores"], a["fitness"], a["steps"], a["mut"]
+        agent.index, agent.learn_counter, agent.current_noise = a["index"], a["learn_counter"], a["current_noise"]
+        return agent
+
     # -- checkpoints: the base class knows ONE optimiser; these learners own two or three --------------------------------
     def save_checkpoint(self, path: str) -> None:
         super().save_checkpoint(path)

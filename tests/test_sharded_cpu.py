@@ -186,3 +186,57 @@ def test_sharded_tournament_moves_maddpg_members_world2_gloo():
         assert fit == [{0: 1.0, 1: 9.0, 2: 5.0, 3: 3.0}[parent]] and ids == ["speaker_0", "listener_0"]
         crossed += int(slot // 2 != parent // 2)
     assert crossed >= 1                                                          # at least one member changed rank
+
+
+def _td3_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from agilerl_b200 import _lib
+    _lib.as_device = lambda d: torch.device("cpu")                 # test-only: flat buffers as CPU tensors
+    _lib.load = lambda require_cuda=False: None
+    from agilerl_b200.algorithms import TD3
+    from agilerl_b200.compat import spaces
+    from agilerl_b200.hpo.tournament import TournamentSelection
+    osp, asp = spaces.Box(-np.inf, np.inf, (17,), np.float32), spaces.Box(-1.0, 1.0, (6,), np.float32)
+    n_local, fitness = 2, {0: 1.0, 1: 9.0, 2: 5.0, 3: 3.0}
+    pop = []
+    for i in range(n_local):
+        gi = rank * n_local + i
+        torch.manual_seed(200 + gi)
+        m = TD3(osp, asp, index=gi, batch_size=8, lr_critic=1e-3 * (gi + 1),
+                net_config={"head_config": {"hidden_size": [16 * (gi + 1)]}})         # members differ in architecture too
+        m.fitness, m.learn_counter = [fitness[gi]], 10 + gi
+        m.critic_2_optimizer.step = 20 + gi
+        m.critic_2_optimizer.exp_avg_sq.fill_(float(gi))
+        pop.append(m)
+    marks = {m.index: (float(m.critic_2.buffers.params.sum()), list(m.critic_2.head_net.hidden_size)) for m in pop}
+    ts = TournamentSelection(2, True, 2 * world, 1, seed=7)
+    elite, new_pop = ts.select(pop)
+    out[rank] = {"plan": ts.last_plan, "marks": marks,
+                 "local": [(m.index, float(m.critic_2.buffers.params.sum()), list(m.critic_2.head_net.hidden_size), m.lr_critic,
+                            m.critic_2_optimizer.step, float(m.critic_2_optimizer.exp_avg_sq[0]), m.learn_counter, list(m.fitness))
+                           for m in new_pop]}
+    dist.destroy_process_group()
+
+
+def test_sharded_tournament_moves_td3_members_world2_gloo():
+    """BASELINE configs[2] shards the TD3 population over the GPUs: a winner on another rank travels with its six networks
+    (their own, possibly mutated, architectures), all three optimisers' moments / step counts, the policy_freq phase and its
+    hyper-parameters."""
+    world = 2
+    port = 35500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_td3_worker, args=(world, port, out), nprocs=world, join=True)
+    r0, r1 = out[0], out[1]
+    assert r0["plan"] == r1["plan"]
+    _, slots = r0["plan"]
+    marks = {**r0["marks"], **r1["marks"]}
+    crossed = 0
+    for slot, ((parent, new_index), (idx, mark, hidden, lr, step, v0, lc, fit)) in enumerate(zip(slots, r0["local"] + r1["local"])):
+        assert idx == new_index and (mark, hidden) == marks[parent]
+        assert lr == pytest.approx(1e-3 * (parent + 1)) and step == 20 + parent and v0 == float(parent) and lc == 10 + parent
+        assert fit == [{0: 1.0, 1: 9.0, 2: 5.0, 3: 3.0}[parent]]
+        crossed += int(slot // 2 != parent // 2)
+    assert crossed >= 1
