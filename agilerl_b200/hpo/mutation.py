@@ -135,9 +135,19 @@ class Mutations:
             individual.mut = "None"
             return individual
         method = policy.sample_mutation_method(self.new_layer_prob, self.rng)
-        method()
+        mut_dict = method()
         applied = policy.last_mutation_attr
         individual.mut = applied if applied is not None else "None"
+        # mutation.py:875-879: the SAME mutation (name and the parameters the policy's mutation drew) goes to the other
+        # evaluation networks that have it — the critics of DDPG / TD3 keep the policy's architecture
+        if applied is not None:
+            for group in registry.groups:
+                if group.policy:
+                    continue
+                other = getattr(individual, group.eval_network)
+                methods = other.get_mutation_methods() if hasattr(other, "get_mutation_methods") else {}
+                if applied in methods:
+                    methods[applied](**(mut_dict if isinstance(mut_dict, dict) else {}))
         self._reinit_shared(individual)
         individual.reinit_optimizers()
         return individual

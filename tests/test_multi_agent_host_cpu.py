@@ -10,6 +10,7 @@ or record what they were handed (``b2rl_maddpg_learn``), which pins everything t
 * ``Mutations._gaussian_parameter_mutation_device``: keys / rows / columns / branches drawn like the reference, the
   last-writer mask of duplicate positions."""
 import ctypes
+import warnings
 import random
 
 import numpy as np
@@ -581,3 +582,56 @@ def test_td3_checkpoint_carries_every_optimiser(standin, tmp_path):
         assert torch.equal(getattr(a, crit).buffers.params, getattr(b, crit).buffers.params)
         assert float(bopt.exp_avg[0]) == 0.5 and float(bopt.exp_avg_sq[0]) == 0.25 and bopt.step == 7 and bopt.lr == 0.005
         assert b.actor_optimizer.step == 3 and b.learn_counter == 5 and b.lr_critic == 0.005
+
+
+def test_mutation_sweep_keeps_td3_and_ddpg_members_consistent(standin):
+    """Every mutation kind over DDPG (``share_encoders=True``: the reference ``create_population``'s default) and TD3 members,
+    a learn call after each: the architecture mutation the policy drew is applied — same name, same drawn parameters — to the
+    critics too (mutation.py:875-879), targets are rebuilt, shared encoders re-pinned by the mutation hook, optimisers
+    restarted; the layer tables the kernels would walk stay consistent and the member still clones / moves."""
+    import pickle
+    from agilerl_b200.algorithms import DDPG, TD3
+    from agilerl_b200.algorithms.core.registry import HyperparameterConfig, RLParameter
+    from agilerl_b200.compat import spaces
+    from agilerl_b200.hpo import Mutations
+
+    def learn(actor, critic, cfg, bufs, stream):
+        a, c = actor._obj, critic._obj
+        assert c.val[0].in_c == c.enc[c.n_enc - 1].out_c + a.val[a.n_val - 1].out_c and a.val[0].in_c == a.enc[a.n_enc - 1].out_c
+        for d in (a, c):
+            for layers, n in ((d.enc, d.n_enc), (d.val, d.n_val)):
+                assert all(layers[i].in_c == layers[i - 1].out_c for i in range(1, n))
+        _f32(bufs._obj.critic_loss, 1)[0] = 0.5
+        _f32(bufs._obj.actor_loss, 1)[0] = 0.1
+        return 0
+    standin.b2rl_ddpg_learn = learn
+    standin.b2rl_ddpg_workspace_bytes = lambda a, c, B, out: setattr(out._obj, "value", 64) or 0
+    hp = HyperparameterConfig(lr_actor=RLParameter(min=1e-5, max=1e-2), lr_critic=RLParameter(min=1e-5, max=1e-2),
+                              batch_size=RLParameter(min=8, max=64, dtype=int))
+    osp, asp = spaces.Box(-np.inf, np.inf, (17,), np.float32), spaces.Box(-1.0, 1.0, (6,), np.float32)
+    g = torch.Generator().manual_seed(0)
+    for cls in (DDPG, TD3):
+        agent = cls(osp, asp, batch_size=8, hp_config=hp, share_encoders=(cls is DDPG))
+        muts = Mutations(0.1, 0.4, 0.3, 0.2, 0.1, 0.2, rand_seed=3, device="cuda")
+        seen = set()
+        for _ in range(30):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                [agent] = muts.mutation([agent.clone()])
+            seen.add(agent.mut)
+            B = agent.batch_size
+            agent.learn(dict(obs=torch.randn(B, 17, generator=g), action=torch.rand(B, 6, generator=g), reward=torch.randn(B, generator=g),
+                             next_obs=torch.randn(B, 17, generator=g), done=torch.zeros(B)))
+            pairs = (("actor", "actor_target"),) + tuple(zip(agent._critic_names, agent._target_names))
+            for n, t in pairs:
+                sd_n, sd_t = getattr(agent, n).state_dict(), getattr(agent, t).state_dict()
+                assert list(sd_n) == list(sd_t) and all(sd_n[k].shape == sd_t[k].shape for k in sd_n), (agent.mut, n)
+            crit = getattr(agent, agent._critic_names[0])
+            assert list(crit.encoder.hidden_size) == list(agent.actor.encoder.hidden_size), agent.mut      # analogous mutation
+            if agent.share_encoders:
+                enc = [k for k in agent.actor.state_dict() if k.startswith("encoder.")]
+                assert all(torch.equal(crit.state_dict()[k], getattr(agent, agent._target_names[0]).state_dict()[k]) for k in enc)
+            meta, tensors = agent.export_state()
+            moved = cls.from_state(pickle.loads(pickle.dumps(meta)), [t.clone() for t in tensors], agent)
+            assert torch.equal(moved.actor.buffers.params, agent.actor.buffers.params)
+        assert {"param", "None"} <= seen and any(m.startswith("encoder.") for m in seen) and any(m.startswith("lr_") for m in seen), seen
