@@ -75,3 +75,15 @@ def test_unchanged_reference_multi_agent_driver_trains_our_maddpg_population():
     assert all(s >= 96 for s in r["steps"]) and all(n == 3 for n in r["fitness_len"]) and all(n > 0 for n in r["scores"])
     assert c["saves"] == 144 and r["counter"] == 288 and r["memory_len"] == 200        # 2 envs per save; 200-slot ring wrapped
     assert 130 <= c["learn"] <= 144 and c["forward_rows"] > 3 * 2 * c["saves"]          # 3 actors x 2 envs per acting step
+
+
+def test_mutation_sweep_keeps_value_based_members_consistent_movable_and_restorable():
+    """tests/_host_sweep_standin.py: 40 mutations of every kind per (Rainbow DQN | DQN) x (image | vector observations) member;
+    after each one the target mirrors the evaluation network, the layer table is consistent, acting works, and the member
+    survives ``export_state -> pickle -> from_state`` and a checkpoint round trip with its mutated architecture."""
+    r = _run("_host_sweep_standin.py")
+    assert [(c["cls"], len(c["obs"])) for c in r] == [("RainbowDQN", 3), ("RainbowDQN", 1), ("DQN", 3), ("DQN", 1)]
+    for c in r:
+        kinds = set(c["seen"])
+        assert {"param", "act", "None"} <= kinds and any(k.startswith(("encoder.", "head_net.")) for k in kinds), c
+        assert any(k in kinds for k in ("lr", "batch_size", "learn_step")), c
