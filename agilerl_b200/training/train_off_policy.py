@@ -14,9 +14,11 @@ import time
 import warnings
 
 import numpy as np
+import torch
 
-from ..algorithms import DQN, RainbowDQN
+from ..algorithms import DDPG, DQN, TD3, RainbowDQN
 from ..algorithms.dqn_rainbow import obs_channels_to_first
+from ..networks.actors import DeterministicActor
 from ..components import MultiStepReplayBuffer, PrioritizedReplayBuffer, ReplayBuffer, Sampler, Transition
 from ..utils.utils import tournament_selection_and_mutation
 from .population import share_transitions
@@ -83,23 +85,32 @@ def train_off_policy(env, env_name: str, algo: str, pop: list, memory: ReplayBuf
             for idx_step in range(evo_steps // num_envs):
                 if swap_channels:
                     obs = obs_channels_to_first(obs)
-                action_mask = info.get("action_mask", None)
                 if isinstance(agent, DQN):
-                    action = agent.get_action(obs, epsilon, action_mask=action_mask)
+                    action = agent.get_action(obs, epsilon, action_mask=info.get("action_mask", None))
                     epsilon = max(eps_end, epsilon * eps_decay)
-                else:
-                    action = agent.get_action(obs, action_mask=action_mask)
+                elif isinstance(agent, RainbowDQN):
+                    action = agent.get_action(obs, action_mask=info.get("action_mask", None))
+                else:                                                   # DDPG / TD3 (:281-293): the environment gets the
+                    raw_action = agent.get_action(obs)                  # action rescaled to its bounds, the buffer the raw one
+                    action = DeterministicActor.rescale_action(action=torch.from_numpy(raw_action), low=agent.action_low,
+                                                               high=agent.action_high,
+                                                               output_activation=agent.actor.output_activation).cpu().numpy()
                 if not is_vectorised:
                     action = action[0]
                 next_obs, reward, done, trunc, info = env.step(action)
                 scores += np.array(reward)
                 if not is_vectorised:
                     done, trunc = np.array([done]), np.array([trunc])
+                reset_noise_indices = []
                 for idx, (d, t) in enumerate(zip(done, trunc)):
                     if d or t:
                         completed_episode_scores.append(scores[idx])
                         agent.scores.append(scores[idx])
                         scores[idx] = 0
+                        reset_noise_indices.append(idx)
+                if isinstance(agent, (DDPG, TD3)):                      # :312-313, :325-326
+                    agent.reset_action_noise(reset_noise_indices)
+                    action = raw_action
                 total_steps += num_envs
                 steps += num_envs
                 next_obs = obs_channels_to_first(next_obs) if swap_channels else next_obs
@@ -135,10 +146,14 @@ def train_off_policy(env, env_name: str, algo: str, pop: list, memory: ReplayBuf
             pop_fps.append(steps / max(time.time() - start_time, 1e-12))
             pop_episode_scores.append(completed_episode_scores)
             if losses:
-                vals = [float(l.item()) if hasattr(l, "item") else float(l) for l in losses]
-                pop_loss[agent_idx].append(np.mean(vals))
-            if isinstance(agent, DQN):
-                eps_start = epsilon
+                if isinstance(losses[-1], tuple):          # DDPG / TD3: (actor_loss | None, critic_loss) — train_off_policy.py:445-453
+                    actor_losses, critic_losses = list(zip(*losses))
+                    pop_loss[agent_idx].append((np.mean([l for l in actor_losses if l is not None]), np.mean(critic_losses)))
+                else:
+                    vals = [float(l.item()) if hasattr(l, "item") else float(l) for l in losses]
+                    pop_loss[agent_idx].append(np.mean(vals))
+        if isinstance(agent, DQN):        # train_off_policy.py:458-460: ONCE per generation, from the last agent's epsilon
+            eps_start = epsilon
         fitnesses = [agent.test(env, swap_channels=swap_channels, max_steps=eval_steps, loop=eval_loop) for agent in pop]
         pop_fitnesses.append(fitnesses)
         if verbose:
