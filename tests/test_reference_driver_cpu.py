@@ -15,12 +15,29 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference/agilerl"), reason="needs the reference source tree")
 
 
-def _run(script, *args):
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", script), *args], capture_output=True, text=True, timeout=600)
+def _run_one(script, *args):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", script), *args], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-3000:])
     line = [l for l in out.stdout.splitlines() if l.startswith("RESULT ")]
     assert line, out.stdout[-1500:]
     return json.loads(line[-1][len("RESULT "):])
+
+
+_JOBS = [("_reference_driver_standin.py",), ("_reference_driver_standin.py", "TD3"), ("_reference_driver_rainbow_standin.py",),
+         ("_reference_ma_driver_standin.py",), ("_host_sweep_standin.py",), ("_driver_equivalence_standin.py", "DQN"),
+         ("_driver_equivalence_standin.py", "TD3"), ("_driver_equivalence_standin.py", "RAINBOW")]
+_FUTURES: dict = {}
+
+
+def _run(script, *args):
+    """Each helper runs in its own process; all of them start together on first use and every test picks up its own."""
+    if not _FUTURES:
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(max_workers=max(2, min(6, os.cpu_count() or 2)))
+        for job in _JOBS:
+            _FUTURES[job] = pool.submit(_run_one, *job)
+    key = (script, *args)
+    return _FUTURES[key].result() if key in _FUTURES else _run_one(script, *args)
 
 
 def test_unchanged_reference_driver_trains_our_dqn_population():
