@@ -25,7 +25,8 @@ def _run_one(script, *args):
 
 _JOBS = [("_reference_driver_standin.py",), ("_reference_driver_standin.py", "TD3"), ("_reference_driver_rainbow_standin.py",),
          ("_reference_ma_driver_standin.py",), ("_host_sweep_standin.py",), ("_driver_equivalence_standin.py", "DQN"),
-         ("_driver_equivalence_standin.py", "TD3"), ("_driver_equivalence_standin.py", "RAINBOW")]
+         ("_driver_equivalence_standin.py", "TD3"), ("_driver_equivalence_standin.py", "RAINBOW"),
+         ("_driver_equivalence_standin.py", "MADDPG")]
 _FUTURES: dict = {}
 
 
@@ -106,9 +107,10 @@ def test_mutation_sweep_keeps_value_based_members_consistent_movable_and_restora
         assert any(k in kinds for k in ("lr", "batch_size", "learn_step")), c
 
 
-@pytest.mark.parametrize("mode", ["DQN", "TD3", "RAINBOW"])
+@pytest.mark.parametrize("mode", ["DQN", "TD3", "RAINBOW", "MADDPG"])
 def test_our_restated_driver_reproduces_the_reference_driver_exactly(mode):
-    """``agilerl_b200/training/train_off_policy.py`` (what the GPU box drives) against the reference's unchanged file on the
+    """``agilerl_b200/training/train_off_policy.py`` / ``train_multi_agent_off_policy.py`` (what the GPU box drives) against the
+    reference's unchanged files on the
     same seeded population, environment and stand-in kernels: identical fitnesses, steps, mutations, indices, scores, call
     counts, replay contents — and for the north-star flow the same beta schedule, tree sum and n-step ring.  (This is the
     test that found the per-agent instead of per-generation epsilon carry-over and the missing DDPG / TD3 branch of the
