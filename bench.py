@@ -919,7 +919,20 @@ def main():
                                 "mmas_per_product": kdesc["mmas_per_product"],
                                 "peak_kind": f"{peak_kind} bf16 cuBLAS peak x {kdesc['peak_vs_bf16']} (nominal "
                                              f"{kdesc['operand']}:bf16 ratio) / {kdesc['mmas_per_product']}"},
-                     "note": kdesc["note"]},
+                     "note": kdesc["note"],
+                     # NOT live: shares and durations from the committed ncu launch list of this command
+                     # (profiles/r2_launches_warm_final.txt, 33 kernels / 386 us of kernel time per agent-step) and the
+                     # per-kernel table of DESIGN.md par. 5.  The kernel timed live above is the one the round-1 review named
+                     # (first-layer forward); after this round's work the LARGEST share of the step is conv2's forward.
+                     "step_shares_from_profiles": [
+                         {"kernel": "conv_fwd_tc_kernel (conv2 forward 32->32 k4 s2, 3xTF32 gather, 2 launches/step)",
+                          "share_of_step_kernel_time": 0.151, "us_per_launch": 39.0, "alg_mbytes_per_launch": 31.6,
+                          "frac_of_hbm_peak": 0.12},
+                         {"kernel": "conv_fwd_i8_kernel (conv1 forward, the three passes of a step in one launch)",
+                          "share_of_step_kernel_time": 0.061, "us_per_launch": 23.2, "alg_mbytes_per_launch": 53.8,
+                          "frac_of_hbm_peak": 0.35},
+                         {"kernel": "conv_wgrad_tc_kernel (conv2 weight gradient)", "share_of_step_kernel_time": 0.076,
+                          "us_per_launch": 29.4, "alg_mbytes_per_launch": 15.8, "frac_of_hbm_peak": 0.07}]},
     }
     if e2e is not None:
         line["e2e"] = e2e
