@@ -78,14 +78,15 @@ int b2rl_tree_set(double *sum_tree, double *min_tree, int64_t cap, const int64_t
  * starting at tree_ptr, wrapping modulo max_size (not cap — quirk Q7), all set to p_alpha. */
 int b2rl_tree_set_range(double *sum_tree, double *min_tree, int64_t cap, int64_t tree_ptr,
                         int64_t n, int64_t max_size, double p_alpha, void *stream);
-/* Same, for a loop that keeps its running maximum on the device (b2rl_tree_set_from_priorities folds into
+/* Same (replay_buffer.py:306-309), for a loop that keeps its running maximum on the device (b2rl_tree_set_from_priorities folds into
  * *max_priority_dev): leaf = pow(max(host_max, *max_priority_dev), alpha) computed on device — no host read of the
  * device scalar between an update and the next add (device pow: <= 1 ulp from glibc, like the update it follows). */
 int b2rl_tree_set_range_devmax(double *sum_tree, double *min_tree, int64_t cap, int64_t tree_ptr, int64_t n,
                                int64_t max_size, double host_max, const double *max_priority_dev, double alpha,
                                void *stream);
 
-/* Device variant used by the fused path: leaf = pow(max(priority, floor), alpha) computed ON
+/* PrioritizedReplayBuffer.update_priorities (replay_buffer.py:411-428) as a device-only call, used by the fused path:
+ * leaf = pow(max(priority, floor), alpha) computed ON
  * DEVICE (<= 1 ulp from glibc pow: leaves are NOT guaranteed bit-identical to the reference;
  * the tree arithmetic above them is).  Also folds max(priority) into *max_priority (fp64). */
 int b2rl_tree_set_from_priorities(double *sum_tree, double *min_tree, int64_t cap,
@@ -103,7 +104,8 @@ int b2rl_tree_retrieve(const double *sum_tree, int64_t cap, const double *upperb
 int b2rl_per_sample(const double *sum_tree, const double *min_tree, int64_t cap,
                     const float *uniforms, int64_t B, double beta, int64_t size, int64_t *out_idx,
                     float *out_w, void *stream);
-/* Same, drawing the uniforms on device from Philox(seed, offset) (production path). */
+/* Same (replay_buffer.py:357-409), drawing the uniforms on device from Philox(seed, offset) instead of the B
+ * torch.rand(1) draws of replay_buffer.py:377 (production path). */
 int b2rl_per_sample_philox(const double *sum_tree, const double *min_tree, int64_t cap,
                            uint64_t seed, uint64_t offset, int64_t B, double beta, int64_t size,
                            int64_t *out_idx, float *out_w, void *stream);
@@ -120,13 +122,15 @@ int b2rl_per_sample_fused(const double *sum_tree, const double *min_tree, int64_
                           const float *reward_ring, const float *done_ring, int64_t *out_idx,
                           float *out_w, float *out_action, float *out_reward, float *out_done,
                           void *stream);
-/* Same, with beta / size / the Philox offset read on device from *state (graph-replayed steps; Philox only). */
+/* Same (replay_buffer.py:331-355 + :196-204), with beta / size / the Philox offset read on device from *state
+ * (graph-replayed steps; Philox only). */
 int b2rl_per_sample_fused_state(const double *sum_tree, const double *min_tree, int64_t cap, uint64_t seed,
                                 const b2rl_step_state *state, int64_t B, const float *action_ring,
                                 const float *reward_ring, const float *done_ring, int64_t *out_idx, float *out_w,
                                 float *out_action, float *out_reward, float *out_done, void *stream);
 
-/* Read-back of the device random streams (parity tests hand them to the oracle): the B float32 uniforms
+/* No reference counterpart (the reference draws from torch's CPU generator: replay_buffer.py:377,
+ * custom_components.py:118-119).  Read-back of the device random streams (parity tests hand them to the oracle): the B float32 uniforms
  * b2rl_per_sample_philox / b2rl_per_sample_fused(uniforms = NULL) consume at (seed, offset), and the
  * standard normals b2rl_noise_reset_philox consumes at (seed, offset) in b2rl_noise_reset_from_normals' layout. */
 int b2rl_philox_uniforms(uint64_t seed, uint64_t offset, int64_t n, float *out, void *stream);
