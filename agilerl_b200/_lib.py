@@ -160,6 +160,7 @@ _SIGS = {
     "b2rl_actor_forward": ([POINTER(NetDesc), c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p], c_int),
     "b2rl_sample_uniform_distinct": ([c_uint64, c_uint64, c_int64, c_int64, c_void_p, c_void_p], c_int),
     "b2rl_host_priority_pow": ([c_void_p, c_int64, c_double, c_double, c_void_p, POINTER(c_double)], c_int),
+    "b2rl_host_randperm_prefix": ([c_void_p, c_int64, c_int64, c_int64, c_void_p], c_int),
     "b2rl_philox_uniforms": ([c_uint64, c_uint64, c_int64, c_void_p, c_void_p], c_int),
     "b2rl_philox_normals": ([c_uint64, c_uint64, c_int64, c_void_p, c_void_p], c_int),
     "b2rl_ring_write": ([c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p], c_int),

@@ -21,6 +21,7 @@ bit-identical; the trees themselves are updated on the GPU.
 from __future__ import annotations
 
 import ctypes
+import warnings
 from collections import deque
 from typing import Any
 
@@ -113,6 +114,48 @@ class _PinnedRing:
         if ev is None:
             ev = self.events[k] = torch.cuda.Event()
         ev.record()
+
+
+_RANDPERM_FAST: bool | None = None          # None: not checked yet in this process
+
+
+def _randperm_prefix_fast(lib, n: int, B: int) -> torch.Tensor:
+    st = torch.get_rng_state()
+    out = torch.empty(B, dtype=torch.int64)
+    _lib.check(lib.b2rl_host_randperm_prefix(st.data_ptr(), st.numel(), n, B, out.data_ptr()))
+    torch.set_rng_state(st)
+    return out
+
+
+def randperm_prefix(lib, n: int, batch_size: int) -> torch.Tensor:
+    """``torch.randperm(n)[:batch_size]`` (replay_buffer.py:126) — the same indices AND the same state of torch's global CPU
+    generator afterwards — without shuffling all n indices when only a short prefix is used: ``b2rl_host_randperm_prefix``
+    replays the first ``batch_size`` iterations of torch's Fisher-Yates loop on the serialised mt19937 state and skips the
+    draws of the rest (1 M transitions, B = 512: 8 ms -> 0.4 ms of host time per ``sample()``).  Checked once per process
+    against ``torch.randperm`` itself (indices and generator state, on a copy of the live state); any difference — another
+    torch build, another generator — switches the process back to ``torch.randperm`` for good."""
+    global _RANDPERM_FAST
+    B = min(int(batch_size), int(n))
+    fn = getattr(lib, "b2rl_host_randperm_prefix", None)
+    if fn is None or _RANDPERM_FAST is False or B < 0 or n < 4096 or 16 * B > n or n >= 0xFFFFFFFF // 20:
+        return torch.randperm(n)[:batch_size]
+    if _RANDPERM_FAST is None:
+        live = torch.get_rng_state()
+        try:
+            want = torch.randperm(5000)[:37]
+            want_state = torch.get_rng_state()
+            torch.set_rng_state(live)
+            got = _randperm_prefix_fast(lib, 5000, 37)
+            _RANDPERM_FAST = bool(torch.equal(want, got) and torch.equal(want_state, torch.get_rng_state()))
+        except Exception:
+            _RANDPERM_FAST = False
+        finally:
+            torch.set_rng_state(live)
+        if not _RANDPERM_FAST:
+            warnings.warn("b2rl_host_randperm_prefix does not reproduce torch.randperm on this torch build: "
+                          "ReplayBuffer.sample keeps torch.randperm", stacklevel=2)
+            return torch.randperm(n)[:batch_size]
+    return _randperm_prefix_fast(lib, n, B)
 
 
 class ReplayBuffer:
@@ -285,7 +328,7 @@ class ReplayBuffer:
 
     def sample(self, batch_size: int, return_idx: bool = False) -> TensorDict:
         """:114-131 — uniform WITHOUT replacement (randperm from torch's CPU generator, Q12)."""
-        indices = torch.randperm(self.size)[:batch_size]
+        indices = randperm_prefix(self._lib, self.size, batch_size)
         samples = self._gather(indices)
         if return_idx:
             samples["idxs"] = indices.to(self._dev)

@@ -166,6 +166,13 @@ int b2rl_sample_uniform_distinct(uint64_t seed, uint64_t offset, int64_t N, int6
 int b2rl_host_priority_pow(const float *priority_host, int64_t n, double alpha, double floor_, double *out_host,
                            double *max_host);
 
+/* HOST helper (no device work): ReplayBuffer.sample's index draw (replay_buffer.py:126: `torch.randperm(self.size)[:batch_size]`)
+ * without materialising the permutation.  rng_state_host = the bytes of torch.get_rng_state() (CPU generator, mt19937),
+ * updated in place to the state torch.randperm(n) leaves; out_host[0:B] = torch.randperm(n)[:B] (n < UINT32_MAX / 20:
+ * torch's 32-bit Fisher-Yates shuffle, of which entry i is final after iteration i).  Same indices and same generator
+ * stream as the reference; the wrapper verifies that against torch.randperm once per process. */
+int b2rl_host_randperm_prefix(uint8_t *rng_state_host, int64_t state_bytes, int64_t n, int64_t B, int64_t *out_host);
+
 /* MultiStepReplayBuffer._get_n_step_info (replay_buffer.py:206-258) over a device window of n
  * per-env batches (oldest first): reward_out[e] = sum_i gamma^i r_i[e] (fp32 accumulate, gamma^i a
  * double rounded to f32 like torch scalar mul), stop after the first step i>=1 where ANY env is

@@ -81,6 +81,30 @@ def test_golden_ring_wrap_layout():
     assert len(rb) == 0 and rb.storage is None and not rb.initialized
 
 
+def test_uniform_sample_of_a_large_buffer_keeps_the_reference_stream():
+    """ReplayBuffer.sample (replay_buffer.py:114-131) on a buffer large enough for the host prefix helper
+    (b2rl_host_randperm_prefix): same rows as ``storage[torch.randperm(size)[:B]]`` and the same generator state afterwards."""
+    from agilerl_b200.components import ReplayBuffer, replay_buffer as rbm
+    from agilerl_b200.compat import TensorDict
+    n, B = 20_000, 64
+    rb = ReplayBuffer(max_size=n, device="cuda")
+    rows = torch.arange(n, dtype=torch.float32)
+    rb.add(TensorDict({"obs": torch.stack([rows, -rows], dim=1), "reward": rows * 0.5}, batch_size=[n]))
+    torch.manual_seed(123)
+    want = [torch.randperm(n)[:B] for _ in range(3)]
+    want_next = torch.rand(4)
+    torch.manual_seed(123)
+    got = [rb.sample(B, return_idx=True) for _ in range(3)]
+    got_next = torch.rand(4)
+    for w, g in zip(want, got):
+        assert torch.equal(g["idxs"].cpu(), w)
+        assert torch.equal(g["obs"].cpu(), torch.stack([w.float(), -w.float()], dim=1))
+        assert torch.equal(g["reward"].cpu().reshape(-1), w.float() * 0.5)
+    assert torch.equal(want_next, got_next)
+    if rbm._RANDPERM_FAST is not True:                 # either path must give the rows above; say which one ran
+        pytest.skip("b2rl_host_randperm_prefix fell back to torch.randperm on this box")
+
+
 def test_nstep_known_answers():
     """test_replay_buffer.py:499-594 — r1 + g r2 + g^2 r3, and early termination."""
     from agilerl_b200.components import MultiStepReplayBuffer
