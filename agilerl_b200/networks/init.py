@@ -14,6 +14,24 @@ import math
 import torch
 
 
+def _orthogonal_(t: torch.Tensor, gain: float) -> None:
+    """``torch.nn.init.orthogonal_`` with the QR factorisation on ONE thread.  The matrices here are tiny ([32, 256] ..
+    [64, 1024]); the LAPACK call behind ``torch.linalg.qr`` wakes the whole intra-op pool for them, which costs ~1 ms per
+    layer on an idle many-core host and > 100 ms where the pool is oversubscribed (measured: 112 ms vs 0.04 ms for
+    256 x 32) — per conv layer, per network, per ``clone()`` of every member of every generation.  Same draws from torch's
+    generator (the ``normal_`` of the flattened matrix), same distribution; the values agree with a multi-threaded
+    factorisation to ~2e-7 (the blocked and unblocked Householder variants round differently — as they already do between
+    two machines running the reference)."""
+    n = torch.get_num_threads()
+    if n > 1:
+        torch.set_num_threads(1)
+    try:
+        torch.nn.init.orthogonal_(t, gain)
+    finally:
+        if n > 1:
+            torch.set_num_threads(n)
+
+
 def init_state_dict(layout, noise_std: float = 0.5, output_vanish_heads: bool = True, init_mlp_layers: bool = False):
     sd = {}
     for key, e in layout.entries.items():
@@ -21,14 +39,14 @@ def init_state_dict(layout, noise_std: float = 0.5, output_vanish_heads: bool = 
             continue
         t = torch.empty(e.shape, dtype=torch.float32)
         if e.init == "conv":
-            torch.nn.init.orthogonal_(t, math.sqrt(2))
+            _orthogonal_(t, math.sqrt(2))
         elif e.init in ("zeros",):
             t.zero_()
         elif e.init == "ones":
             t.fill_(1.0)
         elif e.init == "linear":
             if init_mlp_layers:
-                torch.nn.init.orthogonal_(t, math.sqrt(2))
+                _orthogonal_(t, math.sqrt(2))
             else:
                 torch.nn.init.kaiming_uniform_(t, a=math.sqrt(5))
         elif e.init == "linear_bias":
